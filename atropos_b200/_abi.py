@@ -1,0 +1,66 @@
+"""ctypes mirror of include/atropos_b200.h (structures and constants only)."""
+import ctypes as C
+
+import numpy as np
+
+ATR_ABI_VERSION = 1
+ATR_OK, ATR_E_ARG, ATR_E_CUDA, ATR_E_NOMEM, ATR_E_LIMIT = 0, -1, -2, -3, -4
+ATR_ST_NONE, ATR_ST_MATCH, ATR_ST_ESCAPED, ATR_ST_INVALID, ATR_ST_KEYERROR = 0, 1, 2, 3, 4
+
+
+class AtrMatch(C.Structure):
+    _fields_ = [("astart", C.c_uint16), ("astop", C.c_uint16), ("rstart", C.c_uint16), ("rstop", C.c_uint16),
+                ("matches", C.c_uint16), ("errors", C.c_uint16), ("adapter", C.c_int16), ("status", C.c_uint16)]
+
+
+#: numpy view of an array of atr_match
+MATCH_DTYPE = np.dtype([("astart", "<u2"), ("astop", "<u2"), ("rstart", "<u2"), ("rstop", "<u2"),
+                        ("matches", "<u2"), ("errors", "<u2"), ("adapter", "<i2"), ("status", "<u2")])
+#: numpy view of an array of atr_insert_result
+INSERT_DTYPE = np.dtype([("insert", MATCH_DTYPE), ("match1", MATCH_DTYPE), ("match2", MATCH_DTYPE)])
+
+assert C.sizeof(AtrMatch) == 16 and MATCH_DTYPE.itemsize == 16 and INSERT_DTYPE.itemsize == 48
+
+
+class AtrAdapterDesc(C.Structure):
+    _fields_ = [("sequence", C.c_char_p), ("length", C.c_int32), ("max_error_rate", C.c_double),
+                ("flags", C.c_int32), ("wildcard_ref", C.c_int32), ("wildcard_query", C.c_int32),
+                ("min_overlap", C.c_int32), ("indel_cost", C.c_int32), ("match_to_semantics", C.c_int32),
+                ("no_indels", C.c_int32), ("rmp_ok", C.c_void_p)]
+
+
+class AtrInsertDesc(C.Structure):
+    _fields_ = [("adapter1", C.c_char_p), ("adapter1_len", C.c_int32),
+                ("adapter2", C.c_char_p), ("adapter2_len", C.c_int32),
+                ("insert_max_rmp", C.c_double), ("adapter_max_rmp", C.c_double),
+                ("min_insert_overlap", C.c_int32), ("max_insert_mismatch_frac", C.c_double),
+                ("min_adapter_overlap", C.c_int32), ("max_adapter_mismatch_frac", C.c_double),
+                ("adapter_check_cutoff", C.c_int32), ("adapter_wildcards", C.c_int32),
+                ("read_wildcards", C.c_int32), ("max_len", C.c_int32),
+                ("insert_prob", C.c_void_p), ("adapter_prob", C.c_void_p)]
+
+
+def make_adapter_desc(sequence, max_error_rate, flags, wildcard_ref=False, wildcard_query=False, min_overlap=1,
+                      indel_cost=1, match_to_semantics=False, no_indels=False, rmp_ok=None):
+    """Build an AtrAdapterDesc; returns (desc, keepalive) -- keep `keepalive` referenced while desc is used."""
+    seq = sequence if isinstance(sequence, bytes) else sequence.encode("ascii")
+    d = AtrAdapterDesc()
+    d.sequence = seq
+    d.length = len(seq)
+    d.max_error_rate = float(max_error_rate)
+    d.flags = int(flags)
+    d.wildcard_ref = int(bool(wildcard_ref))
+    d.wildcard_query = int(bool(wildcard_query))
+    d.min_overlap = int(min_overlap)
+    d.indel_cost = int(indel_cost)
+    d.match_to_semantics = int(bool(match_to_semantics))
+    d.no_indels = int(bool(no_indels))
+    keep = [seq]
+    if rmp_ok is not None:
+        tab = np.ascontiguousarray(rmp_ok, dtype=np.uint8)
+        assert tab.size == (len(seq) + 1) ** 2
+        d.rmp_ok = tab.ctypes.data
+        keep.append(tab)
+    else:
+        d.rmp_ok = None
+    return d, keep

@@ -1,0 +1,250 @@
+// adapter_build.hpp -- host-side preparation of the per-adapter device tables (pure C++, no CUDA).
+//
+// Everything that involves floating point is evaluated HERE, once per adapter, with the very
+// expressions of the reference (C doubles, as Cython compiles them), and shipped to the kernels as
+// small integer tables:
+//   k          = (int)(max_error_rate * m)                      _align.pyx:312
+//   thr_mul[l] = max integer c with (double)c <= l * rate       _align.pyx:447, :468  (cost <= length * max_error_rate)
+//   thr_div[s] = max integer e with (double)e / s <= rate       adapters/__init__.py:389-392 (errors / size <= max_error_rate)
+// Translation tables: _align.pyx:31-83.
+#pragma once
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include <cfenv>
+#include "atr_common.cuh"
+#include "insert_core.cuh"
+
+namespace atr {
+
+inline void build_tables(AtrTables& t) {
+    std::memset(&t, 0, sizeof(t));
+    auto put = [](unsigned char* tab, char c, int v) {
+        tab[(unsigned char)c] = (unsigned char)v;
+        tab[(unsigned char)(c + 32)] = (unsigned char)v;
+    };
+    const int A = 1, C = 2, G = 4, T = 8;
+    put(t.acgt, 'A', A); put(t.acgt, 'C', C); put(t.acgt, 'G', G); put(t.acgt, 'T', T); put(t.acgt, 'U', T);
+    put(t.iupac, 'X', 0); put(t.iupac, 'A', A); put(t.iupac, 'C', C); put(t.iupac, 'G', G); put(t.iupac, 'T', T);
+    put(t.iupac, 'U', T); put(t.iupac, 'R', A | G); put(t.iupac, 'Y', C | T); put(t.iupac, 'S', G | C);
+    put(t.iupac, 'W', A | T); put(t.iupac, 'K', G | T); put(t.iupac, 'M', A | C); put(t.iupac, 'B', C | G | T);
+    put(t.iupac, 'D', A | G | T); put(t.iupac, 'H', A | C | T); put(t.iupac, 'V', A | C | G);
+    put(t.iupac, 'N', A | C | G | T);
+}
+
+// The 16 upper-case letters whose 4-bit IUPAC code identifies them uniquely: for these, equality of
+// codes == equality of ASCII bytes, so the packed kernel is exact in the reference's ASCII mode.
+inline bool exact_symbol(unsigned char c) {
+    switch (c) {
+        case 'X': case 'A': case 'C': case 'G': case 'T': case 'R': case 'Y': case 'S': case 'W':
+        case 'K': case 'M': case 'B': case 'D': case 'H': case 'V': case 'N': return true;
+        default: return false;
+    }
+}
+
+struct HostAdapter {
+    atr_adapter_desc desc;            // copy of the caller's arguments (sequence pointer NOT retained)
+    std::string seq;
+    int m = 0, k = 0, ic_eff = 1;
+    bool and_mode = false, k1a_ok = false;
+    int q_table = 0;                  // 0 ASCII, 1 IUPAC, 2 ACGT
+    int cmp_only = 0;                 // 0 DP, 1 compare_prefixes, 2 compare_suffixes
+    // Adapter.match_to tries str.find/startswith/endswith first when adapter_wildcards is off
+    // (adapters/__init__.py:351-367). In ASCII mode the DP returns the very same hit (cost 0, m matches,
+    // leftmost), so only the RMP bypass has to be honoured; with read wildcards on (AND mode) a cost-0
+    // DP hit need not be a literal hit, so the literal search is run explicitly.
+    bool need_find = false;
+    bool lit_exact = true;            // every adapter letter is one of the 16 exactly-coded symbols
+    std::vector<unsigned char> ref_gen;        // K1g operand: ASCII or translated
+    std::vector<unsigned short> thr_mul, thr_div;
+    std::vector<unsigned char> rmp_ok;         // empty = no gate
+};
+
+// returns 0 or ATR_E_*; msg filled on error
+inline int prepare_adapter(const atr_adapter_desc& d, const AtrTables& tb, HostAdapter& h, std::string& msg) {
+    if (d.sequence == nullptr || d.length < 1) { msg = "empty adapter sequence"; return ATR_E_ARG; }
+    if (d.length > ATR_MAX_ADAPTER) { msg = "adapter longer than 4095 nt"; return ATR_E_LIMIT; }
+    if (d.min_overlap < 1) { msg = "Minimum overlap must be at least 1"; return ATR_E_ARG; }            // _align.pyx:218-220
+    if (d.indel_cost < 1) { msg = "Insertion/deletion cost must be at least 1"; return ATR_E_ARG; }     // _align.pyx:228-230
+    if (!(d.max_error_rate >= 0.0)) { msg = "max_error_rate must be >= 0"; return ATR_E_ARG; }
+    h.desc = d;
+    h.seq.assign(d.sequence, (size_t)d.length);
+    h.desc.sequence = nullptr;
+    h.desc.rmp_ok = nullptr;
+    const int m = h.m = d.length;
+    for (unsigned char c : h.seq) if (c >= 128) { msg = "non-ASCII adapter"; return ATR_E_ARG; }
+    h.k = (int)(d.max_error_rate * m);
+    // indel costs above k+1 all mean "an indel kills the path": clamp so packed costs cannot overflow
+    h.ic_eff = d.indel_cost > h.k + 2 ? h.k + 2 : d.indel_cost;
+    h.and_mode = d.wildcard_ref || d.wildcard_query;
+    h.q_table = !h.and_mode ? 0 : (d.wildcard_query ? 1 : 2);
+    h.ref_gen.resize((size_t)m);
+    bool all_exact = true;
+    for (int i = 0; i < m; i++) {
+        const unsigned char c = (unsigned char)h.seq[i];
+        if (!h.and_mode) { h.ref_gen[i] = c; all_exact = all_exact && exact_symbol(c); }
+        else h.ref_gen[i] = d.wildcard_ref ? tb.iupac[c] : tb.acgt[c];      // _align.pyx:245-248
+    }
+    // packed keys hold cost <= 255: (k+1) + ic_eff <= 2k+3 must fit
+    h.need_find = d.match_to_semantics && !d.wildcard_ref && d.wildcard_query;
+    h.lit_exact = true;
+    for (unsigned char c : h.seq) h.lit_exact = h.lit_exact && exact_symbol(c);
+    h.k1a_ok = m <= ATR_K1A_MAXM && h.k <= 126 && (h.and_mode || all_exact) && (!h.need_find || h.lit_exact);
+    h.thr_mul.assign((size_t)m + 1, 0);
+    h.thr_div.assign((size_t)m + 1, 0);
+    for (int l = 0; l <= m; l++) {
+        const double lim = l * d.max_error_rate;
+        double f = std::floor(lim);
+        if (f > 60000.0) f = 60000.0;
+        int c = (int)f;
+        while ((double)(c + 1) <= lim && c < 60000) c++;
+        while (c > 0 && !((double)c <= lim)) c--;
+        h.thr_mul[l] = (unsigned short)c;
+        int e = 0;
+        if (l > 0) while (e < 60000 && (double)(e + 1) / (double)l <= d.max_error_rate) e++;
+        h.thr_div[l] = (unsigned short)e;
+    }
+    h.cmp_only = 0;
+    if (d.match_to_semantics && d.no_indels) {                              // adapters/__init__.py:370-380
+        if (d.flags == ATR_STOP_WITHIN_SEQ2) h.cmp_only = 1;                // PREFIX
+        else if (d.flags == ATR_START_WITHIN_SEQ2) h.cmp_only = 2;          // SUFFIX
+    }
+    if (d.rmp_ok != nullptr) h.rmp_ok.assign(d.rmp_ok, d.rmp_ok + (size_t)(m + 1) * (m + 1));
+    return ATR_OK;
+}
+
+// Fill the by-value parameter block of the register kernel. rmp_ok_dev: device (or host, for the simulator) pointer.
+inline void fill_k1a(const HostAdapter& h, const AtrTables& tb, int index, int reduce, const unsigned char* rmp_ok_dev,
+                     AdapterK1a& a) {
+    std::memset(&a, 0, sizeof(a));
+    a.m = h.m; a.k = h.k; a.flags = h.desc.flags; a.ic = h.ic_eff; a.min_overlap = h.desc.min_overlap;
+    a.and_mode = h.and_mode; a.q_single_only = h.q_table == 2;
+    a.match_to = h.desc.match_to_semantics; a.exact_bypass = !h.desc.wildcard_ref && !h.need_find; a.cmp_only = h.cmp_only;
+    a.adapter_index = index; a.reduce = reduce;
+    a.need_find = h.need_find;
+    for (int i = 0; i < ATR_K1A_MAXM; i++) a.lit[i] = i < h.m ? tb.iupac[(unsigned char)h.seq[i]] : 0x100;
+    for (int i = 0; i < ATR_K1A_MAXM; i++) {
+        if (i < h.m) a.code[i] = h.and_mode ? h.ref_gen[i] : tb.iupac[(unsigned char)h.seq[i]];
+        else a.code[i] = h.and_mode ? 0 : 0x100;                            // pad rows never match
+    }
+    for (int l = 0; l <= ATR_K1A_MAXM; l++) {
+        a.thr_mul[l] = l <= h.m ? h.thr_mul[l] : 0;
+        a.thr_div[l] = l <= h.m ? h.thr_div[l] : 0;
+    }
+    a.rmp_ok = rmp_ok_dev;
+}
+
+inline void fill_gen(const HostAdapter& h, int index, int reduce, const unsigned char* ref_dev, const unsigned char* lit_dev,
+                     const unsigned short* thr_mul_dev, const unsigned short* thr_div_dev,
+                     const unsigned char* rmp_ok_dev, AdapterGen& g) {
+    std::memset(&g, 0, sizeof(g));
+    g.m = h.m; g.k = h.k; g.flags = h.desc.flags; g.ic = h.ic_eff; g.min_overlap = h.desc.min_overlap;
+    g.and_mode = h.and_mode; g.q_table = h.q_table;
+    g.match_to = h.desc.match_to_semantics; g.exact_bypass = !h.desc.wildcard_ref && !h.need_find; g.cmp_only = h.cmp_only;
+    g.adapter_index = index; g.reduce = reduce; g.rate = h.desc.max_error_rate;
+    g.need_find = h.need_find; g.lit = lit_dev;
+    g.ref = ref_dev; g.thr_mul = thr_mul_dev; g.thr_div = thr_div_dev; g.rmp_ok = rmp_ok_dev;
+}
+
+// ---- 4-bit packing of one read (the device packer runs the same function per output word) ----
+// returns the packed word `widx` of a read of `len` bases; *esc |= 1 if a byte is not exactly representable
+ATR_HD uint32_t pack_word(const unsigned char* __restrict__ ascii, int len, int widx, int fold_case,
+                          const unsigned char* __restrict__ iupac, int* esc) {
+    uint32_t w = 0;
+    const int base = widx * 8;
+#pragma unroll
+    for (int t = 0; t < 8; t++) {
+        const int p = base + t;
+        if (p < len) {
+            unsigned char c = ascii[p];
+            if (fold_case && c >= 'a' && c <= 'z') c = (unsigned char)(c - 32);
+            const unsigned code = iupac[c];
+            // exact iff c is one of the 16 upper-case IUPAC letters: code != 0 and upper case, or 'X'
+            const bool exact = (c >= 'A' && c <= 'Z' && c != 'U' && (code != 0 || c == 'X'));
+            if (!exact) *esc |= 1;
+            w |= code << (4 * t);
+        }
+    }
+    return w;
+}
+
+// thresholds "largest integer c with (double)c <= l * rate" (cost <= length * max_error_rate in C doubles)
+inline unsigned short thr_mul_of(int l, double rate) {
+    const double lim = l * rate;
+    double f = std::floor(lim);
+    if (f > 60000.0) f = 60000.0;
+    if (f < 0) f = 0;
+    int c = (int)f;
+    while (c < 60000 && (double)(c + 1) <= lim) c++;
+    while (c > 0 && !((double)c <= lim)) c--;
+    return (unsigned short)c;
+}
+
+// ---- InsertAligner.__init__ (align/__init__.py:206-233): host tables of the K2 kernels ----------
+struct HostInsert {
+    InsertDev dev;                    // scalar fields filled; pointer fields set by the owner (device or host pointers)
+    std::vector<unsigned short> k_by_len, thr_ins, maxmm;
+    std::vector<unsigned char> a1_code, a2_code, a1_ascii, a2_ascii, comp, ov_tab;
+    std::vector<double> insert_prob, adapter_prob;
+};
+
+inline int prepare_insert(const atr_insert_desc& d, const AtrTables& tb, HostInsert& h, std::string& msg) {
+    if (!d.adapter1 || !d.adapter2 || d.adapter1_len < 1 || d.adapter2_len < 1 || d.max_len < 1 || !d.insert_prob ||
+        !d.adapter_prob) { msg = "bad arguments to atr_insertset_create"; return ATR_E_ARG; }
+    if (d.max_len > ATR_MAX_READ || d.adapter1_len > ATR_MAX_ADAPTER || d.adapter2_len > ATR_MAX_ADAPTER) {
+        msg = "insert aligner: read or adapter too long"; return ATR_E_LIMIT;
+    }
+    if (!(d.max_insert_mismatch_frac >= 0.0) || !(d.max_adapter_mismatch_frac >= 0.0)) {
+        msg = "mismatch fractions must be >= 0"; return ATR_E_ARG;
+    }
+    InsertDev& v = h.dev;
+    std::memset(&v, 0, sizeof(v));
+    const int L = d.max_len, amax = std::max(d.adapter1_len, d.adapter2_len);
+    const double rate = d.max_insert_mismatch_frac;
+    v.min_insert_overlap = d.min_insert_overlap; v.min_adapter_overlap = d.min_adapter_overlap;
+    v.cutoff = d.adapter_check_cutoff; v.max_len = L; v.kmax = (int)(rate * L);
+    v.a1_len = d.adapter1_len; v.a2_len = d.adapter2_len; v.amax = amax;
+    v.insert_max_rmp = d.insert_max_rmp; v.adapter_max_rmp = d.adapter_max_rmp;
+    const bool aw = d.adapter_wildcards != 0, rw = d.read_wildcards != 0;
+    // compare_prefixes(read_overhang, adapter, wildcard_ref=adapter_wildcards, wildcard_query=read_wildcards):
+    // the READ overhang is the "ref" argument (align/__init__.py:285-288; _align.pyx:521-530)
+    v.and_mode = aw || rw;
+    v.ov_single_only = (!aw && rw);
+    h.k_by_len.resize((size_t)L + 1); h.thr_ins.resize((size_t)L + 1); h.maxmm.resize((size_t)amax + 1);
+    for (int l = 0; l <= L; l++) {
+        h.k_by_len[l] = (unsigned short)std::min(60000, (int)(rate * l));            // _align.pyx:634
+        h.thr_ins[l] = thr_mul_of(l, rate);                                          // _align.pyx:728
+    }
+    std::fesetround(FE_TONEAREST);
+    for (int a = 0; a <= amax; a++) {                                                // Python round(): half to even
+        const double r = std::nearbyint(a * d.max_adapter_mismatch_frac);
+        h.maxmm[a] = (unsigned short)std::max(0.0, std::min(60000.0, r));
+    }
+    bool packed_ok = true;
+    auto enc = [&](const char* s, int n, std::vector<unsigned char>& code, std::vector<unsigned char>& asc) {
+        code.resize((size_t)n); asc.resize((size_t)n);
+        for (int i = 0; i < n; i++) {
+            const unsigned char c = (unsigned char)s[i];
+            if (!v.and_mode) { code[i] = tb.iupac[c]; asc[i] = c; packed_ok = packed_ok && exact_symbol(c); }
+            else { code[i] = asc[i] = rw ? tb.iupac[c] : tb.acgt[c]; }
+        }
+    };
+    enc(d.adapter1, d.adapter1_len, h.a1_code, h.a1_ascii);
+    enc(d.adapter2, d.adapter2_len, h.a2_code, h.a2_ascii);
+    v.packed_ok = packed_ok;
+    h.comp.assign(256, 0); h.ov_tab.assign(256, 0);
+    const char* a = "ACRSWKBDN"; const char* b = "TGYSWMVHN";                         // util/__init__.py:67-88
+    for (int i = 0; a[i]; i++) {
+        h.comp[(unsigned char)a[i]] = (unsigned char)b[i]; h.comp[(unsigned char)b[i]] = (unsigned char)a[i];
+        h.comp[(unsigned char)(a[i] + 32)] = (unsigned char)(b[i] + 32);
+        h.comp[(unsigned char)(b[i] + 32)] = (unsigned char)(a[i] + 32);
+    }
+    for (int c = 0; c < 256; c++) h.ov_tab[c] = !v.and_mode ? (unsigned char)c : (aw ? tb.iupac[c] : tb.acgt[c]);
+    h.insert_prob.assign(d.insert_prob, d.insert_prob + (size_t)(L + 1) * (v.kmax + 1));
+    h.adapter_prob.assign(d.adapter_prob, d.adapter_prob + (size_t)(amax + 1) * (amax + 1));
+    return ATR_OK;
+}
+
+}  // namespace atr

@@ -1,0 +1,79 @@
+// atr_common.cuh -- device-side structures shared by the kernels and the C-ABI host code.
+#pragma once
+#include <stdint.h>
+#include "../../include/atropos_b200.h"
+
+#if defined(__CUDACC__)
+#define ATR_HD __host__ __device__ __forceinline__
+#define ATR_D __device__ __forceinline__
+#else
+#define ATR_HD inline
+#define ATR_D inline
+#endif
+
+#define ATR_ESC_BIT 0x8000u          // bit 15 of len[]: read must take the byte-exact general kernel
+#define ATR_LEN_MASK 0x7FFFu
+
+// ---- packed-key cell of the register kernel (K1a) ----------------------------------------
+// bits [24,32) cost (clamped to k+1)   [22,24) tie-break priority (0 while stored)
+//      [7,19)  origin + ATR_ORG_BIAS    [0,7)   matches
+// A single unsigned min over (diag+SUB, up+INS, left+DEL) then reproduces the reference's
+// "mismatch <= insertion <= deletion" preference (_align.pyx:405-419): equal costs are ordered
+// by the priority bits, which are cleared again before the key is stored.
+#define ATR_K1A_MAXM 64
+#define ATR_K1A_MAXN 4000
+#define ATR_COST_SHIFT 24
+#define ATR_PRIO_SHIFT 22
+#define ATR_ORG_SHIFT 7
+#define ATR_ORG_BIAS 64
+#define ATR_ORG_MASK 0xFFFu
+#define ATR_MAT_MASK 0x7Fu
+#define ATR_PRIO_CLEAR (~(3u << ATR_PRIO_SHIFT))
+
+// general kernel (K1g) limits
+#define ATR_MAX_ADAPTER 4095
+#define ATR_MAX_READ 32767
+#define ATR_G_ORG_BIAS 4096
+
+struct AdapterK1a {                   // passed by value as a __grid_constant__ kernel parameter
+    int m, k, flags, ic, min_overlap;
+    int and_mode;                     // 0: codes compared for equality (ASCII mode); 1: (a & q) != 0
+    int q_single_only;                // and_mode with the query under the ACGT table: multi-bit codes -> 0
+    int match_to, exact_bypass, cmp_only;   // cmp_only: 0 DP, 1 compare_prefixes, 2 compare_suffixes
+    int adapter_index;
+    int reduce;                       // 0: overwrite out[i]; 1: keep the previous result unless strictly more matches
+    int mark_routed;                  // no general pass follows: flag routed reads ATR_ST_ESCAPED instead of leaving them
+    int need_find;                    // match_to with read wildcards only: run the literal str.find shortcut explicitly
+    int code[ATR_K1A_MAXM];           // per-row compare operand (4-bit code)
+    int lit[ATR_K1A_MAXM];            // literal 4-bit code of the adapter letters (need_find only)
+    unsigned short thr_mul[ATR_K1A_MAXM + 1];   // floor(length * rate) in double   (_align.pyx:447, :468)
+    unsigned short thr_div[ATR_K1A_MAXM + 1];   // max e with e / size <= rate       (adapters/__init__.py:389-392)
+    const unsigned char* rmp_ok;      // [(m+1)*(m+1)] or nullptr
+};
+
+struct AdapterGen {                   // general kernel: tables live in global memory
+    int m, k, flags, ic, min_overlap;
+    int and_mode, q_table;            // q_table: 0 none (ASCII), 1 IUPAC, 2 ACGT translation of the query byte
+    int match_to, exact_bypass, cmp_only;
+    int adapter_index, reduce;
+    int need_find;
+    double rate;
+    const unsigned char* ref;         // m bytes: ASCII (ascii mode) or translated codes
+    const unsigned char* lit;         // m bytes: the adapter's ASCII letters (need_find only)
+    const unsigned short* thr_mul;    // m+1
+    const unsigned short* thr_div;    // m+1
+    const unsigned char* rmp_ok;
+};
+
+// translation tables (_align.pyx:31-83), built once on the host and uploaded
+struct AtrTables {
+    unsigned char iupac[256];
+    unsigned char acgt[256];
+};
+
+ATR_HD unsigned k1a_key(int cost, int origin, int matches) {
+    return ((unsigned)cost << ATR_COST_SHIFT) | ((unsigned)(origin + ATR_ORG_BIAS) << ATR_ORG_SHIFT) | (unsigned)matches;
+}
+ATR_HD int k1a_cost(unsigned key) { return (int)(key >> ATR_COST_SHIFT); }
+ATR_HD int k1a_origin(unsigned key) { return (int)((key >> ATR_ORG_SHIFT) & ATR_ORG_MASK) - ATR_ORG_BIAS; }
+ATR_HD int k1a_matches(unsigned key) { return (int)(key & ATR_MAT_MASK); }

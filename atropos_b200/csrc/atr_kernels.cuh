@@ -1,0 +1,198 @@
+// atr_kernels.cuh -- the __global__ kernels (sm_100a). Host launch code lives in atr_api.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include "locate_core.cuh"
+#include "insert_core.cuh"
+#include "adapter_build.hpp"
+
+// ---------------------------------------------------------------------------------------------
+// pack: ASCII -> 4-bit codes. One warp per read, one lane per output word (8 bases), so a warp reads
+// up to 256 contiguous bytes and writes up to 128 contiguous bytes per pass.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_word_counts(const int64_t* __restrict__ offsets, int64_t n,
+                                                     uint32_t* __restrict__ counts) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n) counts[r] = (uint32_t)((offsets[r + 1] - offsets[r] + 7) >> 3);
+}
+
+__global__ void __launch_bounds__(256) k_pack(const unsigned char* __restrict__ ascii, const int64_t* __restrict__ offsets,
+                                              int64_t base, int64_t n, int fold_case,
+                                              const AtrTables* __restrict__ tables, const uint32_t* __restrict__ woff,
+                                              uint32_t* __restrict__ codes, uint16_t* __restrict__ len_out) {
+    __shared__ unsigned char s_iupac[256];
+    s_iupac[threadIdx.x] = tables->iupac[threadIdx.x];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (r >= n) return;
+    const int64_t off = offsets[r] - base;
+    const int len = (int)(offsets[r + 1] - offsets[r]);
+    const int nwords = (len + 7) >> 3;
+    const uint32_t w0 = woff[r];
+    int esc = 0;
+    for (int w = lane; w < nwords; w += 32)
+        codes[w0 + w] = atr::pack_word(ascii + off, len, w, fold_case, s_iupac, &esc);
+    esc = __any_sync(0xffffffffu, esc);
+    if (lane == 0) len_out[r] = (uint16_t)(len | (esc ? ATR_ESC_BIT : 0));
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1a: one thread per read, DP column in registers (see locate_core.cuh).
+// ---------------------------------------------------------------------------------------------
+template <bool AND_MODE>
+__global__ void __launch_bounds__(128) k_locate_k1a(const __grid_constant__ AdapterK1a ad,
+                                                    const uint32_t* __restrict__ codes, const uint32_t* __restrict__ woff,
+                                                    const uint16_t* __restrict__ len, const uint16_t* __restrict__ win,
+                                                    int64_t n_reads, atr_match* __restrict__ out) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_reads) return;
+    const unsigned l = len[r];
+    const bool esc = (l & ATR_ESC_BIT) != 0;
+    int hi = (int)(l & ATR_LEN_MASK), lo = 0;
+    if (win != nullptr) {
+        const int wlo = win[2 * r], whi = win[2 * r + 1];
+        hi = atr_min(hi, whi);
+        lo = atr_min(wlo, hi);
+    }
+    const int n = hi - lo;
+    // routed to the byte-exact general kernel (k_locate_gen, launched right after on the same stream)
+    if ((esc && (!AND_MODE || ad.need_find)) || n > ATR_K1A_MAXN) {
+        if (ad.mark_routed) {
+            atr_match m;
+            m.astart = m.astop = m.rstart = m.rstop = m.matches = m.errors = 0;
+            m.adapter = -1; m.status = ATR_ST_ESCAPED;
+            out[r] = m;
+        }
+        return;
+    }
+    k1a_read<AND_MODE>(ad, codes + woff[r], lo, n, out + r);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1g: general kernel on raw ASCII, DP column in global scratch (coalesced: element i of thread t at
+// scratch[i * nthreads + t]). all_reads = 0: only the reads K1a skipped; 1: every read (adapter not K1a-able).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_locate_gen(const __grid_constant__ AdapterGen ad, int k1a_and_mode, int all_reads,
+                                                    const AtrTables* __restrict__ tables,
+                                                    const unsigned char* __restrict__ ascii, const int64_t* __restrict__ offsets,
+                                                    int64_t base, const uint16_t* __restrict__ len,
+                                                    const uint16_t* __restrict__ win, int fold_case, int64_t n_reads,
+                                                    GCell* __restrict__ scratch, atr_match* __restrict__ out) {
+    __shared__ AtrTables s_tb;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) { s_tb.iupac[i] = tables->iupac[i]; s_tb.acgt[i] = tables->acgt[i]; }
+    __syncthreads();
+    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int64_t r = t; r < n_reads; r += nthreads) {
+        const int full = (int)(offsets[r + 1] - offsets[r]);
+        int hi = full, lo = 0;
+        if (win != nullptr) {
+            const int wlo = win[2 * r], whi = win[2 * r + 1];
+            hi = atr_min(hi, whi);
+            lo = atr_min(wlo, hi);
+        }
+        const int n = hi - lo;
+        if (!all_reads) {
+            const bool esc = len != nullptr && (len[r] & ATR_ESC_BIT) != 0;
+            const bool routed = (esc && (!k1a_and_mode || ad.need_find)) || n > ATR_K1A_MAXN;
+            if (!routed) continue;
+        }
+        gen_read(ad, s_tb, ascii + (offsets[r] - base) + lo, n, fold_case, scratch + t, nthreads, out + r);
+    }
+}
+
+__global__ void k_fill_none(atr_match* __restrict__ out, int64_t n) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n) {
+        atr_match m;
+        m.astart = m.astop = m.rstart = m.rstop = m.matches = m.errors = 0;
+        m.adapter = -1; m.status = ATR_ST_NONE;
+        out[r] = m;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2: InsertAligner.match_insert, one thread per pair. The reverse-complemented mate and read 1
+// are staged as packed words in shared memory ([word][thread], conflict-free) because the sliding
+// overlap needs dynamically indexed funnel shifts.
+// ---------------------------------------------------------------------------------------------
+#define ATR_K2_THREADS 64
+__global__ void __launch_bounds__(ATR_K2_THREADS) k_insert_packed(
+        const __grid_constant__ InsertDev d,
+        const uint32_t* __restrict__ codes1, const uint32_t* __restrict__ woff1, const uint16_t* __restrict__ len1,
+        const uint32_t* __restrict__ codes2, const uint32_t* __restrict__ woff2, const uint16_t* __restrict__ len2,
+        int64_t n_pairs, atr_insert_result* __restrict__ out) {
+    __shared__ uint32_t sR[ATR_K2_MAXW * ATR_K2_THREADS];
+    __shared__ uint32_t sQ[ATR_K2_MAXW * ATR_K2_THREADS];
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_pairs) return;
+    const unsigned l1 = len1[r], l2 = len2[r];
+    const int n1 = (int)(l1 & ATR_LEN_MASK), n2 = (int)(l2 & ATR_LEN_MASK);
+    const int m = n1 < n2 ? n1 : n2;
+    atr_insert_result* o = out + r;
+    bool routed = ((l1 | l2) & ATR_ESC_BIT) != 0 || m > ATR_K2_MAXLEN || !d.packed_ok;
+    PackedPair pp;
+    pp.R = sR + threadIdx.x; pp.Q = sQ + threadIdx.x; pp.stride = ATR_K2_THREADS;
+    if (!routed) routed = packed_pair_setup(pp, codes1 + woff1[r], codes2 + woff2[r], m) == 0;
+    if (routed) {                      // the byte-exact kernel (k_insert_bytes) picks these up
+        atr_insert_result e;
+        im_clear(e.insert); im_clear(e.match1); im_clear(e.match2);
+        e.insert.status = ATR_ST_ESCAPED;
+        *o = e;
+        return;
+    }
+    Cand cand[ATR_MAX_CAND];
+    insert_pair(d, pp, true, m, n1, n2, cand, o);
+}
+
+__global__ void __launch_bounds__(128) k_insert_bytes(
+        const __grid_constant__ InsertDev d,
+        const unsigned char* __restrict__ ascii1, const int64_t* __restrict__ off1, int64_t base1,
+        const unsigned char* __restrict__ ascii2, const int64_t* __restrict__ off2, int64_t base2,
+        int64_t n_pairs, atr_insert_result* __restrict__ out) {
+    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_pairs; r += nthreads) {
+        if (out[r].insert.status != ATR_ST_ESCAPED) continue;
+        const int n1 = (int)(off1[r + 1] - off1[r]), n2 = (int)(off2[r + 1] - off2[r]);
+        const int m = n1 < n2 ? n1 : n2;
+        BytePair bp;
+        bp.s1 = ascii1 + (off1[r] - base1); bp.s2 = ascii2 + (off2[r] - base2);
+        bp.comp = d.comp; bp.ov_tab = d.ov_tab; bp.m = m;
+        bool keyerr = false;
+        for (int p = 0; p < m; p++) keyerr = keyerr || d.comp[bp.s2[p]] == 0;
+        if (keyerr) {
+            atr_insert_result e;
+            im_clear(e.insert); im_clear(e.match1); im_clear(e.match2);
+            e.insert.status = ATR_ST_KEYERROR;
+            out[r] = e;
+            continue;
+        }
+        Cand cand[ATR_MAX_CAND];
+        insert_pair(d, bp, false, m, n1, n2, cand, out + r);
+    }
+}
+
+// single-call MultiAligner.locate (any flags): one thread
+__global__ void k_multi_locate(const unsigned char* __restrict__ ref, int m, const unsigned char* __restrict__ query, int n,
+                               int k, const unsigned short* __restrict__ thr, int flags, int min_overlap, int max_matches,
+                               GCellM* col, int* out6, int* n_out) {
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        *n_out = gen_multi_locate(ref, m, query, n, k, thr, flags, min_overlap, max_matches, col, out6);
+}
+
+// single-call compare_prefixes (_align.pyx:501-544): one block, lanes stride the common prefix
+__global__ void __launch_bounds__(256) k_compare_prefixes(const unsigned char* __restrict__ ref, const unsigned char* __restrict__ query,
+                                                          int length, int mode /*0 ascii, 1 and*/, const unsigned char* __restrict__ tr,
+                                                          const unsigned char* __restrict__ tq, int* matches_out) {
+    __shared__ int s_cnt;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    int c = 0;
+    for (int i = threadIdx.x; i < length; i += blockDim.x) {
+        if (mode == 0) c += ref[i] == query[i];
+        else c += (tr[ref[i]] & tq[query[i]]) != 0;
+    }
+    atomicAdd(&s_cnt, c);
+    __syncthreads();
+    if (threadIdx.x == 0) *matches_out = s_cnt;
+}

@@ -1,0 +1,386 @@
+// locate_core.cuh -- per-read alignment logic of the K1 kernels (one thread = one read).
+//
+// Re-designs Aligner.locate (reference: atropos/align/_align.pyx:266-491) for a GPU thread:
+//   * K1a  k1a_locate():  adapter <= 64 nt; the whole DP column lives in registers as packed 32-bit
+//          keys (atr_common.cuh), rows fully unrolled, every column evaluated in full and every cost
+//          clamped to k+1 -- no data-dependent band (the reference's Ukkonen `last` cut-off and the
+//          early exit on an exact hit do not change results: cells with cost > k never feed an
+//          accepted alignment). One unsigned min3 implements the reference's tie order.
+//   * K1g  gen_locate():  any adapter/read length and the byte-exact ASCII alphabet; column in
+//          global scratch, banded like the reference. This is the path for escaped reads,
+//          adapters > 64 nt and reads > 4000 nt.
+// The functions are __host__ __device__ so tests/host_sim can run the very same code on the CPU
+// build box (no GPU there); the product only ever calls them from the kernels in kernels.cu.
+#pragma once
+#include "atr_common.cuh"
+
+struct Best {
+    int matches, cost, origin, ref_stop, q_stop;
+};
+
+ATR_HD int atr_min(int a, int b) { return a < b ? a : b; }
+ATR_HD int atr_max(int a, int b) { return a > b ? a : b; }
+ATR_HD unsigned atr_umin(unsigned a, unsigned b) { return a < b ? a : b; }
+
+// candidate acceptance: _align.pyx:443-449 (row m inside the loop) and :465-474 (last column)
+template <class A>
+ATR_HD void consider(const A& ad, Best& b, int cost, int origin, int matches, int ref_stop, int q_stop) {
+    const int length = ref_stop + atr_min(origin, 0);
+    if (length >= ad.min_overlap && cost <= (int)ad.thr_mul[length] &&
+        (matches > b.matches || (matches == b.matches && cost < b.cost))) {
+        b.matches = matches; b.cost = cost; b.origin = origin; b.ref_stop = ref_stop; b.q_stop = q_stop;
+    }
+}
+
+// AdapterCutter._best_match's reduction over the adapters of a set (modifiers.py:116-121): the kernels run
+// adapter after adapter in list order, a later adapter only replaces the stored match with strictly more matches.
+template <class A>
+ATR_HD void emit(const A& ad, const atr_match& r, atr_match* out) {
+    if (ad.reduce) {
+        const atr_match prev = *out;
+        if (prev.status >= ATR_ST_ESCAPED) return;      // ESCAPED / INVALID / KEYERROR are sticky: the host raises
+        if (r.status == ATR_ST_NONE) return;
+        if (r.status == ATR_ST_MATCH && prev.status == ATR_ST_MATCH && r.matches <= prev.matches) return;
+    }
+    *out = r;
+}
+
+// the literal-hit result of the str.find / startswith / endswith shortcut (adapters/__init__.py:363-367)
+template <class A>
+ATR_HD void emit_exact(const A& ad, int pos, atr_match* out) {
+    atr_match r;
+    r.astart = 0; r.astop = (uint16_t)ad.m; r.rstart = (uint16_t)pos; r.rstop = (uint16_t)(pos + ad.m);
+    r.matches = (uint16_t)ad.m; r.errors = 0; r.adapter = (int16_t)ad.adapter_index; r.status = ATR_ST_MATCH;
+    emit(ad, r, out);
+}
+
+// Turn `best` into the result record: _align.pyx:476-491, then (match_to semantics) the post-filter
+// of Adapter.match_to (adapters/__init__.py:384-398) and Match.__init__'s checks (align/__init__.py:85-88),
+// then AdapterCutter._best_match's reduction over adapters (modifiers.py:116-121).
+template <class A>
+ATR_HD void finalize(const A& ad, const Best& b, int n, atr_match* out) {
+    atr_match r;
+    r.astart = r.astop = r.rstart = r.rstop = r.matches = r.errors = 0;
+    r.adapter = -1;
+    r.status = ATR_ST_NONE;
+    if (b.cost != ad.m + n) {
+        int start1 = 0, start2 = b.origin;
+        if (b.origin < 0) { start1 = -b.origin; start2 = 0; }
+        bool ok = true;
+        bool invalid = false;
+        if (ad.match_to) {
+            const int size = b.ref_stop - start1;
+            ok = size >= ad.min_overlap && b.cost <= (int)ad.thr_div[size];
+            if (ok && ad.rmp_ok != nullptr) {
+                const bool exact = ad.exact_bypass && b.cost == 0 && size == ad.m;     // str.find shortcut skips the gate
+                if (!exact) ok = ad.rmp_ok[size * (ad.m + 1) + b.matches] != 0;
+            }
+            if (ok && size - b.cost <= 0) invalid = true;
+        }
+        if (ok) {
+            r.astart = (uint16_t)start1; r.astop = (uint16_t)b.ref_stop;
+            r.rstart = (uint16_t)start2; r.rstop = (uint16_t)b.q_stop;
+            r.matches = (uint16_t)b.matches; r.errors = (uint16_t)b.cost;
+            r.adapter = (int16_t)ad.adapter_index;
+            r.status = invalid ? ATR_ST_INVALID : ATR_ST_MATCH;
+        }
+    }
+    emit(ad, r, out);
+}
+
+// compare_prefixes / compare_suffixes result -> Best-free direct record (adapters/__init__.py:370-380)
+template <class A>
+ATR_HD void finalize_cmp(const A& ad, int n, int length, int matches, bool suffix, atr_match* out) {
+    Best b;
+    b.matches = matches; b.cost = length - matches; b.ref_stop = suffix ? ad.m : length;
+    b.q_stop = suffix ? n : length;
+    // origin encodes (start1, start2): compare_suffixes returns (m-length, m, n-length, n, ..)
+    // at most one of the two starts is non-zero only if lengths are equal to min(m,n); carry both explicitly.
+    atr_match r;
+    r.astart = r.astop = r.rstart = r.rstop = r.matches = r.errors = 0;
+    r.adapter = -1;
+    r.status = ATR_ST_NONE;
+    const int astart = suffix ? ad.m - length : 0, rstart = suffix ? n - length : 0;
+    const int size = length;                                   // astop - astart
+    bool ok = size >= ad.min_overlap && b.cost <= (int)ad.thr_div[size > 0 ? size : 0];
+    if (ok && ad.rmp_ok != nullptr) {
+        const bool exact = ad.exact_bypass && b.cost == 0 && size == ad.m;
+        if (!exact) ok = ad.rmp_ok[size * (ad.m + 1) + matches] != 0;
+    }
+    if (ok) {
+        r.astart = (uint16_t)astart; r.astop = (uint16_t)b.ref_stop; r.rstart = (uint16_t)rstart;
+        r.rstop = (uint16_t)b.q_stop; r.matches = (uint16_t)matches; r.errors = (uint16_t)b.cost;
+        r.adapter = (int16_t)ad.adapter_index;
+        r.status = (size <= 0 || size - b.cost <= 0) ? ATR_ST_INVALID : ATR_ST_MATCH;
+    }
+    emit(ad, r, out);
+}
+
+// ---- K1a ----------------------------------------------------------------------------------
+
+// uniform binary-search "tap" of register row m (m is a kernel parameter, so the branches never diverge)
+template <int LO, int HI>
+struct Tap {
+    static ATR_HD unsigned get(const unsigned (&col)[ATR_K1A_MAXM + 1], int m) {
+        constexpr int MID = (LO + HI) / 2;
+        return m <= MID ? Tap<LO, MID>::get(col, m) : Tap<MID + 1, HI>::get(col, m);
+    }
+};
+template <int I>
+struct Tap<I, I> {
+    static ATR_HD unsigned get(const unsigned (&col)[ATR_K1A_MAXM + 1], int) { return col[I]; }
+};
+
+ATR_HD unsigned k1a_read_code(const uint32_t* __restrict__ codes, int pos) {
+    return (codes[pos >> 3] >> ((pos & 7) * 4)) & 15u;
+}
+
+// One read (window [lo, lo+n) of the packed read starting at word `codes`) against one adapter.
+template <bool AND_MODE>
+ATR_HD void k1a_locate(const AdapterK1a& ad, const uint32_t* __restrict__ codes, int lo, int n, Best& best) {
+    const int m = ad.m, k = ad.k;
+    const bool start_in_ref = ad.flags & ATR_START_WITHIN_SEQ1, start_in_query = ad.flags & ATR_START_WITHIN_SEQ2;
+    const bool stop_in_ref = ad.flags & ATR_STOP_WITHIN_SEQ1, stop_in_query = ad.flags & ATR_STOP_WITHIN_SEQ2;
+    const unsigned CLAMP = (unsigned)(k + 1) << ATR_COST_SHIFT;
+    const unsigned C_SUB = 1u << ATR_COST_SHIFT;
+    const unsigned C_INS = ((unsigned)ad.ic << ATR_COST_SHIFT) | (1u << ATR_PRIO_SHIFT);
+    const unsigned C_DEL = ((unsigned)ad.ic << ATR_COST_SHIFT) | (2u << ATR_PRIO_SHIFT);
+
+    int max_n = n, min_n = 0;                                              // _align.pyx:315-321
+    if (!start_in_query) max_n = atr_min(n, m + k);
+    if (!stop_in_query) min_n = atr_max(0, n - m - k);
+
+    unsigned col[ATR_K1A_MAXM + 1];
+#pragma unroll
+    for (int i = 0; i <= ATR_K1A_MAXM; i++) {                               // _align.pyx:333-352
+        int cost, origin;
+        if (!start_in_ref && !start_in_query) { cost = atr_max(i, min_n) * ad.ic; origin = 0; }
+        else if (start_in_ref && !start_in_query) { cost = min_n * ad.ic; origin = atr_min(0, min_n - i); }
+        else if (!start_in_ref && start_in_query) { cost = i * ad.ic; origin = atr_max(0, min_n - i); }
+        else { cost = atr_min(i, min_n) * ad.ic; origin = min_n - i; }
+        col[i] = cost > k ? CLAMP : k1a_key(cost, origin, 0);
+    }
+
+    best.ref_stop = m; best.q_stop = n; best.cost = m + n; best.origin = 0; best.matches = 0;
+
+    uint32_t w = 0;
+    if (min_n < max_n) w = codes[(lo + min_n) >> 3];
+#pragma unroll 1
+    for (int j = min_n + 1; j <= max_n; j++) {
+        const int pos = lo + j - 1;
+        if ((pos & 7) == 0) w = codes[pos >> 3];
+        unsigned qc = (w >> ((pos & 7) * 4)) & 15u;
+        if (AND_MODE && ad.q_single_only) qc = (qc & (qc - 1)) ? 0u : qc;
+
+        unsigned diag = col[0];
+        if (start_in_query) col[0] = k1a_key(0, j, 0);                      // :385-386
+        else col[0] = atr_umin(col[0] + ((unsigned)ad.ic << ATR_COST_SHIFT), CLAMP);   // :387-388
+#pragma unroll
+        for (int g = 0; g < ATR_K1A_MAXM / 8; g++) {
+            if (m > g * 8) {
+#pragma unroll
+                for (int r = 1; r <= 8; r++) {
+                    const int i = g * 8 + r;
+                    const unsigned left = col[i];
+                    unsigned t = atr_umin(atr_umin(left + C_DEL, col[i - 1] + C_INS), diag + C_SUB) & ATR_PRIO_CLEAR;
+                    const bool eq = AND_MODE ? ((((unsigned)ad.code[i - 1]) & qc) != 0u) : ((unsigned)ad.code[i - 1] == qc);
+                    unsigned nw = eq ? diag + 1u : t;                       // a match always takes the diagonal (:394-398)
+                    nw = atr_umin(nw, CLAMP);
+                    diag = left;
+                    col[i] = nw;
+                }
+            }
+        }
+        if (stop_in_query) {                                                // :440-458 without the early break
+            const unsigned c = Tap<1, ATR_K1A_MAXM>::get(col, m);
+            if (c < CLAMP) consider(ad, best, k1a_cost(c), k1a_origin(c), k1a_matches(c), m, j);
+        }
+    }
+    if (max_n == n) {                                                       // :461-474
+        if (stop_in_ref) {
+#pragma unroll
+            for (int i = 1; i <= ATR_K1A_MAXM; i++) {
+                if (i <= m) {
+                    const unsigned c = col[i];
+                    if (c < CLAMP) consider(ad, best, k1a_cost(c), k1a_origin(c), k1a_matches(c), i, n);
+                }
+            }
+        } else {
+            const unsigned c = Tap<1, ATR_K1A_MAXM>::get(col, m);
+            if (c < CLAMP) consider(ad, best, k1a_cost(c), k1a_origin(c), k1a_matches(c), m, n);
+        }
+    }
+}
+
+// compare_prefixes / compare_suffixes on packed codes (anchored adapters with indels off)
+template <bool AND_MODE>
+ATR_HD int k1a_compare(const AdapterK1a& ad, const uint32_t* __restrict__ codes, int lo, int n, bool suffix, int& length) {
+    length = atr_min(ad.m, n);
+    int matches = 0;
+    for (int t = 0; t < length; t++) {
+        const int ai = suffix ? ad.m - 1 - t : t;
+        const int pos = lo + (suffix ? n - 1 - t : t);
+        unsigned qc = k1a_read_code(codes, pos);
+        if (AND_MODE && ad.q_single_only) qc = (qc & (qc - 1)) ? 0u : qc;
+        const unsigned a = (unsigned)ad.code[ai];          // uniform index: one constant-bank load
+        matches += AND_MODE ? ((a & qc) != 0u) : (a == qc);
+    }
+    return matches;
+}
+
+// ---- K1g: general byte-exact kernel ---------------------------------------------------------
+
+struct GCell { int cost, pay; };     // pay = (origin + ATR_G_ORG_BIAS) << 16 | matches
+
+ATR_HD int g_pay(int origin, int matches) { return ((origin + ATR_G_ORG_BIAS) << 16) | matches; }
+ATR_HD int g_origin(int pay) { return (int)((unsigned)pay >> 16) - ATR_G_ORG_BIAS; }
+ATR_HD int g_matches(int pay) { return pay & 0xFFFF; }
+
+ATR_HD unsigned gen_qcode(const AdapterGen& ad, const AtrTables& tb, unsigned char ch) {
+    return ad.q_table == 0 ? ch : (ad.q_table == 1 ? tb.iupac[ch] : tb.acgt[ch]);
+}
+
+// col: this thread's DP column, element i at col[i * stride].
+ATR_HD unsigned char gen_char(const unsigned char* __restrict__ read, int p, int fold_case) {
+    unsigned char c = read[p];
+    if (fold_case && c >= 'a' && c <= 'z') c = (unsigned char)(c - 32);      // str.upper() (adapters/__init__.py:349)
+    return c;
+}
+
+ATR_HD void gen_locate(const AdapterGen& ad, const AtrTables& tb, const unsigned char* __restrict__ read, int n,
+                       int fold_case, GCell* col, long stride, Best& best) {
+    const int m = ad.m, k = ad.k, ic = ad.ic;
+    const bool start_in_ref = ad.flags & ATR_START_WITHIN_SEQ1, start_in_query = ad.flags & ATR_START_WITHIN_SEQ2;
+    const bool stop_in_ref = ad.flags & ATR_STOP_WITHIN_SEQ1, stop_in_query = ad.flags & ATR_STOP_WITHIN_SEQ2;
+    int max_n = n, min_n = 0;
+    if (!start_in_query) max_n = atr_min(n, m + k);
+    if (!stop_in_query) min_n = atr_max(0, n - m - k);
+    const int dead = k + 1;
+    for (int i = 0; i <= m; i++) {
+        long cost; int origin;                      // i * ic can exceed int for ic = 100000 and long adapters
+        if (!start_in_ref && !start_in_query) { cost = (long)atr_max(i, min_n) * ic; origin = 0; }
+        else if (start_in_ref && !start_in_query) { cost = (long)min_n * ic; origin = atr_min(0, min_n - i); }
+        else if (!start_in_ref && start_in_query) { cost = (long)i * ic; origin = atr_max(0, min_n - i); }
+        else { cost = (long)atr_min(i, min_n) * ic; origin = min_n - i; }
+        GCell c; c.cost = cost > k ? dead : (int)cost; c.pay = g_pay(origin, 0);
+        col[i * stride] = c;
+    }
+    best.ref_stop = m; best.q_stop = n; best.cost = m + n; best.origin = 0; best.matches = 0;
+    int last = start_in_ref ? m : atr_min(m, k + 1);                        // Ukkonen band (:366-368)
+    for (int j = min_n + 1; j <= max_n; j++) {
+        GCell diag = col[0];
+        GCell up = diag;
+        if (start_in_query) up.pay = g_pay(j, 0);
+        else { long c0 = (long)j * ic; up.cost = c0 > k ? dead : (int)c0; }
+        col[0] = up;
+        const unsigned qc = gen_qcode(ad, tb, gen_char(read, j - 1, fold_case));
+        for (int i = 1; i <= last; i++) {
+            const GCell left = col[i * stride];
+            const unsigned a = ad.ref[i - 1];
+            const bool eq = ad.and_mode ? ((a & qc) != 0u) : (a == qc);
+            GCell nw;
+            if (eq) { nw.cost = diag.cost; nw.pay = diag.pay + 1; }
+            else {
+                const int c_sub = diag.cost + 1, c_del = left.cost + ic, c_ins = up.cost + ic;
+                if (c_sub <= c_del && c_sub <= c_ins) { nw.cost = c_sub; nw.pay = diag.pay; }
+                else if (c_ins <= c_del) { nw.cost = c_ins; nw.pay = up.pay; }
+                else { nw.cost = c_del; nw.pay = left.pay; }
+            }
+            if (nw.cost > k) nw.cost = dead;
+            diag = left;
+            col[i * stride] = nw;
+            up = nw;
+        }
+        while (last >= 0 && col[last * stride].cost > k) last--;           // :433-439
+        if (last < m) {
+            // the row entering the band holds a value > k (initial, or left behind when `last` shrank);
+            // like the reference's stale cells only its being > k matters
+            last++;
+        } else if (stop_in_query) {
+            const GCell c = col[m * stride];
+            consider(ad, best, c.cost, g_origin(c.pay), g_matches(c.pay), m, j);
+        }
+    }
+    if (max_n == n) {
+        for (int i = stop_in_ref ? 0 : m; i <= m; i++) {
+            const GCell c = col[i * stride];
+            if (c.cost <= k) consider(ad, best, c.cost, g_origin(c.pay), g_matches(c.pay), i, n);
+        }
+    }
+}
+
+ATR_HD int gen_compare(const AdapterGen& ad, const AtrTables& tb, const unsigned char* __restrict__ read, int n,
+                       int fold_case, bool suffix, int& length) {
+    length = atr_min(ad.m, n);
+    int matches = 0;
+    for (int t = 0; t < length; t++) {
+        const unsigned a = ad.ref[suffix ? ad.m - 1 - t : t];
+        const unsigned qc = gen_qcode(ad, tb, gen_char(read, suffix ? n - 1 - t : t, fold_case));
+        matches += ad.and_mode ? ((a & qc) != 0u) : (a == qc);
+    }
+    return matches;
+}
+
+// ---- literal search (only for need_find adapters, see adapter_build.hpp) -----------------------
+ATR_HD int k1a_find(const AdapterK1a& ad, const uint32_t* __restrict__ codes, int lo, int n) {
+    const int m = ad.m;
+    if (m > n) return -1;
+    int first = 0, last = n - m;
+    if (ad.flags == ATR_STOP_WITHIN_SEQ2) last = 0;                 // PREFIX: startswith
+    else if (ad.flags == ATR_START_WITHIN_SEQ2) first = n - m;      // SUFFIX: endswith
+    for (int p = first; p <= last; p++) {
+        int t = 0;
+        while (t < m && (unsigned)ad.lit[t] == k1a_read_code(codes, lo + p + t)) t++;
+        if (t == m) return p;
+    }
+    return -1;
+}
+
+ATR_HD int gen_find(const AdapterGen& ad, const unsigned char* __restrict__ read, int n, int fold_case) {
+    const int m = ad.m;
+    if (m > n) return -1;
+    int first = 0, last = n - m;
+    if (ad.flags == ATR_STOP_WITHIN_SEQ2) last = 0;
+    else if (ad.flags == ATR_START_WITHIN_SEQ2) first = n - m;
+    for (int p = first; p <= last; p++) {
+        int t = 0;
+        while (t < m && ad.lit[t] == gen_char(read, p + t, fold_case)) t++;
+        if (t == m) return p;
+    }
+    return -1;
+}
+
+// ---- one read against one adapter, start to finish ---------------------------------------------
+template <bool AND_MODE>
+ATR_HD void k1a_read(const AdapterK1a& ad, const uint32_t* __restrict__ codes, int lo, int n, atr_match* out) {
+    if (ad.need_find) {
+        const int pos = k1a_find(ad, codes, lo, n);
+        if (pos >= 0) { emit_exact(ad, pos, out); return; }
+    }
+    if (ad.cmp_only) {
+        int length;
+        const int matches = k1a_compare<AND_MODE>(ad, codes, lo, n, ad.cmp_only == 2, length);
+        finalize_cmp(ad, n, length, matches, ad.cmp_only == 2, out);
+    } else {
+        Best b;
+        k1a_locate<AND_MODE>(ad, codes, lo, n, b);
+        finalize(ad, b, n, out);
+    }
+}
+
+ATR_HD void gen_read(const AdapterGen& ad, const AtrTables& tb, const unsigned char* __restrict__ read, int n,
+                     int fold_case, GCell* col, long stride, atr_match* out) {
+    if (ad.need_find) {
+        const int pos = gen_find(ad, read, n, fold_case);
+        if (pos >= 0) { emit_exact(ad, pos, out); return; }
+    }
+    if (ad.cmp_only) {
+        int length;
+        const int matches = gen_compare(ad, tb, read, n, fold_case, ad.cmp_only == 2, length);
+        finalize_cmp(ad, n, length, matches, ad.cmp_only == 2, out);
+    } else {
+        Best b;
+        gen_locate(ad, tb, read, n, fold_case, col, stride, b);
+        finalize(ad, b, n, out);
+    }
+}

@@ -1,0 +1,215 @@
+/*
+ * atropos_b200.h -- C ABI of the B200-native adapter-alignment engine.
+ *
+ * This is the drop-in boundary for ONE hot path of jdidion/atropos: the compiled extension
+ * module `atropos.align._align` (Cython) and the two Python methods that call it per read,
+ * `Adapter.match_to()` and `InsertAligner.match_insert()`.  Every entry point below names the
+ * reference interface it replaces (paths relative to the reference checkout).  The reference-side
+ * binding a maintainer would add (a ctypes stub inside atropos/align/__init__.py) is shown in
+ * INTEGRATION.md; `atropos_b200/` in this repository is that binding plus batched twins of the
+ * reference classes.
+ *
+ * Conventions
+ *   - plain C: pointers and sizes only, no C++/torch types; every function returns 0 on success
+ *     or a negative ATR_E_* code, and atr_last_error(ctx) gives a message;
+ *   - the caller owns every buffer it passes; `*_host` entry points take HOST pointers (pageable
+ *     or pinned) and do the H2D/D2H copies themselves, `*_device` entry points take DEVICE
+ *     pointers on the ctx's device and only enqueue kernels on the ctx's stream;
+ *   - one atr_ctx per GPU per host thread; no global state; a ctx is not re-entrant (the
+ *     reference's Aligner is not either: it owns one DP column, _align.pyx:184, :239-242);
+ *   - there is NO CPU fallback: without a CUDA device atr_ctx_create fails with ATR_E_CUDA.
+ *
+ * Data layout in HBM ("packed reads")
+ *   codes   4-bit IUPAC code per base (A=1 C=2 G=4 T=8, unions for R,Y,S,W,K,M,B,D,H,V, N=15,
+ *           X=0 -- the bit assignment of _align.pyx:46-83), two bases per byte, base j of a read
+ *           in bits 4*(j%8) .. 4*(j%8)+3 of 32-bit word j/8; every read starts on a word boundary.
+ *   woff    uint32 per read: index of its first 32-bit word inside `codes`.
+ *   len     uint16 per read: length in bases; bit 15 set = "escaped" read: it holds a byte
+ *           that the 4-bit code cannot represent exactly for ASCII-compare adapters (anything
+ *           outside the 16 upper-case IUPAC letters, e.g. 'U', '.', lower case when case folding
+ *           is off). Escaped reads are aligned by the byte-exact kernel from the raw ASCII.
+ *   result  one 16-byte atr_match per read.
+ */
+#ifndef ATROPOS_B200_H
+#define ATROPOS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ATR_ABI_VERSION 1
+
+/* error codes */
+#define ATR_OK          0
+#define ATR_E_ARG      -1   /* invalid argument (ValueError on the Python side, cf. _align.pyx:214-232) */
+#define ATR_E_CUDA     -2   /* CUDA runtime error / no device */
+#define ATR_E_NOMEM    -3   /* allocation failed (MemoryError, _align.pyx:240-241) */
+#define ATR_E_LIMIT    -4   /* size outside what the kernels support (read > 32767 nt, adapter > 4095 nt) */
+
+/* alignment flags: atropos/align/__init__.py:17-26, _align.pyx:12-16 */
+#define ATR_START_WITHIN_SEQ1 1
+#define ATR_START_WITHIN_SEQ2 2
+#define ATR_STOP_WITHIN_SEQ1  4
+#define ATR_STOP_WITHIN_SEQ2  8
+#define ATR_SEMIGLOBAL       15
+
+/* atr_match.status */
+#define ATR_ST_NONE    0    /* no acceptable alignment: locate() returned None / match_to() returned None */
+#define ATR_ST_MATCH   1
+#define ATR_ST_ESCAPED 2    /* the read needs the byte-exact kernel but no ASCII was supplied (device entry points only) */
+#define ATR_ST_INVALID 3    /* Match.__init__ would raise ValueError (align/__init__.py:85-88) */
+#define ATR_ST_KEYERROR 4   /* reverse_complement would raise KeyError: a byte outside the IUPAC table (util/__init__.py:479-482) */
+
+/* One alignment result: the 6-tuple of Aligner.locate (_align.pyx:491) == the fields of
+ * Match (align/__init__.py:51-88), plus which adapter of the set won (AdapterCutter._best_match,
+ * commands/trim/modifiers.py:107-122). 16 bytes. */
+typedef struct atr_match {
+    uint16_t astart, astop;   /* refstart, refstop   (within the adapter) */
+    uint16_t rstart, rstop;   /* querystart, querystop (within the read / window) */
+    uint16_t matches, errors;
+    int16_t  adapter;         /* index into the adapter set, -1 if none */
+    uint16_t status;          /* ATR_ST_* */
+} atr_match;
+
+/* Result of InsertAligner.match_insert (align/__init__.py:250-377) for one pair. 48 bytes.
+ * status: ATR_ST_NONE -> returned None; ATR_ST_MATCH -> (insert_match, match1, match2) where
+ * match{1,2}.status == ATR_ST_NONE encodes Python None (the "(insert_match, None, None)" case). */
+typedef struct atr_insert_result {
+    atr_match insert;         /* the winning MultiAligner tuple; .adapter unused */
+    atr_match match1, match2; /* Match(0, alen, insert_size, slen, alen-mm, mm) */
+} atr_insert_result;
+
+/* Constructor arguments of Aligner (_align.pyx:197-208) + the post-filter of Adapter.match_to
+ * (adapters/__init__.py:338-400). */
+typedef struct atr_adapter_desc {
+    const char* sequence;     /* ASCII, `length` bytes, as the reference would hold it (Adapter upper-cases and U->T first) */
+    int32_t length;
+    double  max_error_rate;
+    int32_t flags;            /* ATR_* flags; BACK=14 FRONT=11 PREFIX=8 SUFFIX=2 ANYWHERE=15 */
+    int32_t wildcard_ref;     /* adapter_wildcards */
+    int32_t wildcard_query;   /* read_wildcards */
+    int32_t min_overlap;      /* >= 1 (ATR_E_ARG otherwise) */
+    int32_t indel_cost;       /* >= 1; 100000 is how the reference spells "--no-indels" */
+    /* 0: raw Aligner.locate semantics.
+     * 1: Adapter.match_to semantics: afterwards require size >= min_overlap and errors/size <= rate
+     *    (adapters/__init__.py:386-392), the rmp_ok gate unless the hit is the exact-find shortcut
+     *    (:351-367), and anchored no-indel adapters use compare_prefixes/suffixes (:370-380). */
+    int32_t match_to_semantics;
+    int32_t no_indels;        /* Adapter(indels=False): only meaningful with match_to_semantics */
+    /* optional max_rmp gate: rmp_ok[size*(length+1)+matches] != 0 iff
+     * match_probability(matches,size) <= max_rmp, for 0 <= matches,size <= length; NULL = no gate.
+     * Computed by the host binding with the reference's own big-int arithmetic
+     * (util/__init__.py:117-155). */
+    const uint8_t* rmp_ok;
+} atr_adapter_desc;
+
+/* Constructor arguments of InsertAligner (align/__init__.py:206-233). The probability tables are
+ * computed by the host binding with RandomMatchProbability (util/__init__.py:104-174):
+ *   insert_prob[size*(kmax+1)+cost]         = match_probability(size-cost,size,**base_probs) (:358)
+ *                                             for size <= max_len, cost <= kmax = (int)(frac*max_len)
+ *   adapter_prob[alen*(alen_max+1)+matches] = match_probability(matches,alen)               (:303-304)
+ * with alen_max = max(len(adapter1), len(adapter2)). Only costs <= (int)(frac*size) are ever looked up. */
+typedef struct atr_insert_desc {
+    const char* adapter1; int32_t adapter1_len;
+    const char* adapter2; int32_t adapter2_len;
+    double  insert_max_rmp, adapter_max_rmp;
+    int32_t min_insert_overlap;
+    double  max_insert_mismatch_frac;
+    int32_t min_adapter_overlap;
+    double  max_adapter_mismatch_frac;
+    int32_t adapter_check_cutoff;
+    int32_t adapter_wildcards, read_wildcards;
+    int32_t max_len;                 /* longest read the tables cover */
+    const double* insert_prob;       /* (max_len+1)*(kmax+1) doubles */
+    const double* adapter_prob;      /* (alen_max+1)^2 doubles */
+} atr_insert_desc;
+
+typedef struct atr_ctx atr_ctx;
+typedef struct atr_adapterset atr_adapterset;
+typedef struct atr_insertset atr_insertset;
+
+/* ---- library / context -------------------------------------------------------------------- */
+int         atr_abi_version(void);
+int         atr_device_count(void);
+/* Owns a CUDA stream, events and grow-only device/pinned scratch. Replaces the per-process
+ * aligner state of the reference workers (commands/multicore.py:404-414). */
+int         atr_ctx_create(int device, atr_ctx** out);
+void        atr_ctx_destroy(atr_ctx* ctx);
+const char* atr_last_error(const atr_ctx* ctx);          /* ctx may be NULL: last global error */
+int         atr_ctx_sync(atr_ctx* ctx);
+void*       atr_ctx_stream(atr_ctx* ctx);                /* cudaStream_t, for callers that time with events */
+/* kernels launched on this ctx since creation / since the last reset (bench.py's gpu_launches) */
+int64_t     atr_ctx_launch_count(atr_ctx* ctx, int reset);
+/* device time in ms of the kernels of the last *_device / *_host call, measured with CUDA events
+ * on the ctx stream around the kernel launches only (copies excluded) */
+float       atr_ctx_last_kernel_ms(atr_ctx* ctx);
+
+/* ---- adapters: Aligner.__cinit__ / Adapter.__init__ ---------------------------------------- */
+/* replaces Aligner(reference, max_error_rate, flags, wildcard_ref, wildcard_query, min_overlap,
+ * indel_cost) (_align.pyx:197-249), one per adapter of an AdapterCutter (modifiers.py:100-105). */
+int  atr_adapterset_create(atr_ctx* ctx, int32_t n_adapters, const atr_adapter_desc* descs, atr_adapterset** out);
+void atr_adapterset_destroy(atr_adapterset* set);
+
+/* ---- reads: 4-bit packing ------------------------------------------------------------------ */
+/* Size in 32-bit words of the packed form of n reads given their ASCII offsets (n+1 entries). */
+int64_t atr_packed_words(const int64_t* offsets, int64_t n);
+/* Device-side packer: d_ascii (bytes), d_offsets (int64[n+1]) -> d_codes/d_woff/d_len as described
+ * above; d_woff must hold n+1 entries. fold_case != 0 applies str.upper() first
+ * (adapters/__init__.py:349). Replaces `query.encode('ascii')` + bytes.translate (_align.pyx:281-297). */
+int  atr_pack_device(atr_ctx* ctx, const uint8_t* d_ascii, const int64_t* d_offsets, int64_t n,
+                     int fold_case, uint32_t* d_codes, uint32_t* d_woff, uint16_t* d_len);
+
+/* ---- Aligner.locate / Adapter.match_to / AdapterCutter._best_match over a batch ------------- */
+/* Device-resident form. For every read i (window d_win[2i], d_win[2i+1] if d_win != NULL, else the
+ * whole read) aligns every adapter of the set and keeps the best (strictly more matches wins, the
+ * first adapter on ties). d_ascii/d_offsets may be NULL if no read is escaped. Asynchronous on the
+ * ctx stream. Replaces Aligner.locate (_align.pyx:266-491) called from Adapter.match_to
+ * (adapters/__init__.py:382) inside AdapterCutter._best_match (modifiers.py:107-122). */
+int  atr_locate_batch_device(atr_ctx* ctx, const atr_adapterset* set, const uint32_t* d_codes,
+                             const uint32_t* d_woff, const uint16_t* d_len, const uint16_t* d_win,
+                             const uint8_t* d_ascii, const int64_t* d_offsets, int fold_case, int64_t n,
+                             atr_match* d_out);
+/* Host form (what the Python binding calls): ASCII reads back to back + offsets[n+1] in host
+ * memory, results into host memory; copies, packing and kernels inside. win may be NULL. */
+int  atr_locate_batch_host(atr_ctx* ctx, const atr_adapterset* set, const uint8_t* ascii,
+                           const int64_t* offsets, const uint16_t* win, int64_t n, int fold_case,
+                           atr_match* out);
+
+/* ---- compare_prefixes (_align.pyx:501-544) -------------------------------------------------- */
+/* One (ref, query) pair per call: compare_prefixes(ref, query, wildcard_ref, wildcard_query);
+ * out6 = (0, length, 0, length, matches, length - matches). compare_suffixes
+ * (align/__init__.py:28-44) is this on reversed strings; the binding does the reversal. */
+int  atr_compare_prefixes(atr_ctx* ctx, const char* ref, int32_t m, const char* query, int32_t n,
+                          int wildcard_ref, int wildcard_query, int32_t* out6);
+
+/* ---- MultiAligner.locate / InsertAligner.match_insert --------------------------------------- */
+/* replaces InsertAligner.__init__ (align/__init__.py:206-233) */
+int  atr_insertset_create(atr_ctx* ctx, const atr_insert_desc* desc, atr_insertset** out);
+void atr_insertset_destroy(atr_insertset* set);
+/* replaces InsertAligner.match_insert(seq1, seq2) (align/__init__.py:250-377), which wraps
+ * reverse_complement (util/__init__.py:479-482), MultiAligner.locate (_align.pyx:593-772) and
+ * compare_prefixes. Reads 1 and 2 are two packed batches of the same n. */
+int  atr_match_insert_batch_device(atr_ctx* ctx, const atr_insertset* set,
+                                   const uint32_t* d_codes1, const uint32_t* d_woff1, const uint16_t* d_len1,
+                                   const uint32_t* d_codes2, const uint32_t* d_woff2, const uint16_t* d_len2,
+                                   const uint8_t* d_ascii1, const int64_t* d_offsets1,
+                                   const uint8_t* d_ascii2, const int64_t* d_offsets2,
+                                   int64_t n, atr_insert_result* d_out);
+int  atr_match_insert_batch_host(atr_ctx* ctx, const atr_insertset* set,
+                                 const uint8_t* ascii1, const int64_t* offsets1,
+                                 const uint8_t* ascii2, const int64_t* offsets2,
+                                 int64_t n, atr_insert_result* out);
+/* replaces MultiAligner(max_error_rate, flags, min_overlap).locate(reference, query, max_matches)
+ * (_align.pyx:593-772) for one pair and any flag set: candidates in emission order (incl. the
+ * duplicate of the last-column scan and the [exact] collapse). out6 must hold
+ * 6*(max_matches+m+2) ints; *n_out = number of tuples (0 == None). */
+int  atr_multi_locate(atr_ctx* ctx, const char* reference, int32_t m, const char* query, int32_t n,
+                      double max_error_rate, int32_t flags, int32_t min_overlap, int32_t max_matches,
+                      int32_t* out6, int32_t* n_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ATROPOS_B200_H */

@@ -1,0 +1,96 @@
+// tests/host_sim/sim.cpp -- TEST-ONLY: runs the per-read device functions of
+// atropos_b200/csrc/locate_core.cuh on the CPU (they are __host__ __device__) so that the kernel
+// logic can be checked against the oracle in the GPU-less build container. Never part of the product.
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include "../../atropos_b200/csrc/adapter_build.hpp"
+#include "../../atropos_b200/csrc/locate_core.cuh"
+#include "../../atropos_b200/csrc/insert_core.cuh"
+
+extern "C" {
+
+// route: 0 = as the kernels would, 1 = force the general kernel (K1g), 2 = force K1a (error if not possible)
+int sim_locate(const atr_adapter_desc* d, int adapter_index, int reduce, const unsigned char* read, int len,
+               int lo, int hi, int fold_case, int route, atr_match* out, int* used_k1a) {
+    AtrTables tb;
+    atr::build_tables(tb);
+    atr::HostAdapter h;
+    std::string msg;
+    int rc = atr::prepare_adapter(*d, tb, h, msg);
+    if (rc != ATR_OK) return rc;
+    if (hi > len) hi = len;
+    if (lo > hi) lo = hi;
+    const int n = hi - lo;
+    const int nwords = (len + 7) / 8;
+    std::vector<uint32_t> codes((size_t)nwords + 1, 0);
+    int esc = 0;
+    for (int w = 0; w < nwords; w++) codes[w] = atr::pack_word(read, len, w, fold_case, tb.iupac, &esc);
+    bool k1a = h.k1a_ok && n <= ATR_K1A_MAXN && !(esc && (!h.and_mode || h.need_find));
+    if (route == 1) k1a = false;
+    if (route == 2 && !k1a) return -100;
+    if (used_k1a) *used_k1a = k1a;
+    const unsigned char* rmp = h.rmp_ok.empty() ? nullptr : h.rmp_ok.data();
+    if (k1a) {
+        AdapterK1a a;
+        atr::fill_k1a(h, tb, adapter_index, reduce, rmp, a);
+        if (h.and_mode) k1a_read<true>(a, codes.data(), lo, n, out);
+        else k1a_read<false>(a, codes.data(), lo, n, out);
+    } else {
+        AdapterGen g;
+        atr::fill_gen(h, adapter_index, reduce, h.ref_gen.data(), (const unsigned char*)h.seq.data(), h.thr_mul.data(),
+                      h.thr_div.data(), rmp, g);
+        std::vector<GCell> col((size_t)h.m + 1);
+        gen_read(g, tb, read + lo, n, fold_case, col.data(), 1, out);
+    }
+    return 0;
+}
+
+// InsertAligner.match_insert for one pair through the K2 per-pair functions.
+// route: 0 as the kernels would (packed path unless escaped / too long / X in read2), 1 force the byte path
+int sim_match_insert(const atr_insert_desc* d, const unsigned char* r1, int len1, const unsigned char* r2, int len2,
+                     int route, atr_insert_result* out, int* used_packed) {
+    AtrTables tb;
+    atr::build_tables(tb);
+    atr::HostInsert h;
+    std::string msg;
+    int rc = atr::prepare_insert(*d, tb, h, msg);
+    if (rc) return rc;
+    InsertDev v = h.dev;
+    v.k_by_len = h.k_by_len.data(); v.thr_ins = h.thr_ins.data(); v.maxmm = h.maxmm.data();
+    v.a1_code = h.a1_code.data(); v.a2_code = h.a2_code.data(); v.a1_ascii = h.a1_ascii.data(); v.a2_ascii = h.a2_ascii.data();
+    v.insert_prob = h.insert_prob.data(); v.adapter_prob = h.adapter_prob.data(); v.comp = h.comp.data(); v.ov_tab = h.ov_tab.data();
+    const int m = len1 < len2 ? len1 : len2;
+    if (m > v.max_len) return ATR_E_LIMIT;
+    std::vector<uint32_t> c1((size_t)(len1 + 7) / 8 + 2, 0), c2((size_t)(len2 + 7) / 8 + 2, 0);
+    int esc = 0;
+    for (int w = 0; w < (len1 + 7) / 8; w++) c1[w] = atr::pack_word(r1, len1, w, 0, tb.iupac, &esc);
+    for (int w = 0; w < (len2 + 7) / 8; w++) c2[w] = atr::pack_word(r2, len2, w, 0, tb.iupac, &esc);
+    std::vector<uint32_t> R(ATR_K2_MAXW + 2, 0), Q(ATR_K2_MAXW + 2, 0);
+    std::vector<Cand> cand(ATR_MAX_CAND + 1);
+    bool routed = esc || m > ATR_K2_MAXLEN || !v.packed_ok || route == 1;
+    PackedPair pp;
+    pp.R = R.data(); pp.Q = Q.data(); pp.stride = 1;
+    if (!routed) routed = packed_pair_setup(pp, c1.data(), c2.data(), m) == 0;
+    if (used_packed) *used_packed = !routed;
+    if (!routed) { insert_pair(v, pp, true, m, len1, len2, cand.data(), out); return 0; }
+    BytePair bp;
+    bp.s1 = r1; bp.s2 = r2; bp.comp = v.comp; bp.ov_tab = v.ov_tab; bp.m = m;
+    for (int p = 0; p < m; p++) if (v.comp[r2[p]] == 0) {
+        im_clear(out->insert); im_clear(out->match1); im_clear(out->match2);
+        out->insert.status = ATR_ST_KEYERROR;
+        return 0;
+    }
+    insert_pair(v, bp, false, m, len1, len2, cand.data(), out);
+    return 0;
+}
+
+int sim_multi_locate(const unsigned char* ref, int m, const unsigned char* query, int n, double rate, int flags,
+                     int min_overlap, int max_matches, int* out6) {
+    std::vector<unsigned short> thr((size_t)m + 1);
+    for (int l = 0; l <= m; l++) thr[l] = atr::thr_mul_of(l, rate);
+    std::vector<GCellM> col((size_t)m + 1);
+    return gen_multi_locate(ref, m, query, n, (int)(rate * m), thr.data(), flags, min_overlap, max_matches, col.data(), out6);
+}
+
+}  // extern "C"

@@ -1,0 +1,374 @@
+"""Parity of the CUDA path (through the C ABI / the reference-shaped Python mirror) with the CPU oracle
+and the committed golden vectors from the real reference. Bar: BIT-EXACT on every field
+(astart, astop, rstart, rstop, matches, errors, None-ness, winning adapter). Needs a GPU."""
+import numpy as np
+import pytest
+
+import fuzzgen
+import golden_util
+from oracle import oracle
+
+pytestmark = pytest.mark.gpu
+
+T1 = "AGATCGGAAGAGCACACGTCTGAACTCCAGTCAC"
+T2 = "AGATCGGAAGAGCGTCGTGTAGGGAAAGAGTGTAGATCTCGGTGGTCGCCGTATCATT"
+FIELDS = ("astart", "astop", "rstart", "rstop", "matches", "errors")
+
+
+def _tup(rec):
+    return tuple(int(rec[k]) for k in FIELDS)
+
+
+def _check_locate_array(got, exp7):
+    """got: MATCH_DTYPE array; exp7: int32 [n,7] from oracle.locate_batch."""
+    from atropos_b200 import _abi
+    found = exp7[:, 0] == 1
+    assert np.array_equal(got["status"] == _abi.ATR_ST_MATCH, found)
+    assert np.array_equal(got["status"] == _abi.ATR_ST_NONE, ~found)
+    for c, k in enumerate(FIELDS):
+        assert np.array_equal(got[k][found].astype(np.int64), exp7[found, c + 1].astype(np.int64)), k
+    return int(found.sum())
+
+
+def test_reference_known_answers():
+    """the reference test-suite's KATs through the drop-in names (tests/test_align.py, tests/test_adapters.py)"""
+    from atropos_b200.adapters import Adapter, BACK, LinkedAdapter
+    from atropos_b200.align import Aligner, InsertAligner, MultiAligner, compare_prefixes, compare_suffixes, locate
+    Aligner('CTCCAGCTTAGACATATC', 0.1, flags=BACK).locate('CC')
+    Aligner('GCTTAGACATATC', 1.0, flags=BACK).locate('CAA')
+    s, t = 'AAAAAAAAAAAAAAAAA', 'ACAGAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAA'
+    assert locate(s, t, 0.0, BACK) == (0, len(s), 4, 4 + len(s), len(s), 0)
+    assert compare_prefixes('AAXAA', 'AAAAATTTTTTTTT') == (0, 5, 0, 5, 4, 1)
+    assert compare_prefixes('AANAA', 'AACAATTTTTTTTT', wildcard_ref=True) == (0, 5, 0, 5, 5, 0)
+    assert compare_prefixes('XAAAAA', 'AAAAATTTTTTTTT') == (0, 6, 0, 6, 4, 2)
+    assert compare_suffixes('AAXAA', 'TTTTTTTAAAAA') == (0, 5, 7, 12, 4, 1)
+    assert compare_suffixes('AANAA', 'TTTTTTTAACAA', wildcard_ref=True) == (0, 5, 7, 12, 5, 0)
+    assert compare_suffixes('AAAAAX', 'TTTTTTTAAAAA') == (0, 6, 6, 12, 4, 2)
+    W = ['CCCATTGATC', 'CCCRTTRATC', 'YCCATYGATC', 'CSSATTSATC', 'CCCWWWGATC', 'CCCATKKATC', 'CCMATTGMTC', 'BCCATTBABC',
+         'CCCDTTDADC', 'CHCATHGATC', 'CVCVTTVATC', 'CCNATNGATC', 'CCCNTTNATC']
+    r = 'CATCTGTCC' + W[0] + 'GCCAGGGTTGATTCGGCTGATCTGGCCG'
+    for a in W:
+        assert locate(a, r, 0.0, BACK, wildcard_ref=True) == (0, 10, 9, 19, 10, 0)
+    assert locate('CCCXTTXATC', r, 0.0, BACK, wildcard_ref=True) is None
+    for sq in W:
+        rr = 'CATCTGTCC' + sq + 'GCCAGGGTTGATTCGGCTGATCTGGCCG'
+        assert locate(W[0], rr, 0.0, BACK, wildcard_query=True) == (0, 10, 9, 19, 10, 0)
+        assert locate(W[3], rr, 0.0, BACK, wildcard_ref=True, wildcard_query=True) == (0, 10, 9, 19, 10, 0)
+    assert locate('CTGATCTGGCCG', 'AAAAGGG', 0.1, BACK) is None
+    # issue 80: the indel tie-break (tests/test_adapters.py:44-68)
+    ad = Adapter("TCGTATGCCGTCTTC", BACK, max_error_rate=0.2, min_overlap=3, read_wildcards=False, adapter_wildcards=False)
+    res = ad.match_to("TCGTATGCCCTCC")
+    assert res.errors == 3 and res.astart == 0 and res.astop == 15
+    # insert aligner (tests/test_align.py:156-179)
+    a1, a2 = 'TTAGACATATGG', 'CAGTGGAGTATA'
+    _, m1, m2 = InsertAligner(a1, a2).match_insert('AGTCGAGCCCATTGCAGACT' + a1[0:10], 'AGTCTGCAATGGGCTCGACT' + a2[0:10])
+    assert (m1.rstart, m1.length, m2.rstart, m2.length) == (20, 10, 20, 10)
+    _, m1, m2 = InsertAligner('TTAGACATAT', 'CAGTGGAGTA').match_insert('GACAGGCCGTTTGAATGTTGACGGGATGTT',
+                                                                       'CATCCCGTCAACATTCAAACGGCCTGTCCA')
+    assert (m1.rstart, m1.length, m2.rstart, m2.length) == (28, 2, 28, 2)
+    # MultiAligner (tests/test_align.py:195-234)
+    ms = MultiAligner(max_error_rate=0, min_overlap=3).locate('AGAGATCAGATGACAGATC', 'GATCA')
+    assert sorted(ms, key=lambda x: -x[4]) == [(3, 8, 0, 5, 5, 0), (15, 19, 0, 4, 4, 0)]
+    ms = MultiAligner(max_error_rate=0.1, min_overlap=10).locate('GATATCAGATGACAGATCAGAGATCAGAT', 'GAGATCAGATGA')
+    assert sorted(ms, key=lambda x: x[5]) == [(19, 29, 0, 10, 10, 0), (0, 12, 0, 12, 11, 1)]
+    # linked adapter (tests/test_adapters.py:119-125)
+    lm = LinkedAdapter('AAAA', 'TTTT').match_to('AAAACCCCCTTTT')
+    assert 'AAAACCCCCTTTT'[lm.front_match.rstop:][:lm.back_match.rstart] == 'CCCCC'
+    with pytest.raises(ValueError):
+        Aligner('ACGT', 0.1).min_overlap = 0
+
+
+def test_golden_locate():
+    """5000 reference-generated cases; grouped so that each adapter configuration is one GPU batch"""
+    from atropos_b200.align import Aligner
+    cases = golden_util.load("locate")
+    groups = {}
+    for c in cases:
+        key = (c["reference"], c["max_error_rate"], c["flags"], c["wildcard_ref"], c["wildcard_query"], c["min_overlap"],
+               c["indel_cost"])
+        groups.setdefault(key, []).append(c)
+    from atropos_b200 import _abi
+    for key, cs in groups.items():
+        al = Aligner(key[0], key[1], key[2], key[3], key[4], key[5], key[6])
+        res = al.locate_batch([c["query"] for c in cs])
+        for c, rec in zip(cs, res):
+            got = None if rec["status"] == _abi.ATR_ST_NONE else _tup(rec)
+            assert got == (None if c["expect"] is None else tuple(c["expect"])), c
+
+
+def test_golden_match_to_insert_multi():
+    from atropos_b200 import _abi
+    from atropos_b200.adapters import Adapter
+    from atropos_b200.align import InsertAligner, MultiAligner
+    from atropos_b200.util import RandomMatchProbability
+    rmp = RandomMatchProbability()
+    for c in golden_util.load("match_to"):
+        ad = Adapter(c["sequence"], c["where"], match_probability=rmp, max_rmp=c["max_rmp"], **c["kw"])
+        res = ad.match_to_batch(c["reads"])
+        for read, exp, rec in zip(c["reads"], c["expect"], res):
+            m = ad.match_from_record(rec)
+            assert (None if m is None else list(m.fields()) + [bool(m.front)]) == exp, (c, read)
+    for g in golden_util.load("match_insert"):
+        ia = InsertAligner(g["adapter1"], g["adapter2"], **g["kw"])
+        res = ia.match_insert_batch([p[0] for p in g["pairs"]], [p[1] for p in g["pairs"]])
+        for exp, rec in zip(g["expect"], res):
+            got = InsertAligner.result_from_record(rec)
+            if exp is None:
+                assert got is None
+            else:
+                assert list(got[0]) == exp[0]
+                for gm, em in ((got[1], exp[1]), (got[2], exp[2])):
+                    assert (None if gm is None else list(gm.fields())) == (None if em is None else em[:6])
+    for c in golden_util.load("multi_locate")[:200]:
+        got = MultiAligner(c["max_error_rate"], c["flags"], c["min_overlap"]).locate(c["reference"], c["query"])
+        assert got == (None if c["expect"] is None else [tuple(t) for t in c["expect"]])
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_locate_fuzz_batches(seed):
+    """random adapter configurations x ragged batches, all flag sets / indel costs / modes, vs the C oracle"""
+    from atropos_b200.align import Aligner
+    rng = np.random.default_rng(900 + seed)
+    total = 0
+    for _ in range(40):
+        wild = rng.random() < 0.3
+        m = int(rng.integers(1, 65)) if rng.random() < 0.85 else int(rng.integers(65, 200))
+        ad = fuzzgen.rand_seq(rng, m, "ACGTACGTACGTNRYSWKMBDHVX" if wild else "ACGT")
+        wr, wq = [(False, False), (True, False), (False, True), (True, True)][int(rng.integers(1, 4)) if wild else 0]
+        rate = float(rng.choice([0.0, 0.05, 0.1, 0.15, 0.2, 0.3, 0.5, 1.0]))
+        flags = int(rng.choice([14, 14, 11, 8, 2, 15, 9, 0, 5, 7]))
+        mo, ic = int(rng.choice([1, 3, 5, 10])), int(rng.choice([1, 1, 2, 3, 100000]))
+        proj = "".join(ch if ch in "ACGT" else "ACGT"[int(rng.integers(0, 4))] for ch in ad)
+        reads = []
+        for _ in range(600):
+            r = fuzzgen.read_with_adapter(rng, proj, int(rng.integers(0, 230)))
+            if rng.random() < 0.05:
+                arr = list(r)
+                for i in range(len(arr)):
+                    if rng.random() < 0.1:
+                        arr[i] = "acgtnNRYU."[int(rng.integers(0, 10))]
+                r = "".join(arr)
+            reads.append(r)
+        blob = np.frombuffer("".join(reads).encode(), dtype=np.uint8)
+        offs = np.zeros(len(reads) + 1, dtype=np.int64)
+        np.cumsum([len(r) for r in reads], out=offs[1:])
+        exp = oracle.locate_batch(ad, blob, offs, rate, flags, wr, wq, mo, ic)
+        got = Aligner(ad, rate, flags, wr, wq, mo, ic).locate_batch((blob, offs))
+        total += _check_locate_array(got, exp)
+    assert total > 2000
+
+
+def test_headline_config_se150():
+    """BASELINE config 2 at a size the oracle finishes in seconds: 300 k synthetic 150 nt reads, TruSeq, 0.1"""
+    from atropos_b200 import synth
+    from atropos_b200.adapters import Adapter, BACK
+    n, L = 300000, 150
+    reads = synth.synth_se(n, L, seed=synth.seed_for(2), device="cpu").numpy().reshape(-1)
+    offs = np.arange(n + 1, dtype=np.int64) * L
+    for adapter, mo in ((T1, 3), ("AGATCGGAAGAGC", 3)):
+        got = Adapter(adapter, BACK, 0.1, mo).match_to_batch((reads, offs))
+        exp = oracle.locate_batch(adapter, reads, offs, 0.1, oracle.BACK, False, False, mo, 1)
+        # match_to's post-filter never rejects what locate accepts for BACK adapters without max_rmp
+        hits = _check_locate_array(got, exp)
+        assert hits > n // 4
+
+
+def test_match_to_semantics_batches():
+    from atropos_b200 import _abi
+    from atropos_b200.adapters import Adapter, ANYWHERE, BACK, FRONT, PREFIX, SUFFIX
+    from atropos_b200.util import RandomMatchProbability
+    rng = np.random.default_rng(77)
+    rmp, rmp_o = RandomMatchProbability(), oracle.RandomMatchProbability()
+    found = 0
+    for _ in range(120):
+        where = [BACK, FRONT, ANYWHERE, PREFIX, SUFFIX][int(rng.integers(0, 5))]
+        wild = rng.random() < 0.3
+        seq = fuzzgen.rand_seq(rng, int(rng.integers(3, 70)), "ACGTACGTACGTNRY" if wild else "ACGT")
+        kw = dict(max_error_rate=float(rng.choice([0.0, 0.1, 0.12, 0.2])), min_overlap=int(rng.choice([1, 3, 5])),
+                  read_wildcards=bool(rng.random() < 0.3), adapter_wildcards=bool(rng.random() < 0.7),
+                  indels=bool(rng.random() < 0.7), indel_cost=int(rng.choice([1, 1, 3])))
+        max_rmp = [None, 1e-6, 1e-3][int(rng.integers(0, 3))]
+        mine = Adapter(seq, where, match_probability=rmp, max_rmp=max_rmp, **kw)
+        orc = oracle.OracleAdapter(seq, where, match_probability=rmp_o, max_rmp=max_rmp, **kw)
+        proj = "".join(ch if ch in "ACGT" else "ACGT"[int(rng.integers(0, 4))] for ch in seq)
+        reads = []
+        for _ in range(100):
+            r = fuzzgen.read_with_adapter(rng, proj if rng.random() < 0.7 else seq, int(rng.integers(0, 160)), n_rate=0.02)
+            reads.append(r.lower() if rng.random() < 0.15 else r)
+        res = mine.match_to_batch(reads)
+        for r, rec in zip(reads, res):
+            exp = orc.match_to(r)
+            m = mine.match_from_record(rec)
+            assert (None if m is None else m.fields() + (m.front,)) == exp, (seq, where, kw, max_rmp, r)
+            found += exp is not None
+    assert found > 1500
+
+
+def test_panel_times_linked():
+    """config 4's shapes: best-of-N panel (_best_match), `times` rounds via windows, linked adapters"""
+    from atropos_b200 import _abi
+    from atropos_b200.adapters import Adapter, BACK, FRONT, LinkedAdapter, PREFIX
+    from atropos_b200.modifiers import AdapterCutter
+    rng = np.random.default_rng(88)
+    specs = [(T1, BACK), (T2, BACK), ("TGGAATTCTCGGGTGCCAAGG", BACK), ("GTTCAGAGTTCTACAGTCCGACGATC", PREFIX),
+             ("ACACTCTTTCCCTACACGACGCTCTTCCGATCT", PREFIX), ("AATGATACGGCGACCACCGA", FRONT)]
+    mine = [Adapter(s, w) for s, w in specs]
+    orc = [oracle.OracleAdapter(s, w) for s, w in specs]
+    reads = []
+    for _ in range(4000):
+        s, w = specs[int(rng.integers(0, len(specs)))]
+        body = fuzzgen.read_with_adapter(rng, s, 150)
+        if w != BACK and rng.random() < 0.7:
+            body = (fuzzgen.mutate(rng, s, 0.03, 0.01, 0.01) + body)[:150]
+        reads.append(body)
+    cutter = AdapterCutter(mine, times=2)
+    rounds = cutter.match_rounds_batch(reads)
+    nhit = n2 = 0
+    for i, r in enumerate(reads):
+        cur = r
+        for t in range(2):
+            exp = oracle.best_match(orc, cur) if len(cur) else None
+            rec = rounds[t][i] if t < len(rounds) else None
+            if exp is None:
+                assert rec is None or rec["status"] == _abi.ATR_ST_NONE, (i, t, r)
+                break
+            assert rec["status"] == _abi.ATR_ST_MATCH and int(rec["adapter"]) == exp[0] and _tup(rec) == exp[1][:6], (i, t, r, exp, rec)
+            nhit += t == 0
+            n2 += t == 1
+            cur = cur[exp[1][3]:] if exp[1][6] else cur[:exp[1][2]]
+    assert nhit > 2000 and n2 > 20
+    front, back = "GTTCAGAGTTCTACAGTCCGACGATC", "TGGAATTCTCGGGTGCCAAGG"
+    la = LinkedAdapter(front, back)
+    fa, ba = oracle.OracleAdapter(front, oracle.PREFIX), oracle.OracleAdapter(back, oracle.BACK)
+    lreads = []
+    for _ in range(2000):
+        f = fuzzgen.mutate(rng, front, 0.03, 0.01, 0.01) if rng.random() < 0.7 else fuzzgen.rand_seq(rng, 26)
+        lreads.append((f + fuzzgen.rand_seq(rng, int(rng.integers(0, 60))) + fuzzgen.mutate(rng, back, 0.03, 0.01, 0.01) +
+                       fuzzgen.rand_seq(rng, 30))[:100])
+    fr, bk = la.match_to_batch(lreads)
+    for i, r in enumerate(lreads):
+        exp = oracle.linked_match_to(fa, ba, r)
+        if exp is None:
+            assert fr[i]["status"] == _abi.ATR_ST_NONE and bk[i]["status"] == _abi.ATR_ST_NONE
+        else:
+            assert _tup(fr[i]) == exp[0][:6]
+            assert (None if bk[i]["status"] == _abi.ATR_ST_NONE else _tup(bk[i])) == (None if exp[1] is None else exp[1][:6])
+
+
+def test_insert_config_pe150():
+    """BASELINE config 3 shape: 2x150 synthetic pairs, TruSeq R1/R2, rate 0.1, vs the Python oracle"""
+    from atropos_b200 import synth
+    from atropos_b200.align import InsertAligner
+    n, L = 20000, 150
+    r1, r2 = synth.synth_pe(n, L, seed=synth.seed_for(3), device="cpu")
+    r1, r2 = r1.numpy(), r2.numpy()
+    offs = np.arange(n + 1, dtype=np.int64) * L
+    kw = dict(max_insert_mismatch_frac=0.1, max_adapter_mismatch_frac=0.1)
+    res = InsertAligner(T1, T2, **kw).match_insert_batch((r1.reshape(-1), offs), (r2.reshape(-1), offs))
+    orc = oracle.OracleInsertAligner(T1, T2, **kw)
+    nm = 0
+    for i in range(n):
+        exp = orc.match_insert(bytes(r1[i]).decode(), bytes(r2[i]).decode())
+        got = InsertAligner.result_from_record(res[i])
+        if exp is None:
+            assert got is None, i
+        else:
+            nm += 1
+            assert got[0] == exp[0] and (got[1].fields() if got[1] else None) == exp[1] and \
+                (got[2].fields() if got[2] else None) == exp[2], (i, got, exp)
+    assert nm > n // 4
+
+
+def test_insert_fuzz_modes_and_escapes():
+    from atropos_b200 import _abi
+    from atropos_b200.align import InsertAligner
+    rng = np.random.default_rng(99)
+    cfgs = [dict(), dict(max_insert_mismatch_frac=0.15, max_adapter_mismatch_frac=0.15),
+            dict(max_insert_mismatch_frac=0.3, max_adapter_mismatch_frac=0.2, min_insert_overlap=10, adapter_wildcards=False),
+            dict(read_wildcards=True), dict(read_wildcards=True, adapter_wildcards=False)]
+    for ci, kw in enumerate(cfgs):
+        pairs = []
+        for r1, r2 in fuzzgen.insert_pairs(600 + ci, 1500, T1, T2, lengths=(50, 100, 150, 300), err=0.03):
+            if rng.random() < 0.05:
+                pos = int(rng.integers(0, len(r2)))
+                r2 = r2[:pos] + "aX.n"[int(rng.integers(0, 4))] + r2[pos + 1:]
+            pairs.append((r1, r2))
+        ia = InsertAligner(T1, T2, **kw)
+        res = ia.match_insert_batch([p[0] for p in pairs], [p[1] for p in pairs])
+        orc = oracle.OracleInsertAligner(T1, T2, **kw)
+        for (r1, r2), rec in zip(pairs, res):
+            try:
+                exp = orc.match_insert(r1, r2)
+            except KeyError:
+                assert int(rec["insert"]["status"]) == _abi.ATR_ST_KEYERROR
+                continue
+            got = InsertAligner.result_from_record(rec)
+            if exp is None:
+                assert got is None
+            else:
+                assert got[0] == exp[0] and (got[1].fields() if got[1] else None) == exp[1] and \
+                    (got[2].fields() if got[2] else None) == exp[2], (kw, r1, r2)
+
+
+def test_edge_cases():
+    from atropos_b200 import _abi
+    from atropos_b200.adapters import Adapter, BACK
+    from atropos_b200.align import Aligner, InsertAligner
+    ad = Adapter(T1, BACK)
+    assert len(ad.match_to_batch([])) == 0                                   # empty batch
+    res = ad.match_to_batch(["", "A", T1, "", "ACGT" * 10 + T1[:7]])          # empty and ragged reads
+    assert [int(s) for s in res["status"]] == [0, 0, 1, 0, 1]
+    assert _tup(res[2]) == (0, 34, 0, 34, 34, 0) and _tup(res[4]) == (0, 7, 40, 47, 7, 0)
+    rng = np.random.default_rng(5)
+    big = fuzzgen.rand_seq(rng, 32000) + T1                                  # maximum read size class
+    assert Aligner(T1, 0.1, BACK).locate(big) == oracle.locate(T1, big, 0.1, oracle.BACK)
+    a64 = fuzzgen.rand_seq(rng, 64)
+    r = fuzzgen.rand_seq(rng, 50) + fuzzgen.mutate(rng, a64, 0.05, 0.02, 0.02) + fuzzgen.rand_seq(rng, 20)
+    assert Aligner(a64, 0.2, 15).locate(r) == oracle.locate(a64, r, 0.2, 15)
+    assert InsertAligner(T1, T2).match_insert("", "") is None
+    with pytest.raises(KeyError):
+        InsertAligner(T1, T2).match_insert("ACGT", "AC.T")
+    with pytest.raises(UnicodeEncodeError):
+        Aligner(T1, 0.1).locate("ACGé")
+
+
+def test_full_size_properties():
+    """BASELINE's full size (10 M reads) through size-independent properties: (1) determinism / independence
+    of reads: aligning a permuted batch gives the permuted results; (2) idempotence of trimming: after cutting
+    at rstart the adapter found in round 1 is gone or strictly shorter; (3) planted exact adapters are reported
+    at their planted position; (4) a 200 k random subsample agrees with the oracle."""
+    import torch
+    from atropos_b200 import _abi, synth
+    from atropos_b200.adapters import Adapter, BACK
+    n, L = 10_000_000, 150
+    reads = synth.synth_se(n, L, seed=synth.seed_for(2), device="cuda").cpu().numpy()
+    offs = np.arange(n + 1, dtype=np.int64) * L
+    ad = Adapter(T1, BACK, 0.1, 3)
+    res = ad.match_to_batch((reads.reshape(-1), offs))
+    hit = res["status"] == _abi.ATR_ST_MATCH
+    assert 0.35 < hit.mean() < 0.45
+    rng = np.random.default_rng(1)
+    sub = rng.choice(n, 200000, replace=False)
+    exp = oracle.locate_batch(T1, reads[sub].reshape(-1), np.arange(len(sub) + 1, dtype=np.int64) * L, 0.1, oracle.BACK,
+                              False, False, 3, 1)
+    _check_locate_array(res[sub], exp)
+    perm = rng.permutation(2_000_000)
+    res_p = ad.match_to_batch((reads[:2_000_000][perm].reshape(-1), offs[:2_000_001]))
+    assert np.array_equal(res_p, res[:2_000_000][perm])
+    # (2) windows [0, rstart): a second round never finds the same or a longer adapter stretch at the same place
+    win = np.zeros((2_000_000, 2), dtype=np.uint16)
+    win[:, 1] = np.where(hit[:2_000_000], res["rstart"][:2_000_000], L)
+    res2 = ad.match_to_batch((reads[:2_000_000].reshape(-1), offs[:2_000_001]), win=win)
+    again = (res2["status"] == _abi.ATR_ST_MATCH) & hit[:2_000_000]
+    assert np.all(res2["rstop"][again] <= res["rstart"][:2_000_000][again])
+    # (3) planted exact adapter
+    planted = reads[:1_000_000].copy()
+    pos = rng.integers(0, L - 34, size=len(planted))
+    a = np.frombuffer(T1.encode(), dtype=np.uint8)
+    cols = pos[:, None] + np.arange(34)[None, :]
+    np.put_along_axis(planted, cols, np.broadcast_to(a, cols.shape), axis=1)
+    res3 = ad.match_to_batch((planted.reshape(-1), offs[:1_000_001]))
+    assert np.all(res3["status"] == _abi.ATR_ST_MATCH)
+    full = (res3["errors"] == 0) & (res3["matches"] == 34)
+    assert np.all(res3["rstart"][full] <= pos[full])        # leftmost exact occurrence (an earlier one can exist by design)
+    assert full.mean() > 0.999

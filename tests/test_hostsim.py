@@ -1,0 +1,232 @@
+"""The per-read / per-pair device functions (atropos_b200/csrc/*_core.cuh are __host__ __device__), compiled
+for the CPU by tests/host_sim and compared with the oracle. This is how kernel LOGIC is checked in the
+GPU-less build container; the same comparisons run through the real kernels in test_gpu_parity.py."""
+import numpy as np
+import pytest
+
+import fuzzgen
+import golden_util
+import hostsim
+from atropos_b200 import _abi
+from atropos_b200.adapters import Adapter, ANYWHERE, BACK, FRONT, PREFIX, SUFFIX
+from atropos_b200.align import InsertAligner
+from atropos_b200.util import RandomMatchProbability
+from oracle import oracle
+
+T1 = "AGATCGGAAGAGCACACGTCTGAACTCCAGTCAC"
+T2 = "AGATCGGAAGAGCGTCGTGTAGGGAAAGAGTGTAGATCTCGGTGGTCGCCGTATCATT"
+
+
+def _tup(rec):
+    return tuple(int(rec[k]) for k in ("astart", "astop", "rstart", "rstop", "matches", "errors"))
+
+
+@pytest.mark.parametrize("route", [0, 1])
+def test_locate_fuzz(route):
+    used = bad = 0
+    for c in fuzzgen.locate_cases(21, 6000):
+        exp = oracle.locate(c["reference"], c["query"], c["max_error_rate"], c["flags"], False, False,
+                            c["min_overlap"], c["indel_cost"])
+        d, keep = _abi.make_adapter_desc(c["reference"], c["max_error_rate"], c["flags"], False, False,
+                                         c["min_overlap"], c["indel_cost"])
+        got, k1a, _ = hostsim.locate(c["query"], d, route=route)
+        used += k1a
+        bad += got != exp
+    assert bad == 0
+    assert (used > 5000) if route == 0 else used == 0
+
+
+@pytest.mark.parametrize("route", [0, 1])
+def test_locate_wildcard_fuzz(route):
+    bad = 0
+    for c in fuzzgen.wildcard_locate_cases(22, 4000):
+        exp = oracle.locate(c["reference"], c["query"], c["max_error_rate"], c["flags"], c["wildcard_ref"],
+                            c["wildcard_query"], c["min_overlap"], c["indel_cost"])
+        d, keep = _abi.make_adapter_desc(c["reference"], c["max_error_rate"], c["flags"], c["wildcard_ref"],
+                                         c["wildcard_query"], c["min_overlap"], c["indel_cost"])
+        got, _, _ = hostsim.locate(c["query"], d, route=route)
+        bad += got != exp
+    assert bad == 0
+
+
+def test_locate_golden():
+    for c in golden_util.load("locate"):
+        d, keep = _abi.make_adapter_desc(c["reference"], c["max_error_rate"], c["flags"], c["wildcard_ref"],
+                                         c["wildcard_query"], c["min_overlap"], c["indel_cost"])
+        got, _, _ = hostsim.locate(c["query"], d)
+        assert got == (None if c["expect"] is None else tuple(c["expect"])), c
+
+
+def test_locate_escaped_and_long_reads():
+    """bytes the 4-bit code cannot hold (lower case, U, '.') and reads > 4000 nt take the byte-exact path"""
+    rng = np.random.default_rng(23)
+    d, keep = _abi.make_adapter_desc(T1, 0.1, BACK, False, False, 3, 1)
+    for _ in range(300):
+        read = list(fuzzgen.read_with_adapter(rng, T1, 120))
+        for i in range(len(read)):
+            if rng.random() < 0.05:
+                read[i] = "acgtnU.x"[int(rng.integers(0, 8))]
+        read = "".join(read)
+        got, k1a, _ = hostsim.locate(read, d)
+        assert got == oracle.locate(T1, read, 0.1, BACK, False, False, 3, 1)
+    long_read = fuzzgen.rand_seq(rng, 4500) + T1[:20] + fuzzgen.rand_seq(rng, 100)
+    got, k1a, _ = hostsim.locate(long_read, d)
+    assert not k1a and got == oracle.locate(T1, long_read, 0.1, BACK, False, False, 3, 1)
+    ok_read = long_read[-3900:]
+    got, k1a, _ = hostsim.locate(ok_read, d)
+    assert k1a and got == oracle.locate(T1, ok_read, 0.1, BACK, False, False, 3, 1)
+
+
+def test_locate_long_adapter_and_high_rate():
+    rng = np.random.default_rng(24)
+    for m in (64, 65, 100, 300):
+        ad = fuzzgen.rand_seq(rng, m)
+        for rate in (0.1, 0.2, 1.0, 2.5):
+            d, keep = _abi.make_adapter_desc(ad, rate, 15, False, False, 3, 1)
+            for _ in range(6):
+                read = fuzzgen.read_with_adapter(rng, ad, int(rng.integers(50, 400)))
+                got, k1a, _ = hostsim.locate(read, d)
+                assert got == oracle.locate(ad, read, rate, 15, False, False, 3, 1), (m, rate, read)
+                assert k1a == (m <= 64 and int(rate * m) <= 126)
+
+
+def test_windows():
+    """a (lo, hi) window must behave exactly like slicing the read (times > 1 rounds, linked adapters)"""
+    rng = np.random.default_rng(25)
+    for _ in range(400):
+        where = [BACK, FRONT, ANYWHERE, PREFIX, SUFFIX][int(rng.integers(0, 5))]
+        ad = fuzzgen.rand_seq(rng, int(rng.integers(5, 40)))
+        read = fuzzgen.read_with_adapter(rng, ad, 100)
+        lo = int(rng.integers(0, 60))
+        hi = int(rng.integers(lo, 101))
+        d, keep = _abi.make_adapter_desc(ad, 0.15, where, False, False, 3, 1)
+        got, _, _ = hostsim.locate(read, d, lo=lo, hi=hi)
+        assert got == oracle.locate(ad, read[lo:hi], 0.15, where, False, False, 3, 1)
+
+
+@pytest.mark.parametrize("where", [BACK, FRONT, ANYWHERE, PREFIX, SUFFIX])
+@pytest.mark.parametrize("route", [0, 1])
+def test_match_to_semantics(where, route):
+    rng = np.random.default_rng(30 + where)
+    rmp, rmp_o = RandomMatchProbability(), oracle.RandomMatchProbability()
+    found = 0
+    for _ in range(250):
+        wild = rng.random() < 0.3
+        seq = fuzzgen.rand_seq(rng, int(rng.integers(3, 50)), "ACGTACGTACGTNRY" if wild else "ACGT")
+        kw = dict(max_error_rate=float(rng.choice([0.0, 0.1, 0.12, 0.2])), min_overlap=int(rng.choice([1, 3, 5])),
+                  read_wildcards=bool(rng.random() < 0.3), adapter_wildcards=bool(rng.random() < 0.7),
+                  indels=bool(rng.random() < 0.7), indel_cost=int(rng.choice([1, 1, 3])))
+        max_rmp = [None, 1e-6, 1e-3][int(rng.integers(0, 3))]
+        mine = Adapter(seq, where, match_probability=rmp, max_rmp=max_rmp, **kw)
+        orc = oracle.OracleAdapter(seq, where, match_probability=rmp_o, max_rmp=max_rmp, **kw)
+        d, keep = mine.descriptor()
+        proj = "".join(ch if ch in "ACGT" else "ACGT"[int(rng.integers(0, 4))] for ch in seq)
+        for _ in range(6):
+            read = fuzzgen.read_with_adapter(rng, proj if rng.random() < 0.7 else seq, int(rng.integers(0, 160)),
+                                             n_rate=0.02)
+            if rng.random() < 0.15:
+                read = read.lower()
+            exp = orc.match_to(read)
+            got, _, _ = hostsim.locate(read, d, route=route, fold_case=True)
+            assert got == (None if exp is None else exp[:6]), (seq, where, kw, max_rmp, read)
+            found += exp is not None
+    assert found > 20
+
+
+def test_match_to_golden():
+    rmp = RandomMatchProbability()
+    for c in golden_util.load("match_to"):
+        d, keep = Adapter(c["sequence"], c["where"], match_probability=rmp, max_rmp=c["max_rmp"], **c["kw"]).descriptor()
+        for read, exp in zip(c["reads"], c["expect"]):
+            got, _, _ = hostsim.locate(read, d, fold_case=True)
+            assert got == (None if exp is None else tuple(exp[:6])), (c, read)
+
+
+def test_best_match_reduction():
+    """AdapterCutter._best_match over a panel: run adapters in order with reduce=1 on the same record"""
+    rng = np.random.default_rng(40)
+    seqs = [T1, T2, "TGGAATTCTCGGGTGCCAAGG", "AGATCGGAAGAGC"]
+    mine = [Adapter(s, BACK) for s in seqs]
+    orc = [oracle.OracleAdapter(s, oracle.BACK) for s in seqs]
+    descs = [a.descriptor() for a in mine]
+    for _ in range(1500):
+        read = fuzzgen.read_with_adapter(rng, seqs[int(rng.integers(0, 4))], 100)
+        prev = None
+        for i, (d, keep) in enumerate(descs):
+            _, _, prev = hostsim.locate(read, d, fold_case=True, prev=prev, adapter_index=i)
+        exp = oracle.best_match(orc, read)
+        if exp is None:
+            assert prev.status == _abi.ATR_ST_NONE
+        else:
+            assert prev.adapter == exp[0] and hostsim.decode(prev) == exp[1][:6]
+
+
+@pytest.mark.parametrize("cfg", range(5))
+def test_match_insert(cfg):
+    kw = [dict(max_insert_mismatch_frac=0.1, max_adapter_mismatch_frac=0.1), dict(),
+          dict(max_insert_mismatch_frac=0.3, max_adapter_mismatch_frac=0.2, min_insert_overlap=10, adapter_wildcards=False),
+          dict(read_wildcards=True), dict(read_wildcards=True, adapter_wildcards=False)][cfg]
+    d, keep = InsertAligner(T1, T2, **kw).descriptor(160)
+    orc = oracle.OracleInsertAligner(T1, T2, **kw)
+    matched = packed = 0
+    rng = np.random.default_rng(50 + cfg)
+    for r1, r2 in fuzzgen.insert_pairs(500 + cfg, 700, T1, T2, err=[0.01, 0.03, 0.08, 0.03, 0.03][cfg]):
+        if rng.random() < 0.05:        # bytes outside the packed alphabet: lower case, X (KeyError), '.'
+            pos = int(rng.integers(0, len(r2)))
+            r2 = r2[:pos] + "aX.n"[int(rng.integers(0, 4))] + r2[pos + 1:]
+        try:
+            exp = orc.match_insert(r1, r2)
+        except KeyError:
+            exp = "KEYERROR"
+        for route in (0, 1):
+            rec, used = hostsim.match_insert(d, r1, r2, route)
+            packed += used
+            st = int(rec["insert"]["status"])
+            if exp == "KEYERROR":
+                assert st == _abi.ATR_ST_KEYERROR
+            elif exp is None:
+                assert st == _abi.ATR_ST_NONE
+            else:
+                matched += 1
+                assert st == _abi.ATR_ST_MATCH and _tup(rec["insert"]) == exp[0]
+                for e, g in ((exp[1], rec["match1"]), (exp[2], rec["match2"])):
+                    if e is None:
+                        assert int(g["status"]) == _abi.ATR_ST_NONE
+                    else:
+                        assert int(g["status"]) == _abi.ATR_ST_MATCH and _tup(g) == e
+    assert matched > 200 and packed > 500
+
+
+def test_match_insert_golden():
+    for g in golden_util.load("match_insert"):
+        d, keep = InsertAligner(g["adapter1"], g["adapter2"], **g["kw"]).descriptor(160)
+        for (r1, r2), exp in zip(g["pairs"], g["expect"]):
+            rec, _ = hostsim.match_insert(d, r1, r2)
+            if exp is None:
+                assert int(rec["insert"]["status"]) == _abi.ATR_ST_NONE
+                continue
+            assert list(_tup(rec["insert"])) == exp[0]
+            for e, gm in ((exp[1], rec["match1"]), (exp[2], rec["match2"])):
+                if e is None:
+                    assert int(gm["status"]) == _abi.ATR_ST_NONE
+                else:
+                    assert list(_tup(gm)) == e[:6]
+
+
+def test_multi_locate_general_flags():
+    rng = np.random.default_rng(60)
+    for _ in range(3000):
+        alpha = rng.choice(["ACGT", "AC", "A"])
+        m = int(rng.integers(1, 80))
+        n = m if rng.random() < 0.6 else int(rng.integers(1, 80))
+        ref, q = fuzzgen.rand_seq(rng, m, alpha), fuzzgen.rand_seq(rng, n, alpha)
+        if rng.random() < 0.6:
+            ov = int(rng.integers(1, min(m, n) + 1))
+            q = (fuzzgen.mutate(rng, ref[m - ov:], 0.05, 0, 0, alpha) + q)[:n]
+        rate = float(rng.choice([0, 0.1, 0.2, 0.3]))
+        flags = int(rng.choice([9, 9, 15, 14, 11, 8, 2]))
+        mo, mm = int(rng.choice([1, 3, 10])), int(rng.choice([100, 5, 1]))
+        assert oracle.multi_locate(ref, q, rate, flags, mo, mm) == hostsim.multi_locate(ref, q, rate, flags, mo, mm)
+    for c in golden_util.load("multi_locate"):
+        got = hostsim.multi_locate(c["reference"], c["query"], c["max_error_rate"], c["flags"], c["min_overlap"])
+        assert got == (None if c["expect"] is None else [tuple(t) for t in c["expect"]])
