@@ -134,6 +134,21 @@ inline void fill_k1a(const HostAdapter& h, const AtrTables& tb, int index, int r
         a.thr_div[l] = l <= h.m ? h.thr_div[l] : 0;
     }
     a.rmp_ok = rmp_ok_dev;
+    // K1f (Myers bit-vector filter + windowed DP) needs unit indel cost, a free start in the read and an
+    // anchored start in the adapter (BACK / SUFFIX style flag sets)
+    const bool start_in_ref = h.desc.flags & ATR_START_WITHIN_SEQ1, start_in_query = h.desc.flags & ATR_START_WITHIN_SEQ2;
+    a.fused_ok = h.k1a_ok && h.desc.indel_cost == 1 && start_in_query && !start_in_ref && !h.cmp_only && !h.need_find;
+    for (int c = 0; c < 16; c++) {
+        unsigned cq = (unsigned)c;
+        if (a.and_mode && a.q_single_only) cq = (cq & (cq - 1)) ? 0u : cq;
+        unsigned long long bits = 0;
+        for (int i = 0; i < h.m && i < 64; i++) {
+            const unsigned code = (unsigned)a.code[i];
+            const bool eq = a.and_mode ? ((code & cq) != 0u) : (code == (unsigned)c);
+            if (eq) bits |= 1ull << i;
+        }
+        a.peq[c] = bits;
+    }
 }
 
 inline void fill_gen(const HostAdapter& h, int index, int reduce, const unsigned char* ref_dev, const unsigned char* lit_dev,

@@ -7,6 +7,7 @@
 #include <cfenv>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -57,6 +58,7 @@ struct atr_ctx {
     std::string err;
     int64_t launches = 0;
     float last_ms = -1.f;
+    int disable_fused = 0;           // ATR_DISABLE_FUSED=1: always use the plain register-DP kernel (A/B measurements)
     DevBuf misc;                     // small single-call scratch (compare_prefixes, multi_locate)
 };
 
@@ -154,7 +156,17 @@ int locate_on_stream(atr_ctx* ctx, cudaStream_t st, DevBuf& gen_scratch, const a
             AdapterK1a p = set->k1a[a];
             p.reduce = a > 0;
             p.mark_routed = !have_ascii;
-            if (h.and_mode) k_locate_k1a<true><<<grid_for(n, 128), 128, 0, st>>>(p, d_codes, d_woff, d_len, d_win, n, d_out);
+            if (p.fused_ok && !ctx->disable_fused) {
+                const unsigned g = grid_for(n, ATR_K1F_THREADS);
+                if (h.m <= 32) {
+                    if (h.and_mode) k_locate_fused<uint32_t, true><<<g, ATR_K1F_THREADS, 0, st>>>(p, d_codes, d_woff, d_len, d_win, n, d_out);
+                    else k_locate_fused<uint32_t, false><<<g, ATR_K1F_THREADS, 0, st>>>(p, d_codes, d_woff, d_len, d_win, n, d_out);
+                } else {
+                    if (h.and_mode) k_locate_fused<unsigned long long, true><<<g, ATR_K1F_THREADS, 0, st>>>(p, d_codes, d_woff, d_len, d_win, n, d_out);
+                    else k_locate_fused<unsigned long long, false><<<g, ATR_K1F_THREADS, 0, st>>>(p, d_codes, d_woff, d_len, d_win, n, d_out);
+                }
+            }
+            else if (h.and_mode) k_locate_k1a<true><<<grid_for(n, 128), 128, 0, st>>>(p, d_codes, d_woff, d_len, d_win, n, d_out);
             else k_locate_k1a<false><<<grid_for(n, 128), 128, 0, st>>>(p, d_codes, d_woff, d_len, d_win, n, d_out);
             LAUNCHED(ctx);
             if (have_ascii) {
@@ -223,6 +235,7 @@ int atr_ctx_create(int device, atr_ctx** out) {
     atr_ctx* ctx = new (std::nothrow) atr_ctx();
     if (!ctx) return fail(nullptr, ATR_E_NOMEM, "out of host memory");
     ctx->device = device;
+    { const char* e = getenv("ATR_DISABLE_FUSED"); ctx->disable_fused = (e && e[0] == '1'); }
     CU(cudaSetDevice(device));
     for (int s = 0; s < 2; s++) CU(cudaStreamCreateWithFlags(&ctx->slot[s].stream, cudaStreamNonBlocking));
     CU(cudaEventCreate(&ctx->ev0));

@@ -196,3 +196,128 @@ __global__ void __launch_bounds__(256) k_compare_prefixes(const unsigned char* _
     __syncthreads();
     if (threadIdx.x == 0) *matches_out = s_cnt;
 }
+
+// ---------------------------------------------------------------------------------------------
+// K1f: fused bit-vector filter + windowed DP (the fast path for BACK/SUFFIX-style adapters with
+// unit indel cost, <= 64 nt). One CTA = one tile of 256 reads:
+//   stage   the tile's packed reads are one contiguous span of `codes`: a single TMA bulk copy
+//           (cp.async.bulk, completion on an mbarrier) brings it into shared memory;
+//   phase 1 every thread runs the Myers/Hyyro filter on its read (exact costs, ~1/10 of the DP's
+//           instructions); reads with no acceptable cell are finished (no match);
+//   compact the survivors (about the adapter-containing fraction) are appended to a list in shared
+//           memory, so that phase 2 runs with fully populated warps;
+//   phase 2 thread s takes survivor s and evaluates the tie-broken 3-field DP only on the column
+//           window that can hold an accepted alignment (k1a_locate with c0/c1).
+// ---------------------------------------------------------------------------------------------
+#define ATR_K1F_THREADS 256
+#define ATR_K1F_TILE_WORDS 8192      // 32 KB: 256 reads of up to 256 nt
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    }
+}
+
+template <class WORD, bool AND_MODE>
+__global__ void __launch_bounds__(ATR_K1F_THREADS, 2) k_locate_fused(const __grid_constant__ AdapterK1a ad,
+        const uint32_t* __restrict__ codes, const uint32_t* __restrict__ woff, const uint16_t* __restrict__ len,
+        const uint16_t* __restrict__ win, int64_t n_reads, atr_match* __restrict__ out) {
+    __shared__ __align__(128) uint32_t s_tile[ATR_K1F_TILE_WORDS];
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ int s_count;
+    __shared__ int4 s_surv[ATR_K1F_THREADS];          // {thread, c0, c1, unused}
+    __shared__ WORD s_peq[16];
+
+    const int tid = threadIdx.x;
+    const int64_t t0 = (int64_t)blockIdx.x * ATR_K1F_THREADS;
+    const int cnt = (int)(n_reads - t0 < ATR_K1F_THREADS ? n_reads - t0 : ATR_K1F_THREADS);
+    const uint32_t w_begin = woff[t0], w_end = woff[t0 + cnt];
+    const uint32_t a_begin = w_begin & ~3u;                         // 16-byte aligned start of the span
+    const uint32_t span = ((w_end - a_begin) + 3u) & ~3u;           // words, multiple of 4
+    // TMA needs 16-byte aligned addresses and sizes; the last tile may not read past the end of `codes`
+    const bool last_tile = (t0 + cnt == n_reads);
+    const bool fits = span <= ATR_K1F_TILE_WORDS;
+    const bool use_tma = fits && !last_tile && ((reinterpret_cast<uintptr_t>(codes) & 15) == 0);
+    if (tid < 16) s_peq[tid] = (WORD)ad.peq[tid];
+    if (tid == 0) {
+        s_count = 0;
+        if (use_tma) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar)) : "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
+    }
+    __syncthreads();
+    if (use_tma) {
+        if (tid == 0 && span > 0) tma_load_1d(s_tile, codes + a_begin, span * 4u, &s_bar);
+    } else if (fits) {                                              // edge tile: coalesced cooperative copy
+        for (uint32_t w = tid; w < w_end - a_begin; w += ATR_K1F_THREADS) s_tile[w] = codes[a_begin + w];
+    }
+    // per-read bookkeeping while the copy is in flight
+    const int64_t r = t0 + tid;
+    bool mine = tid < cnt, routed = false;
+    int lo = 0, n = 0;
+    uint32_t wr = 0;
+    if (mine) {
+        const unsigned l = len[r];
+        const bool esc = (l & ATR_ESC_BIT) != 0;
+        int hi = (int)(l & ATR_LEN_MASK);
+        if (win != nullptr) {
+            const int wlo = win[2 * r], whi = win[2 * r + 1];
+            hi = atr_min(hi, whi);
+            lo = atr_min(wlo, hi);
+        }
+        n = hi - lo;
+        wr = woff[r];
+        routed = (esc && !AND_MODE) || n > ATR_K1A_MAXN;            // byte-exact general kernel picks these up
+        if (routed && ad.mark_routed) {
+            atr_match m;
+            m.astart = m.astop = m.rstart = m.rstop = m.matches = m.errors = 0;
+            m.adapter = -1; m.status = ATR_ST_ESCAPED;
+            out[r] = m;
+        }
+    }
+    if (use_tma) { if (span > 0) mbar_wait(&s_bar, 0); }
+    else __syncthreads();
+    const uint32_t* rd = fits ? (s_tile + (wr - a_begin)) : (codes + wr);
+    // ---- phase 1 ----
+    if (mine && !routed) {
+        int c0, c1;
+        if (myers_filter<WORD>(ad, s_peq, rd, lo, n, c0, c1)) {
+            const int slot = atomicAdd(&s_count, 1);
+            s_surv[slot] = make_int4(tid, c0, c1, 0);
+        } else {
+            Best b;
+            b.ref_stop = ad.m; b.q_stop = n; b.cost = ad.m + n; b.origin = 0; b.matches = 0;
+            finalize(ad, b, n, out + r);                          // "no match" (respects the panel reduction)
+        }
+    }
+    __syncthreads();
+    // ---- phase 2: dense over the survivors ----
+    if (tid < s_count) {
+        const int4 sv = s_surv[tid];
+        const int64_t r2 = t0 + sv.x;
+        const unsigned l = len[r2];
+        int hi = (int)(l & ATR_LEN_MASK), lo2 = 0;
+        if (win != nullptr) {
+            const int wlo = win[2 * r2], whi = win[2 * r2 + 1];
+            hi = atr_min(hi, whi);
+            lo2 = atr_min(wlo, hi);
+        }
+        const int n2 = hi - lo2;
+        const uint32_t wr2 = woff[r2];
+        const uint32_t* rd2 = fits ? (s_tile + (wr2 - a_begin)) : (codes + wr2);
+        Best b;
+        k1a_locate<AND_MODE>(ad, rd2, lo2, n2, b, sv.y, sv.z);
+        finalize(ad, b, n2, out + r2);
+    }
+}

@@ -135,9 +135,37 @@ ATR_HD unsigned k1a_read_code(const uint32_t* __restrict__ codes, int pos) {
     return (codes[pos >> 3] >> ((pos & 7) * 4)) & 15u;
 }
 
-// One read (window [lo, lo+n) of the packed read starting at word `codes`) against one adapter.
+// One DP column of K1a: updates col[0..m] in place for read code qc at column j.
 template <bool AND_MODE>
-ATR_HD void k1a_locate(const AdapterK1a& ad, const uint32_t* __restrict__ codes, int lo, int n, Best& best) {
+ATR_HD void k1a_column(const AdapterK1a& ad, unsigned (&col)[ATR_K1A_MAXM + 1], unsigned qc, int j, bool start_in_query,
+                       unsigned CLAMP, unsigned C_SUB, unsigned C_INS, unsigned C_DEL) {
+    const int m = ad.m;
+    unsigned diag = col[0];
+    if (start_in_query) col[0] = k1a_key(0, j, 0);                          // _align.pyx:385-386
+    else col[0] = atr_umin(col[0] + ((unsigned)ad.ic << ATR_COST_SHIFT), CLAMP);   // :387-388
+#pragma unroll
+    for (int g = 0; g < ATR_K1A_MAXM / 8; g++) {
+        if (m > g * 8) {
+#pragma unroll
+            for (int r = 1; r <= 8; r++) {
+                const int i = g * 8 + r;
+                const unsigned left = col[i];
+                unsigned t = atr_umin(atr_umin(left + C_DEL, col[i - 1] + C_INS), diag + C_SUB) & ATR_PRIO_CLEAR;
+                const bool eq = AND_MODE ? ((((unsigned)ad.code[i - 1]) & qc) != 0u) : ((unsigned)ad.code[i - 1] == qc);
+                unsigned nw = eq ? diag + 1u : t;                           // a match always takes the diagonal (:394-398)
+                nw = atr_umin(nw, CLAMP);
+                diag = left;
+                col[i] = nw;
+            }
+        }
+    }
+}
+
+// One read (window [lo, lo+n) of the packed read starting at word `codes`) against one adapter.
+// c0/c1: evaluate only DP columns c0+1..c1 (K1f's windowed second phase; see myers_filter below). c0 < 0 = all.
+template <bool AND_MODE>
+ATR_HD void k1a_locate(const AdapterK1a& ad, const uint32_t* __restrict__ codes, int lo, int n, Best& best,
+                       int c0 = -1, int c1 = -1) {
     const int m = ad.m, k = ad.k;
     const bool start_in_ref = ad.flags & ATR_START_WITHIN_SEQ1, start_in_query = ad.flags & ATR_START_WITHIN_SEQ2;
     const bool stop_in_ref = ad.flags & ATR_STOP_WITHIN_SEQ1, stop_in_query = ad.flags & ATR_STOP_WITHIN_SEQ2;
@@ -149,12 +177,19 @@ ATR_HD void k1a_locate(const AdapterK1a& ad, const uint32_t* __restrict__ codes,
     int max_n = n, min_n = 0;                                              // _align.pyx:315-321
     if (!start_in_query) max_n = atr_min(n, m + k);
     if (!stop_in_query) min_n = atr_max(0, n - m - k);
+    const bool scan_last = max_n == n;                                     // :461
+    // windowed evaluation: start at column c0 as if the read began there. Exact for every cell that can
+    // lie on an accepted alignment ending in the window ("K1f"): costs elsewhere are only
+    // ever over-estimated. Only used for start_in_query && !start_in_ref flag sets.
+    const bool windowed = c0 > min_n;
+    if (c0 >= 0) { min_n = atr_max(min_n, c0); max_n = atr_min(max_n, c1); }
 
     unsigned col[ATR_K1A_MAXM + 1];
 #pragma unroll
     for (int i = 0; i <= ATR_K1A_MAXM; i++) {                               // _align.pyx:333-352
         int cost, origin;
-        if (!start_in_ref && !start_in_query) { cost = atr_max(i, min_n) * ad.ic; origin = 0; }
+        if (windowed) { cost = i * ad.ic; origin = min_n; }
+        else if (!start_in_ref && !start_in_query) { cost = atr_max(i, min_n) * ad.ic; origin = 0; }
         else if (start_in_ref && !start_in_query) { cost = min_n * ad.ic; origin = atr_min(0, min_n - i); }
         else if (!start_in_ref && start_in_query) { cost = i * ad.ic; origin = atr_max(0, min_n - i); }
         else { cost = atr_min(i, min_n) * ad.ic; origin = min_n - i; }
@@ -171,32 +206,13 @@ ATR_HD void k1a_locate(const AdapterK1a& ad, const uint32_t* __restrict__ codes,
         if ((pos & 7) == 0) w = codes[pos >> 3];
         unsigned qc = (w >> ((pos & 7) * 4)) & 15u;
         if (AND_MODE && ad.q_single_only) qc = (qc & (qc - 1)) ? 0u : qc;
-
-        unsigned diag = col[0];
-        if (start_in_query) col[0] = k1a_key(0, j, 0);                      // :385-386
-        else col[0] = atr_umin(col[0] + ((unsigned)ad.ic << ATR_COST_SHIFT), CLAMP);   // :387-388
-#pragma unroll
-        for (int g = 0; g < ATR_K1A_MAXM / 8; g++) {
-            if (m > g * 8) {
-#pragma unroll
-                for (int r = 1; r <= 8; r++) {
-                    const int i = g * 8 + r;
-                    const unsigned left = col[i];
-                    unsigned t = atr_umin(atr_umin(left + C_DEL, col[i - 1] + C_INS), diag + C_SUB) & ATR_PRIO_CLEAR;
-                    const bool eq = AND_MODE ? ((((unsigned)ad.code[i - 1]) & qc) != 0u) : ((unsigned)ad.code[i - 1] == qc);
-                    unsigned nw = eq ? diag + 1u : t;                       // a match always takes the diagonal (:394-398)
-                    nw = atr_umin(nw, CLAMP);
-                    diag = left;
-                    col[i] = nw;
-                }
-            }
-        }
+        k1a_column<AND_MODE>(ad, col, qc, j, start_in_query, CLAMP, C_SUB, C_INS, C_DEL);
         if (stop_in_query) {                                                // :440-458 without the early break
             const unsigned c = Tap<1, ATR_K1A_MAXM>::get(col, m);
             if (c < CLAMP) consider(ad, best, k1a_cost(c), k1a_origin(c), k1a_matches(c), m, j);
         }
     }
-    if (max_n == n) {                                                       // :461-474
+    if (scan_last && max_n == n) {                                          // :461-474
         if (stop_in_ref) {
 #pragma unroll
             for (int i = 1; i <= ATR_K1A_MAXM; i++) {
@@ -210,6 +226,64 @@ ATR_HD void k1a_locate(const AdapterK1a& ad, const uint32_t* __restrict__ codes,
             if (c < CLAMP) consider(ad, best, k1a_cost(c), k1a_origin(c), k1a_matches(c), m, n);
         }
     }
+}
+
+// ---- K1f phase 1: Myers/Hyyro bit-vector filter ------------------------------------------------------
+// Exact unit-cost DP costs (not the tie-broken path): bit i-1 of Pv/Mv = vertical delta +1/-1 between rows
+// i-1 and i of the current column. Finds every cell the reference could accept:
+//   J = { j : D[m][j] <= k }                      (row m inside the loop, needs stop_in_query)
+//   I = { i : D[i][n] <= floor(i * rate), i >= min_overlap }   (last column; all rows if stop_in_ref, else row m)
+// and returns the DP window [c0, c1] that contains every alignment ending in one of them, or false if
+// there is none (the read has no match). Requires start_in_query && !start_in_ref && indel cost 1.
+template <class WORD>
+ATR_HD bool myers_filter(const AdapterK1a& ad, const WORD* __restrict__ peq, const uint32_t* __restrict__ codes, int lo, int n,
+                         int& c0, int& c1) {
+    const int m = ad.m, k = ad.k;
+    const bool stop_in_ref = ad.flags & ATR_STOP_WITHIN_SEQ1, stop_in_query = ad.flags & ATR_STOP_WITHIN_SEQ2;
+    const int min_n = stop_in_query ? 0 : atr_max(0, n - m - k);
+    const WORD ONE = (WORD)1;
+    const WORD top = ONE << (m - 1);
+    WORD Pv = (m >= (int)(8 * sizeof(WORD))) ? ~(WORD)0 : ((ONE << m) - 1);
+    WORD Mv = 0;
+    int score = m;                                     // D[m][min_n] = m (column min_n: cost i, _align.pyx:345-348)
+    int jmin = 0x7fffffff, jmax = -1;
+    uint32_t w = 0;
+    if (min_n < n) w = codes[(lo + min_n) >> 3];
+#pragma unroll 1
+    for (int j = min_n + 1; j <= n; j++) {
+        const int pos = lo + j - 1;
+        if ((pos & 7) == 0) w = codes[pos >> 3];
+        const unsigned qc = (w >> ((pos & 7) * 4)) & 15u;
+        const WORD Eq = peq[qc];                        // 16-entry table (shared memory on the GPU: conflict-free)
+        const WORD Xv = Eq | Mv;
+        const WORD Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
+        WORD Ph = Mv | ~(Xh | Pv);
+        WORD Mh = Pv & Xh;
+        score += (Ph & top) ? 1 : 0;
+        score -= (Mh & top) ? 1 : 0;
+        Ph <<= 1;                                      // row 0 is free in the read: horizontal delta 0 shifts in
+        Mh <<= 1;
+        Pv = Mh | ~(Xv | Ph);
+        Mv = Ph & Xv;
+        if (stop_in_query && score <= k) { jmin = atr_min(jmin, j); jmax = j; }
+    }
+    // last column: D[i][n] = sum of vertical deltas of rows 1..i
+    int imax = 0;
+    {
+        int d = 0;
+        const int first = stop_in_ref ? 1 : m;
+        for (int i = 1; i <= m; i++) {
+            d += (int)((Pv >> (i - 1)) & ONE) - (int)((Mv >> (i - 1)) & ONE);
+            if (i >= first && i >= ad.min_overlap && d <= (int)ad.thr_mul[i]) imax = i;
+        }
+    }
+    if (jmax < 0 && imax == 0) return false;
+    int start = 0x7fffffff;
+    if (jmax >= 0) start = jmin - m - k;
+    if (imax > 0) start = atr_min(start, n - imax - k);
+    c0 = atr_max(min_n, start);
+    c1 = imax > 0 ? n : jmax;
+    return true;
 }
 
 // compare_prefixes / compare_suffixes on packed codes (anchored adapters with indels off)
@@ -383,4 +457,16 @@ ATR_HD void gen_read(const AdapterGen& ad, const AtrTables& tb, const unsigned c
         gen_locate(ad, tb, read, n, fold_case, col, stride, b);
         finalize(ad, b, n, out);
     }
+}
+
+// ---- K1f per read (what the fused kernel does, minus the block-level compaction between the phases) ----
+template <class WORD, bool AND_MODE>
+ATR_HD void k1f_read(const AdapterK1a& ad, const uint32_t* __restrict__ codes, int lo, int n, atr_match* out) {
+    Best b;
+    b.ref_stop = ad.m; b.q_stop = n; b.cost = ad.m + n; b.origin = 0; b.matches = 0;
+    int c0, c1;
+    WORD peq[16];
+    for (int c = 0; c < 16; c++) peq[c] = (WORD)ad.peq[c];
+    if (myers_filter<WORD>(ad, peq, codes, lo, n, c0, c1)) k1a_locate<AND_MODE>(ad, codes, lo, n, b, c0, c1);
+    finalize(ad, b, n, out);
 }

@@ -61,12 +61,16 @@ class ClockSampler(object):
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index=0):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.marks = index, [], None, []
+
+    def mark(self):
+        """remember how many samples existed at this point (start / end of the kernel-only timed region)"""
+        self.marks.append(len(self.rows))
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -85,8 +89,11 @@ class ClockSampler(object):
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm = sorted(int(float(r[1])) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
-        mx = [int(float(r[2])) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        rows = self.rows
+        timed = rows[self.marks[0]:self.marks[1] + 1] if len(self.marks) >= 2 else []
+        under_load = timed if len(timed) >= 2 else rows      # short timed regions: fall back to warm-up + timed + e2e
+        sm = sorted(int(float(r[1])) for r in under_load if len(r) >= 9 and r[1].replace(".", "").isdigit())
+        mx = [int(float(r[2])) for r in rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = set()
         for r in self.rows:
@@ -95,7 +102,7 @@ class ClockSampler(object):
                     if v.lower().startswith("active"):
                         reasons.add(nm)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "samples_in_timed_region": len(timed)}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -233,13 +240,16 @@ def run_ours(args):
         return float(t.item())
 
     # ---- kernel-only leg (value + roofline) ---------------------------------------------------------
-    for _ in range(args.warmup):
-        step_device()
-    ctx.sync()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        time.sleep(0.5)                      # let nvidia-smi start streaming before the timed region
+    for _ in range(args.warmup):
+        step_device()
+    ctx.sync()
     barrier()
+    if rank == 0:
+        sampler.mark()
     ctx.launch_count(reset=True)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
@@ -250,7 +260,8 @@ def run_ours(args):
     barrier()
     launches = ctx.launch_count()
     dev_ms = max_over_ranks(ev0.elapsed_time(ev1))
-    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        sampler.mark()
     ms_per_step = dev_ms / args.steps
     value = world * n / (ms_per_step * 1e-3) / 1e6
 
@@ -264,6 +275,7 @@ def run_ours(args):
         step_host()
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0) / e2e_steps
+    clocks = sampler.stop() if rank == 0 else None
     e2e_value = world * n / e2e_s / 1e6
 
     # parity spot check of the timed outputs (device leg vs host leg must agree bit for bit)
@@ -297,7 +309,7 @@ def run_ours(args):
     }
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        sample = 150_000 * cores
+        sample = min(n, 400_000 * cores)
         rate, secs, kind = cpu_reference_rate(reads_host.numpy(), sample, cores)
         r1, s1, _ = cpu_reference_rate(reads_host.numpy(), 300_000, 1)
         line["cpu_baseline"] = {"value": rate, "unit": "M reads/s", "cores": cores, "kind": kind,

@@ -10,7 +10,8 @@
 
 extern "C" {
 
-// route: 0 = as the kernels would, 1 = force the general kernel (K1g), 2 = force K1a (error if not possible)
+// route: 0 = as the kernels would (K1f if eligible, else K1a, else K1g), 1 = force the general kernel (K1g),
+// 2 = force plain K1a (error if not possible), 3 = require K1f (error if not eligible). *used_k1a: 0 K1g, 1 K1a, 2 K1f
 int sim_locate(const atr_adapter_desc* d, int adapter_index, int reduce, const unsigned char* read, int len,
                int lo, int hi, int fold_case, int route, atr_match* out, int* used_k1a) {
     AtrTables tb;
@@ -28,13 +29,19 @@ int sim_locate(const atr_adapter_desc* d, int adapter_index, int reduce, const u
     for (int w = 0; w < nwords; w++) codes[w] = atr::pack_word(read, len, w, fold_case, tb.iupac, &esc);
     bool k1a = h.k1a_ok && n <= ATR_K1A_MAXN && !(esc && (!h.and_mode || h.need_find));
     if (route == 1) k1a = false;
-    if (route == 2 && !k1a) return -100;
+    if ((route == 2 || route == 3) && !k1a) return -100;
     if (used_k1a) *used_k1a = k1a;
     const unsigned char* rmp = h.rmp_ok.empty() ? nullptr : h.rmp_ok.data();
     if (k1a) {
         AdapterK1a a;
         atr::fill_k1a(h, tb, adapter_index, reduce, rmp, a);
-        if (h.and_mode) k1a_read<true>(a, codes.data(), lo, n, out);
+        if (route == 3 && !a.fused_ok) return -101;
+        if (used_k1a && a.fused_ok && route != 2) *used_k1a = 2;
+        if (a.fused_ok && route != 2) {                // as the library does: the fused kernel whenever eligible
+            if (h.and_mode) { if (h.m <= 32) k1f_read<uint32_t, true>(a, codes.data(), lo, n, out); else k1f_read<uint64_t, true>(a, codes.data(), lo, n, out); }
+            else { if (h.m <= 32) k1f_read<uint32_t, false>(a, codes.data(), lo, n, out); else k1f_read<uint64_t, false>(a, codes.data(), lo, n, out); }
+        }
+        else if (h.and_mode) k1a_read<true>(a, codes.data(), lo, n, out);
         else k1a_read<false>(a, codes.data(), lo, n, out);
     } else {
         AdapterGen g;
