@@ -138,6 +138,17 @@ inline void fill_k1a(const HostAdapter& h, const AtrTables& tb, int index, int r
     // anchored start in the adapter (BACK / SUFFIX style flag sets)
     const bool start_in_ref = h.desc.flags & ATR_START_WITHIN_SEQ1, start_in_query = h.desc.flags & ATR_START_WITHIN_SEQ2;
     a.fused_ok = h.k1a_ok && h.desc.indel_cost == 1 && start_in_query && !start_in_ref && !h.cmp_only && !h.need_find;
+    // a read code that no adapter row matches: 0 in AND mode, an unused letter code in ASCII mode
+    a.nomatch = 0; a.band_ok = a.fused_ok;
+    if (!a.and_mode) {
+        int free_code = -1;
+        for (int c = 15; c >= 0 && free_code < 0; c--) {
+            bool used = false;
+            for (int i = 0; i < h.m && i < ATR_K1A_MAXM; i++) used = used || a.code[i] == c;
+            if (!used) free_code = c;
+        }
+        if (free_code < 0) a.band_ok = 0; else a.nomatch = free_code;
+    }
     for (int c = 0; c < 16; c++) {
         unsigned cq = (unsigned)c;
         if (a.and_mode && a.q_single_only) cq = (cq & (cq - 1)) ? 0u : cq;

@@ -38,10 +38,10 @@ struct DevBuf {
 // per-stream working set of the host entry points
 struct Slot {
     cudaStream_t stream = nullptr;
-    DevBuf ascii, offsets, win, counts, woff, codes, len, out, scan_tmp, gen_scratch;
+    DevBuf ascii, offsets, win, counts, woff, codes, len, out, scan_tmp, gen_scratch, lists;
     DevBuf ascii2, offsets2, counts2, woff2, codes2, len2;     // second mate (insert aligner)
     void release() {
-        DevBuf* all[] = {&ascii, &offsets, &win, &counts, &woff, &codes, &len, &out, &scan_tmp, &gen_scratch,
+        DevBuf* all[] = {&ascii, &offsets, &win, &counts, &woff, &codes, &len, &out, &scan_tmp, &gen_scratch, &lists,
                          &ascii2, &offsets2, &counts2, &woff2, &codes2, &len2};
         for (DevBuf* b : all) b->release();
     }
@@ -132,7 +132,7 @@ int pack_on_stream(atr_ctx* ctx, cudaStream_t st, DevBuf& counts, DevBuf& scan_t
 }
 
 // ---- K1 launch logic -------------------------------------------------------------------------
-int locate_on_stream(atr_ctx* ctx, cudaStream_t st, DevBuf& gen_scratch, const atr_adapterset* set,
+int locate_on_stream(atr_ctx* ctx, cudaStream_t st, DevBuf& gen_scratch, DevBuf& lists, const atr_adapterset* set,
                      const uint32_t* d_codes, const uint32_t* d_woff, const uint16_t* d_len, const uint16_t* d_win,
                      const uint8_t* d_ascii, const int64_t* d_offsets, int64_t base, int fold_case, int64_t n,
                      atr_match* d_out) {
@@ -156,15 +156,29 @@ int locate_on_stream(atr_ctx* ctx, cudaStream_t st, DevBuf& gen_scratch, const a
             AdapterK1a p = set->k1a[a];
             p.reduce = a > 0;
             p.mark_routed = !have_ascii;
-            if (p.fused_ok && !ctx->disable_fused) {
+            if (p.fused_ok && !ctx->disable_fused && n < (int64_t)0x7fffffff) {
+                // filter -> survivor lists -> banded / windowed DP over the survivors only
+                int rc = lists.ensure((size_t)n * 2 * sizeof(Survivor) + 64);
+                if (rc) return fail(ctx, rc, "out of device memory (survivor lists)");
+                int* counters = lists.as<int>();
+                Survivor* narrow = (Survivor*)(lists.as<char>() + 64);
+                Survivor* wide = narrow + n;
+                CU(cudaMemsetAsync(counters, 0, 2 * sizeof(int), st));
                 const unsigned g = grid_for(n, ATR_K1F_THREADS);
                 if (h.m <= 32) {
-                    if (h.and_mode) k_locate_fused<uint32_t, true><<<g, ATR_K1F_THREADS, 0, st>>>(p, d_codes, d_woff, d_len, d_win, n, d_out);
-                    else k_locate_fused<uint32_t, false><<<g, ATR_K1F_THREADS, 0, st>>>(p, d_codes, d_woff, d_len, d_win, n, d_out);
+                    if (h.and_mode) k_filter<unsigned int, true><<<g, ATR_K1F_THREADS, 0, st>>>(p, d_codes, d_woff, d_len, d_win, n, d_out, narrow, wide, counters);
+                    else k_filter<unsigned int, false><<<g, ATR_K1F_THREADS, 0, st>>>(p, d_codes, d_woff, d_len, d_win, n, d_out, narrow, wide, counters);
                 } else {
-                    if (h.and_mode) k_locate_fused<unsigned long long, true><<<g, ATR_K1F_THREADS, 0, st>>>(p, d_codes, d_woff, d_len, d_win, n, d_out);
-                    else k_locate_fused<unsigned long long, false><<<g, ATR_K1F_THREADS, 0, st>>>(p, d_codes, d_woff, d_len, d_win, n, d_out);
+                    if (h.and_mode) k_filter<unsigned long long, true><<<g, ATR_K1F_THREADS, 0, st>>>(p, d_codes, d_woff, d_len, d_win, n, d_out, narrow, wide, counters);
+                    else k_filter<unsigned long long, false><<<g, ATR_K1F_THREADS, 0, st>>>(p, d_codes, d_woff, d_len, d_win, n, d_out, narrow, wide, counters);
                 }
+                LAUNCHED(ctx);
+                const unsigned gp = (unsigned)std::min<int64_t>((n + 127) / 128, 148 * 12);
+                if (h.and_mode) k_band<true><<<gp, 128, 0, st>>>(p, d_codes, d_woff, d_len, d_win, d_out, narrow, counters + 0);
+                else k_band<false><<<gp, 128, 0, st>>>(p, d_codes, d_woff, d_len, d_win, d_out, narrow, counters + 0);
+                LAUNCHED(ctx);
+                if (h.and_mode) k_wide<true><<<gp, 128, 0, st>>>(p, d_codes, d_woff, d_len, d_win, d_out, wide, counters + 1);
+                else k_wide<false><<<gp, 128, 0, st>>>(p, d_codes, d_woff, d_len, d_win, d_out, wide, counters + 1);
             }
             else if (h.and_mode) k_locate_k1a<true><<<grid_for(n, 128), 128, 0, st>>>(p, d_codes, d_woff, d_len, d_win, n, d_out);
             else k_locate_k1a<false><<<grid_for(n, 128), 128, 0, st>>>(p, d_codes, d_woff, d_len, d_win, n, d_out);
@@ -352,7 +366,7 @@ int atr_locate_batch_device(atr_ctx* ctx, const atr_adapterset* set, const uint3
     CU(cudaSetDevice(ctx->device));
     Slot& s = ctx->slot[0];
     CU(cudaEventRecord(ctx->ev0, s.stream));
-    int rc = locate_on_stream(ctx, s.stream, s.gen_scratch, set, d_codes, d_woff, d_len, d_win, d_ascii, d_offsets, 0,
+    int rc = locate_on_stream(ctx, s.stream, s.gen_scratch, s.lists, set, d_codes, d_woff, d_len, d_win, d_ascii, d_offsets, 0,
                               fold_case, n, d_out);
     if (rc) return rc;
     CU(cudaEventRecord(ctx->ev1, s.stream));
@@ -392,7 +406,7 @@ int atr_locate_batch_host(atr_ctx* ctx, const atr_adapterset* set, const uint8_t
         rc = pack_on_stream(ctx, s.stream, s.counts, s.scan_tmp, s.ascii.as<uint8_t>(), s.offsets.as<int64_t>(), offsets[c0], cn,
                             fold_case, s.codes.as<uint32_t>(), s.woff.as<uint32_t>(), s.len.as<uint16_t>());
         if (rc) return rc;
-        rc = locate_on_stream(ctx, s.stream, s.gen_scratch, set, s.codes.as<uint32_t>(), s.woff.as<uint32_t>(),
+        rc = locate_on_stream(ctx, s.stream, s.gen_scratch, s.lists, set, s.codes.as<uint32_t>(), s.woff.as<uint32_t>(),
                               s.len.as<uint16_t>(), win ? s.win.as<uint16_t>() : nullptr, s.ascii.as<uint8_t>(),
                               s.offsets.as<int64_t>(), offsets[c0], fold_case, cn, s.out.as<atr_match>());
         if (rc) return rc;

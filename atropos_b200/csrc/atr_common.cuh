@@ -49,7 +49,8 @@ struct AdapterK1a {                   // passed by value as a __grid_constant__ 
     unsigned short thr_mul[ATR_K1A_MAXM + 1];   // floor(length * rate) in double   (_align.pyx:447, :468)
     unsigned short thr_div[ATR_K1A_MAXM + 1];   // max e with e / size <= rate       (adapters/__init__.py:389-392)
     const unsigned char* rmp_ok;      // [(m+1)*(m+1)] or nullptr
-    int fused_ok;                     // eligible for the bit-vector filter + windowed DP kernel (K1f)
+    int fused_ok;                     // eligible for the bit-vector filter + banded/windowed DP kernels (K1f)
+    int band_ok, nomatch;             // K1d usable; a 4-bit code that matches no adapter row (virtual columns)
     unsigned long long peq[16];       // K1f: bit i-1 of peq[c] set iff adapter row i matches read code c
 };
 

@@ -198,19 +198,24 @@ __global__ void __launch_bounds__(256) k_compare_prefixes(const unsigned char* _
 }
 
 // ---------------------------------------------------------------------------------------------
-// K1f: fused bit-vector filter + windowed DP (the fast path for BACK/SUFFIX-style adapters with
-// unit indel cost, <= 64 nt). One CTA = one tile of 256 reads:
-//   stage   the tile's packed reads are one contiguous span of `codes`: a single TMA bulk copy
-//           (cp.async.bulk, completion on an mbarrier) brings it into shared memory;
-//   phase 1 every thread runs the Myers/Hyyro filter on its read (exact costs, ~1/10 of the DP's
-//           instructions); reads with no acceptable cell are finished (no match);
-//   compact the survivors (about the adapter-containing fraction) are appended to a list in shared
-//           memory, so that phase 2 runs with fully populated warps;
-//   phase 2 thread s takes survivor s and evaluates the tie-broken 3-field DP only on the column
-//           window that can hold an accepted alignment (k1a_locate with c0/c1).
+// K1f: bit-vector filter + banded DP -- the fast path for BACK/SUFFIX-style adapters with unit indel
+// cost and <= 64 nt (AdapterK1a.fused_ok). Three kernels on one stream:
+//   k_filter  one CTA = one tile of 256 reads. The tile's packed reads are one contiguous span of
+//             `codes`: a single TMA bulk copy (cp.async.bulk, completion on an mbarrier) stages it in
+//             shared memory; every thread runs the Myers/Hyyro filter on its read (exact costs, a small
+//             fraction of the DP's instructions, ~40 registers -> high occupancy). Reads with no
+//             acceptable cell are finished here (no match); survivors (about the adapter-containing
+//             fraction) are appended to one of two lists in global memory;
+//   k_band    dense over the "narrow" survivors: tie-broken 3-field DP on <= 16 diagonals (k1d_band);
+//   k_wide    dense over the rest: the register-column DP restricted to a column window (k1a_locate).
 // ---------------------------------------------------------------------------------------------
 #define ATR_K1F_THREADS 256
-#define ATR_K1F_TILE_WORDS 8192      // 32 KB: 256 reads of up to 256 nt
+#define ATR_K1F_TILE_WORDS 6144      // 24 KB: 256 reads of up to 192 nt
+
+struct Survivor {                    // 8 bytes
+    uint32_t read;
+    short a, b;                      // narrow: a = dlo ; wide: a = c0, b = c1
+};
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -228,14 +233,39 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// warp-aggregated append: one atomicAdd per warp per list
+__device__ __forceinline__ void list_append(bool want, Survivor sv, Survivor* __restrict__ list, int* __restrict__ counter) {
+    const unsigned mask = __ballot_sync(0xffffffffu, want);
+    if (mask == 0) return;
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(mask) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(counter, __popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (want) list[base + __popc(mask & ((1u << lane) - 1u))] = sv;
+}
+
+__device__ __forceinline__ void read_extent(const uint16_t* __restrict__ len, const uint16_t* __restrict__ win, int64_t r,
+                                            int& lo, int& n, bool& esc) {
+    const unsigned l = len[r];
+    esc = (l & ATR_ESC_BIT) != 0;
+    int hi = (int)(l & ATR_LEN_MASK);
+    lo = 0;
+    if (win != nullptr) {
+        const int wlo = win[2 * r], whi = win[2 * r + 1];
+        hi = atr_min(hi, whi);
+        lo = atr_min(wlo, hi);
+    }
+    n = hi - lo;
+}
+
 template <class WORD, bool AND_MODE>
-__global__ void __launch_bounds__(ATR_K1F_THREADS, 2) k_locate_fused(const __grid_constant__ AdapterK1a ad,
+__global__ void __launch_bounds__(ATR_K1F_THREADS) k_filter(const __grid_constant__ AdapterK1a ad,
         const uint32_t* __restrict__ codes, const uint32_t* __restrict__ woff, const uint16_t* __restrict__ len,
-        const uint16_t* __restrict__ win, int64_t n_reads, atr_match* __restrict__ out) {
+        const uint16_t* __restrict__ win, int64_t n_reads, atr_match* __restrict__ out,
+        Survivor* __restrict__ narrow, Survivor* __restrict__ wide, int* __restrict__ counters) {
     __shared__ __align__(128) uint32_t s_tile[ATR_K1F_TILE_WORDS];
     __shared__ __align__(8) uint64_t s_bar;
-    __shared__ int s_count;
-    __shared__ int4 s_surv[ATR_K1F_THREADS];          // {thread, c0, c1, unused}
     __shared__ WORD s_peq[16];
 
     const int tid = threadIdx.x;
@@ -247,38 +277,31 @@ __global__ void __launch_bounds__(ATR_K1F_THREADS, 2) k_locate_fused(const __gri
     // TMA needs 16-byte aligned addresses and sizes; the last tile may not read past the end of `codes`
     const bool last_tile = (t0 + cnt == n_reads);
     const bool fits = span <= ATR_K1F_TILE_WORDS;
-    const bool use_tma = fits && !last_tile && ((reinterpret_cast<uintptr_t>(codes) & 15) == 0);
-    if (tid < 16) s_peq[tid] = (WORD)ad.peq[tid];
-    if (tid == 0) {
-        s_count = 0;
-        if (use_tma) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar)) : "memory");
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        }
+    const bool use_tma = fits && !last_tile && span > 0 && ((reinterpret_cast<uintptr_t>(codes) & 15) == 0);
+    if (tid < 16) {
+        const int WB = (int)(8 * sizeof(WORD)), sh = WB - ad.m;     // left-aligned pattern, virtual rows all ones
+        s_peq[tid] = (WORD)(((WORD)ad.peq[tid] << sh) | (sh ? (((WORD)1 << sh) - 1) : 0));
+    }
+    if (tid == 0 && use_tma) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar)) : "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncthreads();
     if (use_tma) {
-        if (tid == 0 && span > 0) tma_load_1d(s_tile, codes + a_begin, span * 4u, &s_bar);
+        if (tid == 0) tma_load_1d(s_tile, codes + a_begin, span * 4u, &s_bar);
     } else if (fits) {                                              // edge tile: coalesced cooperative copy
         for (uint32_t w = tid; w < w_end - a_begin; w += ATR_K1F_THREADS) s_tile[w] = codes[a_begin + w];
     }
     // per-read bookkeeping while the copy is in flight
     const int64_t r = t0 + tid;
-    bool mine = tid < cnt, routed = false;
+    const bool mine = tid < cnt;
+    bool routed = false, esc = false;
     int lo = 0, n = 0;
-    uint32_t wr = 0;
+    uint32_t wr = a_begin;
     if (mine) {
-        const unsigned l = len[r];
-        const bool esc = (l & ATR_ESC_BIT) != 0;
-        int hi = (int)(l & ATR_LEN_MASK);
-        if (win != nullptr) {
-            const int wlo = win[2 * r], whi = win[2 * r + 1];
-            hi = atr_min(hi, whi);
-            lo = atr_min(wlo, hi);
-        }
-        n = hi - lo;
+        read_extent(len, win, r, lo, n, esc);
         wr = woff[r];
-        routed = (esc && !AND_MODE) || n > ATR_K1A_MAXN;            // byte-exact general kernel picks these up
+        routed = (esc && !AND_MODE) || n > ATR_K1A_MAXN;            // the byte-exact general kernel picks these up
         if (routed && ad.mark_routed) {
             atr_match m;
             m.astart = m.astop = m.rstart = m.rstop = m.matches = m.errors = 0;
@@ -286,38 +309,57 @@ __global__ void __launch_bounds__(ATR_K1F_THREADS, 2) k_locate_fused(const __gri
             out[r] = m;
         }
     }
-    if (use_tma) { if (span > 0) mbar_wait(&s_bar, 0); }
+    if (use_tma) mbar_wait(&s_bar, 0);
     else __syncthreads();
     const uint32_t* rd = fits ? (s_tile + (wr - a_begin)) : (codes + wr);
-    // ---- phase 1 ----
+    bool to_narrow = false, to_wide = false;
+    Survivor sv;
+    sv.read = (uint32_t)r; sv.a = 0; sv.b = 0;
     if (mine && !routed) {
-        int c0, c1;
-        if (myers_filter<WORD>(ad, s_peq, rd, lo, n, c0, c1)) {
-            const int slot = atomicAdd(&s_count, 1);
-            s_surv[slot] = make_int4(tid, c0, c1, 0);
+        FilterHit hit;
+        if (myers_filter<WORD>(ad, s_peq, rd, lo, n, hit)) {
+            if (ad.band_ok && hit.width <= ATR_K1D_W) { to_narrow = true; sv.a = (short)hit.dlo; }
+            else { to_wide = true; sv.a = (short)hit.c0; sv.b = (short)hit.c1; }
         } else {
             Best b;
             b.ref_stop = ad.m; b.q_stop = n; b.cost = ad.m + n; b.origin = 0; b.matches = 0;
-            finalize(ad, b, n, out + r);                          // "no match" (respects the panel reduction)
+            finalize(ad, b, n, out + r);                            // "no match" (respects the panel reduction)
         }
     }
-    __syncthreads();
-    // ---- phase 2: dense over the survivors ----
-    if (tid < s_count) {
-        const int4 sv = s_surv[tid];
-        const int64_t r2 = t0 + sv.x;
-        const unsigned l = len[r2];
-        int hi = (int)(l & ATR_LEN_MASK), lo2 = 0;
-        if (win != nullptr) {
-            const int wlo = win[2 * r2], whi = win[2 * r2 + 1];
-            hi = atr_min(hi, whi);
-            lo2 = atr_min(wlo, hi);
-        }
-        const int n2 = hi - lo2;
-        const uint32_t wr2 = woff[r2];
-        const uint32_t* rd2 = fits ? (s_tile + (wr2 - a_begin)) : (codes + wr2);
+    list_append(to_narrow, sv, narrow, counters + 0);
+    list_append(to_wide, sv, wide, counters + 1);
+}
+
+template <bool AND_MODE>
+__global__ void __launch_bounds__(128) k_band(const __grid_constant__ AdapterK1a ad,
+        const uint32_t* __restrict__ codes, const uint32_t* __restrict__ woff, const uint16_t* __restrict__ len,
+        const uint16_t* __restrict__ win, atr_match* __restrict__ out,
+        const Survivor* __restrict__ list, const int* __restrict__ counter) {
+    const int count = *counter;
+    const int stride = gridDim.x * blockDim.x;
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < count; s += stride) {
+        const Survivor sv = list[s];
+        int lo, n; bool esc;
+        read_extent(len, win, sv.read, lo, n, esc);
         Best b;
-        k1a_locate<AND_MODE>(ad, rd2, lo2, n2, b, sv.y, sv.z);
-        finalize(ad, b, n2, out + r2);
+        k1d_band<AND_MODE, ATR_K1D_W>(ad, codes + woff[sv.read], lo, n, (int)sv.a, b);
+        finalize(ad, b, n, out + sv.read);
+    }
+}
+
+template <bool AND_MODE>
+__global__ void __launch_bounds__(128) k_wide(const __grid_constant__ AdapterK1a ad,
+        const uint32_t* __restrict__ codes, const uint32_t* __restrict__ woff, const uint16_t* __restrict__ len,
+        const uint16_t* __restrict__ win, atr_match* __restrict__ out,
+        const Survivor* __restrict__ list, const int* __restrict__ counter) {
+    const int count = *counter;
+    const int stride = gridDim.x * blockDim.x;
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < count; s += stride) {
+        const Survivor sv = list[s];
+        int lo, n; bool esc;
+        read_extent(len, win, sv.read, lo, n, esc);
+        Best b;
+        k1a_locate<AND_MODE>(ad, codes + woff[sv.read], lo, n, b, (int)sv.a, (int)sv.b);
+        finalize(ad, b, n, out + sv.read);
     }
 }

@@ -14,6 +14,11 @@
 #pragma once
 #include "atr_common.cuh"
 
+template <class T> struct SignedOf;
+template <> struct SignedOf<unsigned int> { typedef int type; };
+template <> struct SignedOf<unsigned long> { typedef long type; };
+template <> struct SignedOf<unsigned long long> { typedef long long type; };
+
 struct Best {
     int matches, cost, origin, ref_stop, q_stop;
 };
@@ -229,61 +234,195 @@ ATR_HD void k1a_locate(const AdapterK1a& ad, const uint32_t* __restrict__ codes,
 }
 
 // ---- K1f phase 1: Myers/Hyyro bit-vector filter ------------------------------------------------------
-// Exact unit-cost DP costs (not the tie-broken path): bit i-1 of Pv/Mv = vertical delta +1/-1 between rows
-// i-1 and i of the current column. Finds every cell the reference could accept:
-//   J = { j : D[m][j] <= k }                      (row m inside the loop, needs stop_in_query)
-//   I = { i : D[i][n] <= floor(i * rate), i >= min_overlap }   (last column; all rows if stop_in_ref, else row m)
-// and returns the DP window [c0, c1] that contains every alignment ending in one of them, or false if
-// there is none (the read has no match). Requires start_in_query && !start_in_ref && indel cost 1.
+// Exact unit-cost DP costs (not the tie-broken path). The adapter sits LEFT-ALIGNED in the word: row i is
+// bit (WB - m + i - 1), so the bottom row m is always the sign bit; the bits below row 1 are "virtual rows"
+// whose Peq bits are all ones and whose vertical deltas stay 0, i.e. they behave exactly like the free row 0.
+// Bit r of Pv/Mv = vertical delta +1/-1 between the rows below/at that bit. The filter finds every cell
+// the reference could accept,
+//   J = { j : D[m][j] <= k }                                   (row m inside the loop; needs stop_in_query)
+//   I = { i : D[i][n] <= floor(i*rate), i >= min_overlap }     (last column; all rows if stop_in_ref, else row m)
+// and reports the range of DP diagonals (column - row) that alignments ending in them can touch:
+// [dlo, dlo + width). false = no acceptable cell = the read has no match.
+// Requires start_in_query && !start_in_ref && indel cost 1 (AdapterK1a.fused_ok).
+struct FilterHit {
+    int dlo, width;      // diagonal band for the banded kernel (K1d)
+    int c0, c1;          // column window for the windowed register kernel (fallback when the band is too wide)
+};
+
+template <class WORD>
+struct MyersState {
+    WORD Pv, Mv;
+    int score;
+};
+
+template <class WORD>
+ATR_HD void myers_col(MyersState<WORD>& st, WORD Eq) {
+    const WORD Pv = st.Pv, Mv = st.Mv;
+    const WORD Xv = Eq | Mv;
+    const WORD Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
+    WORD Ph = Mv | ~(Xh | Pv);
+    WORD Mh = Pv & Xh;
+    typedef typename SignedOf<WORD>::type SWORD;
+    if ((SWORD)Ph < 0) st.score++;                     // bottom row = sign bit
+    if ((SWORD)Mh < 0) st.score--;
+    Ph <<= 1;                                          // row 0 (and the virtual rows) contribute horizontal delta 0
+    Mh <<= 1;
+    st.Pv = Mh | ~(Xv | Ph);
+    st.Mv = Ph & Xv;
+}
+
 template <class WORD>
 ATR_HD bool myers_filter(const AdapterK1a& ad, const WORD* __restrict__ peq, const uint32_t* __restrict__ codes, int lo, int n,
-                         int& c0, int& c1) {
+                         FilterHit& hit) {
     const int m = ad.m, k = ad.k;
+    const int WB = (int)(8 * sizeof(WORD));
+    const int sh = WB - m;                             // first real row sits at bit sh
     const bool stop_in_ref = ad.flags & ATR_STOP_WITHIN_SEQ1, stop_in_query = ad.flags & ATR_STOP_WITHIN_SEQ2;
     const int min_n = stop_in_query ? 0 : atr_max(0, n - m - k);
-    const WORD ONE = (WORD)1;
-    const WORD top = ONE << (m - 1);
-    WORD Pv = (m >= (int)(8 * sizeof(WORD))) ? ~(WORD)0 : ((ONE << m) - 1);
-    WORD Mv = 0;
-    int score = m;                                     // D[m][min_n] = m (column min_n: cost i, _align.pyx:345-348)
+    MyersState<WORD> st;
+    st.Pv = (sh == 0) ? ~(WORD)0 : (WORD)(~(WORD)0 << sh);   // column min_n: cost(i) = i (_align.pyx:345-348)
+    st.Mv = 0;
+    st.score = m;
     int jmin = 0x7fffffff, jmax = -1;
-    uint32_t w = 0;
-    if (min_n < n) w = codes[(lo + min_n) >> 3];
-#pragma unroll 1
-    for (int j = min_n + 1; j <= n; j++) {
-        const int pos = lo + j - 1;
-        if ((pos & 7) == 0) w = codes[pos >> 3];
-        const unsigned qc = (w >> ((pos & 7) * 4)) & 15u;
-        const WORD Eq = peq[qc];                        // 16-entry table (shared memory on the GPU: conflict-free)
-        const WORD Xv = Eq | Mv;
-        const WORD Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
-        WORD Ph = Mv | ~(Xh | Pv);
-        WORD Mh = Pv & Xh;
-        score += (Ph & top) ? 1 : 0;
-        score -= (Mh & top) ? 1 : 0;
-        Ph <<= 1;                                      // row 0 is free in the read: horizontal delta 0 shifts in
-        Mh <<= 1;
-        Pv = Mh | ~(Xv | Ph);
-        Mv = Ph & Xv;
-        if (stop_in_query && score <= k) { jmin = atr_min(jmin, j); jmax = j; }
+    int j = min_n;                                     // columns done so far
+    int pos = lo + min_n;                              // packed position of the next column's base
+    const int pend = lo + n;
+    // head: up to the next word boundary
+    while (pos < pend && (pos & 7) != 0) {
+        const unsigned qc = (codes[pos >> 3] >> ((pos & 7) * 4)) & 15u;
+        myers_col(st, peq[qc]);
+        j++; pos++;
+        if (stop_in_query && st.score <= k) { jmin = atr_min(jmin, j); jmax = j; }
     }
-    // last column: D[i][n] = sum of vertical deltas of rows 1..i
-    int imax = 0;
+    // body: whole words, 8 columns each, fully unrolled
+    while (pos + 8 <= pend) {
+        const uint32_t w = codes[pos >> 3];
+#pragma unroll
+        for (int t = 0; t < 8; t++) {
+            myers_col(st, peq[(w >> (4 * t)) & 15u]);
+            if (stop_in_query && st.score <= k) { jmin = atr_min(jmin, j + t + 1); jmax = j + t + 1; }
+        }
+        j += 8; pos += 8;
+    }
+    // tail
+    if (pos < pend) {
+        const uint32_t w = codes[pos >> 3];
+        for (int t = 0; pos < pend; t++) {
+            myers_col(st, peq[(w >> (4 * t)) & 15u]);
+            j++; pos++;
+            if (stop_in_query && st.score <= k) { jmin = atr_min(jmin, j); jmax = j; }
+        }
+    }
+    // last column: D[i][n] = sum of the vertical deltas of rows 1..i
+    int imin = 0, imax = 0;
     {
         int d = 0;
         const int first = stop_in_ref ? 1 : m;
         for (int i = 1; i <= m; i++) {
-            d += (int)((Pv >> (i - 1)) & ONE) - (int)((Mv >> (i - 1)) & ONE);
-            if (i >= first && i >= ad.min_overlap && d <= (int)ad.thr_mul[i]) imax = i;
+            d += (int)((st.Pv >> (sh + i - 1)) & (WORD)1) - (int)((st.Mv >> (sh + i - 1)) & (WORD)1);
+            if (i >= first && i >= ad.min_overlap && d <= (int)ad.thr_mul[i]) { if (imin == 0) imin = i; imax = i; }
         }
     }
     if (jmax < 0 && imax == 0) return false;
-    int start = 0x7fffffff;
-    if (jmax >= 0) start = jmin - m - k;
-    if (imax > 0) start = atr_min(start, n - imax - k);
-    c0 = atr_max(min_n, start);
-    c1 = imax > 0 ? n : jmax;
+    // end diagonals of the candidate cells: (m, j) -> j - m ; (i, n) -> n - i. An alignment of cost <= k
+    // that ends on diagonal e stays within [e - k, e + k].
+    int elo = 0x7fffffff, ehi = -0x7fffffff;
+    if (jmax >= 0) { elo = jmin - m; ehi = jmax - m; }
+    if (imax > 0) { elo = atr_min(elo, n - imax); ehi = atr_max(ehi, n - imin); }
+    hit.dlo = elo - k;
+    hit.width = (ehi - elo) + 2 * k + 1;
+    hit.c0 = atr_max(min_n, elo - k);                 // first column any such alignment can touch in row 0
+    hit.c1 = imax > 0 ? n : jmax;
     return true;
+}
+
+// ---- K1f phase 2 (narrow bands): K1d, banded DP along diagonals ------------------------------------------
+// B[d] = cell (i, i + dlo + d) of the current row i, d = 0..W-1, as K1a packed keys. Rows run 1..m in a
+// rolled loop (the adapter base of a row is warp-uniform), the W diagonals are unrolled in registers:
+// diag = B[d] (old), up = B[d+1] (old), left = B[d-1] (new); cells outside the band count as dead.
+// Columns left of the first DP column (j <= min_n, including j <= 0) are "virtual": free row 0 and a base
+// that matches nothing. With unit indel cost their cells reproduce the reference's first column exactly
+// (cost i, 0 matches); their origins may come out below 0 / below the true max(0, min_n - i) only where the
+// true origin is 0, hence the clamp at the end (these flag sets never have negative origins).
+template <bool AND_MODE, int W>
+ATR_HD void k1d_band(const AdapterK1a& ad, const uint32_t* __restrict__ codes, int lo, int n, int dlo, Best& best) {
+    const int m = ad.m, k = ad.k;
+    const bool stop_in_ref = ad.flags & ATR_STOP_WITHIN_SEQ1, stop_in_query = ad.flags & ATR_STOP_WITHIN_SEQ2;
+    const int min_n = stop_in_query ? 0 : atr_max(0, n - m - k);
+    const unsigned CLAMP = (unsigned)(k + 1) << ATR_COST_SHIFT;
+    const unsigned C_SUB = 1u << ATR_COST_SHIFT;
+    const unsigned C_INS = (1u << ATR_COST_SHIFT) | (1u << ATR_PRIO_SHIFT);
+    const unsigned C_DEL = (1u << ATR_COST_SHIFT) | (2u << ATR_PRIO_SHIFT);
+    const unsigned nomatch = (unsigned)ad.nomatch;
+
+    // the key's origin field is biased by ATR_ORG_BIAS (64) and dlo >= -(m + k) - k > -ORG range is not
+    // guaranteed for virtual columns far left of 0: clamp the stored row-0 origin at -ATR_ORG_BIAS (any
+    // negative origin means 0 after the final clamp)
+    unsigned B[W];
+#pragma unroll
+    for (int d = 0; d < W; d++) {                      // row 0: cost 0, origin j (:385-386), every column "exists"
+        const int j = dlo + d;
+        B[d] = j > n ? CLAMP : k1a_key(0, atr_max(j, -ATR_ORG_BIAS), 0);
+    }
+    // sliding window of the W read codes of the current row: nibble d = base of column i + dlo + d
+    unsigned long long win = 0;
+    auto base_at = [&](int p) -> unsigned {            // p = 0-based position in the (windowed) read
+        if (p < min_n || p >= n) return nomatch;
+        const int q = lo + p;
+        unsigned c = (codes[q >> 3] >> ((q & 7) * 4)) & 15u;
+        if (AND_MODE && ad.q_single_only) c = (c & (c - 1)) ? 0u : c;
+        return c;
+    };
+#pragma unroll 1
+    for (int d = 0; d < W - 1; d++)                    // row 1 needs columns 1+dlo .. W+dlo -> positions dlo .. dlo+W-1
+        win |= (unsigned long long)base_at(dlo + d) << (4 * (d + 1));
+    Best bl;                                           // last-column candidates, merged after the row-m ones
+    bl.ref_stop = m; bl.q_stop = n; bl.cost = m + n; bl.origin = 0; bl.matches = 0;
+    best = bl;
+    const int first_i = stop_in_ref ? 1 : m;
+#pragma unroll 1
+    for (int i = 1; i <= m; i++) {
+        win = (win >> 4) | ((unsigned long long)base_at(i + dlo + W - 2) << (4 * (W - 1)));
+        const unsigned a = (unsigned)ad.code[i - 1];
+        // per-nibble (mis)match flags for the whole row at once
+        unsigned long long x;
+        if (AND_MODE) x = win & (0x1111111111111111ull * a);
+        else x = win ^ (0x1111111111111111ull * a);
+        x |= x >> 1; x |= x >> 2;                      // bit 4d set <=> nibble d non-zero
+        const unsigned xl = (unsigned)x, xh = (unsigned)(x >> 32);
+        unsigned left = CLAMP;                         // cell (i, i + dlo - 1): outside the band
+#pragma unroll
+        for (int d = 0; d < W; d++) {
+            const unsigned diag = B[d];
+            const unsigned up = (d + 1 < W) ? B[d + 1] : CLAMP;
+            const unsigned nz = ((d < 8 ? xl : xh) >> (4 * (d & 7))) & 1u;
+            const bool eq = AND_MODE ? (nz != 0u) : (nz == 0u);
+            unsigned t = atr_umin(atr_umin(left + C_DEL, up + C_INS), diag + C_SUB) & ATR_PRIO_CLEAR;
+            unsigned nw = eq ? diag + 1u : t;
+            nw = atr_umin(nw, CLAMP);
+            B[d] = nw;
+            left = nw;
+        }
+        // last column (:461-474): cell (i, n) lives on diagonal n - i
+        const int dsel = n - i - dlo;
+        if (i >= first_i && dsel >= 0 && dsel < W) {
+            unsigned c = CLAMP;
+#pragma unroll
+            for (int d = 0; d < W; d++) if (d == dsel) c = B[d];
+            if (c < CLAMP) consider(ad, bl, k1a_cost(c), atr_max(k1a_origin(c), 0), k1a_matches(c), i, n);
+        }
+    }
+    if (stop_in_query) {                               // row m, columns in ascending order (:440-458)
+#pragma unroll
+        for (int d = 0; d < W; d++) {
+            const int j = m + dlo + d;
+            const unsigned c = B[d];
+            if (j > min_n && j <= n && c < CLAMP)
+                consider(ad, best, k1a_cost(c), atr_max(k1a_origin(c), 0), k1a_matches(c), m, j);
+        }
+    }
+    // the reference scans the last column after all in-loop candidates; replacement needs a strictly better key
+    if (bl.cost != m + n && (bl.matches > best.matches || (bl.matches == best.matches && bl.cost < best.cost))) best = bl;
 }
 
 // compare_prefixes / compare_suffixes on packed codes (anchored adapters with indels off)
@@ -459,14 +598,20 @@ ATR_HD void gen_read(const AdapterGen& ad, const AtrTables& tb, const unsigned c
     }
 }
 
-// ---- K1f per read (what the fused kernel does, minus the block-level compaction between the phases) ----
+// ---- K1f per read (what the kernels do, minus the compaction between the phases) ----
+#define ATR_K1D_W 16
 template <class WORD, bool AND_MODE>
-ATR_HD void k1f_read(const AdapterK1a& ad, const uint32_t* __restrict__ codes, int lo, int n, atr_match* out) {
+ATR_HD void k1f_read(const AdapterK1a& ad, const uint32_t* __restrict__ codes, int lo, int n, atr_match* out, int* path = nullptr) {
     Best b;
     b.ref_stop = ad.m; b.q_stop = n; b.cost = ad.m + n; b.origin = 0; b.matches = 0;
-    int c0, c1;
+    FilterHit hit;
+    const int WB = (int)(8 * sizeof(WORD)), sh = WB - ad.m;
     WORD peq[16];
-    for (int c = 0; c < 16; c++) peq[c] = (WORD)ad.peq[c];
-    if (myers_filter<WORD>(ad, peq, codes, lo, n, c0, c1)) k1a_locate<AND_MODE>(ad, codes, lo, n, b, c0, c1);
+    for (int c = 0; c < 16; c++) peq[c] = (WORD)(((WORD)ad.peq[c] << sh) | (sh ? (((WORD)1 << sh) - 1) : 0));
+    if (path) *path = 0;
+    if (myers_filter<WORD>(ad, peq, codes, lo, n, hit)) {
+        if (ad.band_ok && hit.width <= ATR_K1D_W) { if (path) *path = 1; k1d_band<AND_MODE, ATR_K1D_W>(ad, codes, lo, n, hit.dlo, b); }
+        else { if (path) *path = 2; k1a_locate<AND_MODE>(ad, codes, lo, n, b, hit.c0, hit.c1); }
+    }
     finalize(ad, b, n, out);
 }

@@ -37,9 +37,11 @@ int sim_locate(const atr_adapter_desc* d, int adapter_index, int reduce, const u
         atr::fill_k1a(h, tb, adapter_index, reduce, rmp, a);
         if (route == 3 && !a.fused_ok) return -101;
         if (used_k1a && a.fused_ok && route != 2) *used_k1a = 2;
-        if (a.fused_ok && route != 2) {                // as the library does: the fused kernel whenever eligible
-            if (h.and_mode) { if (h.m <= 32) k1f_read<uint32_t, true>(a, codes.data(), lo, n, out); else k1f_read<uint64_t, true>(a, codes.data(), lo, n, out); }
-            else { if (h.m <= 32) k1f_read<uint32_t, false>(a, codes.data(), lo, n, out); else k1f_read<uint64_t, false>(a, codes.data(), lo, n, out); }
+        if (a.fused_ok && route != 2) {                // as the library does: the fused kernels whenever eligible
+            int path = 0;
+            if (h.and_mode) { if (h.m <= 32) k1f_read<unsigned int, true>(a, codes.data(), lo, n, out, &path); else k1f_read<unsigned long long, true>(a, codes.data(), lo, n, out, &path); }
+            else { if (h.m <= 32) k1f_read<unsigned int, false>(a, codes.data(), lo, n, out, &path); else k1f_read<unsigned long long, false>(a, codes.data(), lo, n, out, &path); }
+            if (used_k1a) *used_k1a = 2 + path;       // 2 filtered out, 3 banded K1d, 4 windowed K1a
         }
         else if (h.and_mode) k1a_read<true>(a, codes.data(), lo, n, out);
         else k1a_read<false>(a, codes.data(), lo, n, out);

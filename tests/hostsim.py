@@ -46,7 +46,7 @@ def locate(read, desc, route=0, lo=0, hi=None, fold_case=False, prev=None, adapt
                           int(fold_case), route, C.byref(out), C.byref(used))
     if rc != 0:
         raise RuntimeError("sim_locate rc=%d" % rc)
-    return decode(out), bool(used.value), out
+    return decode(out), used.value, out
 
 
 def decode(m):
