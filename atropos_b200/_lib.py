@@ -16,7 +16,8 @@ _lib = None
 # every symbol include/atropos_b200.h declares (tests check the .so exports all of them)
 SYMBOLS = [
     "atr_abi_version", "atr_device_count", "atr_ctx_create", "atr_ctx_destroy", "atr_last_error", "atr_ctx_sync",
-    "atr_ctx_stream", "atr_ctx_launch_count", "atr_ctx_last_kernel_ms", "atr_adapterset_create",
+    "atr_ctx_stream", "atr_ctx_launch_count", "atr_ctx_last_kernel_ms", "atr_ctx_set_profiling",
+    "atr_ctx_last_phase_ms", "atr_adapterset_create",
     "atr_adapterset_destroy", "atr_packed_words", "atr_pack_device", "atr_locate_batch_device",
     "atr_locate_batch_host", "atr_compare_prefixes", "atr_insertset_create", "atr_insertset_destroy",
     "atr_match_insert_batch_device", "atr_match_insert_batch_host", "atr_multi_locate",
@@ -52,6 +53,8 @@ def load():
     L.atr_ctx_launch_count.restype = i64
     L.atr_ctx_last_kernel_ms.argtypes = [vp]
     L.atr_ctx_last_kernel_ms.restype = C.c_float
+    L.atr_ctx_set_profiling.argtypes = [vp, C.c_int]
+    L.atr_ctx_last_phase_ms.argtypes = [vp, C.POINTER(C.c_float), C.c_int]
     L.atr_adapterset_create.argtypes = [vp, i32, C.POINTER(_abi.AtrAdapterDesc), C.POINTER(vp)]
     L.atr_adapterset_destroy.argtypes = [vp]
     L.atr_adapterset_destroy.restype = None
@@ -64,7 +67,7 @@ def load():
     L.atr_insertset_create.argtypes = [vp, C.POINTER(_abi.AtrInsertDesc), C.POINTER(vp)]
     L.atr_insertset_destroy.argtypes = [vp]
     L.atr_insertset_destroy.restype = None
-    L.atr_match_insert_batch_device.argtypes = [vp] * 14 + [i64, vp]
+    L.atr_match_insert_batch_device.argtypes = [vp] * 12 + [i64, vp]
     L.atr_match_insert_batch_host.argtypes = [vp, vp, vp, vp, vp, vp, i64, vp]
     L.atr_multi_locate.argtypes = [vp, C.c_char_p, i32, C.c_char_p, i32, f64, i32, i32, i32, C.POINTER(i32),
                                    C.POINTER(i32)]

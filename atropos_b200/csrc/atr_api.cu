@@ -58,6 +58,8 @@ struct atr_ctx {
     std::string err;
     int64_t launches = 0;
     float last_ms = -1.f;
+    int profile = 0, phases_valid = 0;
+    cudaEvent_t pev[4] = {nullptr, nullptr, nullptr, nullptr};
     int disable_fused = 0;           // ATR_DISABLE_FUSED=1: always use the plain register-DP kernel (A/B measurements)
     DevBuf misc;                     // small single-call scratch (compare_prefixes, multi_locate)
 };
@@ -164,6 +166,8 @@ int locate_on_stream(atr_ctx* ctx, cudaStream_t st, DevBuf& gen_scratch, DevBuf&
                 Survivor* narrow = (Survivor*)(lists.as<char>() + 64);
                 Survivor* wide = narrow + n;
                 CU(cudaMemsetAsync(counters, 0, 2 * sizeof(int), st));
+                const bool prof = ctx->profile && set->host.size() == 1;
+                if (prof) CU(cudaEventRecord(ctx->pev[0], st));
                 const unsigned g = grid_for(n, ATR_K1F_THREADS);
                 if (h.m <= 32) {
                     if (h.and_mode) k_filter<unsigned int, true><<<g, ATR_K1F_THREADS, 0, st>>>(p, d_codes, d_woff, d_len, d_win, n, d_out, narrow, wide, counters);
@@ -173,12 +177,15 @@ int locate_on_stream(atr_ctx* ctx, cudaStream_t st, DevBuf& gen_scratch, DevBuf&
                     else k_filter<unsigned long long, false><<<g, ATR_K1F_THREADS, 0, st>>>(p, d_codes, d_woff, d_len, d_win, n, d_out, narrow, wide, counters);
                 }
                 LAUNCHED(ctx);
+                if (prof) CU(cudaEventRecord(ctx->pev[1], st));
                 const unsigned gp = (unsigned)std::min<int64_t>((n + 127) / 128, 148 * 12);
                 if (h.and_mode) k_band<true><<<gp, 128, 0, st>>>(p, d_codes, d_woff, d_len, d_win, d_out, narrow, counters + 0);
                 else k_band<false><<<gp, 128, 0, st>>>(p, d_codes, d_woff, d_len, d_win, d_out, narrow, counters + 0);
                 LAUNCHED(ctx);
+                if (prof) CU(cudaEventRecord(ctx->pev[2], st));
                 if (h.and_mode) k_wide<true><<<gp, 128, 0, st>>>(p, d_codes, d_woff, d_len, d_win, d_out, wide, counters + 1);
                 else k_wide<false><<<gp, 128, 0, st>>>(p, d_codes, d_woff, d_len, d_win, d_out, wide, counters + 1);
+                if (prof) { LAUNCHED(ctx); CU(cudaEventRecord(ctx->pev[3], st)); ctx->launches--; ctx->phases_valid = 1; }
             }
             else if (h.and_mode) k_locate_k1a<true><<<grid_for(n, 128), 128, 0, st>>>(p, d_codes, d_woff, d_len, d_win, n, d_out);
             else k_locate_k1a<false><<<grid_for(n, 128), 128, 0, st>>>(p, d_codes, d_woff, d_len, d_win, n, d_out);
@@ -269,6 +276,7 @@ void atr_ctx_destroy(atr_ctx* ctx) {
         ctx->slot[s].release();
     }
     ctx->misc.release();
+    for (int i = 0; i < 4; i++) if (ctx->pev[i]) cudaEventDestroy(ctx->pev[i]);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->d_tables) cudaFree(ctx->d_tables);
@@ -289,6 +297,25 @@ int64_t atr_ctx_launch_count(atr_ctx* ctx, int reset) {
     const int64_t v = ctx->launches;
     if (reset) ctx->launches = 0;
     return v;
+}
+
+int atr_ctx_set_profiling(atr_ctx* ctx, int on) {
+    if (!ctx) return fail(nullptr, ATR_E_ARG, "ctx is NULL");
+    CU(cudaSetDevice(ctx->device));
+    if (on && !ctx->pev[0]) for (int i = 0; i < 4; i++) CU(cudaEventCreate(&ctx->pev[i]));
+    ctx->profile = on ? 1 : 0;
+    ctx->phases_valid = 0;
+    return ATR_OK;
+}
+
+int atr_ctx_last_phase_ms(atr_ctx* ctx, float* out_ms, int n) {
+    if (!ctx || !out_ms || !ctx->profile || !ctx->phases_valid) return 0;
+    cudaSetDevice(ctx->device);
+    if (cudaEventSynchronize(ctx->pev[3]) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int k = 0;
+    for (; k < 3 && k < n; k++)
+        if (cudaEventElapsedTime(&out_ms[k], ctx->pev[k], ctx->pev[k + 1]) != cudaSuccess) { cudaGetLastError(); break; }
+    return k;
 }
 
 float atr_ctx_last_kernel_ms(atr_ctx* ctx) {
@@ -363,7 +390,15 @@ int atr_locate_batch_device(atr_ctx* ctx, const atr_adapterset* set, const uint3
                             const uint16_t* d_len, const uint16_t* d_win, const uint8_t* d_ascii, const int64_t* d_offsets,
                             int fold_case, int64_t n, atr_match* d_out) {
     if (!ctx || !set || !d_out || n < 0) return fail(ctx, ATR_E_ARG, "bad arguments to atr_locate_batch_device");
+    if (set->ctx != ctx) return fail(ctx, ATR_E_ARG, "adapter set belongs to another context");
     CU(cudaSetDevice(ctx->device));
+    {
+        cudaPointerAttributes pa;
+        if (cudaPointerGetAttributes(&pa, d_out) != cudaSuccess || pa.type != cudaMemoryTypeDevice || pa.device != ctx->device) {
+            cudaGetLastError();
+            return fail(ctx, ATR_E_ARG, "d_out is not device memory of this context's GPU");
+        }
+    }
     Slot& s = ctx->slot[0];
     CU(cudaEventRecord(ctx->ev0, s.stream));
     int rc = locate_on_stream(ctx, s.stream, s.gen_scratch, s.lists, set, d_codes, d_woff, d_len, d_win, d_ascii, d_offsets, 0,

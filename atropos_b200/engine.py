@@ -68,6 +68,15 @@ class Context(object):
     def last_kernel_ms(self):
         return float(self._L.atr_ctx_last_kernel_ms(self.handle))
 
+    def set_profiling(self, on=True):
+        _lib.check(self._L.atr_ctx_set_profiling(self.handle, int(bool(on))), self.handle)
+
+    def last_phase_ms(self):
+        """[filter, band, wide] kernel times (ms) of the last device call on the fast path, or []"""
+        buf = (C.c_float * 3)()
+        k = self._L.atr_ctx_last_phase_ms(self.handle, buf, 3)
+        return [float(buf[i]) for i in range(k)]
+
     # ---- single-call functions ----
     def compare_prefixes(self, ref, query, wildcard_ref=False, wildcard_query=False):
         r, q = ref.encode("ascii"), query.encode("ascii")

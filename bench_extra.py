@@ -1,0 +1,117 @@
+#!/usr/bin/env python
+"""bench_extra.py -- kernel-level measurements of the OTHER BASELINE configurations (parity-test cases, not the
+graded bench line): cfg1 (SE100 13-mer), cfg3 (PE 2x150 insert aligner), cfg4 (8-adapter panel, one GPU's share).
+Prints one JSON object per config. Inputs resident in HBM, CUDA events on the ctx stream.
+
+    python bench_extra.py [--pairs N] [--reads N] [--steps K]
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def time_steps(stream, fn, steps, warmup=2):
+    import torch
+    torch.cuda.synchronize()
+    for _ in range(warmup):
+        fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(stream)
+    for _ in range(steps):
+        fn()
+    e1.record(stream)
+    e1.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def pack(ctx, reads_dev, L):
+    import torch
+    from atropos_b200 import engine
+    n = reads_dev.shape[0]
+    dev = reads_dev.device
+    offs = torch.arange(n + 1, dtype=torch.int64, device=dev) * L
+    codes = torch.empty(n * ((L + 7) // 8) + 8, dtype=torch.int32, device=dev)
+    woff = torch.empty(n + 1, dtype=torch.int32, device=dev)
+    lens = torch.empty(n, dtype=torch.int16, device=dev)
+    torch.cuda.synchronize()          # the ctx stream does not synchronise with torch's streams
+    engine._lib.check(ctx._L.atr_pack_device(ctx.handle, reads_dev.data_ptr(), offs.data_ptr(), n, 0, codes.data_ptr(),
+                                             woff.data_ptr(), lens.data_ptr()), ctx.handle)
+    ctx.sync()
+    return codes, woff, lens, offs
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--reads", type=int, default=10_000_000)
+    ap.add_argument("--pairs", type=int, default=10_000_000)
+    ap.add_argument("--steps", type=int, default=5)
+    args = ap.parse_args()
+    import torch
+    from atropos_b200 import _abi, engine, synth
+    from atropos_b200.adapters import Adapter, BACK, FRONT, PREFIX
+    from atropos_b200.align import InsertAligner
+    from atropos_b200.modifiers import AdapterCutter
+    dev = torch.device("cuda", 0)
+    ctx = engine.default_context(0)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    peak = 6538.3
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        pass
+
+    # ---- cfg1: SE 100 bp, 13-mer ------------------------------------------------------------------
+    n, L = args.reads, 100
+    reads = synth.synth_se(n, L, synth.SHORT_ADAPTER, seed=synth.seed_for(1), device=dev)
+    codes, woff, lens, offs = pack(ctx, reads, L)
+    out = torch.empty((n, 16), dtype=torch.uint8, device=dev)
+    aset = Adapter(synth.SHORT_ADAPTER, BACK, 0.1, 3)._adapterset()
+    ms = time_steps(stream, lambda: aset.locate_device(codes.data_ptr(), woff.data_ptr(), lens.data_ptr(), n, out.data_ptr()), args.steps)
+    b = (L + 1) // 2 + 4 + 16
+    print(json.dumps({"config": "cfg1 SE100 13-mer", "reads": n, "ms": ms, "M_reads_per_s": n / ms / 1e3,
+                      "algo_bytes_per_read": b, "hbm_frac": b * n / (ms * 1e-3) / 1e9 / peak}))
+    del reads, codes, woff, lens, offs, out
+
+    # ---- cfg4 (one GPU's share): SE150, 8-adapter panel, best of N + linked -----------------------------
+    n, L = min(args.reads, 5_000_000), 150
+    reads = synth.synth_se(n, L, synth.TRUSEQ_R1, seed=synth.seed_for(4), device=dev)
+    codes, woff, lens, offs = pack(ctx, reads, L)
+    out = torch.empty((n, 16), dtype=torch.uint8, device=dev)
+    specs = [(synth.TRUSEQ_R1, BACK), (synth.TRUSEQ_R2, BACK), ("TGGAATTCTCGGGTGCCAAGG", BACK),
+             ("GTTCAGAGTTCTACAGTCCGACGATC", PREFIX), ("ACACTCTTTCCCTACACGACGCTCTTCCGATCT", PREFIX),
+             ("AATGATACGGCGACCACCGA", FRONT), ("TGGAATTCTCGGGTGCCAAGG", BACK), ("AGATCGGAAGAGC", BACK)]
+    cutter = AdapterCutter([Adapter(s, w) for s, w in specs])
+    pset = cutter._adapterset()
+    ms = time_steps(stream, lambda: pset.locate_device(codes.data_ptr(), woff.data_ptr(), lens.data_ptr(), n, out.data_ptr()), args.steps)
+    b = (L + 1) // 2 + 4 + 16
+    print(json.dumps({"config": "cfg4 SE150 8-adapter panel (best-of-N on GPU)", "reads": n, "ms": ms,
+                      "M_reads_per_s": n / ms / 1e3, "algo_bytes_per_read": b,
+                      "hbm_frac": b * n / (ms * 1e-3) / 1e9 / peak}))
+    del reads, codes, woff, lens, offs, out
+
+    # ---- cfg3: PE 2x150 insert aligner ------------------------------------------------------------------
+    n, L = args.pairs, 150
+    r1, r2 = synth.synth_pe(n, L, seed=synth.seed_for(3), device=dev)
+    c1, w1, l1, _ = pack(ctx, r1, L)
+    c2, w2, l2, _ = pack(ctx, r2, L)
+    del r1, r2
+    ia = InsertAligner(synth.TRUSEQ_R1, synth.TRUSEQ_R2, max_insert_mismatch_frac=0.1, max_adapter_mismatch_frac=0.1)
+    iset = ia._insertset(L)
+    iout = torch.empty((n, 48), dtype=torch.uint8, device=dev)
+    ms = time_steps(stream, lambda: iset.match_insert_device(c1.data_ptr(), w1.data_ptr(), l1.data_ptr(), c2.data_ptr(),
+                                                              w2.data_ptr(), l2.data_ptr(), n, iout.data_ptr()), args.steps)
+    b = 2 * ((L + 1) // 2) + 8 + 48
+    res = iout.cpu().numpy().view(_abi.INSERT_DTYPE).reshape(-1)
+    print(json.dumps({"config": "cfg3 PE 2x150 insert aligner (match_insert)", "pairs": n, "ms": ms,
+                      "M_pairs_per_s": n / ms / 1e3, "algo_bytes_per_pair": b,
+                      "hbm_frac": b * n / (ms * 1e-3) / 1e9 / peak,
+                      "insert_match_fraction": float((res["insert"]["status"] == 1).mean())}))
+
+
+if __name__ == "__main__":
+    main()

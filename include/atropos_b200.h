@@ -14,7 +14,9 @@
  *     or a negative ATR_E_* code, and atr_last_error(ctx) gives a message;
  *   - the caller owns every buffer it passes; `*_host` entry points take HOST pointers (pageable
  *     or pinned) and do the H2D/D2H copies themselves, `*_device` entry points take DEVICE
- *     pointers on the ctx's device and only enqueue kernels on the ctx's stream;
+ *     pointers on the ctx's device and only enqueue kernels on the ctx's stream (a non-blocking stream:
+ *     it does not synchronise with the legacy default stream, so inputs produced on other streams must be
+ *     complete before the call);
  *   - one atr_ctx per GPU per host thread; no global state; a ctx is not re-entrant (the
  *     reference's Aligner is not either: it owns one DP column, _align.pyx:184, :239-242);
  *   - there is NO CPU fallback: without a CUDA device atr_ctx_create fails with ATR_E_CUDA.
@@ -145,6 +147,12 @@ int64_t     atr_ctx_launch_count(atr_ctx* ctx, int reset);
 /* device time in ms of the kernels of the last *_device / *_host call, measured with CUDA events
  * on the ctx stream around the kernel launches only (copies excluded) */
 float       atr_ctx_last_kernel_ms(atr_ctx* ctx);
+/* Per-kernel device times of the last atr_locate_batch_device call on the fast path (single adapter):
+ * out_ms[0] = filter kernel, [1] = banded-DP kernel, [2] = windowed-DP kernel, measured with CUDA events
+ * recorded between the launches once atr_ctx_set_profiling(ctx, 1) was called. Returns the number of
+ * valid entries (0 if the last call did not take the fast path or profiling is off). */
+int         atr_ctx_set_profiling(atr_ctx* ctx, int on);
+int         atr_ctx_last_phase_ms(atr_ctx* ctx, float* out_ms, int n);
 
 /* ---- adapters: Aligner.__cinit__ / Adapter.__init__ ---------------------------------------- */
 /* replaces Aligner(reference, max_error_rate, flags, wildcard_ref, wildcard_query, min_overlap,

@@ -32,6 +32,19 @@ def test_exports_every_declared_symbol(lib):
     assert sorted(_lib.SYMBOLS) == declared
 
 
+def test_argtypes_match_header_arity(lib):
+    """every ctypes prototype has as many arguments as the C declaration"""
+    text = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    for name, params in re.findall(r"\b(atr_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S):
+        params = params.strip()
+        arity = 0 if params in ("", "void") else params.count(",") + 1
+        fn = getattr(lib, name)
+        if fn.argtypes is not None:
+            assert len(fn.argtypes) == arity, (name, len(fn.argtypes), arity)
+        else:
+            assert arity == 0, name
+
+
 def test_struct_layout(lib):
     from atropos_b200 import _abi
     assert lib.atr_abi_version() == _abi.ATR_ABI_VERSION
