@@ -160,6 +160,21 @@ inline void fill_k1a(const HostAdapter& h, const AtrTables& tb, int index, int r
         }
         a.peq[c] = bits;
     }
+    // Shift-And pieces over the first min(m, 32) rows: k+1 pieces, each at least 6 rows (shorter pieces hit at
+    // random too often to be a filter); needs row-m candidates to be reported inside the loop (stop_in_query)
+    a.sa_ok = 0; a.sa_rows = h.m < 32 ? h.m : 32; a.sa_start = 0; a.sa_end = 0;
+    const bool stop_in_query = h.desc.flags & ATR_STOP_WITHIN_SEQ2;
+    const int pieces = h.k + 1;
+    if (a.fused_ok && stop_in_query && pieces <= a.sa_rows && a.sa_rows / pieces >= 6) {
+        a.sa_ok = 1;
+        int row = 1;
+        for (int pc = 0; pc < pieces; pc++) {
+            const int len = a.sa_rows / pieces + (pc < a.sa_rows % pieces ? 1 : 0);
+            a.sa_start |= 1u << (row - 1);
+            a.sa_end |= 1u << (row + len - 2);
+            row += len;
+        }
+    }
 }
 
 inline void fill_gen(const HostAdapter& h, int index, int reduce, const unsigned char* ref_dev, const unsigned char* lit_dev,

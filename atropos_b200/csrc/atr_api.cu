@@ -59,7 +59,8 @@ struct atr_ctx {
     int64_t launches = 0;
     float last_ms = -1.f;
     int profile = 0, phases_valid = 0;
-    cudaEvent_t pev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t pev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // start, after refine, after band, after wide, after filter
+    int disable_sa = 0;
     int disable_fused = 0;           // ATR_DISABLE_FUSED=1: always use the plain register-DP kernel (A/B measurements)
     DevBuf misc;                     // small single-call scratch (compare_prefixes, multi_locate)
 };
@@ -160,16 +161,22 @@ int locate_on_stream(atr_ctx* ctx, cudaStream_t st, DevBuf& gen_scratch, DevBuf&
             p.mark_routed = !have_ascii;
             if (p.fused_ok && !ctx->disable_fused && n < (int64_t)0x7fffffff) {
                 // filter -> survivor lists -> banded / windowed DP over the survivors only
-                int rc = lists.ensure((size_t)n * 2 * sizeof(Survivor) + 64);
+                int rc = lists.ensure((size_t)n * 3 * sizeof(Survivor) + 64);
                 if (rc) return fail(ctx, rc, "out of device memory (survivor lists)");
                 int* counters = lists.as<int>();
                 Survivor* narrow = (Survivor*)(lists.as<char>() + 64);
                 Survivor* wide = narrow + n;
-                CU(cudaMemsetAsync(counters, 0, 2 * sizeof(int), st));
+                Survivor* refine = wide + n;
+                CU(cudaMemsetAsync(counters, 0, 4 * sizeof(int), st));
                 const bool prof = ctx->profile && set->host.size() == 1;
                 if (prof) CU(cudaEventRecord(ctx->pev[0], st));
                 const unsigned g = grid_for(n, ATR_K1F_THREADS);
-                if (h.m <= 32) {
+                const unsigned gp = (unsigned)std::min<int64_t>((n + 127) / 128, 148 * 12);
+                const bool use_sa = p.sa_ok && !ctx->disable_sa;
+                if (use_sa) {
+                    if (h.and_mode) k_filter_sa<true><<<g, ATR_K1F_THREADS, 0, st>>>(p, d_codes, d_woff, d_len, d_win, n, d_out, narrow, wide, refine, counters);
+                    else k_filter_sa<false><<<g, ATR_K1F_THREADS, 0, st>>>(p, d_codes, d_woff, d_len, d_win, n, d_out, narrow, wide, refine, counters);
+                } else if (h.m <= 32) {
                     if (h.and_mode) k_filter<unsigned int, true><<<g, ATR_K1F_THREADS, 0, st>>>(p, d_codes, d_woff, d_len, d_win, n, d_out, narrow, wide, counters);
                     else k_filter<unsigned int, false><<<g, ATR_K1F_THREADS, 0, st>>>(p, d_codes, d_woff, d_len, d_win, n, d_out, narrow, wide, counters);
                 } else {
@@ -177,8 +184,18 @@ int locate_on_stream(atr_ctx* ctx, cudaStream_t st, DevBuf& gen_scratch, DevBuf&
                     else k_filter<unsigned long long, false><<<g, ATR_K1F_THREADS, 0, st>>>(p, d_codes, d_woff, d_len, d_win, n, d_out, narrow, wide, counters);
                 }
                 LAUNCHED(ctx);
+                if (prof) CU(cudaEventRecord(ctx->pev[4], st));
+                if (use_sa) {
+                    if (h.m <= 32) {
+                        if (h.and_mode) k_refine<unsigned int, true><<<gp, 128, 0, st>>>(p, d_codes, d_woff, d_len, d_win, d_out, refine, narrow, wide, counters);
+                        else k_refine<unsigned int, false><<<gp, 128, 0, st>>>(p, d_codes, d_woff, d_len, d_win, d_out, refine, narrow, wide, counters);
+                    } else {
+                        if (h.and_mode) k_refine<unsigned long long, true><<<gp, 128, 0, st>>>(p, d_codes, d_woff, d_len, d_win, d_out, refine, narrow, wide, counters);
+                        else k_refine<unsigned long long, false><<<gp, 128, 0, st>>>(p, d_codes, d_woff, d_len, d_win, d_out, refine, narrow, wide, counters);
+                    }
+                    LAUNCHED(ctx);
+                }
                 if (prof) CU(cudaEventRecord(ctx->pev[1], st));
-                const unsigned gp = (unsigned)std::min<int64_t>((n + 127) / 128, 148 * 12);
                 if (h.and_mode) k_band<true><<<gp, 128, 0, st>>>(p, d_codes, d_woff, d_len, d_win, d_out, narrow, counters + 0);
                 else k_band<false><<<gp, 128, 0, st>>>(p, d_codes, d_woff, d_len, d_win, d_out, narrow, counters + 0);
                 LAUNCHED(ctx);
@@ -257,6 +274,7 @@ int atr_ctx_create(int device, atr_ctx** out) {
     if (!ctx) return fail(nullptr, ATR_E_NOMEM, "out of host memory");
     ctx->device = device;
     { const char* e = getenv("ATR_DISABLE_FUSED"); ctx->disable_fused = (e && e[0] == '1'); }
+    { const char* e = getenv("ATR_DISABLE_SA"); ctx->disable_sa = (e && e[0] == '1'); }
     CU(cudaSetDevice(device));
     for (int s = 0; s < 2; s++) CU(cudaStreamCreateWithFlags(&ctx->slot[s].stream, cudaStreamNonBlocking));
     CU(cudaEventCreate(&ctx->ev0));
@@ -276,7 +294,7 @@ void atr_ctx_destroy(atr_ctx* ctx) {
         ctx->slot[s].release();
     }
     ctx->misc.release();
-    for (int i = 0; i < 4; i++) if (ctx->pev[i]) cudaEventDestroy(ctx->pev[i]);
+    for (int i = 0; i < 5; i++) if (ctx->pev[i]) cudaEventDestroy(ctx->pev[i]);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->d_tables) cudaFree(ctx->d_tables);
@@ -302,7 +320,7 @@ int64_t atr_ctx_launch_count(atr_ctx* ctx, int reset) {
 int atr_ctx_set_profiling(atr_ctx* ctx, int on) {
     if (!ctx) return fail(nullptr, ATR_E_ARG, "ctx is NULL");
     CU(cudaSetDevice(ctx->device));
-    if (on && !ctx->pev[0]) for (int i = 0; i < 4; i++) CU(cudaEventCreate(&ctx->pev[i]));
+    if (on && !ctx->pev[0]) for (int i = 0; i < 5; i++) CU(cudaEventCreate(&ctx->pev[i]));
     ctx->profile = on ? 1 : 0;
     ctx->phases_valid = 0;
     return ATR_OK;
@@ -312,9 +330,11 @@ int atr_ctx_last_phase_ms(atr_ctx* ctx, float* out_ms, int n) {
     if (!ctx || !out_ms || !ctx->profile || !ctx->phases_valid) return 0;
     cudaSetDevice(ctx->device);
     if (cudaEventSynchronize(ctx->pev[3]) != cudaSuccess) { cudaGetLastError(); return 0; }
+    // events: 0 start, 4 after the filter kernel, 1 after the refine kernel (if any), 2 after band, 3 after wide
+    const int order[5] = {0, 4, 1, 2, 3};
     int k = 0;
-    for (; k < 3 && k < n; k++)
-        if (cudaEventElapsedTime(&out_ms[k], ctx->pev[k], ctx->pev[k + 1]) != cudaSuccess) { cudaGetLastError(); break; }
+    for (; k < 4 && k < n; k++)
+        if (cudaEventElapsedTime(&out_ms[k], ctx->pev[order[k]], ctx->pev[order[k + 1]]) != cudaSuccess) { cudaGetLastError(); break; }
     return k;
 }
 

@@ -52,6 +52,10 @@ struct AdapterK1a {                   // passed by value as a __grid_constant__ 
     int fused_ok;                     // eligible for the bit-vector filter + banded/windowed DP kernels (K1f)
     int band_ok, nomatch;             // K1d usable; a 4-bit code that matches no adapter row (virtual columns)
     unsigned long long peq[16];       // K1f: bit i-1 of peq[c] set iff adapter row i matches read code c
+    // Shift-And pre-filter (k_filter_sa): the first sa_rows (<= 32) adapter rows cut into k+1 pieces; an alignment
+    // with <= k errors must contain one piece verbatim (pigeonhole)
+    int sa_ok, sa_rows;
+    unsigned sa_start, sa_end;        // bit r-1: row r is the first / last row of a piece
 };
 
 struct AdapterGen {                   // general kernel: tables live in global memory

@@ -330,6 +330,127 @@ __global__ void __launch_bounds__(ATR_K1F_THREADS) k_filter(const __grid_constan
     list_append(to_wide, sv, wide, counters + 1);
 }
 
+// ---------------------------------------------------------------------------------------------
+// k_filter_sa: the cheaper first stage used when the adapter's pieces are long enough (AdapterK1a.sa_ok):
+// Shift-And over k+1 verbatim pieces of the first <= 32 adapter rows (~7 instructions per column) plus an exact
+// 32-bit Myers over the last columns for the partial matches at the read end. Reads with a piece hit go to
+// k_refine (exact Myers on the few columns around the hits), which feeds the same narrow / wide lists.
+// ---------------------------------------------------------------------------------------------
+template <bool AND_MODE>
+__global__ void __launch_bounds__(ATR_K1F_THREADS) k_filter_sa(const __grid_constant__ AdapterK1a ad,
+        const uint32_t* __restrict__ codes, const uint32_t* __restrict__ woff, const uint16_t* __restrict__ len,
+        const uint16_t* __restrict__ win, int64_t n_reads, atr_match* __restrict__ out,
+        Survivor* __restrict__ narrow, Survivor* __restrict__ wide, Survivor* __restrict__ refine, int* __restrict__ counters) {
+    __shared__ __align__(128) uint32_t s_tile[ATR_K1F_TILE_WORDS];
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ unsigned s_sa_peq[16], s_tail_peq[16];
+
+    const int tid = threadIdx.x;
+    const int64_t t0 = (int64_t)blockIdx.x * ATR_K1F_THREADS;
+    const int cnt = (int)(n_reads - t0 < ATR_K1F_THREADS ? n_reads - t0 : ATR_K1F_THREADS);
+    const uint32_t w_begin = woff[t0], w_end = woff[t0 + cnt];
+    const uint32_t a_begin = w_begin & ~3u;
+    const uint32_t span = ((w_end - a_begin) + 3u) & ~3u;
+    const bool last_tile = (t0 + cnt == n_reads);
+    const bool fits = span <= ATR_K1F_TILE_WORDS;
+    const bool use_tma = fits && !last_tile && span > 0 && ((reinterpret_cast<uintptr_t>(codes) & 15) == 0);
+    if (tid < 16) {
+        const int mp = ad.sa_rows, sh32 = 32 - mp;
+        const unsigned low = (unsigned)(ad.peq[tid] & (mp >= 32 ? 0xFFFFFFFFull : ((1ull << mp) - 1)));
+        s_sa_peq[tid] = low;
+        s_tail_peq[tid] = sh32 ? ((low << sh32) | ((1u << sh32) - 1u)) : low;
+    }
+    if (tid == 0 && use_tma) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar)) : "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    if (use_tma) {
+        if (tid == 0) tma_load_1d(s_tile, codes + a_begin, span * 4u, &s_bar);
+    } else if (fits) {
+        for (uint32_t w = tid; w < w_end - a_begin; w += ATR_K1F_THREADS) s_tile[w] = codes[a_begin + w];
+    }
+    const int64_t r = t0 + tid;
+    const bool mine = tid < cnt;
+    bool routed = false, esc = false;
+    int lo = 0, n = 0;
+    uint32_t wr = a_begin;
+    if (mine) {
+        read_extent(len, win, r, lo, n, esc);
+        wr = woff[r];
+        routed = (esc && !AND_MODE) || n > ATR_K1A_MAXN;
+        if (routed && ad.mark_routed) {
+            atr_match m;
+            m.astart = m.astop = m.rstart = m.rstop = m.matches = m.errors = 0;
+            m.adapter = -1; m.status = ATR_ST_ESCAPED;
+            out[r] = m;
+        }
+    }
+    if (use_tma) mbar_wait(&s_bar, 0);
+    else __syncthreads();
+    const uint32_t* rd = fits ? (s_tile + (wr - a_begin)) : (codes + wr);
+    bool to_narrow = false, to_wide = false, to_refine = false;
+    Survivor sv;
+    sv.read = (uint32_t)r; sv.a = 0; sv.b = 0;
+    if (mine && !routed) {
+        SaResult sr;
+        sa_filter(ad, s_sa_peq, s_tail_peq, rd, lo, n, sr);
+        if (sr.cls == 0) {
+            Best b;
+            b.ref_stop = ad.m; b.q_stop = n; b.cost = ad.m + n; b.origin = 0; b.matches = 0;
+            finalize(ad, b, n, out + r);
+        } else if (sr.cls == 1) {
+            if (ad.band_ok && sr.width <= ATR_K1D_W) { to_narrow = true; sv.a = (short)sr.dlo; }
+            else { to_wide = true; sv.a = (short)sr.c0; sv.b = (short)sr.c1; }
+        } else {
+            to_refine = true; sv.a = (short)sr.c0; sv.b = (short)sr.c1;
+        }
+    }
+    list_append(to_narrow, sv, narrow, counters + 0);
+    list_append(to_wide, sv, wide, counters + 1);
+    list_append(to_refine, sv, refine, counters + 2);
+}
+
+// k_refine: exact Myers over the column range the piece hits point at; dense over the refine list
+template <class WORD, bool AND_MODE>
+__global__ void __launch_bounds__(128) k_refine(const __grid_constant__ AdapterK1a ad,
+        const uint32_t* __restrict__ codes, const uint32_t* __restrict__ woff, const uint16_t* __restrict__ len,
+        const uint16_t* __restrict__ win, atr_match* __restrict__ out, const Survivor* __restrict__ list,
+        Survivor* __restrict__ narrow, Survivor* __restrict__ wide, int* __restrict__ counters) {
+    __shared__ WORD s_peq[16];
+    if (threadIdx.x < 16) {
+        const int WB = (int)(8 * sizeof(WORD)), sh = WB - ad.m;
+        s_peq[threadIdx.x] = (WORD)(((WORD)ad.peq[threadIdx.x] << sh) | (sh ? (((WORD)1 << sh) - 1) : 0));
+    }
+    __syncthreads();
+    const int count = counters[2];
+    const int stride = gridDim.x * blockDim.x;
+    const int rounds = (count + stride - 1) / stride;          // uniform trip count: the appends use warp ballots
+    for (int it = 0; it < rounds; it++) {
+        const int s = it * stride + blockIdx.x * blockDim.x + threadIdx.x;
+        bool to_narrow = false, to_wide = false;
+        Survivor sv;
+        sv.read = 0; sv.a = 0; sv.b = 0;
+        if (s < count) {
+            const Survivor in = list[s];
+            int lo, n; bool esc;
+            read_extent(len, win, in.read, lo, n, esc);
+            FilterHit hit;
+            sv.read = in.read;
+            if (myers_filter<WORD>(ad, s_peq, codes + woff[in.read], lo, n, hit, (int)in.a, (int)in.b)) {
+                if (ad.band_ok && hit.width <= ATR_K1D_W) { to_narrow = true; sv.a = (short)hit.dlo; }
+                else { to_wide = true; sv.a = (short)hit.c0; sv.b = (short)hit.c1; }
+            } else {
+                Best b;
+                b.ref_stop = ad.m; b.q_stop = n; b.cost = ad.m + n; b.origin = 0; b.matches = 0;
+                finalize(ad, b, n, out + in.read);
+            }
+        }
+        list_append(to_narrow, sv, narrow, counters + 0);
+        list_append(to_wide, sv, wide, counters + 1);
+    }
+}
+
 template <bool AND_MODE>
 __global__ void __launch_bounds__(128) k_band(const __grid_constant__ AdapterK1a ad,
         const uint32_t* __restrict__ codes, const uint32_t* __restrict__ woff, const uint16_t* __restrict__ len,

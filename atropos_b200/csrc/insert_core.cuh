@@ -87,14 +87,24 @@ struct PackedPair {
     const uint32_t* S1;
     int stride;
     int m;
-    ATR_HD int overlap_cost(int j) const {             // Hamming(R[m-j:m], Q[0:j])
+    // Hamming(R[m-j:m], Q[0:j]), abandoned as soon as it exceeds k (the caller skips such offsets anyway:
+    // random offsets die after ~3 words instead of j/8)
+    ATR_HD int overlap_cost(int j, int k) const {
         const int s = m - j, ws = s >> 3;
         const unsigned bs = (unsigned)(s & 7) * 4u;
-        const int nw = (j + 7) >> 3;
+        const int nfull = j >> 3;                       // whole words
         unsigned cost = 0;
-        for (int w = 0; w < nw; w++) {
-            uint32_t x = funnel_r(R[(ws + w) * stride], R[(ws + w + 1) * stride], bs) ^ Q[w * stride];
-            if (w == nw - 1 && (j & 7)) x &= (1u << ((j & 7) * 4)) - 1u;
+        uint32_t lo = R[ws * stride];
+        int w = 0;
+        for (; w < nfull; w++) {
+            const uint32_t hi = R[(ws + w + 1) * stride];
+            cost += nib_mismatches(funnel_r(lo, hi, bs) ^ Q[w * stride]);
+            lo = hi;
+            if ((int)cost > k) return (int)cost;
+        }
+        if (j & 7) {
+            const uint32_t hi = R[(ws + w + 1) * stride];
+            const uint32_t x = (funnel_r(lo, hi, bs) ^ Q[w * stride]) & ((1u << ((j & 7) * 4)) - 1u);
             cost += nib_mismatches(x);
         }
         return (int)cost;
@@ -109,9 +119,9 @@ struct BytePair {
     const unsigned char* comp;
     const unsigned char* ov_tab;
     int m;
-    ATR_HD int overlap_cost(int j) const {             // ref[i] = comp[s2[m-1-i]]
+    ATR_HD int overlap_cost(int j, int k) const {      // ref[i] = comp[s2[m-1-i]]
         int cost = 0;
-        for (int t = 0; t < j; t++) cost += (comp[s2[j - 1 - t]] != s1[t]);      // ref[m-j+t] = comp[s2[m-1-(m-j+t)]] = comp[s2[j-1-t]]
+        for (int t = 0; t < j && cost <= k; t++) cost += (comp[s2[j - 1 - t]] != s1[t]);      // ref[m-j+t] = comp[s2[j-1-t]]
         return cost;
     }
     ATR_HD unsigned ov1(int p) const { return ov_tab[s1[p]]; }
@@ -179,7 +189,7 @@ ATR_HD void insert_pair(const InsertDev& d, const P& pr, bool packed, int m, int
     const int k = d.k_by_len[m];
     int count = 0;
     for (int j = 1; j <= m; j++) {                                            // Appendix B of SURVEY.md
-        const int cost = pr.overlap_cost(j);
+        const int cost = pr.overlap_cost(j, k);
         if (cost > k) continue;
         if (j >= d.min_insert_overlap && cost <= (int)d.thr_ins[j]) {
             if (cost == 0 && j == m) { cand[0].j = (unsigned short)j; cand[0].cost = 0; count = 1; break; }   // [exact]

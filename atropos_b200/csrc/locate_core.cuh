@@ -26,6 +26,13 @@ struct Best {
 ATR_HD int atr_min(int a, int b) { return a < b ? a : b; }
 ATR_HD int atr_max(int a, int b) { return a > b ? a : b; }
 ATR_HD unsigned atr_umin(unsigned a, unsigned b) { return a < b ? a : b; }
+ATR_HD int atr_ctz(unsigned x) {
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)x) - 1;
+#else
+    return __builtin_ctz(x);
+#endif
+}
 
 // candidate acceptance: _align.pyx:443-449 (row m inside the loop) and :465-474 (last column)
 template <class A>
@@ -273,12 +280,16 @@ ATR_HD void myers_col(MyersState<WORD>& st, WORD Eq) {
 
 template <class WORD>
 ATR_HD bool myers_filter(const AdapterK1a& ad, const WORD* __restrict__ peq, const uint32_t* __restrict__ codes, int lo, int n,
-                         FilterHit& hit) {
+                         FilterHit& hit, int cstart = -1, int cstop = -1) {
+    // cstart/cstop: evaluate only columns cstart+1..cstop, starting afresh at cstart (k_refine). The costs of
+    // cells whose cheap alignments start at or after cstart are exact, all others only grow.
     const int m = ad.m, k = ad.k;
     const int WB = (int)(8 * sizeof(WORD));
     const int sh = WB - m;                             // first real row sits at bit sh
     const bool stop_in_ref = ad.flags & ATR_STOP_WITHIN_SEQ1, stop_in_query = ad.flags & ATR_STOP_WITHIN_SEQ2;
-    const int min_n = stop_in_query ? 0 : atr_max(0, n - m - k);
+    int min_n = stop_in_query ? 0 : atr_max(0, n - m - k);
+    const int n_full = n;
+    if (cstart >= 0) { min_n = atr_max(min_n, cstart); n = atr_min(n, cstop); }
     MyersState<WORD> st;
     st.Pv = (sh == 0) ? ~(WORD)0 : (WORD)(~(WORD)0 << sh);   // column min_n: cost(i) = i (_align.pyx:345-348)
     st.Mv = 0;
@@ -315,7 +326,7 @@ ATR_HD bool myers_filter(const AdapterK1a& ad, const WORD* __restrict__ peq, con
     }
     // last column: D[i][n] = sum of the vertical deltas of rows 1..i
     int imin = 0, imax = 0;
-    {
+    if (n == n_full) {
         int d = 0;
         const int first = stop_in_ref ? 1 : m;
         for (int i = 1; i <= m; i++) {
@@ -334,6 +345,104 @@ ATR_HD bool myers_filter(const AdapterK1a& ad, const WORD* __restrict__ peq, con
     hit.c0 = atr_max(min_n, elo - k);                 // first column any such alignment can touch in row 0
     hit.c1 = imax > 0 ? n : jmax;
     return true;
+}
+
+// ---- K1f phase 0: Shift-And pre-filter + 32-bit tail Myers (k_filter_sa) ---------------------------------------
+// Pigeonhole: an alignment of the adapter's first sa_rows rows with <= k unit-cost errors contains one of the
+// k+1 pieces verbatim, so a read without any verbatim piece has no row-m candidate and none in the last column
+// below row sa_rows... The Shift-And automaton over all pieces costs ~7 instructions per column (vs ~31 for the
+// 64-bit Myers). Candidates in the last column with row <= sa_rows are found exactly by a 32-bit Myers over the
+// last sa_rows + k columns. Result classes:
+//   0  nothing can match                       -> the read is finished (no match)
+//   1  no piece hit, but last-column candidates -> band known exactly (dlo / width, or window if too wide)
+//   2  piece hit(s)                             -> exact 64/32-bit Myers over columns [c0, c1] decides (k_refine)
+struct SaResult {
+    int cls;
+    int dlo, width;      // class 1
+    int c0, c1;          // class 1 (window form) and class 2
+};
+
+ATR_HD void sa_filter(const AdapterK1a& ad, const unsigned* __restrict__ sa_peq, const unsigned* __restrict__ tail_peq,
+                      const uint32_t* __restrict__ codes, int lo, int n, SaResult& res) {
+    const int m = ad.m, k = ad.k, mp = ad.sa_rows;
+    const bool stop_in_ref = ad.flags & ATR_STOP_WITHIN_SEQ1;
+    const unsigned S0 = ad.sa_start, E = ad.sa_end;
+    unsigned St = 0;
+    int hmin = 0x7fffffff, hmax = -0x7fffffff;       // over hits: (column of the piece end) - (row of the piece end)
+    int j = 0, pos = lo;
+    const int pend = lo + n;
+    while (pos < pend && (pos & 7) != 0) {
+        const unsigned qc = (codes[pos >> 3] >> ((pos & 7) * 4)) & 15u;
+        St = ((St << 1) | S0) & sa_peq[qc];
+        j++; pos++;
+        unsigned hb = St & E;
+        while (hb) { const int b = atr_ctz(hb); hb &= hb - 1; const int v = j - (b + 1); hmin = atr_min(hmin, v); hmax = atr_max(hmax, v); }
+    }
+    while (pos + 8 <= pend) {
+        const uint32_t w = codes[pos >> 3];
+        unsigned any = 0;
+        unsigned Ss[8];
+#pragma unroll
+        for (int t = 0; t < 8; t++) {
+            St = ((St << 1) | S0) & sa_peq[(w >> (4 * t)) & 15u];
+            Ss[t] = St;
+            any |= St;
+        }
+        if (any & E) {                                 // rare: some piece ended inside this word
+#pragma unroll
+            for (int t = 0; t < 8; t++) {
+                unsigned hb = Ss[t] & E;
+                while (hb) { const int b = atr_ctz(hb); hb &= hb - 1; const int v = j + t + 1 - (b + 1); hmin = atr_min(hmin, v); hmax = atr_max(hmax, v); }
+            }
+        }
+        j += 8; pos += 8;
+    }
+    if (pos < pend) {
+        const uint32_t w = codes[pos >> 3];
+        for (int t = 0; pos < pend; t++) {
+            St = ((St << 1) | S0) & sa_peq[(w >> (4 * t)) & 15u];
+            j++; pos++;
+            unsigned hb = St & E;
+            while (hb) { const int b = atr_ctz(hb); hb &= hb - 1; const int v = j - (b + 1); hmin = atr_min(hmin, v); hmax = atr_max(hmax, v); }
+        }
+    }
+    // tail: exact D[i][n] for rows i <= mp from a 32-bit Myers over the last mp + k columns (rows left-aligned)
+    int imin = 0, imax = 0;
+    if (stop_in_ref || m <= mp) {
+        const int sh = 32 - mp;
+        MyersState<unsigned> st;
+        st.Pv = (sh == 0) ? ~0u : (~0u << sh);
+        st.Mv = 0; st.score = mp;
+        const int ts = atr_max(0, n - mp - k);
+        for (int p = lo + ts; p < pend; p++) {
+            const unsigned qc = (codes[p >> 3] >> ((p & 7) * 4)) & 15u;
+            myers_col(st, tail_peq[qc]);
+        }
+        int d = 0;
+        const int first = stop_in_ref ? 1 : m;
+        for (int i = 1; i <= mp; i++) {
+            d += (int)((st.Pv >> (sh + i - 1)) & 1u) - (int)((st.Mv >> (sh + i - 1)) & 1u);
+            if (i >= first && i >= ad.min_overlap && d <= (int)ad.thr_mul[i]) { if (imin == 0) imin = i; imax = i; }
+        }
+    }
+    const bool have_hit = hmax != -0x7fffffff;
+    if (!have_hit && imax == 0) { res.cls = 0; return; }
+    if (!have_hit) {
+        res.cls = 1;
+        res.dlo = (n - imax) - k;
+        res.width = (imax - imin) + 2 * k + 1;
+        res.c0 = atr_max(0, n - imax - k);
+        res.c1 = n;
+        return;
+    }
+    // a verbatim piece ending at (row r1, column jh), v = jh - r1: the alignment through it starts in row 0 at a
+    // column >= v - k and reaches row m at a column in [v + m - k, v + m + k]
+    res.cls = 2;
+    int c0 = hmin - k - 1;
+    int c1 = hmax + m + k + 1;
+    if (imax > 0) { c0 = atr_min(c0, n - imax - k - 1); c1 = n; }
+    res.c0 = atr_max(0, c0);
+    res.c1 = atr_min(n, c1);
 }
 
 // ---- K1f phase 2 (narrow bands): K1d, banded DP along diagonals ------------------------------------------
@@ -609,9 +718,26 @@ ATR_HD void k1f_read(const AdapterK1a& ad, const uint32_t* __restrict__ codes, i
     WORD peq[16];
     for (int c = 0; c < 16; c++) peq[c] = (WORD)(((WORD)ad.peq[c] << sh) | (sh ? (((WORD)1 << sh) - 1) : 0));
     if (path) *path = 0;
-    if (myers_filter<WORD>(ad, peq, codes, lo, n, hit)) {
+    bool have = false;
+    if (ad.sa_ok) {
+        unsigned sa_peq[16], tail_peq[16];
+        const int mp = ad.sa_rows, sh32 = 32 - mp;
+        for (int c = 0; c < 16; c++) {
+            const unsigned low = (unsigned)(ad.peq[c] & (mp >= 32 ? 0xFFFFFFFFull : ((1ull << mp) - 1)));
+            sa_peq[c] = low;
+            tail_peq[c] = (sh32 ? (low << sh32) | ((1u << sh32) - 1u) : low);
+        }
+        SaResult sr;
+        sa_filter(ad, sa_peq, tail_peq, codes, lo, n, sr);
+        if (sr.cls == 1) { have = true; hit.dlo = sr.dlo; hit.width = sr.width; hit.c0 = sr.c0; hit.c1 = sr.c1; }
+        else if (sr.cls == 2) have = myers_filter<WORD>(ad, peq, codes, lo, n, hit, sr.c0, sr.c1);
+    } else {
+        have = myers_filter<WORD>(ad, peq, codes, lo, n, hit);
+    }
+    if (have) {
         if (ad.band_ok && hit.width <= ATR_K1D_W) { if (path) *path = 1; k1d_band<AND_MODE, ATR_K1D_W>(ad, codes, lo, n, hit.dlo, b); }
         else { if (path) *path = 2; k1a_locate<AND_MODE>(ad, codes, lo, n, b, hit.c0, hit.c1); }
     }
+    if (path && ad.sa_ok) *path += 10;                 // tests: 10 + x = went through the Shift-And pre-filter
     finalize(ad, b, n, out);
 }

@@ -72,9 +72,9 @@ class Context(object):
         _lib.check(self._L.atr_ctx_set_profiling(self.handle, int(bool(on))), self.handle)
 
     def last_phase_ms(self):
-        """[filter, band, wide] kernel times (ms) of the last device call on the fast path, or []"""
-        buf = (C.c_float * 3)()
-        k = self._L.atr_ctx_last_phase_ms(self.handle, buf, 3)
+        """[filter, refine, band, wide] kernel times (ms) of the last device call on the fast path, or []"""
+        buf = (C.c_float * 4)()
+        k = self._L.atr_ctx_last_phase_ms(self.handle, buf, 4)
         return [float(buf[i]) for i in range(k)]
 
     # ---- single-call functions ----

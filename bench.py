@@ -274,14 +274,14 @@ def run_ours(args):
     for _ in range(args.steps):
         step_device()
         ph = ctx.last_phase_ms()
-        if len(ph) == 3:
+        if len(ph) == 4:
             phase.append(ph)
     ctx.set_profiling(False)
     ctx.sync()
     kernels_ms = None
     if phase:
-        kernels_ms = {"k_filter": sum(p[0] for p in phase) / len(phase), "k_band": sum(p[1] for p in phase) / len(phase),
-                      "k_wide": sum(p[2] for p in phase) / len(phase)}
+        names = ["k_filter_sa", "k_refine", "k_band", "k_wide"]
+        kernels_ms = {nm: sum(p[i] for p in phase) / len(phase) for i, nm in enumerate(names)}
 
     # ---- e2e leg: host buffers through the public host entry point ------------------------------------
     e2e_steps = max(1, min(args.steps, 5))

@@ -148,7 +148,7 @@ int64_t     atr_ctx_launch_count(atr_ctx* ctx, int reset);
  * on the ctx stream around the kernel launches only (copies excluded) */
 float       atr_ctx_last_kernel_ms(atr_ctx* ctx);
 /* Per-kernel device times of the last atr_locate_batch_device call on the fast path (single adapter):
- * out_ms[0] = filter kernel, [1] = banded-DP kernel, [2] = windowed-DP kernel, measured with CUDA events
+ * out_ms[0] = filter kernel, [1] = refine kernel, [2] = banded-DP kernel, [3] = windowed-DP kernel, measured with CUDA events
  * recorded between the launches once atr_ctx_set_profiling(ctx, 1) was called. Returns the number of
  * valid entries (0 if the last call did not take the fast path or profiling is off). */
 int         atr_ctx_set_profiling(atr_ctx* ctx, int on);
