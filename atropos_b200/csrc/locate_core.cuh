@@ -413,10 +413,18 @@ ATR_HD void sa_filter(const AdapterK1a& ad, const unsigned* __restrict__ sa_peq,
         MyersState<unsigned> st;
         st.Pv = (sh == 0) ? ~0u : (~0u << sh);
         st.Mv = 0; st.score = mp;
-        const int ts = atr_max(0, n - mp - k);
-        for (int p = lo + ts; p < pend; p++) {
-            const unsigned qc = (codes[p >> 3] >> ((p & 7) * 4)) & 15u;
-            myers_col(st, tail_peq[qc]);
+        // start on a word boundary at or before column n - mp - k (an earlier start is always safe)
+        int p = atr_max(lo, (lo + atr_max(0, n - mp - k)) & ~7);
+        while (p < pend && (p & 7) != 0) { myers_col(st, tail_peq[(codes[p >> 3] >> ((p & 7) * 4)) & 15u]); p++; }
+        while (p + 8 <= pend) {
+            const uint32_t w = codes[p >> 3];
+#pragma unroll
+            for (int t = 0; t < 8; t++) myers_col(st, tail_peq[(w >> (4 * t)) & 15u]);
+            p += 8;
+        }
+        if (p < pend) {
+            const uint32_t w = codes[p >> 3];
+            for (int t = 0; p < pend; t++, p++) myers_col(st, tail_peq[(w >> (4 * t)) & 15u]);
         }
         int d = 0;
         const int first = stop_in_ref ? 1 : m;
@@ -441,8 +449,11 @@ ATR_HD void sa_filter(const AdapterK1a& ad, const unsigned* __restrict__ sa_peq,
     int c0 = hmin - k - 1;
     int c1 = hmax + m + k + 1;
     if (imax > 0) { c0 = atr_min(c0, n - imax - k - 1); c1 = n; }
-    res.c0 = atr_max(0, c0);
-    res.c1 = atr_min(n, c1);
+    // widen to word boundaries of the packed read (a wider range is always safe; it keeps k_refine in its
+    // unrolled whole-word loop)
+    c0 = atr_max(0, c0); c1 = atr_min(n, c1);
+    res.c0 = atr_max(0, ((lo + c0) & ~7) - lo);
+    res.c1 = atr_min(n, ((lo + c1 + 7) & ~7) - lo);
 }
 
 // ---- K1f phase 2 (narrow bands): K1d, banded DP along diagonals ------------------------------------------
@@ -458,76 +469,86 @@ ATR_HD void k1d_band(const AdapterK1a& ad, const uint32_t* __restrict__ codes, i
     const int m = ad.m, k = ad.k;
     const bool stop_in_ref = ad.flags & ATR_STOP_WITHIN_SEQ1, stop_in_query = ad.flags & ATR_STOP_WITHIN_SEQ2;
     const int min_n = stop_in_query ? 0 : atr_max(0, n - m - k);
-    const unsigned CLAMP = (unsigned)(k + 1) << ATR_COST_SHIFT;
+    const unsigned DEAD = (unsigned)(k + 1) << ATR_COST_SHIFT;
     const unsigned C_SUB = 1u << ATR_COST_SHIFT;
     const unsigned C_INS = (1u << ATR_COST_SHIFT) | (1u << ATR_PRIO_SHIFT);
     const unsigned C_DEL = (1u << ATR_COST_SHIFT) | (2u << ATR_PRIO_SHIFT);
     const unsigned nomatch = (unsigned)ad.nomatch;
+    // No per-cell clamp here: a cell costs at most one more than the cell above it on its diagonal, so after
+    // <= 64 rows the 8-bit cost field holds at most (k+1) + 64 <= 191. Cells with cost > k are dead whatever
+    // their exact value.
 
-    // the key's origin field is biased by ATR_ORG_BIAS (64) and dlo >= -(m + k) - k > -ORG range is not
-    // guaranteed for virtual columns far left of 0: clamp the stored row-0 origin at -ATR_ORG_BIAS (any
-    // negative origin means 0 after the final clamp)
     unsigned B[W];
 #pragma unroll
-    for (int d = 0; d < W; d++) {                      // row 0: cost 0, origin j (:385-386), every column "exists"
+    for (int d = 0; d < W; d++) {                      // row 0: cost 0, origin j (:385-386); no column beyond n
         const int j = dlo + d;
-        B[d] = j > n ? CLAMP : k1a_key(0, atr_max(j, -ATR_ORG_BIAS), 0);
+        B[d] = j > n ? DEAD : k1a_key(0, atr_max(j, -ATR_ORG_BIAS), 0);
     }
-    // sliding window of the W read codes of the current row: nibble d = base of column i + dlo + d
-    unsigned long long win = 0;
+    // Sliding window of the W read codes of the current row: nibble d = base of column i + dlo + d.
+    //  * left of the first DP column: a code that matches nothing (see above);
+    //  * right of the read end: a base that matches EVERYTHING (vm marks those nibbles). A match always takes
+    //    the diagonal, so cell (i, n) travels unchanged (plus one match per step) down its diagonal to row m:
+    //    the reference's last-column candidates (:461-474) are read off row m at columns n+1.., no per-row tap.
+    unsigned long long win = 0, vm = 0;
     auto base_at = [&](int p) -> unsigned {            // p = 0-based position in the (windowed) read
-        if (p < min_n || p >= n) return nomatch;
+        if (p < min_n) return nomatch;
+        if (p >= n) return 0u;
         const int q = lo + p;
         unsigned c = (codes[q >> 3] >> ((q & 7) * 4)) & 15u;
         if (AND_MODE && ad.q_single_only) c = (c & (c - 1)) ? 0u : c;
         return c;
     };
 #pragma unroll 1
-    for (int d = 0; d < W - 1; d++)                    // row 1 needs columns 1+dlo .. W+dlo -> positions dlo .. dlo+W-1
+    for (int d = 0; d < W - 1; d++) {                  // row 1 needs columns 1+dlo .. W+dlo -> positions dlo .. dlo+W-1
         win |= (unsigned long long)base_at(dlo + d) << (4 * (d + 1));
-    Best bl;                                           // last-column candidates, merged after the row-m ones
-    bl.ref_stop = m; bl.q_stop = n; bl.cost = m + n; bl.origin = 0; bl.matches = 0;
-    best = bl;
-    const int first_i = stop_in_ref ? 1 : m;
+        if (dlo + d >= n) vm |= 0xFull << (4 * (d + 1));
+    }
 #pragma unroll 1
     for (int i = 1; i <= m; i++) {
-        win = (win >> 4) | ((unsigned long long)base_at(i + dlo + W - 2) << (4 * (W - 1)));
+        const int pnew = i + dlo + W - 2;
+        win = (win >> 4) | ((unsigned long long)base_at(pnew) << (4 * (W - 1)));
+        vm = (vm >> 4) | (pnew >= n ? (0xFull << (4 * (W - 1))) : 0ull);
         const unsigned a = (unsigned)ad.code[i - 1];
         // per-nibble (mis)match flags for the whole row at once
         unsigned long long x;
-        if (AND_MODE) x = win & (0x1111111111111111ull * a);
-        else x = win ^ (0x1111111111111111ull * a);
+        if (AND_MODE) x = (win & (0x1111111111111111ull * a)) | vm;
+        else x = (win ^ (0x1111111111111111ull * a)) & ~vm;
         x |= x >> 1; x |= x >> 2;                      // bit 4d set <=> nibble d non-zero
         const unsigned xl = (unsigned)x, xh = (unsigned)(x >> 32);
-        unsigned left = CLAMP;                         // cell (i, i + dlo - 1): outside the band
+        unsigned left = DEAD;                          // cell (i, i + dlo - 1): outside the band
 #pragma unroll
         for (int d = 0; d < W; d++) {
             const unsigned diag = B[d];
-            const unsigned up = (d + 1 < W) ? B[d + 1] : CLAMP;
+            const unsigned up = (d + 1 < W) ? B[d + 1] : DEAD;
             const unsigned nz = ((d < 8 ? xl : xh) >> (4 * (d & 7))) & 1u;
             const bool eq = AND_MODE ? (nz != 0u) : (nz == 0u);
-            unsigned t = atr_umin(atr_umin(left + C_DEL, up + C_INS), diag + C_SUB) & ATR_PRIO_CLEAR;
-            unsigned nw = eq ? diag + 1u : t;
-            nw = atr_umin(nw, CLAMP);
+            const unsigned t = atr_umin(atr_umin(left + C_DEL, up + C_INS), diag + C_SUB) & ATR_PRIO_CLEAR;
+            const unsigned nw = eq ? diag + 1u : t;
             B[d] = nw;
             left = nw;
         }
-        // last column (:461-474): cell (i, n) lives on diagonal n - i
-        const int dsel = n - i - dlo;
-        if (i >= first_i && dsel >= 0 && dsel < W) {
-            unsigned c = CLAMP;
-#pragma unroll
-            for (int d = 0; d < W; d++) if (d == dsel) c = B[d];
-            if (c < CLAMP) consider(ad, bl, k1a_cost(c), atr_max(k1a_origin(c), 0), k1a_matches(c), i, n);
-        }
     }
+    Best bl;                                           // last-column candidates, merged after the row-m ones
+    bl.ref_stop = m; bl.q_stop = n; bl.cost = m + n; bl.origin = 0; bl.matches = 0;
+    best = bl;
     if (stop_in_query) {                               // row m, columns in ascending order (:440-458)
 #pragma unroll
         for (int d = 0; d < W; d++) {
             const int j = m + dlo + d;
             const unsigned c = B[d];
-            if (j > min_n && j <= n && c < CLAMP)
+            if (j > min_n && j <= n && k1a_cost(c) <= k)
                 consider(ad, best, k1a_cost(c), atr_max(k1a_origin(c), 0), k1a_matches(c), m, j);
+        }
+    }
+    {                                                  // last column, rows ascending = virtual columns descending
+        const int first_i = stop_in_ref ? 1 : m;
+#pragma unroll
+        for (int d = W - 1; d >= 0; d--) {
+            const int j = m + dlo + d;
+            const int i = m - (j - n);                 // cell (i, n) arrived here after j - n forced matches
+            const unsigned c = B[d];
+            if (j >= n && i >= first_i && i >= 1 && k1a_cost(c) <= k)
+                consider(ad, bl, k1a_cost(c), atr_max(k1a_origin(c), 0), k1a_matches(c) - (j - n), i, n);
         }
     }
     // the reference scans the last column after all in-loop candidates; replacement needs a strictly better key
