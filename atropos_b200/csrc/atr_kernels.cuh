@@ -402,6 +402,8 @@ __global__ void __launch_bounds__(ATR_K1F_THREADS) k_filter_sa(const __grid_cons
         } else if (sr.cls == 1) {
             if (ad.band_ok && sr.width <= ATR_K1D_W) { to_narrow = true; sv.a = (short)sr.dlo; }
             else { to_wide = true; sv.a = (short)sr.c0; sv.b = (short)sr.c1; }
+        } else if (ad.band_ok && sr.width <= ATR_K1D_W) {
+            to_narrow = true; sv.a = (short)sr.dlo;                 // band known from the hits: no exact pass needed
         } else {
             to_refine = true; sv.a = (short)sr.c0; sv.b = (short)sr.c1;
         }

@@ -426,11 +426,14 @@ ATR_HD void sa_filter(const AdapterK1a& ad, const unsigned* __restrict__ sa_peq,
             const uint32_t w = codes[p >> 3];
             for (int t = 0; p < pend; t++, p++) myers_col(st, tail_peq[(w >> (4 * t)) & 15u]);
         }
+        // D[i][n] = running sum of the vertical deltas; rows right-aligned so that the shifts are static
+        const unsigned pv = st.Pv >> sh, mv = st.Mv >> sh;
+        const int row_lo = atr_max(stop_in_ref ? 1 : m, ad.min_overlap);
         int d = 0;
-        const int first = stop_in_ref ? 1 : m;
-        for (int i = 1; i <= mp; i++) {
-            d += (int)((st.Pv >> (sh + i - 1)) & 1u) - (int)((st.Mv >> (sh + i - 1)) & 1u);
-            if (i >= first && i >= ad.min_overlap && d <= (int)ad.thr_mul[i]) { if (imin == 0) imin = i; imax = i; }
+#pragma unroll
+        for (int i = 1; i <= 32; i++) {
+            d += (int)((pv >> (i - 1)) & 1u) - (int)((mv >> (i - 1)) & 1u);
+            if (i >= row_lo && i <= mp && d <= (int)ad.thr_mul[i]) { imin = imin == 0 ? i : imin; imax = i; }
         }
     }
     const bool have_hit = hmax != -0x7fffffff;
@@ -446,6 +449,15 @@ ATR_HD void sa_filter(const AdapterK1a& ad, const unsigned* __restrict__ sa_peq,
     // a verbatim piece ending at (row r1, column jh), v = jh - r1: the alignment through it starts in row 0 at a
     // column >= v - k and reaches row m at a column in [v + m - k, v + m + k]
     res.cls = 2;
+    // Every candidate tied to a hit v ends on a diagonal in [v - k, v + k] and its cheap alignments stay within
+    // [v - 2k, v + 2k]: if that (plus the last-column candidates' diagonals) fits the banded kernel, the band
+    // is known without the exact Myers pass and the read skips k_refine.
+    {
+        int blo = hmin - 2 * k, bhi = hmax + 2 * k;
+        if (imax > 0) { blo = atr_min(blo, n - imax - k); bhi = atr_max(bhi, n - imin + k); }
+        res.dlo = blo;
+        res.width = bhi - blo + 1;
+    }
     int c0 = hmin - k - 1;
     int c1 = hmax + m + k + 1;
     if (imax > 0) { c0 = atr_min(c0, n - imax - k - 1); c1 = n; }
@@ -751,7 +763,10 @@ ATR_HD void k1f_read(const AdapterK1a& ad, const uint32_t* __restrict__ codes, i
         SaResult sr;
         sa_filter(ad, sa_peq, tail_peq, codes, lo, n, sr);
         if (sr.cls == 1) { have = true; hit.dlo = sr.dlo; hit.width = sr.width; hit.c0 = sr.c0; hit.c1 = sr.c1; }
-        else if (sr.cls == 2) have = myers_filter<WORD>(ad, peq, codes, lo, n, hit, sr.c0, sr.c1);
+        else if (sr.cls == 2) {
+            if (ad.band_ok && sr.width <= ATR_K1D_W) { have = true; hit.dlo = sr.dlo; hit.width = sr.width; hit.c0 = sr.c0; hit.c1 = sr.c1; }
+            else have = myers_filter<WORD>(ad, peq, codes, lo, n, hit, sr.c0, sr.c1);
+        }
     } else {
         have = myers_filter<WORD>(ad, peq, codes, lo, n, hit);
     }
