@@ -43,6 +43,8 @@ struct InsertDev {
 struct Cand { unsigned short j, cost; };
 struct GCellM { long long cost; int origin, matches; };
 
+ATR_HD int atr_imin(int a, int b) { return a < b ? a : b; }
+
 ATR_HD void im_clear(atr_match& m) {
     m.astart = m.astop = m.rstart = m.rstop = m.matches = m.errors = 0;
     m.adapter = -1; m.status = ATR_ST_NONE;
@@ -189,9 +191,13 @@ ATR_HD void insert_pair(const InsertDev& d, const P& pr, bool packed, int m, int
     const int k = d.k_by_len[m];
     int count = 0;
     for (int j = 1; j <= m; j++) {                                            // Appendix B of SURVEY.md
-        const int cost = pr.overlap_cost(j, k);
-        if (cost > k) continue;
-        if (j >= d.min_insert_overlap && cost <= (int)d.thr_ins[j]) {
+        // a candidate needs cost <= k AND cost <= floor(j * rate) (_align.pyx:722-728): scanning stops at the
+        // smaller bound, which for short overlaps is reached within the first word
+        const int bound = atr_imin(k, (int)d.thr_ins[j]);
+        if (j < d.min_insert_overlap) continue;
+        const int cost = pr.overlap_cost(j, bound);
+        if (cost > bound) continue;
+        {
             if (cost == 0 && j == m) { cand[0].j = (unsigned short)j; cand[0].cost = 0; count = 1; break; }   // [exact]
             cand[count].j = (unsigned short)j; cand[count].cost = (unsigned short)cost;
             count++;

@@ -515,8 +515,11 @@ ATR_HD void k1d_band(const AdapterK1a& ad, const uint32_t* __restrict__ codes, i
         win |= (unsigned long long)base_at(dlo + d) << (4 * (d + 1));
         if (dlo + d >= n) vm |= 0xFull << (4 * (d + 1));
     }
+    // Rows beyond R = n - dlo have their whole band right of the read end: pure forced-match propagation, which
+    // the candidate extraction below accounts for in closed form (partial adapters at the read end stop early).
+    const int R = atr_max(0, atr_min(m, n - dlo));
 #pragma unroll 1
-    for (int i = 1; i <= m; i++) {
+    for (int i = 1; i <= R; i++) {
         const int pnew = i + dlo + W - 2;
         win = (win >> 4) | ((unsigned long long)base_at(pnew) << (4 * (W - 1)));
         vm = (vm >> 4) | (pnew >= n ? (0xFull << (4 * (W - 1))) : 0ull);
@@ -543,7 +546,7 @@ ATR_HD void k1d_band(const AdapterK1a& ad, const uint32_t* __restrict__ codes, i
     Best bl;                                           // last-column candidates, merged after the row-m ones
     bl.ref_stop = m; bl.q_stop = n; bl.cost = m + n; bl.origin = 0; bl.matches = 0;
     best = bl;
-    if (stop_in_query) {                               // row m, columns in ascending order (:440-458)
+    if (stop_in_query && R == m) {                     // row m, columns in ascending order (:440-458)
 #pragma unroll
         for (int d = 0; d < W; d++) {
             const int j = m + dlo + d;
@@ -556,8 +559,8 @@ ATR_HD void k1d_band(const AdapterK1a& ad, const uint32_t* __restrict__ codes, i
         const int first_i = stop_in_ref ? 1 : m;
 #pragma unroll
         for (int d = W - 1; d >= 0; d--) {
-            const int j = m + dlo + d;
-            const int i = m - (j - n);                 // cell (i, n) arrived here after j - n forced matches
+            const int j = R + dlo + d;                 // B[d] = cell (R, j)
+            const int i = R - (j - n);                 // cell (i, n) arrived here after j - n forced matches
             const unsigned c = B[d];
             if (j >= n && i >= first_i && i >= 1 && k1a_cost(c) <= k)
                 consider(ad, bl, k1a_cost(c), atr_max(k1a_origin(c), 0), k1a_matches(c) - (j - n), i, n);
