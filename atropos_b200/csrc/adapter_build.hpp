@@ -137,7 +137,17 @@ inline void fill_k1a(const HostAdapter& h, const AtrTables& tb, int index, int r
     // K1f (Myers bit-vector filter + windowed DP) needs unit indel cost, a free start in the read and an
     // anchored start in the adapter (BACK / SUFFIX style flag sets)
     const bool start_in_ref = h.desc.flags & ATR_START_WITHIN_SEQ1, start_in_query = h.desc.flags & ATR_START_WITHIN_SEQ2;
-    a.fused_ok = h.k1a_ok && h.desc.indel_cost == 1 && start_in_query && !start_in_ref && !h.cmp_only && !h.need_find;
+    const bool stop_q = h.desc.flags & ATR_STOP_WITHIN_SEQ2;
+    // BACK / SUFFIX style (anchored start in the adapter), or FRONT / ANYWHERE style (free start in both, needs
+    // stop_in_query so that the first DP column is column 0)
+    a.fused_ok = h.k1a_ok && h.desc.indel_cost == 1 && start_in_query && (!start_in_ref || stop_q) && !h.cmp_only && !h.need_find;
+    // an alignment that starts inside the adapter and ends at (m, j) covers at most j + k adapter rows, so its
+    // cost is bounded by floor(min(m, j + k) * rate) and it needs j + k >= min_overlap rows
+    for (int j = 0; j <= ATR_K1A_MAXM; j++) {
+        const int jj = j < h.m ? j : h.m;
+        const int len = jj + h.k < h.m ? jj + h.k : h.m;
+        a.thrJ[j] = (short)(len >= h.desc.min_overlap ? (int)h.thr_mul[len] : -1);
+    }
     // a read code that no adapter row matches: 0 in AND mode, an unused letter code in ASCII mode
     a.nomatch = 0; a.band_ok = a.fused_ok;
     if (!a.and_mode) {
@@ -165,7 +175,7 @@ inline void fill_k1a(const HostAdapter& h, const AtrTables& tb, int index, int r
     a.sa_ok = 0; a.sa_rows = h.m < 32 ? h.m : 32; a.sa_start = 0; a.sa_end = 0;
     const bool stop_in_query = h.desc.flags & ATR_STOP_WITHIN_SEQ2;
     const int pieces = h.k + 1;
-    if (a.fused_ok && stop_in_query && pieces <= a.sa_rows && a.sa_rows / pieces >= 6) {
+    if (a.fused_ok && !start_in_ref && stop_in_query && pieces <= a.sa_rows && a.sa_rows / pieces >= 6) {
         a.sa_ok = 1;
         int row = 1;
         for (int pc = 0; pc < pieces; pc++) {

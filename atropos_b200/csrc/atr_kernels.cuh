@@ -465,7 +465,8 @@ __global__ void __launch_bounds__(128) k_band(const __grid_constant__ AdapterK1a
         int lo, n; bool esc;
         read_extent(len, win, sv.read, lo, n, esc);
         Best b;
-        k1d_band<AND_MODE, ATR_K1D_W>(ad, codes + woff[sv.read], lo, n, (int)sv.a, b);
+        if (ad.flags & ATR_START_WITHIN_SEQ1) k1d_band<AND_MODE, ATR_K1D_W, true>(ad, codes + woff[sv.read], lo, n, (int)sv.a, b);
+        else k1d_band<AND_MODE, ATR_K1D_W, false>(ad, codes + woff[sv.read], lo, n, (int)sv.a, b);
         finalize(ad, b, n, out + sv.read);
     }
 }

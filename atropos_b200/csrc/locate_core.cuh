@@ -287,6 +287,7 @@ ATR_HD bool myers_filter(const AdapterK1a& ad, const WORD* __restrict__ peq, con
     const int WB = (int)(8 * sizeof(WORD));
     const int sh = WB - m;                             // first real row sits at bit sh
     const bool stop_in_ref = ad.flags & ATR_STOP_WITHIN_SEQ1, stop_in_query = ad.flags & ATR_STOP_WITHIN_SEQ2;
+    const bool start_in_ref = ad.flags & ATR_START_WITHIN_SEQ1;
     int min_n = stop_in_query ? 0 : atr_max(0, n - m - k);
     const int n_full = n;
     if (cstart >= 0) { min_n = atr_max(min_n, cstart); n = atr_min(n, cstop); }
@@ -295,9 +296,21 @@ ATR_HD bool myers_filter(const AdapterK1a& ad, const WORD* __restrict__ peq, con
     st.Mv = 0;
     st.score = m;
     int jmin = 0x7fffffff, jmax = -1;
+    if (start_in_ref) {
+        // FRONT / ANYWHERE (:349-352 with min_n = 0): the first column costs 0 in every row, and an alignment
+        // may start inside the adapter, so the bound on D[m][j] depends on j (AdapterK1a.thrJ). Plain loop.
+        st.Pv = 0; st.score = 0;
+        for (int j = 1; j <= n; j++) {
+            const int pos = lo + j - 1;
+            myers_col(st, peq[(codes[pos >> 3] >> ((pos & 7) * 4)) & 15u]);
+            if (st.score <= (int)ad.thrJ[j < m ? j : m]) { jmin = atr_min(jmin, j); jmax = j; }
+        }
+        min_n = n;                                     // the loops below have nothing left to do
+    }
     int j = min_n;                                     // columns done so far
     int pos = lo + min_n;                              // packed position of the next column's base
     const int pend = lo + n;
+    if (start_in_ref) min_n = 0;
     // head: up to the next word boundary
     while (pos < pend && (pos & 7) != 0) {
         const unsigned qc = (codes[pos >> 3] >> ((pos & 7) * 4)) & 15u;
@@ -476,8 +489,12 @@ ATR_HD void sa_filter(const AdapterK1a& ad, const unsigned* __restrict__ sa_peq,
 // that matches nothing. With unit indel cost their cells reproduce the reference's first column exactly
 // (cost i, 0 matches); their origins may come out below 0 / below the true max(0, min_n - i) only where the
 // true origin is 0, hence the clamp at the end (these flag sets never have negative origins).
-template <bool AND_MODE, int W>
+template <bool AND_MODE, int W, bool SIR = false>
 ATR_HD void k1d_band(const AdapterK1a& ad, const uint32_t* __restrict__ codes, int lo, int n, int dlo, Best& best) {
+    // SIR (start_in_ref: FRONT / ANYWHERE adapters): the first DP column costs 0 in every row with origin -i
+    // (:349-352). Modelled by bases left of the read that match EVERYTHING under a free row 0: cell (i, 0) comes
+    // out as (cost 0, origin -i, matches i); the i surplus matches are taken off at the end (matches + min(origin, 0)),
+    // comparisons never look at matches. Negative origins are real here (the alignment starts inside the adapter).
     const int m = ad.m, k = ad.k;
     const bool stop_in_ref = ad.flags & ATR_STOP_WITHIN_SEQ1, stop_in_query = ad.flags & ATR_STOP_WITHIN_SEQ2;
     const int min_n = stop_in_query ? 0 : atr_max(0, n - m - k);
@@ -503,7 +520,7 @@ ATR_HD void k1d_band(const AdapterK1a& ad, const uint32_t* __restrict__ codes, i
     //    the reference's last-column candidates (:461-474) are read off row m at columns n+1.., no per-row tap.
     unsigned long long win = 0, vm = 0;
     auto base_at = [&](int p) -> unsigned {            // p = 0-based position in the (windowed) read
-        if (p < min_n) return nomatch;
+        if (p < min_n) return SIR ? 0u : nomatch;
         if (p >= n) return 0u;
         const int q = lo + p;
         unsigned c = (codes[q >> 3] >> ((q & 7) * 4)) & 15u;
@@ -513,7 +530,7 @@ ATR_HD void k1d_band(const AdapterK1a& ad, const uint32_t* __restrict__ codes, i
 #pragma unroll 1
     for (int d = 0; d < W - 1; d++) {                  // row 1 needs columns 1+dlo .. W+dlo -> positions dlo .. dlo+W-1
         win |= (unsigned long long)base_at(dlo + d) << (4 * (d + 1));
-        if (dlo + d >= n) vm |= 0xFull << (4 * (d + 1));
+        if (dlo + d >= n || (SIR && dlo + d < 0)) vm |= 0xFull << (4 * (d + 1));
     }
     // Rows beyond R = n - dlo have their whole band right of the read end: pure forced-match propagation, which
     // the candidate extraction below accounts for in closed form (partial adapters at the read end stop early).
@@ -522,7 +539,7 @@ ATR_HD void k1d_band(const AdapterK1a& ad, const uint32_t* __restrict__ codes, i
     for (int i = 1; i <= R; i++) {
         const int pnew = i + dlo + W - 2;
         win = (win >> 4) | ((unsigned long long)base_at(pnew) << (4 * (W - 1)));
-        vm = (vm >> 4) | (pnew >= n ? (0xFull << (4 * (W - 1))) : 0ull);
+        vm = (vm >> 4) | ((pnew >= n || (SIR && pnew < 0)) ? (0xFull << (4 * (W - 1))) : 0ull);
         const unsigned a = (unsigned)ad.code[i - 1];
         // per-nibble (mis)match flags for the whole row at once
         unsigned long long x;
@@ -551,8 +568,10 @@ ATR_HD void k1d_band(const AdapterK1a& ad, const uint32_t* __restrict__ codes, i
         for (int d = 0; d < W; d++) {
             const int j = m + dlo + d;
             const unsigned c = B[d];
-            if (j > min_n && j <= n && k1a_cost(c) <= k)
-                consider(ad, best, k1a_cost(c), atr_max(k1a_origin(c), 0), k1a_matches(c), m, j);
+            if (j > min_n && j <= n && k1a_cost(c) <= k) {
+                const int org = SIR ? k1a_origin(c) : atr_max(k1a_origin(c), 0);
+                consider(ad, best, k1a_cost(c), org, k1a_matches(c) + (SIR ? atr_min(org, 0) : 0), m, j);
+            }
         }
     }
     {                                                  // last column, rows ascending = virtual columns descending
@@ -562,8 +581,10 @@ ATR_HD void k1d_band(const AdapterK1a& ad, const uint32_t* __restrict__ codes, i
             const int j = R + dlo + d;                 // B[d] = cell (R, j)
             const int i = R - (j - n);                 // cell (i, n) arrived here after j - n forced matches
             const unsigned c = B[d];
-            if (j >= n && i >= first_i && i >= 1 && k1a_cost(c) <= k)
-                consider(ad, bl, k1a_cost(c), atr_max(k1a_origin(c), 0), k1a_matches(c) - (j - n), i, n);
+            if (j >= n && i >= first_i && i >= 1 && k1a_cost(c) <= k) {
+                const int org = SIR ? k1a_origin(c) : atr_max(k1a_origin(c), 0);
+                consider(ad, bl, k1a_cost(c), org, k1a_matches(c) - (j - n) + (SIR ? atr_min(org, 0) : 0), i, n);
+            }
         }
     }
     // the reference scans the last column after all in-loop candidates; replacement needs a strictly better key
@@ -774,7 +795,11 @@ ATR_HD void k1f_read(const AdapterK1a& ad, const uint32_t* __restrict__ codes, i
         have = myers_filter<WORD>(ad, peq, codes, lo, n, hit);
     }
     if (have) {
-        if (ad.band_ok && hit.width <= ATR_K1D_W) { if (path) *path = 1; k1d_band<AND_MODE, ATR_K1D_W>(ad, codes, lo, n, hit.dlo, b); }
+        if (ad.band_ok && hit.width <= ATR_K1D_W) {
+            if (path) *path = 1;
+            if (ad.flags & ATR_START_WITHIN_SEQ1) k1d_band<AND_MODE, ATR_K1D_W, true>(ad, codes, lo, n, hit.dlo, b);
+            else k1d_band<AND_MODE, ATR_K1D_W, false>(ad, codes, lo, n, hit.dlo, b);
+        }
         else { if (path) *path = 2; k1a_locate<AND_MODE>(ad, codes, lo, n, b, hit.c0, hit.c1); }
     }
     if (path && ad.sa_ok) *path += 10;                 // tests: 10 + x = went through the Shift-And pre-filter
