@@ -89,20 +89,19 @@ struct PackedPair {
     const uint32_t* S1;
     int stride;
     int m;
-    // Hamming(R[m-j:m], Q[0:j]), abandoned as soon as it exceeds k (the caller skips such offsets anyway:
-    // random offsets die after ~3 words instead of j/8)
-    ATR_HD int overlap_cost(int j, int k) const {
+    // Hamming(R[m-j:m], Q[0:j]) continued from whole word w0 (cost so far c0), abandoned once it exceeds `bound`
+    ATR_HD int overlap_cost(int j, int bound, int w0 = 0, unsigned c0 = 0) const {
         const int s = m - j, ws = s >> 3;
         const unsigned bs = (unsigned)(s & 7) * 4u;
         const int nfull = j >> 3;                       // whole words
-        unsigned cost = 0;
-        uint32_t lo = R[ws * stride];
-        int w = 0;
+        unsigned cost = c0;
+        int w = w0;
+        uint32_t lo = R[(ws + w) * stride];
         for (; w < nfull; w++) {
             const uint32_t hi = R[(ws + w + 1) * stride];
             cost += nib_mismatches(funnel_r(lo, hi, bs) ^ Q[w * stride]);
             lo = hi;
-            if ((int)cost > k) return (int)cost;
+            if ((int)cost > bound) return (int)cost;
         }
         if (j & 7) {
             const uint32_t hi = R[(ws + w + 1) * stride];
@@ -110,6 +109,52 @@ struct PackedPair {
             cost += nib_mismatches(x);
         }
         return (int)cost;
+    }
+
+    // Enumerate the overlap lengths j = 1..m in ascending order and call emit(j, cost) for every j >= min_overlap
+    // with cost <= min(k, thr[j]); emit returns false to stop (_align.pyx:722-745).
+    // Overlaps of >= 32 bases are handled in groups of 8 shifts that share the same word offset: the 5 words of
+    // rc(read2) a group needs and the first 4 words of read 1 stay in registers, the funnel shifts are static,
+    // and the first 16 or 32 bases are compared unconditionally (no per-word exit test, no shared-memory
+    // traffic). A random overlap is almost surely over its bound after that; only real overlaps continue with
+    // the word-by-word scan.
+    template <class F>
+    ATR_HD void scan(const InsertDev& d, int k, F&& emit) const {
+        const int jsmall = m < 31 ? m : 31;
+        for (int j = 1; j <= jsmall; j++) {
+            if (j < d.min_insert_overlap) continue;
+            const int bound = atr_imin(k, (int)d.thr_ins[j]);
+            const int cost = overlap_cost(j, bound);
+            if (cost <= bound && !emit(j, cost)) return;
+        }
+        if (m < 32) return;
+        const uint32_t q0 = Q[0], q1 = Q[stride], q2 = Q[2 * stride], q3 = Q[3 * stride];
+        int g = (m - 32) >> 3;                         // word offset of the first (shortest) overlap handled here
+        int bstart = (m - 32) & 7;
+        uint32_t r0 = R[g * stride], r1 = R[(g + 1) * stride], r2 = R[(g + 2) * stride], r3 = R[(g + 3) * stride],
+                 r4 = R[(g + 4) * stride];
+        for (; g >= 0; g--) {
+#pragma unroll
+            for (int b = 7; b >= 0; b--) {
+                if (b > bstart) continue;
+                const int j = m - (8 * g + b);
+                const int tj = (int)d.thr_ins[j];
+                const int bound = atr_imin(k, tj);
+                unsigned cost = nib_mismatches(funnel_r(r0, r1, 4u * b) ^ q0) + nib_mismatches(funnel_r(r1, r2, 4u * b) ^ q1);
+                int wdone = 2;
+                if (tj > 6) {                          // long overlaps tolerate more mismatches: look at 32 bases
+                    cost += nib_mismatches(funnel_r(r2, r3, 4u * b) ^ q2) + nib_mismatches(funnel_r(r3, r4, 4u * b) ^ q3);
+                    wdone = 4;
+                }
+                if ((int)cost <= bound && j >= d.min_insert_overlap) {
+                    const int full = overlap_cost(j, bound, wdone, cost);
+                    if (full <= bound && !emit(j, full)) return;
+                }
+            }
+            bstart = 7;
+            r4 = r3; r3 = r2; r2 = r1; r1 = r0;
+            if (g > 0) r0 = R[(g - 1) * stride];
+        }
     }
     ATR_HD unsigned ov1(int p) const { return (S1[p >> 3] >> ((p & 7) * 4)) & 15u; }
     ATR_HD unsigned ov2(int p) const { return (S2[p >> 3] >> ((p & 7) * 4)) & 15u; }
@@ -125,6 +170,15 @@ struct BytePair {
         int cost = 0;
         for (int t = 0; t < j && cost <= k; t++) cost += (comp[s2[j - 1 - t]] != s1[t]);      // ref[m-j+t] = comp[s2[j-1-t]]
         return cost;
+    }
+    template <class F>
+    ATR_HD void scan(const InsertDev& d, int k, F&& emit) const {
+        for (int j = 1; j <= m; j++) {
+            if (j < d.min_insert_overlap) continue;
+            const int bound = atr_imin(k, (int)d.thr_ins[j]);
+            const int cost = overlap_cost(j, bound);
+            if (cost <= bound && !emit(j, cost)) return;
+        }
     }
     ATR_HD unsigned ov1(int p) const { return ov_tab[s1[p]]; }
     ATR_HD unsigned ov2(int p) const { return ov_tab[s2[p]]; }
@@ -190,20 +244,13 @@ ATR_HD void insert_pair(const InsertDev& d, const P& pr, bool packed, int m, int
     if (m <= 0) return;
     const int k = d.k_by_len[m];
     int count = 0;
-    for (int j = 1; j <= m; j++) {                                            // Appendix B of SURVEY.md
-        // a candidate needs cost <= k AND cost <= floor(j * rate) (_align.pyx:722-728): scanning stops at the
-        // smaller bound, which for short overlaps is reached within the first word
-        const int bound = atr_imin(k, (int)d.thr_ins[j]);
-        if (j < d.min_insert_overlap) continue;
-        const int cost = pr.overlap_cost(j, bound);
-        if (cost > bound) continue;
-        {
-            if (cost == 0 && j == m) { cand[0].j = (unsigned short)j; cand[0].cost = 0; count = 1; break; }   // [exact]
-            cand[count].j = (unsigned short)j; cand[count].cost = (unsigned short)cost;
-            count++;
-            if (count >= ATR_MAX_CAND) break;
-        }
-    }
+    // Appendix B of SURVEY.md: a candidate needs cost <= k AND cost <= floor(j * rate) (_align.pyx:722-728)
+    pr.scan(d, k, [&](int j, int cost) -> bool {
+        if (cost == 0 && j == m) { cand[0].j = (unsigned short)j; cand[0].cost = 0; count = 1; return false; }   // [exact]
+        cand[count].j = (unsigned short)j; cand[count].cost = (unsigned short)cost;
+        count++;
+        return count < ATR_MAX_CAND;
+    });
     // (the reference may append the j == m candidate a second time, :746-763; a duplicate cannot change the outcome)
     if (count == 0) return;
     // random-match-probability filter, then candidates in order of probability (stable) :353-375
