@@ -443,9 +443,13 @@ int atr_locate_batch_host(atr_ctx* ctx, const atr_adapterset* set, const uint8_t
         int64_t c1 = std::min(n, c0 + max_reads);
         while (c1 > c0 + 1 && offsets[c1] - offsets[c0] > max_bytes) c1 = c0 + (c1 - c0) / 2;
         const int64_t cn = c1 - c0, bytes = offsets[c1] - offsets[c0];
-        for (int64_t i = c0; i < c1; i++)
-            if (offsets[i + 1] - offsets[i] > ATR_MAX_READ || offsets[i + 1] < offsets[i])
-                return fail(ctx, ATR_E_LIMIT, "read longer than 32767 nt (or offsets not monotone)");
+        bool uniform = true;
+        const int64_t len0 = offsets[c0 + 1] - offsets[c0];
+        for (int64_t i = c0; i < c1; i++) {
+            const int64_t li = offsets[i + 1] - offsets[i];
+            if (li > ATR_MAX_READ || li < 0) return fail(ctx, ATR_E_LIMIT, "read longer than 32767 nt (or offsets not monotone)");
+            uniform = uniform && li == len0;
+        }
         Slot& s = ctx->slot[which];
         int rc = s.ascii.ensure((size_t)bytes + 16);
         if (!rc) rc = s.offsets.ensure((size_t)(cn + 1) * sizeof(int64_t));
@@ -456,7 +460,12 @@ int atr_locate_batch_host(atr_ctx* ctx, const atr_adapterset* set, const uint8_t
         if (!rc && win) rc = s.win.ensure((size_t)cn * 2 * sizeof(uint16_t));
         if (rc) return fail(ctx, rc, "out of device memory (host entry point staging)");
         if (bytes) CU(cudaMemcpyAsync(s.ascii.p, ascii + offsets[c0], (size_t)bytes, cudaMemcpyHostToDevice, s.stream));
-        CU(cudaMemcpyAsync(s.offsets.p, offsets + c0, (size_t)(cn + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s.stream));
+        if (uniform) {      // all reads of the chunk have one length: build the offsets on the device
+            k_make_offsets<<<grid_for(cn + 1, 256), 256, 0, s.stream>>>(s.offsets.as<int64_t>(), cn, offsets[c0], len0);
+            LAUNCHED(ctx);
+        } else {
+            CU(cudaMemcpyAsync(s.offsets.p, offsets + c0, (size_t)(cn + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s.stream));
+        }
         if (win) CU(cudaMemcpyAsync(s.win.p, win + 2 * c0, (size_t)cn * 2 * sizeof(uint16_t), cudaMemcpyHostToDevice, s.stream));
         rc = pack_on_stream(ctx, s.stream, s.counts, s.scan_tmp, s.ascii.as<uint8_t>(), s.offsets.as<int64_t>(), offsets[c0], cn,
                             fold_case, s.codes.as<uint32_t>(), s.woff.as<uint32_t>(), s.len.as<uint16_t>());

@@ -26,6 +26,13 @@ struct Best {
 ATR_HD int atr_min(int a, int b) { return a < b ? a : b; }
 ATR_HD int atr_max(int a, int b) { return a > b ? a : b; }
 ATR_HD unsigned atr_umin(unsigned a, unsigned b) { return a < b ? a : b; }
+ATR_HD int atr_msb(unsigned x) {          // index of the highest set bit (x != 0)
+#if defined(__CUDA_ARCH__)
+    return 31 - __clz((int)x);
+#else
+    return 31 - __builtin_clz(x);
+#endif
+}
 ATR_HD int atr_ctz(unsigned x) {
 #if defined(__CUDA_ARCH__)
     return __ffs((int)x) - 1;
@@ -401,11 +408,11 @@ ATR_HD void sa_filter(const AdapterK1a& ad, const unsigned* __restrict__ sa_peq,
             Ss[t] = St;
             any |= St;
         }
-        if (any & E) {                                 // rare: some piece ended inside this word
+        if (any & E) {                                 // some piece ended inside this word (a few lanes per warp)
 #pragma unroll
             for (int t = 0; t < 8; t++) {
-                unsigned hb = Ss[t] & E;
-                while (hb) { const int b = atr_ctz(hb); hb &= hb - 1; const int v = j + t + 1 - (b + 1); hmin = atr_min(hmin, v); hmax = atr_max(hmax, v); }
+                const unsigned hb = Ss[t] & E;         // v = column - row: smallest for the highest row, largest for the lowest
+                if (hb) { hmin = atr_min(hmin, j + t - atr_msb(hb)); hmax = atr_max(hmax, j + t - atr_ctz(hb)); }
             }
         }
         j += 8; pos += 8;

@@ -331,7 +331,7 @@ def run_ours(args):
         "dtype": "u32 packed integer DP (4-bit bases)", "data": "synthetic",
         "config": dict(CONFIG, reads_per_gpu=n, adapter_hit_fraction=round(hit_frac, 4)),
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": "M reads/s", "h2d_bytes_per_step": int(n * L + 8 * (n + 1)),
+        "e2e": {"value": e2e_value, "unit": "M reads/s", "h2d_bytes_per_step": int(n * L),      # fixed-length batch: the offsets are rebuilt on the device
                 "d2h_bytes_per_step": int(16 * n), "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
                 "api": "atr_locate_batch_host (Adapter.match_to_batch)"},
         "gpu_launches": int(launches),
