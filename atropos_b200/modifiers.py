@@ -81,8 +81,13 @@ class InsertAdapterCutter(object):
         skipped = (l1 < self.min_insert_overlap) | (l2 < self.min_insert_overlap)
         ins["insert"]["status"][skipped] = _abi.ATR_ST_NONE
         need = (ins["insert"]["status"] == _abi.ATR_ST_NONE) & ~skipped
-        fb1 = self.adapter1.match_to_batch((a1, o1))
-        fb2 = self.adapter2.match_to_batch((a2, o2))
+        # the per-read fallback only runs where it is needed: everything else gets an empty window (no DP work)
+        win1 = np.zeros((len(l1), 2), dtype=np.uint16)
+        win2 = np.zeros((len(l2), 2), dtype=np.uint16)
+        win1[need, 1] = l1[need]
+        win2[need, 1] = l2[need]
+        fb1 = self.adapter1.match_to_batch((a1, o1), win=win1)
+        fb2 = self.adapter2.match_to_batch((a2, o2), win=win2)
         fb1["status"][~need] = _abi.ATR_ST_NONE
         fb2["status"][~need] = _abi.ATR_ST_NONE
         return ins, fb1, fb2, need

@@ -372,3 +372,48 @@ def test_full_size_properties():
     full = (res3["errors"] == 0) & (res3["matches"] == 34)
     assert np.all(res3["rstart"][full] <= pos[full])        # leftmost exact occurrence (an earlier one can exist by design)
     assert full.mean() > 0.999
+
+
+def test_insert_adapter_cutter_matching_half():
+    """InsertAdapterCutter.__call__ up to the point where Match objects exist (modifiers.py:391-406): insert match
+    first, per-read adapter match (insert-mode adapters: max_rmp 1e-6, overlap 1, indel cost 3; trim/cli.py:667-684)
+    only for the pairs without one."""
+    from atropos_b200 import _abi, synth
+    from atropos_b200.adapters import Adapter, BACK
+    from atropos_b200.align import InsertAligner
+    from atropos_b200.modifiers import InsertAdapterCutter
+    from atropos_b200.util import RandomMatchProbability
+    n, L = 6000, 150
+    r1, r2 = synth.synth_pe(n, L, seed=synth.seed_for(3, 7), device="cpu", sub=0.03)
+    reads1 = [bytes(x).decode() for x in r1.numpy()]
+    reads2 = [bytes(x).decode() for x in r2.numpy()]
+    reads1[5], reads2[5] = "", "ACGT"                      # shorter than min_insert_overlap -> skipped
+    rmp = RandomMatchProbability()
+    kw = dict(max_error_rate=0.1, min_overlap=1, indel_cost=3, match_probability=rmp, max_rmp=1e-6)
+    a1, a2 = Adapter(T1, BACK, **kw), Adapter(T2, BACK, **kw)
+    ikw = dict(max_insert_mismatch_frac=0.1, max_adapter_mismatch_frac=0.1)
+    cutter = InsertAdapterCutter(a1, a2, InsertAligner(T1, T2, **ikw))
+    ins, fb1, fb2, need = cutter.match_batch(reads1, reads2)
+    o_rmp = oracle.RandomMatchProbability()
+    okw = dict(max_error_rate=0.1, min_overlap=1, indel_cost=3, match_probability=o_rmp, max_rmp=1e-6)
+    o1, o2 = oracle.OracleAdapter(T1, oracle.BACK, **okw), oracle.OracleAdapter(T2, oracle.BACK, **okw)
+    oia = oracle.OracleInsertAligner(T1, T2, **ikw)
+    n_fb = n_ins = 0
+    for i in range(n):
+        if len(reads1[i]) < 1 or len(reads2[i]) < 1:
+            assert ins[i]["insert"]["status"] == _abi.ATR_ST_NONE and not need[i]
+            continue
+        exp = oia.match_insert(reads1[i], reads2[i])
+        got = InsertAligner.result_from_record(ins[i])
+        if exp is not None:
+            n_ins += 1
+            assert got is not None and got[0] == exp[0] and not need[i]
+            assert fb1[i]["status"] == _abi.ATR_ST_NONE and fb2[i]["status"] == _abi.ATR_ST_NONE
+        else:
+            assert got is None and need[i]
+            for rec, orc_ad, read in ((fb1[i], o1, reads1[i]), (fb2[i], o2, reads2[i])):
+                e = orc_ad.match_to(read)
+                g = None if rec["status"] == _abi.ATR_ST_NONE else _tup(rec)
+                assert g == (None if e is None else e[:6]), (i, read)
+                n_fb += e is not None
+    assert n_ins > 1500 and n_fb > 20
