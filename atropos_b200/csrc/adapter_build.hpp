@@ -170,6 +170,9 @@ inline void fill_k1a(const HostAdapter& h, const AtrTables& tb, int index, int r
         }
         a.peq[c] = bits;
     }
+    for (int w = 0; w < ATR_K1A_MAXM / 8; w++) a.apack[w] = 0;
+    for (int i = 0; i < h.m && i < ATR_K1A_MAXM; i++) a.apack[i >> 3] |= ((unsigned)a.code[i] & 15u) << (4 * (i & 7));
+    a.exact_ok = !(a.and_mode && a.q_single_only) && h.m >= h.desc.min_overlap;
     // Shift-And pieces over the first min(m, 32) rows: k+1 pieces, each at least 6 rows (shorter pieces hit at
     // random too often to be a filter); needs row-m candidates to be reported inside the loop (stop_in_query)
     a.sa_ok = 0; a.sa_rows = h.m < 32 ? h.m : 32; a.sa_start = 0; a.sa_end = 0;

@@ -405,6 +405,10 @@ __global__ void __launch_bounds__(ATR_K1F_THREADS) k_filter_sa(const __grid_cons
             Best b;
             b.ref_stop = ad.m; b.q_stop = n; b.cost = ad.m + n; b.origin = 0; b.matches = 0;
             finalize(ad, b, n, out + r);
+        } else if (sr.cls == 3) {                                   // verbatim occurrence: result known (str.find shortcut)
+            Best b;
+            b.matches = ad.m; b.cost = 0; b.origin = sr.v; b.ref_stop = ad.m; b.q_stop = sr.v + ad.m;
+            finalize(ad, b, n, out + r);
         } else if (sr.cls == 1) {
             if (ad.band_ok && sr.width <= ATR_K1D_W) { to_narrow = true; sv.a = (short)sr.dlo; }
             else { to_wide = true; sv.a = (short)sr.c0; sv.b = (short)sr.c1; }

@@ -26,6 +26,13 @@ struct Best {
 ATR_HD int atr_min(int a, int b) { return a < b ? a : b; }
 ATR_HD int atr_max(int a, int b) { return a > b ? a : b; }
 ATR_HD unsigned atr_umin(unsigned a, unsigned b) { return a < b ? a : b; }
+ATR_HD uint32_t funnel_r32(uint32_t lo, uint32_t hi, unsigned shift) {   // (hi:lo) >> shift, shift in [0,32)
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, shift);
+#else
+    return shift == 0 ? lo : ((lo >> shift) | (hi << (32 - shift)));
+#endif
+}
 ATR_HD int atr_msb(unsigned x) {          // index of the highest set bit (x != 0)
 #if defined(__CUDA_ARCH__)
     return 31 - __clz((int)x);
@@ -376,10 +383,14 @@ ATR_HD bool myers_filter(const AdapterK1a& ad, const WORD* __restrict__ peq, con
 //   0  nothing can match                       -> the read is finished (no match)
 //   1  no piece hit, but last-column candidates -> band known exactly (dlo / width, or window if too wide)
 //   2  piece hit(s)                             -> exact 64/32-bit Myers over columns [c0, c1] decides (k_refine)
+//   3  all hits on one diagonal v and the whole adapter occurs there verbatim -> the result is known: this is
+//      the reference's own str.find shortcut (adapters/__init__.py:351-367); an exact occurrence has the
+//      maximal number of matches at cost 0, and being the only diagonal with hits it is the leftmost one
 struct SaResult {
     int cls;
     int dlo, width;      // class 1
     int c0, c1;          // class 1 (window form) and class 2
+    int v;               // class 3: read position of the exact occurrence
 };
 
 ATR_HD void sa_filter(const AdapterK1a& ad, const unsigned* __restrict__ sa_peq, const unsigned* __restrict__ tail_peq,
@@ -458,6 +469,30 @@ ATR_HD void sa_filter(const AdapterK1a& ad, const unsigned* __restrict__ sa_peq,
     }
     const bool have_hit = hmax != -0x7fffffff;
     if (!have_hit && imax == 0) { res.cls = 0; return; }
+    if (have_hit && hmin == hmax && ad.exact_ok && hmin >= 0 && hmin + m <= n) {
+        // verify the whole adapter at read position v, 8 bases per step
+        const int q = lo + hmin;
+        const unsigned sh = (unsigned)(q & 7) * 4u;
+        bool same = true;
+        for (int w = 0; w * 8 < m; w++) {
+            const int rows = atr_min(8, m - 8 * w);                       // adapter rows in this word
+            const uint32_t w0 = codes[(q >> 3) + w];
+            const bool need_hi = ((q & 7) + rows) > 8;                       // the rows spill into the next read word
+            const uint32_t w1 = need_hi ? codes[(q >> 3) + w + 1] : 0u;
+            const uint32_t rd = funnel_r32(w0, w1, sh);
+            const uint32_t mask = rows == 8 ? 0xFFFFFFFFu : ((1u << (4 * rows)) - 1u);
+            uint32_t x;
+            if (ad.and_mode) {                                               // every nibble must share a bit
+                x = rd & ad.apack[w];
+                x |= x >> 1; x |= x >> 2;
+                x = (~x) & 0x11111111u & mask;
+            } else {
+                x = (rd ^ ad.apack[w]) & mask;
+            }
+            same = same && x == 0u;
+        }
+        if (same) { res.cls = 3; res.v = hmin; return; }
+    }
     if (!have_hit) {
         res.cls = 1;
         res.dlo = (n - imax) - k;
@@ -793,7 +828,11 @@ ATR_HD void k1f_read(const AdapterK1a& ad, const uint32_t* __restrict__ codes, i
         }
         SaResult sr;
         sa_filter(ad, sa_peq, tail_peq, codes, lo, n, sr);
-        if (sr.cls == 1) { have = true; hit.dlo = sr.dlo; hit.width = sr.width; hit.c0 = sr.c0; hit.c1 = sr.c1; }
+        if (sr.cls == 3) {
+            b.matches = ad.m; b.cost = 0; b.origin = sr.v; b.ref_stop = ad.m; b.q_stop = sr.v + ad.m;
+            if (path) *path = 5;
+        }
+        else if (sr.cls == 1) { have = true; hit.dlo = sr.dlo; hit.width = sr.width; hit.c0 = sr.c0; hit.c1 = sr.c1; }
         else if (sr.cls == 2) {
             if (ad.band_ok && sr.width <= ATR_K1D_W) { have = true; hit.dlo = sr.dlo; hit.width = sr.width; hit.c0 = sr.c0; hit.c1 = sr.c1; }
             else have = myers_filter<WORD>(ad, peq, codes, lo, n, hit, sr.c0, sr.c1);
