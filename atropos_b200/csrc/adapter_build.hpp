@@ -175,7 +175,7 @@ inline void fill_k1a(const HostAdapter& h, const AtrTables& tb, int index, int r
     a.exact_ok = !(a.and_mode && a.q_single_only) && h.m >= h.desc.min_overlap;
     // Shift-And pieces over the first min(m, 32) rows: k+1 pieces, each at least 6 rows (shorter pieces hit at
     // random too often to be a filter); needs row-m candidates to be reported inside the loop (stop_in_query)
-    a.sa_ok = 0; a.sa_rows = h.m < 32 ? h.m : 32; a.sa_start = 0; a.sa_end = 0;
+    a.sa_ok = 0; a.sa_rows = h.m < 32 ? h.m : 32; a.sa_start = 0; a.sa_end = 0; a.tail_gate_ok = 0; a.tail_mask = 0;
     const bool stop_in_query = h.desc.flags & ATR_STOP_WITHIN_SEQ2;
     const int pieces = h.k + 1;
     if (a.fused_ok && !start_in_ref && stop_in_query && pieces <= a.sa_rows && a.sa_rows / pieces >= 6) {
@@ -186,6 +186,27 @@ inline void fill_k1a(const HostAdapter& h, const AtrTables& tb, int index, int r
             a.sa_start |= 1u << (row - 1);
             a.sa_end |= 1u << (row + len - 2);
             row += len;
+        }
+        // Gate for the exact tail pass. A last-column candidate (i, n), i <= sa_rows, has e <= thr_mul[i] errors
+        // over rows 1..i, which contain c(i) complete pieces. e < c: a complete piece is verbatim (a hit near the
+        // read end). e == c: either that, or every complete piece is broken and the rows after them -- the begun
+        // piece -- are verbatim up to column n, which the automaton shows as bit i-1 of its final state.
+        // e > c (or e == c with no begun piece): no cheap certificate -> the tail pass always runs.
+        const bool stop_in_ref = h.desc.flags & ATR_STOP_WITHIN_SEQ1;
+        a.tail_gate_ok = 1; a.tail_mask = 0;
+        const int first = stop_in_ref ? 1 : h.m;
+        for (int i = 1; i <= a.sa_rows; i++) {
+            if (i < first || i < h.desc.min_overlap) continue;
+            int c = 0, end_c = 0, r = 1;
+            for (int pc = 0; pc < pieces; pc++) {
+                const int len = a.sa_rows / pieces + (pc < a.sa_rows % pieces ? 1 : 0);
+                if (r + len - 1 <= i) { c++; end_c = r + len - 1; }
+                r += len;
+            }
+            const int e = (int)h.thr_mul[i];
+            if (e < c) continue;
+            if (e == c && i > end_c) { a.tail_mask |= 1u << (i - 1); continue; }
+            a.tail_gate_ok = 0;
         }
     }
 }

@@ -317,7 +317,8 @@ __global__ void __launch_bounds__(ATR_K1F_THREADS) k_filter(const __grid_constan
     }
     if (use_tma) mbar_wait(&s_bar, 0);
     else __syncthreads();
-    const uint32_t* rd = fits ? (s_tile + (wr - a_begin)) : (codes + wr);
+    const uint32_t* rd = codes + wr;                       // generic pointer: shared tile or global
+    if (fits) rd = s_tile + (wr - a_begin);
     bool to_narrow = false, to_wide = false;
     Survivor sv;
     sv.read = (uint32_t)r; sv.a = 0; sv.b = 0;
@@ -342,6 +343,14 @@ __global__ void __launch_bounds__(ATR_K1F_THREADS) k_filter(const __grid_constan
 // 32-bit Myers over the last columns for the partial matches at the read end. Reads with a piece hit go to
 // k_refine (exact Myers on the few columns around the hits), which feeds the same narrow / wide lists.
 // ---------------------------------------------------------------------------------------------
+// The tail pass is a separate (non-inlined) device function: it is executed by few, compacted warps and must
+// not inflate the register allocation of the Shift-And scan that every thread runs.
+__device__ __noinline__ int sa_tail_packed(const AdapterK1a* ad, const unsigned* tail_peq, const uint32_t* rd, int lo, int n) {
+    int imin, imax;
+    sa_tail(*ad, tail_peq, rd, lo, n, imin, imax);
+    return (imin << 16) | imax;
+}
+
 template <bool AND_MODE>
 __global__ void __launch_bounds__(ATR_K1F_THREADS) k_filter_sa(const __grid_constant__ AdapterK1a ad,
         const uint32_t* __restrict__ codes, const uint32_t* __restrict__ woff, const uint16_t* __restrict__ len,
@@ -350,6 +359,9 @@ __global__ void __launch_bounds__(ATR_K1F_THREADS) k_filter_sa(const __grid_cons
     __shared__ __align__(128) uint32_t s_tile[ATR_K1F_TILE_WORDS];
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ unsigned s_sa_peq[16], s_tail_peq[16];
+    __shared__ int s_im[ATR_K1F_THREADS];
+    __shared__ unsigned short s_tail_list[ATR_K1F_THREADS];
+    __shared__ int s_tail_count;
 
     const int tid = threadIdx.x;
     const int64_t t0 = (int64_t)blockIdx.x * ATR_K1F_THREADS;
@@ -366,6 +378,7 @@ __global__ void __launch_bounds__(ATR_K1F_THREADS) k_filter_sa(const __grid_cons
         s_sa_peq[tid] = low;
         s_tail_peq[tid] = sh32 ? ((low << sh32) | ((1u << sh32) - 1u)) : low;
     }
+    if (tid == 0) s_tail_count = 0;
     if (tid == 0 && use_tma) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar)) : "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -394,20 +407,49 @@ __global__ void __launch_bounds__(ATR_K1F_THREADS) k_filter_sa(const __grid_cons
     }
     if (use_tma) mbar_wait(&s_bar, 0);
     else __syncthreads();
-    const uint32_t* rd = fits ? (s_tile + (wr - a_begin)) : (codes + wr);
+    const uint32_t* rd = codes + wr;                       // generic pointer: shared tile or global
+    if (fits) rd = s_tile + (wr - a_begin);
     bool to_narrow = false, to_wide = false, to_refine = false;
     Survivor sv;
     sv.read = (uint32_t)r; sv.a = 0; sv.b = 0;
+    // ---- phase A (every thread): Shift-And scan, exact-occurrence shortcut, does this read need the tail pass? ----
+    int hmin = 0x7fffffff, hmax = -0x7fffffff;
+    bool exact = false, need_tail = false;
     if (mine && !routed) {
+        unsigned st_final;
+        sa_scan(ad, s_sa_peq, rd, lo, n, hmin, hmax, st_final);
+        exact = sa_exact(ad, rd, lo, n, hmin, hmax);
+        if (exact) {                                                // verbatim occurrence: result known (str.find shortcut)
+            Best b;
+            b.matches = ad.m; b.cost = 0; b.origin = hmin; b.ref_stop = ad.m; b.q_stop = hmin + ad.m;
+            finalize(ad, b, n, out + r);
+        } else {
+            need_tail = sa_need_tail(ad, n, hmax, st_final);
+        }
+    }
+    // ---- phase B: the exact 32-bit Myers over the read tail, only for the reads that can have a partial match at
+    // the end (~20 %), compacted so that the warps running it are full ----
+    s_im[tid] = 0;
+    if (need_tail) s_tail_list[atomicAdd(&s_tail_count, 1)] = (unsigned short)tid;
+    __syncthreads();
+    for (int e = tid; e < s_tail_count; e += ATR_K1F_THREADS) {
+        const int t2 = s_tail_list[e];
+        int lo2, n2; bool esc2;
+        read_extent(len, win, t0 + t2, lo2, n2, esc2);
+        const uint32_t wr2 = woff[t0 + t2];
+        const uint32_t* rd2 = codes + wr2;
+        if (fits) rd2 = s_tile + (wr2 - a_begin);
+        s_im[t2] = sa_tail_packed(&ad, s_tail_peq, rd2, lo2, n2);
+    }
+    __syncthreads();
+    // ---- phase C (every thread): classify ----
+    if (mine && !routed && !exact) {
+        const int im = s_im[tid];
         SaResult sr;
-        sa_filter(ad, s_sa_peq, s_tail_peq, rd, lo, n, sr);
+        sa_classify(ad, lo, n, hmin, hmax, im >> 16, im & 0xFFFF, sr);
         if (sr.cls == 0) {
             Best b;
             b.ref_stop = ad.m; b.q_stop = n; b.cost = ad.m + n; b.origin = 0; b.matches = 0;
-            finalize(ad, b, n, out + r);
-        } else if (sr.cls == 3) {                                   // verbatim occurrence: result known (str.find shortcut)
-            Best b;
-            b.matches = ad.m; b.cost = 0; b.origin = sr.v; b.ref_stop = ad.m; b.q_stop = sr.v + ad.m;
             finalize(ad, b, n, out + r);
         } else if (sr.cls == 1) {
             if (ad.band_ok && sr.width <= ATR_K1D_W) { to_narrow = true; sv.a = (short)sr.dlo; }

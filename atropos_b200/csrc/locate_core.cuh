@@ -393,21 +393,20 @@ struct SaResult {
     int v;               // class 3: read position of the exact occurrence
 };
 
-ATR_HD void sa_filter(const AdapterK1a& ad, const unsigned* __restrict__ sa_peq, const unsigned* __restrict__ tail_peq,
-                      const uint32_t* __restrict__ codes, int lo, int n, SaResult& res) {
-    const int m = ad.m, k = ad.k, mp = ad.sa_rows;
-    const bool stop_in_ref = ad.flags & ATR_STOP_WITHIN_SEQ1;
+// (a) Shift-And over all columns: range of hit diagonals and the automaton's final state
+ATR_HD void sa_scan(const AdapterK1a& ad, const unsigned* __restrict__ sa_peq, const uint32_t* __restrict__ codes, int lo, int n,
+                    int& hmin, int& hmax, unsigned& st_final) {
     const unsigned S0 = ad.sa_start, E = ad.sa_end;
     unsigned St = 0;
-    int hmin = 0x7fffffff, hmax = -0x7fffffff;       // over hits: (column of the piece end) - (row of the piece end)
+    hmin = 0x7fffffff; hmax = -0x7fffffff;           // over hits: (column of the piece end) - (row of the piece end)
     int j = 0, pos = lo;
     const int pend = lo + n;
     while (pos < pend && (pos & 7) != 0) {
         const unsigned qc = (codes[pos >> 3] >> ((pos & 7) * 4)) & 15u;
         St = ((St << 1) | S0) & sa_peq[qc];
         j++; pos++;
-        unsigned hb = St & E;
-        while (hb) { const int b = atr_ctz(hb); hb &= hb - 1; const int v = j - (b + 1); hmin = atr_min(hmin, v); hmax = atr_max(hmax, v); }
+        const unsigned hb = St & E;
+        if (hb) { hmin = atr_min(hmin, j - 1 - atr_msb(hb)); hmax = atr_max(hmax, j - 1 - atr_ctz(hb)); }
     }
     while (pos + 8 <= pend) {
         const uint32_t w = codes[pos >> 3];
@@ -433,66 +432,89 @@ ATR_HD void sa_filter(const AdapterK1a& ad, const unsigned* __restrict__ sa_peq,
         for (int t = 0; pos < pend; t++) {
             St = ((St << 1) | S0) & sa_peq[(w >> (4 * t)) & 15u];
             j++; pos++;
-            unsigned hb = St & E;
-            while (hb) { const int b = atr_ctz(hb); hb &= hb - 1; const int v = j - (b + 1); hmin = atr_min(hmin, v); hmax = atr_max(hmax, v); }
+            const unsigned hb = St & E;
+            if (hb) { hmin = atr_min(hmin, j - 1 - atr_msb(hb)); hmax = atr_max(hmax, j - 1 - atr_ctz(hb)); }
         }
     }
-    // tail: exact D[i][n] for rows i <= mp from a 32-bit Myers over the last mp + k columns (rows left-aligned)
-    int imin = 0, imax = 0;
-    if (stop_in_ref || m <= mp) {
-        const int sh = 32 - mp;
-        MyersState<unsigned> st;
-        st.Pv = (sh == 0) ? ~0u : (~0u << sh);
-        st.Mv = 0; st.score = mp;
-        // start on a word boundary at or before column n - mp - k (an earlier start is always safe)
-        int p = atr_max(lo, (lo + atr_max(0, n - mp - k)) & ~7);
-        while (p < pend && (p & 7) != 0) { myers_col(st, tail_peq[(codes[p >> 3] >> ((p & 7) * 4)) & 15u]); p++; }
-        while (p + 8 <= pend) {
-            const uint32_t w = codes[p >> 3];
-#pragma unroll
-            for (int t = 0; t < 8; t++) myers_col(st, tail_peq[(w >> (4 * t)) & 15u]);
-            p += 8;
+    st_final = St;
+}
+
+// (b) the reference's str.find shortcut: all hits on one diagonal v and the whole adapter verbatim there
+ATR_HD bool sa_exact(const AdapterK1a& ad, const uint32_t* __restrict__ codes, int lo, int n, int hmin, int hmax) {
+    const int m = ad.m;
+    if (!(hmax != -0x7fffffff && hmin == hmax && ad.exact_ok && hmin >= 0 && hmin + m <= n)) return false;
+    const int q = lo + hmin;
+    const unsigned sh = (unsigned)(q & 7) * 4u;
+    bool same = true;
+    for (int w = 0; w * 8 < m; w++) {                  // 8 bases per step
+        const int rows = atr_min(8, m - 8 * w);        // adapter rows in this word
+        const uint32_t w0 = codes[(q >> 3) + w];
+        const bool need_hi = ((q & 7) + rows) > 8;     // the rows spill into the next read word
+        const uint32_t w1 = need_hi ? codes[(q >> 3) + w + 1] : 0u;
+        const uint32_t rd = funnel_r32(w0, w1, sh);
+        const uint32_t mask = rows == 8 ? 0xFFFFFFFFu : ((1u << (4 * rows)) - 1u);
+        uint32_t x;
+        if (ad.and_mode) {                             // every nibble must share a bit
+            x = rd & ad.apack[w];
+            x |= x >> 1; x |= x >> 2;
+            x = (~x) & 0x11111111u & mask;
+        } else {
+            x = (rd ^ ad.apack[w]) & mask;
         }
-        if (p < pend) {
-            const uint32_t w = codes[p >> 3];
-            for (int t = 0; p < pend; t++, p++) myers_col(st, tail_peq[(w >> (4 * t)) & 15u]);
-        }
-        // D[i][n] = running sum of the vertical deltas; rows right-aligned so that the shifts are static
-        const unsigned pv = st.Pv >> sh, mv = st.Mv >> sh;
-        const int row_lo = atr_max(stop_in_ref ? 1 : m, ad.min_overlap);
-        int d = 0;
-#pragma unroll
-        for (int i = 1; i <= 32; i++) {
-            d += (int)((pv >> (i - 1)) & 1u) - (int)((mv >> (i - 1)) & 1u);
-            if (i >= row_lo && i <= mp && d <= (int)ad.thr_mul[i]) { imin = imin == 0 ? i : imin; imax = i; }
-        }
+        same = same && x == 0u;
     }
+    return same;
+}
+
+// (c) can there be a candidate in the last column with row <= sa_rows? (see adapter_build.hpp: tail gate)
+ATR_HD bool sa_need_tail(const AdapterK1a& ad, int n, int hmax, unsigned st_final) {
+    const bool stop_in_ref = ad.flags & ATR_STOP_WITHIN_SEQ1;
+    if (!(stop_in_ref || ad.m <= ad.sa_rows)) return false;
+    if (!ad.tail_gate_ok) return true;
+    if (st_final & ad.tail_mask) return true;
+    return hmax != -0x7fffffff && hmax >= n - ad.sa_rows - ad.k;
+}
+
+// (d) exact D[i][n] for rows i <= sa_rows from a 32-bit Myers over the last sa_rows + k columns (rows left-aligned)
+ATR_HD void sa_tail(const AdapterK1a& ad, const unsigned* __restrict__ tail_peq, const uint32_t* __restrict__ codes, int lo, int n,
+                    int& imin, int& imax) {
+    const int m = ad.m, k = ad.k, mp = ad.sa_rows;
+    const bool stop_in_ref = ad.flags & ATR_STOP_WITHIN_SEQ1;
+    const int pend = lo + n;
+    imin = 0; imax = 0;
+    const int sh = 32 - mp;
+    MyersState<unsigned> st;
+    st.Pv = (sh == 0) ? ~0u : (~0u << sh);
+    st.Mv = 0; st.score = mp;
+    // start on a word boundary at or before column n - mp - k (an earlier start is always safe)
+    int p = atr_max(lo, (lo + atr_max(0, n - mp - k)) & ~7);
+    while (p < pend && (p & 7) != 0) { myers_col(st, tail_peq[(codes[p >> 3] >> ((p & 7) * 4)) & 15u]); p++; }
+    while (p + 8 <= pend) {
+        const uint32_t w = codes[p >> 3];
+#pragma unroll
+        for (int t = 0; t < 8; t++) myers_col(st, tail_peq[(w >> (4 * t)) & 15u]);
+        p += 8;
+    }
+    if (p < pend) {
+        const uint32_t w = codes[p >> 3];
+        for (int t = 0; p < pend; t++, p++) myers_col(st, tail_peq[(w >> (4 * t)) & 15u]);
+    }
+    // D[i][n] = running sum of the vertical deltas; rows right-aligned so that the shifts are static
+    const unsigned pv = st.Pv >> sh, mv = st.Mv >> sh;
+    const int row_lo = atr_max(stop_in_ref ? 1 : m, ad.min_overlap);
+    int d = 0;
+#pragma unroll
+    for (int i = 1; i <= 32; i++) {
+        d += (int)((pv >> (i - 1)) & 1u) - (int)((mv >> (i - 1)) & 1u);
+        if (i >= row_lo && i <= mp && d <= (int)ad.thr_mul[i]) { imin = imin == 0 ? i : imin; imax = i; }
+    }
+}
+
+// (e) classes 0 / 1 / 2 from the hit range and the last-column rows
+ATR_HD void sa_classify(const AdapterK1a& ad, int lo, int n, int hmin, int hmax, int imin, int imax, SaResult& res) {
+    const int m = ad.m, k = ad.k;
     const bool have_hit = hmax != -0x7fffffff;
     if (!have_hit && imax == 0) { res.cls = 0; return; }
-    if (have_hit && hmin == hmax && ad.exact_ok && hmin >= 0 && hmin + m <= n) {
-        // verify the whole adapter at read position v, 8 bases per step
-        const int q = lo + hmin;
-        const unsigned sh = (unsigned)(q & 7) * 4u;
-        bool same = true;
-        for (int w = 0; w * 8 < m; w++) {
-            const int rows = atr_min(8, m - 8 * w);                       // adapter rows in this word
-            const uint32_t w0 = codes[(q >> 3) + w];
-            const bool need_hi = ((q & 7) + rows) > 8;                       // the rows spill into the next read word
-            const uint32_t w1 = need_hi ? codes[(q >> 3) + w + 1] : 0u;
-            const uint32_t rd = funnel_r32(w0, w1, sh);
-            const uint32_t mask = rows == 8 ? 0xFFFFFFFFu : ((1u << (4 * rows)) - 1u);
-            uint32_t x;
-            if (ad.and_mode) {                                               // every nibble must share a bit
-                x = rd & ad.apack[w];
-                x |= x >> 1; x |= x >> 2;
-                x = (~x) & 0x11111111u & mask;
-            } else {
-                x = (rd ^ ad.apack[w]) & mask;
-            }
-            same = same && x == 0u;
-        }
-        if (same) { res.cls = 3; res.v = hmin; return; }
-    }
     if (!have_hit) {
         res.cls = 1;
         res.dlo = (n - imax) - k;
@@ -521,6 +543,17 @@ ATR_HD void sa_filter(const AdapterK1a& ad, const unsigned* __restrict__ sa_peq,
     c0 = atr_max(0, c0); c1 = atr_min(n, c1);
     res.c0 = atr_max(0, ((lo + c0) & ~7) - lo);
     res.c1 = atr_min(n, ((lo + c1 + 7) & ~7) - lo);
+}
+
+// the whole stage for one read (host simulator; the kernel interleaves a block-level compaction before (d))
+ATR_HD void sa_filter(const AdapterK1a& ad, const unsigned* __restrict__ sa_peq, const unsigned* __restrict__ tail_peq,
+                      const uint32_t* __restrict__ codes, int lo, int n, SaResult& res) {
+    int hmin, hmax, imin = 0, imax = 0;
+    unsigned st_final;
+    sa_scan(ad, sa_peq, codes, lo, n, hmin, hmax, st_final);
+    if (sa_exact(ad, codes, lo, n, hmin, hmax)) { res.cls = 3; res.v = hmin; return; }
+    if (sa_need_tail(ad, n, hmax, st_final)) sa_tail(ad, tail_peq, codes, lo, n, imin, imax);
+    sa_classify(ad, lo, n, hmin, hmax, imin, imax, res);
 }
 
 // ---- K1f phase 2 (narrow bands): K1d, banded DP along diagonals ------------------------------------------
