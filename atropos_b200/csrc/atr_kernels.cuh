@@ -359,6 +359,7 @@ __global__ void __launch_bounds__(ATR_K1F_THREADS) k_filter_sa(const __grid_cons
     __shared__ __align__(128) uint32_t s_tile[ATR_K1F_TILE_WORDS];
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ unsigned s_sa_peq[16], s_tail_peq[16];
+    __shared__ unsigned long long s_sa_pair[256];      // Peq of two bases per byte of the packed read
     __shared__ int s_im[ATR_K1F_THREADS];
     __shared__ unsigned short s_tail_list[ATR_K1F_THREADS];
     __shared__ int s_tail_count;
@@ -379,6 +380,11 @@ __global__ void __launch_bounds__(ATR_K1F_THREADS) k_filter_sa(const __grid_cons
         s_tail_peq[tid] = sh32 ? ((low << sh32) | ((1u << sh32) - 1u)) : low;
     }
     if (tid == 0) s_tail_count = 0;
+    {
+        const int mp = ad.sa_rows;
+        const unsigned long long mk = mp >= 32 ? 0xFFFFFFFFull : ((1ull << mp) - 1);
+        s_sa_pair[tid] = (ad.peq[tid & 15] & mk) | ((ad.peq[tid >> 4] & mk) << 32);
+    }
     if (tid == 0 && use_tma) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar)) : "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -417,7 +423,7 @@ __global__ void __launch_bounds__(ATR_K1F_THREADS) k_filter_sa(const __grid_cons
     bool exact = false, need_tail = false;
     if (mine && !routed) {
         unsigned st_final;
-        sa_scan(ad, s_sa_peq, rd, lo, n, hmin, hmax, st_final);
+        sa_scan(ad, s_sa_peq, s_sa_pair, rd, lo, n, hmin, hmax, st_final);
         exact = sa_exact(ad, rd, lo, n, hmin, hmax);
         if (exact) {                                                // verbatim occurrence: result known (str.find shortcut)
             Best b;

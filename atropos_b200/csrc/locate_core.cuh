@@ -394,8 +394,10 @@ struct SaResult {
 };
 
 // (a) Shift-And over all columns: range of hit diagonals and the automaton's final state
-ATR_HD void sa_scan(const AdapterK1a& ad, const unsigned* __restrict__ sa_peq, const uint32_t* __restrict__ codes, int lo, int n,
-                    int& hmin, int& hmax, unsigned& st_final) {
+// sa_pair: 256-entry table indexed by a byte of the packed read (two bases): low word = Peq of the first base,
+// high word = Peq of the second -- one 8-byte shared-memory load serves two columns.
+ATR_HD void sa_scan(const AdapterK1a& ad, const unsigned* __restrict__ sa_peq, const unsigned long long* __restrict__ sa_pair,
+                    const uint32_t* __restrict__ codes, int lo, int n, int& hmin, int& hmax, unsigned& st_final) {
     const unsigned S0 = ad.sa_start, E = ad.sa_end;
     unsigned St = 0;
     hmin = 0x7fffffff; hmax = -0x7fffffff;           // over hits: (column of the piece end) - (row of the piece end)
@@ -413,9 +415,13 @@ ATR_HD void sa_scan(const AdapterK1a& ad, const unsigned* __restrict__ sa_peq, c
         unsigned any = 0;
         unsigned Ss[8];
 #pragma unroll
-        for (int t = 0; t < 8; t++) {
-            St = ((St << 1) | S0) & sa_peq[(w >> (4 * t)) & 15u];
+        for (int t = 0; t < 8; t += 2) {
+            const unsigned long long pr = sa_pair[(w >> (4 * t)) & 255u];
+            St = ((St << 1) | S0) & (unsigned)pr;
             Ss[t] = St;
+            any |= St;
+            St = ((St << 1) | S0) & (unsigned)(pr >> 32);
+            Ss[t + 1] = St;
             any |= St;
         }
         if (any & E) {                                 // some piece ended inside this word (a few lanes per warp)
@@ -550,7 +556,9 @@ ATR_HD void sa_filter(const AdapterK1a& ad, const unsigned* __restrict__ sa_peq,
                       const uint32_t* __restrict__ codes, int lo, int n, SaResult& res) {
     int hmin, hmax, imin = 0, imax = 0;
     unsigned st_final;
-    sa_scan(ad, sa_peq, codes, lo, n, hmin, hmax, st_final);
+    unsigned long long sa_pair[256];
+    for (int b = 0; b < 256; b++) sa_pair[b] = (unsigned long long)sa_peq[b & 15] | ((unsigned long long)sa_peq[b >> 4] << 32);
+    sa_scan(ad, sa_peq, sa_pair, codes, lo, n, hmin, hmax, st_final);
     if (sa_exact(ad, codes, lo, n, hmin, hmax)) { res.cls = 3; res.v = hmin; return; }
     if (sa_need_tail(ad, n, hmax, st_final)) sa_tail(ad, tail_peq, codes, lo, n, imin, imax);
     sa_classify(ad, lo, n, hmin, hmax, imin, imax, res);
