@@ -417,3 +417,68 @@ def test_insert_adapter_cutter_matching_half():
                 assert g == (None if e is None else e[:6]), (i, read)
                 n_fb += e is not None
     assert n_ins > 1500 and n_fb > 20
+
+
+def test_full_size_properties_pe():
+    """BASELINE config 3 at full size (10 M pairs, 2 x 150) through size-independent properties: (1) a random 20 k
+    subsample agrees with the oracle; (2) pairs are independent: a permuted batch gives the permuted records;
+    (3) swapping mates with swapped adapters mirrors the result (the overlap is symmetric under reverse
+    complement: same insert size, match1 <-> match2); (4) planted error-free fragments shorter than the read are
+    all found with insert size == fragment length."""
+    import torch
+    from atropos_b200 import _abi, synth
+    from atropos_b200.align import InsertAligner
+    n, L = 10_000_000, 150
+    r1, r2 = synth.synth_pe(n, L, seed=synth.seed_for(3), device="cuda")
+    r1, r2 = r1.cpu().numpy(), r2.cpu().numpy()
+    offs = np.arange(n + 1, dtype=np.int64) * L
+    kw = dict(max_insert_mismatch_frac=0.1, max_adapter_mismatch_frac=0.1)
+    ia = InsertAligner(T1, T2, **kw)
+    res = ia.match_insert_batch((r1.reshape(-1), offs), (r2.reshape(-1), offs))
+    st = res["insert"]["status"]
+    assert set(np.unique(st)) <= {_abi.ATR_ST_NONE, _abi.ATR_ST_MATCH}
+    assert 0.35 < (st == _abi.ATR_ST_MATCH).mean() < 0.45
+    rng = np.random.default_rng(3)
+    orc = oracle.OracleInsertAligner(T1, T2, **kw)
+    for i in rng.choice(n, 20000, replace=False):
+        exp = orc.match_insert(bytes(r1[i]).decode(), bytes(r2[i]).decode())
+        got = InsertAligner.result_from_record(res[i])
+        if exp is None:
+            assert got is None
+        else:
+            assert got[0] == exp[0] and (got[1].fields() if got[1] else None) == exp[1] and \
+                (got[2].fields() if got[2] else None) == exp[2]
+    m = 2_000_000
+    perm = rng.permutation(m)
+    res_p = ia.match_insert_batch((r1[:m][perm].reshape(-1), offs[:m + 1]), (r2[:m][perm].reshape(-1), offs[:m + 1]))
+    assert np.array_equal(res_p, res[:m][perm])
+    # (3) mirror: Hamming(rc(r2)[m-j:], r1[:j]) == Hamming(rc(r1)[m-j:], r2[:j]) for every j, and the decision
+    # procedure is symmetric in (read1, adapter1) <-> (read2, adapter2)
+    ia_sw = InsertAligner(T2, T1, **kw)
+    res_sw = ia_sw.match_insert_batch((r2[:m].reshape(-1), offs[:m + 1]), (r1[:m].reshape(-1), offs[:m + 1]))
+    assert np.array_equal(res[:m]["insert"], res_sw["insert"])
+    assert np.array_equal(res[:m]["match1"][list(FIELDS)], res_sw["match2"][list(FIELDS)])
+    assert np.array_equal(res[:m]["match2"][list(FIELDS)], res_sw["match1"][list(FIELDS)])
+    # (4) planted fragments
+    k = 500_000
+    frag = rng.integers(40, L - 12, size=k)
+    comp = np.zeros(256, dtype=np.uint8)
+    for a, b in zip(b"ACGT", b"TGCA"):
+        comp[a] = b
+    base = np.frombuffer(b"ACGT", dtype=np.uint8)
+    F = base[rng.integers(0, 4, size=(k, L))]
+    p1 = base[rng.integers(0, 4, size=(k, L))]
+    p2 = base[rng.integers(0, 4, size=(k, L))]
+    a1 = np.frombuffer(T1.encode(), dtype=np.uint8)
+    a2 = np.frombuffer(T2.encode(), dtype=np.uint8)
+    col = np.arange(L)[None, :]
+    rel = col - frag[:, None]
+    p1 = np.where(rel < 0, F, np.where(rel < len(a1), a1[np.clip(rel, 0, len(a1) - 1)], p1))
+    Frc = comp[np.take_along_axis(F, np.clip(frag[:, None] - 1 - col, 0, L - 1), axis=1)]
+    p2 = np.where(rel < 0, Frc, np.where(rel < len(a2), a2[np.clip(rel, 0, len(a2) - 1)], p2))
+    res4 = ia.match_insert_batch((np.ascontiguousarray(p1).reshape(-1), offs[:k + 1]),
+                                 (np.ascontiguousarray(p2).reshape(-1), offs[:k + 1]))
+    assert np.all(res4["insert"]["status"] == _abi.ATR_ST_MATCH)
+    ok = res4["match1"]["rstart"] == frag
+    assert ok.mean() > 0.999        # a chance longer overlap of the random tails can win by probability
+    assert np.all(res4["match1"]["status"][ok] == _abi.ATR_ST_MATCH) and np.all(res4["match2"]["rstart"][ok] == frag[ok])
