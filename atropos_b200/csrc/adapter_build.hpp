@@ -262,6 +262,7 @@ struct HostInsert {
     InsertDev dev;                    // scalar fields filled; pointer fields set by the owner (device or host pointers)
     std::vector<unsigned short> k_by_len, thr_ins, maxmm;
     std::vector<unsigned char> a1_code, a2_code, a1_ascii, a2_ascii, comp, ov_tab;
+    std::vector<uint32_t> a1_pack, a2_pack;
     std::vector<double> insert_prob, adapter_prob;
 };
 
@@ -308,6 +309,12 @@ inline int prepare_insert(const atr_insert_desc& d, const AtrTables& tb, HostIns
     };
     enc(d.adapter1, d.adapter1_len, h.a1_code, h.a1_ascii);
     enc(d.adapter2, d.adapter2_len, h.a2_code, h.a2_ascii);
+    auto packw = [](const std::vector<unsigned char>& code, std::vector<uint32_t>& out) {
+        out.assign(code.size() / 8 + 2, 0u);
+        for (size_t i = 0; i < code.size(); i++) out[i >> 3] |= ((uint32_t)code[i] & 15u) << (4 * (i & 7));
+    };
+    packw(h.a1_code, h.a1_pack);
+    packw(h.a2_code, h.a2_pack);
     v.packed_ok = packed_ok;
     h.comp.assign(256, 0); h.ov_tab.assign(256, 0);
     const char* a = "ACRSWKBDN"; const char* b = "TGYSWMVHN";                         // util/__init__.py:67-88

@@ -530,6 +530,8 @@ int atr_insertset_create(atr_ctx* ctx, const atr_insert_desc* d, atr_insertset**
     if (!rc) rc = upload(ctx, set->dev_allocs, h.maxmm.data(), h.maxmm.size(), &v.maxmm);
     if (!rc) rc = upload(ctx, set->dev_allocs, h.a1_code.data(), h.a1_code.size(), &v.a1_code);
     if (!rc) rc = upload(ctx, set->dev_allocs, h.a2_code.data(), h.a2_code.size(), &v.a2_code);
+    if (!rc) rc = upload(ctx, set->dev_allocs, h.a1_pack.data(), h.a1_pack.size(), &v.a1_pack);
+    if (!rc) rc = upload(ctx, set->dev_allocs, h.a2_pack.data(), h.a2_pack.size(), &v.a2_pack);
     if (!rc) rc = upload(ctx, set->dev_allocs, h.a1_ascii.data(), h.a1_ascii.size(), &v.a1_ascii);
     if (!rc) rc = upload(ctx, set->dev_allocs, h.a2_ascii.data(), h.a2_ascii.size(), &v.a2_ascii);
     if (!rc) rc = upload(ctx, set->dev_allocs, h.insert_prob.data(), h.insert_prob.size(), &v.insert_prob);

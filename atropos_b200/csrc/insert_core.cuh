@@ -32,6 +32,8 @@ struct InsertDev {
     const unsigned short* maxmm;    // [amax+1]     round(alen * max_adapter_mismatch_frac) align/__init__.py:290
     const unsigned char* a1_code;   // packed-path compare operand per adapter base
     const unsigned char* a2_code;
+    const uint32_t* a1_pack;        // the same codes packed 8 per word like a read (word-wise overhang compare)
+    const uint32_t* a2_pack;
     const unsigned char* a1_ascii;  // byte path: adapter bytes / translated per mode
     const unsigned char* a2_ascii;
     const double* insert_prob;      // [(max_len+1) * (kmax+1)]  P(matches = size - cost, size)   align/__init__.py:358
@@ -133,31 +135,58 @@ struct PackedPair {
         int bstart = (m - 32) & 7;
         uint32_t r0 = R[g * stride], r1 = R[(g + 1) * stride], r2 = R[(g + 2) * stride], r3 = R[(g + 3) * stride],
                  r4 = R[(g + 4) * stride];
-        for (; g >= 0; g--) {
+        // Overlaps that survive the unconditional part are rare (the real one, plus noise): they are parked and
+        // finished after the loop, all lanes together, instead of one lane at a time in the middle of it.
+        // pend[] holds (j << 16 | words done << 8 | cost so far), in ascending j.
+        unsigned pend0 = 0, pend1 = 0, pend2 = 0, pend3 = 0;
+        int npend = 0;
+        bool go_on = true;
+        auto finish = [&](unsigned e) -> bool {        // complete one parked overlap; false = stop everything
+            const int j = (int)(e >> 16), wdone = (int)((e >> 8) & 255u);
+            const int bound = atr_imin(k, (int)d.thr_ins[j]);
+            const int full = overlap_cost(j, bound, wdone, e & 255u);
+            return !(full <= bound) || emit(j, full);
+        };
+        auto flush = [&]() -> bool {
+            if (npend > 0 && !finish(pend0)) return false;
+            if (npend > 1 && !finish(pend1)) return false;
+            if (npend > 2 && !finish(pend2)) return false;
+            if (npend > 3 && !finish(pend3)) return false;
+            npend = 0;
+            return true;
+        };
+        for (; g >= 0 && go_on; g--) {
 #pragma unroll
             for (int b = 7; b >= 0; b--) {
-                if (b > bstart) continue;
+                if (b > bstart || !go_on) continue;
                 const int j = m - (8 * g + b);
                 const int tj = (int)d.thr_ins[j];
                 const int bound = atr_imin(k, tj);
                 unsigned cost = nib_mismatches(funnel_r(r0, r1, 4u * b) ^ q0) + nib_mismatches(funnel_r(r1, r2, 4u * b) ^ q1);
-                int wdone = 2;
+                unsigned wdone = 2;
                 if (tj > 6) {                          // long overlaps tolerate more mismatches: look at 32 bases
                     cost += nib_mismatches(funnel_r(r2, r3, 4u * b) ^ q2) + nib_mismatches(funnel_r(r3, r4, 4u * b) ^ q3);
                     wdone = 4;
                 }
                 if ((int)cost <= bound && j >= d.min_insert_overlap) {
-                    const int full = overlap_cost(j, bound, wdone, cost);
-                    if (full <= bound && !emit(j, full)) return;
+                    if (npend == 4) go_on = flush();   // full (low-complexity read): finish the parked ones in order
+                    if (go_on) {
+                        const unsigned e = ((unsigned)j << 16) | (wdone << 8) | cost;
+                        if (npend == 0) pend0 = e; else if (npend == 1) pend1 = e; else if (npend == 2) pend2 = e; else pend3 = e;
+                        npend++;
+                    }
                 }
             }
             bstart = 7;
             r4 = r3; r3 = r2; r2 = r1; r1 = r0;
             if (g > 0) r0 = R[(g - 1) * stride];
         }
+        if (go_on) flush();
     }
     ATR_HD unsigned ov1(int p) const { return (S1[p >> 3] >> ((p & 7) * 4)) & 15u; }
     ATR_HD unsigned ov2(int p) const { return (S2[p >> 3] >> ((p & 7) * 4)) & 15u; }
+    ATR_HD const uint32_t* fwd1() const { return S1; }
+    ATR_HD const uint32_t* fwd2() const { return S2; }
 };
 
 struct BytePair {
@@ -182,6 +211,8 @@ struct BytePair {
     }
     ATR_HD unsigned ov1(int p) const { return ov_tab[s1[p]]; }
     ATR_HD unsigned ov2(int p) const { return ov_tab[s2[p]]; }
+    ATR_HD const uint32_t* fwd1() const { return nullptr; }
+    ATR_HD const uint32_t* fwd2() const { return nullptr; }
 };
 
 // compare_prefixes(read[size:], adapter) (align/__init__.py:285-288): mismatches over alen bases
@@ -194,6 +225,30 @@ ATR_HD int overhang_mismatches(const InsertDev& d, const P& pr, int size, int al
         if (packed && d.ov_single_only) rc = (rc & (rc - 1)) ? 0u : rc;
         const unsigned a = ac[t];
         mm += d.and_mode ? ((rc & a) == 0u) : (rc != a);
+    }
+    return mm;
+}
+
+// the same on packed words, 8 bases per step (packed path, not the ACGT-filtered overhang mode)
+template <bool FIRST>
+ATR_HD int overhang_mismatches_words(const InsertDev& d, const uint32_t* __restrict__ S, int size, int alen) {
+    const uint32_t* ap = FIRST ? d.a1_pack : d.a2_pack;
+    const unsigned sh = (unsigned)(size & 7) * 4u;
+    int mm = 0;
+    for (int w = 0; w * 8 < alen; w++) {
+        const int rows = alen - 8 * w < 8 ? alen - 8 * w : 8;
+        const uint32_t w0 = S[(size >> 3) + w];
+        const uint32_t w1 = ((size & 7) + rows) > 8 ? S[(size >> 3) + w + 1] : 0u;     // only if the bases spill over
+        const uint32_t rd = funnel_r(w0, w1, sh);
+        const uint32_t mask = rows == 8 ? 0x11111111u : (0x11111111u & ((1u << (4 * rows)) - 1u));
+        uint32_t x = d.and_mode ? (rd & ap[w]) : (rd ^ ap[w]);
+        x |= x >> 1; x |= x >> 2;                      // bit 4t set <=> nibble t non-zero
+        x = d.and_mode ? (~x & mask) : (x & mask);     // AND mode: a mismatch is a nibble with no common bit
+#if defined(__CUDA_ARCH__)
+        mm += __popc(x);
+#else
+        mm += __builtin_popcount(x);
+#endif
     }
     return mm;
 }
@@ -211,8 +266,14 @@ ATR_HD int insert_try(const InsertDev& d, const P& pr, bool packed, int m, int j
     if (offset < d.min_adapter_overlap) { *out = r; return 1; }              // (insert_match, None, None)
     const int alen1 = offset < d.a1_len ? offset : d.a1_len;
     const int alen2 = offset < d.a2_len ? offset : d.a2_len;
-    const int mm1 = overhang_mismatches<P, true>(d, pr, size, alen1, packed);
-    const int mm2 = overhang_mismatches<P, false>(d, pr, size, alen2, packed);
+    int mm1, mm2;
+    if (packed && !d.ov_single_only) {
+        mm1 = overhang_mismatches_words<true>(d, pr.fwd1(), size, alen1);
+        mm2 = overhang_mismatches_words<false>(d, pr.fwd2(), size, alen2);
+    } else {
+        mm1 = overhang_mismatches<P, true>(d, pr, size, alen1, packed);
+        mm2 = overhang_mismatches<P, false>(d, pr, size, alen2, packed);
+    }
     if (mm1 > (int)d.maxmm[alen1] && mm2 > (int)d.maxmm[alen2]) return 0;    // :297-300
     if ((alen1 < alen2 ? alen1 : alen2) > d.cutoff) {                        // :302-306
         const double p1 = d.adapter_prob[alen1 * (d.amax + 1) + (alen1 - mm1)];

@@ -67,6 +67,7 @@ int sim_match_insert(const atr_insert_desc* d, const unsigned char* r1, int len1
     if (rc) return rc;
     InsertDev v = h.dev;
     v.k_by_len = h.k_by_len.data(); v.thr_ins = h.thr_ins.data(); v.maxmm = h.maxmm.data();
+    v.a1_pack = h.a1_pack.data(); v.a2_pack = h.a2_pack.data();
     v.a1_code = h.a1_code.data(); v.a2_code = h.a2_code.data(); v.a1_ascii = h.a1_ascii.data(); v.a2_ascii = h.a2_ascii.data();
     v.insert_prob = h.insert_prob.data(); v.adapter_prob = h.adapter_prob.data(); v.comp = h.comp.data(); v.ov_tab = h.ov_tab.data();
     const int m = len1 < len2 ? len1 : len2;
