@@ -38,6 +38,8 @@ struct DevBuf {
 // per-stream working set of the host entry points
 struct Slot {
     cudaStream_t stream = nullptr;
+    cudaStream_t aux = nullptr;          // k_wide runs here, concurrently with k_band on `stream`
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     DevBuf ascii, offsets, win, counts, woff, codes, len, out, scan_tmp, gen_scratch, lists;
     DevBuf ascii2, offsets2, counts2, woff2, codes2, len2;     // second mate (insert aligner)
     void release() {
@@ -135,11 +137,14 @@ int pack_on_stream(atr_ctx* ctx, cudaStream_t st, DevBuf& counts, DevBuf& scan_t
 }
 
 // ---- K1 launch logic -------------------------------------------------------------------------
-int locate_on_stream(atr_ctx* ctx, cudaStream_t st, DevBuf& gen_scratch, DevBuf& lists, const atr_adapterset* set,
+int locate_on_stream(atr_ctx* ctx, Slot& slot, const atr_adapterset* set,
                      const uint32_t* d_codes, const uint32_t* d_woff, const uint16_t* d_len, const uint16_t* d_win,
                      const uint8_t* d_ascii, const int64_t* d_offsets, int64_t base, int fold_case, int64_t n,
                      atr_match* d_out) {
     if (n <= 0) return ATR_OK;
+    cudaStream_t st = slot.stream;
+    DevBuf& gen_scratch = slot.gen_scratch;
+    DevBuf& lists = slot.lists;
     const bool have_ascii = d_ascii != nullptr && d_offsets != nullptr;
     const bool have_packed = d_codes != nullptr && d_woff != nullptr && d_len != nullptr;
     // general-kernel geometry (grid-stride; scratch is per thread)
@@ -196,12 +201,17 @@ int locate_on_stream(atr_ctx* ctx, cudaStream_t st, DevBuf& gen_scratch, DevBuf&
                     LAUNCHED(ctx);
                 }
                 if (prof) CU(cudaEventRecord(ctx->pev[1], st));
+                // the two DP kernels work on disjoint survivors and records: unless the per-kernel timing is on,
+                // the (small, latency-bound) windowed kernel runs on a side stream underneath the banded one
+                cudaStream_t sw = prof ? st : slot.aux;
+                if (!prof) { CU(cudaEventRecord(slot.ev_fork, st)); CU(cudaStreamWaitEvent(sw, slot.ev_fork, 0)); }
                 if (h.and_mode) k_band<true><<<gp, 128, 0, st>>>(p, d_codes, d_woff, d_len, d_win, d_out, narrow, counters + 0);
                 else k_band<false><<<gp, 128, 0, st>>>(p, d_codes, d_woff, d_len, d_win, d_out, narrow, counters + 0);
                 LAUNCHED(ctx);
                 if (prof) CU(cudaEventRecord(ctx->pev[2], st));
-                if (h.and_mode) k_wide<true><<<gp, 128, 0, st>>>(p, d_codes, d_woff, d_len, d_win, d_out, wide, counters + 1);
-                else k_wide<false><<<gp, 128, 0, st>>>(p, d_codes, d_woff, d_len, d_win, d_out, wide, counters + 1);
+                if (h.and_mode) k_wide<true><<<gp, 128, 0, sw>>>(p, d_codes, d_woff, d_len, d_win, d_out, wide, counters + 1);
+                else k_wide<false><<<gp, 128, 0, sw>>>(p, d_codes, d_woff, d_len, d_win, d_out, wide, counters + 1);
+                if (!prof) { LAUNCHED(ctx); ctx->launches--; CU(cudaEventRecord(slot.ev_join, sw)); CU(cudaStreamWaitEvent(st, slot.ev_join, 0)); }
                 if (prof) { LAUNCHED(ctx); CU(cudaEventRecord(ctx->pev[3], st)); ctx->launches--; ctx->phases_valid = 1; }
             }
             else if (h.and_mode) k_locate_k1a<true><<<grid_for(n, 128), 128, 0, st>>>(p, d_codes, d_woff, d_len, d_win, n, d_out);
@@ -276,7 +286,12 @@ int atr_ctx_create(int device, atr_ctx** out) {
     { const char* e = getenv("ATR_DISABLE_FUSED"); ctx->disable_fused = (e && e[0] == '1'); }
     { const char* e = getenv("ATR_DISABLE_SA"); ctx->disable_sa = (e && e[0] == '1'); }
     CU(cudaSetDevice(device));
-    for (int s = 0; s < 2; s++) CU(cudaStreamCreateWithFlags(&ctx->slot[s].stream, cudaStreamNonBlocking));
+    for (int s = 0; s < 2; s++) {
+        CU(cudaStreamCreateWithFlags(&ctx->slot[s].stream, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&ctx->slot[s].aux, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&ctx->slot[s].ev_fork, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ctx->slot[s].ev_join, cudaEventDisableTiming));
+    }
     CU(cudaEventCreate(&ctx->ev0));
     CU(cudaEventCreate(&ctx->ev1));
     atr::build_tables(ctx->h_tables);
@@ -291,6 +306,9 @@ void atr_ctx_destroy(atr_ctx* ctx) {
     cudaSetDevice(ctx->device);
     for (int s = 0; s < 2; s++) {
         if (ctx->slot[s].stream) { cudaStreamSynchronize(ctx->slot[s].stream); cudaStreamDestroy(ctx->slot[s].stream); }
+        if (ctx->slot[s].aux) { cudaStreamSynchronize(ctx->slot[s].aux); cudaStreamDestroy(ctx->slot[s].aux); }
+        if (ctx->slot[s].ev_fork) cudaEventDestroy(ctx->slot[s].ev_fork);
+        if (ctx->slot[s].ev_join) cudaEventDestroy(ctx->slot[s].ev_join);
         ctx->slot[s].release();
     }
     ctx->misc.release();
@@ -421,7 +439,7 @@ int atr_locate_batch_device(atr_ctx* ctx, const atr_adapterset* set, const uint3
     }
     Slot& s = ctx->slot[0];
     CU(cudaEventRecord(ctx->ev0, s.stream));
-    int rc = locate_on_stream(ctx, s.stream, s.gen_scratch, s.lists, set, d_codes, d_woff, d_len, d_win, d_ascii, d_offsets, 0,
+    int rc = locate_on_stream(ctx, s, set, d_codes, d_woff, d_len, d_win, d_ascii, d_offsets, 0,
                               fold_case, n, d_out);
     if (rc) return rc;
     CU(cudaEventRecord(ctx->ev1, s.stream));
@@ -470,7 +488,7 @@ int atr_locate_batch_host(atr_ctx* ctx, const atr_adapterset* set, const uint8_t
         rc = pack_on_stream(ctx, s.stream, s.counts, s.scan_tmp, s.ascii.as<uint8_t>(), s.offsets.as<int64_t>(), offsets[c0], cn,
                             fold_case, s.codes.as<uint32_t>(), s.woff.as<uint32_t>(), s.len.as<uint16_t>());
         if (rc) return rc;
-        rc = locate_on_stream(ctx, s.stream, s.gen_scratch, s.lists, set, s.codes.as<uint32_t>(), s.woff.as<uint32_t>(),
+        rc = locate_on_stream(ctx, s, set, s.codes.as<uint32_t>(), s.woff.as<uint32_t>(),
                               s.len.as<uint16_t>(), win ? s.win.as<uint16_t>() : nullptr, s.ascii.as<uint8_t>(),
                               s.offsets.as<int64_t>(), offsets[c0], fold_case, cn, s.out.as<atr_match>());
         if (rc) return rc;
