@@ -482,3 +482,35 @@ def test_full_size_properties_pe():
     ok = res4["match1"]["rstart"] == frag
     assert ok.mean() > 0.999        # a chance longer overlap of the random tails can win by probability
     assert np.all(res4["match1"]["status"][ok] == _abi.ATR_ST_MATCH) and np.all(res4["match2"]["rstart"][ok] == frag[ok])
+
+
+def test_batched_trim_consumes_gpu_records():
+    """f-1/f-3: trimming windows and adapter statistics from the GPU's records equal those from the oracle's"""
+    from atropos_b200 import trim
+    from atropos_b200.adapters import Adapter
+    from atropos_b200.modifiers import AdapterCutter
+    from test_trim_vs_reference import SPECS, _oracle_rounds
+    rng = np.random.default_rng(2025)
+    reads = []
+    for _ in range(3000):
+        s, w = SPECS[int(rng.integers(0, len(SPECS)))]
+        body = fuzzgen.read_with_adapter(rng, s, int(rng.integers(0, 160)), n_rate=0.01)
+        if w != oracle.BACK and rng.random() < 0.6:
+            body = (fuzzgen.mutate(rng, s, 0.03, 0.01, 0.01) + body)[:150]
+        reads.append(body)
+    gpu_adapters = [Adapter(s, w) for s, w in SPECS]
+    cutter = AdapterCutter(gpu_adapters, times=2)
+    blob = np.frombuffer("".join(reads).encode(), dtype=np.uint8)
+    offs = np.zeros(len(reads) + 1, dtype=np.int64)
+    np.cumsum([len(r) for r in reads], out=offs[1:])
+    g_rounds = cutter.match_rounds_batch((blob, offs))
+    o_rounds = _oracle_rounds(reads, [oracle.OracleAdapter(s, w) for s, w in SPECS], 2)
+    ff = [a._front_flag for a in gpu_adapters]
+    g = trim.apply_rounds(blob, offs, g_rounds, ff)
+    o = trim.apply_rounds(blob, offs, o_rounds, ff)
+    assert np.array_equal(g[0], o[0]) and np.array_equal(g[1], o[1]) and g[3] == o[3]
+    for a, b in zip(g[2], o[2]):
+        assert a.lengths_front == b.lengths_front and a.lengths_back == b.lengths_back
+        assert a.errors_front == b.errors_front and a.errors_back == b.errors_back
+        assert a.adjacent_bases == b.adjacent_bases
+    assert g[3] > 1000
