@@ -134,7 +134,7 @@ inline void fill_k1a(const HostAdapter& h, const AtrTables& tb, int index, int r
         a.thr_div[l] = l <= h.m ? h.thr_div[l] : 0;
     }
     a.rmp_ok = rmp_ok_dev;
-    // K1f (Myers bit-vector filter + windowed DP) needs unit indel cost, a free start in the read and an
+    // the filter -> banded DP funnel needs unit indel cost, a free start in the read and an
     // anchored start in the adapter (BACK / SUFFIX style flag sets)
     const bool start_in_ref = h.desc.flags & ATR_START_WITHIN_SEQ1, start_in_query = h.desc.flags & ATR_START_WITHIN_SEQ2;
     const bool stop_q = h.desc.flags & ATR_STOP_WITHIN_SEQ2;

@@ -49,9 +49,9 @@ struct AdapterK1a {                   // passed by value as a __grid_constant__ 
     unsigned short thr_mul[ATR_K1A_MAXM + 1];   // floor(length * rate) in double   (_align.pyx:447, :468)
     unsigned short thr_div[ATR_K1A_MAXM + 1];   // max e with e / size <= rate       (adapters/__init__.py:389-392)
     const unsigned char* rmp_ok;      // [(m+1)*(m+1)] or nullptr
-    int fused_ok;                     // eligible for the bit-vector filter + banded/windowed DP kernels (K1f)
+    int fused_ok;                     // eligible for the filter -> banded/windowed DP funnel (atr_kernels.cuh)
     int band_ok, nomatch;             // K1d usable; a 4-bit code that matches no adapter row (virtual columns)
-    unsigned long long peq[16];       // K1f: bit i-1 of peq[c] set iff adapter row i matches read code c
+    unsigned long long peq[16];       // bit i-1 of peq[c] set iff adapter row i matches read code c (Shift-And / Myers)
     // Shift-And pre-filter (k_filter_sa): the first sa_rows (<= 32) adapter rows cut into k+1 pieces; an alignment
     // with <= k errors must contain one piece verbatim (pigeonhole)
     int sa_ok, sa_rows;

@@ -204,16 +204,19 @@ __global__ void __launch_bounds__(256) k_compare_prefixes(const unsigned char* _
 }
 
 // ---------------------------------------------------------------------------------------------
-// K1f: bit-vector filter + banded DP -- the fast path for BACK/SUFFIX-style adapters with unit indel
-// cost and <= 64 nt (AdapterK1a.fused_ok). Three kernels on one stream:
-//   k_filter  one CTA = one tile of 256 reads. The tile's packed reads are one contiguous span of
-//             `codes`: a single TMA bulk copy (cp.async.bulk, completion on an mbarrier) stages it in
-//             shared memory; every thread runs the Myers/Hyyro filter on its read (exact costs, a small
-//             fraction of the DP's instructions, ~40 registers -> high occupancy). Reads with no
-//             acceptable cell are finished here (no match); survivors (about the adapter-containing
-//             fraction) are appended to one of two lists in global memory;
-//   k_band    dense over the "narrow" survivors: tie-broken 3-field DP on <= 16 diagonals (k1d_band);
-//   k_wide    dense over the rest: the register-column DP restricted to a column window (k1a_locate).
+// The fast path (AdapterK1a.fused_ok: unit indel cost, free start in the read, adapter <= 64 nt) is a funnel of
+// kernels on one stream; survivors are compacted into lists in global memory so that every stage runs dense:
+//   k_filter_sa  (adapters whose k+1 pieces are >= 6 rows, BACK/SUFFIX style) one CTA = one tile of 256 reads,
+//                staged in shared memory by a single TMA bulk copy (cp.async.bulk completing on an mbarrier):
+//                Shift-And over verbatim pieces, the str.find shortcut, an exact 32-bit Myers over the read tail
+//                for the reads that can have a partial match there (compacted inside the CTA);
+//   k_filter     (every other eligible adapter, incl. FRONT/ANYWHERE) same tiling; exact 32/64-bit Myers/Hyyro
+//                bit-vector DP over the whole read;
+//   k_refine     dense over the reads whose piece hits do not pin a narrow band: exact Myers on the columns around
+//                the hits;
+//   k_band       dense over the "narrow" survivors: tie-broken 3-field DP on 16 diagonals (k1d_band);
+//   k_wide       dense over the rest: the register-column DP restricted to a column window (k1a_locate); runs on a
+//                side stream underneath k_band.
 // ---------------------------------------------------------------------------------------------
 #define ATR_K1F_THREADS 256
 #define ATR_K1F_TILE_WORDS 6144      // 24 KB: 256 reads of up to 192 nt

@@ -9,6 +9,9 @@
 //   * K1g  gen_locate():  any adapter/read length and the byte-exact ASCII alphabet; column in
 //          global scratch, banded like the reference. This is the path for escaped reads,
 //          adapters > 64 nt and reads > 4000 nt.
+//   * the fast funnel: sa_scan / sa_exact / sa_tail / sa_classify (Shift-And pre-filter), myers_filter
+//          (exact bit-vector costs), k1d_band (banded 3-field DP on 16 diagonals), k1a_locate with a
+//          column window. k1f_read() chains them for one read exactly as the kernels do.
 // The functions are __host__ __device__ so tests/host_sim can run the very same code on the CPU
 // build box (no GPU there); the product only ever calls them from the kernels in kernels.cu.
 #pragma once
@@ -188,7 +191,7 @@ ATR_HD void k1a_column(const AdapterK1a& ad, unsigned (&col)[ATR_K1A_MAXM + 1], 
 }
 
 // One read (window [lo, lo+n) of the packed read starting at word `codes`) against one adapter.
-// c0/c1: evaluate only DP columns c0+1..c1 (K1f's windowed second phase; see myers_filter below). c0 < 0 = all.
+// c0/c1: evaluate only DP columns c0+1..c1 (the windowed DP stage k_wide; see myers_filter below). c0 < 0 = all.
 template <bool AND_MODE>
 ATR_HD void k1a_locate(const AdapterK1a& ad, const uint32_t* __restrict__ codes, int lo, int n, Best& best,
                        int c0 = -1, int c1 = -1) {
@@ -205,7 +208,7 @@ ATR_HD void k1a_locate(const AdapterK1a& ad, const uint32_t* __restrict__ codes,
     if (!stop_in_query) min_n = atr_max(0, n - m - k);
     const bool scan_last = max_n == n;                                     // :461
     // windowed evaluation: start at column c0 as if the read began there. Exact for every cell that can
-    // lie on an accepted alignment ending in the window ("K1f"): costs elsewhere are only
+    // lie on an accepted alignment ending in the window ("Exactness"): costs elsewhere are only
     // ever over-estimated. Only used for start_in_query && !start_in_ref flag sets.
     const bool windowed = c0 > min_n;
     if (c0 >= 0) { min_n = atr_max(min_n, c0); max_n = atr_min(max_n, c1); }
@@ -254,7 +257,7 @@ ATR_HD void k1a_locate(const AdapterK1a& ad, const uint32_t* __restrict__ codes,
     }
 }
 
-// ---- K1f phase 1: Myers/Hyyro bit-vector filter ------------------------------------------------------
+// ---- filter stage (k_filter, k_refine): Myers/Hyyro bit-vector DP ------------------------------------------------------
 // Exact unit-cost DP costs (not the tie-broken path). The adapter sits LEFT-ALIGNED in the word: row i is
 // bit (WB - m + i - 1), so the bottom row m is always the sign bit; the bits below row 1 are "virtual rows"
 // whose Peq bits are all ones and whose vertical deltas stay 0, i.e. they behave exactly like the free row 0.
@@ -374,7 +377,7 @@ ATR_HD bool myers_filter(const AdapterK1a& ad, const WORD* __restrict__ peq, con
     return true;
 }
 
-// ---- K1f phase 0: Shift-And pre-filter + 32-bit tail Myers (k_filter_sa) ---------------------------------------
+// ---- filter stage (k_filter_sa): Shift-And pre-filter + 32-bit tail Myers ---------------------------------------
 // Pigeonhole: an alignment of the adapter's first sa_rows rows with <= k unit-cost errors contains one of the
 // k+1 pieces verbatim, so a read without any verbatim piece has no row-m candidate and none in the last column
 // below row sa_rows... The Shift-And automaton over all pieces costs ~7 instructions per column (vs ~31 for the
@@ -564,7 +567,7 @@ ATR_HD void sa_filter(const AdapterK1a& ad, const unsigned* __restrict__ sa_peq,
     sa_classify(ad, lo, n, hmin, hmax, imin, imax, res);
 }
 
-// ---- K1f phase 2 (narrow bands): K1d, banded DP along diagonals ------------------------------------------
+// ---- DP stage for narrow bands (k_band): K1d, banded DP along diagonals ------------------------------------------
 // B[d] = cell (i, i + dlo + d) of the current row i, d = 0..W-1, as K1a packed keys. Rows run 1..m in a
 // rolled loop (the adapter base of a row is warp-uniform), the W diagonals are unrolled in registers:
 // diag = B[d] (old), up = B[d+1] (old), left = B[d-1] (new); cells outside the band count as dead.
@@ -847,7 +850,7 @@ ATR_HD void gen_read(const AdapterGen& ad, const AtrTables& tb, const unsigned c
     }
 }
 
-// ---- K1f per read (what the kernels do, minus the compaction between the phases) ----
+// ---- the whole funnel for one read (what the kernels do, minus the compaction between the stages) ----
 #define ATR_K1D_W 16
 template <class WORD, bool AND_MODE>
 ATR_HD void k1f_read(const AdapterK1a& ad, const uint32_t* __restrict__ codes, int lo, int n, atr_match* out, int* path = nullptr) {
