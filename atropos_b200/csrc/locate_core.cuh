@@ -396,6 +396,25 @@ struct SaResult {
     int v;               // class 3: read position of the exact occurrence
 };
 
+// eight columns (one packed word) of the Shift-And automaton; G = columns per hit-accumulation group (see sa_scan)
+template <int G>
+ATR_HD void sa_word(uint32_t w, unsigned& St, unsigned S0, unsigned E, const unsigned long long* __restrict__ sa_pair,
+                    int j, int& hmin, int& hmax) {
+#pragma unroll
+    for (int g = 0; g < 8; g += G) {
+        unsigned H = 0;
+#pragma unroll
+        for (int t = g; t < g + G; t += 2) {
+            const unsigned long long pr = sa_pair[(w >> (4 * t)) & 255u];
+            St = ((St << 1) | S0) & (unsigned)pr;
+            H |= (St & E) >> (t - g);
+            St = ((St << 1) | S0) & (unsigned)(pr >> 32);
+            H |= (St & E) >> (t + 1 - g);
+        }
+        if (H) { hmin = atr_min(hmin, j + g - atr_msb(H)); hmax = atr_max(hmax, j + g - atr_ctz(H)); }
+    }
+}
+
 // (a) Shift-And over all columns: range of hit diagonals and the automaton's final state
 // sa_pair: 256-entry table indexed by a byte of the packed read (two bases): low word = Peq of the first base,
 // high word = Peq of the second -- one 8-byte shared-memory load serves two columns.
@@ -413,28 +432,14 @@ ATR_HD void sa_scan(const AdapterK1a& ad, const unsigned* __restrict__ sa_peq, c
         const unsigned hb = St & E;
         if (hb) { hmin = atr_min(hmin, j - 1 - atr_msb(hb)); hmax = atr_max(hmax, j - 1 - atr_ctz(hb)); }
     }
-    while (pos + 8 <= pend) {
-        const uint32_t w = codes[pos >> 3];
-        unsigned any = 0;
-        unsigned Ss[8];
-#pragma unroll
-        for (int t = 0; t < 8; t += 2) {
-            const unsigned long long pr = sa_pair[(w >> (4 * t)) & 255u];
-            St = ((St << 1) | S0) & (unsigned)pr;
-            Ss[t] = St;
-            any |= St;
-            St = ((St << 1) | S0) & (unsigned)(pr >> 32);
-            Ss[t + 1] = St;
-            any |= St;
-        }
-        if (any & E) {                                 // some piece ended inside this word (a few lanes per warp)
-#pragma unroll
-            for (int t = 0; t < 8; t++) {
-                const unsigned hb = Ss[t] & E;         // v = column - row: smallest for the highest row, largest for the lowest
-                if (hb) { hmin = atr_min(hmin, j + t - atr_msb(hb)); hmax = atr_max(hmax, j + t - atr_ctz(hb)); }
-            }
-        }
-        j += 8; pos += 8;
+    // Whole words: the piece ends of G consecutive columns are folded into one word H, column t's shifted right by
+    // t, so that bit b of H = a piece ending in row r1 at column j + t with r1 - t = b, i.e. on diagonal v = j - b:
+    // one test and one msb / ctz per group instead of one per column (the hits sit in a few lanes of a warp, so
+    // every instruction spent on them runs almost empty). G = 8 needs every piece to end in row >= 8 (bit >= 7).
+    if (ad.sa_end & 0x7Fu) {
+        while (pos + 8 <= pend) { sa_word<4>(codes[pos >> 3], St, S0, E, sa_pair, j, hmin, hmax); j += 8; pos += 8; }
+    } else {
+        while (pos + 8 <= pend) { sa_word<8>(codes[pos >> 3], St, S0, E, sa_pair, j, hmin, hmax); j += 8; pos += 8; }
     }
     if (pos < pend) {
         const uint32_t w = codes[pos >> 3];

@@ -43,9 +43,14 @@ def main(tag, reads=10_000_000):
         with open(os.path.join(PROF, "r1_%s_source_hot.csv" % kernel), "w") as fh:
             for ln in lines:
                 fh.write(",".join(next(csv.reader([ln]))[:8]) + "\n") if ln.startswith('"0x') or ln.startswith('"Address') else None
-    json.dump(traffic, open(os.path.join(PROF, "traffic.json"), "w"), indent=1)
-    with open(os.path.join(PROF, "r1_kernel_summary.json"), "w") as fh:
-        json.dump(dict(summary), fh, indent=1)
+    # merge into what is tracked already: a refresh may cover only the kernels that changed
+    tpath, spath = os.path.join(PROF, "traffic.json"), os.path.join(PROF, "r1_kernel_summary.json")
+    old_t = json.load(open(tpath)) if os.path.exists(tpath) else {}
+    old_s = json.load(open(spath)) if os.path.exists(spath) else {}
+    old_t.update(traffic)
+    old_s.update(dict(summary))
+    json.dump(old_t, open(tpath, "w"), indent=1)
+    json.dump(old_s, open(spath, "w"), indent=1)
     for name, dst in (("launches_%s.csv" % tag, "r1_launches_fastpath.csv"), ("bench_%s.log" % tag, "r1_bench_line.json")):
         p = os.path.join(OUT, name)
         if os.path.exists(p):
