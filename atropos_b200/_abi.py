@@ -4,7 +4,9 @@ import ctypes as C
 import numpy as np
 
 ATR_ABI_VERSION = 1
-ATR_OK, ATR_E_ARG, ATR_E_CUDA, ATR_E_NOMEM, ATR_E_LIMIT = 0, -1, -2, -3, -4
+ATR_OK, ATR_E_ARG, ATR_E_CUDA, ATR_E_NOMEM, ATR_E_LIMIT, ATR_E_FORMAT = 0, -1, -2, -3, -4, -5
+(ATR_FQ_OK, ATR_FQ_NO_AT, ATR_FQ_NO_PLUS, ATR_FQ_NAME_MISMATCH, ATR_FQ_LENGTH, ATR_FQ_TRUNCATED, ATR_FQ_BARE_CR,
+ ATR_FQ_TOO_LONG, ATR_FQ_INVALID_MATCH) = range(9)
 ATR_ST_NONE, ATR_ST_MATCH, ATR_ST_ESCAPED, ATR_ST_INVALID, ATR_ST_KEYERROR = 0, 1, 2, 3, 4
 
 
@@ -38,6 +40,22 @@ class AtrInsertDesc(C.Structure):
                 ("adapter_check_cutoff", C.c_int32), ("adapter_wildcards", C.c_int32),
                 ("read_wildcards", C.c_int32), ("max_len", C.c_int32),
                 ("insert_prob", C.c_void_p), ("adapter_prob", C.c_void_p)]
+
+
+class AtrFastqError(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("line_in_record", C.c_int32), ("record", C.c_int64), ("line_begin", C.c_int64),
+                ("line_end", C.c_int64), ("terminated", C.c_int32), ("pad", C.c_int32)]
+
+
+class AtrTrimOpts(C.Structure):
+    _fields_ = [("times", C.c_int32), ("max_len", C.c_int32), ("max_errors", C.c_int32), ("final_chunk", C.c_int32),
+                ("chunk_bytes", C.c_int64)]
+
+
+class AtrTrimStats(C.Structure):
+    _fields_ = [("records", C.c_int64), ("with_adapters", C.c_int64), ("bp_in", C.c_int64), ("bp_out", C.c_int64),
+                ("overflow", C.c_int64), ("errors_front", C.c_void_p), ("errors_back", C.c_void_p),
+                ("adjacent_bases", C.c_void_p)]
 
 
 def make_adapter_desc(sequence, max_error_rate, flags, wildcard_ref=False, wildcard_query=False, min_overlap=1,

@@ -35,6 +35,10 @@ struct DevBuf {
     template <class T> T* as() const { return (T*)p; }
 };
 
+}  // namespace
+struct FqInfo;                           // fastq_kernels.cuh
+namespace {
+
 // per-stream working set of the host entry points
 struct Slot {
     cudaStream_t stream = nullptr;
@@ -42,10 +46,15 @@ struct Slot {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     DevBuf ascii, offsets, win, counts, woff, codes, len, out, scan_tmp, gen_scratch, lists;
     DevBuf ascii2, offsets2, counts2, woff2, codes2, len2;     // second mate (insert aligner)
+    // FASTQ path (atr_fastq_api.cuh): chunk text, newline index, record table, windows, formatted text
+    DevBuf fq_text, fq_tiles, fq_tile_offs, fq_nl, fq_info, fq_recs, fq_len64, fq_outoff, fq_fwin, fq_outtext;
+    FqInfo* fq_hinfo = nullptr;          // pinned
     void release() {
         DevBuf* all[] = {&ascii, &offsets, &win, &counts, &woff, &codes, &len, &out, &scan_tmp, &gen_scratch, &lists,
-                         &ascii2, &offsets2, &counts2, &woff2, &codes2, &len2};
+                         &ascii2, &offsets2, &counts2, &woff2, &codes2, &len2,
+                         &fq_text, &fq_tiles, &fq_tile_offs, &fq_nl, &fq_info, &fq_recs, &fq_len64, &fq_outoff, &fq_fwin, &fq_outtext};
         for (DevBuf* b : all) b->release();
+        if (fq_hinfo) { cudaFreeHost(fq_hinfo); fq_hinfo = nullptr; }
     }
 };
 
@@ -65,6 +74,7 @@ struct atr_ctx {
     int disable_sa = 0;
     int disable_fused = 0;           // ATR_DISABLE_FUSED=1: always use the plain register-DP kernel (A/B measurements)
     DevBuf misc;                     // small single-call scratch (compare_prefixes, multi_locate)
+    DevBuf fq_stats;                 // counters + histograms of atr_trim_fastq_host
 };
 
 struct atr_adapterset {
@@ -312,6 +322,7 @@ void atr_ctx_destroy(atr_ctx* ctx) {
         ctx->slot[s].release();
     }
     ctx->misc.release();
+    ctx->fq_stats.release();
     for (int i = 0; i < 5; i++) if (ctx->pev[i]) cudaEventDestroy(ctx->pev[i]);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -672,3 +683,5 @@ int atr_multi_locate(atr_ctx* ctx, const char* reference, int32_t m, const char*
 }
 
 }  // extern "C"
+
+#include "atr_fastq_api.cuh"

@@ -1,0 +1,155 @@
+// fastq_core.cuh -- per-record logic of the FASTQ-in -> trimmed-FASTQ-out path ("next" rows f-1/f-2/f-3 of
+// SURVEY.md section 8), __host__ __device__ so that tests/host_sim runs the very same functions on the CPU.
+//
+// What it restates (paths relative to the reference checkout):
+//   fq_frame    FastqReader.__iter__            atropos/io/_seqio.pyx:180-245  (+ Sequence.__init__ :33-44)
+//   fq_apply    AdapterCutter.__call__ loop     atropos/commands/trim/modifiers.py:141-149
+//               Adapter._trimmed_front / _back  atropos/adapters/__init__.py:413-436
+//               Match._guess_is_front           atropos/align/__init__.py:108-114
+//   fq_out_len / fq_out_byte   FastqFormat.format_entry   atropos/io/seqio.py:693-700
+//
+// Text model: the reference opens the file in text mode (io/__init__.py:148-149), i.e. with universal newlines:
+// "\r\n" reaches the reader as "\n". A bare '\r' (not followed by '\n') would also split a line there; that is
+// not reproduced -- such input is refused (ATR_FQ_BARE_CR) instead of being framed differently.
+#pragma once
+#include "atr_common.cuh"
+
+struct FqLine {
+    uint32_t b, e;       // content [b, e): without the terminator ("\n" or "\r\n")
+    int term;            // 1: a '\n' ended the line; 0: the text ended first (only the last line of a file)
+};
+
+// 20 bytes per record: where its pieces are in the chunk's text
+struct FqRec {
+    uint32_t hdr_b;      // '@'
+    uint32_t seq_b;
+    uint32_t qual_b;
+    uint16_t hdr_len;    // "@name" without terminator
+    uint16_t seq_len;    // == quality length for every accepted record
+    uint16_t name2;      // 1: the '+' line repeats the name
+    uint16_t pad;
+};
+
+// line li of the chunk; nl[] = ascending positions of '\n', n_nl of them. Line n_nl (if any) is unterminated.
+ATR_HD FqLine fq_line(const unsigned char* __restrict__ text, const uint32_t* __restrict__ nl, int64_t n_nl, int64_t nbytes,
+                      int64_t li) {
+    FqLine L;
+    L.b = li == 0 ? 0u : nl[li - 1] + 1u;
+    if (li < n_nl) {
+        L.e = nl[li];
+        L.term = 1;
+        if (L.e > L.b && text[L.e - 1] == '\r') L.e--;
+    } else {
+        L.e = (uint32_t)nbytes;
+        L.term = 0;
+    }
+    return L;
+}
+
+// The reader slices every line with `line[:strip]`, strip = -1 (the "\n"): an unterminated line loses its last
+// character that way (_seqio.pyx:196-197, :207-209, :213).
+ATR_HD uint32_t fq_sliced_end(const FqLine& L) { return L.term ? L.e : (L.e > L.b ? L.e - 1u : L.b); }
+
+// Frame and validate record r (lines 4r .. 4r+3). lines_avail < 4 only for the partial record at the end of the
+// input: its lines are still checked in order before the reader reports "ended prematurely" (:244-245).
+// Returns ATR_FQ_OK or the ATR_FQ_* kind; *bad_line = index (0..3) of the offending line.
+ATR_HD int fq_frame(const unsigned char* __restrict__ text, const uint32_t* __restrict__ nl, int64_t n_nl, int64_t nbytes,
+                    int64_t r, int lines_avail, FqRec& R, int& bad_line) {
+    R.hdr_b = R.seq_b = R.qual_b = 0; R.hdr_len = R.seq_len = R.name2 = R.pad = 0;
+    bad_line = 0;
+    // line 0: `if not (line and line[0] == '@')` (:202-206)
+    const FqLine h = fq_line(text, nl, n_nl, nbytes, 4 * r);
+    if (!(h.e > h.b && text[h.b] == '@')) return ATR_FQ_NO_AT;
+    const uint32_t name_b = h.b + 1u, name_e = fq_sliced_end(h);
+    if (lines_avail < 2) { bad_line = 1; return ATR_FQ_TRUNCATED; }
+    const FqLine s = fq_line(text, nl, n_nl, nbytes, 4 * r + 1);
+    const uint32_t seq_e = fq_sliced_end(s);
+    if (lines_avail < 3) { bad_line = 2; return ATR_FQ_TRUNCATED; }
+    // line 2: '+\n' is the common case; else the sliced line must start with '+', and if it goes on it must
+    // repeat the name (:210-230)
+    const FqLine p = fq_line(text, nl, n_nl, nbytes, 4 * r + 2);
+    const uint32_t plus_e = fq_sliced_end(p);
+    bad_line = 2;
+    if (!(plus_e > p.b && text[p.b] == '+')) return ATR_FQ_NO_PLUS;
+    int name2 = 0;
+    if (plus_e - p.b > 1u) {
+        const uint32_t l2 = plus_e - (p.b + 1u);
+        bool same = l2 == (name_e >= name_b ? name_e - name_b : 0u);
+        for (uint32_t t = 0; same && t < l2; t++) same = text[p.b + 1u + t] == text[name_b + t];
+        if (!same) return ATR_FQ_NAME_MISMATCH;
+        name2 = 1;
+    }
+    if (lines_avail < 4) { bad_line = 3; return ATR_FQ_TRUNCATED; }
+    // line 3: `if len(line) == len(sequence) - strip: qualities = line[:strip] else: line.rstrip('\r\n')`
+    // (:231-235): a terminated line is its content; an unterminated one that is exactly one character too long
+    // loses that character (and is accepted), anything else is kept whole. Then Sequence.__init__ demands equal
+    // lengths (:33-44), reported as "Error creating sequence record" (:236-241).
+    const FqLine q = fq_line(text, nl, n_nl, nbytes, 4 * r + 3);
+    const uint32_t slen = seq_e - s.b;
+    uint32_t qlen = q.e - q.b;
+    if (!q.term && qlen == slen + 1u) qlen = slen;
+    bad_line = 3;
+    if (qlen != slen) return ATR_FQ_LENGTH;
+    if (slen > (uint32_t)ATR_MAX_READ || h.e - h.b > 65535u) return ATR_FQ_TOO_LONG;
+    R.hdr_b = h.b; R.seq_b = s.b; R.qual_b = q.b;
+    R.hdr_len = (uint16_t)(h.e - h.b); R.seq_len = (uint16_t)slen; R.name2 = (uint16_t)name2;
+    bad_line = 0;
+    return ATR_FQ_OK;
+}
+
+// One round of AdapterCutter.__call__ for one read: the match record `m` (coordinates relative to the window
+// [lo, hi) the previous rounds left) -> new window and the statistics bin. front_flag: 1 FRONT/PREFIX, 0 BACK/SUFFIX,
+// -1 ANYWHERE (front iff rstart == 0). Returns false if the record is not a match (the loop ends for this read).
+struct FqApply {
+    int front;           // which histogram
+    int length;          // lengths_front[rstop] / lengths_back[len(read) - rstart]
+    int errors;
+    int adjacent;        // 0..3 = A C G T, 4 = '' (anything else, or no base before the adapter); back only
+    int new_lo, new_hi;
+};
+
+ATR_HD bool fq_apply(const atr_match& m, int front_flag, int lo, int hi, const unsigned char* __restrict__ seq, FqApply& a) {
+    if (m.status != ATR_ST_MATCH) return false;
+    const int rstart = m.rstart, rstop = m.rstop;
+    a.front = front_flag < 0 ? (rstart == 0) : front_flag;
+    a.errors = m.errors;
+    a.adjacent = 4;
+    if (a.front) {
+        a.length = rstop;
+        a.new_lo = lo + rstop; a.new_hi = hi;
+    } else {
+        a.length = (hi - lo) - rstart;
+        if (rstart >= 1) {
+            const unsigned char c = seq[lo + rstart - 1];          // the original letter: 'a' is not in 'ACGT'
+            a.adjacent = c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : 4;
+        }
+        a.new_lo = lo; a.new_hi = lo + rstart;
+    }
+    return true;
+}
+
+// '@' name '\n' sequence '\n+' name2 '\n' qualities '\n'
+ATR_HD uint32_t fq_out_len(const FqRec& R, int lo, int hi) {
+    const uint32_t w = (uint32_t)(hi - lo);
+    return (uint32_t)R.hdr_len + 1u + w + 1u + (R.name2 ? (uint32_t)R.hdr_len : 1u) + 1u + w + 1u;
+}
+
+// byte i of the formatted record
+ATR_HD unsigned char fq_out_byte(const unsigned char* __restrict__ text, const FqRec& R, int lo, int hi, uint32_t i) {
+    const uint32_t w = (uint32_t)(hi - lo), H = R.hdr_len;
+    if (i < H) return text[R.hdr_b + i];
+    i -= H;
+    if (i == 0) return '\n';
+    i -= 1;
+    if (i < w) return text[R.seq_b + (uint32_t)lo + i];
+    i -= w;
+    if (i == 0) return '\n';
+    i -= 1;
+    const uint32_t P = R.name2 ? H : 1u;
+    if (i < P) return i == 0 ? (unsigned char)'+' : text[R.hdr_b + i];
+    i -= P;
+    if (i == 0) return '\n';
+    i -= 1;
+    if (i < w) return text[R.qual_b + (uint32_t)lo + i];
+    return '\n';
+}

@@ -1,0 +1,244 @@
+// fastq_kernels.cuh -- the __global__ kernels of the FASTQ-in -> trimmed-FASTQ-out path (sm_100a).
+// All of them are HBM-bound byte work: 16-byte vector loads where the layout allows, one pass per stage,
+// nothing re-read from PCIe. Per-record logic lives in fastq_core.cuh (shared with the host simulator).
+#pragma once
+#include <cuda_runtime.h>
+#include "fastq_core.cuh"
+
+#define FQ_THREADS 256
+#define FQ_TILE (FQ_THREADS * 16)        // bytes of text per CTA of the newline kernels
+
+// device-side bookkeeping of one chunk
+struct FqInfo {
+    unsigned long long err_key;      // min over errors of (line index << 8 | kind); ~0 = none
+    unsigned long long out_bytes;    // total size of the formatted chunk
+    long long n_nl;                  // '\n' count of the chunk
+    long long n_rec;                 // complete records
+    long long consumed;              // bytes up to and including the last complete record
+    int nl_overflow;                 // the newline index did not fit its buffer
+    int lines_left;                  // lines of a trailing partial record
+    int bare_cr;
+    int pad;
+};
+
+// statistics block shared by all chunks of a call (atomics)
+struct FqCounters {
+    unsigned long long records, with_adapters, bp_in, bp_out, overflow, invalid;
+};
+
+// 16 text bytes -> bit i set iff byte i == c. __vcmpeq4 gives 0xff per equal byte; the multiply gathers the four
+// low bits into bits 24..27 (distinct powers, no carries).
+__device__ __forceinline__ unsigned fq_eq_mask16(const uint4& v, unsigned c4) {
+    const unsigned a = ((__vcmpeq4(v.x, c4) & 0x01010101u) * 0x01020408u) >> 24;
+    const unsigned b = ((__vcmpeq4(v.y, c4) & 0x01010101u) * 0x01020408u) >> 24;
+    const unsigned c = ((__vcmpeq4(v.z, c4) & 0x01010101u) * 0x01020408u) >> 24;
+    const unsigned d = ((__vcmpeq4(v.w, c4) & 0x01010101u) * 0x01020408u) >> 24;
+    return a | (b << 4) | (c << 8) | (d << 12);
+}
+
+__device__ __forceinline__ uint4 fq_load16(const unsigned char* __restrict__ text, long long nbytes, long long off) {
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (off + 16 <= nbytes) {
+        v = *reinterpret_cast<const uint4*>(text + off);
+    } else if (off < nbytes) {
+        unsigned w[4] = {0u, 0u, 0u, 0u};
+        for (int i = 0; off + i < nbytes; i++) w[i >> 2] |= (unsigned)text[off + i] << (8 * (i & 3));
+        v = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    return v;
+}
+
+// pass 1: newlines per tile; bare carriage returns
+__global__ void __launch_bounds__(FQ_THREADS) k_fq_nl_count(const unsigned char* __restrict__ text, long long nbytes, int final_text,
+                                                            unsigned* __restrict__ tile_counts, FqInfo* __restrict__ info) {
+    __shared__ unsigned s_warp[FQ_THREADS / 32];
+    const long long off = ((long long)blockIdx.x * FQ_THREADS + threadIdx.x) * 16;
+    const uint4 v = fq_load16(text, nbytes, off);
+    const unsigned nlm = fq_eq_mask16(v, 0x0a0a0a0au);
+    const unsigned crm = fq_eq_mask16(v, 0x0d0d0d0du);
+    if (crm) {
+        unsigned ok = nlm >> 1;                                   // '\r' at byte i is fine if byte i+1 is '\n'
+        if ((crm & 0x8000u) && off + 16 < nbytes && text[off + 16] == '\n') ok |= 0x8000u;
+        unsigned bad = crm & ~ok;
+        // the text's very last byte has no successor yet: acceptable only when more text follows in a later call
+        const long long last = nbytes - 1 - off;
+        if (!final_text && last >= 0 && last < 16) bad &= ~(1u << last);
+        if (bad) info->bare_cr = 1;
+    }
+    unsigned c = __popc(nlm);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) c += __shfl_down_sync(0xffffffffu, c, d);
+    if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned t = 0;
+#pragma unroll
+        for (int w = 0; w < FQ_THREADS / 32; w++) t += s_warp[w];
+        tile_counts[blockIdx.x] = t;
+    }
+}
+
+// pass 2: positions of the newlines, in order (tile_offs = exclusive scan of tile_counts)
+__global__ void __launch_bounds__(FQ_THREADS) k_fq_nl_fill(const unsigned char* __restrict__ text, long long nbytes,
+                                                           const unsigned* __restrict__ tile_offs, uint32_t* __restrict__ nl,
+                                                           long long nl_cap, FqInfo* __restrict__ info) {
+    __shared__ unsigned s_warp[FQ_THREADS / 32];
+    const long long off = ((long long)blockIdx.x * FQ_THREADS + threadIdx.x) * 16;
+    const uint4 v = fq_load16(text, nbytes, off);
+    unsigned nlm = fq_eq_mask16(v, 0x0a0a0a0au);
+    const unsigned cnt = __popc(nlm);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned inc = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += t;
+    }
+    if (lane == 31) s_warp[wid] = inc;
+    __syncthreads();
+    unsigned wbase = 0;
+#pragma unroll
+    for (int w = 0; w < FQ_THREADS / 32; w++) wbase += (w < wid) ? s_warp[w] : 0u;
+    long long pos = (long long)tile_offs[blockIdx.x] + wbase + (inc - cnt);
+    while (nlm) {
+        const int b = __ffs((int)nlm) - 1;
+        nlm &= nlm - 1;
+        if (pos < nl_cap) nl[pos] = (uint32_t)(off + b);
+        else info->nl_overflow = 1;
+        pos++;
+    }
+}
+
+// one thread: lines -> complete records, consumed bytes (tile_offs[n_tiles] = total newline count)
+__global__ void k_fq_info(const unsigned* __restrict__ tile_offs, int n_tiles, const uint32_t* __restrict__ nl, long long nl_cap,
+                          long long nbytes, int unterminated_last_line, FqInfo* __restrict__ info) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    const long long n_nl = tile_offs[n_tiles];
+    const long long lines = n_nl + (unterminated_last_line ? 1 : 0);
+    const long long n_rec = lines / 4;
+    info->n_nl = n_nl;
+    info->n_rec = n_rec;
+    info->lines_left = (int)(lines % 4);
+    long long consumed = 0;
+    if (n_rec > 0) {
+        const long long last = 4 * n_rec - 1;                     // line index of the last quality line
+        if (last < n_nl) consumed = (last < nl_cap) ? (long long)nl[last] + 1 : 0;
+        else consumed = nbytes;                                   // it is the unterminated last line
+    }
+    info->consumed = consumed;
+}
+
+__device__ __forceinline__ void fq_report(FqInfo* info, long long line, int kind) {
+    atomicMin(&info->err_key, ((unsigned long long)line << 8) | (unsigned long long)kind);
+}
+
+// frame + validate: one thread per record (plus one for a trailing partial record when the text is final)
+__global__ void __launch_bounds__(256) k_fq_frame(const unsigned char* __restrict__ text, const uint32_t* __restrict__ nl,
+                                                  long long n_nl, long long nbytes, long long n_rec, int lines_left,
+                                                  FqRec* __restrict__ recs, long long* __restrict__ seq_len64,
+                                                  FqInfo* __restrict__ info) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r > n_rec || (r == n_rec && lines_left == 0)) return;
+    FqRec R;
+    int bad = 0;
+    const int avail = r < n_rec ? 4 : lines_left;
+    const int kind = fq_frame(text, nl, n_nl, nbytes, r, avail, R, bad);
+    if (kind != ATR_FQ_OK) fq_report(info, 4 * r + bad, kind);
+    if (r < n_rec) {
+        recs[r] = R;
+        seq_len64[r] = R.seq_len;
+    }
+}
+
+// sequence lines -> contiguous ASCII batch (the layout the packer and the byte-exact kernel take): warp per record
+__global__ void __launch_bounds__(256) k_fq_gather(const unsigned char* __restrict__ text, const FqRec* __restrict__ recs,
+                                                   const long long* __restrict__ offsets, long long n_rec,
+                                                   unsigned char* __restrict__ ascii) {
+    const long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (r >= n_rec) return;
+    const int lane = threadIdx.x & 31;
+    const FqRec R = recs[r];
+    const unsigned char* src = text + R.seq_b;
+    unsigned char* dst = ascii + offsets[r];
+    for (int i = lane; i < (int)R.seq_len; i += 32) dst[i] = src[i];
+}
+
+// initial windows
+__global__ void __launch_bounds__(256) k_fq_init_win(const FqRec* __restrict__ recs, long long n_rec, uint16_t* __restrict__ fwin,
+                                                     FqCounters* __restrict__ ctr) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long bp = 0;
+    if (r < n_rec) {
+        const unsigned len = recs[r].seq_len;
+        fwin[2 * r] = 0; fwin[2 * r + 1] = (uint16_t)len;
+        bp = len;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) bp += __shfl_down_sync(0xffffffffu, bp, d);
+    if ((threadIdx.x & 31) == 0 && bp) atomicAdd(&ctr->bp_in, bp);
+    if (r == 0) atomicAdd(&ctr->records, (unsigned long long)n_rec);
+}
+
+// one round of the AdapterCutter loop: shrink the windows, count. hist_front/back: [a][max_len+1][max_errors+1]
+__global__ void __launch_bounds__(256) k_fq_apply(const unsigned char* __restrict__ text, const FqRec* __restrict__ recs,
+                                                  const atr_match* __restrict__ matches, long long n_rec, int round, int more_rounds,
+                                                  const signed char* __restrict__ front_flags, int max_len, int max_errors,
+                                                  uint16_t* __restrict__ fwin, uint16_t* __restrict__ rwin,
+                                                  unsigned long long* __restrict__ hist_front, unsigned long long* __restrict__ hist_back,
+                                                  unsigned long long* __restrict__ adjacent, FqCounters* __restrict__ ctr) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    bool hit = false;
+    if (r < n_rec) {
+        const atr_match m = matches[r];
+        const int lo = fwin[2 * r], hi = fwin[2 * r + 1];
+        FqApply a;
+        if (m.status == ATR_ST_INVALID) atomicAdd(&ctr->invalid, 1ull);
+        if (fq_apply(m, m.adapter >= 0 ? front_flags[m.adapter] : 0, lo, hi, text + recs[r].seq_b, a)) {
+            hit = true;
+            if (a.length <= max_len && a.errors <= max_errors) {
+                unsigned long long* h = a.front ? hist_front : hist_back;
+                atomicAdd(&h[((size_t)m.adapter * (size_t)(max_len + 1) + (size_t)a.length) * (size_t)(max_errors + 1) + (size_t)a.errors], 1ull);
+            } else {
+                atomicAdd(&ctr->overflow, 1ull);
+            }
+            if (!a.front) atomicAdd(&adjacent[(size_t)m.adapter * 5 + (size_t)a.adjacent], 1ull);
+            fwin[2 * r] = (uint16_t)a.new_lo; fwin[2 * r + 1] = (uint16_t)a.new_hi;
+            if (more_rounds) { rwin[2 * r] = (uint16_t)a.new_lo; rwin[2 * r + 1] = (uint16_t)a.new_hi; }
+        } else if (more_rounds) {
+            rwin[2 * r] = 0; rwin[2 * r + 1] = 0;                // no match: the loop ends for this read (:145-147)
+        }
+    }
+    if (round == 0) {
+        const unsigned b = __ballot_sync(0xffffffffu, hit);
+        if ((threadIdx.x & 31) == 0 && b) atomicAdd(&ctr->with_adapters, (unsigned long long)__popc(b));
+    }
+}
+
+__global__ void __launch_bounds__(256) k_fq_outlen(const FqRec* __restrict__ recs, const uint16_t* __restrict__ fwin, long long n_rec,
+                                                   long long* __restrict__ out_len, FqCounters* __restrict__ ctr) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long bp = 0;
+    if (r < n_rec) {
+        const int lo = fwin[2 * r], hi = fwin[2 * r + 1];
+        out_len[r] = fq_out_len(recs[r], lo, hi);
+        bp = (unsigned long long)(hi - lo);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) bp += __shfl_down_sync(0xffffffffu, bp, d);
+    if ((threadIdx.x & 31) == 0 && bp) atomicAdd(&ctr->bp_out, bp);
+}
+
+// formatted records: warp per record, lanes stride the output bytes (coalesced stores)
+__global__ void __launch_bounds__(256) k_fq_format(const unsigned char* __restrict__ text, const FqRec* __restrict__ recs,
+                                                   const uint16_t* __restrict__ fwin, const long long* __restrict__ out_off,
+                                                   long long n_rec, unsigned char* __restrict__ out, FqInfo* __restrict__ info) {
+    const long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (r >= n_rec) return;
+    const int lane = threadIdx.x & 31;
+    const FqRec R = recs[r];
+    const int lo = fwin[2 * r], hi = fwin[2 * r + 1];
+    const uint32_t total = fq_out_len(R, lo, hi);
+    unsigned char* dst = out + out_off[r];
+    for (uint32_t i = lane; i < total; i += 32) dst[i] = fq_out_byte(text, R, lo, hi, i);
+    if (r == n_rec - 1 && lane == 0) info->out_bytes = (unsigned long long)(out_off[r] + total);
+}

@@ -111,3 +111,27 @@ def synth_pe(n, L, adapter1=TRUSEQ_R1, adapter2=TRUSEQ_R2, seed=BASE_SEED, devic
     if len(o1) == 1:
         return o1[0], o2[0]
     return torch.cat(o1, 0), torch.cat(o2, 0)
+
+
+def fastq_text(reads, name_prefix="r", qual_char=73):
+    """reads: uint8 array/tensor [n, L] (ASCII) -> FASTQ text as a uint8 numpy array, records
+    '@<prefix><9-digit index>\\n<read>\\n+\\n<qualities>\\n' (fixed-width names keep the construction vectorised)."""
+    import numpy as np
+    reads = reads.cpu().numpy() if hasattr(reads, "cpu") else np.asarray(reads)
+    n, L = reads.shape
+    p = np.frombuffer(name_prefix.encode("ascii"), dtype=np.uint8)
+    H = 1 + len(p) + 9
+    rec = np.empty((n, H + 1 + L + 1 + 2 + L + 1), dtype=np.uint8)
+    rec[:, 0] = 64
+    rec[:, 1:1 + len(p)] = p
+    idx = np.arange(n, dtype=np.int64)
+    for d in range(9):
+        rec[:, H - 1 - d] = 48 + (idx // 10 ** d) % 10
+    rec[:, H] = 10
+    rec[:, H + 1:H + 1 + L] = reads
+    rec[:, H + 1 + L] = 10
+    rec[:, H + 2 + L] = 43
+    rec[:, H + 3 + L] = 10
+    rec[:, H + 4 + L:H + 4 + 2 * L] = qual_char
+    rec[:, H + 4 + 2 * L] = 10
+    return rec.reshape(-1)

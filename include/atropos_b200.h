@@ -49,6 +49,7 @@ extern "C" {
 #define ATR_E_CUDA     -2   /* CUDA runtime error / no device */
 #define ATR_E_NOMEM    -3   /* allocation failed (MemoryError, _align.pyx:240-241) */
 #define ATR_E_LIMIT    -4   /* size outside what the kernels support (read > 32767 nt, adapter > 4095 nt) */
+#define ATR_E_FORMAT   -5   /* malformed FASTQ: the reader's FormatError (io/_seqio.pyx:180-245); see atr_fastq_error */
 
 /* alignment flags: atropos/align/__init__.py:17-26, _align.pyx:12-16 */
 #define ATR_START_WITHIN_SEQ1 1
@@ -216,6 +217,63 @@ int  atr_match_insert_batch_host(atr_ctx* ctx, const atr_insertset* set,
 int  atr_multi_locate(atr_ctx* ctx, const char* reference, int32_t m, const char* query, int32_t n,
                       double max_error_rate, int32_t flags, int32_t min_overlap, int32_t max_matches,
                       int32_t* out6, int32_t* n_out);
+
+/* ---- FASTQ text in -> trimmed FASTQ text out ("next" rows of the hot path: its reader and its consumer) ---- */
+/* atr_fastq_error.kind: the FormatErrors of FastqReader.__iter__ (io/_seqio.pyx:180-245) */
+#define ATR_FQ_OK            0
+#define ATR_FQ_NO_AT         1   /* "Line 1 in FASTQ file is expected to start with '@', but found ..." (:192-195, :202-206) */
+#define ATR_FQ_NO_PLUS       2   /* "Line 3 in FASTQ file is expected to start with '+', but found ..." (:214-217) */
+#define ATR_FQ_NAME_MISMATCH 3   /* "At line 3: Sequence descriptions in the FASTQ file don't match" (:219-226) */
+#define ATR_FQ_LENGTH        4   /* "Error creating sequence record at line 4": qualities and sequence differ in length (:33-44, :236-241) */
+#define ATR_FQ_TRUNCATED     5   /* "FASTQ file ended prematurely" (:244-245) */
+#define ATR_FQ_BARE_CR       6   /* a '\r' not followed by '\n' (universal-newline splitting is not reproduced: refused) */
+#define ATR_FQ_TOO_LONG      7   /* read > 32767 nt or header > 65535 bytes, or one record larger than a chunk */
+#define ATR_FQ_INVALID_MATCH 8   /* Match.__init__ would raise ValueError (align/__init__.py:85-88) */
+
+typedef struct atr_fastq_error {
+    int32_t kind;             /* ATR_FQ_* of the FIRST error in file order */
+    int32_t line_in_record;   /* 0..3 */
+    int64_t record;           /* index of the record within this call's text */
+    int64_t line_begin;       /* byte offsets of the offending line's content within this call's text */
+    int64_t line_end;         /* (terminator excluded) */
+    int32_t terminated;       /* 1: the line ends with a newline, 0: the text ended first */
+    int32_t pad;
+} atr_fastq_error;
+
+/* AdapterCutter(adapters, times, action='trim') (commands/trim/modifiers.py:91-105) */
+typedef struct atr_trim_opts {
+    int32_t times;            /* >= 1: rounds of best-match-and-trim per read (modifiers.py:141-149) */
+    int32_t max_len;          /* the statistics cover removed lengths 0..max_len ... */
+    int32_t max_errors;       /* ... and error counts 0..max_errors */
+    int32_t final_chunk;      /* 1: `text` ends the file (a partial last record is an error, an unterminated last
+                                 line is a line); 0: stop after the last complete record and report `consumed` */
+    int64_t chunk_bytes;      /* internal H2D chunk size, 0 = default (64 MiB) */
+} atr_trim_opts;
+
+/* What Adapter.trimmed() accumulates (adapters/__init__.py:413-436) and the report prints. The histogram
+ * arrays are caller-allocated and ADDED to (zero them first; calls and shards then merge by themselves, like
+ * Summary.merge, commands/multicore.py:389). Index: ((a*(max_len+1) + length)*(max_errors+1) + errors;
+ * lengths_front/back of the reference are the row sums. */
+typedef struct atr_trim_stats {
+    int64_t records, with_adapters, bp_in, bp_out;
+    int64_t overflow;         /* matches outside the histogram extents (not counted in the arrays) */
+    int64_t* errors_front;    /* [n_adapters][max_len+1][max_errors+1] */
+    int64_t* errors_back;     /* same shape */
+    int64_t* adjacent_bases;  /* [n_adapters][5]: A, C, G, T, '' (anything else) */
+} atr_trim_stats;
+
+/* Replaces, for single-end FASTQ and the adapter-trimming modifier, the per-record pipeline
+ *   FastqReader.__iter__ (io/_seqio.pyx:180-245) -> AdapterCutter.__call__ (modifiers.py:124-187; reads are
+ *   upper-cased for matching only, adapters/__init__.py:349) -> Adapter.trimmed (adapters/__init__.py:413-436)
+ *   -> FastqFormat.format (io/seqio.py:686-700)
+ * by one pass on the GPU: newline index, record framing + validation, 4-bit packing, the adapter-alignment
+ * kernels, trimming windows + statistics, formatting. `text`/`out_text` are HOST buffers (pinned for full speed);
+ * out_cap >= nbytes always suffices (trimming never grows a record). The adapter set must have been created with
+ * match_to_semantics = 1. *consumed = bytes of `text` that were processed (all of it if final_chunk).
+ * On ATR_E_FORMAT *err describes the first malformed line. */
+int  atr_trim_fastq_host(atr_ctx* ctx, const atr_adapterset* set, const atr_trim_opts* opts,
+                         const uint8_t* text, int64_t nbytes, uint8_t* out_text, int64_t out_cap,
+                         int64_t* out_bytes, int64_t* consumed, atr_trim_stats* stats, atr_fastq_error* err);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,41 @@
+"""Shared by the CPU (host simulator) and GPU tests of the FASTQ path: golden cases produced by the reference
+command line (tests/golden/make_fastq_golden.py) and the comparison of a result with them."""
+import golden_util
+from atropos_b200.adapters import ANYWHERE, BACK, FRONT, Adapter
+
+WHERE = {"back": BACK, "front": FRONT, "anywhere": ANYWHERE}
+
+
+def cases():
+    return golden_util.load("fastq_trim")
+
+
+def adapters_of(case):
+    """Adapter objects in the order the reference's AdapterCutter tried them (the order of its report)."""
+    res = case["result"]
+    if "adapters" in res:
+        order = [(a["sequence"], a["where"]) for a in res["adapters"]]
+    else:
+        order = [tuple(a) for a in case["adapters"]]
+    return [Adapter(seq, WHERE[w], max_error_rate=case["error_rate"], min_overlap=case["overlap"]) for seq, w in order]
+
+
+def _str_keys(d):
+    return {str(k): ({str(k2): v2 for k2, v2 in v.items()} if isinstance(v, dict) else v) for k, v in d.items()}
+
+
+def check(case, out, stats, adapters):
+    res = case["result"]
+    assert bytes(out) == res["out"].encode("latin-1")
+    assert stats.records == res["records"]
+    assert stats.with_adapters == res["with_adapters"]
+    assert stats.bp_in == res["bp_in"]
+    if res["bp_out"] is not None:
+        assert stats.bp_out == res["bp_out"]
+    assert stats.overflow == 0
+    for a, (ad, gold) in enumerate(zip(adapters, res["adapters"])):
+        mine = stats.adapter_summary(a, ad.where)
+        for key in ("lengths_front", "lengths_back", "errors_front", "errors_back", "adjacent_bases"):
+            assert (key in gold) == (key in mine), (case["label"], a, key)
+            if key in gold:
+                assert _str_keys(mine[key]) == gold[key], (case["label"], a, key)

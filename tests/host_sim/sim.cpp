@@ -7,6 +7,7 @@
 #include "../../atropos_b200/csrc/adapter_build.hpp"
 #include "../../atropos_b200/csrc/locate_core.cuh"
 #include "../../atropos_b200/csrc/insert_core.cuh"
+#include "../../atropos_b200/csrc/fastq_core.cuh"
 
 extern "C" {
 
@@ -101,6 +102,87 @@ int sim_multi_locate(const unsigned char* ref, int m, const unsigned char* query
     for (int l = 0; l <= m; l++) thr[l] = atr::thr_mul_of(l, rate);
     std::vector<GCellM> col((size_t)m + 1);
     return gen_multi_locate(ref, m, query, n, (int)(rate * m), thr.data(), flags, min_overlap, max_matches, col.data(), out6);
+}
+
+// The FASTQ-in -> trimmed-FASTQ-out path with the device functions of fastq_core.cuh (framing, window/statistics
+// bookkeeping, formatting) and sim_locate for the alignments: what atr_trim_fastq_host computes, one record at a
+// time. counters = {records, with_adapters, bp_in, bp_out, overflow}. Returns 0, or ATR_E_FORMAT with *err filled.
+int sim_trim_fastq(const atr_adapter_desc* descs, int n_adapters, const atr_trim_opts* o, const unsigned char* text,
+                   long long nbytes, unsigned char* out_text, long long* out_bytes, long long* consumed, long long* counters,
+                   long long* errors_front, long long* errors_back, long long* adjacent, atr_fastq_error* err) {
+    std::vector<uint32_t> nl;
+    for (long long i = 0; i < nbytes; i++) {
+        if (text[i] == '\n') nl.push_back((uint32_t)i);
+        if (text[i] == '\r' && !(i + 1 < nbytes && text[i + 1] == '\n') && (o->final_chunk || i + 1 < nbytes)) {
+            err->kind = ATR_FQ_BARE_CR; err->record = -1;
+            return ATR_E_FORMAT;
+        }
+    }
+    const long long n_nl = (long long)nl.size();
+    const int unterminated = o->final_chunk && nbytes > 0 && text[nbytes - 1] != '\n';
+    const long long lines = n_nl + unterminated, n_rec = lines / 4;
+    const int lines_left = o->final_chunk ? (int)(lines % 4) : 0;
+    *consumed = 0;
+    if (n_rec > 0) *consumed = (4 * n_rec - 1 < n_nl) ? (long long)nl[4 * n_rec - 1] + 1 : nbytes;
+    if (o->final_chunk) *consumed = nbytes;
+    nl.push_back(0);
+    std::vector<FqRec> recs((size_t)n_rec + 1);
+    long long bad_key = -1;
+    for (long long r = 0; r <= n_rec; r++) {
+        if (r == n_rec && lines_left == 0) break;
+        int bad = 0;
+        FqRec R;
+        const int kind = fq_frame(text, nl.data(), n_nl, nbytes, r, r < n_rec ? 4 : lines_left, R, bad);
+        if (r < n_rec) recs[(size_t)r] = R;
+        if (kind != ATR_FQ_OK) { bad_key = ((4 * r + bad) << 8) | kind; break; }       // records are visited in file order
+    }
+    if (bad_key >= 0) {
+        const long long line = bad_key >> 8;
+        err->kind = (int)(bad_key & 0xFF); err->record = line / 4; err->line_in_record = (int)(line % 4);
+        if (line >= lines) { err->line_begin = err->line_end = nbytes; err->terminated = 0; }
+        else {
+            err->line_begin = line > 0 ? (long long)nl[line - 1] + 1 : 0;
+            err->line_end = line < n_nl ? (long long)nl[line] : nbytes;
+            err->terminated = line < n_nl;
+        }
+        return ATR_E_FORMAT;
+    }
+    const size_t H = (size_t)(o->max_len + 1) * (size_t)(o->max_errors + 1);
+    long long opos = 0;
+    for (long long r = 0; r < n_rec; r++) {
+        const FqRec& R = recs[(size_t)r];
+        int lo = 0, hi = R.seq_len;
+        counters[0]++; counters[2] += R.seq_len;
+        bool any = false;
+        for (int round = 0; round < o->times; round++) {
+            atr_match m;
+            m.astart = m.astop = m.rstart = m.rstop = m.matches = m.errors = 0; m.adapter = -1; m.status = ATR_ST_NONE;
+            for (int a = 0; a < n_adapters; a++) {
+                int used = 0;
+                int rc = sim_locate(&descs[a], a, a > 0, text + R.seq_b, R.seq_len, lo, hi, 1, 0, &m, &used);
+                if (rc) return rc;
+            }
+            if (m.status == ATR_ST_INVALID) { err->kind = ATR_FQ_INVALID_MATCH; err->record = -1; return ATR_E_FORMAT; }
+            FqApply ap;
+            const int w = m.adapter >= 0 ? descs[m.adapter].flags : 0;
+            const int ff = (w == ATR_SEMIGLOBAL) ? -1 : ((w == 14 || w == 2) ? 0 : 1);
+            if (!fq_apply(m, ff, lo, hi, text + R.seq_b, ap)) break;
+            any = true;
+            if (ap.length <= o->max_len && ap.errors <= o->max_errors)
+                (ap.front ? errors_front : errors_back)[((size_t)m.adapter * (size_t)(o->max_len + 1) + (size_t)ap.length) * (size_t)(o->max_errors + 1) + (size_t)ap.errors]++;
+            else counters[4]++;
+            if (!ap.front) adjacent[(size_t)m.adapter * 5 + (size_t)ap.adjacent]++;
+            lo = ap.new_lo; hi = ap.new_hi;
+        }
+        (void)H;
+        if (any) counters[1]++;
+        counters[3] += hi - lo;
+        const uint32_t total = fq_out_len(R, lo, hi);
+        for (uint32_t i = 0; i < total; i++) out_text[opos + i] = fq_out_byte(text, R, lo, hi, i);
+        opos += total;
+    }
+    *out_bytes = opos;
+    return 0;
 }
 
 }  // extern "C"

@@ -29,6 +29,10 @@ def lib():
         L.sim_multi_locate.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int,
                                        C.POINTER(C.c_int)]
         L.sim_multi_locate.restype = C.c_int
+        L.sim_trim_fastq.argtypes = [C.POINTER(_abi.AtrAdapterDesc), C.c_int, C.POINTER(_abi.AtrTrimOpts), C.c_char_p,
+                                     C.c_longlong, C.c_void_p, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong),
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_abi.AtrFastqError)]
+        L.sim_trim_fastq.restype = C.c_int
         _lib = L
     return _lib
 
@@ -77,3 +81,28 @@ def multi_locate(ref, query, rate, flags, min_overlap, max_matches=100):
     if cnt == 0:
         return None
     return [tuple(out[6 * t:6 * t + 6]) for t in range(cnt)]
+
+
+def trim_fastq(text, adapters, times=1, max_len=512, final=True):
+    """CPU run of the FASTQ path's device functions. adapters: atropos_b200.adapters.Adapter objects.
+    Returns (out bytes, TrimStats, consumed) or raises atropos_b200.fastq.FormatError."""
+    import numpy as np
+    from atropos_b200 import fastq
+    descs, keep = zip(*[a.descriptor() for a in adapters])
+    arr = (_abi.AtrAdapterDesc * len(descs))(*descs)
+    max_errors = max(int(a.max_error_rate * len(a.sequence)) for a in adapters)
+    stats = fastq.TrimStats(len(adapters), max_len, max_errors)
+    opts = _abi.AtrTrimOpts(times, max_len, max_errors, int(bool(final)), 0)
+    out = np.empty(max(len(text), 1), dtype=np.uint8)
+    counters = np.zeros(5, dtype=np.int64)
+    nout, consumed = C.c_longlong(0), C.c_longlong(0)
+    err = _abi.AtrFastqError()
+    rc = lib().sim_trim_fastq(arr, len(descs), C.byref(opts), text, len(text), out.ctypes.data, C.byref(nout),
+                              C.byref(consumed), counters.ctypes.data, stats.errors_front.ctypes.data,
+                              stats.errors_back.ctypes.data, stats.adjacent.ctypes.data, C.byref(err))
+    if rc == _abi.ATR_E_FORMAT:
+        raise fastq.FormatError(fastq.format_error_message(np.frombuffer(text, dtype=np.uint8), err))
+    if rc != 0:
+        raise RuntimeError("sim_trim_fastq rc=%d" % rc)
+    stats.records, stats.with_adapters, stats.bp_in, stats.bp_out, stats.overflow = (int(x) for x in counters)
+    return bytes(out[:nout.value]), stats, consumed.value
