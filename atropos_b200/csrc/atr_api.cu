@@ -48,13 +48,18 @@ struct Slot {
     DevBuf ascii2, offsets2, counts2, woff2, codes2, len2;     // second mate (insert aligner)
     // FASTQ path (atr_fastq_api.cuh): chunk text, newline index, record table, windows, formatted text
     DevBuf fq_text, fq_tiles, fq_tile_offs, fq_nl, fq_info, fq_recs, fq_len64, fq_outoff, fq_fwin, fq_outtext;
-    FqInfo* fq_hinfo = nullptr;          // pinned
+    FqInfo* fq_hinfo = nullptr;          // mapped pinned
+    cudaStream_t fq_out_stream = nullptr; // D2H of the formatted text
+    cudaEvent_t fq_ev_d2h = nullptr;
+    int fq_d2h_pending = 0;
     void release() {
         DevBuf* all[] = {&ascii, &offsets, &win, &counts, &woff, &codes, &len, &out, &scan_tmp, &gen_scratch, &lists,
                          &ascii2, &offsets2, &counts2, &woff2, &codes2, &len2,
                          &fq_text, &fq_tiles, &fq_tile_offs, &fq_nl, &fq_info, &fq_recs, &fq_len64, &fq_outoff, &fq_fwin, &fq_outtext};
         for (DevBuf* b : all) b->release();
         if (fq_hinfo) { cudaFreeHost(fq_hinfo); fq_hinfo = nullptr; }
+        if (fq_out_stream) { cudaStreamSynchronize(fq_out_stream); cudaStreamDestroy(fq_out_stream); fq_out_stream = nullptr; }
+        if (fq_ev_d2h) { cudaEventDestroy(fq_ev_d2h); fq_ev_d2h = nullptr; }
     }
 };
 

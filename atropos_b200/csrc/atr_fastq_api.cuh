@@ -9,6 +9,7 @@
 // The H2D of chunk c+1 is issued as soon as chunk c's front is known, so it runs under chunk c's kernels and
 // chunk c-1's D2H (PCIe is full duplex).
 #pragma once
+#include <time.h>
 #include "fastq_kernels.cuh"
 
 namespace {
@@ -80,9 +81,9 @@ int fq_index(atr_ctx* ctx, Slot& s, const FqChunk& c, int final_text, int unterm
                                                                  s.fq_nl.as<uint32_t>(), nl_cap, d_info);
         LAUNCHED(ctx);
     }
-    k_fq_info<<<1, 32, 0, st>>>(s.fq_tile_offs.as<unsigned>(), c.n_tiles, s.fq_nl.as<uint32_t>(), nl_cap, c.len, unterminated, d_info);
+    k_fq_info<<<1, 32, 0, st>>>(s.fq_tile_offs.as<unsigned>(), c.n_tiles, s.fq_nl.as<uint32_t>(), nl_cap, c.len, unterminated, d_info,
+                                s.fq_hinfo);
     LAUNCHED(ctx);
-    CU(cudaMemcpyAsync(s.fq_hinfo, d_info, sizeof(FqInfo), cudaMemcpyDeviceToHost, st));
     return ATR_OK;
 }
 
@@ -94,7 +95,11 @@ int fq_front(atr_ctx* ctx, Slot& s, FqChunk& c, const uint8_t* text, int final_t
     if (!rc) rc = s.fq_nl.ensure((size_t)(c.len / 8 + 1024) * sizeof(uint32_t));      // >= 8 bytes per line on average; grown on demand
     if (!rc) rc = s.fq_info.ensure(sizeof(FqInfo));
     if (rc) return fail(ctx, rc, "out of device memory (FASTQ chunk)");
-    if (!s.fq_hinfo) CU(cudaHostAlloc((void**)&s.fq_hinfo, sizeof(FqInfo), cudaHostAllocDefault));
+    if (!s.fq_hinfo) {                   // mapped pinned (UVA: the same pointer is valid in kernels)
+        CU(cudaHostAlloc((void**)&s.fq_hinfo, sizeof(FqInfo), cudaHostAllocMapped));
+        CU(cudaStreamCreateWithFlags(&s.fq_out_stream, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&s.fq_ev_d2h, cudaEventDisableTiming));
+    }
     if (c.len) CU(cudaMemcpyAsync(s.fq_text.p, text + c.start, (size_t)c.len, cudaMemcpyHostToDevice, s.stream));
     return fq_index(ctx, s, c, final_text, unterminated);
 }
@@ -119,6 +124,8 @@ int fq_back(atr_ctx* ctx, Slot& s, const FqChunk& c, const atr_adapterset* set, 
     if (!rc) rc = s.fq_fwin.ensure((size_t)(n + 1) * 2 * sizeof(uint16_t));
     if (!rc) rc = s.fq_outtext.ensure((size_t)c.len + 64);
     if (rc) return fail(ctx, rc, "out of device memory (FASTQ records)");
+    // the formatted text of the chunk that used this slot before may still be on its way to the host
+    if (s.fq_d2h_pending) { CU(cudaStreamWaitEvent(st, s.fq_ev_d2h, 0)); s.fq_d2h_pending = 0; }
     // frame + validate (one extra thread for a trailing partial record)
     CU(cudaMemsetAsync(s.fq_len64.p, 0, (size_t)(n + 2) * sizeof(long long), st));
     k_fq_frame<<<grid_for(n + 1, 256), 256, 0, st>>>(d_text, s.fq_nl.as<uint32_t>(), c.n_nl, c.len, n, c.lines_left,
@@ -157,7 +164,8 @@ int fq_back(atr_ctx* ctx, Slot& s, const FqChunk& c, const atr_adapterset* set, 
                                                            s.fq_outoff.as<long long>(), n, s.fq_outtext.as<unsigned char>(), d_info);
         LAUNCHED(ctx);
     }
-    CU(cudaMemcpyAsync(s.fq_hinfo, d_info, sizeof(FqInfo), cudaMemcpyDeviceToHost, st));
+    k_fq_publish<<<1, 32, 0, st>>>(d_info, s.fq_hinfo);
+    LAUNCHED(ctx);
     return ATR_OK;
 }
 
@@ -220,6 +228,13 @@ extern "C" int atr_trim_fastq_host(atr_ctx* ctx, const atr_adapterset* set, cons
         CU(cudaMemcpy(d_stats + L.o_flags, ff.data(), nA, cudaMemcpyHostToDevice));
     }
     int64_t opos = 0, records_before = 0, done = 0;
+    // measurement knobs (never set in production): skip the D2H of the text / print per-phase device times
+    static const bool dbg_no_d2h = getenv("ATR_FQ_NO_D2H") != nullptr;
+    static const bool dbg_timing = getenv("ATR_FQ_TIMING") != nullptr;
+    double t_front = 0, t_back = 0, t_wait_front = 0, t_wait_back = 0;
+    cudaEvent_t evs[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};
+    if (dbg_timing) for (int a = 0; a < 2; a++) for (int b = 0; b < 4; b++) cudaEventCreate(&evs[a][b]);
+    auto now = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
     const bool final_call = opts->final_chunk != 0;
     auto make_chunk = [&](int slot, int64_t start) {
         FqChunk c;
@@ -240,7 +255,9 @@ extern "C" int atr_trim_fastq_host(atr_ctx* ctx, const atr_adapterset* set, cons
     int result = ATR_OK;
     while (true) {
         Slot& s = ctx->slot[cur.slot];
+        const double tw0 = now();
         CU(cudaStreamSynchronize(s.stream));
+        t_wait_front += now() - tw0;
         if (s.fq_hinfo->nl_overflow) {                   // more lines than the index was sized for: grow, redo the index
             rc = s.fq_nl.ensure((size_t)(s.fq_hinfo->n_nl + 16) * sizeof(uint32_t));
             if (rc) return fail(ctx, rc, "out of device memory (newline index)");
@@ -271,9 +288,14 @@ extern "C" int atr_trim_fastq_host(atr_ctx* ctx, const atr_adapterset* set, cons
             rc = fq_front(ctx, ctx->slot[nxt.slot], nxt, text, ft2, ut2);
             if (rc) { result = rc; break; }
         }
+        if (dbg_timing) cudaEventRecord(evs[cur.slot][2], s.stream);
         rc = fq_back(ctx, s, cur, set, opts, L, d_stats);
         if (rc) { result = rc; break; }
+        if (dbg_timing) cudaEventRecord(evs[cur.slot][3], s.stream);
+        const double tw1 = now();
         CU(cudaStreamSynchronize(s.stream));
+        t_wait_back += now() - tw1;
+        if (dbg_timing) { float ms = 0; cudaEventElapsedTime(&ms, evs[cur.slot][2], evs[cur.slot][3]); t_back += ms; }
         const FqInfo hb = *s.fq_hinfo;
         if (hb.err_key != ~0ull) {
             rc = fq_describe(ctx, s, cur, hb.err_key, records_before, err);
@@ -281,14 +303,28 @@ extern "C" int atr_trim_fastq_host(atr_ctx* ctx, const atr_adapterset* set, cons
             break;
         }
         if (opos + (int64_t)hb.out_bytes > out_cap) { result = fail(ctx, ATR_E_ARG, "out_cap too small for the trimmed text"); break; }
-        if (hb.out_bytes) CU(cudaMemcpyAsync(out_text + opos, s.fq_outtext.p, (size_t)hb.out_bytes, cudaMemcpyDeviceToHost, s.stream));
+        // own stream: the next chunk's H2D into this slot must not queue behind this copy
+        if (hb.out_bytes && !dbg_no_d2h) {
+            CU(cudaMemcpyAsync(out_text + opos, s.fq_outtext.p, (size_t)hb.out_bytes, cudaMemcpyDeviceToHost, s.fq_out_stream));
+            CU(cudaEventRecord(s.fq_ev_d2h, s.fq_out_stream));
+            s.fq_d2h_pending = 1;
+        }
         opos += (int64_t)hb.out_bytes;
         records_before += cur.n_rec;
         done = cur.start + ((cur.last && final_call) ? cur.len : cur.consumed);
         if (cur.last) break;
         cur = nxt;
     }
-    for (int k = 0; k < 2; k++) CU(cudaStreamSynchronize(ctx->slot[k].stream));
+    for (int k = 0; k < 2; k++) {
+        CU(cudaStreamSynchronize(ctx->slot[k].stream));
+        if (ctx->slot[k].fq_out_stream) CU(cudaStreamSynchronize(ctx->slot[k].fq_out_stream));
+        ctx->slot[k].fq_d2h_pending = 0;
+    }
+    if (dbg_timing) {
+        fprintf(stderr, "[atr_trim_fastq_host] back kernels %.2f ms, host waits: front %.2f ms, back %.2f ms (front kernels %.2f)\n",
+                t_back, t_wait_front, t_wait_back, t_front);
+        for (int a = 0; a < 2; a++) for (int b = 0; b < 4; b++) cudaEventDestroy(evs[a][b]);
+    }
     if (result != ATR_OK) return result;
     // statistics: device block -> added to the caller's arrays
     std::vector<char> hst(L.total);

@@ -110,8 +110,10 @@ __global__ void __launch_bounds__(FQ_THREADS) k_fq_nl_fill(const unsigned char* 
 }
 
 // one thread: lines -> complete records, consumed bytes (tile_offs[n_tiles] = total newline count)
+// The result is also stored straight into mapped pinned host memory (h_info): a D2H copy of these 64 bytes would
+// queue in the copy engine behind the previous chunk's formatted text and stall the pipeline by a whole chunk.
 __global__ void k_fq_info(const unsigned* __restrict__ tile_offs, int n_tiles, const uint32_t* __restrict__ nl, long long nl_cap,
-                          long long nbytes, int unterminated_last_line, FqInfo* __restrict__ info) {
+                          long long nbytes, int unterminated_last_line, FqInfo* __restrict__ info, FqInfo* h_info) {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
     const long long n_nl = tile_offs[n_tiles];
     const long long lines = n_nl + (unterminated_last_line ? 1 : 0);
@@ -126,6 +128,12 @@ __global__ void k_fq_info(const unsigned* __restrict__ tile_offs, int n_tiles, c
         else consumed = nbytes;                                   // it is the unterminated last line
     }
     info->consumed = consumed;
+    *h_info = *info;
+}
+
+// end of a chunk's kernels: error key and output size -> mapped pinned host memory
+__global__ void k_fq_publish(const FqInfo* __restrict__ info, FqInfo* h_info) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) *h_info = *info;
 }
 
 __device__ __forceinline__ void fq_report(FqInfo* info, long long line, int kind) {
