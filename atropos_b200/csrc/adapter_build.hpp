@@ -173,6 +173,11 @@ inline void fill_k1a(const HostAdapter& h, const AtrTables& tb, int index, int r
     for (int w = 0; w < ATR_K1A_MAXM / 8; w++) a.apack[w] = 0;
     for (int i = 0; i < h.m && i < ATR_K1A_MAXM; i++) a.apack[i >> 3] |= ((unsigned)a.code[i] & 15u) << (4 * (i & 7));
     a.exact_ok = !(a.and_mode && a.q_single_only) && h.m >= h.desc.min_overlap;
+    // anchored adapters (PREFIX = stop_in_query only, SUFFIX = start_in_query only) that the funnel does not take:
+    // the whole adapter must align at the read start / end with <= k errors, so one of k+1 pieces sits verbatim
+    // within k columns of its anchored position (locate_core.cuh: anchor_filter)
+    a.anchor_ok = h.k1a_ok && !a.fused_ok && !h.cmp_only && !h.need_find && a.exact_ok &&
+                  (h.desc.flags == ATR_STOP_WITHIN_SEQ2 || h.desc.flags == ATR_START_WITHIN_SEQ2);
     // Shift-And pieces over the first min(m, 32) rows: k+1 pieces, each at least 6 rows (shorter pieces hit at
     // random too often to be a filter); needs row-m candidates to be reported inside the loop (stop_in_query)
     a.sa_ok = 0; a.sa_rows = h.m < 32 ? h.m : 32; a.sa_start = 0; a.sa_end = 0; a.tail_gate_ok = 0; a.tail_mask = 0;

@@ -229,6 +229,20 @@ int locate_on_stream(atr_ctx* ctx, Slot& slot, const atr_adapterset* set,
                 if (!prof) { LAUNCHED(ctx); ctx->launches--; CU(cudaEventRecord(slot.ev_join, sw)); CU(cudaStreamWaitEvent(st, slot.ev_join, 0)); }
                 if (prof) { LAUNCHED(ctx); CU(cudaEventRecord(ctx->pev[3], st)); ctx->launches--; ctx->phases_valid = 1; }
             }
+            else if (p.anchor_ok && !ctx->disable_fused && n < (int64_t)0x7fffffff) {
+                // anchored adapter with indels: fixed-position piece filter, register DP over the survivors only
+                int rc = lists.ensure((size_t)n * 3 * sizeof(Survivor) + 64);
+                if (rc) return fail(ctx, rc, "out of device memory (survivor lists)");
+                int* counters = lists.as<int>();
+                Survivor* surv = (Survivor*)(lists.as<char>() + 64);
+                CU(cudaMemsetAsync(counters, 0, 4 * sizeof(int), st));
+                const unsigned gp = (unsigned)std::min<int64_t>((n + 127) / 128, 148 * 12);
+                if (h.and_mode) k_filter_anchor<true><<<grid_for(n, 256), 256, 0, st>>>(p, d_codes, d_woff, d_len, d_win, n, d_out, surv, counters);
+                else k_filter_anchor<false><<<grid_for(n, 256), 256, 0, st>>>(p, d_codes, d_woff, d_len, d_win, n, d_out, surv, counters);
+                LAUNCHED(ctx);
+                if (h.and_mode) k_anchor_dp<true><<<gp, 128, 0, st>>>(p, d_codes, d_woff, d_len, d_win, d_out, surv, counters);
+                else k_anchor_dp<false><<<gp, 128, 0, st>>>(p, d_codes, d_woff, d_len, d_win, d_out, surv, counters);
+            }
             else if (h.and_mode) k_locate_k1a<true><<<grid_for(n, 128), 128, 0, st>>>(p, d_codes, d_woff, d_len, d_win, n, d_out);
             else k_locate_k1a<false><<<grid_for(n, 128), 128, 0, st>>>(p, d_codes, d_woff, d_len, d_win, n, d_out);
             LAUNCHED(ctx);

@@ -548,3 +548,54 @@ __global__ void __launch_bounds__(128) k_wide(const __grid_constant__ AdapterK1a
         finalize(ad, b, n, out + sv.read);
     }
 }
+
+
+// ---------------------------------------------------------------------------------------------
+// Anchored adapters with indels (PREFIX / SUFFIX flag sets the funnel does not take): a fixed-position piece
+// filter over every read, then the register DP over the survivors only (dense list).
+// ---------------------------------------------------------------------------------------------
+template <bool AND_MODE>
+__global__ void __launch_bounds__(256) k_filter_anchor(const __grid_constant__ AdapterK1a ad,
+        const uint32_t* __restrict__ codes, const uint32_t* __restrict__ woff, const uint16_t* __restrict__ len,
+        const uint16_t* __restrict__ win, int64_t n_reads, atr_match* __restrict__ out,
+        Survivor* __restrict__ list, int* __restrict__ counter) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool want = false;
+    Survivor sv;
+    sv.read = (uint32_t)r; sv.a = 0; sv.b = 0;
+    if (r < n_reads) {
+        int lo, n; bool esc;
+        read_extent(len, win, r, lo, n, esc);
+        const bool routed = (esc && !AND_MODE) || n > ATR_K1A_MAXN;
+        if (routed) {
+            if (ad.mark_routed) {
+                atr_match m;
+                m.astart = m.astop = m.rstart = m.rstop = m.matches = m.errors = 0;
+                m.adapter = -1; m.status = ATR_ST_ESCAPED;
+                out[r] = m;
+            }
+        } else if (anchor_filter(ad, codes + woff[r], lo, n)) {
+            want = true;
+        } else {
+            Best b;
+            b.ref_stop = ad.m; b.q_stop = n; b.cost = ad.m + n; b.origin = 0; b.matches = 0;
+            finalize(ad, b, n, out + r);
+        }
+    }
+    list_append(want, sv, list, counter);
+}
+
+template <bool AND_MODE>
+__global__ void __launch_bounds__(128) k_anchor_dp(const __grid_constant__ AdapterK1a ad,
+        const uint32_t* __restrict__ codes, const uint32_t* __restrict__ woff, const uint16_t* __restrict__ len,
+        const uint16_t* __restrict__ win, atr_match* __restrict__ out,
+        const Survivor* __restrict__ list, const int* __restrict__ counter) {
+    const int count = *counter;
+    const int stride = gridDim.x * blockDim.x;
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < count; s += stride) {
+        const Survivor sv = list[s];
+        int lo, n; bool esc;
+        read_extent(len, win, sv.read, lo, n, esc);
+        k1a_read<AND_MODE>(ad, codes + woff[sv.read], lo, n, out + sv.read);
+    }
+}

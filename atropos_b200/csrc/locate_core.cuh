@@ -855,6 +855,57 @@ ATR_HD void gen_read(const AdapterGen& ad, const AtrTables& tb, const unsigned c
     }
 }
 
+// ---- anchored adapters outside the funnel (k_filter_anchor): fixed-position pigeonhole --------------------------
+// PREFIX (flags == stop_in_query): the alignment runs from cell (0, 0) to (m, j), j <= m + k, cost <= k (:315-321,
+// :333-352 with neither start flag, candidates only in row m). SUFFIX (flags == start_in_query): from row 0 to cell
+// (m, n) exactly (:461-474 with stop_in_ref unset). Either way the whole adapter is aligned with at most k edits, each
+// costing >= 1 whatever the indel cost, so of k + 1 pieces one is matched verbatim, and with at most k indels it sits
+// within k columns of its anchored position. A read without such a piece cannot match; the others take the full
+// register DP (k1a_read). Necessary condition only -- exactness comes from the DP.
+ATR_HD bool anchor_piece_equal(const AdapterK1a& ad, const uint32_t* __restrict__ codes, int q, int row, int len) {
+    for (int w = 0; w * 8 < len; w++) {
+        const int rows = atr_min(8, len - 8 * w);
+        const int qq = q + 8 * w, rr = row + 8 * w;
+        const uint32_t r0 = codes[qq >> 3];
+        const uint32_t r1 = ((qq & 7) + rows > 8) ? codes[(qq >> 3) + 1] : 0u;
+        const uint32_t rd = funnel_r32(r0, r1, (unsigned)(qq & 7) * 4u);
+        const uint32_t a0 = ad.apack[rr >> 3];
+        const uint32_t a1 = ((rr & 7) + rows > 8) ? ad.apack[(rr >> 3) + 1] : 0u;
+        const uint32_t ap = funnel_r32(a0, a1, (unsigned)(rr & 7) * 4u);
+        const uint32_t mask = rows == 8 ? 0xFFFFFFFFu : ((1u << (4 * rows)) - 1u);
+        uint32_t x;
+        if (ad.and_mode) {                             // every nibble must share a bit
+            x = rd & ap;
+            x |= x >> 1; x |= x >> 2;
+            x = (~x) & 0x11111111u & mask;
+        } else {
+            x = (rd ^ ap) & mask;
+        }
+        if (x != 0u) return false;
+    }
+    return true;
+}
+
+ATR_HD bool anchor_filter(const AdapterK1a& ad, const uint32_t* __restrict__ codes, int lo, int n) {
+    const int m = ad.m, k = ad.k, pieces = k + 1;
+    if (m < pieces) return true;                       // degenerate: empty pieces prove nothing
+    const int base = (ad.flags == ATR_START_WITHIN_SEQ2) ? n - m : 0;
+    int row = 0;
+    for (int pc = 0; pc < pieces; pc++) {
+        const int len = m / pieces + (pc < m % pieces ? 1 : 0);
+        for (int d = -k; d <= k; d++) {
+            const int p0 = base + row + d;             // read position of the piece's first base
+            if (p0 < 0 || p0 + len > n) continue;
+            if (anchor_piece_equal(ad, codes, lo + p0, row, len)) return true;
+        }
+        row += len;
+    }
+    return false;
+}
+
+template <bool AND_MODE>
+ATR_HD void anchor_read(const AdapterK1a& ad, const uint32_t* __restrict__ codes, int lo, int n, atr_match* out);
+
 // ---- the whole funnel for one read (what the kernels do, minus the compaction between the stages) ----
 #define ATR_K1D_W 16
 template <class WORD, bool AND_MODE>
@@ -898,5 +949,15 @@ ATR_HD void k1f_read(const AdapterK1a& ad, const uint32_t* __restrict__ codes, i
         else { if (path) *path = 2; k1a_locate<AND_MODE>(ad, codes, lo, n, b, hit.c0, hit.c1); }
     }
     if (path && ad.sa_ok) *path += 10;                 // tests: 10 + x = went through the Shift-And pre-filter
+    finalize(ad, b, n, out);
+}
+
+
+// anchored adapter, one read: filter, then the register DP (what k_filter_anchor + k_anchor_dp do)
+template <bool AND_MODE>
+ATR_HD void anchor_read(const AdapterK1a& ad, const uint32_t* __restrict__ codes, int lo, int n, atr_match* out) {
+    if (anchor_filter(ad, codes, lo, n)) { k1a_read<AND_MODE>(ad, codes, lo, n, out); return; }
+    Best b;
+    b.ref_stop = ad.m; b.q_stop = n; b.cost = ad.m + n; b.origin = 0; b.matches = 0;
     finalize(ad, b, n, out);
 }

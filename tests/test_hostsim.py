@@ -230,3 +230,36 @@ def test_multi_locate_general_flags():
     for c in golden_util.load("multi_locate"):
         got = hostsim.multi_locate(c["reference"], c["query"], c["max_error_rate"], c["flags"], c["min_overlap"])
         assert got == (None if c["expect"] is None else [tuple(t) for t in c["expect"]])
+
+
+@pytest.mark.parametrize("where", [PREFIX, SUFFIX])
+def test_anchored_piece_filter(where):
+    """PREFIX / SUFFIX adapters with indels take the fixed-position piece filter (k_filter_anchor) and the register
+    DP only for its survivors: same answers as the oracle, and the filter really rejects most adapter-free reads."""
+    rng = np.random.default_rng(400 + where)
+    took = passed = found = 0
+    for _ in range(400):
+        m = int(rng.integers(8, 60))
+        seq = fuzzgen.rand_seq(rng, m, "ACGT")
+        rate = float(rng.choice([0.0, 0.1, 0.15, 0.2]))
+        ic = int(rng.choice([1, 1, 3]))
+        mo = int(rng.choice([1, 3, 5]))
+        d, keep = _abi.make_adapter_desc(seq, rate, where, False, False, mo, ic)
+        for _ in range(8):
+            n = int(rng.integers(0, 160))
+            body = fuzzgen.rand_seq(rng, n, "ACGT")
+            r = rng.random()
+            if r < 0.6:                       # the adapter (mutated, possibly shifted by an indel) at the anchored end
+                mut = fuzzgen.mutate(rng, seq, sub=rate / 2, ins=rate / 4, dele=rate / 4)
+                body = (mut + body)[:max(n, len(mut))] if where == PREFIX else (body + mut)[-max(n, len(mut)):]
+            elif r < 0.7:
+                body = (seq[:m // 2] + body) if where == PREFIX else (body + seq[m // 2:])
+            exp = oracle.locate(seq, body, rate, where, False, False, mo, ic)
+            got, used, _ = hostsim.locate(body, d)
+            assert got == exp, (seq, rate, ic, mo, body)
+            took += used >= 20
+            passed += used == 21
+            found += exp is not None
+    # SUFFIX with unit indel cost is taken by the funnel (fused_ok); only its indel_cost 3 third comes here
+    assert took > (2000 if where == PREFIX else 800) and found > 500
+    assert passed < 0.85 * took           # the filter is selective
