@@ -20,7 +20,7 @@ SYMBOLS = [
     "atr_ctx_last_phase_ms", "atr_adapterset_create",
     "atr_adapterset_destroy", "atr_packed_words", "atr_pack_device", "atr_locate_batch_device",
     "atr_locate_batch_host", "atr_compare_prefixes", "atr_insertset_create", "atr_insertset_destroy",
-    "atr_match_insert_batch_device", "atr_match_insert_batch_host", "atr_multi_locate", "atr_trim_fastq_host",
+    "atr_match_insert_batch_device", "atr_match_insert_batch_host", "atr_multi_locate", "atr_trim_fastq_host", "atr_trim_fastq_pe_host",
 ]
 
 
@@ -73,6 +73,9 @@ def load():
                                    C.POINTER(i32)]
     L.atr_trim_fastq_host.argtypes = [vp, vp, C.POINTER(_abi.AtrTrimOpts), vp, i64, vp, i64, C.POINTER(i64), C.POINTER(i64),
                                       C.POINTER(_abi.AtrTrimStats), C.POINTER(_abi.AtrFastqError)]
+    L.atr_trim_fastq_pe_host.argtypes = [vp, vp, vp, vp, C.POINTER(_abi.AtrTrimPeOpts), vp, i64, vp, i64, vp, i64, vp, i64,
+                                         C.POINTER(i64), C.POINTER(i64), C.POINTER(_abi.AtrTrimPeStats),
+                                         C.POINTER(_abi.AtrFastqError)]
     if L.atr_abi_version() != _abi.ATR_ABI_VERSION:
         raise ImportError("atropos_b200: ABI version mismatch, rebuild with `python -m atropos_b200.build --force`")
     _lib = L

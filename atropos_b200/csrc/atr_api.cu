@@ -39,6 +39,22 @@ struct DevBuf {
 struct FqInfo;                           // fastq_kernels.cuh
 namespace {
 
+// one FASTQ text stream of a slot: chunk text, newline index, record table, windows, formatted text
+struct FqSide {
+    DevBuf text, tiles, tile_offs, nl, info, recs, len64, outoff, fwin, outtext;
+    FqInfo* hinfo = nullptr;             // mapped pinned
+    cudaStream_t out_stream = nullptr;   // D2H of the formatted text
+    cudaEvent_t ev_d2h = nullptr;
+    int d2h_pending = 0;
+    void release() {
+        DevBuf* all[] = {&text, &tiles, &tile_offs, &nl, &info, &recs, &len64, &outoff, &fwin, &outtext};
+        for (DevBuf* b : all) b->release();
+        if (hinfo) { cudaFreeHost(hinfo); hinfo = nullptr; }
+        if (out_stream) { cudaStreamSynchronize(out_stream); cudaStreamDestroy(out_stream); out_stream = nullptr; }
+        if (ev_d2h) { cudaEventDestroy(ev_d2h); ev_d2h = nullptr; }
+    }
+};
+
 // per-stream working set of the host entry points
 struct Slot {
     cudaStream_t stream = nullptr;
@@ -46,20 +62,15 @@ struct Slot {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     DevBuf ascii, offsets, win, counts, woff, codes, len, out, scan_tmp, gen_scratch, lists;
     DevBuf ascii2, offsets2, counts2, woff2, codes2, len2;     // second mate (insert aligner)
-    // FASTQ path (atr_fastq_api.cuh): chunk text, newline index, record table, windows, formatted text
-    DevBuf fq_text, fq_tiles, fq_tile_offs, fq_nl, fq_info, fq_recs, fq_len64, fq_outoff, fq_fwin, fq_outtext;
-    FqInfo* fq_hinfo = nullptr;          // mapped pinned
-    cudaStream_t fq_out_stream = nullptr; // D2H of the formatted text
-    cudaEvent_t fq_ev_d2h = nullptr;
-    int fq_d2h_pending = 0;
+    // FASTQ paths (atr_fastq_api.cuh): one FqSide per input text (single-end uses fq[0]); second mate's windows,
+    // fallback matches and the insert-aligner results of the paired-end path
+    FqSide fq[2];
+    DevBuf win2, out2, ins_out;
     void release() {
         DevBuf* all[] = {&ascii, &offsets, &win, &counts, &woff, &codes, &len, &out, &scan_tmp, &gen_scratch, &lists,
-                         &ascii2, &offsets2, &counts2, &woff2, &codes2, &len2,
-                         &fq_text, &fq_tiles, &fq_tile_offs, &fq_nl, &fq_info, &fq_recs, &fq_len64, &fq_outoff, &fq_fwin, &fq_outtext};
+                         &ascii2, &offsets2, &counts2, &woff2, &codes2, &len2, &win2, &out2, &ins_out};
         for (DevBuf* b : all) b->release();
-        if (fq_hinfo) { cudaFreeHost(fq_hinfo); fq_hinfo = nullptr; }
-        if (fq_out_stream) { cudaStreamSynchronize(fq_out_stream); cudaStreamDestroy(fq_out_stream); fq_out_stream = nullptr; }
-        if (fq_ev_d2h) { cudaEventDestroy(fq_ev_d2h); fq_ev_d2h = nullptr; }
+        fq[0].release(); fq[1].release();
     }
 };
 

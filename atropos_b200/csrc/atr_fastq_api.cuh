@@ -62,117 +62,119 @@ int fq_scan_i64(atr_ctx* ctx, cudaStream_t st, DevBuf& tmp, const long long* in,
 }
 
 // newline index of the chunk (re-runnable: a too small index buffer is grown and the pass repeated)
-int fq_index(atr_ctx* ctx, Slot& s, const FqChunk& c, int final_text, int unterminated) {
+int fq_index(atr_ctx* ctx, Slot& s, int side, const FqChunk& c, int final_text, int unterminated) {
     cudaStream_t st = s.stream;
-    FqInfo* d_info = s.fq_info.as<FqInfo>();
+    FqSide& f = s.fq[side];
+    FqInfo* d_info = f.info.as<FqInfo>();
     CU(cudaMemsetAsync(d_info, 0, sizeof(FqInfo), st));
     CU(cudaMemsetAsync(d_info, 0xFF, sizeof(unsigned long long), st));       // err_key = "none"
-    CU(cudaMemsetAsync(s.fq_tiles.p, 0, (size_t)(c.n_tiles + 1) * sizeof(unsigned), st));
+    CU(cudaMemsetAsync(f.tiles.p, 0, (size_t)(c.n_tiles + 1) * sizeof(unsigned), st));
     if (c.n_tiles > 0) {
-        k_fq_nl_count<<<(unsigned)c.n_tiles, FQ_THREADS, 0, st>>>(s.fq_text.as<unsigned char>(), c.len, final_text,
-                                                                  s.fq_tiles.as<unsigned>(), d_info);
+        k_fq_nl_count<<<(unsigned)c.n_tiles, FQ_THREADS, 0, st>>>(f.text.as<unsigned char>(), c.len, final_text,
+                                                                  f.tiles.as<unsigned>(), d_info);
         LAUNCHED(ctx);
     }
-    int rc = fq_scan_u32(ctx, st, s.scan_tmp, s.fq_tiles.as<unsigned>(), s.fq_tile_offs.as<unsigned>(), c.n_tiles + 1);
+    int rc = fq_scan_u32(ctx, st, s.scan_tmp, f.tiles.as<unsigned>(), f.tile_offs.as<unsigned>(), c.n_tiles + 1);
     if (rc) return rc;
-    const long long nl_cap = (long long)(s.fq_nl.cap / sizeof(uint32_t));
+    const long long nl_cap = (long long)(f.nl.cap / sizeof(uint32_t));
     if (c.n_tiles > 0) {
-        k_fq_nl_fill<<<(unsigned)c.n_tiles, FQ_THREADS, 0, st>>>(s.fq_text.as<unsigned char>(), c.len, s.fq_tile_offs.as<unsigned>(),
-                                                                 s.fq_nl.as<uint32_t>(), nl_cap, d_info);
+        k_fq_nl_fill<<<(unsigned)c.n_tiles, FQ_THREADS, 0, st>>>(f.text.as<unsigned char>(), c.len, f.tile_offs.as<unsigned>(),
+                                                                 f.nl.as<uint32_t>(), nl_cap, d_info);
         LAUNCHED(ctx);
     }
-    k_fq_info<<<1, 32, 0, st>>>(s.fq_tile_offs.as<unsigned>(), c.n_tiles, s.fq_nl.as<uint32_t>(), nl_cap, c.len, unterminated, d_info,
-                                s.fq_hinfo);
+    k_fq_info<<<1, 32, 0, st>>>(f.tile_offs.as<unsigned>(), c.n_tiles, f.nl.as<uint32_t>(), nl_cap, c.len, unterminated, d_info,
+                                f.hinfo);
     LAUNCHED(ctx);
     return ATR_OK;
 }
 
-int fq_front(atr_ctx* ctx, Slot& s, FqChunk& c, const uint8_t* text, int final_text, int unterminated) {
+int fq_front(atr_ctx* ctx, Slot& s, int side, FqChunk& c, const uint8_t* text, int final_text, int unterminated) {
+    FqSide& f = s.fq[side];
     c.n_tiles = (int)((c.len + FQ_TILE - 1) / FQ_TILE);
-    int rc = s.fq_text.ensure((size_t)c.len + 64);
-    if (!rc) rc = s.fq_tiles.ensure((size_t)(c.n_tiles + 2) * sizeof(unsigned));
-    if (!rc) rc = s.fq_tile_offs.ensure((size_t)(c.n_tiles + 2) * sizeof(unsigned));
-    if (!rc) rc = s.fq_nl.ensure((size_t)(c.len / 8 + 1024) * sizeof(uint32_t));      // >= 8 bytes per line on average; grown on demand
-    if (!rc) rc = s.fq_info.ensure(sizeof(FqInfo));
+    int rc = f.text.ensure((size_t)c.len + 64);
+    if (!rc) rc = f.tiles.ensure((size_t)(c.n_tiles + 2) * sizeof(unsigned));
+    if (!rc) rc = f.tile_offs.ensure((size_t)(c.n_tiles + 2) * sizeof(unsigned));
+    if (!rc) rc = f.nl.ensure((size_t)(c.len / 8 + 1024) * sizeof(uint32_t));      // >= 8 bytes per line on average; grown on demand
+    if (!rc) rc = f.info.ensure(sizeof(FqInfo));
     if (rc) return fail(ctx, rc, "out of device memory (FASTQ chunk)");
-    if (!s.fq_hinfo) {                   // mapped pinned (UVA: the same pointer is valid in kernels)
-        CU(cudaHostAlloc((void**)&s.fq_hinfo, sizeof(FqInfo), cudaHostAllocMapped));
-        CU(cudaStreamCreateWithFlags(&s.fq_out_stream, cudaStreamNonBlocking));
-        CU(cudaEventCreateWithFlags(&s.fq_ev_d2h, cudaEventDisableTiming));
+    if (!f.hinfo) {                   // mapped pinned (UVA: the same pointer is valid in kernels)
+        CU(cudaHostAlloc((void**)&f.hinfo, sizeof(FqInfo), cudaHostAllocMapped));
+        CU(cudaStreamCreateWithFlags(&f.out_stream, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&f.ev_d2h, cudaEventDisableTiming));
     }
-    if (c.len) CU(cudaMemcpyAsync(s.fq_text.p, text + c.start, (size_t)c.len, cudaMemcpyHostToDevice, s.stream));
-    return fq_index(ctx, s, c, final_text, unterminated);
+    if (c.len) CU(cudaMemcpyAsync(f.text.p, text + c.start, (size_t)c.len, cudaMemcpyHostToDevice, s.stream));
+    return fq_index(ctx, s, side, c, final_text, unterminated);
 }
 
 int fq_back(atr_ctx* ctx, Slot& s, const FqChunk& c, const atr_adapterset* set, const atr_trim_opts* o, const FqStatsLayout& L,
             char* d_stats) {
     cudaStream_t st = s.stream;
+    FqSide& f = s.fq[0];
     const int64_t n = c.n_rec;
-    FqInfo* d_info = s.fq_info.as<FqInfo>();
-    const unsigned char* d_text = s.fq_text.as<unsigned char>();
+    FqInfo* d_info = f.info.as<FqInfo>();
+    const unsigned char* d_text = f.text.as<unsigned char>();
     FqCounters* d_ctr = (FqCounters*)(d_stats + L.o_ctr);
-    int rc = s.fq_recs.ensure((size_t)(n + 1) * sizeof(FqRec));
-    if (!rc) rc = s.fq_len64.ensure((size_t)(n + 2) * sizeof(long long));
+    int rc = f.recs.ensure((size_t)(n + 1) * sizeof(FqRec));
+    if (!rc) rc = f.len64.ensure((size_t)(n + 2) * sizeof(long long));
     if (!rc) rc = s.offsets.ensure((size_t)(n + 2) * sizeof(int64_t));
-    if (!rc) rc = s.fq_outoff.ensure((size_t)(n + 2) * sizeof(long long));
+    if (!rc) rc = f.outoff.ensure((size_t)(n + 2) * sizeof(long long));
     if (!rc) rc = s.ascii.ensure((size_t)c.len + 64);
     if (!rc) rc = s.codes.ensure((size_t)(c.len / 8 + n + 2) * sizeof(uint32_t));
     if (!rc) rc = s.woff.ensure((size_t)(n + 1) * sizeof(uint32_t));
     if (!rc) rc = s.len.ensure((size_t)(n + 1) * sizeof(uint16_t));
     if (!rc) rc = s.out.ensure((size_t)(n + 1) * sizeof(atr_match));
     if (!rc) rc = s.win.ensure((size_t)(n + 1) * 2 * sizeof(uint16_t));
-    if (!rc) rc = s.fq_fwin.ensure((size_t)(n + 1) * 2 * sizeof(uint16_t));
-    if (!rc) rc = s.fq_outtext.ensure((size_t)c.len + 64);
+    if (!rc) rc = f.fwin.ensure((size_t)(n + 1) * 2 * sizeof(uint16_t));
+    if (!rc) rc = f.outtext.ensure((size_t)c.len + 64);
     if (rc) return fail(ctx, rc, "out of device memory (FASTQ records)");
     // the formatted text of the chunk that used this slot before may still be on its way to the host
-    if (s.fq_d2h_pending) { CU(cudaStreamWaitEvent(st, s.fq_ev_d2h, 0)); s.fq_d2h_pending = 0; }
+    if (f.d2h_pending) { CU(cudaStreamWaitEvent(st, f.ev_d2h, 0)); f.d2h_pending = 0; }
     // frame + validate (one extra thread for a trailing partial record)
-    CU(cudaMemsetAsync(s.fq_len64.p, 0, (size_t)(n + 2) * sizeof(long long), st));
-    k_fq_frame<<<grid_for(n + 1, 256), 256, 0, st>>>(d_text, s.fq_nl.as<uint32_t>(), c.n_nl, c.len, n, c.lines_left,
-                                                     s.fq_recs.as<FqRec>(), s.fq_len64.as<long long>(), d_info);
+    CU(cudaMemsetAsync(f.len64.p, 0, (size_t)(n + 2) * sizeof(long long), st));
+    k_fq_frame<<<grid_for(n + 1, 256), 256, 0, st>>>(d_text, f.nl.as<uint32_t>(), c.n_nl, c.len, n, c.lines_left,
+                                                     f.recs.as<FqRec>(), f.len64.as<long long>(), d_info, 4, 0);
     LAUNCHED(ctx);
     if (n > 0) {
-        rc = fq_scan_i64(ctx, st, s.scan_tmp, s.fq_len64.as<long long>(), (long long*)s.offsets.p, n + 1);
+        rc = fq_scan_i64(ctx, st, s.scan_tmp, f.len64.as<long long>(), (long long*)s.offsets.p, n + 1);
         if (rc) return rc;
-        k_fq_gather<<<grid_for(n * 32, 256), 256, 0, st>>>(d_text, s.fq_recs.as<FqRec>(), (const long long*)s.offsets.p, n,
+        k_fq_gather<<<grid_for(n * 32, 256), 256, 0, st>>>(d_text, f.recs.as<FqRec>(), (const long long*)s.offsets.p, n,
                                                            s.ascii.as<unsigned char>());
         LAUNCHED(ctx);
         // the reads are upper-cased for matching only (adapters/__init__.py:349): fold_case = 1
         rc = pack_on_stream(ctx, st, s.counts, s.scan_tmp, s.ascii.as<uint8_t>(), s.offsets.as<int64_t>(), 0, n, 1,
                             s.codes.as<uint32_t>(), s.woff.as<uint32_t>(), s.len.as<uint16_t>());
         if (rc) return rc;
-        k_fq_init_win<<<grid_for(n, 256), 256, 0, st>>>(s.fq_recs.as<FqRec>(), n, s.fq_fwin.as<uint16_t>(), d_ctr);
+        k_fq_init_win<<<grid_for(n, 256), 256, 0, st>>>(f.recs.as<FqRec>(), n, f.fwin.as<uint16_t>(), &d_ctr->records, &d_ctr->bp_in);
         LAUNCHED(ctx);
         for (int round = 0; round < o->times; round++) {
             rc = locate_on_stream(ctx, s, set, s.codes.as<uint32_t>(), s.woff.as<uint32_t>(), s.len.as<uint16_t>(),
                                   round ? s.win.as<uint16_t>() : nullptr, s.ascii.as<uint8_t>(), s.offsets.as<int64_t>(), 0, 1, n,
                                   s.out.as<atr_match>());
             if (rc) return rc;
-            k_fq_apply<<<grid_for(n, 256), 256, 0, st>>>(d_text, s.fq_recs.as<FqRec>(), s.out.as<atr_match>(), n, round,
+            k_fq_apply<<<grid_for(n, 256), 256, 0, st>>>(d_text, f.recs.as<FqRec>(), s.out.as<atr_match>(), n, round,
                                                          round + 1 < o->times ? 1 : 0, (const signed char*)(d_stats + L.o_flags),
-                                                         o->max_len, o->max_errors, s.fq_fwin.as<uint16_t>(), s.win.as<uint16_t>(),
+                                                         o->max_len, o->max_errors, f.fwin.as<uint16_t>(), s.win.as<uint16_t>(),
                                                          (unsigned long long*)(d_stats + L.o_front), (unsigned long long*)(d_stats + L.o_back),
                                                          (unsigned long long*)(d_stats + L.o_adj), d_ctr);
             LAUNCHED(ctx);
         }
-        CU(cudaMemsetAsync(s.fq_len64.p, 0, (size_t)(n + 2) * sizeof(long long), st));
-        k_fq_outlen<<<grid_for(n, 256), 256, 0, st>>>(s.fq_recs.as<FqRec>(), s.fq_fwin.as<uint16_t>(), n, s.fq_len64.as<long long>(), d_ctr);
+        CU(cudaMemsetAsync(f.len64.p, 0, (size_t)(n + 2) * sizeof(long long), st));
+        k_fq_outlen<<<grid_for(n, 256), 256, 0, st>>>(f.recs.as<FqRec>(), f.fwin.as<uint16_t>(), n, f.len64.as<long long>(), &d_ctr->bp_out);
         LAUNCHED(ctx);
-        rc = fq_scan_i64(ctx, st, s.scan_tmp, s.fq_len64.as<long long>(), s.fq_outoff.as<long long>(), n + 1);
+        rc = fq_scan_i64(ctx, st, s.scan_tmp, f.len64.as<long long>(), f.outoff.as<long long>(), n + 1);
         if (rc) return rc;
-        k_fq_format<<<grid_for(n * 32, 256), 256, 0, st>>>(d_text, s.fq_recs.as<FqRec>(), s.fq_fwin.as<uint16_t>(),
-                                                           s.fq_outoff.as<long long>(), n, s.fq_outtext.as<unsigned char>(), d_info);
+        k_fq_format<<<grid_for(n * 32, 256), 256, 0, st>>>(d_text, f.recs.as<FqRec>(), f.fwin.as<uint16_t>(),
+                                                           f.outoff.as<long long>(), n, f.outtext.as<unsigned char>(), d_info);
         LAUNCHED(ctx);
     }
-    k_fq_publish<<<1, 32, 0, st>>>(d_info, s.fq_hinfo);
+    k_fq_publish<<<1, 32, 0, st>>>(d_info, f.hinfo);
     LAUNCHED(ctx);
     return ATR_OK;
 }
 
 // describe the first malformed line of chunk c (key = line index << 8 | kind) in coordinates of the call's text
-int fq_describe(atr_ctx* ctx, Slot& s, const FqChunk& c, unsigned long long key, int64_t records_before, atr_fastq_error* err) {
-    const int64_t line = (int64_t)(key >> 8);
-    err->kind = (int32_t)(key & 0xFF);
+int fq_describe(atr_ctx* ctx, FqSide& f, const FqChunk& c, int64_t line, int kind, int64_t records_before, atr_fastq_error* err) {
+    err->kind = kind;
     err->record = records_before + line / 4;
     err->line_in_record = (int32_t)(line % 4);
     const int64_t total_lines = c.n_nl + ((c.n_rec * 4 + c.lines_left) > c.n_nl ? 1 : 0);
@@ -182,11 +184,11 @@ int fq_describe(atr_ctx* ctx, Slot& s, const FqChunk& c, unsigned long long key,
         return ATR_OK;
     }
     uint32_t prev = 0, cur = 0;
-    if (line > 0) CU(cudaMemcpy(&prev, s.fq_nl.as<uint32_t>() + (line - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (line > 0) CU(cudaMemcpy(&prev, f.nl.as<uint32_t>() + (line - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost));
     int64_t b = line > 0 ? (int64_t)prev + 1 : 0, e = c.len;
     err->terminated = 0;
     if (line < c.n_nl) {
-        CU(cudaMemcpy(&cur, s.fq_nl.as<uint32_t>() + line, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(&cur, f.nl.as<uint32_t>() + line, sizeof(uint32_t), cudaMemcpyDeviceToHost));
         e = cur;
         err->terminated = 1;
     }
@@ -250,23 +252,24 @@ extern "C" int atr_trim_fastq_host(atr_ctx* ctx, const atr_adapterset* set, cons
     FqChunk cur = make_chunk(0, 0), nxt;
     int ft = 0, ut = 0;
     flags_of(cur, ft, ut);
-    rc = fq_front(ctx, ctx->slot[0], cur, text, ft, ut);
+    rc = fq_front(ctx, ctx->slot[0], 0, cur, text, ft, ut);
     if (rc) return rc;
     int result = ATR_OK;
     while (true) {
         Slot& s = ctx->slot[cur.slot];
+        FqSide& f = s.fq[0];
         const double tw0 = now();
         CU(cudaStreamSynchronize(s.stream));
         t_wait_front += now() - tw0;
-        if (s.fq_hinfo->nl_overflow) {                   // more lines than the index was sized for: grow, redo the index
-            rc = s.fq_nl.ensure((size_t)(s.fq_hinfo->n_nl + 16) * sizeof(uint32_t));
+        if (f.hinfo->nl_overflow) {                   // more lines than the index was sized for: grow, redo the index
+            rc = f.nl.ensure((size_t)(f.hinfo->n_nl + 16) * sizeof(uint32_t));
             if (rc) return fail(ctx, rc, "out of device memory (newline index)");
             flags_of(cur, ft, ut);
-            rc = fq_index(ctx, s, cur, ft, ut);
+            rc = fq_index(ctx, s, 0, cur, ft, ut);
             if (rc) return rc;
             CU(cudaStreamSynchronize(s.stream));
         }
-        const FqInfo hi = *s.fq_hinfo;
+        const FqInfo hi = *f.hinfo;
         cur.n_rec = hi.n_rec; cur.n_nl = hi.n_nl; cur.consumed = hi.consumed;
         flags_of(cur, ft, ut);
         cur.lines_left = ft ? hi.lines_left : 0;
@@ -285,7 +288,7 @@ extern "C" int atr_trim_fastq_host(atr_ctx* ctx, const atr_adapterset* set, cons
             nxt = make_chunk(cur.slot ^ 1, cur.start + cur.consumed);
             int ft2, ut2;
             flags_of(nxt, ft2, ut2);
-            rc = fq_front(ctx, ctx->slot[nxt.slot], nxt, text, ft2, ut2);
+            rc = fq_front(ctx, ctx->slot[nxt.slot], 0, nxt, text, ft2, ut2);
             if (rc) { result = rc; break; }
         }
         if (dbg_timing) cudaEventRecord(evs[cur.slot][2], s.stream);
@@ -296,18 +299,18 @@ extern "C" int atr_trim_fastq_host(atr_ctx* ctx, const atr_adapterset* set, cons
         CU(cudaStreamSynchronize(s.stream));
         t_wait_back += now() - tw1;
         if (dbg_timing) { float ms = 0; cudaEventElapsedTime(&ms, evs[cur.slot][2], evs[cur.slot][3]); t_back += ms; }
-        const FqInfo hb = *s.fq_hinfo;
+        const FqInfo hb = *f.hinfo;
         if (hb.err_key != ~0ull) {
-            rc = fq_describe(ctx, s, cur, hb.err_key, records_before, err);
+            rc = fq_describe(ctx, f, cur, (int64_t)(hb.err_key >> 8), (int)(hb.err_key & 0xFF), records_before, err);
             result = rc ? rc : fail(ctx, ATR_E_FORMAT, "malformed FASTQ (see atr_fastq_error)");
             break;
         }
         if (opos + (int64_t)hb.out_bytes > out_cap) { result = fail(ctx, ATR_E_ARG, "out_cap too small for the trimmed text"); break; }
         // own stream: the next chunk's H2D into this slot must not queue behind this copy
         if (hb.out_bytes && !dbg_no_d2h) {
-            CU(cudaMemcpyAsync(out_text + opos, s.fq_outtext.p, (size_t)hb.out_bytes, cudaMemcpyDeviceToHost, s.fq_out_stream));
-            CU(cudaEventRecord(s.fq_ev_d2h, s.fq_out_stream));
-            s.fq_d2h_pending = 1;
+            CU(cudaMemcpyAsync(out_text + opos, f.outtext.p, (size_t)hb.out_bytes, cudaMemcpyDeviceToHost, f.out_stream));
+            CU(cudaEventRecord(f.ev_d2h, f.out_stream));
+            f.d2h_pending = 1;
         }
         opos += (int64_t)hb.out_bytes;
         records_before += cur.n_rec;
@@ -317,8 +320,8 @@ extern "C" int atr_trim_fastq_host(atr_ctx* ctx, const atr_adapterset* set, cons
     }
     for (int k = 0; k < 2; k++) {
         CU(cudaStreamSynchronize(ctx->slot[k].stream));
-        if (ctx->slot[k].fq_out_stream) CU(cudaStreamSynchronize(ctx->slot[k].fq_out_stream));
-        ctx->slot[k].fq_d2h_pending = 0;
+        if (ctx->slot[k].fq[0].out_stream) CU(cudaStreamSynchronize(ctx->slot[k].fq[0].out_stream));
+        ctx->slot[k].fq[0].d2h_pending = 0;
     }
     if (dbg_timing) {
         fprintf(stderr, "[atr_trim_fastq_host] back kernels %.2f ms, host waits: front %.2f ms, back %.2f ms (front kernels %.2f)\n",
@@ -347,6 +350,388 @@ extern "C" int atr_trim_fastq_host(atr_ctx* ctx, const atr_adapterset* set, cons
     if (stats->adjacent_bases) for (size_t i = 0; i < nA * 5; i++) stats->adjacent_bases[i] += (int64_t)ha[i];
     *out_bytes = opos;
     *consumed = done;
+    ctx->last_ms = -1.f;
+    return ATR_OK;
+}
+
+// =====================================================================================================================
+// Paired-end twin: two texts read in lockstep. Per step one chunk of each text on the same slot; the number of pairs
+// is the smaller of the two chunks' complete records, and each side resumes right after its n-th record.
+// =====================================================================================================================
+namespace {
+
+struct PeStep {
+    int slot = 0;
+    FqChunk c[2];
+    int64_t n = 0;
+};
+
+struct PeLayout { size_t H, o_ctr, o_hist[2], o_adj[2], total; };
+
+PeLayout pe_layout(int max_len, int max_errors) {
+    PeLayout L;
+    L.H = (size_t)(max_len + 1) * (size_t)(max_errors + 1);
+    L.o_ctr = 0;
+    L.o_hist[0] = 128; L.o_hist[1] = L.o_hist[0] + L.H * 8;
+    L.o_adj[0] = L.o_hist[1] + L.H * 8; L.o_adj[1] = L.o_adj[0] + 64;
+    L.total = L.o_adj[1] + 64;
+    return L;
+}
+
+// per-side buffers of a slot that the single-end path keeps in unnumbered fields
+struct PeSide {
+    DevBuf &ascii, &offsets, &counts, &woff, &codes, &len, &win, &out;
+};
+PeSide pe_side(Slot& s, int f) {
+    if (f == 0) return PeSide{s.ascii, s.offsets, s.counts, s.woff, s.codes, s.len, s.win, s.out};
+    return PeSide{s.ascii2, s.offsets2, s.counts2, s.woff2, s.codes2, s.len2, s.win2, s.out2};
+}
+
+int pe_back(atr_ctx* ctx, Slot& s, const PeStep& P, const atr_insertset* iset, const atr_adapterset* const sets[2],
+            const atr_trim_pe_opts* o, const PeLayout& L, char* d_stats) {
+    cudaStream_t st = s.stream;
+    const int64_t n = P.n;
+    FqPeCounters* d_ctr = (FqPeCounters*)(d_stats + L.o_ctr);
+    FqInfo* d_info0 = s.fq[0].info.as<FqInfo>();
+    for (int f = 0; f < 2; f++) {
+        FqSide& q = s.fq[f];
+        PeSide b = pe_side(s, f);
+        const int64_t len = P.c[f].len;
+        int rc = q.recs.ensure((size_t)(n + 1) * sizeof(FqRec));
+        if (!rc) rc = q.len64.ensure((size_t)(n + 2) * sizeof(long long));
+        if (!rc) rc = b.offsets.ensure((size_t)(n + 2) * sizeof(int64_t));
+        if (!rc) rc = q.outoff.ensure((size_t)(n + 2) * sizeof(long long));
+        if (!rc) rc = b.ascii.ensure((size_t)len + 64);
+        if (!rc) rc = b.codes.ensure((size_t)(len / 8 + n + 2) * sizeof(uint32_t));
+        if (!rc) rc = b.woff.ensure((size_t)(n + 1) * sizeof(uint32_t));
+        if (!rc) rc = b.len.ensure((size_t)(n + 1) * sizeof(uint16_t));
+        if (!rc) rc = b.out.ensure((size_t)(n + 1) * sizeof(atr_match));
+        if (!rc) rc = b.win.ensure((size_t)(n + 1) * 2 * sizeof(uint16_t));
+        if (!rc) rc = q.fwin.ensure((size_t)(n + 1) * 2 * sizeof(uint16_t));
+        if (!rc) rc = q.outtext.ensure((size_t)len + 64);
+        if (rc) return fail(ctx, rc, "out of device memory (paired FASTQ records)");
+        if (q.d2h_pending) { CU(cudaStreamWaitEvent(st, q.ev_d2h, 0)); q.d2h_pending = 0; }
+    }
+    int rc = s.ins_out.ensure((size_t)(n + 1) * sizeof(atr_insert_result));
+    if (rc) return fail(ctx, rc, "out of device memory (insert results)");
+    // frame + validate both sides, then the names; every error goes to side 0's key
+    for (int f = 0; f < 2; f++) {
+        FqSide& q = s.fq[f];
+        CU(cudaMemsetAsync(q.len64.p, 0, (size_t)(n + 2) * sizeof(long long), st));
+        k_fq_frame<<<grid_for(n, 256), 256, 0, st>>>(q.text.as<unsigned char>(), q.nl.as<uint32_t>(), P.c[f].n_nl, P.c[f].len, n, 0,
+                                                     q.recs.as<FqRec>(), q.len64.as<long long>(), d_info0, 16, 4 * f);
+        LAUNCHED(ctx);
+    }
+    k_pe_names<<<grid_for(n, 256), 256, 0, st>>>(s.fq[0].text.as<unsigned char>(), s.fq[0].recs.as<FqRec>(),
+                                                 s.fq[1].text.as<unsigned char>(), s.fq[1].recs.as<FqRec>(), n, d_info0);
+    LAUNCHED(ctx);
+    for (int f = 0; f < 2; f++) {
+        FqSide& q = s.fq[f];
+        PeSide b = pe_side(s, f);
+        rc = fq_scan_i64(ctx, st, s.scan_tmp, q.len64.as<long long>(), (long long*)b.offsets.p, n + 1);
+        if (rc) return rc;
+        k_fq_gather<<<grid_for(n * 32, 256), 256, 0, st>>>(q.text.as<unsigned char>(), q.recs.as<FqRec>(), (const long long*)b.offsets.p, n,
+                                                           b.ascii.as<unsigned char>());
+        LAUNCHED(ctx);
+        // match_insert compares the reads as they are (no upper-casing, align/__init__.py:250-267): fold_case = 0;
+        // lower-case reads come out "escaped" and take the byte-exact kernels in both stages
+        rc = pack_on_stream(ctx, st, b.counts, s.scan_tmp, b.ascii.as<uint8_t>(), b.offsets.as<int64_t>(), 0, n, 0,
+                            b.codes.as<uint32_t>(), b.woff.as<uint32_t>(), b.len.as<uint16_t>());
+        if (rc) return rc;
+        k_fq_init_win<<<grid_for(n, 256), 256, 0, st>>>(q.recs.as<FqRec>(), n, q.fwin.as<uint16_t>(), f == 0 ? &d_ctr->records : nullptr,
+                                                        &d_ctr->bp_in[f]);
+        LAUNCHED(ctx);
+    }
+    PeSide b0 = pe_side(s, 0), b1 = pe_side(s, 1);
+    rc = insert_on_stream(ctx, st, iset, b0.codes.as<uint32_t>(), b0.woff.as<uint32_t>(), b0.len.as<uint16_t>(),
+                          b1.codes.as<uint32_t>(), b1.woff.as<uint32_t>(), b1.len.as<uint16_t>(),
+                          b0.ascii.as<uint8_t>(), b0.offsets.as<int64_t>(), 0, b1.ascii.as<uint8_t>(), b1.offsets.as<int64_t>(), 0, n,
+                          s.ins_out.as<atr_insert_result>());
+    if (rc) return rc;
+    k_pe_prepare<<<grid_for(n, 256), 256, 0, st>>>(s.ins_out.as<atr_insert_result>(), s.fq[0].recs.as<FqRec>(), s.fq[1].recs.as<FqRec>(), n,
+                                                   o->min_insert_overlap, b0.win.as<uint16_t>(), b1.win.as<uint16_t>());
+    LAUNCHED(ctx);
+    for (int f = 0; f < 2; f++) {               // adapter{1,2}.match_to(read{1,2}) where there was no insert match
+        PeSide b = pe_side(s, f);
+        rc = locate_on_stream(ctx, s, sets[f], b.codes.as<uint32_t>(), b.woff.as<uint32_t>(), b.len.as<uint16_t>(), b.win.as<uint16_t>(),
+                              b.ascii.as<uint8_t>(), b.offsets.as<int64_t>(), 0, 1, n, b.out.as<atr_match>());
+        if (rc) return rc;
+    }
+    k_pe_apply<<<grid_for(n, 256), 256, 0, st>>>(s.fq[0].text.as<unsigned char>(), s.fq[0].recs.as<FqRec>(),
+                                                 s.fq[1].text.as<unsigned char>(), s.fq[1].recs.as<FqRec>(),
+                                                 s.ins_out.as<atr_insert_result>(), b0.out.as<atr_match>(), b1.out.as<atr_match>(), n,
+                                                 o->symmetric, o->min_insert_overlap, o->max_len, o->max_errors,
+                                                 s.fq[0].fwin.as<uint16_t>(), s.fq[1].fwin.as<uint16_t>(),
+                                                 (unsigned long long*)(d_stats + L.o_hist[0]), (unsigned long long*)(d_stats + L.o_hist[1]),
+                                                 (unsigned long long*)(d_stats + L.o_adj[0]), (unsigned long long*)(d_stats + L.o_adj[1]), d_ctr);
+    LAUNCHED(ctx);
+    for (int f = 0; f < 2; f++) {
+        FqSide& q = s.fq[f];
+        CU(cudaMemsetAsync(q.len64.p, 0, (size_t)(n + 2) * sizeof(long long), st));
+        k_fq_outlen<<<grid_for(n, 256), 256, 0, st>>>(q.recs.as<FqRec>(), q.fwin.as<uint16_t>(), n, q.len64.as<long long>(), &d_ctr->bp_out[f]);
+        LAUNCHED(ctx);
+        rc = fq_scan_i64(ctx, st, s.scan_tmp, q.len64.as<long long>(), q.outoff.as<long long>(), n + 1);
+        if (rc) return rc;
+        k_fq_format<<<grid_for(n * 32, 256), 256, 0, st>>>(q.text.as<unsigned char>(), q.recs.as<FqRec>(), q.fwin.as<uint16_t>(),
+                                                           q.outoff.as<long long>(), n, q.outtext.as<unsigned char>(), q.info.as<FqInfo>());
+        LAUNCHED(ctx);
+        k_fq_publish<<<1, 32, 0, st>>>(q.info.as<FqInfo>(), q.hinfo);
+        LAUNCHED(ctx);
+    }
+    return ATR_OK;
+}
+
+// frame `n_full` complete records (0 or 1) or the partial record of side f starting at record index `first`: the key
+// of the first error, ~0 if none. Synchronous (only used at the very end of the inputs).
+int pe_probe(atr_ctx* ctx, Slot& s, int f, const FqChunk& c, int64_t first, int lines_left, unsigned long long* key) {
+    FqSide& q = s.fq[f];
+    cudaStream_t st = s.stream;
+    int rc = q.recs.ensure((size_t)(first + 2) * sizeof(FqRec));
+    if (!rc) rc = q.len64.ensure((size_t)(first + 3) * sizeof(long long));
+    if (rc) return fail(ctx, rc, "out of device memory");
+    CU(cudaMemsetAsync(q.info.p, 0xFF, sizeof(unsigned long long), st));
+    // records [0, first) are framed again (cheap: `first` is 0 or 1 here); the thread of record `first` is the probe
+    k_fq_frame<<<grid_for(first + 1, 256), 256, 0, st>>>(q.text.as<unsigned char>(), q.nl.as<uint32_t>(), c.n_nl, c.len, first, lines_left,
+                                                         q.recs.as<FqRec>(), q.len64.as<long long>(), q.info.as<FqInfo>(), 4, 0);
+    LAUNCHED(ctx);
+    k_fq_publish<<<1, 32, 0, st>>>(q.info.as<FqInfo>(), q.hinfo);
+    LAUNCHED(ctx);
+    CU(cudaStreamSynchronize(st));
+    *key = q.hinfo->err_key;
+    return ATR_OK;
+}
+
+}  // namespace
+
+extern "C" int atr_trim_fastq_pe_host(atr_ctx* ctx, const atr_insertset* iset, const atr_adapterset* set1, const atr_adapterset* set2,
+                                      const atr_trim_pe_opts* opts, const uint8_t* text1, int64_t nbytes1, const uint8_t* text2,
+                                      int64_t nbytes2, uint8_t* out1, int64_t out_cap1, uint8_t* out2, int64_t out_cap2,
+                                      int64_t* out_bytes, int64_t* consumed, atr_trim_pe_stats* stats, atr_fastq_error* err) {
+    if (!ctx || !iset || !set1 || !set2 || !opts || nbytes1 < 0 || nbytes2 < 0 || (nbytes1 > 0 && (!text1 || !out1)) ||
+        (nbytes2 > 0 && (!text2 || !out2)) || !out_bytes || !consumed || !stats || !err)
+        return fail(ctx, ATR_E_ARG, "bad arguments to atr_trim_fastq_pe_host");
+    if (set1->ctx != ctx || set2->ctx != ctx || iset->ctx != ctx) return fail(ctx, ATR_E_ARG, "adapter / insert set belongs to another context");
+    if (opts->max_len < 0 || opts->max_len > ATR_MAX_READ || opts->max_errors < 0 || opts->max_errors > 4095 || opts->min_insert_overlap < 0)
+        return fail(ctx, ATR_E_ARG, "bad atr_trim_pe_opts");
+    const atr_adapterset* sets[2] = {set1, set2};
+    for (int f = 0; f < 2; f++) {
+        if (sets[f]->host.size() != 1 || !sets[f]->host[0].desc.match_to_semantics || sets[f]->host[0].desc.flags != 14)
+            return fail(ctx, ATR_E_ARG, "atr_trim_fastq_pe_host takes one 3' (BACK) adapter per read, created with match_to_semantics = 1");
+    }
+    CU(cudaSetDevice(ctx->device));
+    memset(err, 0, sizeof(*err));
+    out_bytes[0] = out_bytes[1] = 0;
+    consumed[0] = consumed[1] = 0;
+    const uint8_t* text[2] = {text1, text2};
+    const int64_t nbytes[2] = {nbytes1, nbytes2};
+    uint8_t* outp[2] = {out1, out2};
+    const int64_t out_cap[2] = {out_cap1, out_cap2};
+    int64_t chunk = opts->chunk_bytes > 0 ? opts->chunk_bytes : ((int64_t)32 << 20);
+    chunk = std::max<int64_t>(4096, std::min<int64_t>(chunk, (int64_t)1 << 30));
+    const PeLayout L = pe_layout(opts->max_len, opts->max_errors);
+    int rc = ctx->fq_stats.ensure(L.total);
+    if (rc) return fail(ctx, rc, "out of device memory (statistics)");
+    char* d_stats = ctx->fq_stats.as<char>();
+    CU(cudaMemset(d_stats, 0, L.total));
+    const bool final_call = opts->final_chunk != 0;
+    int64_t pos[2] = {0, 0}, opos[2] = {0, 0}, records_before = 0;
+    auto make_step = [&](int slot) {
+        PeStep P;
+        P.slot = slot;
+        for (int f = 0; f < 2; f++) {
+            P.c[f].slot = slot; P.c[f].start = pos[f];
+            P.c[f].len = std::min(chunk, nbytes[f] - pos[f]);
+            P.c[f].last = (pos[f] + P.c[f].len == nbytes[f]);
+        }
+        return P;
+    };
+    auto flags_of = [&](const FqChunk& c, int f, int& final_text, int& unterminated) {
+        final_text = (c.last && final_call) ? 1 : 0;
+        unterminated = (final_text && c.len > 0 && text[f][c.start + c.len - 1] != '\n') ? 1 : 0;
+    };
+    auto front = [&](PeStep& P) -> int {
+        for (int f = 0; f < 2; f++) {
+            int ft, ut;
+            flags_of(P.c[f], f, ft, ut);
+            int r2 = fq_front(ctx, ctx->slot[P.slot], f, P.c[f], text[f], ft, ut);
+            if (r2) return r2;
+        }
+        return ATR_OK;
+    };
+    auto line_error = [&](Slot& s, int f, const FqChunk& c, int64_t line, int kind, int64_t rec_base) -> int {
+        int r2 = fq_describe(ctx, s.fq[f], c, line, kind, rec_base, err);
+        err->file = f;
+        return r2 ? r2 : fail(ctx, ATR_E_FORMAT, "malformed FASTQ (see atr_fastq_error)");
+    };
+    PeStep cur = make_step(0), nxt;
+    rc = front(cur);
+    if (rc) return rc;
+    int result = ATR_OK;
+    while (true) {
+        Slot& s = ctx->slot[cur.slot];
+        CU(cudaStreamSynchronize(s.stream));
+        bool redo = false;
+        for (int f = 0; f < 2; f++) {
+            if (s.fq[f].hinfo->nl_overflow) {
+                rc = s.fq[f].nl.ensure((size_t)(s.fq[f].hinfo->n_nl + 16) * sizeof(uint32_t));
+                if (rc) return fail(ctx, rc, "out of device memory (newline index)");
+                int ft, ut;
+                flags_of(cur.c[f], f, ft, ut);
+                rc = fq_index(ctx, s, f, cur.c[f], ft, ut);
+                if (rc) return rc;
+                redo = true;
+            }
+        }
+        if (redo) CU(cudaStreamSynchronize(s.stream));
+        bool bare = false;
+        for (int f = 0; f < 2; f++) {
+            const FqInfo hi = *s.fq[f].hinfo;
+            int ft, ut;
+            flags_of(cur.c[f], f, ft, ut);
+            cur.c[f].n_rec = hi.n_rec; cur.c[f].n_nl = hi.n_nl; cur.c[f].consumed = hi.consumed;
+            cur.c[f].lines_left = ft ? hi.lines_left : 0;
+            if (hi.bare_cr && !bare) {
+                bare = true;
+                err->kind = ATR_FQ_BARE_CR; err->file = f; err->record = -1;
+            }
+        }
+        if (bare) { result = fail(ctx, ATR_E_FORMAT, "FASTQ text holds a carriage return that is not followed by a newline"); break; }
+        const int64_t n = std::min(cur.c[0].n_rec, cur.c[1].n_rec);
+        cur.n = n;
+        if (n > (int64_t)0x7ffffff0) { result = fail(ctx, ATR_E_LIMIT, "too many records in one chunk"); break; }
+        if (n == 0) {
+            // No complete pair in this step. Either a record does not fit a chunk, or an input is exhausted.
+            bool too_long = false;
+            for (int f = 0; f < 2; f++) if (cur.c[f].n_rec == 0 && !cur.c[f].last) too_long = true;
+            if (too_long) {
+                err->kind = ATR_FQ_TOO_LONG; err->record = records_before;
+                result = fail(ctx, ATR_E_FORMAT, "one FASTQ record is larger than the chunk size");
+                break;
+            }
+            if (!final_call) break;                  // the caller supplies more text later
+            // end of the files, in the reader's order (io/seqio.py:431-447): next(it1), then next(it2)
+            unsigned long long key = ~0ull;
+            const bool more1 = cur.c[0].n_rec > 0, more2 = cur.c[1].n_rec > 0;
+            if (more1) {                             // read 1 exists: it must be well-formed; then file 2 ends (or fails)
+                rc = pe_probe(ctx, s, 0, cur.c[0], 1, 0, &key);
+                if (rc) { result = rc; break; }
+                if (key != ~0ull) { result = line_error(s, 0, cur.c[0], (int64_t)(key >> 8), (int)(key & 0xFF), records_before); break; }
+                if (cur.c[1].lines_left) {
+                    rc = pe_probe(ctx, s, 1, cur.c[1], 0, cur.c[1].lines_left, &key);
+                    if (rc) { result = rc; break; }
+                    result = line_error(s, 1, cur.c[1], (int64_t)(key >> 8), (int)(key & 0xFF), records_before);
+                    break;
+                }
+                err->kind = ATR_FQ_MORE_IN_1; err->file = 0; err->record = records_before;
+                result = fail(ctx, ATR_E_FORMAT, "Reads are improperly paired. There are more reads in file 1 than in file 2.");
+                break;
+            }
+            if (cur.c[0].lines_left) {
+                rc = pe_probe(ctx, s, 0, cur.c[0], 0, cur.c[0].lines_left, &key);
+                if (rc) { result = rc; break; }
+                result = line_error(s, 0, cur.c[0], (int64_t)(key >> 8), (int)(key & 0xFF), records_before);
+                break;
+            }
+            if (more2) {
+                rc = pe_probe(ctx, s, 1, cur.c[1], 1, 0, &key);
+                if (rc) { result = rc; break; }
+                if (key != ~0ull) { result = line_error(s, 1, cur.c[1], (int64_t)(key >> 8), (int)(key & 0xFF), records_before); break; }
+                err->kind = ATR_FQ_MORE_IN_2; err->file = 1; err->record = records_before;
+                result = fail(ctx, ATR_E_FORMAT, "Reads are improperly paired. There are more reads in file 2 than in file 1.");
+                break;
+            }
+            if (cur.c[1].lines_left) {
+                rc = pe_probe(ctx, s, 1, cur.c[1], 0, cur.c[1].lines_left, &key);
+                if (rc) { result = rc; break; }
+                result = line_error(s, 1, cur.c[1], (int64_t)(key >> 8), (int)(key & 0xFF), records_before);
+                break;
+            }
+            pos[0] = nbytes[0]; pos[1] = nbytes[1];  // both inputs end cleanly
+            break;
+        }
+        // where does each side resume? its own complete-record count may exceed n
+        bool need_sync = false;
+        for (int f = 0; f < 2; f++) {
+            if (cur.c[f].n_rec != n) {
+                k_fq_consumed<<<1, 32, 0, s.stream>>>(s.fq[f].nl.as<uint32_t>(), n, s.fq[f].hinfo);
+                LAUNCHED(ctx);
+                need_sync = true;
+            }
+        }
+        if (need_sync) {
+            CU(cudaStreamSynchronize(s.stream));
+            for (int f = 0; f < 2; f++) cur.c[f].consumed = s.fq[f].hinfo->consumed;
+        }
+        for (int f = 0; f < 2; f++) pos[f] = cur.c[f].start + cur.c[f].consumed;
+        // the next step's texts start crossing PCIe now
+        nxt = make_step(cur.slot ^ 1);
+        rc = front(nxt);
+        if (rc) { result = rc; break; }
+        rc = pe_back(ctx, s, cur, iset, sets, opts, L, d_stats);
+        if (rc) { result = rc; break; }
+        CU(cudaStreamSynchronize(s.stream));
+        const unsigned long long key = s.fq[0].hinfo->err_key;
+        if (key != ~0ull) {
+            const int64_t code = (int64_t)(key >> 8), r = code / 16, sub = code % 16;
+            const int kind = (int)(key & 0xFF);
+            if (sub < 8) {
+                const int f = sub < 4 ? 0 : 1;
+                result = line_error(s, f, cur.c[f], 4 * r + (sub & 3), kind, records_before);
+            } else {                                 // names: both header lines
+                FqRec R[2];
+                for (int f = 0; f < 2; f++) CU(cudaMemcpy(&R[f], s.fq[f].recs.as<FqRec>() + r, sizeof(FqRec), cudaMemcpyDeviceToHost));
+                err->kind = kind; err->file = 0; err->record = records_before + r; err->terminated = 1;
+                err->line_begin = cur.c[0].start + R[0].hdr_b; err->line_end = err->line_begin + R[0].hdr_len;
+                err->line_begin2 = cur.c[1].start + R[1].hdr_b; err->line_end2 = err->line_begin2 + R[1].hdr_len;
+                result = fail(ctx, ATR_E_FORMAT, "Reads are improperly paired (read names differ)");
+            }
+            break;
+        }
+        bool cap_bad = false;
+        for (int f = 0; f < 2; f++) {
+            FqSide& q = s.fq[f];
+            const int64_t ob = (int64_t)q.hinfo->out_bytes;
+            if (opos[f] + ob > out_cap[f]) { cap_bad = true; break; }
+            if (ob) {
+                CU(cudaMemcpyAsync(outp[f] + opos[f], q.outtext.p, (size_t)ob, cudaMemcpyDeviceToHost, q.out_stream));
+                CU(cudaEventRecord(q.ev_d2h, q.out_stream));
+                q.d2h_pending = 1;
+            }
+            opos[f] += ob;
+        }
+        if (cap_bad) { result = fail(ctx, ATR_E_ARG, "out_cap too small for the trimmed text"); break; }
+        records_before += n;
+        cur = nxt;
+    }
+    for (int k = 0; k < 2; k++) {
+        CU(cudaStreamSynchronize(ctx->slot[k].stream));
+        for (int f = 0; f < 2; f++) {
+            if (ctx->slot[k].fq[f].out_stream) CU(cudaStreamSynchronize(ctx->slot[k].fq[f].out_stream));
+            ctx->slot[k].fq[f].d2h_pending = 0;
+        }
+    }
+    if (result != ATR_OK) return result;
+    std::vector<char> hst(L.total);
+    CU(cudaMemcpy(hst.data(), d_stats, L.total, cudaMemcpyDeviceToHost));
+    const FqPeCounters* hc = (const FqPeCounters*)(hst.data() + L.o_ctr);
+    if (hc->invalid) {
+        err->kind = ATR_FQ_INVALID_MATCH; err->record = -1;
+        return fail(ctx, ATR_E_FORMAT, "a pair for which the reference raises (Match with length <= errors, or a byte reverse_complement rejects)");
+    }
+    stats->records += (int64_t)hc->records;
+    stats->insert_matches += (int64_t)hc->insert_matches;
+    stats->overflow += (int64_t)hc->overflow;
+    for (int f = 0; f < 2; f++) {
+        stats->with_adapters[f] += (int64_t)hc->with_adapters[f];
+        stats->bp_in[f] += (int64_t)hc->bp_in[f];
+        stats->bp_out[f] += (int64_t)hc->bp_out[f];
+        const unsigned long long* hh = (const unsigned long long*)(hst.data() + L.o_hist[f]);
+        const unsigned long long* ha = (const unsigned long long*)(hst.data() + L.o_adj[f]);
+        if (stats->errors_back[f]) for (size_t i = 0; i < L.H; i++) stats->errors_back[f][i] += (int64_t)hh[i];
+        if (stats->adjacent_bases[f]) for (size_t i = 0; i < 5; i++) stats->adjacent_bases[f][i] += (int64_t)ha[i];
+    }
+    out_bytes[0] = opos[0]; out_bytes[1] = opos[1];
+    consumed[0] = pos[0]; consumed[1] = pos[1];
     ctx->last_ms = -1.f;
     return ATR_OK;
 }

@@ -153,3 +153,85 @@ ATR_HD unsigned char fq_out_byte(const unsigned char* __restrict__ text, const F
     if (i < w) return text[R.qual_b + (uint32_t)lo + i];
     return '\n';
 }
+
+// ---- paired-end ("--aligner insert") ------------------------------------------------------------------------------
+// sequence_names_match (atropos/io/seqio.py:773-791): first whitespace-delimited token of each name, a trailing '1' /
+// '2' dropped when both have one. Returns 0 equal, 1 different, 2 a name without any token (the reference dies with
+// an IndexError there). Whitespace = the ASCII characters str.split() splits on.
+ATR_HD bool fq_is_space(unsigned char c) { return c == ' ' || (c >= 9 && c <= 13) || (c >= 28 && c <= 31); }
+
+ATR_HD void fq_name_token(const unsigned char* __restrict__ text, const FqRec& R, uint32_t& b, uint32_t& e) {
+    b = R.hdr_b + 1u;
+    const uint32_t end = R.hdr_b + R.hdr_len;
+    while (b < end && fq_is_space(text[b])) b++;
+    e = b;
+    while (e < end && !fq_is_space(text[e])) e++;
+}
+
+ATR_HD int fq_names_match(const unsigned char* __restrict__ t1, const FqRec& R1, const unsigned char* __restrict__ t2, const FqRec& R2) {
+    uint32_t b1, e1, b2, e2;
+    fq_name_token(t1, R1, b1, e1);
+    fq_name_token(t2, R2, b2, e2);
+    if (e1 == b1 || e2 == b2) return 2;
+    const unsigned char l1 = t1[e1 - 1], l2 = t2[e2 - 1];
+    if ((l1 == '1' || l1 == '2') && (l2 == '1' || l2 == '2')) { e1--; e2--; }
+    if (e1 - b1 != e2 - b2) return 1;
+    for (uint32_t i = 0; i < e1 - b1; i++) if (t1[b1 + i] != t2[b2 + i]) return 1;
+    return 0;
+}
+
+// InsertAdapterCutter.__call__ (commands/trim/modifiers.py:391-453) with mismatch_action None, for one pair: which
+// match each read ends up with. ins = InsertAligner.match_insert's result, fb1/fb2 = adapter{1,2}.match_to(read{1,2})
+// (only consulted without an insert match, :401-406).
+struct PeMatch { int present, rstart, rstop, astop, errors; };
+
+ATR_HD void fq_pe_load(const atr_match& m, PeMatch& p, int& invalid) {
+    p.present = m.status == ATR_ST_MATCH;
+    if (m.status == ATR_ST_INVALID || m.status == ATR_ST_KEYERROR) invalid = 1;
+    p.rstart = m.rstart; p.rstop = m.rstop; p.astop = m.astop; p.errors = m.errors;
+}
+
+// create_symmetric_match (:421-433)
+ATR_HD void fq_pe_symmetric(const PeMatch& src, int read_len, PeMatch& dst) {
+    dst = src;
+    if (src.rstart > read_len) { dst.present = 0; return; }
+    if (dst.rstop < read_len) { dst.astop -= (read_len - dst.rstop); dst.rstop = read_len; }
+}
+
+ATR_HD void fq_pe_decide(const atr_insert_result& ins, const atr_match& fb1, const atr_match& fb2, int len1, int len2,
+                         int min_insert_len, int symmetric, PeMatch& m1, PeMatch& m2, int& insert_hit, int& invalid) {
+    m1.present = m2.present = 0; m1.rstart = m1.rstop = m1.astop = m1.errors = 0; m2 = m1;
+    insert_hit = 0;
+    if (len1 < min_insert_len || len2 < min_insert_len) return;          // :392-394
+    if (ins.insert.status == ATR_ST_INVALID || ins.insert.status == ATR_ST_KEYERROR) invalid = 1;
+    if (ins.insert.status == ATR_ST_MATCH) {
+        insert_hit = 1;
+        fq_pe_load(ins.match1, m1, invalid);
+        fq_pe_load(ins.match2, m2, invalid);
+    } else {
+        fq_pe_load(fb1, m1, invalid);
+        fq_pe_load(fb2, m2, invalid);
+    }
+    if (symmetric && (m1.present + m2.present) == 1) {                    // :417-437
+        if (m1.present) fq_pe_symmetric(m1, len2, m2);
+        else fq_pe_symmetric(m2, len1, m1);
+    }
+}
+
+// InsertAdapterCutter.trim (:455-496), action 'trim', the adapter being a 3' (BACK) adapter: match.front = False,
+// no trimming (and no statistics) when the match starts at or beyond the read end. Returns the new read length.
+ATR_HD int fq_pe_trim(const PeMatch& m, int len, const unsigned char* __restrict__ seq, FqApply& a, bool& counted) {
+    counted = false;
+    if (!m.present || m.rstart >= len) return len;
+    counted = true;
+    a.front = 0;
+    a.length = len - m.rstart;
+    a.errors = m.errors;
+    a.adjacent = 4;
+    if (m.rstart >= 1) {
+        const unsigned char c = seq[m.rstart - 1];
+        a.adjacent = c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : 4;
+    }
+    a.new_lo = 0; a.new_hi = m.rstart;
+    return m.rstart;
+}

@@ -141,17 +141,19 @@ __device__ __forceinline__ void fq_report(FqInfo* info, long long line, int kind
 }
 
 // frame + validate: one thread per record (plus one for a trailing partial record when the text is final)
+// Error key = (r * key_mul + key_add + line) << 8 | kind: single-end 4 / 0 (the line index), paired-end 16 / 0 for
+// file 1 and 16 / 4 for file 2 (pairs are read in the order read 1, read 2, names: io/seqio.py:431-452).
 __global__ void __launch_bounds__(256) k_fq_frame(const unsigned char* __restrict__ text, const uint32_t* __restrict__ nl,
                                                   long long n_nl, long long nbytes, long long n_rec, int lines_left,
                                                   FqRec* __restrict__ recs, long long* __restrict__ seq_len64,
-                                                  FqInfo* __restrict__ info) {
+                                                  FqInfo* __restrict__ info, int key_mul, int key_add) {
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (r > n_rec || (r == n_rec && lines_left == 0)) return;
     FqRec R;
     int bad = 0;
     const int avail = r < n_rec ? 4 : lines_left;
     const int kind = fq_frame(text, nl, n_nl, nbytes, r, avail, R, bad);
-    if (kind != ATR_FQ_OK) fq_report(info, 4 * r + bad, kind);
+    if (kind != ATR_FQ_OK) fq_report(info, r * key_mul + key_add + bad, kind);
     if (r < n_rec) {
         recs[r] = R;
         seq_len64[r] = R.seq_len;
@@ -173,7 +175,7 @@ __global__ void __launch_bounds__(256) k_fq_gather(const unsigned char* __restri
 
 // initial windows
 __global__ void __launch_bounds__(256) k_fq_init_win(const FqRec* __restrict__ recs, long long n_rec, uint16_t* __restrict__ fwin,
-                                                     FqCounters* __restrict__ ctr) {
+                                                     unsigned long long* __restrict__ records, unsigned long long* __restrict__ bp_in) {
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long bp = 0;
     if (r < n_rec) {
@@ -183,8 +185,8 @@ __global__ void __launch_bounds__(256) k_fq_init_win(const FqRec* __restrict__ r
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) bp += __shfl_down_sync(0xffffffffu, bp, d);
-    if ((threadIdx.x & 31) == 0 && bp) atomicAdd(&ctr->bp_in, bp);
-    if (r == 0) atomicAdd(&ctr->records, (unsigned long long)n_rec);
+    if ((threadIdx.x & 31) == 0 && bp) atomicAdd(bp_in, bp);
+    if (r == 0 && records != nullptr) atomicAdd(records, (unsigned long long)n_rec);
 }
 
 // one round of the AdapterCutter loop: shrink the windows, count. hist_front/back: [a][max_len+1][max_errors+1]
@@ -223,7 +225,7 @@ __global__ void __launch_bounds__(256) k_fq_apply(const unsigned char* __restric
 }
 
 __global__ void __launch_bounds__(256) k_fq_outlen(const FqRec* __restrict__ recs, const uint16_t* __restrict__ fwin, long long n_rec,
-                                                   long long* __restrict__ out_len, FqCounters* __restrict__ ctr) {
+                                                   long long* __restrict__ out_len, unsigned long long* __restrict__ bp_out) {
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long bp = 0;
     if (r < n_rec) {
@@ -233,7 +235,7 @@ __global__ void __launch_bounds__(256) k_fq_outlen(const FqRec* __restrict__ rec
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) bp += __shfl_down_sync(0xffffffffu, bp, d);
-    if ((threadIdx.x & 31) == 0 && bp) atomicAdd(&ctr->bp_out, bp);
+    if ((threadIdx.x & 31) == 0 && bp) atomicAdd(bp_out, bp);
 }
 
 // formatted records: warp per record, lanes stride the output bytes (coalesced stores)
@@ -249,4 +251,74 @@ __global__ void __launch_bounds__(256) k_fq_format(const unsigned char* __restri
     unsigned char* dst = out + out_off[r];
     for (uint32_t i = lane; i < total; i += 32) dst[i] = fq_out_byte(text, R, lo, hi, i);
     if (r == n_rec - 1 && lane == 0) info->out_bytes = (unsigned long long)(out_off[r] + total);
+}
+
+// ---- paired-end ------------------------------------------------------------------------------------------------
+struct FqPeCounters {
+    unsigned long long records, insert_matches, with_adapters[2], bp_in[2], bp_out[2], overflow, invalid;
+};
+
+// sequence_names_match for every pair (io/seqio.py:448-452, :773-791)
+__global__ void __launch_bounds__(256) k_pe_names(const unsigned char* __restrict__ t1, const FqRec* __restrict__ r1,
+                                                  const unsigned char* __restrict__ t2, const FqRec* __restrict__ r2,
+                                                  long long n, FqInfo* __restrict__ info) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const int nm = fq_names_match(t1, r1[r], t2, r2[r]);
+    if (nm) fq_report(info, r * 16 + 8, nm == 1 ? ATR_FQ_PAIR_NAMES : ATR_FQ_EMPTY_NAME);
+}
+
+// windows of the per-read fallback (adapter.match_to only where match_insert returned None: modifiers.py:401-406)
+__global__ void __launch_bounds__(256) k_pe_prepare(const atr_insert_result* __restrict__ ins, const FqRec* __restrict__ r1,
+                                                    const FqRec* __restrict__ r2, long long n, int min_insert_len,
+                                                    uint16_t* __restrict__ win1, uint16_t* __restrict__ win2) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const int l1 = r1[r].seq_len, l2 = r2[r].seq_len;
+    const bool need = l1 >= min_insert_len && l2 >= min_insert_len && ins[r].insert.status == ATR_ST_NONE;
+    win1[2 * r] = 0; win1[2 * r + 1] = need ? (uint16_t)l1 : (uint16_t)0;
+    win2[2 * r] = 0; win2[2 * r + 1] = need ? (uint16_t)l2 : (uint16_t)0;
+}
+
+// InsertAdapterCutter.__call__ after the alignments + trim() + the adapters' statistics, one thread per pair
+__global__ void __launch_bounds__(256) k_pe_apply(const unsigned char* __restrict__ t1, const FqRec* __restrict__ r1,
+                                                  const unsigned char* __restrict__ t2, const FqRec* __restrict__ r2,
+                                                  const atr_insert_result* __restrict__ ins, const atr_match* __restrict__ fb1,
+                                                  const atr_match* __restrict__ fb2, long long n, int symmetric, int min_insert_len,
+                                                  int max_len, int max_errors, uint16_t* __restrict__ fwin1, uint16_t* __restrict__ fwin2,
+                                                  unsigned long long* __restrict__ hist1, unsigned long long* __restrict__ hist2,
+                                                  unsigned long long* __restrict__ adj1, unsigned long long* __restrict__ adj2,
+                                                  FqPeCounters* __restrict__ ctr) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const FqRec A = r1[r], B = r2[r];
+    const int len1 = A.seq_len, len2 = B.seq_len;
+    PeMatch m1, m2;
+    int hit = 0, invalid = 0;
+    fq_pe_decide(ins[r], fb1[r], fb2[r], len1, len2, min_insert_len, symmetric, m1, m2, hit, invalid);
+    if (invalid) atomicAdd(&ctr->invalid, 1ull);
+    if (hit) atomicAdd(&ctr->insert_matches, 1ull);
+    FqApply ap;
+    bool counted;
+    const int k1 = fq_pe_trim(m1, len1, t1 + A.seq_b, ap, counted);
+    if (m1.present) atomicAdd(&ctr->with_adapters[0], 1ull);
+    if (counted) {
+        if (ap.length <= max_len && ap.errors <= max_errors) atomicAdd(&hist1[(size_t)ap.length * (size_t)(max_errors + 1) + (size_t)ap.errors], 1ull);
+        else atomicAdd(&ctr->overflow, 1ull);
+        atomicAdd(&adj1[ap.adjacent], 1ull);
+    }
+    const int k2 = fq_pe_trim(m2, len2, t2 + B.seq_b, ap, counted);
+    if (m2.present) atomicAdd(&ctr->with_adapters[1], 1ull);
+    if (counted) {
+        if (ap.length <= max_len && ap.errors <= max_errors) atomicAdd(&hist2[(size_t)ap.length * (size_t)(max_errors + 1) + (size_t)ap.errors], 1ull);
+        else atomicAdd(&ctr->overflow, 1ull);
+        atomicAdd(&adj2[ap.adjacent], 1ull);
+    }
+    fwin1[2 * r] = 0; fwin1[2 * r + 1] = (uint16_t)k1;
+    fwin2[2 * r] = 0; fwin2[2 * r + 1] = (uint16_t)k2;
+}
+
+// bytes consumed by the first n records (n < the chunk's complete records): -> mapped pinned host memory
+__global__ void k_fq_consumed(const uint32_t* __restrict__ nl, long long n, FqInfo* h_info) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) h_info->consumed = n > 0 ? (long long)nl[4 * n - 1] + 1 : 0;
 }

@@ -81,9 +81,22 @@ def format_error_message(text, err):
     if kind == _abi.ATR_FQ_INVALID_MATCH:
         return "A Match requires at least one matching position."
 
-    def content(b, e):
-        s = bytes(text[b:e])
+    if kind == _abi.ATR_FQ_MORE_IN_1:
+        return "Reads are improperly paired. There are more reads in file 1 than in file 2."
+    if kind == _abi.ATR_FQ_MORE_IN_2:
+        return "Reads are improperly paired. There are more reads in file 2 than in file 1."
+    if kind == _abi.ATR_FQ_EMPTY_NAME:
+        return "a read name without any token (the reference raises IndexError in sequence_names_match)"
+
+    def content(b, e, t=None):
+        s = bytes((text if t is None else t)[b:e])
         return (s[:-1] if s.endswith(b"\r") else s).decode("latin-1")
+
+    if kind == _abi.ATR_FQ_PAIR_NAMES:      # io/seqio.py:448-452; text = (text1, text2)
+        return "Reads are improperly paired. Read name '{0}' in file 1 does not match '{1}' in file 2.".format(
+            content(err.line_begin, err.line_end, text[0])[1:], content(err.line_begin2, err.line_end2, text[1])[1:])
+    if isinstance(text, tuple):
+        text = text[err.file]
 
     line = content(err.line_begin, err.line_end)
     if kind == _abi.ATR_FQ_NO_AT:           # the raw line, newline included (universal newlines: "\n")
@@ -147,3 +160,97 @@ class FastqTrimmer(object):
         if st.overflow:
             raise OverflowError("a removed length exceeds max_len=%d: create the FastqTrimmer with a larger max_len" % self.max_len)
         return out[:nout.value], stats, int(consumed.value)
+
+
+class PairTrimStats(object):
+    """InsertAdapterCutter.summarize() (commands/trim/modifiers.py:498-509): per read the adapter's statistics."""
+
+    def __init__(self, max_len, max_errors):
+        self.max_len, self.max_errors = max_len, max_errors
+        self.errors_back = [np.zeros((max_len + 1, max_errors + 1), dtype=np.int64) for _ in range(2)]
+        self.adjacent = [np.zeros(5, dtype=np.int64) for _ in range(2)]
+        self.records = self.insert_matches = self.overflow = 0
+        self.with_adapters, self.bp_in, self.bp_out = [0, 0], [0, 0], [0, 0]
+
+    def merge(self, other):
+        for i in range(2):
+            self.errors_back[i] += other.errors_back[i]
+            self.adjacent[i] += other.adjacent[i]
+            self.with_adapters[i] += other.with_adapters[i]
+            self.bp_in[i] += other.bp_in[i]
+            self.bp_out[i] += other.bp_out[i]
+        self.records += other.records
+        self.insert_matches += other.insert_matches
+        self.overflow += other.overflow
+        return self
+
+    def adapter_summary(self, i):
+        eb = TrimStats._nested(self.errors_back[i])
+        return {"errors_back": eb, "lengths_back": {ln: sum(v.values()) for ln, v in eb.items()},
+                "adjacent_bases": {b: int(self.adjacent[i][k]) for k, b in enumerate(_BASES)}}
+
+
+class FastqPairTrimmer(object):
+    """Paired-end twin of FastqTrimmer: the reference's `--aligner insert` pipeline for two FASTQ texts read in
+    lockstep (PairedSequenceReader io/seqio.py:397-453 -> InsertAdapterCutter modifiers.py:359-496 -> two
+    FastqFormat outputs) in one `atr_trim_fastq_pe_host` call.
+
+    adapter1 / adapter2: atropos_b200.adapters.Adapter, the 3' adapters of read 1 / read 2 as the reference's command
+    line builds them for insert mode (max_rmp 1e-6, min_overlap 1, indel_cost 3: trim/cli.py:667-679);
+    insert_aligner: atropos_b200.align.InsertAligner with the same sequences."""
+
+    def __init__(self, adapter1, adapter2, insert_aligner, symmetric=True, min_insert_overlap=1, max_len=256, device=0,
+                 chunk_bytes=0):
+        for a in (adapter1, adapter2):
+            if a.where != BACK:
+                raise ValueError("the insert-aligner path takes one 3' adapter per read")
+        self.adapter1, self.adapter2, self.aligner = adapter1, adapter2, insert_aligner
+        self.symmetric, self.min_insert_overlap = bool(symmetric), int(min_insert_overlap)
+        self.max_len = int(max_len)
+        self.max_errors = max(len(adapter1.sequence), len(adapter2.sequence))
+        self.ctx = engine.default_context(device)
+        self._set1 = engine.AdapterSet(self.ctx, [adapter1.descriptor()])
+        self._set2 = engine.AdapterSet(self.ctx, [adapter2.descriptor()])
+        self._iset = insert_aligner._insertset(self.max_len)
+        self.chunk_bytes = int(chunk_bytes)
+
+    def new_stats(self):
+        return PairTrimStats(self.max_len, self.max_errors)
+
+    def trim(self, text1, text2, final=True, stats=None, out1=None, out2=None):
+        """Returns ((out1, out2) uint8 views, stats, (consumed1, consumed2))."""
+        b1 = np.frombuffer(text1, dtype=np.uint8) if not isinstance(text1, np.ndarray) else text1
+        b2 = np.frombuffer(text2, dtype=np.uint8) if not isinstance(text2, np.ndarray) else text2
+        if out1 is None:
+            out1 = np.empty(max(int(b1.size), 1), dtype=np.uint8)
+        if out2 is None:
+            out2 = np.empty(max(int(b2.size), 1), dtype=np.uint8)
+        if stats is None:
+            stats = self.new_stats()
+        opts = _abi.AtrTrimPeOpts(int(self.symmetric), self.min_insert_overlap, self.max_len, self.max_errors,
+                                  int(bool(final)), 0, self.chunk_bytes)
+        st = _abi.AtrTrimPeStats()
+        for i in range(2):
+            st.errors_back[i] = stats.errors_back[i].ctypes.data
+            st.adjacent_bases[i] = stats.adjacent[i].ctypes.data
+        err = _abi.AtrFastqError()
+        nout, consumed = (C.c_int64 * 2)(), (C.c_int64 * 2)()
+        L = _lib.load()
+        rc = L.atr_trim_fastq_pe_host(self.ctx.handle, self._iset.handle, self._set1.handle, self._set2.handle, C.byref(opts),
+                                      b1.ctypes.data if b1.size else None, int(b1.size),
+                                      b2.ctypes.data if b2.size else None, int(b2.size),
+                                      out1.ctypes.data, int(out1.size), out2.ctypes.data, int(out2.size), nout, consumed,
+                                      C.byref(st), C.byref(err))
+        if rc == _abi.ATR_E_FORMAT:
+            raise FormatError(format_error_message((b1, b2), err))
+        _lib.check(rc, self.ctx.handle)
+        stats.records += int(st.records)
+        stats.insert_matches += int(st.insert_matches)
+        stats.overflow += int(st.overflow)
+        for i in range(2):
+            stats.with_adapters[i] += int(st.with_adapters[i])
+            stats.bp_in[i] += int(st.bp_in[i])
+            stats.bp_out[i] += int(st.bp_out[i])
+        if st.overflow:
+            raise OverflowError("a removed length exceeds max_len=%d: create the FastqPairTrimmer with a larger max_len" % self.max_len)
+        return (out1[:nout[0]], out2[:nout[1]]), stats, (int(consumed[0]), int(consumed[1]))

@@ -228,7 +228,11 @@ int  atr_multi_locate(atr_ctx* ctx, const char* reference, int32_t m, const char
 #define ATR_FQ_TRUNCATED     5   /* "FASTQ file ended prematurely" (:244-245) */
 #define ATR_FQ_BARE_CR       6   /* a '\r' not followed by '\n' (universal-newline splitting is not reproduced: refused) */
 #define ATR_FQ_TOO_LONG      7   /* read > 32767 nt or header > 65535 bytes, or one record larger than a chunk */
-#define ATR_FQ_INVALID_MATCH 8   /* Match.__init__ would raise ValueError (align/__init__.py:85-88) */
+#define ATR_FQ_INVALID_MATCH 8   /* Match.__init__ would raise ValueError (align/__init__.py:85-88), or reverse_complement KeyError */
+#define ATR_FQ_MORE_IN_1     9   /* "Reads are improperly paired. There are more reads in file 1 than in file 2." (io/seqio.py:444-447) */
+#define ATR_FQ_MORE_IN_2    10   /* "... more reads in file 2 than in file 1." (:436-440) */
+#define ATR_FQ_PAIR_NAMES   11   /* "Read name '..' in file 1 does not match '..' in file 2." (:448-452, sequence_names_match :773-791) */
+#define ATR_FQ_EMPTY_NAME   12   /* a read name without any token: the reference dies with an IndexError in sequence_names_match */
 
 typedef struct atr_fastq_error {
     int32_t kind;             /* ATR_FQ_* of the FIRST error in file order */
@@ -237,7 +241,9 @@ typedef struct atr_fastq_error {
     int64_t line_begin;       /* byte offsets of the offending line's content within this call's text */
     int64_t line_end;         /* (terminator excluded) */
     int32_t terminated;       /* 1: the line ends with a newline, 0: the text ended first */
-    int32_t pad;
+    int32_t file;             /* paired-end: 0 = the error is in file 1, 1 = file 2; line offsets are within that text */
+    int64_t line_begin2;      /* ATR_FQ_PAIR_NAMES / ATR_FQ_EMPTY_NAME: line_begin/line_end = header line of the read in */
+    int64_t line_end2;        /* file 1, line_begin2/line_end2 = header line of its mate in file 2 */
 } atr_fastq_error;
 
 /* AdapterCutter(adapters, times, action='trim') (commands/trim/modifiers.py:91-105) */
@@ -274,6 +280,38 @@ typedef struct atr_trim_stats {
 int  atr_trim_fastq_host(atr_ctx* ctx, const atr_adapterset* set, const atr_trim_opts* opts,
                          const uint8_t* text, int64_t nbytes, uint8_t* out_text, int64_t out_cap,
                          int64_t* out_bytes, int64_t* consumed, atr_trim_stats* stats, atr_fastq_error* err);
+
+/* ---- paired-end twin: two FASTQ texts in -> two trimmed FASTQ texts out ("--aligner insert") ---- */
+/* InsertAdapterCutter(adapter1, adapter2, action='trim', mismatch_action=None, symmetric, min_insert_overlap)
+ * (commands/trim/modifiers.py:359-389) */
+typedef struct atr_trim_pe_opts {
+    int32_t symmetric;          /* duplicate the one good adapter match onto the other read (:417-437) */
+    int32_t min_insert_overlap; /* pairs with a shorter read are left alone (:392-394) */
+    int32_t max_len;            /* statistics cover removed lengths 0..max_len and error counts 0..max_errors */
+    int32_t max_errors;
+    int32_t final_chunk;        /* 1: both texts end their files */
+    int32_t pad;
+    int64_t chunk_bytes;        /* per text; 0 = default (32 MiB) */
+} atr_trim_pe_opts;
+
+typedef struct atr_trim_pe_stats {
+    int64_t records, insert_matches;          /* pairs; pairs for which match_insert returned a match */
+    int64_t with_adapters[2], bp_in[2], bp_out[2];
+    int64_t overflow;
+    int64_t* errors_back[2];                  /* per read: [max_len+1][max_errors+1], ADDED to */
+    int64_t* adjacent_bases[2];               /* per read: [5] */
+} atr_trim_pe_stats;
+
+/* Replaces, for two FASTQ files read in lockstep, PairedSequenceReader.__iter__ (io/seqio.py:429-453: pairing and
+ * name checks) over two FastqReaders, InsertAdapterCutter.__call__ (modifiers.py:391-453 with mismatch_action None:
+ * InsertAligner.match_insert first, adapter{1,2}.match_to as the fallback, the symmetric fix-up), its trim() and the
+ * adapters' statistics (:455-496, adapters/__init__.py:424-436) and FastqFormat.format for both outputs.
+ * set1 / set2: one 3' (BACK) adapter each, created with match_to_semantics = 1 (the fallback adapters).
+ * consumed[i]: bytes of text i that were processed. On ATR_E_FORMAT *err names the file and the line. */
+int  atr_trim_fastq_pe_host(atr_ctx* ctx, const atr_insertset* iset, const atr_adapterset* set1, const atr_adapterset* set2,
+                            const atr_trim_pe_opts* opts, const uint8_t* text1, int64_t nbytes1, const uint8_t* text2,
+                            int64_t nbytes2, uint8_t* out1, int64_t out_cap1, uint8_t* out2, int64_t out_cap2,
+                            int64_t* out_bytes, int64_t* consumed, atr_trim_pe_stats* stats, atr_fastq_error* err);
 
 #ifdef __cplusplus
 }

@@ -39,3 +39,40 @@ def check(case, out, stats, adapters):
             assert (key in gold) == (key in mine), (case["label"], a, key)
             if key in gold:
                 assert _str_keys(mine[key]) == gold[key], (case["label"], a, key)
+
+
+# ---- paired-end ("--aligner insert") -----------------------------------------------------------------------------
+def pe_cases():
+    return golden_util.load("fastq_trim_pe")
+
+
+def pe_objects(case):
+    """(adapter1, adapter2, insert_aligner) as the reference's command line builds them in insert mode
+    (trim/cli.py:667-684, :801-802; trim/__init__.py:356-371, 444-456)."""
+    from atropos_b200 import synth
+    from atropos_b200.align import InsertAligner
+    from atropos_b200.util import RandomMatchProbability
+    e = case["error_rate"]
+    insert_rate = e or 0.2            # evaluated before error_rate gets its 0.1 default
+    adapter_rate = 0.1 if e is None else e
+    rmp = RandomMatchProbability()
+    kw = dict(max_error_rate=adapter_rate, min_overlap=1, indel_cost=3, max_rmp=1e-6, match_probability=rmp)
+    a1 = Adapter(synth.TRUSEQ_R1, BACK, **kw)
+    a2 = Adapter(synth.TRUSEQ_R2, BACK, **kw)
+    ia = InsertAligner(synth.TRUSEQ_R1, synth.TRUSEQ_R2, match_probability=rmp, max_insert_mismatch_frac=insert_rate,
+                       max_adapter_mismatch_frac=insert_rate)
+    return a1, a2, ia
+
+
+def pe_check(case, outs, stats):
+    res = case["result"]
+    assert bytes(outs[0]) == res["out1"].encode("latin-1")
+    assert bytes(outs[1]) == res["out2"].encode("latin-1")
+    assert stats.records == res["records"]
+    assert list(stats.with_adapters) == res["with_adapters"]
+    assert list(stats.bp_in) == res["bp_in"] and list(stats.bp_out) == res["bp_out"]
+    assert stats.overflow == 0
+    for i, gold in enumerate(res["adapters"]):
+        mine = stats.adapter_summary(i)
+        for key in ("lengths_back", "errors_back", "adjacent_bases"):
+            assert _str_keys(mine[key]) == gold[key], (case["label"], i, key)

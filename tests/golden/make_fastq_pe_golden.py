@@ -1,0 +1,155 @@
+#!/usr/bin/env python
+"""Generate tests/golden/fastq_trim_pe.json.gz from the REAL reference command line (build container only).
+
+    python tests/golden/make_fastq_pe_golden.py
+
+Paired-end twin of make_fastq_golden.py: every case is a pair of small FASTQ texts run through the unmodified
+
+    atropos trim --aligner insert -a ADAPTER1 -A ADAPTER2 -pe1 in1.fq -pe2 in2.fq -o out1.fq -p out2.fq
+
+(PairedSequenceReader io/seqio.py:397-453 -> InsertAdapterCutter commands/trim/modifiers.py:359-496 ->
+FastqFormat io/seqio.py:686-700). Stored: both output texts and the report's statistics, or the FormatError.
+"""
+import gzip
+import json
+import os
+import shutil
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from atropos_b200 import synth  # noqa: E402
+from oracle import build_ref, ref_loader  # noqa: E402
+
+A1, A2 = synth.TRUSEQ_R1, synth.TRUSEQ_R2
+
+
+def quals(rng, n):
+    return "".join(chr(int(c)) for c in rng.integers(33, 74, n))
+
+
+def fastq(records, eol="\n"):
+    return "".join("@" + name + eol + seq + eol + "+" + name2 + eol + q + eol for name, seq, name2, q in records)
+
+
+def make_pairs(rng, n, L=150, ragged=False, lower=0.0, suffix=False, seed=1):
+    r1, r2 = synth.synth_pe(n, L, seed=seed, device="cpu")
+    r1, r2 = r1.numpy(), r2.numpy()
+    recs1, recs2 = [], []
+    for i in range(n):
+        s1, s2 = bytes(r1[i]).decode(), bytes(r2[i]).decode()
+        if ragged:
+            if rng.random() < 0.4:
+                s1 = s1[:int(rng.integers(0, L + 1))]
+            if rng.random() < 0.4:
+                s2 = s2[:int(rng.integers(0, L + 1))]
+        if rng.random() < lower:
+            s1 = s1.lower()
+        if rng.random() < lower:
+            s2 = s2.lower()
+        base = "pair%d" % i
+        c = " 1:N:0:%d" % int(rng.integers(0, 99)) if rng.random() < 0.5 else ""
+        n1, n2 = (base + "/1" + c, base + "/2" + c) if suffix else (base + c, base + c.replace(" 1:", " 2:"))
+        recs1.append((n1, s1, n1 if rng.random() < 0.1 else "", quals(rng, len(s1))))
+        recs2.append((n2, s2, "", quals(rng, len(s2))))
+    return recs1, recs2
+
+
+def adapter_stats(st):
+    d = {"sequence": st["sequence"], "where": st["where"]["name"]}
+    for key in ("lengths_front", "lengths_back", "adjacent_bases"):
+        if key in st:
+            d[key] = st[key]
+    for key in ("errors_front", "errors_back"):
+        if key in st:
+            cols = st[key]["columns"]
+            d[key] = {ln: {str(c): v for c, v in zip(cols, row) if v} for ln, row in st[key]["rows"].items()}
+    return d
+
+
+def run_reference(text1, text2, error_rate, extra=()):
+    from atropos.commands import get_command
+    tmp = tempfile.mkdtemp(prefix="fqpegold")
+    try:
+        p = {k: os.path.join(tmp, k) for k in ("in1.fq", "in2.fq", "out1.fq", "out2.fq", "rep")}
+        for key, text in (("in1.fq", text1), ("in2.fq", text2)):
+            with open(p[key], "w", newline="") as fh:
+                fh.write(text)
+        args = ["--aligner", "insert", "-a", A1, "-A", A2, "-pe1", p["in1.fq"], "-pe2", p["in2.fq"], "-o", p["out1.fq"],
+                "-p", p["out2.fq"], "--no-default-adapters", "--no-cache-adapters", "--quiet", "--report-file", p["rep"],
+                "--report-formats", "json"] + list(extra)
+        if error_rate is not None:
+            args += ["-e", repr(error_rate)]
+        rc, summary = get_command("trim").execute(args)
+        if rc != 0:
+            from atropos.io.seqio import FormatError, PairedSequenceReader
+            try:
+                reader = PairedSequenceReader(p["in1.fq"], p["in2.fq"])
+                for _ in reader:
+                    pass
+            except FormatError as exc:
+                return {"error": str(exc)}
+            return {"exception": "trim returned %r but the reader raised nothing" % (rc,)}
+        outs = []
+        for key in ("out1.fq", "out2.fq"):
+            with open(p[key], "r", newline="") as fh:
+                outs.append(fh.read())
+        rep = p["rep"] + ".json" if os.path.exists(p["rep"] + ".json") else p["rep"]
+        with open(rep) as fh:
+            rj = json.load(fh)
+        cutter = rj["trim"]["modifiers"]["InsertAdapterCutter"]
+        ads = [adapter_stats(list(d.values())[0]) for d in cutter["adapters"]]
+        return {"out1": outs[0], "out2": outs[1], "records": rj["record_counts"].get("0", 0),
+                "with_adapters": cutter["records_with_adapters"], "bp_in": rj["bp_counts"].get("0", [0, 0]),
+                "bp_out": rj["trim"]["formatters"]["bp_written"], "adapters": ads}
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+def main():
+    build_ref.build()
+    ref_loader.load_package()
+    rng = np.random.default_rng(9101)
+    cases = []
+
+    def add(label, recs, error_rate=0.1, edit=None):
+        t1, t2 = fastq(recs[0]), fastq(recs[1])
+        if edit:
+            t1, t2 = edit(t1, t2)
+        res = run_reference(t1, t2, error_rate)
+        print(label, {k: (v if not isinstance(v, (str, list)) else (len(v) if isinstance(v, str) else v if len(v) < 3 else len(v)))
+                      for k, v in res.items()})
+        cases.append({"label": label, "text1": t1, "text2": t2, "error_rate": error_rate, "result": res})
+
+    add("pe150", make_pairs(rng, 500, seed=11))
+    add("pe150_suffix_names", make_pairs(rng, 300, suffix=True, seed=12))
+    add("ragged_lower", make_pairs(rng, 500, ragged=True, lower=0.05, seed=13))
+    add("default_rates", make_pairs(rng, 300, ragged=True, seed=14), error_rate=None)
+    add("pe100_e02", make_pairs(rng, 300, L=100, seed=15), error_rate=0.2)
+    add("empty_files", ([], []))
+    # --- improper pairing / malformed input --------------------------------------------------------------------
+    def drop_last(which):
+        def f(t1, t2):
+            cut = lambda t: "\n".join(t.split("\n")[:-5]) + "\n"
+            return (cut(t1), t2) if which == 1 else (t1, cut(t2))
+        return f
+    add("err_more_in_2", make_pairs(rng, 6, seed=16), edit=drop_last(1))
+    add("err_more_in_1", make_pairs(rng, 6, seed=17), edit=drop_last(2))
+    add("err_names", make_pairs(rng, 6, seed=18), edit=lambda t1, t2: (t1, t2.replace("@pair3", "@other3")))
+    add("err_format_file2", make_pairs(rng, 6, seed=19), edit=lambda t1, t2: (t1, t2.replace("\n+\n", "\n-\n", 3).replace("\n-\n", "\n+\n", 2)))
+    add("err_truncated_file1", make_pairs(rng, 6, seed=20), edit=lambda t1, t2: ("\n".join(t1.split("\n")[:-3]) + "\n", t2))
+
+    path = os.path.join(HERE, "fastq_trim_pe.json.gz")
+    with open(path, "wb") as raw, gzip.GzipFile(fileobj=raw, mode="wb", mtime=0) as fh:
+        fh.write(json.dumps(cases, separators=(",", ":")).encode("ascii"))
+    print("fastq_trim_pe.json.gz", os.path.getsize(path), "bytes,", len(cases), "cases")
+
+
+if __name__ == "__main__":
+    main()

@@ -189,4 +189,126 @@ int sim_trim_fastq(const atr_adapter_desc* descs, int n_adapters, const atr_trim
     return 0;
 }
 
+// Paired-end twin (atr_trim_fastq_pe_host): PairedSequenceReader + InsertAdapterCutter + two formatters, one pair at a
+// time, with the device functions of fastq_core.cuh, sim_match_insert and sim_locate.
+// counters = {records, insert_matches, with1, with2, bp_in1, bp_in2, bp_out1, bp_out2, overflow}
+namespace {
+struct SimText {
+    const unsigned char* text; long long nbytes; std::vector<uint32_t> nl; long long n_nl, lines, n_rec; int lines_left;
+    bool index(int final_chunk) {
+        for (long long i = 0; i < nbytes; i++) {
+            if (text[i] == '\n') nl.push_back((uint32_t)i);
+            if (text[i] == '\r' && !(i + 1 < nbytes && text[i + 1] == '\n') && (final_chunk || i + 1 < nbytes)) return false;
+        }
+        n_nl = (long long)nl.size();
+        const int unterminated = final_chunk && nbytes > 0 && text[nbytes - 1] != '\n';
+        lines = n_nl + unterminated; n_rec = lines / 4; lines_left = final_chunk ? (int)(lines % 4) : 0;
+        nl.push_back(0);
+        return true;
+    }
+    long long consumed_for(long long n) const { return n == 0 ? 0 : (4 * n - 1 < n_nl ? (long long)nl[4 * n - 1] + 1 : nbytes); }
+    void describe(long long line, atr_fastq_error* err) const {
+        if (line >= lines) { err->line_begin = err->line_end = nbytes; err->terminated = 0; return; }
+        err->line_begin = line > 0 ? (long long)nl[line - 1] + 1 : 0;
+        err->line_end = line < n_nl ? (long long)nl[line] : nbytes;
+        err->terminated = line < n_nl;
+    }
+};
+}
+
+int sim_trim_fastq_pe(const atr_insert_desc* idesc, const atr_adapter_desc* d1, const atr_adapter_desc* d2,
+                      const atr_trim_pe_opts* o, const unsigned char* text1, long long nbytes1, const unsigned char* text2,
+                      long long nbytes2, unsigned char* out1, unsigned char* out2, long long* out_bytes, long long* consumed,
+                      long long* counters, long long* eb1, long long* eb2, long long* adj1, long long* adj2, atr_fastq_error* err) {
+    SimText T[2];
+    T[0].text = text1; T[0].nbytes = nbytes1; T[1].text = text2; T[1].nbytes = nbytes2;
+    for (int f = 0; f < 2; f++) if (!T[f].index(o->final_chunk)) { err->kind = ATR_FQ_BARE_CR; err->file = f; err->record = -1; return ATR_E_FORMAT; }
+    const long long n = T[0].n_rec < T[1].n_rec ? T[0].n_rec : T[1].n_rec;
+    auto fail_line = [&](int f, long long r, int bad, int kind) {
+        err->kind = kind; err->file = f; err->record = r; err->line_in_record = bad;
+        T[f].describe(4 * r + bad, err);
+        return ATR_E_FORMAT;
+    };
+    std::vector<FqRec> R1((size_t)n + 1), R2((size_t)n + 1);
+    for (long long r = 0; r < n; r++) {                 // pairs in file order: read 1, read 2, names
+        int bad = 0;
+        int kind = fq_frame(text1, T[0].nl.data(), T[0].n_nl, nbytes1, r, 4, R1[(size_t)r], bad);
+        if (kind) return fail_line(0, r, bad, kind);
+        kind = fq_frame(text2, T[1].nl.data(), T[1].n_nl, nbytes2, r, 4, R2[(size_t)r], bad);
+        if (kind) return fail_line(1, r, bad, kind);
+        const int nm = fq_names_match(text1, R1[(size_t)r], text2, R2[(size_t)r]);
+        if (nm) { err->kind = nm == 1 ? ATR_FQ_PAIR_NAMES : ATR_FQ_EMPTY_NAME; err->file = 0; err->record = r;
+                  err->line_begin = R1[(size_t)r].hdr_b; err->line_end = R1[(size_t)r].hdr_b + R1[(size_t)r].hdr_len;
+                  err->line_begin2 = R2[(size_t)r].hdr_b; err->line_end2 = R2[(size_t)r].hdr_b + R2[(size_t)r].hdr_len;
+                  err->terminated = 1; return ATR_E_FORMAT; }
+    }
+    if (o->final_chunk) {                               // the end of the files: PairedSequenceReader.__iter__ :431-447
+        FqRec tmp; int bad = 0;
+        const bool more1 = T[0].n_rec > n, more2 = T[1].n_rec > n;
+        if (more1) {                                    // next(it1) yields record n (validated), next(it2) ends (or fails)
+            int kind = fq_frame(text1, T[0].nl.data(), T[0].n_nl, nbytes1, n, 4, tmp, bad);
+            if (kind) return fail_line(0, n, bad, kind);
+            if (T[1].lines_left) { kind = fq_frame(text2, T[1].nl.data(), T[1].n_nl, nbytes2, n, T[1].lines_left, tmp, bad); return fail_line(1, n, bad, kind); }
+            err->kind = ATR_FQ_MORE_IN_1; err->file = 0; err->record = n; return ATR_E_FORMAT;
+        }
+        if (T[0].lines_left) { int kind = fq_frame(text1, T[0].nl.data(), T[0].n_nl, nbytes1, n, T[0].lines_left, tmp, bad); return fail_line(0, n, bad, kind); }
+        if (more2) {
+            int kind = fq_frame(text2, T[1].nl.data(), T[1].n_nl, nbytes2, n, 4, tmp, bad);
+            if (kind) return fail_line(1, n, bad, kind);
+            err->kind = ATR_FQ_MORE_IN_2; err->file = 1; err->record = n; return ATR_E_FORMAT;
+        }
+        if (T[1].lines_left) { int kind = fq_frame(text2, T[1].nl.data(), T[1].n_nl, nbytes2, n, T[1].lines_left, tmp, bad); return fail_line(1, n, bad, kind); }
+    }
+    consumed[0] = o->final_chunk ? nbytes1 : T[0].consumed_for(n);
+    consumed[1] = o->final_chunk ? nbytes2 : T[1].consumed_for(n);
+    long long opos1 = 0, opos2 = 0;
+    for (long long r = 0; r < n; r++) {
+        const FqRec &A = R1[(size_t)r], &B = R2[(size_t)r];
+        const int len1 = A.seq_len, len2 = B.seq_len;
+        counters[0]++; counters[4] += len1; counters[5] += len2;
+        atr_insert_result ins;
+        im_clear(ins.insert); im_clear(ins.match1); im_clear(ins.match2);
+        atr_match fb1, fb2;
+        im_clear(fb1); im_clear(fb2);
+        if (len1 >= o->min_insert_overlap && len2 >= o->min_insert_overlap) {
+            int used = 0;
+            int rc = sim_match_insert(idesc, text1 + A.seq_b, len1, text2 + B.seq_b, len2, 0, &ins, &used);
+            if (rc) return rc;
+            if (ins.insert.status == ATR_ST_NONE) {
+                rc = sim_locate(d1, 0, 0, text1 + A.seq_b, len1, 0, len1, 1, 0, &fb1, &used);
+                if (!rc) rc = sim_locate(d2, 0, 0, text2 + B.seq_b, len2, 0, len2, 1, 0, &fb2, &used);
+                if (rc) return rc;
+            }
+        }
+        PeMatch m1, m2;
+        int hit = 0, invalid = 0;
+        fq_pe_decide(ins, fb1, fb2, len1, len2, o->min_insert_overlap, o->symmetric, m1, m2, hit, invalid);
+        if (invalid) { err->kind = ATR_FQ_INVALID_MATCH; err->record = r; return ATR_E_FORMAT; }
+        counters[1] += hit;
+        FqApply ap;
+        bool counted;
+        const int k1 = fq_pe_trim(m1, len1, text1 + A.seq_b, ap, counted);
+        if (m1.present) counters[2]++;
+        if (counted) {
+            if (ap.length <= o->max_len && ap.errors <= o->max_errors) eb1[(size_t)ap.length * (size_t)(o->max_errors + 1) + (size_t)ap.errors]++; else counters[8]++;
+            adj1[ap.adjacent]++;
+        }
+        const int k2 = fq_pe_trim(m2, len2, text2 + B.seq_b, ap, counted);
+        if (m2.present) counters[3]++;
+        if (counted) {
+            if (ap.length <= o->max_len && ap.errors <= o->max_errors) eb2[(size_t)ap.length * (size_t)(o->max_errors + 1) + (size_t)ap.errors]++; else counters[8]++;
+            adj2[ap.adjacent]++;
+        }
+        counters[6] += k1; counters[7] += k2;
+        uint32_t total = fq_out_len(A, 0, k1);
+        for (uint32_t i = 0; i < total; i++) out1[opos1 + i] = fq_out_byte(text1, A, 0, k1, i);
+        opos1 += total;
+        total = fq_out_len(B, 0, k2);
+        for (uint32_t i = 0; i < total; i++) out2[opos2 + i] = fq_out_byte(text2, B, 0, k2, i);
+        opos2 += total;
+    }
+    out_bytes[0] = opos1; out_bytes[1] = opos2;
+    return 0;
+}
+
 }  // extern "C"

@@ -33,6 +33,12 @@ def lib():
                                      C.c_longlong, C.c_void_p, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong),
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_abi.AtrFastqError)]
         L.sim_trim_fastq.restype = C.c_int
+        L.sim_trim_fastq_pe.argtypes = [C.POINTER(_abi.AtrInsertDesc), C.POINTER(_abi.AtrAdapterDesc),
+                                        C.POINTER(_abi.AtrAdapterDesc), C.POINTER(_abi.AtrTrimPeOpts), C.c_char_p,
+                                        C.c_longlong, C.c_char_p, C.c_longlong, C.c_void_p, C.c_void_p,
+                                        C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_abi.AtrFastqError)]
+        L.sim_trim_fastq_pe.restype = C.c_int
         _lib = L
     return _lib
 
@@ -106,3 +112,34 @@ def trim_fastq(text, adapters, times=1, max_len=512, final=True):
         raise RuntimeError("sim_trim_fastq rc=%d" % rc)
     stats.records, stats.with_adapters, stats.bp_in, stats.bp_out, stats.overflow = (int(x) for x in counters)
     return bytes(out[:nout.value]), stats, consumed.value
+
+
+def trim_fastq_pe(text1, text2, adapter1, adapter2, insert_aligner, symmetric=True, min_insert_overlap=1, max_len=256,
+                  final=True):
+    """CPU run of the paired-end FASTQ path's device functions. Returns ((out1, out2), PairTrimStats, consumed)."""
+    import numpy as np
+    from atropos_b200 import fastq
+    d1, k1 = adapter1.descriptor()
+    d2, k2 = adapter2.descriptor()
+    idesc, k3 = insert_aligner.descriptor(max_len)
+    max_errors = max(len(adapter1.sequence), len(adapter2.sequence))
+    stats = fastq.PairTrimStats(max_len, max_errors)
+    opts = _abi.AtrTrimPeOpts(int(symmetric), min_insert_overlap, max_len, max_errors, int(bool(final)), 0, 0)
+    o1 = np.empty(max(len(text1), 1), dtype=np.uint8)
+    o2 = np.empty(max(len(text2), 1), dtype=np.uint8)
+    counters = np.zeros(9, dtype=np.int64)
+    nout, consumed = (C.c_longlong * 2)(), (C.c_longlong * 2)()
+    err = _abi.AtrFastqError()
+    rc = lib().sim_trim_fastq_pe(C.byref(idesc), C.byref(d1), C.byref(d2), C.byref(opts), text1, len(text1), text2, len(text2),
+                                 o1.ctypes.data, o2.ctypes.data, nout, consumed, counters.ctypes.data,
+                                 stats.errors_back[0].ctypes.data, stats.errors_back[1].ctypes.data,
+                                 stats.adjacent[0].ctypes.data, stats.adjacent[1].ctypes.data, C.byref(err))
+    if rc == _abi.ATR_E_FORMAT:
+        raise fastq.FormatError(fastq.format_error_message((np.frombuffer(text1, dtype=np.uint8),
+                                                            np.frombuffer(text2, dtype=np.uint8)), err))
+    if rc != 0:
+        raise RuntimeError("sim_trim_fastq_pe rc=%d" % rc)
+    c = [int(x) for x in counters]
+    stats.records, stats.insert_matches, stats.overflow = c[0], c[1], c[8]
+    stats.with_adapters, stats.bp_in, stats.bp_out = [c[2], c[3]], [c[4], c[5]], [c[6], c[7]]
+    return (bytes(o1[:nout[0]]), bytes(o2[:nout[1]])), stats, (consumed[0], consumed[1])

@@ -41,3 +41,21 @@ def test_streaming_chunks_reassemble():
         pos += consumed
     assert pos == len(text)
     fastq_cases.check(case, b"".join(outs), stats, adapters)
+
+
+PE_CASES = fastq_cases.pe_cases()
+
+
+@pytest.mark.parametrize("case", PE_CASES, ids=[c["label"] for c in PE_CASES])
+def test_pe_against_reference_cli(case):
+    a1, a2, ia = fastq_cases.pe_objects(case)
+    t1, t2 = case["text1"].encode("latin-1"), case["text2"].encode("latin-1")
+    res = case["result"]
+    if "error" in res:
+        with pytest.raises(fastq.FormatError) as ei:
+            hostsim.trim_fastq_pe(t1, t2, a1, a2, ia)
+        assert str(ei.value) == res["error"]
+        return
+    outs, stats, consumed = hostsim.trim_fastq_pe(t1, t2, a1, a2, ia)
+    assert consumed == (len(t1), len(t2))
+    fastq_cases.pe_check(case, outs, stats)

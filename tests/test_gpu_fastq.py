@@ -71,3 +71,76 @@ def test_one_million_reads_against_match_records():
     removed = (L - rec["rstart"].astype(np.int64))[hit]
     hist = np.bincount(removed, minlength=L + 1)
     assert np.array_equal(stats.errors_back[0].sum(axis=1), hist)
+
+
+# ---- paired-end ("--aligner insert") ----------------------------------------------------------------------------
+PE_CASES = fastq_cases.pe_cases()
+
+
+@pytest.mark.parametrize("chunk", [0, 4096, 30000])
+@pytest.mark.parametrize("case", PE_CASES, ids=[c["label"] for c in PE_CASES])
+def test_pe_against_reference_cli(case, chunk):
+    a1, a2, ia = fastq_cases.pe_objects(case)
+    t1, t2 = case["text1"].encode("latin-1"), case["text2"].encode("latin-1")
+    res = case["result"]
+    tr = fastq.FastqPairTrimmer(a1, a2, ia, chunk_bytes=chunk)
+    if "error" in res:
+        with pytest.raises(fastq.FormatError) as ei:
+            tr.trim(t1, t2)
+        assert str(ei.value) == res["error"]
+        return
+    outs, stats, consumed = tr.trim(t1, t2)
+    assert consumed == (len(t1), len(t2))
+    fastq_cases.pe_check(case, (outs[0].tobytes(), outs[1].tobytes()), stats)
+
+
+def test_pe_streaming_calls_reassemble():
+    case = [c for c in PE_CASES if c["label"] == "ragged_lower"][0]
+    a1, a2, ia = fastq_cases.pe_objects(case)
+    t1, t2 = case["text1"].encode("latin-1"), case["text2"].encode("latin-1")
+    tr = fastq.FastqPairTrimmer(a1, a2, ia, chunk_bytes=8192)
+    o1, o2, stats, p1, p2 = [], [], tr.new_stats(), 0, 0
+    cuts = [(20_000, 9_000), (50_000, 80_000), (len(t1), len(t2))]
+    for c1, c2 in cuts:
+        final = (c1, c2) == (len(t1), len(t2))
+        outs, stats, consumed = tr.trim(t1[p1:c1], t2[p2:c2], final=final, stats=stats)
+        o1.append(outs[0].tobytes()); o2.append(outs[1].tobytes())
+        p1 += consumed[0]; p2 += consumed[1]
+    assert (p1, p2) == (len(t1), len(t2))
+    fastq_cases.pe_check(case, (b"".join(o1), b"".join(o2)), stats)
+
+
+def test_pe_200k_pairs_against_match_records():
+    """the fused path against the separately verified batch calls (InsertAdapterCutter.match_batch) + the reference's
+    decision rules restated with numpy"""
+    from atropos_b200.modifiers import InsertAdapterCutter
+    n, L = 200_000, 150
+    r1, r2 = synth.synth_pe(n, L, seed=synth.seed_for(3, 5), device="cpu")
+    r1, r2 = r1.numpy(), r2.numpy()
+    case = {"error_rate": 0.1}
+    a1, a2, ia = fastq_cases.pe_objects(case)
+    tr = fastq.FastqPairTrimmer(a1, a2, ia, max_len=L, chunk_bytes=16 << 20)
+    outs, stats, consumed = tr.trim(synth.fastq_text(r1), synth.fastq_text(r2))
+    assert stats.records == n
+    offs = np.arange(n + 1, dtype=np.int64) * L
+    cutter = InsertAdapterCutter(a1, a2, ia)
+    ins, fb1, fb2, need = cutter.match_batch((r1.reshape(-1), offs), (r2.reshape(-1), offs))
+    hit = ins["insert"]["status"] == _abi.ATR_ST_MATCH
+    m1 = np.where(hit, ins["match1"]["status"], fb1["status"]) == _abi.ATR_ST_MATCH
+    m2 = np.where(hit, ins["match2"]["status"], fb2["status"]) == _abi.ATR_ST_MATCH
+    s1 = np.where(hit, ins["match1"]["rstart"], fb1["rstart"]).astype(np.int64)
+    s2 = np.where(hit, ins["match2"]["rstart"], fb2["rstart"]).astype(np.int64)
+    only1, only2 = m1 & ~m2, m2 & ~m1                       # symmetric duplication (equal read lengths here)
+    p1 = m1 | (only2 & (s2 <= L))
+    p2 = m2 | (only1 & (s1 <= L))
+    s1 = np.where(only2, s2, s1)
+    s2 = np.where(only1, s1, s2)
+    k1 = np.where(p1 & (s1 < L), s1, L)
+    k2 = np.where(p2 & (s2 < L), s2, L)
+    assert stats.insert_matches == int(hit.sum())
+    assert stats.with_adapters == [int(p1.sum()), int(p2.sum())]
+    assert stats.bp_out == [int(k1.sum()), int(k2.sum())]
+    for out, k in ((outs[0], k1), (outs[1], k2)):
+        assert out.size == int((12 + 2 * k + 4).sum())
+        seq_lens = np.array([len(x) for x in out.tobytes().split(b"\n")[1::4]], dtype=np.int64)
+        assert np.array_equal(seq_lens, k)
