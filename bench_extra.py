@@ -111,6 +111,38 @@ def main():
                       "M_pairs_per_s": n / ms / 1e3, "algo_bytes_per_pair": b,
                       "hbm_frac": b * n / (ms * 1e-3) / 1e9 / peak,
                       "insert_match_fraction": float((res["insert"]["status"] == 1).mean())}))
+    del c1, w1, l1, c2, w2, l2, iout
+
+    # ---- cfg3 end to end: two FASTQ texts (pinned host) -> atr_trim_fastq_pe_host -> two trimmed FASTQ texts --------
+    import time
+    from atropos_b200 import fastq
+    from atropos_b200.util import RandomMatchProbability
+    n = min(args.pairs, 4_000_000)
+    r1, r2 = synth.synth_pe(n, L, seed=synth.seed_for(3), device=dev)
+    texts, outs = [], []
+    for r in (r1, r2):
+        t = synth.fastq_text(r)
+        th = torch.empty(t.size, dtype=torch.uint8, pin_memory=True)
+        th.numpy()[:] = t
+        texts.append(th)
+        outs.append(torch.empty(t.size, dtype=torch.uint8, pin_memory=True))
+    del r1, r2
+    rmp = RandomMatchProbability()
+    kw = dict(max_error_rate=0.1, min_overlap=1, indel_cost=3, max_rmp=1e-6, match_probability=rmp)
+    tr = fastq.FastqPairTrimmer(Adapter(synth.TRUSEQ_R1, BACK, **kw), Adapter(synth.TRUSEQ_R2, BACK, **kw),
+                                InsertAligner(synth.TRUSEQ_R1, synth.TRUSEQ_R2, match_probability=rmp,
+                                              max_insert_mismatch_frac=0.1, max_adapter_mismatch_frac=0.1), max_len=L)
+    run = lambda: tr.trim(texts[0].numpy(), texts[1].numpy(), out1=outs[0].numpy(), out2=outs[1].numpy())
+    run()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(2):
+        o, st, _ = run()
+    dt = (time.perf_counter() - t0) / 2
+    print(json.dumps({"config": "cfg3 PE 2x150 FASTQ text -> trimmed FASTQ text (atr_trim_fastq_pe_host, --aligner insert)",
+                      "pairs": n, "ms": dt * 1e3, "M_pairs_per_s": n / dt / 1e6,
+                      "h2d_bytes": int(texts[0].numel() + texts[1].numel()), "d2h_bytes": int(o[0].size + o[1].size),
+                      "insert_matches": int(st.insert_matches), "with_adapters": st.with_adapters}))
 
 
 if __name__ == "__main__":
