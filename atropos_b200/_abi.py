@@ -48,26 +48,69 @@ class AtrFastqError(C.Structure):
                 ("line_end2", C.c_int64)]
 
 
-class AtrTrimPeOpts(C.Structure):
-    _fields_ = [("symmetric", C.c_int32), ("min_insert_overlap", C.c_int32), ("max_len", C.c_int32),
-                ("max_errors", C.c_int32), ("final_chunk", C.c_int32), ("pad", C.c_int32), ("chunk_bytes", C.c_int64)]
+class AtrReadOps(C.Structure):
+    _fields_ = [("cut_front", C.c_int32 * 2), ("cut_back", C.c_int32 * 2), ("quality_front", C.c_int32),
+                ("quality_back", C.c_int32), ("quality_base", C.c_int32), ("trim_n", C.c_int32),
+                ("minimum_length", C.c_int32), ("maximum_length", C.c_int32), ("discard_trimmed", C.c_int32),
+                ("discard_untrimmed", C.c_int32), ("max_n", C.c_double)]
 
 
-class AtrTrimPeStats(C.Structure):
-    _fields_ = [("records", C.c_int64), ("insert_matches", C.c_int64), ("with_adapters", C.c_int64 * 2),
-                ("bp_in", C.c_int64 * 2), ("bp_out", C.c_int64 * 2), ("overflow", C.c_int64),
-                ("errors_back", C.c_void_p * 2), ("adjacent_bases", C.c_void_p * 2)]
+class AtrReadOpsStats(C.Structure):
+    _fields_ = [("bp_cut", C.c_int64 * 2), ("bp_quality", C.c_int64 * 2), ("bp_n_ends", C.c_int64 * 2),
+                ("too_short", C.c_int64), ("too_long", C.c_int64), ("too_many_n", C.c_int64),
+                ("discarded_trimmed", C.c_int64), ("discarded_untrimmed", C.c_int64), ("records_written", C.c_int64)]
+
+
+OPS_STAT_KEYS = ("too_short", "too_long", "too_many_n", "discarded_trimmed", "discarded_untrimmed", "records_written")
+
+
+def make_read_ops(cut=(), cut2=(), quality_cutoff=None, quality_base=33, trim_n=False, minimum_length=None,
+                  maximum_length=None, max_n=None, discard_trimmed=False, discard_untrimmed=False):
+    """The `trim` command's options (trim/cli.py) -> atr_read_ops. cut / cut2: the -u / -U values (lists of ints);
+    quality_cutoff: -q as the command normalises it, [back] or [front, back] (trim/cli.py:750-754)."""
+    o = AtrReadOps()
+    for i, lengths in enumerate((cut, cut2)):
+        lengths = [lengths] if isinstance(lengths, int) else list(lengths or ())
+        o.cut_front[i] = sum(x for x in lengths if x > 0)          # UnconditionalCutter.__init__ (modifiers.py:578-582)
+        o.cut_back[i] = sum(x for x in lengths if x < 0)
+    q = quality_cutoff
+    if q is not None:
+        q = [q] if isinstance(q, int) else list(q)
+        if all(c <= 0 for c in q):
+            q = None
+        elif len(q) == 1:
+            q = [0] + q
+    o.quality_front, o.quality_back = (q[0], q[1]) if q else (0, 0)
+    o.quality_base = int(quality_base)
+    o.trim_n = int(bool(trim_n))
+    o.minimum_length = int(minimum_length) if minimum_length and minimum_length > 0 else 0
+    o.maximum_length = int(maximum_length) if maximum_length is not None else -1
+    o.max_n = float(max_n) if max_n is not None else -1.0
+    o.discard_trimmed, o.discard_untrimmed = int(bool(discard_trimmed)), int(bool(discard_untrimmed))
+    return o
 
 
 class AtrTrimOpts(C.Structure):
     _fields_ = [("times", C.c_int32), ("max_len", C.c_int32), ("max_errors", C.c_int32), ("final_chunk", C.c_int32),
-                ("chunk_bytes", C.c_int64)]
+                ("chunk_bytes", C.c_int64), ("ops", AtrReadOps)]
 
 
 class AtrTrimStats(C.Structure):
     _fields_ = [("records", C.c_int64), ("with_adapters", C.c_int64), ("bp_in", C.c_int64), ("bp_out", C.c_int64),
                 ("overflow", C.c_int64), ("errors_front", C.c_void_p), ("errors_back", C.c_void_p),
-                ("adjacent_bases", C.c_void_p)]
+                ("adjacent_bases", C.c_void_p), ("ops", AtrReadOpsStats)]
+
+
+class AtrTrimPeOpts(C.Structure):
+    _fields_ = [("symmetric", C.c_int32), ("min_insert_overlap", C.c_int32), ("max_len", C.c_int32),
+                ("max_errors", C.c_int32), ("final_chunk", C.c_int32), ("pad", C.c_int32), ("chunk_bytes", C.c_int64),
+                ("ops", AtrReadOps)]
+
+
+class AtrTrimPeStats(C.Structure):
+    _fields_ = [("records", C.c_int64), ("insert_matches", C.c_int64), ("with_adapters", C.c_int64 * 2),
+                ("bp_in", C.c_int64 * 2), ("bp_out", C.c_int64 * 2), ("overflow", C.c_int64),
+                ("errors_back", C.c_void_p * 2), ("adjacent_bases", C.c_void_p * 2), ("ops", AtrReadOpsStats)]
 
 
 def make_adapter_desc(sequence, max_error_rate, flags, wildcard_ref=False, wildcard_query=False, min_overlap=1,

@@ -41,13 +41,13 @@ namespace {
 
 // one FASTQ text stream of a slot: chunk text, newline index, record table, windows, formatted text
 struct FqSide {
-    DevBuf text, tiles, tile_offs, nl, info, recs, len64, outoff, fwin, outtext;
+    DevBuf text, tiles, tile_offs, nl, info, recs, len64, outoff, fwin, outtext, flags;
     FqInfo* hinfo = nullptr;             // mapped pinned
     cudaStream_t out_stream = nullptr;   // D2H of the formatted text
     cudaEvent_t ev_d2h = nullptr;
     int d2h_pending = 0;
     void release() {
-        DevBuf* all[] = {&text, &tiles, &tile_offs, &nl, &info, &recs, &len64, &outoff, &fwin, &outtext};
+        DevBuf* all[] = {&text, &tiles, &tile_offs, &nl, &info, &recs, &len64, &outoff, &fwin, &outtext, &flags};
         for (DevBuf* b : all) b->release();
         if (hinfo) { cudaFreeHost(hinfo); hinfo = nullptr; }
         if (out_stream) { cudaStreamSynchronize(out_stream); cudaStreamDestroy(out_stream); out_stream = nullptr; }

@@ -25,7 +25,7 @@ struct FqChunk {
 
 struct FqStatsLayout {
     size_t n_adapters, H;            // H = (max_len+1)*(max_errors+1)
-    size_t o_ctr, o_front, o_back, o_adj, o_flags, total;
+    size_t o_ctr, o_front, o_back, o_adj, o_flags, o_ops, total;
 };
 
 FqStatsLayout fq_layout(size_t n_adapters, int max_len, int max_errors) {
@@ -37,8 +37,23 @@ FqStatsLayout fq_layout(size_t n_adapters, int max_len, int max_errors) {
     L.o_back = L.o_front + n_adapters * L.H * 8;
     L.o_adj = L.o_back + n_adapters * L.H * 8;
     L.o_flags = L.o_adj + n_adapters * 5 * 8;
-    L.total = L.o_flags + ((n_adapters + 15) & ~(size_t)15);
+    L.o_ops = L.o_flags + ((n_adapters + 15) & ~(size_t)15);
+    L.total = L.o_ops + ((sizeof(FqOpsCounters) + 15) & ~(size_t)15);
     return L;
+}
+
+void fq_add_ops(atr_read_ops_stats& dst, const FqOpsCounters& c) {
+    for (int i = 0; i < 2; i++) {
+        dst.bp_cut[i] += (int64_t)c.bp_cut[i];
+        dst.bp_quality[i] += (int64_t)c.bp_quality[i];
+        dst.bp_n_ends[i] += (int64_t)c.bp_n_ends[i];
+    }
+    dst.too_short += (int64_t)c.too_short;
+    dst.too_long += (int64_t)c.too_long;
+    dst.too_many_n += (int64_t)c.too_many_n;
+    dst.discarded_trimmed += (int64_t)c.discarded_trimmed;
+    dst.discarded_untrimmed += (int64_t)c.discarded_untrimmed;
+    dst.records_written += (int64_t)c.records_written;
 }
 
 int fq_scan_u32(atr_ctx* ctx, cudaStream_t st, DevBuf& tmp, const unsigned* in, unsigned* out, int n) {
@@ -126,7 +141,9 @@ int fq_back(atr_ctx* ctx, Slot& s, const FqChunk& c, const atr_adapterset* set, 
     if (!rc) rc = s.win.ensure((size_t)(n + 1) * 2 * sizeof(uint16_t));
     if (!rc) rc = f.fwin.ensure((size_t)(n + 1) * 2 * sizeof(uint16_t));
     if (!rc) rc = f.outtext.ensure((size_t)c.len + 64);
+    if (!rc) rc = f.flags.ensure((size_t)n + 16);
     if (rc) return fail(ctx, rc, "out of device memory (FASTQ records)");
+    FqOpsCounters* d_ops = (FqOpsCounters*)(d_stats + L.o_ops);
     // the formatted text of the chunk that used this slot before may still be on its way to the host
     if (f.d2h_pending) { CU(cudaStreamWaitEvent(st, f.ev_d2h, 0)); f.d2h_pending = 0; }
     // frame + validate (one extra thread for a trailing partial record)
@@ -135,6 +152,10 @@ int fq_back(atr_ctx* ctx, Slot& s, const FqChunk& c, const atr_adapterset* set, 
                                                      f.recs.as<FqRec>(), f.len64.as<long long>(), d_info, 4, 0);
     LAUNCHED(ctx);
     if (n > 0) {
+        // cut / quality-trim before the adapters: from here on a record IS what these modifiers left of it
+        k_fq_pre<<<grid_for(n, 256), 256, 0, st>>>(d_text, f.recs.as<FqRec>(), n, o->ops, 0, f.len64.as<long long>(), &d_ctr->bp_in, d_ops);
+        LAUNCHED(ctx);
+        CU(cudaMemsetAsync(f.flags.p, 0, (size_t)n, st));
         rc = fq_scan_i64(ctx, st, s.scan_tmp, f.len64.as<long long>(), (long long*)s.offsets.p, n + 1);
         if (rc) return rc;
         k_fq_gather<<<grid_for(n * 32, 256), 256, 0, st>>>(d_text, f.recs.as<FqRec>(), (const long long*)s.offsets.p, n,
@@ -144,7 +165,7 @@ int fq_back(atr_ctx* ctx, Slot& s, const FqChunk& c, const atr_adapterset* set, 
         rc = pack_on_stream(ctx, st, s.counts, s.scan_tmp, s.ascii.as<uint8_t>(), s.offsets.as<int64_t>(), 0, n, 1,
                             s.codes.as<uint32_t>(), s.woff.as<uint32_t>(), s.len.as<uint16_t>());
         if (rc) return rc;
-        k_fq_init_win<<<grid_for(n, 256), 256, 0, st>>>(f.recs.as<FqRec>(), n, f.fwin.as<uint16_t>(), &d_ctr->records, &d_ctr->bp_in);
+        k_fq_init_win<<<grid_for(n, 256), 256, 0, st>>>(f.recs.as<FqRec>(), n, f.fwin.as<uint16_t>(), &d_ctr->records);
         LAUNCHED(ctx);
         for (int round = 0; round < o->times; round++) {
             rc = locate_on_stream(ctx, s, set, s.codes.as<uint32_t>(), s.woff.as<uint32_t>(), s.len.as<uint16_t>(),
@@ -154,10 +175,13 @@ int fq_back(atr_ctx* ctx, Slot& s, const FqChunk& c, const atr_adapterset* set, 
             k_fq_apply<<<grid_for(n, 256), 256, 0, st>>>(d_text, f.recs.as<FqRec>(), s.out.as<atr_match>(), n, round,
                                                          round + 1 < o->times ? 1 : 0, (const signed char*)(d_stats + L.o_flags),
                                                          o->max_len, o->max_errors, f.fwin.as<uint16_t>(), s.win.as<uint16_t>(),
-                                                         (unsigned long long*)(d_stats + L.o_front), (unsigned long long*)(d_stats + L.o_back),
+                                                         f.flags.as<unsigned char>(), (unsigned long long*)(d_stats + L.o_front), (unsigned long long*)(d_stats + L.o_back),
                                                          (unsigned long long*)(d_stats + L.o_adj), d_ctr);
             LAUNCHED(ctx);
         }
+        // N-end trimming and the filters
+        k_fq_post<<<grid_for(n, 256), 256, 0, st>>>(d_text, f.recs.as<FqRec>(), n, o->ops, f.fwin.as<uint16_t>(), f.flags.as<unsigned char>(), d_ops);
+        LAUNCHED(ctx);
         CU(cudaMemsetAsync(f.len64.p, 0, (size_t)(n + 2) * sizeof(long long), st));
         k_fq_outlen<<<grid_for(n, 256), 256, 0, st>>>(f.recs.as<FqRec>(), f.fwin.as<uint16_t>(), n, f.len64.as<long long>(), &d_ctr->bp_out);
         LAUNCHED(ctx);
@@ -348,6 +372,7 @@ extern "C" int atr_trim_fastq_host(atr_ctx* ctx, const atr_adapterset* set, cons
     if (stats->errors_front) for (size_t i = 0; i < nA * L.H; i++) stats->errors_front[i] += (int64_t)hf[i];
     if (stats->errors_back) for (size_t i = 0; i < nA * L.H; i++) stats->errors_back[i] += (int64_t)hbk[i];
     if (stats->adjacent_bases) for (size_t i = 0; i < nA * 5; i++) stats->adjacent_bases[i] += (int64_t)ha[i];
+    fq_add_ops(stats->ops, *(const FqOpsCounters*)(hst.data() + L.o_ops));
     *out_bytes = opos;
     *consumed = done;
     ctx->last_ms = -1.f;
@@ -366,7 +391,7 @@ struct PeStep {
     int64_t n = 0;
 };
 
-struct PeLayout { size_t H, o_ctr, o_hist[2], o_adj[2], total; };
+struct PeLayout { size_t H, o_ctr, o_hist[2], o_adj[2], o_ops, total; };
 
 PeLayout pe_layout(int max_len, int max_errors) {
     PeLayout L;
@@ -374,7 +399,8 @@ PeLayout pe_layout(int max_len, int max_errors) {
     L.o_ctr = 0;
     L.o_hist[0] = 128; L.o_hist[1] = L.o_hist[0] + L.H * 8;
     L.o_adj[0] = L.o_hist[1] + L.H * 8; L.o_adj[1] = L.o_adj[0] + 64;
-    L.total = L.o_adj[1] + 64;
+    L.o_ops = L.o_adj[1] + 64;
+    L.total = L.o_ops + ((sizeof(FqOpsCounters) + 15) & ~(size_t)15);
     return L;
 }
 
@@ -392,6 +418,7 @@ int pe_back(atr_ctx* ctx, Slot& s, const PeStep& P, const atr_insertset* iset, c
     cudaStream_t st = s.stream;
     const int64_t n = P.n;
     FqPeCounters* d_ctr = (FqPeCounters*)(d_stats + L.o_ctr);
+    FqOpsCounters* d_ops = (FqOpsCounters*)(d_stats + L.o_ops);
     FqInfo* d_info0 = s.fq[0].info.as<FqInfo>();
     for (int f = 0; f < 2; f++) {
         FqSide& q = s.fq[f];
@@ -428,6 +455,9 @@ int pe_back(atr_ctx* ctx, Slot& s, const PeStep& P, const atr_insertset* iset, c
     for (int f = 0; f < 2; f++) {
         FqSide& q = s.fq[f];
         PeSide b = pe_side(s, f);
+        k_fq_pre<<<grid_for(n, 256), 256, 0, st>>>(q.text.as<unsigned char>(), q.recs.as<FqRec>(), n, o->ops, f, q.len64.as<long long>(),
+                                                   &d_ctr->bp_in[f], d_ops);
+        LAUNCHED(ctx);
         rc = fq_scan_i64(ctx, st, s.scan_tmp, q.len64.as<long long>(), (long long*)b.offsets.p, n + 1);
         if (rc) return rc;
         k_fq_gather<<<grid_for(n * 32, 256), 256, 0, st>>>(q.text.as<unsigned char>(), q.recs.as<FqRec>(), (const long long*)b.offsets.p, n,
@@ -438,8 +468,7 @@ int pe_back(atr_ctx* ctx, Slot& s, const PeStep& P, const atr_insertset* iset, c
         rc = pack_on_stream(ctx, st, b.counts, s.scan_tmp, b.ascii.as<uint8_t>(), b.offsets.as<int64_t>(), 0, n, 0,
                             b.codes.as<uint32_t>(), b.woff.as<uint32_t>(), b.len.as<uint16_t>());
         if (rc) return rc;
-        k_fq_init_win<<<grid_for(n, 256), 256, 0, st>>>(q.recs.as<FqRec>(), n, q.fwin.as<uint16_t>(), f == 0 ? &d_ctr->records : nullptr,
-                                                        &d_ctr->bp_in[f]);
+        k_fq_init_win<<<grid_for(n, 256), 256, 0, st>>>(q.recs.as<FqRec>(), n, q.fwin.as<uint16_t>(), f == 0 ? &d_ctr->records : nullptr);
         LAUNCHED(ctx);
     }
     PeSide b0 = pe_side(s, 0), b1 = pe_side(s, 1);
@@ -463,7 +492,8 @@ int pe_back(atr_ctx* ctx, Slot& s, const PeStep& P, const atr_insertset* iset, c
                                                  o->symmetric, o->min_insert_overlap, o->max_len, o->max_errors,
                                                  s.fq[0].fwin.as<uint16_t>(), s.fq[1].fwin.as<uint16_t>(),
                                                  (unsigned long long*)(d_stats + L.o_hist[0]), (unsigned long long*)(d_stats + L.o_hist[1]),
-                                                 (unsigned long long*)(d_stats + L.o_adj[0]), (unsigned long long*)(d_stats + L.o_adj[1]), d_ctr);
+                                                 (unsigned long long*)(d_stats + L.o_adj[0]), (unsigned long long*)(d_stats + L.o_adj[1]), d_ctr,
+                                                 o->ops, d_ops);
     LAUNCHED(ctx);
     for (int f = 0; f < 2; f++) {
         FqSide& q = s.fq[f];
@@ -730,6 +760,7 @@ extern "C" int atr_trim_fastq_pe_host(atr_ctx* ctx, const atr_insertset* iset, c
         if (stats->errors_back[f]) for (size_t i = 0; i < L.H; i++) stats->errors_back[f][i] += (int64_t)hh[i];
         if (stats->adjacent_bases[f]) for (size_t i = 0; i < 5; i++) stats->adjacent_bases[f][i] += (int64_t)ha[i];
     }
+    fq_add_ops(stats->ops, *(const FqOpsCounters*)(hst.data() + L.o_ops));
     out_bytes[0] = opos[0]; out_bytes[1] = opos[1];
     consumed[0] = pos[0]; consumed[1] = pos[1];
     ctx->last_ms = -1.f;

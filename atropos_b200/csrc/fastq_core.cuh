@@ -235,3 +235,98 @@ ATR_HD int fq_pe_trim(const PeMatch& m, int len, const unsigned char* __restrict
     a.new_lo = 0; a.new_hi = m.rstart;
     return m.rstart;
 }
+
+// ---- the modifiers and filters around the adapter stage (atr_read_ops) ------------------------------------------------
+// Device-side counters, one block per call.
+struct FqOpsCounters {
+    unsigned long long bp_cut[2], bp_quality[2], bp_n_ends[2];
+    unsigned long long too_short, too_long, too_many_n, discarded_trimmed, discarded_untrimmed;
+    unsigned long long records_written;
+};
+
+// quality_trim_index (commands/trim/_qualtrim.pyx:7-49), the BWA rule on both ends
+ATR_HD void fq_quality_trim_index(const unsigned char* __restrict__ q, int len, int cutoff_front, int cutoff_back, int base,
+                                  int& start, int& stop) {
+    start = 0; stop = len;
+    int s = 0, max_qual = 0;
+    for (int i = 0; i < len; i++) {
+        s += cutoff_front - ((int)q[i] - base);
+        if (s < 0) break;
+        if (s > max_qual) { max_qual = s; start = i + 1; }
+    }
+    max_qual = 0; s = 0;
+    for (int i = len - 1; i >= 0; i--) {
+        s += cutoff_back - ((int)q[i] - base);
+        if (s < 0) break;
+        if (s > max_qual) { max_qual = s; stop = i; }
+    }
+    if (start >= stop) { start = 0; stop = 0; }
+}
+
+// UnconditionalCutter then QualityTrimmer on one record, BEFORE the adapters: the record table entry is narrowed to what
+// is left (nothing downstream needs the removed ends). bp_cut / bp_quality get Trimmer.trimmed_bases' increments:
+// clip() counts the nominal lengths (modifiers.py:73-82, _seqio.pyx:76-88), subseq() begin + (len - end) (:54-71).
+ATR_HD void fq_pre_ops(const atr_read_ops& o, int side, const unsigned char* __restrict__ text, FqRec& R,
+                       unsigned& bp_cut, unsigned& bp_quality) {
+    bp_cut = bp_quality = 0;
+    int lo = 0, hi = R.seq_len;
+    const int front = o.cut_front[side], back = o.cut_back[side];
+    if ((front || back) && hi - lo > 0) {
+        const int L = hi - lo;
+        int a = front < L ? front : L;                 // read[front:back] / read[front:]
+        int b = back < 0 ? (L + back > 0 ? L + back : 0) : L;
+        if (a > b) a = b;
+        bp_cut = (unsigned)(front + (back < 0 ? -back : 0));
+        hi = lo + b; lo = lo + a;
+    }
+    if ((o.quality_front > 0 || o.quality_back > 0) && hi - lo > 0) {
+        int start, stop;
+        fq_quality_trim_index(text + R.qual_b + lo, hi - lo, o.quality_front, o.quality_back, o.quality_base, start, stop);
+        bp_quality = (unsigned)(start + ((hi - lo) - stop));
+        hi = lo + stop; lo = lo + start;
+    }
+    R.seq_b += (uint32_t)lo; R.qual_b += (uint32_t)lo; R.seq_len = (uint16_t)(hi - lo);
+}
+
+// NEndTrimmer on the window the adapters left (modifiers.py:776-784): leading and trailing runs of 'N'
+ATR_HD void fq_trim_n(const unsigned char* __restrict__ seq, int& lo, int& hi, unsigned& bp_n) {
+    bp_n = 0;
+    const int L = hi - lo;
+    if (L == 0) return;
+    int start = 0;
+    while (start < L && seq[lo + start] == 'N') start++;
+    int end = L;
+    while (end > 0 && seq[lo + end - 1] == 'N') end--;
+    // re: '^N+' and 'N+$' are found independently: an all-N read gives start = L and end = 0, both counted
+    bp_n = (unsigned)(start + (L - end));
+    int a = start, b = end;
+    if (a > b) { a = 0; b = 0; }
+    hi = lo + b; lo = lo + a;
+}
+
+// one read against the filters; returns 0 keep, or 1 too_short, 2 too_long, 3 too_many_n, 4 trimmed, 5 untrimmed: the
+// first filter that fires, in the order the command adds them (commands/trim/__init__.py:566-620)
+ATR_HD int fq_filter_one(const atr_read_ops& o, const unsigned char* __restrict__ seq, int lo, int hi, bool matched, int which) {
+    const int L = hi - lo;
+    if (which == 1) return o.minimum_length > 0 && L < o.minimum_length;
+    if (which == 2) return o.maximum_length >= 0 && L > o.maximum_length;
+    if (which == 3) {
+        if (!(o.max_n >= 0.0)) return 0;
+        int n = 0;
+        for (int i = lo; i < hi; i++) n += (seq[i] == 'N' || seq[i] == 'n');
+        if (o.max_n < 1.0) return L == 0 ? 0 : ((double)n / (double)L > o.max_n);
+        return (double)n > o.max_n;
+    }
+    if (which == 4) return o.discard_trimmed && matched;
+    return o.discard_untrimmed && !matched;
+}
+
+// single-end: SingleWrapper; paired-end: PairedWrapper with min_affected = 1 == either read (filters.py:54-95)
+ATR_HD int fq_filter(const atr_read_ops& o, const unsigned char* __restrict__ seq1, int lo1, int hi1, bool matched1,
+                     const unsigned char* __restrict__ seq2, int lo2, int hi2, bool matched2, bool paired) {
+    for (int which = 1; which <= 5; which++) {
+        if (fq_filter_one(o, seq1, lo1, hi1, matched1, which)) return which;
+        if (paired && fq_filter_one(o, seq2, lo2, hi2, matched2, which)) return which;
+    }
+    return 0;
+}

@@ -173,19 +173,39 @@ __global__ void __launch_bounds__(256) k_fq_gather(const unsigned char* __restri
     for (int i = lane; i < (int)R.seq_len; i += 32) dst[i] = src[i];
 }
 
-// initial windows
-__global__ void __launch_bounds__(256) k_fq_init_win(const FqRec* __restrict__ recs, long long n_rec, uint16_t* __restrict__ fwin,
-                                                     unsigned long long* __restrict__ records, unsigned long long* __restrict__ bp_in) {
+// UnconditionalCutter + QualityTrimmer before the adapters (fq_pre_ops): narrows the record table entries; also the
+// place where the input bases are counted
+__global__ void __launch_bounds__(256) k_fq_pre(const unsigned char* __restrict__ text, FqRec* __restrict__ recs, long long n_rec,
+                                                const __grid_constant__ atr_read_ops ops, int side, long long* __restrict__ seq_len64,
+                                                unsigned long long* __restrict__ bp_in, FqOpsCounters* __restrict__ oc) {
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned long long bp = 0;
+    unsigned long long bp = 0, cut = 0, qual = 0;
     if (r < n_rec) {
-        const unsigned len = recs[r].seq_len;
-        fwin[2 * r] = 0; fwin[2 * r + 1] = (uint16_t)len;
-        bp = len;
+        FqRec R = recs[r];
+        bp = R.seq_len;
+        unsigned c, q;
+        fq_pre_ops(ops, side, text, R, c, q);
+        cut = c; qual = q;
+        if (c || q) { recs[r] = R; seq_len64[r] = R.seq_len; }
     }
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) bp += __shfl_down_sync(0xffffffffu, bp, d);
-    if ((threadIdx.x & 31) == 0 && bp) atomicAdd(bp_in, bp);
+    for (int d = 16; d > 0; d >>= 1) {
+        bp += __shfl_down_sync(0xffffffffu, bp, d);
+        cut += __shfl_down_sync(0xffffffffu, cut, d);
+        qual += __shfl_down_sync(0xffffffffu, qual, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (bp) atomicAdd(bp_in, bp);
+        if (cut) atomicAdd(&oc->bp_cut[side], cut);
+        if (qual) atomicAdd(&oc->bp_quality[side], qual);
+    }
+}
+
+// initial windows
+__global__ void __launch_bounds__(256) k_fq_init_win(const FqRec* __restrict__ recs, long long n_rec, uint16_t* __restrict__ fwin,
+                                                     unsigned long long* __restrict__ records) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n_rec) { fwin[2 * r] = 0; fwin[2 * r + 1] = recs[r].seq_len; }
     if (r == 0 && records != nullptr) atomicAdd(records, (unsigned long long)n_rec);
 }
 
@@ -193,7 +213,7 @@ __global__ void __launch_bounds__(256) k_fq_init_win(const FqRec* __restrict__ r
 __global__ void __launch_bounds__(256) k_fq_apply(const unsigned char* __restrict__ text, const FqRec* __restrict__ recs,
                                                   const atr_match* __restrict__ matches, long long n_rec, int round, int more_rounds,
                                                   const signed char* __restrict__ front_flags, int max_len, int max_errors,
-                                                  uint16_t* __restrict__ fwin, uint16_t* __restrict__ rwin,
+                                                  uint16_t* __restrict__ fwin, uint16_t* __restrict__ rwin, unsigned char* __restrict__ flags,
                                                   unsigned long long* __restrict__ hist_front, unsigned long long* __restrict__ hist_back,
                                                   unsigned long long* __restrict__ adjacent, FqCounters* __restrict__ ctr) {
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -205,6 +225,7 @@ __global__ void __launch_bounds__(256) k_fq_apply(const unsigned char* __restric
         if (m.status == ATR_ST_INVALID) atomicAdd(&ctr->invalid, 1ull);
         if (fq_apply(m, m.adapter >= 0 ? front_flags[m.adapter] : 0, lo, hi, text + recs[r].seq_b, a)) {
             hit = true;
+            if (round == 0) flags[r] = 1;                            // read.match is not None (filters.py:170-180)
             if (a.length <= max_len && a.errors <= max_errors) {
                 unsigned long long* h = a.front ? hist_front : hist_back;
                 atomicAdd(&h[((size_t)m.adapter * (size_t)(max_len + 1) + (size_t)a.length) * (size_t)(max_errors + 1) + (size_t)a.errors], 1ull);
@@ -230,8 +251,10 @@ __global__ void __launch_bounds__(256) k_fq_outlen(const FqRec* __restrict__ rec
     unsigned long long bp = 0;
     if (r < n_rec) {
         const int lo = fwin[2 * r], hi = fwin[2 * r + 1];
-        out_len[r] = fq_out_len(recs[r], lo, hi);
-        bp = (unsigned long long)(hi - lo);
+        if (lo <= hi) {                                            // lo > hi marks a read the filters discarded
+            out_len[r] = fq_out_len(recs[r], lo, hi);
+            bp = (unsigned long long)(hi - lo);
+        }
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) bp += __shfl_down_sync(0xffffffffu, bp, d);
@@ -247,7 +270,7 @@ __global__ void __launch_bounds__(256) k_fq_format(const unsigned char* __restri
     const int lane = threadIdx.x & 31;
     const FqRec R = recs[r];
     const int lo = fwin[2 * r], hi = fwin[2 * r + 1];
-    const uint32_t total = fq_out_len(R, lo, hi);
+    const uint32_t total = lo <= hi ? fq_out_len(R, lo, hi) : 0u;
     unsigned char* dst = out + out_off[r];
     for (uint32_t i = lane; i < total; i += 32) dst[i] = fq_out_byte(text, R, lo, hi, i);
     if (r == n_rec - 1 && lane == 0) info->out_bytes = (unsigned long long)(out_off[r] + total);
@@ -288,7 +311,8 @@ __global__ void __launch_bounds__(256) k_pe_apply(const unsigned char* __restric
                                                   int max_len, int max_errors, uint16_t* __restrict__ fwin1, uint16_t* __restrict__ fwin2,
                                                   unsigned long long* __restrict__ hist1, unsigned long long* __restrict__ hist2,
                                                   unsigned long long* __restrict__ adj1, unsigned long long* __restrict__ adj2,
-                                                  FqPeCounters* __restrict__ ctr) {
+                                                  FqPeCounters* __restrict__ ctr, const __grid_constant__ atr_read_ops ops,
+                                                  FqOpsCounters* __restrict__ oc) {
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n) return;
     const FqRec A = r1[r], B = r2[r];
@@ -314,11 +338,55 @@ __global__ void __launch_bounds__(256) k_pe_apply(const unsigned char* __restric
         else atomicAdd(&ctr->overflow, 1ull);
         atomicAdd(&adj2[ap.adjacent], 1ull);
     }
-    fwin1[2 * r] = 0; fwin1[2 * r + 1] = (uint16_t)k1;
-    fwin2[2 * r] = 0; fwin2[2 * r + 1] = (uint16_t)k2;
+    // NEndTrimmer on both reads, then the pair filters ("any": either read)
+    int lo1 = 0, hi1 = k1, lo2 = 0, hi2 = k2;
+    if (ops.trim_n) {
+        unsigned bp_n;
+        fq_trim_n(t1 + A.seq_b, lo1, hi1, bp_n);
+        if (bp_n) atomicAdd(&oc->bp_n_ends[0], (unsigned long long)bp_n);
+        fq_trim_n(t2 + B.seq_b, lo2, hi2, bp_n);
+        if (bp_n) atomicAdd(&oc->bp_n_ends[1], (unsigned long long)bp_n);
+    }
+    const int flt = fq_filter(ops, t1 + A.seq_b, lo1, hi1, m1.present != 0, t2 + B.seq_b, lo2, hi2, m2.present != 0, true);
+    if (flt) {
+        unsigned long long* c = flt == 1 ? &oc->too_short : flt == 2 ? &oc->too_long : flt == 3 ? &oc->too_many_n
+                                : flt == 4 ? &oc->discarded_trimmed : &oc->discarded_untrimmed;
+        atomicAdd(c, 1ull);
+        lo1 = lo2 = 1; hi1 = hi2 = 0;
+    } else {
+        atomicAdd(&oc->records_written, 1ull);
+    }
+    fwin1[2 * r] = (uint16_t)lo1; fwin1[2 * r + 1] = (uint16_t)hi1;
+    fwin2[2 * r] = (uint16_t)lo2; fwin2[2 * r + 1] = (uint16_t)hi2;
 }
 
 // bytes consumed by the first n records (n < the chunk's complete records): -> mapped pinned host memory
 __global__ void k_fq_consumed(const uint32_t* __restrict__ nl, long long n, FqInfo* h_info) {
     if (blockIdx.x == 0 && threadIdx.x == 0) h_info->consumed = n > 0 ? (long long)nl[4 * n - 1] + 1 : 0;
+}
+
+// NEndTrimmer + the filters after the adapter stage, single-end: final window, or the "discarded" mark (lo > hi)
+__global__ void __launch_bounds__(256) k_fq_post(const unsigned char* __restrict__ text, const FqRec* __restrict__ recs, long long n_rec,
+                                                 const __grid_constant__ atr_read_ops ops, uint16_t* __restrict__ fwin,
+                                                 const unsigned char* __restrict__ flags, FqOpsCounters* __restrict__ oc) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rec) return;
+    const FqRec R = recs[r];
+    int lo = fwin[2 * r], hi = fwin[2 * r + 1];
+    const unsigned char* seq = text + R.seq_b;
+    if (ops.trim_n) {
+        unsigned bp_n;
+        fq_trim_n(seq, lo, hi, bp_n);
+        if (bp_n) atomicAdd(&oc->bp_n_ends[0], (unsigned long long)bp_n);
+    }
+    const int f = fq_filter(ops, seq, lo, hi, flags[r] != 0, seq, 0, 0, false, false);
+    if (f) {
+        unsigned long long* c = f == 1 ? &oc->too_short : f == 2 ? &oc->too_long : f == 3 ? &oc->too_many_n
+                                : f == 4 ? &oc->discarded_trimmed : &oc->discarded_untrimmed;
+        atomicAdd(c, 1ull);
+        lo = 1; hi = 0;
+    } else {
+        atomicAdd(&oc->records_written, 1ull);
+    }
+    fwin[2 * r] = (uint16_t)lo; fwin[2 * r + 1] = (uint16_t)hi;
 }

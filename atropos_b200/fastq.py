@@ -24,6 +24,29 @@ class FormatError(Exception):
 _BASES = ('A', 'C', 'G', 'T', '')
 
 
+def new_ops_stats():
+    """Trimmer.trimmed_bases per modifier ([read 1, read 2]) and FilterWrapper.filtered per filter, as the report
+    names them (modifiers.py:84-88, filters.py:48-52), plus the records written."""
+    d = {"bp_cut": [0, 0], "bp_quality": [0, 0], "bp_n_ends": [0, 0]}
+    d.update({k: 0 for k in _abi.OPS_STAT_KEYS})
+    return d
+
+
+def merge_ops_stats(mine, theirs):
+    for k, v in theirs.items():
+        if isinstance(v, list):
+            mine[k] = [a + b for a, b in zip(mine[k], v)]
+        else:
+            mine[k] += v
+
+
+def _add_ops_stats(dst, st):
+    for k in ("bp_cut", "bp_quality", "bp_n_ends"):
+        dst[k] = [dst[k][i] + int(getattr(st, k)[i]) for i in range(2)]
+    for k in _abi.OPS_STAT_KEYS:
+        dst[k] += int(getattr(st, k))
+
+
 class TrimStats(object):
     """What the reference's report holds for one AdapterCutter (commands/trim/modifiers.py:189-195 and
     adapters/__init__.py:474-505), accumulated over calls / shards with `merge`."""
@@ -35,8 +58,10 @@ class TrimStats(object):
         self.errors_back = np.zeros(shape, dtype=np.int64)
         self.adjacent = np.zeros((n_adapters, 5), dtype=np.int64)
         self.records = self.with_adapters = self.bp_in = self.bp_out = self.overflow = 0
+        self.ops = new_ops_stats()
 
     def merge(self, other):
+        merge_ops_stats(self.ops, other.ops)
         self.errors_front += other.errors_front
         self.errors_back += other.errors_back
         self.adjacent += other.adjacent
@@ -122,7 +147,11 @@ class FastqTrimmer(object):
     `adapters`: atropos_b200.adapters.Adapter objects in the order the reference's AdapterCutter would try them
     (the command line collects -a, then -b, then -g). Linked adapters are not handled by this path."""
 
-    def __init__(self, adapters, times=1, max_len=512, device=0, chunk_bytes=0):
+    def __init__(self, adapters, times=1, max_len=512, device=0, chunk_bytes=0, **read_ops):
+        """read_ops: the command's modifier / filter options around the adapter stage, see _abi.make_read_ops (cut,
+        quality_cutoff, quality_base, trim_n, minimum_length, maximum_length, max_n, discard_trimmed,
+        discard_untrimmed), applied in the default operation order."""
+        self.ops = _abi.make_read_ops(**read_ops)
         self.adapters = list(adapters)
         self.times = int(times)
         self.max_len = int(max_len)
@@ -142,7 +171,7 @@ class FastqTrimmer(object):
             out = np.empty(max(n, 1), dtype=np.uint8)
         if stats is None:
             stats = self.new_stats()
-        opts = _abi.AtrTrimOpts(self.times, self.max_len, self.max_errors, int(bool(final)), self.chunk_bytes)
+        opts = _abi.AtrTrimOpts(self.times, self.max_len, self.max_errors, int(bool(final)), self.chunk_bytes, self.ops)
         st = _abi.AtrTrimStats()
         st.errors_front = stats.errors_front.ctypes.data
         st.errors_back = stats.errors_back.ctypes.data
@@ -157,6 +186,7 @@ class FastqTrimmer(object):
         _lib.check(rc, self.ctx.handle)
         for k in ("records", "with_adapters", "bp_in", "bp_out", "overflow"):
             setattr(stats, k, getattr(stats, k) + int(getattr(st, k)))
+        _add_ops_stats(stats.ops, st.ops)
         if st.overflow:
             raise OverflowError("a removed length exceeds max_len=%d: create the FastqTrimmer with a larger max_len" % self.max_len)
         return out[:nout.value], stats, int(consumed.value)
@@ -171,8 +201,10 @@ class PairTrimStats(object):
         self.adjacent = [np.zeros(5, dtype=np.int64) for _ in range(2)]
         self.records = self.insert_matches = self.overflow = 0
         self.with_adapters, self.bp_in, self.bp_out = [0, 0], [0, 0], [0, 0]
+        self.ops = new_ops_stats()
 
     def merge(self, other):
+        merge_ops_stats(self.ops, other.ops)
         for i in range(2):
             self.errors_back[i] += other.errors_back[i]
             self.adjacent[i] += other.adjacent[i]
@@ -200,7 +232,8 @@ class FastqPairTrimmer(object):
     insert_aligner: atropos_b200.align.InsertAligner with the same sequences."""
 
     def __init__(self, adapter1, adapter2, insert_aligner, symmetric=True, min_insert_overlap=1, max_len=256, device=0,
-                 chunk_bytes=0):
+                 chunk_bytes=0, **read_ops):
+        self.ops = _abi.make_read_ops(**read_ops)
         for a in (adapter1, adapter2):
             if a.where != BACK:
                 raise ValueError("the insert-aligner path takes one 3' adapter per read")
@@ -228,7 +261,7 @@ class FastqPairTrimmer(object):
         if stats is None:
             stats = self.new_stats()
         opts = _abi.AtrTrimPeOpts(int(self.symmetric), self.min_insert_overlap, self.max_len, self.max_errors,
-                                  int(bool(final)), 0, self.chunk_bytes)
+                                  int(bool(final)), 0, self.chunk_bytes, self.ops)
         st = _abi.AtrTrimPeStats()
         for i in range(2):
             st.errors_back[i] = stats.errors_back[i].ctypes.data
@@ -251,6 +284,7 @@ class FastqPairTrimmer(object):
             stats.with_adapters[i] += int(st.with_adapters[i])
             stats.bp_in[i] += int(st.bp_in[i])
             stats.bp_out[i] += int(st.bp_out[i])
+        _add_ops_stats(stats.ops, st.ops)
         if st.overflow:
             raise OverflowError("a removed length exceeds max_len=%d: create the FastqPairTrimmer with a larger max_len" % self.max_len)
         return (out1[:nout[0]], out2[:nout[1]]), stats, (int(consumed[0]), int(consumed[1]))

@@ -246,6 +246,31 @@ typedef struct atr_fastq_error {
     int64_t line_end2;        /* file 1, line_begin2/line_end2 = header line of its mate in file 2 */
 } atr_fastq_error;
 
+/* The modifiers and filters the `trim` command puts around the adapter stage (commands/trim/__init__.py:422-620),
+ * in the default operation order "CGQAW" (trim/cli.py:232-241): cut and quality-trim BEFORE the adapters, N-end
+ * trimming after them, then the filters in the order the command adds them. All zero / off by default. */
+typedef struct atr_read_ops {
+    int32_t cut_front[2];     /* -u N / -U N, N > 0 summed: UnconditionalCutter.front_length of read 1 / read 2 (modifiers.py:565-585) */
+    int32_t cut_back[2];      /* -u -N / -U -N summed (<= 0): back_length */
+    int32_t quality_front;    /* -q F,B: QualityTrimmer cutoffs (modifiers.py:748-764, _qualtrim.pyx:7-49); 0,0 = off */
+    int32_t quality_back;
+    int32_t quality_base;     /* --quality-base, 33 */
+    int32_t trim_n;           /* --trim-n: NEndTrimmer (modifiers.py:766-784) */
+    int32_t minimum_length;   /* -m: TooShortReadFilter, 0 = off (filters.py:118-128) */
+    int32_t maximum_length;   /* -M: TooLongReadFilter, < 0 = off (filters.py:130-140) */
+    int32_t discard_trimmed;  /* --discard-trimmed: TrimmedFilter (filters.py:176-180) */
+    int32_t discard_untrimmed;/* --discard-untrimmed: UntrimmedFilter (filters.py:170-174) */
+    double  max_n;            /* --max-n: NContentFilter, < 0 = off; < 1 is a proportion (filters.py:142-168) */
+} atr_read_ops;
+
+/* Trimmer.trimmed_bases per modifier and read (modifiers.py:45-88), FilterWrapper.filtered per filter (filters.py:18-52;
+ * paired-end: the pair filter "any", PairedWrapper with min_affected = 1), and what was written. ADDED to. */
+typedef struct atr_read_ops_stats {
+    int64_t bp_cut[2], bp_quality[2], bp_n_ends[2];
+    int64_t too_short, too_long, too_many_n, discarded_trimmed, discarded_untrimmed;
+    int64_t records_written;  /* reads (pairs) that passed every filter; their bases are bp_out of the enclosing struct */
+} atr_read_ops_stats;
+
 /* AdapterCutter(adapters, times, action='trim') (commands/trim/modifiers.py:91-105) */
 typedef struct atr_trim_opts {
     int32_t times;            /* >= 1: rounds of best-match-and-trim per read (modifiers.py:141-149) */
@@ -254,6 +279,7 @@ typedef struct atr_trim_opts {
     int32_t final_chunk;      /* 1: `text` ends the file (a partial last record is an error, an unterminated last
                                  line is a line); 0: stop after the last complete record and report `consumed` */
     int64_t chunk_bytes;      /* internal H2D chunk size, 0 = default (64 MiB) */
+    atr_read_ops ops;         /* index 0 of the per-read fields */
 } atr_trim_opts;
 
 /* What Adapter.trimmed() accumulates (adapters/__init__.py:413-436) and the report prints. The histogram
@@ -261,11 +287,12 @@ typedef struct atr_trim_opts {
  * Summary.merge, commands/multicore.py:389). Index: ((a*(max_len+1) + length)*(max_errors+1) + errors;
  * lengths_front/back of the reference are the row sums. */
 typedef struct atr_trim_stats {
-    int64_t records, with_adapters, bp_in, bp_out;
+    int64_t records, with_adapters, bp_in, bp_out;   /* bp_out = bases written (reads that passed the filters) */
     int64_t overflow;         /* matches outside the histogram extents (not counted in the arrays) */
     int64_t* errors_front;    /* [n_adapters][max_len+1][max_errors+1] */
     int64_t* errors_back;     /* same shape */
     int64_t* adjacent_bases;  /* [n_adapters][5]: A, C, G, T, '' (anything else) */
+    atr_read_ops_stats ops;
 } atr_trim_stats;
 
 /* Replaces, for single-end FASTQ and the adapter-trimming modifier, the per-record pipeline
@@ -292,6 +319,7 @@ typedef struct atr_trim_pe_opts {
     int32_t final_chunk;        /* 1: both texts end their files */
     int32_t pad;
     int64_t chunk_bytes;        /* per text; 0 = default (32 MiB) */
+    atr_read_ops ops;
 } atr_trim_pe_opts;
 
 typedef struct atr_trim_pe_stats {
@@ -300,6 +328,7 @@ typedef struct atr_trim_pe_stats {
     int64_t overflow;
     int64_t* errors_back[2];                  /* per read: [max_len+1][max_errors+1], ADDED to */
     int64_t* adjacent_bases[2];               /* per read: [5] */
+    atr_read_ops_stats ops;
 } atr_trim_pe_stats;
 
 /* Replaces, for two FASTQ files read in lockstep, PairedSequenceReader.__iter__ (io/seqio.py:429-453: pairing and

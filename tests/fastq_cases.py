@@ -24,8 +24,23 @@ def _str_keys(d):
     return {str(k): ({str(k2): v2 for k2, v2 in v.items()} if isinstance(v, dict) else v) for k, v in d.items()}
 
 
+def check_ops(case, stats, paired=False):
+    """Trimmer.trimmed_bases / FilterWrapper.filtered / records written, for every modifier and filter that was on"""
+    gold = case["result"].get("ops")
+    if gold is None:
+        return
+    for key, val in gold.items():
+        if val is None:                                   # that modifier / filter was not part of the command
+            assert stats.ops[key] in (0, [0, 0]), (case["label"], key)
+        elif isinstance(val, list):
+            assert stats.ops[key][:len(val)] == val and not any(stats.ops[key][len(val):]), (case["label"], key)
+        else:
+            assert stats.ops[key] == val, (case["label"], key)
+
+
 def check(case, out, stats, adapters):
     res = case["result"]
+    check_ops(case, stats)
     assert bytes(out) == res["out"].encode("latin-1")
     assert stats.records == res["records"]
     assert stats.with_adapters == res["with_adapters"]
@@ -66,6 +81,7 @@ def pe_objects(case):
 
 def pe_check(case, outs, stats):
     res = case["result"]
+    check_ops(case, stats, paired=True)
     assert bytes(outs[0]) == res["out1"].encode("latin-1")
     assert bytes(outs[1]) == res["out2"].encode("latin-1")
     assert stats.records == res["records"]

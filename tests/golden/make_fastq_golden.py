@@ -71,6 +71,18 @@ def make_records(rng, n, adapters, max_len=150, ragged=True, lower=0.05, with_fr
     return recs
 
 
+def ops_stats(rj, read):
+    """bp_trimmed of the cutters / trimmers, records_filtered of the filters, records written"""
+    t = rj["trim"]
+    mods, flt = t["modifiers"], t.get("filters", {})
+    bp = lambda name: [int(x or 0) for x in mods[name]["bp_trimmed"]] if name in mods else None
+    nf = lambda name: flt[name]["records_filtered"] if name in flt else None
+    return {"bp_cut": bp("UnconditionalCutter"), "bp_quality": bp("QualityTrimmer"), "bp_n_ends": bp("NEndTrimmer"),
+            "too_short": nf("too_short"), "too_long": nf("too_long"), "too_many_n": nf("too_many_n"),
+            "discarded_trimmed": nf("TrimmedFilter"), "discarded_untrimmed": nf("UntrimmedFilter"),
+            "records_written": t["formatters"]["records_written"]}
+
+
 def run_reference(text, adapters, times, error_rate, overlap, extra=()):
     from atropos.commands import get_command
     tmp = tempfile.mkdtemp(prefix="fqgold")
@@ -117,7 +129,9 @@ def run_reference(text, adapters, times, error_rate, overlap, extra=()):
                     cols = st[key]["columns"]
                     d[key] = {ln: {str(c): v for c, v in zip(cols, row) if v} for ln, row in st[key]["rows"].items()}
             ad_stats.append(d)
-        return {"out": out_text, "records": rj["record_counts"].get("0", 0), "with_adapters": cutter["records_with_adapters"][0],
+        extra_stats = ops_stats(rj, 0)
+        return {"ops": extra_stats,
+                "out": out_text, "records": rj["record_counts"].get("0", 0), "with_adapters": cutter["records_with_adapters"][0],
                 "bp_in": rj["bp_counts"].get("0", [0, 0])[0],
                 "bp_out": rj["trim"]["formatters"]["bp_written"][0] if "formatters" in rj["trim"] else None,
                 "adapters": ad_stats}
@@ -131,11 +145,11 @@ def main():
     rng = np.random.default_rng(9001)
     cases = []
 
-    def add(label, text, adapters, times=1, error_rate=0.1, overlap=3):
-        res = run_reference(text, adapters, times, error_rate, overlap)
+    def add(label, text, adapters, times=1, error_rate=0.1, overlap=3, extra=(), read_ops=None):
+        res = run_reference(text, adapters, times, error_rate, overlap, extra)
         print(label, {k: (v if not isinstance(v, (str, list)) else len(v)) for k, v in res.items()})
         cases.append({"label": label, "text": text, "adapters": adapters, "times": times, "error_rate": error_rate,
-                      "overlap": overlap, "result": res})
+                      "overlap": overlap, "read_ops": read_ops or {}, "result": res})
 
     one = [(TRUSEQ1, "back")]
     add("se150_truseq", fastq(make_records(rng, 700, one, ragged=False, lower=0.0)), one)
@@ -148,6 +162,28 @@ def main():
     add("no_final_newline", fastq(make_records(rng, 50, one, ragged=False), final_eol=False), one)
     add("empty_file", "", one)
     add("single_empty_read", "@r\n\n+\n\n", one)
+    # --- the modifiers / filters around the adapter stage (default operation order) --------------------------------
+    def lowq(recs, rng):                                   # qualities that decay towards the ends, some N ends
+        out = []
+        for name, seq, name2, q in recs:
+            L = len(seq)
+            q = "".join(chr(33 + int(max(2, min(40, 40 - abs(i - L * 0.4) * rng.uniform(0.2, 0.9) + rng.normal(0, 4))))) for i in range(L))
+            if rng.random() < 0.2 and L > 6:
+                k1, k2 = int(rng.integers(0, 4)), int(rng.integers(0, 5))
+                seq = "N" * k1 + seq[k1:L - k2] + "N" * k2
+            if rng.random() < 0.02:
+                seq = "N" * L
+            out.append((name, seq, name2, q))
+        return out
+    add("ops_quality_trimn_minlen", fastq(lowq(make_records(rng, 500, one, ragged=True), rng)), one,
+        extra=["-q", "15,20", "--trim-n", "-m", "25"], read_ops=dict(quality_cutoff=[15, 20], trim_n=True, minimum_length=25))
+    add("ops_cut_maxlen_maxn", fastq(lowq(make_records(rng, 500, one, ragged=True), rng)), one,
+        extra=["-u", "5", "-u", "-3", "-M", "120", "--max-n", "2"], read_ops=dict(cut=[5, -3], maximum_length=120, max_n=2))
+    add("ops_q_single_maxn_frac_discard_untrimmed", fastq(lowq(make_records(rng, 400, one, ragged=True), rng)), one,
+        extra=["-q", "20", "--max-n", "0.05", "--discard-untrimmed"], read_ops=dict(quality_cutoff=[20], max_n=0.05, discard_untrimmed=True))
+    add("ops_panel_times2_all", fastq(lowq(make_records(rng, 500, panel), rng)), panel, times=2,
+        extra=["-u", "2", "-q", "10,10", "--trim-n", "-m", "20", "-M", "140", "--discard-trimmed"],
+        read_ops=dict(cut=[2], quality_cutoff=[10, 10], trim_n=True, minimum_length=20, maximum_length=140, discard_trimmed=True))
     # --- malformed inputs: the reader's FormatErrors -------------------------------------------------
     good = make_records(rng, 8, one, ragged=False)
     t = fastq(good)

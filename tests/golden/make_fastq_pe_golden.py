@@ -73,6 +73,17 @@ def adapter_stats(st):
     return d
 
 
+def ops_stats(rj):
+    t = rj["trim"]
+    mods, flt = t["modifiers"], t.get("filters", {})
+    bp = lambda name: [int(x or 0) for x in mods[name]["bp_trimmed"]] if name in mods else None
+    nf = lambda name: flt[name]["records_filtered"] if name in flt else None
+    return {"bp_cut": bp("UnconditionalCutter"), "bp_quality": bp("QualityTrimmer"), "bp_n_ends": bp("NEndTrimmer"),
+            "too_short": nf("too_short"), "too_long": nf("too_long"), "too_many_n": nf("too_many_n"),
+            "discarded_trimmed": nf("TrimmedFilter"), "discarded_untrimmed": nf("UntrimmedFilter"),
+            "records_written": t["formatters"]["records_written"]}
+
+
 def run_reference(text1, text2, error_rate, extra=()):
     from atropos.commands import get_command
     tmp = tempfile.mkdtemp(prefix="fqpegold")
@@ -105,7 +116,7 @@ def run_reference(text1, text2, error_rate, extra=()):
             rj = json.load(fh)
         cutter = rj["trim"]["modifiers"]["InsertAdapterCutter"]
         ads = [adapter_stats(list(d.values())[0]) for d in cutter["adapters"]]
-        return {"out1": outs[0], "out2": outs[1], "records": rj["record_counts"].get("0", 0),
+        return {"ops": ops_stats(rj), "out1": outs[0], "out2": outs[1], "records": rj["record_counts"].get("0", 0),
                 "with_adapters": cutter["records_with_adapters"], "bp_in": rj["bp_counts"].get("0", [0, 0]),
                 "bp_out": rj["trim"]["formatters"]["bp_written"], "adapters": ads}
     finally:
@@ -118,14 +129,15 @@ def main():
     rng = np.random.default_rng(9101)
     cases = []
 
-    def add(label, recs, error_rate=0.1, edit=None):
+    def add(label, recs, error_rate=0.1, edit=None, extra=(), read_ops=None):
         t1, t2 = fastq(recs[0]), fastq(recs[1])
         if edit:
             t1, t2 = edit(t1, t2)
-        res = run_reference(t1, t2, error_rate)
+        res = run_reference(t1, t2, error_rate, extra)
         print(label, {k: (v if not isinstance(v, (str, list)) else (len(v) if isinstance(v, str) else v if len(v) < 3 else len(v)))
                       for k, v in res.items()})
-        cases.append({"label": label, "text1": t1, "text2": t2, "error_rate": error_rate, "result": res})
+        cases.append({"label": label, "text1": t1, "text2": t2, "error_rate": error_rate, "read_ops": read_ops or {},
+                      "result": res})
 
     add("pe150", make_pairs(rng, 500, seed=11))
     add("pe150_suffix_names", make_pairs(rng, 300, suffix=True, seed=12))
@@ -133,6 +145,24 @@ def main():
     add("default_rates", make_pairs(rng, 300, ragged=True, seed=14), error_rate=None)
     add("pe100_e02", make_pairs(rng, 300, L=100, seed=15), error_rate=0.2)
     add("empty_files", ([], []))
+    # --- the paper's benchmark options (paper/workflow/simulated.nf:143-150: -q 0 --trim-n -m 25) and friends -----------
+    def lowq(recs):
+        out = []
+        for name, seq, name2, q in recs:
+            L = len(seq)
+            q = "".join(chr(33 + int(max(2, min(40, 38 - i * rng.uniform(0.0, 0.35) + rng.normal(0, 4))))) for i in range(L))
+            if rng.random() < 0.2 and L > 6:
+                k1, k2 = int(rng.integers(0, 3)), int(rng.integers(0, 5))
+                seq = "N" * k1 + seq[k1:L - k2] + "N" * k2
+            out.append((name, seq, name2, q))
+        return out
+    r = make_pairs(rng, 400, ragged=True, seed=21)
+    add("ops_trimn_minlen", (lowq(r[0]), lowq(r[1])), extra=["--trim-n", "-m", "25"], read_ops=dict(trim_n=True, minimum_length=25))
+    r = make_pairs(rng, 400, ragged=True, seed=22)
+    add("ops_quality_cut_maxn", (lowq(r[0]), lowq(r[1])), extra=["-q", "10,20", "-u", "3", "-U", "-4", "--max-n", "3", "-m", "30", "-M", "140"],
+        read_ops=dict(quality_cutoff=[10, 20], cut=[3], cut2=[-4], max_n=3, minimum_length=30, maximum_length=140))
+    r = make_pairs(rng, 300, seed=23)
+    add("ops_discard_untrimmed", (lowq(r[0]), lowq(r[1])), extra=["--discard-untrimmed", "--trim-n"], read_ops=dict(discard_untrimmed=True, trim_n=True))
     # --- improper pairing / malformed input --------------------------------------------------------------------
     def drop_last(which):
         def f(t1, t2):

@@ -111,9 +111,15 @@ int sim_multi_locate(const unsigned char* ref, int m, const unsigned char* query
 // The FASTQ-in -> trimmed-FASTQ-out path with the device functions of fastq_core.cuh (framing, window/statistics
 // bookkeeping, formatting) and sim_locate for the alignments: what atr_trim_fastq_host computes, one record at a
 // time. counters = {records, with_adapters, bp_in, bp_out, overflow}. Returns 0, or ATR_E_FORMAT with *err filled.
+static void sim_count_filter(FqOpsCounters& oc, int f) {
+    if (f == 1) oc.too_short++; else if (f == 2) oc.too_long++; else if (f == 3) oc.too_many_n++;
+    else if (f == 4) oc.discarded_trimmed++; else if (f == 5) oc.discarded_untrimmed++; else oc.records_written++;
+}
+
 int sim_trim_fastq(const atr_adapter_desc* descs, int n_adapters, const atr_trim_opts* o, const unsigned char* text,
                    long long nbytes, unsigned char* out_text, long long* out_bytes, long long* consumed, long long* counters,
-                   long long* errors_front, long long* errors_back, long long* adjacent, atr_fastq_error* err) {
+                   long long* errors_front, long long* errors_back, long long* adjacent, atr_fastq_error* err,
+                   FqOpsCounters* oc) {
     std::vector<uint32_t> nl;
     for (long long i = 0; i < nbytes; i++) {
         if (text[i] == '\n') nl.push_back((uint32_t)i);
@@ -154,9 +160,12 @@ int sim_trim_fastq(const atr_adapter_desc* descs, int n_adapters, const atr_trim
     const size_t H = (size_t)(o->max_len + 1) * (size_t)(o->max_errors + 1);
     long long opos = 0;
     for (long long r = 0; r < n_rec; r++) {
-        const FqRec& R = recs[(size_t)r];
-        int lo = 0, hi = R.seq_len;
+        FqRec R = recs[(size_t)r];
         counters[0]++; counters[2] += R.seq_len;
+        unsigned bpc, bpq;
+        fq_pre_ops(o->ops, 0, text, R, bpc, bpq);
+        oc->bp_cut[0] += bpc; oc->bp_quality[0] += bpq;
+        int lo = 0, hi = R.seq_len;
         bool any = false;
         for (int round = 0; round < o->times; round++) {
             atr_match m;
@@ -180,6 +189,10 @@ int sim_trim_fastq(const atr_adapter_desc* descs, int n_adapters, const atr_trim
         }
         (void)H;
         if (any) counters[1]++;
+        if (o->ops.trim_n) { unsigned bpn; fq_trim_n(text + R.seq_b, lo, hi, bpn); oc->bp_n_ends[0] += bpn; }
+        const int flt = fq_filter(o->ops, text + R.seq_b, lo, hi, any, text, 0, 0, false, false);
+        sim_count_filter(*oc, flt);
+        if (flt) continue;
         counters[3] += hi - lo;
         const uint32_t total = fq_out_len(R, lo, hi);
         for (uint32_t i = 0; i < total; i++) out_text[opos + i] = fq_out_byte(text, R, lo, hi, i);
@@ -219,7 +232,8 @@ struct SimText {
 int sim_trim_fastq_pe(const atr_insert_desc* idesc, const atr_adapter_desc* d1, const atr_adapter_desc* d2,
                       const atr_trim_pe_opts* o, const unsigned char* text1, long long nbytes1, const unsigned char* text2,
                       long long nbytes2, unsigned char* out1, unsigned char* out2, long long* out_bytes, long long* consumed,
-                      long long* counters, long long* eb1, long long* eb2, long long* adj1, long long* adj2, atr_fastq_error* err) {
+                      long long* counters, long long* eb1, long long* eb2, long long* adj1, long long* adj2, atr_fastq_error* err,
+                      FqOpsCounters* oc) {
     SimText T[2];
     T[0].text = text1; T[0].nbytes = nbytes1; T[1].text = text2; T[1].nbytes = nbytes2;
     for (int f = 0; f < 2; f++) if (!T[f].index(o->final_chunk)) { err->kind = ATR_FQ_BARE_CR; err->file = f; err->record = -1; return ATR_E_FORMAT; }
@@ -263,9 +277,14 @@ int sim_trim_fastq_pe(const atr_insert_desc* idesc, const atr_adapter_desc* d1, 
     consumed[1] = o->final_chunk ? nbytes2 : T[1].consumed_for(n);
     long long opos1 = 0, opos2 = 0;
     for (long long r = 0; r < n; r++) {
-        const FqRec &A = R1[(size_t)r], &B = R2[(size_t)r];
+        FqRec A = R1[(size_t)r], B = R2[(size_t)r];
+        counters[0]++; counters[4] += A.seq_len; counters[5] += B.seq_len;
+        unsigned bpc, bpq;
+        fq_pre_ops(o->ops, 0, text1, A, bpc, bpq);
+        oc->bp_cut[0] += bpc; oc->bp_quality[0] += bpq;
+        fq_pre_ops(o->ops, 1, text2, B, bpc, bpq);
+        oc->bp_cut[1] += bpc; oc->bp_quality[1] += bpq;
         const int len1 = A.seq_len, len2 = B.seq_len;
-        counters[0]++; counters[4] += len1; counters[5] += len2;
         atr_insert_result ins;
         im_clear(ins.insert); im_clear(ins.match1); im_clear(ins.match2);
         atr_match fb1, fb2;
@@ -299,12 +318,21 @@ int sim_trim_fastq_pe(const atr_insert_desc* idesc, const atr_adapter_desc* d1, 
             if (ap.length <= o->max_len && ap.errors <= o->max_errors) eb2[(size_t)ap.length * (size_t)(o->max_errors + 1) + (size_t)ap.errors]++; else counters[8]++;
             adj2[ap.adjacent]++;
         }
-        counters[6] += k1; counters[7] += k2;
-        uint32_t total = fq_out_len(A, 0, k1);
-        for (uint32_t i = 0; i < total; i++) out1[opos1 + i] = fq_out_byte(text1, A, 0, k1, i);
+        int lo1 = 0, hi1 = k1, lo2 = 0, hi2 = k2;
+        if (o->ops.trim_n) {
+            unsigned bpn;
+            fq_trim_n(text1 + A.seq_b, lo1, hi1, bpn); oc->bp_n_ends[0] += bpn;
+            fq_trim_n(text2 + B.seq_b, lo2, hi2, bpn); oc->bp_n_ends[1] += bpn;
+        }
+        const int flt = fq_filter(o->ops, text1 + A.seq_b, lo1, hi1, m1.present != 0, text2 + B.seq_b, lo2, hi2, m2.present != 0, true);
+        sim_count_filter(*oc, flt);
+        if (flt) continue;
+        counters[6] += hi1 - lo1; counters[7] += hi2 - lo2;
+        uint32_t total = fq_out_len(A, lo1, hi1);
+        for (uint32_t i = 0; i < total; i++) out1[opos1 + i] = fq_out_byte(text1, A, lo1, hi1, i);
         opos1 += total;
-        total = fq_out_len(B, 0, k2);
-        for (uint32_t i = 0; i < total; i++) out2[opos2 + i] = fq_out_byte(text2, B, 0, k2, i);
+        total = fq_out_len(B, lo2, hi2);
+        for (uint32_t i = 0; i < total; i++) out2[opos2 + i] = fq_out_byte(text2, B, lo2, hi2, i);
         opos2 += total;
     }
     out_bytes[0] = opos1; out_bytes[1] = opos2;

@@ -12,6 +12,10 @@ CSRC = os.path.join(os.path.dirname(HERE), "atropos_b200", "csrc")
 _lib = None
 
 
+class SimOpsCounters(C.Structure):          # FqOpsCounters (fastq_core.cuh): same fields as atr_read_ops_stats, unsigned
+    _fields_ = [(n, t) for n, t in _abi.AtrReadOpsStats._fields_]
+
+
 def lib():
     global _lib
     if _lib is None:
@@ -31,13 +35,15 @@ def lib():
         L.sim_multi_locate.restype = C.c_int
         L.sim_trim_fastq.argtypes = [C.POINTER(_abi.AtrAdapterDesc), C.c_int, C.POINTER(_abi.AtrTrimOpts), C.c_char_p,
                                      C.c_longlong, C.c_void_p, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong),
-                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_abi.AtrFastqError)]
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_abi.AtrFastqError),
+                                     C.POINTER(SimOpsCounters)]
         L.sim_trim_fastq.restype = C.c_int
         L.sim_trim_fastq_pe.argtypes = [C.POINTER(_abi.AtrInsertDesc), C.POINTER(_abi.AtrAdapterDesc),
                                         C.POINTER(_abi.AtrAdapterDesc), C.POINTER(_abi.AtrTrimPeOpts), C.c_char_p,
                                         C.c_longlong, C.c_char_p, C.c_longlong, C.c_void_p, C.c_void_p,
                                         C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.c_void_p, C.c_void_p,
-                                        C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_abi.AtrFastqError)]
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_abi.AtrFastqError),
+                                        C.POINTER(SimOpsCounters)]
         L.sim_trim_fastq_pe.restype = C.c_int
         _lib = L
     return _lib
@@ -89,7 +95,7 @@ def multi_locate(ref, query, rate, flags, min_overlap, max_matches=100):
     return [tuple(out[6 * t:6 * t + 6]) for t in range(cnt)]
 
 
-def trim_fastq(text, adapters, times=1, max_len=512, final=True):
+def trim_fastq(text, adapters, times=1, max_len=512, final=True, **read_ops):
     """CPU run of the FASTQ path's device functions. adapters: atropos_b200.adapters.Adapter objects.
     Returns (out bytes, TrimStats, consumed) or raises atropos_b200.fastq.FormatError."""
     import numpy as np
@@ -98,24 +104,26 @@ def trim_fastq(text, adapters, times=1, max_len=512, final=True):
     arr = (_abi.AtrAdapterDesc * len(descs))(*descs)
     max_errors = max(int(a.max_error_rate * len(a.sequence)) for a in adapters)
     stats = fastq.TrimStats(len(adapters), max_len, max_errors)
-    opts = _abi.AtrTrimOpts(times, max_len, max_errors, int(bool(final)), 0)
+    opts = _abi.AtrTrimOpts(times, max_len, max_errors, int(bool(final)), 0, _abi.make_read_ops(**read_ops))
+    oc = SimOpsCounters()
     out = np.empty(max(len(text), 1), dtype=np.uint8)
     counters = np.zeros(5, dtype=np.int64)
     nout, consumed = C.c_longlong(0), C.c_longlong(0)
     err = _abi.AtrFastqError()
     rc = lib().sim_trim_fastq(arr, len(descs), C.byref(opts), text, len(text), out.ctypes.data, C.byref(nout),
                               C.byref(consumed), counters.ctypes.data, stats.errors_front.ctypes.data,
-                              stats.errors_back.ctypes.data, stats.adjacent.ctypes.data, C.byref(err))
+                              stats.errors_back.ctypes.data, stats.adjacent.ctypes.data, C.byref(err), C.byref(oc))
     if rc == _abi.ATR_E_FORMAT:
         raise fastq.FormatError(fastq.format_error_message(np.frombuffer(text, dtype=np.uint8), err))
     if rc != 0:
         raise RuntimeError("sim_trim_fastq rc=%d" % rc)
+    fastq._add_ops_stats(stats.ops, oc)
     stats.records, stats.with_adapters, stats.bp_in, stats.bp_out, stats.overflow = (int(x) for x in counters)
     return bytes(out[:nout.value]), stats, consumed.value
 
 
 def trim_fastq_pe(text1, text2, adapter1, adapter2, insert_aligner, symmetric=True, min_insert_overlap=1, max_len=256,
-                  final=True):
+                  final=True, **read_ops):
     """CPU run of the paired-end FASTQ path's device functions. Returns ((out1, out2), PairTrimStats, consumed)."""
     import numpy as np
     from atropos_b200 import fastq
@@ -124,7 +132,9 @@ def trim_fastq_pe(text1, text2, adapter1, adapter2, insert_aligner, symmetric=Tr
     idesc, k3 = insert_aligner.descriptor(max_len)
     max_errors = max(len(adapter1.sequence), len(adapter2.sequence))
     stats = fastq.PairTrimStats(max_len, max_errors)
-    opts = _abi.AtrTrimPeOpts(int(symmetric), min_insert_overlap, max_len, max_errors, int(bool(final)), 0, 0)
+    opts = _abi.AtrTrimPeOpts(int(symmetric), min_insert_overlap, max_len, max_errors, int(bool(final)), 0, 0,
+                              _abi.make_read_ops(**read_ops))
+    oc = SimOpsCounters()
     o1 = np.empty(max(len(text1), 1), dtype=np.uint8)
     o2 = np.empty(max(len(text2), 1), dtype=np.uint8)
     counters = np.zeros(9, dtype=np.int64)
@@ -133,12 +143,13 @@ def trim_fastq_pe(text1, text2, adapter1, adapter2, insert_aligner, symmetric=Tr
     rc = lib().sim_trim_fastq_pe(C.byref(idesc), C.byref(d1), C.byref(d2), C.byref(opts), text1, len(text1), text2, len(text2),
                                  o1.ctypes.data, o2.ctypes.data, nout, consumed, counters.ctypes.data,
                                  stats.errors_back[0].ctypes.data, stats.errors_back[1].ctypes.data,
-                                 stats.adjacent[0].ctypes.data, stats.adjacent[1].ctypes.data, C.byref(err))
+                                 stats.adjacent[0].ctypes.data, stats.adjacent[1].ctypes.data, C.byref(err), C.byref(oc))
     if rc == _abi.ATR_E_FORMAT:
         raise fastq.FormatError(fastq.format_error_message((np.frombuffer(text1, dtype=np.uint8),
                                                             np.frombuffer(text2, dtype=np.uint8)), err))
     if rc != 0:
         raise RuntimeError("sim_trim_fastq_pe rc=%d" % rc)
+    fastq._add_ops_stats(stats.ops, oc)
     c = [int(x) for x in counters]
     stats.records, stats.insert_matches, stats.overflow = c[0], c[1], c[8]
     stats.with_adapters, stats.bp_in, stats.bp_out = [c[2], c[3]], [c[4], c[5]], [c[6], c[7]]
