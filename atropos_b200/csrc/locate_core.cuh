@@ -396,19 +396,31 @@ struct SaResult {
     int v;               // class 3: read position of the exact occurrence
 };
 
+#ifndef ATR_SA_PAIR_TABLE
+#define ATR_SA_PAIR_TABLE 1          // measured on B200: pair table 0.856 ms, single-base table 0.891 ms per 10 M reads
+#endif
 // eight columns (one packed word) of the Shift-And automaton; G = columns per hit-accumulation group (see sa_scan)
 template <int G>
-ATR_HD void sa_word(uint32_t w, unsigned& St, unsigned S0, unsigned E, const unsigned long long* __restrict__ sa_pair,
-                    int j, int& hmin, int& hmax) {
+ATR_HD void sa_word(uint32_t w, unsigned& St, unsigned S0, unsigned E, const unsigned* __restrict__ sa_peq,
+                    const unsigned long long* __restrict__ sa_pair, int j, int& hmin, int& hmax) {
 #pragma unroll
     for (int g = 0; g < 8; g += G) {
         unsigned H = 0;
 #pragma unroll
         for (int t = g; t < g + G; t += 2) {
+#if ATR_SA_PAIR_TABLE
             const unsigned long long pr = sa_pair[(w >> (4 * t)) & 255u];
-            St = ((St << 1) | S0) & (unsigned)pr;
+            const unsigned p0 = (unsigned)pr, p1 = (unsigned)(pr >> 32);
+#else
+            // Alternative kept for the record: 16 entries x 4 bytes sit in 16 different banks, so every load is one
+            // wavefront, whereas the pair table's random accesses conflict (7 wavefronts per load measured, the
+            // shared-memory pipe busy for 64 % of the kernel). It still loses: the kernel is bound by instruction
+            // issue, and this form needs one more index extraction per column.
+            const unsigned p0 = sa_peq[(w >> (4 * t)) & 15u], p1 = sa_peq[(w >> (4 * t + 4)) & 15u];
+#endif
+            St = ((St << 1) | S0) & p0;
             H |= (St & E) >> (t - g);
-            St = ((St << 1) | S0) & (unsigned)(pr >> 32);
+            St = ((St << 1) | S0) & p1;
             H |= (St & E) >> (t + 1 - g);
         }
         if (H) { hmin = atr_min(hmin, j + g - atr_msb(H)); hmax = atr_max(hmax, j + g - atr_ctz(H)); }
@@ -437,9 +449,9 @@ ATR_HD void sa_scan(const AdapterK1a& ad, const unsigned* __restrict__ sa_peq, c
     // one test and one msb / ctz per group instead of one per column (the hits sit in a few lanes of a warp, so
     // every instruction spent on them runs almost empty). G = 8 needs every piece to end in row >= 8 (bit >= 7).
     if (ad.sa_end & 0x7Fu) {
-        while (pos + 8 <= pend) { sa_word<4>(codes[pos >> 3], St, S0, E, sa_pair, j, hmin, hmax); j += 8; pos += 8; }
+        while (pos + 8 <= pend) { sa_word<4>(codes[pos >> 3], St, S0, E, sa_peq, sa_pair, j, hmin, hmax); j += 8; pos += 8; }
     } else {
-        while (pos + 8 <= pend) { sa_word<8>(codes[pos >> 3], St, S0, E, sa_pair, j, hmin, hmax); j += 8; pos += 8; }
+        while (pos + 8 <= pend) { sa_word<8>(codes[pos >> 3], St, S0, E, sa_peq, sa_pair, j, hmin, hmax); j += 8; pos += 8; }
     }
     if (pos < pend) {
         const uint32_t w = codes[pos >> 3];
