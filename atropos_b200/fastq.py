@@ -192,6 +192,66 @@ class FastqTrimmer(object):
         return out[:nout.value], stats, int(consumed.value)
 
 
+def _stream_blocks(fh, block_bytes):
+    while True:
+        block = fh.read(block_bytes)
+        yield block
+        if not block:
+            return
+
+
+def trim_file(trimmer, src, dst, block_bytes=1 << 28):
+    """Stream a FASTQ file through a FastqTrimmer block by block: the partial last record of a block is carried
+    into the next one (`consumed`). src / dst: paths or binary file objects. Returns the accumulated TrimStats."""
+    fin = open(src, "rb") if isinstance(src, (str, bytes)) else src
+    fout = open(dst, "wb") if isinstance(dst, (str, bytes)) else dst
+    try:
+        stats, carry = trimmer.new_stats(), b""
+        for block in _stream_blocks(fin, block_bytes):
+            text = carry + block
+            out, stats, consumed = trimmer.trim(text, final=not block, stats=stats)
+            fout.write(out.tobytes())
+            carry = text[consumed:]
+        return stats
+    finally:
+        if fin is not src:
+            fin.close()
+        if fout is not dst:
+            fout.close()
+
+
+def trim_file_pair(trimmer, src1, src2, dst1, dst2, block_bytes=1 << 27):
+    """Paired-end twin of trim_file for a FastqPairTrimmer: the two inputs advance independently."""
+    opened = []
+
+    def _open(x, mode):
+        if isinstance(x, (str, bytes)):
+            fh = open(x, mode)
+            opened.append(fh)
+            return fh
+        return x
+
+    f1, f2, o1, o2 = _open(src1, "rb"), _open(src2, "rb"), _open(dst1, "wb"), _open(dst2, "wb")
+    try:
+        stats, c1, c2 = trimmer.new_stats(), b"", b""
+        eof1 = eof2 = False
+        while True:
+            b1 = b"" if eof1 else f1.read(block_bytes)
+            b2 = b"" if eof2 else f2.read(block_bytes)
+            eof1, eof2 = eof1 or not b1, eof2 or not b2
+            t1, t2 = c1 + b1, c2 + b2
+            final = eof1 and eof2
+            outs, stats, consumed = trimmer.trim(t1, t2, final=final, stats=stats)
+            o1.write(outs[0].tobytes())
+            o2.write(outs[1].tobytes())
+            c1, c2 = t1[consumed[0]:], t2[consumed[1]:]
+            if final:
+                return stats
+    finally:
+        for fh in opened:
+            fh.close()
+
+
 class PairTrimStats(object):
     """InsertAdapterCutter.summarize() (commands/trim/modifiers.py:498-509): per read the adapter's statistics."""
 

@@ -144,3 +144,21 @@ def test_pe_200k_pairs_against_match_records():
         assert out.size == int((12 + 2 * k + 4).sum())
         seq_lens = np.array([len(x) for x in out.tobytes().split(b"\n")[1::4]], dtype=np.int64)
         assert np.array_equal(seq_lens, k)
+
+
+def test_file_streaming_helpers(tmp_path):
+    """fastq.trim_file / trim_file_pair: blocks far smaller than the files, partial records carried over"""
+    case = [c for c in CASES if c["label"] == "ops_quality_trimn_minlen"][0]
+    adapters = fastq_cases.adapters_of(case)
+    (tmp_path / "in.fq").write_bytes(case["text"].encode("latin-1"))
+    tr = fastq.FastqTrimmer(adapters, times=case["times"], **case["read_ops"])
+    stats = fastq.trim_file(tr, str(tmp_path / "in.fq"), str(tmp_path / "out.fq"), block_bytes=7001)
+    fastq_cases.check(case, (tmp_path / "out.fq").read_bytes(), stats, adapters)
+    pcase = [c for c in PE_CASES if c["label"] == "ops_trimn_minlen"][0]
+    a1, a2, ia = fastq_cases.pe_objects(pcase)
+    (tmp_path / "in1.fq").write_bytes(pcase["text1"].encode("latin-1"))
+    (tmp_path / "in2.fq").write_bytes(pcase["text2"].encode("latin-1"))
+    ptr = fastq.FastqPairTrimmer(a1, a2, ia, **pcase["read_ops"])
+    pstats = fastq.trim_file_pair(ptr, str(tmp_path / "in1.fq"), str(tmp_path / "in2.fq"), str(tmp_path / "o1.fq"),
+                                  str(tmp_path / "o2.fq"), block_bytes=9973)
+    fastq_cases.pe_check(pcase, ((tmp_path / "o1.fq").read_bytes(), (tmp_path / "o2.fq").read_bytes()), pstats)
