@@ -120,6 +120,9 @@ struct PackedPair {
     // and the first 16 or 32 bases are compared unconditionally (no per-word exit test, no shared-memory
     // traffic). A random overlap is almost surely over its bound after that; only real overlaps continue with
     // the word-by-word scan.
+#ifndef ATR_K2_INLINE_THR
+#define ATR_K2_INLINE_THR 18
+#endif
     template <class F>
     ATR_HD void scan(const InsertDev& d, int k, F&& emit) const {
         const int jsmall = m < 31 ? m : 31;
@@ -168,7 +171,17 @@ struct PackedPair {
                     cost += nib_mismatches(funnel_r(r2, r3, 4u * b) ^ q2) + nib_mismatches(funnel_r(r3, r4, 4u * b) ^ q3);
                     wdone = 4;
                 }
-                if ((int)cost <= bound && j >= d.min_insert_overlap) {
+                if ((int)cost <= bound && j >= d.min_insert_overlap && tj >= ATR_K2_INLINE_THR) {
+                    // A bound this high cannot be exceeded within 32 bases often enough (random bases mismatch at
+                    // 3/4: 24 +- 2.4 of 32), so nearly every lane would park nearly every overlap: finish it right
+                    // here, word by word with the exit test -- all lanes are in the same situation, so this does
+                    // not diverge. A real candidate is emitted after the parked (shorter) ones, in order.
+                    const int full = overlap_cost(j, bound, (int)wdone, cost);
+                    if (full <= bound) {
+                        go_on = flush();
+                        if (go_on) go_on = emit(j, full);
+                    }
+                } else if ((int)cost <= bound && j >= d.min_insert_overlap) {
                     if (npend == 4) go_on = flush();   // full (low-complexity read): finish the parked ones in order
                     if (go_on) {
                         const unsigned e = ((unsigned)j << 16) | (wdone << 8) | cost;

@@ -3,6 +3,7 @@ and the committed golden vectors from the real reference. Bar: BIT-EXACT on ever
 (astart, astop, rstart, rstop, matches, errors, None-ness, winning adapter). Needs a GPU."""
 import numpy as np
 import pytest
+from atropos_b200 import _abi as _abi_mod
 
 import fuzzgen
 import golden_util
@@ -277,6 +278,43 @@ def test_insert_config_pe150():
             assert got[0] == exp[0] and (got[1].fields() if got[1] else None) == exp[1] and \
                 (got[2].fields() if got[2] else None) == exp[2], (i, got, exp)
     assert nm > n // 4
+
+
+def test_insert_config_pe300():
+    """BASELINE config 5 shape: 2x300 synthetic pairs, error rate 0.15 (k = 45), vs the Python oracle; also the
+    per-read fallback adapters of insert mode (max_rmp 1e-6, min_overlap 1, indel cost 3) at 300 nt"""
+    from atropos_b200 import synth
+    from atropos_b200.adapters import Adapter, BACK
+    from atropos_b200.align import InsertAligner
+    from atropos_b200.util import RandomMatchProbability
+    n, L = 4000, 300
+    r1, r2 = synth.synth_pe(n, L, seed=synth.seed_for(5), device="cpu", sub=0.02)
+    r1, r2 = r1.numpy(), r2.numpy()
+    offs = np.arange(n + 1, dtype=np.int64) * L
+    kw = dict(max_insert_mismatch_frac=0.15, max_adapter_mismatch_frac=0.15)
+    res = InsertAligner(T1, T2, **kw).match_insert_batch((r1.reshape(-1), offs), (r2.reshape(-1), offs))
+    orc = oracle.OracleInsertAligner(T1, T2, **kw)
+    nm = 0
+    for i in range(n):
+        exp = orc.match_insert(bytes(r1[i]).decode(), bytes(r2[i]).decode())
+        got = InsertAligner.result_from_record(res[i])
+        if exp is None:
+            assert got is None, i
+        else:
+            nm += 1
+            assert got[0] == exp[0] and (got[1].fields() if got[1] else None) == exp[1] and \
+                (got[2].fields() if got[2] else None) == exp[2], (i, got, exp)
+    assert nm > n // 4
+    rmp, rmp_o = RandomMatchProbability(), oracle.RandomMatchProbability()
+    akw = dict(max_error_rate=0.15, min_overlap=1, indel_cost=3, max_rmp=1e-6)
+    mine = Adapter(T2, BACK, match_probability=rmp, **akw)
+    o_ad = oracle.OracleAdapter(T2, oracle.BACK, match_probability=rmp_o, **akw)
+    rec = mine.match_to_batch((r2.reshape(-1), offs))
+    for i in range(0, n, 3):
+        exp = o_ad.match_to(bytes(r2[i]).decode())
+        got = None if rec[i]["status"] == _abi_mod.ATR_ST_NONE else tuple(int(rec[i][k]) for k in
+                                                                         ("astart", "astop", "rstart", "rstop", "matches", "errors"))
+        assert got == (None if exp is None else tuple(exp[:6])), i
 
 
 def test_insert_fuzz_modes_and_escapes():

@@ -263,3 +263,36 @@ def test_anchored_piece_filter(where):
     # SUFFIX with unit indel cost is taken by the funnel (fused_ok); only its indel_cost 3 third comes here
     assert took > (2000 if where == PREFIX else 800) and found > 500
     assert passed < 0.85 * took           # the filter is selective
+
+
+def test_match_insert_long_reads_high_rate():
+    """BASELINE config 5 shape (2x300, rate 0.15 => bounds up to 45): the overlaps whose bound a 32-base look cannot
+    exceed are finished inline instead of being parked (ATR_K2_INLINE_THR); candidates must still come out in order"""
+    from atropos_b200 import synth
+    kw = dict(max_insert_mismatch_frac=0.15, max_adapter_mismatch_frac=0.15)
+    L = 300
+    d, keep = InsertAligner(T1, T2, **kw).descriptor(L)
+    orc = oracle.OracleInsertAligner(T1, T2, **kw)
+    r1, r2 = synth.synth_pe(260, L, seed=77, device="cpu", sub=0.03)
+    r1, r2 = r1.numpy(), r2.numpy()
+    rng = np.random.default_rng(78)
+    matched = 0
+    for i in range(260):
+        a, b = bytes(r1[i]).decode(), bytes(r2[i]).decode()
+        if i % 5 == 0:                   # low-complexity mates: many candidates, the 100-candidate cap
+            a = ("AC" * 150)[:int(rng.integers(200, 301))]
+            b = ("GT" * 150)[:int(rng.integers(200, 301))]
+        elif i % 7 == 0:
+            a, b = a[:int(rng.integers(120, 301))], b[:int(rng.integers(120, 301))]
+        exp = orc.match_insert(a, b)
+        rec, used = hostsim.match_insert(d, a, b, 0)
+        assert used
+        st = int(rec["insert"]["status"])
+        if exp is None:
+            assert st == _abi.ATR_ST_NONE, i
+        else:
+            matched += 1
+            assert st == _abi.ATR_ST_MATCH and _tup(rec["insert"]) == exp[0], i
+            for e, g in ((exp[1], rec["match1"]), (exp[2], rec["match2"])):
+                assert (int(g["status"]) == _abi.ATR_ST_NONE) if e is None else (_tup(g) == e), i
+    assert matched > 60
