@@ -104,6 +104,7 @@ struct atr_adapterset {
 
 struct atr_insertset {
     atr_ctx* ctx = nullptr;
+    int kmax = 0;                    // largest error budget of the set: k_by_len[max_len]
     InsertDev dev;
     std::vector<void*> dev_allocs;
 };
@@ -285,7 +286,9 @@ int insert_on_stream(atr_ctx* ctx, cudaStream_t st, const atr_insertset* set,
                      const uint8_t* a1, const int64_t* o1, int64_t base1,
                      const uint8_t* a2, const int64_t* o2, int64_t base2, int64_t n, atr_insert_result* d_out) {
     if (n <= 0) return ATR_OK;
-    k_insert_packed<<<grid_for(n, ATR_K2_THREADS), ATR_K2_THREADS, 0, st>>>(set->dev, c1, w1, l1, c2, w2, l2, n, d_out);
+    // bounds that a 32-base look cannot exceed (rate x read length >= ATR_K2_INLINE_THR) take the other instantiation
+    if (set->kmax >= ATR_K2_INLINE_THR) k_insert_packed<true><<<grid_for(n, ATR_K2_THREADS), ATR_K2_THREADS, 0, st>>>(set->dev, c1, w1, l1, c2, w2, l2, n, d_out);
+    else k_insert_packed<false><<<grid_for(n, ATR_K2_THREADS), ATR_K2_THREADS, 0, st>>>(set->dev, c1, w1, l1, c2, w2, l2, n, d_out);
     LAUNCHED(ctx);
     if (a1 && o1 && a2 && o2) {
         const unsigned g = (unsigned)std::min<int64_t>((n + 127) / 128, 148 * 8);
@@ -582,6 +585,7 @@ int atr_insertset_create(atr_ctx* ctx, const atr_insert_desc* d, atr_insertset**
     atr_insertset* set = new (std::nothrow) atr_insertset();
     if (!set) return fail(ctx, ATR_E_NOMEM, "out of host memory");
     set->ctx = ctx;
+    set->kmax = h.k_by_len.empty() ? 0 : (int)h.k_by_len.back();
     set->dev = h.dev;
     InsertDev& v = set->dev;
     rc = upload(ctx, set->dev_allocs, h.k_by_len.data(), h.k_by_len.size(), &v.k_by_len);

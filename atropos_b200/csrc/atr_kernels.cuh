@@ -123,6 +123,7 @@ __global__ void k_fill_none(atr_match* __restrict__ out, int64_t n) {
 // overlap needs dynamically indexed funnel shifts.
 // ---------------------------------------------------------------------------------------------
 #define ATR_K2_THREADS 64
+template <bool INLINE_HIGH>
 __global__ void __launch_bounds__(ATR_K2_THREADS) k_insert_packed(
         const __grid_constant__ InsertDev d,
         const uint32_t* __restrict__ codes1, const uint32_t* __restrict__ woff1, const uint16_t* __restrict__ len1,
@@ -137,7 +138,7 @@ __global__ void __launch_bounds__(ATR_K2_THREADS) k_insert_packed(
     const int m = n1 < n2 ? n1 : n2;
     atr_insert_result* o = out + r;
     bool routed = ((l1 | l2) & ATR_ESC_BIT) != 0 || m > ATR_K2_MAXLEN || !d.packed_ok;
-    PackedPair pp;
+    PackedPairT<INLINE_HIGH> pp;
     pp.R = sR + threadIdx.x; pp.Q = sQ + threadIdx.x; pp.stride = ATR_K2_THREADS;
     if (!routed) routed = packed_pair_setup(pp, codes1 + woff1[r], codes2 + woff2[r], m) == 0;
     if (routed) {                      // the byte-exact kernel (k_insert_bytes) picks these up

@@ -84,7 +84,13 @@ ATR_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, unsigned shift) {   // (hi:lo
 
 // Accessors give the pair's two sequences to the shared decision code.
 //   PackedPair: R/Q are per-thread word arrays with element w at [w * stride] (shared memory on the GPU)
-struct PackedPair {
+#ifndef ATR_K2_INLINE_THR
+#define ATR_K2_INLINE_THR 18
+#endif
+// INLINE_HIGH selects, at compile time, the scan that finishes high-bound overlaps inline (see scan_impl): the kernel
+// for insert sets whose bounds stay below ATR_K2_INLINE_THR keeps the leaner loop.
+template <bool INLINE_HIGH>
+struct PackedPairT {
     uint32_t* R;            // rc(seq2[:m]) packed, >= W+2 words, zero padded
     uint32_t* Q;            // seq1 packed (only the first m bases are looked at)
     const uint32_t* S2;     // forward read2 packed (for the overhang)
@@ -120,9 +126,6 @@ struct PackedPair {
     // and the first 16 or 32 bases are compared unconditionally (no per-word exit test, no shared-memory
     // traffic). A random overlap is almost surely over its bound after that; only real overlaps continue with
     // the word-by-word scan.
-#ifndef ATR_K2_INLINE_THR
-#define ATR_K2_INLINE_THR 18
-#endif
     template <class F>
     ATR_HD void scan(const InsertDev& d, int k, F&& emit) const {
         const int jsmall = m < 31 ? m : 31;
@@ -171,7 +174,7 @@ struct PackedPair {
                     cost += nib_mismatches(funnel_r(r2, r3, 4u * b) ^ q2) + nib_mismatches(funnel_r(r3, r4, 4u * b) ^ q3);
                     wdone = 4;
                 }
-                if ((int)cost <= bound && j >= d.min_insert_overlap && tj >= ATR_K2_INLINE_THR) {
+                if (INLINE_HIGH && (int)cost <= bound && j >= d.min_insert_overlap && tj >= ATR_K2_INLINE_THR) {
                     // A bound this high cannot be exceeded within 32 bases often enough (random bases mismatch at
                     // 3/4: 24 +- 2.4 of 32), so nearly every lane would park nearly every overlap: finish it right
                     // here, word by word with the exit test -- all lanes are in the same situation, so this does
@@ -201,6 +204,8 @@ struct PackedPair {
     ATR_HD const uint32_t* fwd1() const { return S1; }
     ATR_HD const uint32_t* fwd2() const { return S2; }
 };
+typedef PackedPairT<false> PackedPair;
+
 
 struct BytePair {
     const unsigned char* s1;   // read1 bytes
@@ -351,7 +356,8 @@ ATR_HD void insert_pair(const InsertDev& d, const P& pr, bool packed, int m, int
 
 // Build the packed operands of a pair. S1/S2: forward packed reads; m = min(len1, len2).
 // Returns 0 if read2[:m] contains code 0 ('X': reverse_complement raises KeyError) -> byte path decides.
-ATR_HD int packed_pair_setup(PackedPair& pp, const uint32_t* S1, const uint32_t* S2, int m) {
+template <bool IH>
+ATR_HD int packed_pair_setup(PackedPairT<IH>& pp, const uint32_t* S1, const uint32_t* S2, int m) {
     const int W = (m + 7) >> 3;
     const int st = pp.stride;
     int ok = 1;

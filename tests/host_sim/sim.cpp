@@ -84,11 +84,20 @@ int sim_match_insert(const atr_insert_desc* d, const unsigned char* r1, int len1
     std::vector<uint32_t> R(ATR_K2_MAXW + 2, 0), Q(ATR_K2_MAXW + 2, 0);
     std::vector<Cand> cand(ATR_MAX_CAND + 1);
     bool routed = esc || m > ATR_K2_MAXLEN || !v.packed_ok || route == 1;
-    PackedPair pp;
-    pp.R = R.data(); pp.Q = Q.data(); pp.stride = 1;
-    if (!routed) routed = packed_pair_setup(pp, c1.data(), c2.data(), m) == 0;
-    if (used_packed) *used_packed = !routed;
-    if (!routed) { insert_pair(v, pp, true, m, len1, len2, cand.data(), out); return 0; }
+    const bool high = !h.k_by_len.empty() && (int)h.k_by_len.back() >= ATR_K2_INLINE_THR;      // as the library picks the kernel
+    if (high) {
+        PackedPairT<true> pp;
+        pp.R = R.data(); pp.Q = Q.data(); pp.stride = 1;
+        if (!routed) routed = packed_pair_setup(pp, c1.data(), c2.data(), m) == 0;
+        if (used_packed) *used_packed = !routed;
+        if (!routed) { insert_pair(v, pp, true, m, len1, len2, cand.data(), out); return 0; }
+    } else {
+        PackedPairT<false> pp;
+        pp.R = R.data(); pp.Q = Q.data(); pp.stride = 1;
+        if (!routed) routed = packed_pair_setup(pp, c1.data(), c2.data(), m) == 0;
+        if (used_packed) *used_packed = !routed;
+        if (!routed) { insert_pair(v, pp, true, m, len1, len2, cand.data(), out); return 0; }
+    }
     BytePair bp;
     bp.s1 = r1; bp.s2 = r2; bp.comp = v.comp; bp.ov_tab = v.ov_tab; bp.m = m;
     for (int p = 0; p < m; p++) if (v.comp[r2[p]] == 0) {
