@@ -140,7 +140,12 @@ inline void fill_k1a(const HostAdapter& h, const AtrTables& tb, int index, int r
     const bool stop_q = h.desc.flags & ATR_STOP_WITHIN_SEQ2;
     // BACK / SUFFIX style (anchored start in the adapter), or FRONT / ANYWHERE style (free start in both, needs
     // stop_in_query so that the first DP column is column 0)
-    a.fused_ok = h.k1a_ok && h.desc.indel_cost == 1 && start_in_query && (!start_in_ref || stop_q) && !h.cmp_only && !h.need_find;
+    const bool funnel_shape = h.k1a_ok && start_in_query && (!start_in_ref || stop_q) && !h.cmp_only && !h.need_find;
+    a.fused_ok = funnel_shape && h.desc.indel_cost == 1;
+    // Dearer indels (insert mode's fallback adapters cost 3, --no-indels 100000): every accepted alignment is also one of
+    // at most k unit-cost edits, so the unit-cost filter stage is still a valid necessary condition (and its verbatim-
+    // occurrence shortcut is still the answer); only the DP itself has to price the indels -- the register DP does.
+    a.filter_only = funnel_shape && h.desc.indel_cost != 1;
     // an alignment that starts inside the adapter and ends at (m, j) covers at most j + k adapter rows, so its
     // cost is bounded by floor(min(m, j + k) * rate) and it needs j + k >= min_overlap rows
     for (int j = 0; j <= ATR_K1A_MAXM; j++) {
@@ -183,7 +188,7 @@ inline void fill_k1a(const HostAdapter& h, const AtrTables& tb, int index, int r
     a.sa_ok = 0; a.sa_rows = h.m < 32 ? h.m : 32; a.sa_start = 0; a.sa_end = 0; a.tail_gate_ok = 0; a.tail_mask = 0;
     const bool stop_in_query = h.desc.flags & ATR_STOP_WITHIN_SEQ2;
     const int pieces = h.k + 1;
-    if (a.fused_ok && !start_in_ref && stop_in_query && pieces <= a.sa_rows && a.sa_rows / pieces >= 6) {
+    if ((a.fused_ok || a.filter_only) && !start_in_ref && stop_in_query && pieces <= a.sa_rows && a.sa_rows / pieces >= 6) {
         a.sa_ok = 1;
         int row = 1;
         for (int pc = 0; pc < pieces; pc++) {

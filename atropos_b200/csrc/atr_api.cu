@@ -241,6 +241,36 @@ int locate_on_stream(atr_ctx* ctx, Slot& slot, const atr_adapterset* set,
                 if (!prof) { LAUNCHED(ctx); ctx->launches--; CU(cudaEventRecord(slot.ev_join, sw)); CU(cudaStreamWaitEvent(st, slot.ev_join, 0)); }
                 if (prof) { LAUNCHED(ctx); CU(cudaEventRecord(ctx->pev[3], st)); ctx->launches--; ctx->phases_valid = 1; }
             }
+            else if (p.filter_only && !p.anchor_ok && !ctx->disable_fused && n < (int64_t)0x7fffffff) {
+                // funnel shape, dearer indels: the funnel's filter kernel, then the register DP over all survivor lists
+                int rc = lists.ensure((size_t)n * 3 * sizeof(Survivor) + 64);
+                if (rc) return fail(ctx, rc, "out of device memory (survivor lists)");
+                int* counters = lists.as<int>();
+                Survivor* narrow = (Survivor*)(lists.as<char>() + 64);
+                Survivor* wide = narrow + n;
+                Survivor* refine = wide + n;
+                CU(cudaMemsetAsync(counters, 0, 4 * sizeof(int), st));
+                const unsigned g = grid_for(n, ATR_K1F_THREADS);
+                const unsigned gp = (unsigned)std::min<int64_t>((n + 127) / 128, 148 * 12);
+                const bool use_sa = p.sa_ok && !ctx->disable_sa;
+                if (use_sa) {
+                    if (h.and_mode) k_filter_sa<true><<<g, ATR_K1F_THREADS, 0, st>>>(p, d_codes, d_woff, d_len, d_win, n, d_out, narrow, wide, refine, counters);
+                    else k_filter_sa<false><<<g, ATR_K1F_THREADS, 0, st>>>(p, d_codes, d_woff, d_len, d_win, n, d_out, narrow, wide, refine, counters);
+                } else if (h.m <= 32) {
+                    if (h.and_mode) k_filter<unsigned int, true><<<g, ATR_K1F_THREADS, 0, st>>>(p, d_codes, d_woff, d_len, d_win, n, d_out, narrow, wide, counters);
+                    else k_filter<unsigned int, false><<<g, ATR_K1F_THREADS, 0, st>>>(p, d_codes, d_woff, d_len, d_win, n, d_out, narrow, wide, counters);
+                } else {
+                    if (h.and_mode) k_filter<unsigned long long, true><<<g, ATR_K1F_THREADS, 0, st>>>(p, d_codes, d_woff, d_len, d_win, n, d_out, narrow, wide, counters);
+                    else k_filter<unsigned long long, false><<<g, ATR_K1F_THREADS, 0, st>>>(p, d_codes, d_woff, d_len, d_win, n, d_out, narrow, wide, counters);
+                }
+                LAUNCHED(ctx);
+                Survivor* ls[3] = {narrow, wide, refine};
+                for (int li = 0; li < (use_sa ? 3 : 2); li++) {
+                    if (h.and_mode) k_anchor_dp<true><<<gp, 128, 0, st>>>(p, d_codes, d_woff, d_len, d_win, d_out, ls[li], counters + li);
+                    else k_anchor_dp<false><<<gp, 128, 0, st>>>(p, d_codes, d_woff, d_len, d_win, d_out, ls[li], counters + li);
+                    if (li + 1 < (use_sa ? 3 : 2)) LAUNCHED(ctx);
+                }
+            }
             else if (p.anchor_ok && !ctx->disable_fused && n < (int64_t)0x7fffffff) {
                 // anchored adapter with indels: fixed-position piece filter, register DP over the survivors only
                 int rc = lists.ensure((size_t)n * 3 * sizeof(Survivor) + 64);

@@ -973,3 +973,39 @@ ATR_HD void anchor_read(const AdapterK1a& ad, const uint32_t* __restrict__ codes
     b.ref_stop = ad.m; b.q_stop = n; b.cost = ad.m + n; b.origin = 0; b.matches = 0;
     finalize(ad, b, n, out);
 }
+
+// funnel shape with dearer indels, one read: the funnel's first stage as a filter, then the register DP (what
+// k_filter_sa / k_filter + k_anchor_dp over the survivor lists do)
+template <class WORD, bool AND_MODE>
+ATR_HD void icfilter_read(const AdapterK1a& ad, const uint32_t* __restrict__ codes, int lo, int n, atr_match* out, int* path = nullptr) {
+    Best b;
+    b.ref_stop = ad.m; b.q_stop = n; b.cost = ad.m + n; b.origin = 0; b.matches = 0;
+    bool have = false;
+    if (path) *path = 0;
+    if (ad.sa_ok) {
+        unsigned sa_peq[16], tail_peq[16];
+        const int mp = ad.sa_rows, sh32 = 32 - mp;
+        for (int c = 0; c < 16; c++) {
+            const unsigned low = (unsigned)(ad.peq[c] & (mp >= 32 ? 0xFFFFFFFFull : ((1ull << mp) - 1)));
+            sa_peq[c] = low;
+            tail_peq[c] = (sh32 ? (low << sh32) | ((1u << sh32) - 1u) : low);
+        }
+        SaResult sr;
+        sa_filter(ad, sa_peq, tail_peq, codes, lo, n, sr);
+        if (sr.cls == 3) {
+            b.matches = ad.m; b.cost = 0; b.origin = sr.v; b.ref_stop = ad.m; b.q_stop = sr.v + ad.m;
+            if (path) *path = 5;
+            finalize(ad, b, n, out);
+            return;
+        }
+        have = sr.cls != 0;
+    } else {
+        const int WB = (int)(8 * sizeof(WORD)), sh = WB - ad.m;
+        WORD peq[16];
+        for (int c = 0; c < 16; c++) peq[c] = (WORD)(((WORD)ad.peq[c] << sh) | (sh ? (((WORD)1 << sh) - 1) : 0));
+        FilterHit hit;
+        have = myers_filter<WORD>(ad, peq, codes, lo, n, hit);
+    }
+    if (have) { if (path) *path = 1; k1a_read<AND_MODE>(ad, codes, lo, n, out); return; }
+    finalize(ad, b, n, out);
+}

@@ -44,6 +44,12 @@ int sim_locate(const atr_adapter_desc* d, int adapter_index, int reduce, const u
             else { if (h.m <= 32) k1f_read<unsigned int, false>(a, codes.data(), lo, n, out, &path); else k1f_read<unsigned long long, false>(a, codes.data(), lo, n, out, &path); }
             if (used_k1a) *used_k1a = 2 + path;       // 2 filtered out, 3 banded K1d, 4 windowed K1a
         }
+        else if (a.filter_only && !a.anchor_ok && route != 2) {   // funnel shape, dearer indels: filter stage, then the register DP
+            int path = 0;
+            if (h.and_mode) { if (h.m <= 32) icfilter_read<unsigned int, true>(a, codes.data(), lo, n, out, &path); else icfilter_read<unsigned long long, true>(a, codes.data(), lo, n, out, &path); }
+            else { if (h.m <= 32) icfilter_read<unsigned int, false>(a, codes.data(), lo, n, out, &path); else icfilter_read<unsigned long long, false>(a, codes.data(), lo, n, out, &path); }
+            if (used_k1a) *used_k1a = 30 + path;       // 30 filtered out, 31 register DP, 35 verbatim shortcut
+        }
         else if (a.anchor_ok && route != 2) {          // anchored adapter: piece filter, then the register DP
             if (used_k1a) *used_k1a = 20 + (anchor_filter(a, codes.data(), lo, n) ? 1 : 0);
             if (h.and_mode) anchor_read<true>(a, codes.data(), lo, n, out); else anchor_read<false>(a, codes.data(), lo, n, out);

@@ -296,3 +296,28 @@ def test_match_insert_long_reads_high_rate():
             for e, g in ((exp[1], rec["match1"]), (exp[2], rec["match2"])):
                 assert (int(g["status"]) == _abi.ATR_ST_NONE) if e is None else (_tup(g) == e), i
     assert matched > 60
+
+
+@pytest.mark.parametrize("where", [BACK, FRONT, ANYWHERE])
+def test_filter_only_funnel_for_dearer_indels(where):
+    """indel cost 3 (insert mode's fallback adapters) and 100000 (--no-indels): the funnel's unit-cost filter stage
+    in front of the register DP -- same answers as the oracle, most adapter-free reads never reach the DP"""
+    rng = np.random.default_rng(600 + where)
+    took = dp = found = 0
+    for _ in range(300):
+        m = int(rng.integers(8, 62))
+        seq = fuzzgen.rand_seq(rng, m, "ACGT")
+        rate = float(rng.choice([0.0, 0.1, 0.15, 0.2]))
+        ic = int(rng.choice([3, 3, 100000]))
+        mo = int(rng.choice([1, 3, 5]))
+        d, keep = _abi.make_adapter_desc(seq, rate, where, False, False, mo, ic)
+        for _ in range(8):
+            read = fuzzgen.read_with_adapter(rng, seq, int(rng.integers(0, 160)), n_rate=0.01)
+            exp = oracle.locate(seq, read, rate, where, False, False, mo, ic)
+            got, used, _ = hostsim.locate(read, d)
+            assert got == exp, (seq, rate, ic, mo, read)
+            took += used >= 30
+            dp += used == 31
+            found += exp is not None
+    assert took > 2000 and found > 400
+    assert dp < 0.9 * took
