@@ -76,6 +76,22 @@ int fq_scan_i64(atr_ctx* ctx, cudaStream_t st, DevBuf& tmp, const long long* in,
     return ATR_OK;
 }
 
+// 4-bit packing from the chunk text through the record table (the twin of pack_on_stream)
+int fq_pack_on_stream(atr_ctx* ctx, cudaStream_t st, DevBuf& counts, DevBuf& scan_tmp, const unsigned char* d_text,
+                      const FqRec* d_recs, int64_t n, int fold_case, uint32_t* d_codes, uint32_t* d_woff, uint16_t* d_len) {
+    if (n <= 0) return ATR_OK;
+    int rc = counts.ensure((size_t)(n + 1) * sizeof(uint32_t));
+    if (rc) return fail(ctx, rc, "out of device memory (pack counts)");
+    CU(cudaMemsetAsync(counts.p, 0, (size_t)(n + 1) * sizeof(uint32_t), st));
+    k_fq_word_counts<<<grid_for(n, 256), 256, 0, st>>>(d_recs, n, counts.as<uint32_t>());
+    LAUNCHED(ctx);
+    rc = fq_scan_u32(ctx, st, scan_tmp, counts.as<unsigned>(), d_woff, (int)(n + 1));
+    if (rc) return rc;
+    k_fq_pack<<<grid_for(n * 32, 256), 256, 0, st>>>(d_text, d_recs, n, fold_case, ctx->d_tables, d_woff, d_codes, d_len);
+    LAUNCHED(ctx);
+    return ATR_OK;
+}
+
 // newline index of the chunk (re-runnable: a too small index buffer is grown and the pass repeated)
 int fq_index(atr_ctx* ctx, Slot& s, int side, const FqChunk& c, int final_text, int unterminated) {
     cudaStream_t st = s.stream;
@@ -158,13 +174,15 @@ int fq_back(atr_ctx* ctx, Slot& s, const FqChunk& c, const atr_adapterset* set, 
         CU(cudaMemsetAsync(f.flags.p, 0, (size_t)n, st));
         rc = fq_scan_i64(ctx, st, s.scan_tmp, f.len64.as<long long>(), (long long*)s.offsets.p, n + 1);
         if (rc) return rc;
-        k_fq_gather<<<grid_for(n * 32, 256), 256, 0, st>>>(d_text, f.recs.as<FqRec>(), (const long long*)s.offsets.p, n,
-                                                           s.ascii.as<unsigned char>());
-        LAUNCHED(ctx);
         // the reads are upper-cased for matching only (adapters/__init__.py:349): fold_case = 1
-        rc = pack_on_stream(ctx, st, s.counts, s.scan_tmp, s.ascii.as<uint8_t>(), s.offsets.as<int64_t>(), 0, n, 1,
-                            s.codes.as<uint32_t>(), s.woff.as<uint32_t>(), s.len.as<uint16_t>());
+        rc = fq_pack_on_stream(ctx, st, s.counts, s.scan_tmp, d_text, f.recs.as<FqRec>(), n, 1, s.codes.as<uint32_t>(),
+                               s.woff.as<uint32_t>(), s.len.as<uint16_t>());
         if (rc) return rc;
+        int gather_all = 0;
+        for (const atr::HostAdapter& h : set->host) if (!h.k1a_ok) gather_all = 1;
+        k_fq_gather<<<grid_for(n * 32, 256), 256, 0, st>>>(d_text, f.recs.as<FqRec>(), (const long long*)s.offsets.p, s.len.as<uint16_t>(), n,
+                                                           gather_all, s.ascii.as<unsigned char>());
+        LAUNCHED(ctx);
         k_fq_init_win<<<grid_for(n, 256), 256, 0, st>>>(f.recs.as<FqRec>(), n, f.fwin.as<uint16_t>(), &d_ctr->records);
         LAUNCHED(ctx);
         for (int round = 0; round < o->times; round++) {
@@ -460,14 +478,14 @@ int pe_back(atr_ctx* ctx, Slot& s, const PeStep& P, const atr_insertset* iset, c
         LAUNCHED(ctx);
         rc = fq_scan_i64(ctx, st, s.scan_tmp, q.len64.as<long long>(), (long long*)b.offsets.p, n + 1);
         if (rc) return rc;
-        k_fq_gather<<<grid_for(n * 32, 256), 256, 0, st>>>(q.text.as<unsigned char>(), q.recs.as<FqRec>(), (const long long*)b.offsets.p, n,
-                                                           b.ascii.as<unsigned char>());
-        LAUNCHED(ctx);
         // match_insert compares the reads as they are (no upper-casing, align/__init__.py:250-267): fold_case = 0;
         // lower-case reads come out "escaped" and take the byte-exact kernels in both stages
-        rc = pack_on_stream(ctx, st, b.counts, s.scan_tmp, b.ascii.as<uint8_t>(), b.offsets.as<int64_t>(), 0, n, 0,
-                            b.codes.as<uint32_t>(), b.woff.as<uint32_t>(), b.len.as<uint16_t>());
+        rc = fq_pack_on_stream(ctx, st, b.counts, s.scan_tmp, q.text.as<unsigned char>(), q.recs.as<FqRec>(), n, 0,
+                               b.codes.as<uint32_t>(), b.woff.as<uint32_t>(), b.len.as<uint16_t>());
         if (rc) return rc;
+        k_fq_gather<<<grid_for(n * 32, 256), 256, 0, st>>>(q.text.as<unsigned char>(), q.recs.as<FqRec>(), (const long long*)b.offsets.p,
+                                                           b.len.as<uint16_t>(), n, 1, b.ascii.as<unsigned char>());
+        LAUNCHED(ctx);
         k_fq_init_win<<<grid_for(n, 256), 256, 0, st>>>(q.recs.as<FqRec>(), n, q.fwin.as<uint16_t>(), f == 0 ? &d_ctr->records : nullptr);
         LAUNCHED(ctx);
     }

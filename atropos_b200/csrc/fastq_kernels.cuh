@@ -160,12 +160,42 @@ __global__ void __launch_bounds__(256) k_fq_frame(const unsigned char* __restric
     }
 }
 
-// sequence lines -> contiguous ASCII batch (the layout the packer and the byte-exact kernel take): warp per record
-__global__ void __launch_bounds__(256) k_fq_gather(const unsigned char* __restrict__ text, const FqRec* __restrict__ recs,
-                                                   const long long* __restrict__ offsets, long long n_rec,
-                                                   unsigned char* __restrict__ ascii) {
+// 4-bit packing straight from the text (the record table says where each read is): one warp per record, one lane per
+// output word, like k_pack. The contiguous ASCII batch is no longer needed for this.
+__global__ void __launch_bounds__(256) k_fq_pack(const unsigned char* __restrict__ text, const FqRec* __restrict__ recs, long long n_rec,
+                                                 int fold_case, const AtrTables* __restrict__ tables, const uint32_t* __restrict__ woff,
+                                                 uint32_t* __restrict__ codes, uint16_t* __restrict__ len_out) {
+    __shared__ unsigned char s_iupac[256];
+    s_iupac[threadIdx.x] = tables->iupac[threadIdx.x];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
     const long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (r >= n_rec) return;
+    const FqRec R = recs[r];
+    const int len = R.seq_len, nwords = (len + 7) >> 3;
+    const uint32_t w0 = woff[r];
+    int esc = 0;
+    for (int w = lane; w < nwords; w += 32) codes[w0 + w] = atr::pack_word(text + R.seq_b, len, w, fold_case, s_iupac, &esc);
+    esc = __any_sync(0xffffffffu, esc);
+    if (lane == 0) len_out[r] = (uint16_t)(len | (esc ? ATR_ESC_BIT : 0));
+}
+
+__global__ void __launch_bounds__(256) k_fq_word_counts(const FqRec* __restrict__ recs, long long n, uint32_t* __restrict__ counts) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n) counts[r] = ((uint32_t)recs[r].seq_len + 7u) >> 3;
+}
+
+// The byte-exact kernels (k_locate_gen, k_insert_bytes) address reads through a contiguous ASCII batch + offsets; they
+// single-end they only ever touch ESCAPED reads (a byte outside the packed alphabet) and reads longer than the register
+// kernels take, so only those are copied there (all = 0). all = 1 copies every read: adapter sets with an adapter that
+// always takes the byte-exact kernel, and the paired-end path (a pair goes to k_insert_bytes as a whole when either
+// mate is escaped, or holds an X). Warp per record.
+__global__ void __launch_bounds__(256) k_fq_gather(const unsigned char* __restrict__ text, const FqRec* __restrict__ recs,
+                                                   const long long* __restrict__ offsets, const uint16_t* __restrict__ len16,
+                                                   long long n_rec, int all, unsigned char* __restrict__ ascii) {
+    const long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (r >= n_rec) return;
+    if (!all && !(len16[r] & ATR_ESC_BIT) && (len16[r] & ATR_LEN_MASK) <= ATR_K1A_MAXN) return;
     const int lane = threadIdx.x & 31;
     const FqRec R = recs[r];
     const unsigned char* src = text + R.seq_b;
@@ -261,7 +291,27 @@ __global__ void __launch_bounds__(256) k_fq_outlen(const FqRec* __restrict__ rec
     if ((threadIdx.x & 31) == 0 && bp) atomicAdd(bp_out, bp);
 }
 
-// formatted records: warp per record, lanes stride the output bytes (coalesced stores)
+// Warp-cooperative copy of `len` bytes between arbitrarily aligned addresses: byte stores up to the destination's
+// 4-byte boundary, then one aligned 32-bit store per lane built from two aligned source words (funnel shift), then the
+// tail. Reads up to 3 bytes past src + len inside the same (padded) buffer.
+__device__ __forceinline__ void fq_warp_copy(unsigned char* __restrict__ dst, const unsigned char* __restrict__ src, int len, int lane) {
+    int head = (int)((4u - (unsigned)(reinterpret_cast<uintptr_t>(dst) & 3u)) & 3u);
+    if (head > len) head = len;
+    if (lane < head) dst[lane] = src[lane];
+    const int nwords = (len - head) >> 2;
+    const unsigned char* s0 = src + head;
+    const unsigned sh = (unsigned)(reinterpret_cast<uintptr_t>(s0) & 3u) * 8u;
+    const uint32_t* sw = reinterpret_cast<const uint32_t*>(s0 - (sh >> 3));
+    uint32_t* dw = reinterpret_cast<uint32_t*>(dst + head);
+    for (int t = lane; t < nwords; t += 32) {
+        const uint32_t a = sw[t];
+        dw[t] = sh ? __funnelshift_r(a, sw[t + 1], sh) : a;
+    }
+    const int done = head + 4 * nwords;
+    if (lane < len - done) dst[done + lane] = src[done + lane];
+}
+
+// formatted records: warp per record, '@name' / sequence / '+[name]' / qualities as four word-wise copies
 __global__ void __launch_bounds__(256) k_fq_format(const unsigned char* __restrict__ text, const FqRec* __restrict__ recs,
                                                    const uint16_t* __restrict__ fwin, const long long* __restrict__ out_off,
                                                    long long n_rec, unsigned char* __restrict__ out, FqInfo* __restrict__ info) {
@@ -272,7 +322,19 @@ __global__ void __launch_bounds__(256) k_fq_format(const unsigned char* __restri
     const int lo = fwin[2 * r], hi = fwin[2 * r + 1];
     const uint32_t total = lo <= hi ? fq_out_len(R, lo, hi) : 0u;
     unsigned char* dst = out + out_off[r];
-    for (uint32_t i = lane; i < total; i += 32) dst[i] = fq_out_byte(text, R, lo, hi, i);
+    if (total) {
+        const int w = hi - lo, H = R.hdr_len;
+        const int P = R.name2 ? H : 1;
+        fq_warp_copy(dst, text + R.hdr_b, H, lane);
+        fq_warp_copy(dst + H + 1, text + R.seq_b + lo, w, lane);
+        if (P > 1) fq_warp_copy(dst + H + 1 + w + 2, text + R.hdr_b + 1, P - 1, lane);
+        fq_warp_copy(dst + H + 1 + w + 1 + P + 1, text + R.qual_b + lo, w, lane);
+        if (lane == 0) dst[H] = '\n';
+        if (lane == 1) dst[H + 1 + w] = '\n';
+        if (lane == 2) dst[H + 1 + w + 1] = '+';
+        if (lane == 3) dst[H + 1 + w + 1 + P] = '\n';
+        if (lane == 4) dst[total - 1] = '\n';
+    }
     if (r == n_rec - 1 && lane == 0) info->out_bytes = (unsigned long long)(out_off[r] + total);
 }
 
