@@ -52,7 +52,7 @@ class AtrReadOps(C.Structure):
     _fields_ = [("cut_front", C.c_int32 * 2), ("cut_back", C.c_int32 * 2), ("quality_front", C.c_int32),
                 ("quality_back", C.c_int32), ("quality_base", C.c_int32), ("trim_n", C.c_int32),
                 ("minimum_length", C.c_int32), ("maximum_length", C.c_int32), ("discard_trimmed", C.c_int32),
-                ("discard_untrimmed", C.c_int32), ("max_n", C.c_double)]
+                ("discard_untrimmed", C.c_int32), ("legacy_first", C.c_int32), ("pad", C.c_int32), ("max_n", C.c_double)]
 
 
 class AtrReadOpsStats(C.Structure):
@@ -65,7 +65,7 @@ OPS_STAT_KEYS = ("too_short", "too_long", "too_many_n", "discarded_trimmed", "di
 
 
 def make_read_ops(cut=(), cut2=(), quality_cutoff=None, quality_base=33, trim_n=False, minimum_length=None,
-                  maximum_length=None, max_n=None, discard_trimmed=False, discard_untrimmed=False):
+                  maximum_length=None, max_n=None, discard_trimmed=False, discard_untrimmed=False, legacy_first=False):
     """The `trim` command's options (trim/cli.py) -> atr_read_ops. cut / cut2: the -u / -U values (lists of ints);
     quality_cutoff: -q as the command normalises it, [back] or [front, back] (trim/cli.py:750-754)."""
     o = AtrReadOps()
@@ -87,6 +87,8 @@ def make_read_ops(cut=(), cut2=(), quality_cutoff=None, quality_base=33, trim_n=
     o.maximum_length = int(maximum_length) if maximum_length is not None else -1
     o.max_n = float(max_n) if max_n is not None else -1.0
     o.discard_trimmed, o.discard_untrimmed = int(bool(discard_trimmed)), int(bool(discard_untrimmed))
+    # paired-end legacy mode (trim/cli.py:629-645): nothing on the command line touches read 2 -> filters see read 1 only
+    o.legacy_first = int(bool(legacy_first))
     return o
 
 
@@ -103,14 +105,15 @@ class AtrTrimStats(C.Structure):
 
 class AtrTrimPeOpts(C.Structure):
     _fields_ = [("symmetric", C.c_int32), ("min_insert_overlap", C.c_int32), ("max_len", C.c_int32),
-                ("max_errors", C.c_int32), ("final_chunk", C.c_int32), ("pad", C.c_int32), ("chunk_bytes", C.c_int64),
+                ("max_errors", C.c_int32), ("final_chunk", C.c_int32), ("times", C.c_int32), ("chunk_bytes", C.c_int64),
                 ("ops", AtrReadOps)]
 
 
 class AtrTrimPeStats(C.Structure):
     _fields_ = [("records", C.c_int64), ("insert_matches", C.c_int64), ("with_adapters", C.c_int64 * 2),
                 ("bp_in", C.c_int64 * 2), ("bp_out", C.c_int64 * 2), ("overflow", C.c_int64),
-                ("errors_back", C.c_void_p * 2), ("adjacent_bases", C.c_void_p * 2), ("ops", AtrReadOpsStats)]
+                ("errors_back", C.c_void_p * 2), ("adjacent_bases", C.c_void_p * 2), ("errors_front", C.c_void_p * 2),
+                ("ops", AtrReadOpsStats)]
 
 
 def make_adapter_desc(sequence, max_error_rate, flags, wildcard_ref=False, wildcard_query=False, min_overlap=1,

@@ -304,11 +304,12 @@ extern "C" int atr_trim_fastq_host(atr_ctx* ctx, const atr_adapterset* set, cons
         CU(cudaStreamSynchronize(s.stream));
         t_wait_front += now() - tw0;
         if (f.hinfo->nl_overflow) {                   // more lines than the index was sized for: grow, redo the index
+            // (an error leaves the loop instead of returning: copies into the caller's buffers may still be in flight)
             rc = f.nl.ensure((size_t)(f.hinfo->n_nl + 16) * sizeof(uint32_t));
-            if (rc) return fail(ctx, rc, "out of device memory (newline index)");
+            if (rc) { result = fail(ctx, rc, "out of device memory (newline index)"); break; }
             flags_of(cur, ft, ut);
             rc = fq_index(ctx, s, 0, cur, ft, ut);
-            if (rc) return rc;
+            if (rc) { result = rc; break; }
             CU(cudaStreamSynchronize(s.stream));
         }
         const FqInfo hi = *f.hinfo;
@@ -409,15 +410,23 @@ struct PeStep {
     int64_t n = 0;
 };
 
-struct PeLayout { size_t H, o_ctr, o_hist[2], o_adj[2], o_ops, total; };
+// statistics block: pair counters | per read: AdapterCutter counters, back / front histograms, adjacent bases, front flags
+struct PeLayout { size_t H, nA[2], o_ctr, o_side[2], o_hist[2], o_front[2], o_adj[2], o_flags[2], o_ops, total; };
 
-PeLayout pe_layout(int max_len, int max_errors) {
+PeLayout pe_layout(int max_len, int max_errors, size_t nA0, size_t nA1) {
     PeLayout L;
     L.H = (size_t)(max_len + 1) * (size_t)(max_errors + 1);
+    L.nA[0] = nA0 ? nA0 : 1; L.nA[1] = nA1 ? nA1 : 1;
     L.o_ctr = 0;
-    L.o_hist[0] = 128; L.o_hist[1] = L.o_hist[0] + L.H * 8;
-    L.o_adj[0] = L.o_hist[1] + L.H * 8; L.o_adj[1] = L.o_adj[0] + 64;
-    L.o_ops = L.o_adj[1] + 64;
+    size_t o = 128;
+    for (int f = 0; f < 2; f++) {
+        L.o_side[f] = o; o += 64;
+        L.o_hist[f] = o; o += L.nA[f] * L.H * 8;
+        L.o_front[f] = o; o += L.nA[f] * L.H * 8;
+        L.o_adj[f] = o; o += ((L.nA[f] * 5 * 8 + 63) & ~(size_t)63);
+        L.o_flags[f] = o; o += ((L.nA[f] + 63) & ~(size_t)63);
+    }
+    L.o_ops = o;
     L.total = L.o_ops + ((sizeof(FqOpsCounters) + 15) & ~(size_t)15);
     return L;
 }
@@ -454,10 +463,11 @@ int pe_back(atr_ctx* ctx, Slot& s, const PeStep& P, const atr_insertset* iset, c
         if (!rc) rc = b.win.ensure((size_t)(n + 1) * 2 * sizeof(uint16_t));
         if (!rc) rc = q.fwin.ensure((size_t)(n + 1) * 2 * sizeof(uint16_t));
         if (!rc) rc = q.outtext.ensure((size_t)len + 64);
+        if (!rc) rc = q.flags.ensure((size_t)n + 16);
         if (rc) return fail(ctx, rc, "out of device memory (paired FASTQ records)");
         if (q.d2h_pending) { CU(cudaStreamWaitEvent(st, q.ev_d2h, 0)); q.d2h_pending = 0; }
     }
-    int rc = s.ins_out.ensure((size_t)(n + 1) * sizeof(atr_insert_result));
+    int rc = iset ? s.ins_out.ensure((size_t)(n + 1) * sizeof(atr_insert_result)) : ATR_OK;
     if (rc) return fail(ctx, rc, "out of device memory (insert results)");
     // frame + validate both sides, then the names; every error goes to side 0's key
     for (int f = 0; f < 2; f++) {
@@ -480,7 +490,8 @@ int pe_back(atr_ctx* ctx, Slot& s, const PeStep& P, const atr_insertset* iset, c
         if (rc) return rc;
         // match_insert compares the reads as they are (no upper-casing, align/__init__.py:250-267): fold_case = 0;
         // lower-case reads come out "escaped" and take the byte-exact kernels in both stages
-        rc = fq_pack_on_stream(ctx, st, b.counts, s.scan_tmp, q.text.as<unsigned char>(), q.recs.as<FqRec>(), n, 0,
+        // (adapter mode only has match_to, which upper-cases: fold there)
+        rc = fq_pack_on_stream(ctx, st, b.counts, s.scan_tmp, q.text.as<unsigned char>(), q.recs.as<FqRec>(), n, iset ? 0 : 1,
                                b.codes.as<uint32_t>(), b.woff.as<uint32_t>(), b.len.as<uint16_t>());
         if (rc) return rc;
         k_fq_gather<<<grid_for(n * 32, 256), 256, 0, st>>>(q.text.as<unsigned char>(), q.recs.as<FqRec>(), (const long long*)b.offsets.p,
@@ -490,29 +501,57 @@ int pe_back(atr_ctx* ctx, Slot& s, const PeStep& P, const atr_insertset* iset, c
         LAUNCHED(ctx);
     }
     PeSide b0 = pe_side(s, 0), b1 = pe_side(s, 1);
-    rc = insert_on_stream(ctx, st, iset, b0.codes.as<uint32_t>(), b0.woff.as<uint32_t>(), b0.len.as<uint16_t>(),
-                          b1.codes.as<uint32_t>(), b1.woff.as<uint32_t>(), b1.len.as<uint16_t>(),
-                          b0.ascii.as<uint8_t>(), b0.offsets.as<int64_t>(), 0, b1.ascii.as<uint8_t>(), b1.offsets.as<int64_t>(), 0, n,
-                          s.ins_out.as<atr_insert_result>());
-    if (rc) return rc;
-    k_pe_prepare<<<grid_for(n, 256), 256, 0, st>>>(s.ins_out.as<atr_insert_result>(), s.fq[0].recs.as<FqRec>(), s.fq[1].recs.as<FqRec>(), n,
-                                                   o->min_insert_overlap, b0.win.as<uint16_t>(), b1.win.as<uint16_t>());
-    LAUNCHED(ctx);
-    for (int f = 0; f < 2; f++) {               // adapter{1,2}.match_to(read{1,2}) where there was no insert match
-        PeSide b = pe_side(s, f);
-        rc = locate_on_stream(ctx, s, sets[f], b.codes.as<uint32_t>(), b.woff.as<uint32_t>(), b.len.as<uint16_t>(), b.win.as<uint16_t>(),
-                              b.ascii.as<uint8_t>(), b.offsets.as<int64_t>(), 0, 1, n, b.out.as<atr_match>());
+    if (iset) {
+        rc = insert_on_stream(ctx, st, iset, b0.codes.as<uint32_t>(), b0.woff.as<uint32_t>(), b0.len.as<uint16_t>(),
+                              b1.codes.as<uint32_t>(), b1.woff.as<uint32_t>(), b1.len.as<uint16_t>(),
+                              b0.ascii.as<uint8_t>(), b0.offsets.as<int64_t>(), 0, b1.ascii.as<uint8_t>(), b1.offsets.as<int64_t>(), 0, n,
+                              s.ins_out.as<atr_insert_result>());
         if (rc) return rc;
+        k_pe_prepare<<<grid_for(n, 256), 256, 0, st>>>(s.ins_out.as<atr_insert_result>(), s.fq[0].recs.as<FqRec>(), s.fq[1].recs.as<FqRec>(), n,
+                                                       o->min_insert_overlap, b0.win.as<uint16_t>(), b1.win.as<uint16_t>());
+        LAUNCHED(ctx);
+        for (int f = 0; f < 2; f++) {               // adapter{1,2}.match_to(read{1,2}) where there was no insert match
+            PeSide b = pe_side(s, f);
+            rc = locate_on_stream(ctx, s, sets[f], b.codes.as<uint32_t>(), b.woff.as<uint32_t>(), b.len.as<uint16_t>(), b.win.as<uint16_t>(),
+                                  b.ascii.as<uint8_t>(), b.offsets.as<int64_t>(), 0, 1, n, b.out.as<atr_match>());
+            if (rc) return rc;
+        }
+        k_pe_apply<<<grid_for(n, 256), 256, 0, st>>>(s.fq[0].text.as<unsigned char>(), s.fq[0].recs.as<FqRec>(),
+                                                     s.fq[1].text.as<unsigned char>(), s.fq[1].recs.as<FqRec>(),
+                                                     s.ins_out.as<atr_insert_result>(), b0.out.as<atr_match>(), b1.out.as<atr_match>(), n,
+                                                     o->symmetric, o->min_insert_overlap, o->max_len, o->max_errors,
+                                                     s.fq[0].fwin.as<uint16_t>(), s.fq[1].fwin.as<uint16_t>(),
+                                                     (unsigned long long*)(d_stats + L.o_hist[0]), (unsigned long long*)(d_stats + L.o_hist[1]),
+                                                     (unsigned long long*)(d_stats + L.o_adj[0]), (unsigned long long*)(d_stats + L.o_adj[1]), d_ctr,
+                                                     o->ops, d_ops);
+        LAUNCHED(ctx);
+    } else {
+        // "--aligner adapter": two independent AdapterCutters (the single-end adapter stage per read), then the pair filters
+        for (int f = 0; f < 2; f++) {
+            FqSide& q = s.fq[f];
+            PeSide b = pe_side(s, f);
+            CU(cudaMemsetAsync(q.flags.p, 0, (size_t)n, st));
+            if (!sets[f]) continue;
+            for (int round = 0; round < o->times; round++) {
+                rc = locate_on_stream(ctx, s, sets[f], b.codes.as<uint32_t>(), b.woff.as<uint32_t>(), b.len.as<uint16_t>(),
+                                      round ? b.win.as<uint16_t>() : nullptr, b.ascii.as<uint8_t>(), b.offsets.as<int64_t>(), 0, 1, n,
+                                      b.out.as<atr_match>());
+                if (rc) return rc;
+                k_fq_apply<<<grid_for(n, 256), 256, 0, st>>>(q.text.as<unsigned char>(), q.recs.as<FqRec>(), b.out.as<atr_match>(), n, round,
+                                                             round + 1 < o->times ? 1 : 0, (const signed char*)(d_stats + L.o_flags[f]),
+                                                             o->max_len, o->max_errors, q.fwin.as<uint16_t>(), b.win.as<uint16_t>(),
+                                                             q.flags.as<unsigned char>(), (unsigned long long*)(d_stats + L.o_front[f]),
+                                                             (unsigned long long*)(d_stats + L.o_hist[f]),
+                                                             (unsigned long long*)(d_stats + L.o_adj[f]), (FqCounters*)(d_stats + L.o_side[f]));
+                LAUNCHED(ctx);
+            }
+        }
+        k_pe_post<<<grid_for(n, 256), 256, 0, st>>>(s.fq[0].text.as<unsigned char>(), s.fq[0].recs.as<FqRec>(),
+                                                    s.fq[1].text.as<unsigned char>(), s.fq[1].recs.as<FqRec>(), n, o->ops,
+                                                    s.fq[0].fwin.as<uint16_t>(), s.fq[1].fwin.as<uint16_t>(),
+                                                    s.fq[0].flags.as<unsigned char>(), s.fq[1].flags.as<unsigned char>(), d_ops);
+        LAUNCHED(ctx);
     }
-    k_pe_apply<<<grid_for(n, 256), 256, 0, st>>>(s.fq[0].text.as<unsigned char>(), s.fq[0].recs.as<FqRec>(),
-                                                 s.fq[1].text.as<unsigned char>(), s.fq[1].recs.as<FqRec>(),
-                                                 s.ins_out.as<atr_insert_result>(), b0.out.as<atr_match>(), b1.out.as<atr_match>(), n,
-                                                 o->symmetric, o->min_insert_overlap, o->max_len, o->max_errors,
-                                                 s.fq[0].fwin.as<uint16_t>(), s.fq[1].fwin.as<uint16_t>(),
-                                                 (unsigned long long*)(d_stats + L.o_hist[0]), (unsigned long long*)(d_stats + L.o_hist[1]),
-                                                 (unsigned long long*)(d_stats + L.o_adj[0]), (unsigned long long*)(d_stats + L.o_adj[1]), d_ctr,
-                                                 o->ops, d_ops);
-    LAUNCHED(ctx);
     for (int f = 0; f < 2; f++) {
         FqSide& q = s.fq[f];
         CU(cudaMemsetAsync(q.len64.p, 0, (size_t)(n + 2) * sizeof(long long), st));
@@ -555,16 +594,20 @@ extern "C" int atr_trim_fastq_pe_host(atr_ctx* ctx, const atr_insertset* iset, c
                                       const atr_trim_pe_opts* opts, const uint8_t* text1, int64_t nbytes1, const uint8_t* text2,
                                       int64_t nbytes2, uint8_t* out1, int64_t out_cap1, uint8_t* out2, int64_t out_cap2,
                                       int64_t* out_bytes, int64_t* consumed, atr_trim_pe_stats* stats, atr_fastq_error* err) {
-    if (!ctx || !iset || !set1 || !set2 || !opts || nbytes1 < 0 || nbytes2 < 0 || (nbytes1 > 0 && (!text1 || !out1)) ||
+    if (!ctx || (iset && (!set1 || !set2)) || !opts || nbytes1 < 0 || nbytes2 < 0 || (nbytes1 > 0 && (!text1 || !out1)) ||
         (nbytes2 > 0 && (!text2 || !out2)) || !out_bytes || !consumed || !stats || !err)
         return fail(ctx, ATR_E_ARG, "bad arguments to atr_trim_fastq_pe_host");
-    if (set1->ctx != ctx || set2->ctx != ctx || iset->ctx != ctx) return fail(ctx, ATR_E_ARG, "adapter / insert set belongs to another context");
+    if ((set1 && set1->ctx != ctx) || (set2 && set2->ctx != ctx) || (iset && iset->ctx != ctx))
+        return fail(ctx, ATR_E_ARG, "adapter / insert set belongs to another context");
+    if (!iset && opts->times < 1) return fail(ctx, ATR_E_ARG, "atr_trim_pe_opts.times must be >= 1 in adapter mode");
     if (opts->max_len < 0 || opts->max_len > ATR_MAX_READ || opts->max_errors < 0 || opts->max_errors > 4095 || opts->min_insert_overlap < 0)
         return fail(ctx, ATR_E_ARG, "bad atr_trim_pe_opts");
     const atr_adapterset* sets[2] = {set1, set2};
     for (int f = 0; f < 2; f++) {
-        if (sets[f]->host.size() != 1 || !sets[f]->host[0].desc.match_to_semantics || sets[f]->host[0].desc.flags != 14)
-            return fail(ctx, ATR_E_ARG, "atr_trim_fastq_pe_host takes one 3' (BACK) adapter per read, created with match_to_semantics = 1");
+        if (iset && (sets[f]->host.size() != 1 || !sets[f]->host[0].desc.match_to_semantics || sets[f]->host[0].desc.flags != 14))
+            return fail(ctx, ATR_E_ARG, "insert mode takes one 3' (BACK) adapter per read, created with match_to_semantics = 1");
+        if (sets[f]) for (const atr::HostAdapter& h : sets[f]->host)
+            if (!h.desc.match_to_semantics) return fail(ctx, ATR_E_ARG, "atr_trim_fastq_pe_host needs adapters created with match_to_semantics = 1");
     }
     CU(cudaSetDevice(ctx->device));
     memset(err, 0, sizeof(*err));
@@ -576,11 +619,20 @@ extern "C" int atr_trim_fastq_pe_host(atr_ctx* ctx, const atr_insertset* iset, c
     const int64_t out_cap[2] = {out_cap1, out_cap2};
     int64_t chunk = opts->chunk_bytes > 0 ? opts->chunk_bytes : ((int64_t)32 << 20);
     chunk = std::max<int64_t>(4096, std::min<int64_t>(chunk, (int64_t)1 << 30));
-    const PeLayout L = pe_layout(opts->max_len, opts->max_errors);
+    const PeLayout L = pe_layout(opts->max_len, opts->max_errors, set1 ? set1->host.size() : 0, set2 ? set2->host.size() : 0);
     int rc = ctx->fq_stats.ensure(L.total);
     if (rc) return fail(ctx, rc, "out of device memory (statistics)");
     char* d_stats = ctx->fq_stats.as<char>();
     CU(cudaMemset(d_stats, 0, L.total));
+    for (int f = 0; f < 2; f++) {
+        if (!sets[f]) continue;
+        std::vector<signed char> ff(sets[f]->host.size());
+        for (size_t a = 0; a < ff.size(); a++) {
+            const int w = sets[f]->host[a].desc.flags;
+            ff[a] = (w == ATR_SEMIGLOBAL) ? (signed char)-1 : ((w == 14 || w == 2) ? (signed char)0 : (signed char)1);
+        }
+        CU(cudaMemcpy(d_stats + L.o_flags[f], ff.data(), ff.size(), cudaMemcpyHostToDevice));
+    }
     const bool final_call = opts->final_chunk != 0;
     int64_t pos[2] = {0, 0}, opos[2] = {0, 0}, records_before = 0;
     auto make_step = [&](int slot) {
@@ -619,17 +671,18 @@ extern "C" int atr_trim_fastq_pe_host(atr_ctx* ctx, const atr_insertset* iset, c
         Slot& s = ctx->slot[cur.slot];
         CU(cudaStreamSynchronize(s.stream));
         bool redo = false;
-        for (int f = 0; f < 2; f++) {
+        for (int f = 0; f < 2 && result == ATR_OK; f++) {
             if (s.fq[f].hinfo->nl_overflow) {
                 rc = s.fq[f].nl.ensure((size_t)(s.fq[f].hinfo->n_nl + 16) * sizeof(uint32_t));
-                if (rc) return fail(ctx, rc, "out of device memory (newline index)");
+                if (rc) { result = fail(ctx, rc, "out of device memory (newline index)"); break; }
                 int ft, ut;
                 flags_of(cur.c[f], f, ft, ut);
                 rc = fq_index(ctx, s, f, cur.c[f], ft, ut);
-                if (rc) return rc;
+                if (rc) { result = rc; break; }
                 redo = true;
             }
         }
+        if (result != ATR_OK) break;
         if (redo) CU(cudaStreamSynchronize(s.stream));
         bool bare = false;
         for (int f = 0; f < 2; f++) {
@@ -770,13 +823,22 @@ extern "C" int atr_trim_fastq_pe_host(atr_ctx* ctx, const atr_insertset* iset, c
     stats->insert_matches += (int64_t)hc->insert_matches;
     stats->overflow += (int64_t)hc->overflow;
     for (int f = 0; f < 2; f++) {
+        const FqCounters* sc = (const FqCounters*)(hst.data() + L.o_side[f]);     // adapter mode: the read's AdapterCutter
+        if (sc->invalid) {
+            err->kind = ATR_FQ_INVALID_MATCH; err->record = -1;
+            return fail(ctx, ATR_E_FORMAT, "an alignment of length <= errors: Match.__init__ raises ValueError in the reference");
+        }
+        stats->with_adapters[f] += (int64_t)sc->with_adapters;
+        stats->overflow += (int64_t)sc->overflow;
+        const unsigned long long* hfr = (const unsigned long long*)(hst.data() + L.o_front[f]);
+        if (stats->errors_front[f]) for (size_t i = 0; i < L.nA[f] * L.H; i++) stats->errors_front[f][i] += (int64_t)hfr[i];
         stats->with_adapters[f] += (int64_t)hc->with_adapters[f];
         stats->bp_in[f] += (int64_t)hc->bp_in[f];
         stats->bp_out[f] += (int64_t)hc->bp_out[f];
         const unsigned long long* hh = (const unsigned long long*)(hst.data() + L.o_hist[f]);
         const unsigned long long* ha = (const unsigned long long*)(hst.data() + L.o_adj[f]);
-        if (stats->errors_back[f]) for (size_t i = 0; i < L.H; i++) stats->errors_back[f][i] += (int64_t)hh[i];
-        if (stats->adjacent_bases[f]) for (size_t i = 0; i < 5; i++) stats->adjacent_bases[f][i] += (int64_t)ha[i];
+        if (stats->errors_back[f]) for (size_t i = 0; i < L.nA[f] * L.H; i++) stats->errors_back[f][i] += (int64_t)hh[i];
+        if (stats->adjacent_bases[f]) for (size_t i = 0; i < L.nA[f] * 5; i++) stats->adjacent_bases[f][i] += (int64_t)ha[i];
     }
     fq_add_ops(stats->ops, *(const FqOpsCounters*)(hst.data() + L.o_ops));
     out_bytes[0] = opos[0]; out_bytes[1] = opos[1];

@@ -326,7 +326,7 @@ ATR_HD int fq_filter(const atr_read_ops& o, const unsigned char* __restrict__ se
                      const unsigned char* __restrict__ seq2, int lo2, int hi2, bool matched2, bool paired) {
     for (int which = 1; which <= 5; which++) {
         if (fq_filter_one(o, seq1, lo1, hi1, matched1, which)) return which;
-        if (paired && fq_filter_one(o, seq2, lo2, hi2, matched2, which)) return which;
+        if (paired && !o.legacy_first && fq_filter_one(o, seq2, lo2, hi2, matched2, which)) return which;
     }
     return 0;
 }

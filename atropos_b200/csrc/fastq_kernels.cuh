@@ -422,6 +422,36 @@ __global__ void __launch_bounds__(256) k_pe_apply(const unsigned char* __restric
     fwin2[2 * r] = (uint16_t)lo2; fwin2[2 * r + 1] = (uint16_t)hi2;
 }
 
+// adapter mode: NEndTrimmer + the pair filters after two independent AdapterCutters (flags: bit 0 = read.match is set)
+__global__ void __launch_bounds__(256) k_pe_post(const unsigned char* __restrict__ t1, const FqRec* __restrict__ r1,
+                                                 const unsigned char* __restrict__ t2, const FqRec* __restrict__ r2, long long n,
+                                                 const __grid_constant__ atr_read_ops ops, uint16_t* __restrict__ fwin1,
+                                                 uint16_t* __restrict__ fwin2, const unsigned char* __restrict__ flags1,
+                                                 const unsigned char* __restrict__ flags2, FqOpsCounters* __restrict__ oc) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const FqRec A = r1[r], B = r2[r];
+    int lo1 = fwin1[2 * r], hi1 = fwin1[2 * r + 1], lo2 = fwin2[2 * r], hi2 = fwin2[2 * r + 1];
+    if (ops.trim_n) {
+        unsigned bp_n;
+        fq_trim_n(t1 + A.seq_b, lo1, hi1, bp_n);
+        if (bp_n) atomicAdd(&oc->bp_n_ends[0], (unsigned long long)bp_n);
+        fq_trim_n(t2 + B.seq_b, lo2, hi2, bp_n);
+        if (bp_n) atomicAdd(&oc->bp_n_ends[1], (unsigned long long)bp_n);
+    }
+    const int flt = fq_filter(ops, t1 + A.seq_b, lo1, hi1, flags1[r] != 0, t2 + B.seq_b, lo2, hi2, flags2[r] != 0, true);
+    if (flt) {
+        unsigned long long* c = flt == 1 ? &oc->too_short : flt == 2 ? &oc->too_long : flt == 3 ? &oc->too_many_n
+                                : flt == 4 ? &oc->discarded_trimmed : &oc->discarded_untrimmed;
+        atomicAdd(c, 1ull);
+        lo1 = lo2 = 1; hi1 = hi2 = 0;
+    } else {
+        atomicAdd(&oc->records_written, 1ull);
+    }
+    fwin1[2 * r] = (uint16_t)lo1; fwin1[2 * r + 1] = (uint16_t)hi1;
+    fwin2[2 * r] = (uint16_t)lo2; fwin2[2 * r + 1] = (uint16_t)hi2;
+}
+
 // bytes consumed by the first n records (n < the chunk's complete records): -> mapped pinned host memory
 __global__ void k_fq_consumed(const uint32_t* __restrict__ nl, long long n, FqInfo* h_info) {
     if (blockIdx.x == 0 && threadIdx.x == 0) h_info->consumed = n > 0 ? (long long)nl[4 * n - 1] + 1 : 0;

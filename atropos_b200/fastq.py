@@ -253,12 +253,15 @@ def trim_file_pair(trimmer, src1, src2, dst1, dst2, block_bytes=1 << 27):
 
 
 class PairTrimStats(object):
-    """InsertAdapterCutter.summarize() (commands/trim/modifiers.py:498-509): per read the adapter's statistics."""
+    """InsertAdapterCutter.summarize() (commands/trim/modifiers.py:498-509) or, in adapter mode, the two AdapterCutters'
+    (:189-195): per read and adapter the statistics Adapter.trimmed() keeps."""
 
-    def __init__(self, max_len, max_errors):
-        self.max_len, self.max_errors = max_len, max_errors
-        self.errors_back = [np.zeros((max_len + 1, max_errors + 1), dtype=np.int64) for _ in range(2)]
-        self.adjacent = [np.zeros(5, dtype=np.int64) for _ in range(2)]
+    def __init__(self, max_len, max_errors, n_adapters=(1, 1)):
+        self.max_len, self.max_errors, self.n_adapters = max_len, max_errors, tuple(max(1, k) for k in n_adapters)
+        shape = lambda i: (self.n_adapters[i], max_len + 1, max_errors + 1)
+        self.errors_back = [np.zeros(shape(i), dtype=np.int64) for i in range(2)]
+        self.errors_front = [np.zeros(shape(i), dtype=np.int64) for i in range(2)]
+        self.adjacent = [np.zeros((self.n_adapters[i], 5), dtype=np.int64) for i in range(2)]
         self.records = self.insert_matches = self.overflow = 0
         self.with_adapters, self.bp_in, self.bp_out = [0, 0], [0, 0], [0, 0]
         self.ops = new_ops_stats()
@@ -267,6 +270,7 @@ class PairTrimStats(object):
         merge_ops_stats(self.ops, other.ops)
         for i in range(2):
             self.errors_back[i] += other.errors_back[i]
+            self.errors_front[i] += other.errors_front[i]
             self.adjacent[i] += other.adjacent[i]
             self.with_adapters[i] += other.with_adapters[i]
             self.bp_in[i] += other.bp_in[i]
@@ -276,10 +280,18 @@ class PairTrimStats(object):
         self.overflow += other.overflow
         return self
 
-    def adapter_summary(self, i):
-        eb = TrimStats._nested(self.errors_back[i])
-        return {"errors_back": eb, "lengths_back": {ln: sum(v.values()) for ln, v in eb.items()},
-                "adjacent_bases": {b: int(self.adjacent[i][k]) for k, b in enumerate(_BASES)}}
+    def adapter_summary(self, i, a=0, where=BACK):
+        """statistics of adapter `a` of read `i` (0 / 1), the keys Adapter.summarize() emits for its type"""
+        d = {}
+        if where not in (BACK, SUFFIX):
+            d["errors_front"] = TrimStats._nested(self.errors_front[i][a])
+            d["lengths_front"] = {ln: sum(v.values()) for ln, v in d["errors_front"].items()}
+        if where in (ANYWHERE, BACK, SUFFIX):
+            d["errors_back"] = TrimStats._nested(self.errors_back[i][a])
+            d["lengths_back"] = {ln: sum(v.values()) for ln, v in d["errors_back"].items()}
+        if where in (BACK, SUFFIX):
+            d["adjacent_bases"] = {b: int(self.adjacent[i][a, k]) for k, b in enumerate(_BASES)}
+        return d
 
 
 class FastqPairTrimmer(object):
@@ -291,24 +303,35 @@ class FastqPairTrimmer(object):
     line builds them for insert mode (max_rmp 1e-6, min_overlap 1, indel_cost 3: trim/cli.py:667-679);
     insert_aligner: atropos_b200.align.InsertAligner with the same sequences."""
 
-    def __init__(self, adapter1, adapter2, insert_aligner, symmetric=True, min_insert_overlap=1, max_len=256, device=0,
-                 chunk_bytes=0, **read_ops):
+    def __init__(self, adapter1, adapter2, insert_aligner=None, symmetric=True, min_insert_overlap=1, max_len=256, device=0,
+                 chunk_bytes=0, times=1, **read_ops):
+        """insert_aligner given: `--aligner insert` (adapter1 / adapter2 = the one 3' adapter of each read).
+        insert_aligner None: the command's default `--aligner adapter`: adapter1 / adapter2 are lists of Adapters (or
+        None) for read 1 / read 2, cut independently with `times` rounds each (commands/trim/__init__.py:457-476)."""
         self.ops = _abi.make_read_ops(**read_ops)
-        for a in (adapter1, adapter2):
-            if a.where != BACK:
-                raise ValueError("the insert-aligner path takes one 3' adapter per read")
-        self.adapter1, self.adapter2, self.aligner = adapter1, adapter2, insert_aligner
-        self.symmetric, self.min_insert_overlap = bool(symmetric), int(min_insert_overlap)
+        self.aligner = insert_aligner
+        as_list = lambda a: [] if a is None else (list(a) if isinstance(a, (list, tuple)) else [a])
+        self.adapters = [as_list(adapter1), as_list(adapter2)]
+        if insert_aligner is not None:
+            for ads in self.adapters:
+                if len(ads) != 1 or ads[0].where != BACK:
+                    raise ValueError("Insert aligner requires a single 3' adapter for each read")
+        self.adapter1 = self.adapters[0][0] if self.adapters[0] else None
+        self.adapter2 = self.adapters[1][0] if self.adapters[1] else None
+        self.symmetric, self.min_insert_overlap, self.times = bool(symmetric), int(min_insert_overlap), int(times)
         self.max_len = int(max_len)
-        self.max_errors = max(len(adapter1.sequence), len(adapter2.sequence))
+        every = self.adapters[0] + self.adapters[1]
+        if insert_aligner is not None:
+            self.max_errors = max(len(a.sequence) for a in every)
+        else:
+            self.max_errors = max([int(a.max_error_rate * len(a.sequence)) for a in every] or [0])
         self.ctx = engine.default_context(device)
-        self._set1 = engine.AdapterSet(self.ctx, [adapter1.descriptor()])
-        self._set2 = engine.AdapterSet(self.ctx, [adapter2.descriptor()])
-        self._iset = insert_aligner._insertset(self.max_len)
+        self._sets = [engine.AdapterSet(self.ctx, [a.descriptor() for a in ads]) if ads else None for ads in self.adapters]
+        self._iset = insert_aligner._insertset(self.max_len) if insert_aligner is not None else None
         self.chunk_bytes = int(chunk_bytes)
 
     def new_stats(self):
-        return PairTrimStats(self.max_len, self.max_errors)
+        return PairTrimStats(self.max_len, self.max_errors, (len(self.adapters[0]), len(self.adapters[1])))
 
     def trim(self, text1, text2, final=True, stats=None, out1=None, out2=None):
         """Returns ((out1, out2) uint8 views, stats, (consumed1, consumed2))."""
@@ -321,15 +344,17 @@ class FastqPairTrimmer(object):
         if stats is None:
             stats = self.new_stats()
         opts = _abi.AtrTrimPeOpts(int(self.symmetric), self.min_insert_overlap, self.max_len, self.max_errors,
-                                  int(bool(final)), 0, self.chunk_bytes, self.ops)
+                                  int(bool(final)), self.times, self.chunk_bytes, self.ops)
         st = _abi.AtrTrimPeStats()
         for i in range(2):
             st.errors_back[i] = stats.errors_back[i].ctypes.data
+            st.errors_front[i] = stats.errors_front[i].ctypes.data
             st.adjacent_bases[i] = stats.adjacent[i].ctypes.data
         err = _abi.AtrFastqError()
         nout, consumed = (C.c_int64 * 2)(), (C.c_int64 * 2)()
         L = _lib.load()
-        rc = L.atr_trim_fastq_pe_host(self.ctx.handle, self._iset.handle, self._set1.handle, self._set2.handle, C.byref(opts),
+        h = lambda x: x.handle if x is not None else None
+        rc = L.atr_trim_fastq_pe_host(self.ctx.handle, h(self._iset), h(self._sets[0]), h(self._sets[1]), C.byref(opts),
                                       b1.ctypes.data if b1.size else None, int(b1.size),
                                       b2.ctypes.data if b2.size else None, int(b2.size),
                                       out1.ctypes.data, int(out1.size), out2.ctypes.data, int(out2.size), nout, consumed,

@@ -260,6 +260,9 @@ typedef struct atr_read_ops {
     int32_t maximum_length;   /* -M: TooLongReadFilter, < 0 = off (filters.py:130-140) */
     int32_t discard_trimmed;  /* --discard-trimmed: TrimmedFilter (filters.py:176-180) */
     int32_t discard_untrimmed;/* --discard-untrimmed: UntrimmedFilter (filters.py:170-174) */
+    int32_t legacy_first;     /* paired-end "legacy mode" (paired == 'first', trim/cli.py:629-645: no option touches read 2):
+                                 the filters look at read 1 only (SingleWrapper, filters.py:54-61) */
+    int32_t pad;
     double  max_n;            /* --max-n: NContentFilter, < 0 = off; < 1 is a proportion (filters.py:142-168) */
 } atr_read_ops;
 
@@ -317,7 +320,7 @@ typedef struct atr_trim_pe_opts {
     int32_t max_len;            /* statistics cover removed lengths 0..max_len and error counts 0..max_errors */
     int32_t max_errors;
     int32_t final_chunk;        /* 1: both texts end their files */
-    int32_t pad;
+    int32_t times;              /* adapter mode (iset == NULL): AdapterCutter(times) of both reads, >= 1 */
     int64_t chunk_bytes;        /* per text; 0 = default (32 MiB) */
     atr_read_ops ops;
 } atr_trim_pe_opts;
@@ -326,8 +329,9 @@ typedef struct atr_trim_pe_stats {
     int64_t records, insert_matches;          /* pairs; pairs for which match_insert returned a match */
     int64_t with_adapters[2], bp_in[2], bp_out[2];
     int64_t overflow;
-    int64_t* errors_back[2];                  /* per read: [max_len+1][max_errors+1], ADDED to */
-    int64_t* adjacent_bases[2];               /* per read: [5] */
+    int64_t* errors_back[2];                  /* per read: [n_adapters of that read][max_len+1][max_errors+1], ADDED to */
+    int64_t* adjacent_bases[2];               /* per read: [n_adapters][5] */
+    int64_t* errors_front[2];                 /* adapter mode only (may be NULL): same shape as errors_back */
     atr_read_ops_stats ops;
 } atr_trim_pe_stats;
 
@@ -336,6 +340,11 @@ typedef struct atr_trim_pe_stats {
  * InsertAligner.match_insert first, adapter{1,2}.match_to as the fallback, the symmetric fix-up), its trim() and the
  * adapters' statistics (:455-496, adapters/__init__.py:424-436) and FastqFormat.format for both outputs.
  * set1 / set2: one 3' (BACK) adapter each, created with match_to_semantics = 1 (the fallback adapters).
+ *
+ * iset == NULL selects the command's default paired-end mode instead ("--aligner adapter", commands/trim/__init__.py:
+ * 457-476: modifiers.add_modifier_pair(AdapterCutter, ...)): read 1 is cut with the adapters of set1, read 2 with those of
+ * set2 (any adapter types, `times` rounds; either set may be NULL), independently of each other; pairing checks,
+ * modifiers, pair filters and outputs as above.
  * consumed[i]: bytes of text i that were processed. On ATR_E_FORMAT *err names the file and the line. */
 int  atr_trim_fastq_pe_host(atr_ctx* ctx, const atr_insertset* iset, const atr_adapterset* set1, const atr_adapterset* set2,
                             const atr_trim_pe_opts* opts, const uint8_t* text1, int64_t nbytes1, const uint8_t* text2,

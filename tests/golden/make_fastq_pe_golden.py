@@ -84,7 +84,7 @@ def ops_stats(rj):
             "records_written": t["formatters"]["records_written"]}
 
 
-def run_reference(text1, text2, error_rate, extra=()):
+def run_reference(text1, text2, error_rate, extra=(), adapter_args=None):
     from atropos.commands import get_command
     tmp = tempfile.mkdtemp(prefix="fqpegold")
     try:
@@ -92,7 +92,7 @@ def run_reference(text1, text2, error_rate, extra=()):
         for key, text in (("in1.fq", text1), ("in2.fq", text2)):
             with open(p[key], "w", newline="") as fh:
                 fh.write(text)
-        args = ["--aligner", "insert", "-a", A1, "-A", A2, "-pe1", p["in1.fq"], "-pe2", p["in2.fq"], "-o", p["out1.fq"],
+        args = (["--aligner", "insert", "-a", A1, "-A", A2] if adapter_args is None else list(adapter_args)) + ["-pe1", p["in1.fq"], "-pe2", p["in2.fq"], "-o", p["out1.fq"],
                 "-p", p["out2.fq"], "--no-default-adapters", "--no-cache-adapters", "--quiet", "--report-file", p["rep"],
                 "--report-formats", "json"] + list(extra)
         if error_rate is not None:
@@ -114,8 +114,12 @@ def run_reference(text1, text2, error_rate, extra=()):
         rep = p["rep"] + ".json" if os.path.exists(p["rep"] + ".json") else p["rep"]
         with open(rep) as fh:
             rj = json.load(fh)
-        cutter = rj["trim"]["modifiers"]["InsertAdapterCutter"]
-        ads = [adapter_stats(list(d.values())[0]) for d in cutter["adapters"]]
+        if adapter_args is None:
+            cutter = rj["trim"]["modifiers"]["InsertAdapterCutter"]
+            ads = [adapter_stats(list(d.values())[0]) for d in cutter["adapters"]]
+        else:                                          # two AdapterCutters: per read a dict name -> statistics
+            cutter = rj["trim"]["modifiers"]["AdapterCutter"]
+            ads = [[adapter_stats(st) for st in (d or {}).values()] for d in cutter["adapters"]]
         return {"ops": ops_stats(rj), "out1": outs[0], "out2": outs[1], "records": rj["record_counts"].get("0", 0),
                 "with_adapters": cutter["records_with_adapters"], "bp_in": rj["bp_counts"].get("0", [0, 0]),
                 "bp_out": rj["trim"]["formatters"]["bp_written"], "adapters": ads}
@@ -129,15 +133,15 @@ def main():
     rng = np.random.default_rng(9101)
     cases = []
 
-    def add(label, recs, error_rate=0.1, edit=None, extra=(), read_ops=None):
+    def add(label, recs, error_rate=0.1, edit=None, extra=(), read_ops=None, adapter_args=None, times=1):
         t1, t2 = fastq(recs[0]), fastq(recs[1])
         if edit:
             t1, t2 = edit(t1, t2)
-        res = run_reference(t1, t2, error_rate, extra)
+        res = run_reference(t1, t2, error_rate, extra, adapter_args)
         print(label, {k: (v if not isinstance(v, (str, list)) else (len(v) if isinstance(v, str) else v if len(v) < 3 else len(v)))
                       for k, v in res.items()})
         cases.append({"label": label, "text1": t1, "text2": t2, "error_rate": error_rate, "read_ops": read_ops or {},
-                      "result": res})
+                      "mode": "insert" if adapter_args is None else "adapter", "times": times, "result": res})
 
     add("pe150", make_pairs(rng, 500, seed=11))
     add("pe150_suffix_names", make_pairs(rng, 300, suffix=True, seed=12))
@@ -163,6 +167,17 @@ def main():
         read_ops=dict(quality_cutoff=[10, 20], cut=[3], cut2=[-4], max_n=3, minimum_length=30, maximum_length=140))
     r = make_pairs(rng, 300, seed=23)
     add("ops_discard_untrimmed", (lowq(r[0]), lowq(r[1])), extra=["--discard-untrimmed", "--trim-n"], read_ops=dict(discard_untrimmed=True, trim_n=True))
+    # --- the command's default paired-end mode: --aligner adapter, independent adapter cutters per read ------------------
+    FRONT5, SMALL3 = "GTTCAGAGTTCTACAGTCCGACGATC", "TGGAATTCTCGGGTGCCAAGG"
+    r = make_pairs(rng, 400, ragged=True, lower=0.03, seed=24)
+    add("adapter_mode_basic", r, adapter_args=["-a", A1, "-A", A2])
+    r = make_pairs(rng, 400, ragged=True, seed=25)
+    add("adapter_mode_panel_times2_ops", (lowq(r[0]), lowq(r[1])),
+        adapter_args=["-a", A1, "-a", SMALL3, "-g", FRONT5, "-A", A2, "-G", FRONT5, "-n", "2"], times=2,
+        extra=["-q", "10", "--trim-n", "-m", "20"], read_ops=dict(quality_cutoff=[10], trim_n=True, minimum_length=20))
+    r = make_pairs(rng, 300, seed=26)
+    add("adapter_mode_read1_only", r, adapter_args=["-a", A1], extra=["--discard-untrimmed"], read_ops=dict(discard_untrimmed=True, legacy_first=True))
+
     # --- improper pairing / malformed input --------------------------------------------------------------------
     def drop_last(which):
         def f(t1, t2):

@@ -244,7 +244,9 @@ struct SimText {
 };
 }
 
-int sim_trim_fastq_pe(const atr_insert_desc* idesc, const atr_adapter_desc* d1, const atr_adapter_desc* d2,
+// idesc == NULL: adapter mode, n_ad1 / n_ad2 adapters per read (d1 / d2 arrays), `times` rounds each; ef1 / ef2 = front histograms
+int sim_trim_fastq_pe(const atr_insert_desc* idesc, const atr_adapter_desc* d1, int n_ad1, const atr_adapter_desc* d2, int n_ad2,
+                      long long* ef1, long long* ef2,
                       const atr_trim_pe_opts* o, const unsigned char* text1, long long nbytes1, const unsigned char* text2,
                       long long nbytes2, unsigned char* out1, unsigned char* out2, long long* out_bytes, long long* consumed,
                       long long* counters, long long* eb1, long long* eb2, long long* adj1, long long* adj2, atr_fastq_error* err,
@@ -300,38 +302,77 @@ int sim_trim_fastq_pe(const atr_insert_desc* idesc, const atr_adapter_desc* d1, 
         fq_pre_ops(o->ops, 1, text2, B, bpc, bpq);
         oc->bp_cut[1] += bpc; oc->bp_quality[1] += bpq;
         const int len1 = A.seq_len, len2 = B.seq_len;
-        atr_insert_result ins;
-        im_clear(ins.insert); im_clear(ins.match1); im_clear(ins.match2);
-        atr_match fb1, fb2;
-        im_clear(fb1); im_clear(fb2);
-        if (len1 >= o->min_insert_overlap && len2 >= o->min_insert_overlap) {
-            int used = 0;
-            int rc = sim_match_insert(idesc, text1 + A.seq_b, len1, text2 + B.seq_b, len2, 0, &ins, &used);
-            if (rc) return rc;
-            if (ins.insert.status == ATR_ST_NONE) {
-                rc = sim_locate(d1, 0, 0, text1 + A.seq_b, len1, 0, len1, 1, 0, &fb1, &used);
-                if (!rc) rc = sim_locate(d2, 0, 0, text2 + B.seq_b, len2, 0, len2, 1, 0, &fb2, &used);
-                if (rc) return rc;
-            }
-        }
+        int k1 = len1, k2 = len2;
         PeMatch m1, m2;
-        int hit = 0, invalid = 0;
-        fq_pe_decide(ins, fb1, fb2, len1, len2, o->min_insert_overlap, o->symmetric, m1, m2, hit, invalid);
-        if (invalid) { err->kind = ATR_FQ_INVALID_MATCH; err->record = r; return ATR_E_FORMAT; }
-        counters[1] += hit;
-        FqApply ap;
-        bool counted;
-        const int k1 = fq_pe_trim(m1, len1, text1 + A.seq_b, ap, counted);
-        if (m1.present) counters[2]++;
-        if (counted) {
-            if (ap.length <= o->max_len && ap.errors <= o->max_errors) eb1[(size_t)ap.length * (size_t)(o->max_errors + 1) + (size_t)ap.errors]++; else counters[8]++;
-            adj1[ap.adjacent]++;
-        }
-        const int k2 = fq_pe_trim(m2, len2, text2 + B.seq_b, ap, counted);
-        if (m2.present) counters[3]++;
-        if (counted) {
-            if (ap.length <= o->max_len && ap.errors <= o->max_errors) eb2[(size_t)ap.length * (size_t)(o->max_errors + 1) + (size_t)ap.errors]++; else counters[8]++;
-            adj2[ap.adjacent]++;
+        m1.present = m2.present = 0;
+        if (idesc) {
+            atr_insert_result ins;
+            im_clear(ins.insert); im_clear(ins.match1); im_clear(ins.match2);
+            atr_match fb1, fb2;
+            im_clear(fb1); im_clear(fb2);
+            if (len1 >= o->min_insert_overlap && len2 >= o->min_insert_overlap) {
+                int used = 0;
+                int rc = sim_match_insert(idesc, text1 + A.seq_b, len1, text2 + B.seq_b, len2, 0, &ins, &used);
+                if (rc) return rc;
+                if (ins.insert.status == ATR_ST_NONE) {
+                    rc = sim_locate(d1, 0, 0, text1 + A.seq_b, len1, 0, len1, 1, 0, &fb1, &used);
+                    if (!rc) rc = sim_locate(d2, 0, 0, text2 + B.seq_b, len2, 0, len2, 1, 0, &fb2, &used);
+                    if (rc) return rc;
+                }
+            }
+            int hit = 0, invalid = 0;
+            fq_pe_decide(ins, fb1, fb2, len1, len2, o->min_insert_overlap, o->symmetric, m1, m2, hit, invalid);
+            if (invalid) { err->kind = ATR_FQ_INVALID_MATCH; err->record = r; return ATR_E_FORMAT; }
+            counters[1] += hit;
+            FqApply ap;
+            bool counted;
+            k1 = fq_pe_trim(m1, len1, text1 + A.seq_b, ap, counted);
+            if (m1.present) counters[2]++;
+            if (counted) {
+                if (ap.length <= o->max_len && ap.errors <= o->max_errors) eb1[(size_t)ap.length * (size_t)(o->max_errors + 1) + (size_t)ap.errors]++; else counters[8]++;
+                adj1[ap.adjacent]++;
+            }
+            k2 = fq_pe_trim(m2, len2, text2 + B.seq_b, ap, counted);
+            if (m2.present) counters[3]++;
+            if (counted) {
+                if (ap.length <= o->max_len && ap.errors <= o->max_errors) eb2[(size_t)ap.length * (size_t)(o->max_errors + 1) + (size_t)ap.errors]++; else counters[8]++;
+                adj2[ap.adjacent]++;
+            }
+        } else {                                         // two independent AdapterCutters (the single-end loop per read)
+            for (int f = 0; f < 2; f++) {
+                const atr_adapter_desc* descs = f ? d2 : d1;
+                const int n_ad = f ? n_ad2 : n_ad1;
+                const unsigned char* text = f ? text2 : text1;
+                const FqRec& R = f ? B : A;
+                long long *efr = f ? ef2 : ef1, *eb = f ? eb2 : eb1, *adj = f ? adj2 : adj1;
+                int lo = 0, hi = R.seq_len;
+                bool any = false;
+                for (int round = 0; round < o->times && n_ad > 0; round++) {
+                    atr_match m;
+                    im_clear(m);
+                    for (int a = 0; a < n_ad; a++) {
+                        int used = 0;
+                        int rc = sim_locate(&descs[a], a, a > 0, text + R.seq_b, R.seq_len, lo, hi, 1, 0, &m, &used);
+                        if (rc) return rc;
+                    }
+                    if (m.status == ATR_ST_INVALID) { err->kind = ATR_FQ_INVALID_MATCH; err->record = r; return ATR_E_FORMAT; }
+                    FqApply ap;
+                    const int w = m.adapter >= 0 ? descs[m.adapter].flags : 0;
+                    const int ff = (w == ATR_SEMIGLOBAL) ? -1 : ((w == 14 || w == 2) ? 0 : 1);
+                    if (!fq_apply(m, ff, lo, hi, text + R.seq_b, ap)) break;
+                    any = true;
+                    if (ap.length <= o->max_len && ap.errors <= o->max_errors)
+                        (ap.front ? efr : eb)[((size_t)m.adapter * (size_t)(o->max_len + 1) + (size_t)ap.length) * (size_t)(o->max_errors + 1) + (size_t)ap.errors]++;
+                    else counters[8]++;
+                    if (!ap.front) adj[(size_t)m.adapter * 5 + (size_t)ap.adjacent]++;
+                    lo = ap.new_lo; hi = ap.new_hi;
+                }
+                if (any) counters[2 + f]++;
+                (f ? m2 : m1).present = any;
+                // windows may start beyond 0 (front adapters): carried into the post stage below
+                if (f == 0) { k1 = hi; A.seq_b += (uint32_t)lo; A.qual_b += (uint32_t)lo; k1 -= lo; }
+                else { k2 = hi; B.seq_b += (uint32_t)lo; B.qual_b += (uint32_t)lo; k2 -= lo; }
+            }
         }
         int lo1 = 0, hi1 = k1, lo2 = 0, hi2 = k2;
         if (o->ops.trim_n) {

@@ -38,8 +38,9 @@ def lib():
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_abi.AtrFastqError),
                                      C.POINTER(SimOpsCounters)]
         L.sim_trim_fastq.restype = C.c_int
-        L.sim_trim_fastq_pe.argtypes = [C.POINTER(_abi.AtrInsertDesc), C.POINTER(_abi.AtrAdapterDesc),
-                                        C.POINTER(_abi.AtrAdapterDesc), C.POINTER(_abi.AtrTrimPeOpts), C.c_char_p,
+        L.sim_trim_fastq_pe.argtypes = [C.POINTER(_abi.AtrInsertDesc), C.POINTER(_abi.AtrAdapterDesc), C.c_int,
+                                        C.POINTER(_abi.AtrAdapterDesc), C.c_int, C.c_void_p, C.c_void_p,
+                                        C.POINTER(_abi.AtrTrimPeOpts), C.c_char_p,
                                         C.c_longlong, C.c_char_p, C.c_longlong, C.c_void_p, C.c_void_p,
                                         C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_abi.AtrFastqError),
@@ -122,17 +123,28 @@ def trim_fastq(text, adapters, times=1, max_len=512, final=True, **read_ops):
     return bytes(out[:nout.value]), stats, consumed.value
 
 
-def trim_fastq_pe(text1, text2, adapter1, adapter2, insert_aligner, symmetric=True, min_insert_overlap=1, max_len=256,
-                  final=True, **read_ops):
-    """CPU run of the paired-end FASTQ path's device functions. Returns ((out1, out2), PairTrimStats, consumed)."""
+def trim_fastq_pe(text1, text2, adapter1, adapter2, insert_aligner=None, symmetric=True, min_insert_overlap=1, max_len=256,
+                  final=True, times=1, **read_ops):
+    """CPU run of the paired-end FASTQ path's device functions (insert mode, or adapter mode when insert_aligner is
+    None and adapter1 / adapter2 are lists). Returns ((out1, out2), PairTrimStats, consumed)."""
     import numpy as np
     from atropos_b200 import fastq
-    d1, k1 = adapter1.descriptor()
-    d2, k2 = adapter2.descriptor()
-    idesc, k3 = insert_aligner.descriptor(max_len)
-    max_errors = max(len(adapter1.sequence), len(adapter2.sequence))
-    stats = fastq.PairTrimStats(max_len, max_errors)
-    opts = _abi.AtrTrimPeOpts(int(symmetric), min_insert_overlap, max_len, max_errors, int(bool(final)), 0, 0,
+    as_list = lambda a: [] if a is None else (list(a) if isinstance(a, (list, tuple)) else [a])
+    ads = [as_list(adapter1), as_list(adapter2)]
+    keep, arrs = [], []
+    for lst in ads:
+        pairs = [a.descriptor() for a in lst]
+        keep.append(pairs)
+        arrs.append((_abi.AtrAdapterDesc * max(1, len(pairs)))(*[d for d, _ in pairs]))
+    if insert_aligner is not None:
+        idesc, k3 = insert_aligner.descriptor(max_len)
+        iref = C.byref(idesc)
+        max_errors = max(len(a.sequence) for a in ads[0] + ads[1])
+    else:
+        iref = None
+        max_errors = max([int(a.max_error_rate * len(a.sequence)) for a in ads[0] + ads[1]] or [0])
+    stats = fastq.PairTrimStats(max_len, max_errors, (len(ads[0]), len(ads[1])))
+    opts = _abi.AtrTrimPeOpts(int(symmetric), min_insert_overlap, max_len, max_errors, int(bool(final)), times, 0,
                               _abi.make_read_ops(**read_ops))
     oc = SimOpsCounters()
     o1 = np.empty(max(len(text1), 1), dtype=np.uint8)
@@ -140,7 +152,8 @@ def trim_fastq_pe(text1, text2, adapter1, adapter2, insert_aligner, symmetric=Tr
     counters = np.zeros(9, dtype=np.int64)
     nout, consumed = (C.c_longlong * 2)(), (C.c_longlong * 2)()
     err = _abi.AtrFastqError()
-    rc = lib().sim_trim_fastq_pe(C.byref(idesc), C.byref(d1), C.byref(d2), C.byref(opts), text1, len(text1), text2, len(text2),
+    rc = lib().sim_trim_fastq_pe(iref, arrs[0], len(ads[0]), arrs[1], len(ads[1]), stats.errors_front[0].ctypes.data,
+                                 stats.errors_front[1].ctypes.data, C.byref(opts), text1, len(text1), text2, len(text2),
                                  o1.ctypes.data, o2.ctypes.data, nout, consumed, counters.ctypes.data,
                                  stats.errors_back[0].ctypes.data, stats.errors_back[1].ctypes.data,
                                  stats.adjacent[0].ctypes.data, stats.adjacent[1].ctypes.data, C.byref(err), C.byref(oc))
