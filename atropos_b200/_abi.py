@@ -6,7 +6,9 @@ import numpy as np
 ATR_ABI_VERSION = 1
 ATR_OK, ATR_E_ARG, ATR_E_CUDA, ATR_E_NOMEM, ATR_E_LIMIT, ATR_E_FORMAT = 0, -1, -2, -3, -4, -5
 (ATR_FQ_OK, ATR_FQ_NO_AT, ATR_FQ_NO_PLUS, ATR_FQ_NAME_MISMATCH, ATR_FQ_LENGTH, ATR_FQ_TRUNCATED, ATR_FQ_BARE_CR,
- ATR_FQ_TOO_LONG, ATR_FQ_INVALID_MATCH, ATR_FQ_MORE_IN_1, ATR_FQ_MORE_IN_2, ATR_FQ_PAIR_NAMES, ATR_FQ_EMPTY_NAME) = range(13)
+ ATR_FQ_TOO_LONG, ATR_FQ_INVALID_MATCH, ATR_FQ_MORE_IN_1, ATR_FQ_MORE_IN_2, ATR_FQ_PAIR_NAMES, ATR_FQ_EMPTY_NAME,
+ ATR_FQ_CORRECTION) = range(14)
+MISMATCH_ACTIONS = {None: 0, "liberal": 1, "conservative": 2, "N": 3}
 ATR_ST_NONE, ATR_ST_MATCH, ATR_ST_ESCAPED, ATR_ST_INVALID, ATR_ST_KEYERROR = 0, 1, 2, 3, 4
 
 
@@ -105,7 +107,8 @@ class AtrTrimStats(C.Structure):
 
 class AtrTrimPeOpts(C.Structure):
     _fields_ = [("symmetric", C.c_int32), ("min_insert_overlap", C.c_int32), ("max_len", C.c_int32),
-                ("max_errors", C.c_int32), ("final_chunk", C.c_int32), ("times", C.c_int32), ("chunk_bytes", C.c_int64),
+                ("max_errors", C.c_int32), ("final_chunk", C.c_int32), ("times", C.c_int32), ("mismatch_action", C.c_int32), ("pad", C.c_int32),
+                ("chunk_bytes", C.c_int64),
                 ("ops", AtrReadOps)]
 
 
@@ -113,7 +116,7 @@ class AtrTrimPeStats(C.Structure):
     _fields_ = [("records", C.c_int64), ("insert_matches", C.c_int64), ("with_adapters", C.c_int64 * 2),
                 ("bp_in", C.c_int64 * 2), ("bp_out", C.c_int64 * 2), ("overflow", C.c_int64),
                 ("errors_back", C.c_void_p * 2), ("adjacent_bases", C.c_void_p * 2), ("errors_front", C.c_void_p * 2),
-                ("ops", AtrReadOpsStats)]
+                ("records_corrected", C.c_int64), ("bp_corrected", C.c_int64 * 2), ("ops", AtrReadOpsStats)]
 
 
 def make_adapter_desc(sequence, max_error_rate, flags, wildcard_ref=False, wildcard_query=False, min_overlap=1,

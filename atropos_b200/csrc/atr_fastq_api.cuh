@@ -600,6 +600,8 @@ extern "C" int atr_trim_fastq_pe_host(atr_ctx* ctx, const atr_insertset* iset, c
     if ((set1 && set1->ctx != ctx) || (set2 && set2->ctx != ctx) || (iset && iset->ctx != ctx))
         return fail(ctx, ATR_E_ARG, "adapter / insert set belongs to another context");
     if (!iset && opts->times < 1) return fail(ctx, ATR_E_ARG, "atr_trim_pe_opts.times must be >= 1 in adapter mode");
+    if (opts->mismatch_action < 0 || opts->mismatch_action > 3 || (opts->mismatch_action && !iset))
+        return fail(ctx, ATR_E_ARG, "mismatch_action is 0..3 and needs the insert aligner");
     if (opts->max_len < 0 || opts->max_len > ATR_MAX_READ || opts->max_errors < 0 || opts->max_errors > 4095 || opts->min_insert_overlap < 0)
         return fail(ctx, ATR_E_ARG, "bad atr_trim_pe_opts");
     const atr_adapterset* sets[2] = {set1, set2};
@@ -819,6 +821,13 @@ extern "C" int atr_trim_fastq_pe_host(atr_ctx* ctx, const atr_insertset* iset, c
         err->kind = ATR_FQ_INVALID_MATCH; err->record = -1;
         return fail(ctx, ATR_E_FORMAT, "a pair for which the reference raises (Match with length <= errors, or a byte reverse_complement rejects)");
     }
+    if (hc->correction_errors) {
+        err->kind = ATR_FQ_CORRECTION; err->record = -1;
+        return fail(ctx, ATR_E_FORMAT, "error correction would raise in the reference (reads of unequal length or bytes outside the complement table)");
+    }
+    stats->records_corrected += (int64_t)hc->records_corrected;
+    stats->bp_corrected[0] += (int64_t)hc->bp_corrected[0];
+    stats->bp_corrected[1] += (int64_t)hc->bp_corrected[1];
     stats->records += (int64_t)hc->records;
     stats->insert_matches += (int64_t)hc->insert_matches;
     stats->overflow += (int64_t)hc->overflow;

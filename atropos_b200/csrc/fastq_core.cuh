@@ -198,23 +198,42 @@ ATR_HD void fq_pe_symmetric(const PeMatch& src, int read_len, PeMatch& dst) {
     if (dst.rstop < read_len) { dst.astop -= (read_len - dst.rstop); dst.rstop = read_len; }
 }
 
+// correct / im: whether ErrorCorrectorMixin.correct_errors runs for this pair and with which insert_match[0..3]
+// (mismatch_action set: :399-400 an insert match with mismatches; :407-414 complementary adapter matches; :439-446
+// after the symmetric duplication)
 ATR_HD void fq_pe_decide(const atr_insert_result& ins, const atr_match& fb1, const atr_match& fb2, int len1, int len2,
-                         int min_insert_len, int symmetric, PeMatch& m1, PeMatch& m2, int& insert_hit, int& invalid) {
+                         int min_insert_len, int symmetric, int action, PeMatch& m1, PeMatch& m2, int& insert_hit, int& invalid,
+                         bool& correct, int* im) {
     m1.present = m2.present = 0; m1.rstart = m1.rstop = m1.astop = m1.errors = 0; m2 = m1;
     insert_hit = 0;
+    correct = false;
+    bool have_im = false;
+    im[0] = im[1] = im[2] = im[3] = 0;
     if (len1 < min_insert_len || len2 < min_insert_len) return;          // :392-394
     if (ins.insert.status == ATR_ST_INVALID || ins.insert.status == ATR_ST_KEYERROR) invalid = 1;
     if (ins.insert.status == ATR_ST_MATCH) {
         insert_hit = 1;
         fq_pe_load(ins.match1, m1, invalid);
         fq_pe_load(ins.match2, m2, invalid);
+        have_im = true;
+        im[0] = ins.insert.astart; im[1] = ins.insert.astop; im[2] = ins.insert.rstart; im[3] = ins.insert.rstop;
+        correct = action != 0 && ins.insert.errors > 0;
     } else {
         fq_pe_load(fb1, m1, invalid);
         fq_pe_load(fb2, m2, invalid);
+        if (action != 0 && m1.present && m2.present && m1.rstart == m2.rstart) {
+            im[0] = len2 - m1.rstart; im[1] = len2; im[2] = 0; im[3] = m1.rstart;
+            have_im = true;
+            correct = true;
+        }
     }
     if (symmetric && (m1.present + m2.present) == 1) {                    // :417-437
         if (m1.present) fq_pe_symmetric(m1, len2, m2);
         else fq_pe_symmetric(m2, len1, m1);
+        if (action != 0 && !have_im && m1.present && m2.present) {
+            im[0] = len2 - m1.rstart; im[1] = len2; im[2] = 0; im[3] = m1.rstart;
+            correct = true;
+        }
     }
 }
 
@@ -329,4 +348,79 @@ ATR_HD int fq_filter(const atr_read_ops& o, const unsigned char* __restrict__ se
         if (paired && !o.legacy_first && fq_filter_one(o, seq2, lo2, hi2, matched2, which)) return which;
     }
     return 0;
+}
+
+// ---- ErrorCorrectorMixin.correct_errors(read1, read2, insert_match, truncate_seqs=True) ---------------------------
+// (commands/trim/modifiers.py:219-350), in place on the two reads' bases and qualities. im = insert_match[0..3].
+// action: 1 liberal, 2 conservative, 3 'N'; min_qual_difference is the constructor default 1 (:212-216).
+// Python semantics kept where the reference leans on them: list indices may be negative (wrap), slices clamp.
+// Returns false where the reference would raise; changed1 / changed2 = bases changed; new_len1 = read 1's length
+// afterwards (the reference re-assembles a changed read 1 from the TRUNCATED list when it is the longer read, :328-336
+// with len1 never updated by :260-269).
+ATR_HD bool fq_py_index(int& i, int L) { if (i < 0) i += L; return i >= 0 && i < L; }
+ATR_HD void fq_py_slice(int& a, int& b, int L) {
+    if (a < 0) { a += L; if (a < 0) a = 0; } else if (a > L) a = L;
+    if (b < 0) { b += L; if (b < 0) b = 0; } else if (b > L) b = L;
+    if (b < a) b = a;
+}
+
+ATR_HD bool fq_pe_correct(unsigned char* s1, unsigned char* q1, int len1_full, unsigned char* s2, unsigned char* q2, int len2_full,
+                          int im0, int im1, int im2, int im3, int action, const unsigned char* __restrict__ comp,
+                          int& changed1, int& changed2, int& new_len1) {
+    changed1 = changed2 = 0;
+    new_len1 = len1_full;
+    int L1 = len1_full, L2 = len2_full, len2 = len2_full;
+    if (len1_full > len2_full) L1 = len2_full;
+    else if (len2_full > len1_full) { L2 = len1_full; len2 = len1_full; }
+    const int r1_start = im2, r1_end = im3, r2_start = len2 - im1, r2_end = len2 - im0;
+    int n1 = r1_end - r1_start, n2 = r2_end - r2_start;
+    if (n1 < 0) n1 = 0;
+    if (n2 < 0) n2 = 0;
+    const int npairs = n1 < n2 ? n1 : n2;
+    const int mqd = 1;
+    int n_equal = 0;
+    for (int pass = 0; pass < 2; pass++) {
+        int toward = 0;                                  // pass 1 (liberal ties): 1 = read 1 is better, 2 = read 2 is better
+        if (pass == 1) {
+            if (n_equal == 0) break;
+            int a1 = r1_start, b1 = r1_end, a2 = r2_start, b2 = r2_end;
+            fq_py_slice(a1, b1, L1);
+            fq_py_slice(a2, b2, L2);
+            if (b1 == a1 || b2 == a2) return false;      // mean() of an empty sequence raises
+            long long sum1 = 0, sum2 = 0;
+            for (int i = a1; i < b1; i++) sum1 += q1[i];
+            for (int j = a2; j < b2; j++) sum2 += q2[j];
+            const double diff = (double)sum1 / (double)(b1 - a1) - (double)sum2 / (double)(b2 - a2);
+            if (diff > 1) toward = 1; else if (diff < -1) toward = 2; else break;
+        }
+        for (int t = 0; t < npairs; t++) {
+            int i = r1_start + t, j = r2_end - 1 - t;
+            if (!fq_py_index(i, L1) || !fq_py_index(j, L2)) return false;
+            const unsigned char base1 = s1[i];
+            const unsigned char base2 = comp[s2[j]];
+            if (base2 == 0) return false;                // KeyError
+            if (base1 == base2) continue;
+            if (pass == 0) {
+                if (action == 3) { s1[i] = 'N'; s2[j] = 'N'; changed1++; changed2++; }
+                else if (base1 == 'N') { s1[i] = base2; q1[i] = q2[j]; changed1++; }
+                else if (base2 == 'N') { const unsigned char c = comp[base1]; if (c == 0) return false; s2[j] = c; q2[j] = q1[i]; changed2++; }
+                else {
+                    const int diff = (int)q1[i] - (int)q2[j];
+                    if (diff >= mqd) { const unsigned char c = comp[base1]; if (c == 0) return false; s2[j] = c; q2[j] = q1[i]; changed2++; }
+                    else if (diff <= -mqd) { s1[i] = base2; q1[i] = q2[j]; changed1++; }
+                    else if (action == 1) n_equal++;
+                }
+            } else {
+                // the ties left by pass 0: still mismatching, neither base N, qualities within the margin
+                if (base1 == 'N' || base2 == 'N') continue;
+                const int diff = (int)q1[i] - (int)q2[j];
+                if (diff >= mqd || diff <= -mqd) continue;
+                if (toward == 1) { const unsigned char c = comp[base1]; if (c == 0) return false; s2[j] = c; q2[j] = q1[i]; changed2++; }
+                else { s1[i] = base2; q1[i] = q2[j]; changed1++; }
+            }
+        }
+        if (action != 1) break;
+    }
+    if (changed1 && len1_full > len2_full) new_len1 = len2_full;
+    return true;
 }

@@ -341,6 +341,7 @@ __global__ void __launch_bounds__(256) k_fq_format(const unsigned char* __restri
 // ---- paired-end ------------------------------------------------------------------------------------------------
 struct FqPeCounters {
     unsigned long long records, insert_matches, with_adapters[2], bp_in[2], bp_out[2], overflow, invalid;
+    unsigned long long records_corrected, bp_corrected[2], correction_errors;
 };
 
 // sequence_names_match for every pair (io/seqio.py:448-452, :773-791)
@@ -366,24 +367,36 @@ __global__ void __launch_bounds__(256) k_pe_prepare(const atr_insert_result* __r
 }
 
 // InsertAdapterCutter.__call__ after the alignments + trim() + the adapters' statistics, one thread per pair
-__global__ void __launch_bounds__(256) k_pe_apply(const unsigned char* __restrict__ t1, const FqRec* __restrict__ r1,
-                                                  const unsigned char* __restrict__ t2, const FqRec* __restrict__ r2,
+__global__ void __launch_bounds__(256) k_pe_apply(unsigned char* __restrict__ t1, const FqRec* __restrict__ r1,
+                                                  unsigned char* __restrict__ t2, const FqRec* __restrict__ r2,
                                                   const atr_insert_result* __restrict__ ins, const atr_match* __restrict__ fb1,
                                                   const atr_match* __restrict__ fb2, long long n, int symmetric, int min_insert_len,
                                                   int max_len, int max_errors, uint16_t* __restrict__ fwin1, uint16_t* __restrict__ fwin2,
                                                   unsigned long long* __restrict__ hist1, unsigned long long* __restrict__ hist2,
                                                   unsigned long long* __restrict__ adj1, unsigned long long* __restrict__ adj2,
                                                   FqPeCounters* __restrict__ ctr, const __grid_constant__ atr_read_ops ops,
-                                                  FqOpsCounters* __restrict__ oc) {
+                                                  FqOpsCounters* __restrict__ oc, int mismatch_action,
+                                                  const unsigned char* __restrict__ comp) {
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n) return;
     const FqRec A = r1[r], B = r2[r];
-    const int len1 = A.seq_len, len2 = B.seq_len;
+    int len1 = A.seq_len;
+    const int len2 = B.seq_len;
     PeMatch m1, m2;
-    int hit = 0, invalid = 0;
-    fq_pe_decide(ins[r], fb1[r], fb2[r], len1, len2, min_insert_len, symmetric, m1, m2, hit, invalid);
+    int hit = 0, invalid = 0, im[4];
+    bool correct = false;
+    fq_pe_decide(ins[r], fb1[r], fb2[r], len1, len2, min_insert_len, symmetric, mismatch_action, m1, m2, hit, invalid, correct, im);
     if (invalid) atomicAdd(&ctr->invalid, 1ull);
     if (hit) atomicAdd(&ctr->insert_matches, 1ull);
+    if (correct) {                                     // error correction edits this chunk's copy of the text in place
+        int c1 = 0, c2 = 0, nl1 = len1;
+        if (!fq_pe_correct(t1 + A.seq_b, t1 + A.qual_b, len1, t2 + B.seq_b, t2 + B.qual_b, len2, im[0], im[1], im[2], im[3],
+                           mismatch_action, comp, c1, c2, nl1)) atomicAdd(&ctr->correction_errors, 1ull);
+        if (c1 || c2) atomicAdd(&ctr->records_corrected, 1ull);
+        if (c1) atomicAdd(&ctr->bp_corrected[0], (unsigned long long)c1);
+        if (c2) atomicAdd(&ctr->bp_corrected[1], (unsigned long long)c2);
+        len1 = nl1;
+    }
     FqApply ap;
     bool counted;
     const int k1 = fq_pe_trim(m1, len1, t1 + A.seq_b, ap, counted);

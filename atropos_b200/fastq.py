@@ -110,6 +110,8 @@ def format_error_message(text, err):
         return "Reads are improperly paired. There are more reads in file 1 than in file 2."
     if kind == _abi.ATR_FQ_MORE_IN_2:
         return "Reads are improperly paired. There are more reads in file 2 than in file 1."
+    if kind == _abi.ATR_FQ_CORRECTION:
+        return "error correction would raise in the reference (reads of unequal length or bytes outside the complement table)"
     if kind == _abi.ATR_FQ_EMPTY_NAME:
         return "a read name without any token (the reference raises IndexError in sequence_names_match)"
 
@@ -264,11 +266,14 @@ class PairTrimStats(object):
         self.adjacent = [np.zeros((self.n_adapters[i], 5), dtype=np.int64) for i in range(2)]
         self.records = self.insert_matches = self.overflow = 0
         self.with_adapters, self.bp_in, self.bp_out = [0, 0], [0, 0], [0, 0]
+        self.records_corrected, self.bp_corrected = 0, [0, 0]      # ErrorCorrectorMixin.summarize (modifiers.py:352-357)
         self.ops = new_ops_stats()
 
     def merge(self, other):
         merge_ops_stats(self.ops, other.ops)
+        self.records_corrected += other.records_corrected
         for i in range(2):
+            self.bp_corrected[i] += other.bp_corrected[i]
             self.errors_back[i] += other.errors_back[i]
             self.errors_front[i] += other.errors_front[i]
             self.adjacent[i] += other.adjacent[i]
@@ -304,8 +309,9 @@ class FastqPairTrimmer(object):
     insert_aligner: atropos_b200.align.InsertAligner with the same sequences."""
 
     def __init__(self, adapter1, adapter2, insert_aligner=None, symmetric=True, min_insert_overlap=1, max_len=256, device=0,
-                 chunk_bytes=0, times=1, **read_ops):
-        """insert_aligner given: `--aligner insert` (adapter1 / adapter2 = the one 3' adapter of each read).
+                 chunk_bytes=0, times=1, mismatch_action=None, **read_ops):
+        """mismatch_action: --correct-mismatches ('liberal', 'conservative', 'N'; insert mode only).
+        insert_aligner given: `--aligner insert` (adapter1 / adapter2 = the one 3' adapter of each read).
         insert_aligner None: the command's default `--aligner adapter`: adapter1 / adapter2 are lists of Adapters (or
         None) for read 1 / read 2, cut independently with `times` rounds each (commands/trim/__init__.py:457-476)."""
         self.ops = _abi.make_read_ops(**read_ops)
@@ -319,6 +325,9 @@ class FastqPairTrimmer(object):
         self.adapter1 = self.adapters[0][0] if self.adapters[0] else None
         self.adapter2 = self.adapters[1][0] if self.adapters[1] else None
         self.symmetric, self.min_insert_overlap, self.times = bool(symmetric), int(min_insert_overlap), int(times)
+        self.mismatch_action = _abi.MISMATCH_ACTIONS[mismatch_action]
+        if self.mismatch_action and insert_aligner is None:
+            raise ValueError("error correction needs the insert aligner")
         self.max_len = int(max_len)
         every = self.adapters[0] + self.adapters[1]
         if insert_aligner is not None:
@@ -344,7 +353,7 @@ class FastqPairTrimmer(object):
         if stats is None:
             stats = self.new_stats()
         opts = _abi.AtrTrimPeOpts(int(self.symmetric), self.min_insert_overlap, self.max_len, self.max_errors,
-                                  int(bool(final)), self.times, self.chunk_bytes, self.ops)
+                                  int(bool(final)), self.times, self.mismatch_action, 0, self.chunk_bytes, self.ops)
         st = _abi.AtrTrimPeStats()
         for i in range(2):
             st.errors_back[i] = stats.errors_back[i].ctypes.data
@@ -365,7 +374,9 @@ class FastqPairTrimmer(object):
         stats.records += int(st.records)
         stats.insert_matches += int(st.insert_matches)
         stats.overflow += int(st.overflow)
+        stats.records_corrected += int(st.records_corrected)
         for i in range(2):
+            stats.bp_corrected[i] += int(st.bp_corrected[i])
             stats.with_adapters[i] += int(st.with_adapters[i])
             stats.bp_in[i] += int(st.bp_in[i])
             stats.bp_out[i] += int(st.bp_out[i])

@@ -233,6 +233,8 @@ int  atr_multi_locate(atr_ctx* ctx, const char* reference, int32_t m, const char
 #define ATR_FQ_MORE_IN_2    10   /* "... more reads in file 2 than in file 1." (:436-440) */
 #define ATR_FQ_PAIR_NAMES   11   /* "Read name '..' in file 1 does not match '..' in file 2." (:448-452, sequence_names_match :773-791) */
 #define ATR_FQ_EMPTY_NAME   12   /* a read name without any token: the reference dies with an IndexError in sequence_names_match */
+#define ATR_FQ_CORRECTION   13   /* error correction would raise in the reference (IndexError / KeyError / ValueError on reads of
+                                    unequal length or bytes outside the complement table) */
 
 typedef struct atr_fastq_error {
     int32_t kind;             /* ATR_FQ_* of the FIRST error in file order */
@@ -321,6 +323,9 @@ typedef struct atr_trim_pe_opts {
     int32_t max_errors;
     int32_t final_chunk;        /* 1: both texts end their files */
     int32_t times;              /* adapter mode (iset == NULL): AdapterCutter(times) of both reads, >= 1 */
+    int32_t mismatch_action;    /* insert mode, --correct-mismatches: 0 off, 1 liberal, 2 conservative, 3 N (ErrorCorrectorMixin,
+                                   commands/trim/modifiers.py:201-357) */
+    int32_t pad;
     int64_t chunk_bytes;        /* per text; 0 = default (32 MiB) */
     atr_read_ops ops;
 } atr_trim_pe_opts;
@@ -332,6 +337,7 @@ typedef struct atr_trim_pe_stats {
     int64_t* errors_back[2];                  /* per read: [n_adapters of that read][max_len+1][max_errors+1], ADDED to */
     int64_t* adjacent_bases[2];               /* per read: [n_adapters][5] */
     int64_t* errors_front[2];                 /* adapter mode only (may be NULL): same shape as errors_back */
+    int64_t records_corrected, bp_corrected[2];   /* ErrorCorrectorMixin.summarize (modifiers.py:352-357) */
     atr_read_ops_stats ops;
 } atr_trim_pe_stats;
 

@@ -93,6 +93,9 @@ def pe_check(case, outs, stats):
     assert list(stats.with_adapters) == [w or 0 for w in res["with_adapters"]]
     assert list(stats.bp_in) == res["bp_in"] and list(stats.bp_out) == res["bp_out"]
     assert stats.overflow == 0
+    if res.get("corrected"):
+        assert stats.records_corrected == res["corrected"]["records_corrected"]
+        assert list(stats.bp_corrected) == res["corrected"]["bp_corrected"]
     for i, gold in enumerate(res["adapters"]):
         per_adapter = gold if isinstance(gold, list) else [gold]          # adapter mode: several adapters per read
         for a, g in enumerate(per_adapter):

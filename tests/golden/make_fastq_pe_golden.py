@@ -107,6 +107,7 @@ def run_reference(text1, text2, error_rate, extra=(), adapter_args=None):
             except FormatError as exc:
                 return {"error": str(exc)}
             return {"exception": "trim returned %r but the reader raised nothing" % (rc,)}
+        corrected = None
         outs = []
         for key in ("out1.fq", "out2.fq"):
             with open(p[key], "r", newline="") as fh:
@@ -117,10 +118,12 @@ def run_reference(text1, text2, error_rate, extra=(), adapter_args=None):
         if adapter_args is None:
             cutter = rj["trim"]["modifiers"]["InsertAdapterCutter"]
             ads = [adapter_stats(list(d.values())[0]) for d in cutter["adapters"]]
+            if "records_corrected" in cutter:
+                corrected = {"records_corrected": cutter["records_corrected"], "bp_corrected": cutter["bp_corrected"]}
         else:                                          # two AdapterCutters: per read a dict name -> statistics
             cutter = rj["trim"]["modifiers"]["AdapterCutter"]
             ads = [[adapter_stats(st) for st in (d or {}).values()] for d in cutter["adapters"]]
-        return {"ops": ops_stats(rj), "out1": outs[0], "out2": outs[1], "records": rj["record_counts"].get("0", 0),
+        return {"ops": ops_stats(rj), "corrected": corrected, "out1": outs[0], "out2": outs[1], "records": rj["record_counts"].get("0", 0),
                 "with_adapters": cutter["records_with_adapters"], "bp_in": rj["bp_counts"].get("0", [0, 0]),
                 "bp_out": rj["trim"]["formatters"]["bp_written"], "adapters": ads}
     finally:
@@ -133,7 +136,9 @@ def main():
     rng = np.random.default_rng(9101)
     cases = []
 
-    def add(label, recs, error_rate=0.1, edit=None, extra=(), read_ops=None, adapter_args=None, times=1):
+    def add(label, recs, error_rate=0.1, edit=None, extra=(), read_ops=None, adapter_args=None, times=1, mismatch_action=None):
+        if mismatch_action:
+            extra = list(extra) + ["--correct-mismatches", mismatch_action]
         t1, t2 = fastq(recs[0]), fastq(recs[1])
         if edit:
             t1, t2 = edit(t1, t2)
@@ -141,7 +146,8 @@ def main():
         print(label, {k: (v if not isinstance(v, (str, list)) else (len(v) if isinstance(v, str) else v if len(v) < 3 else len(v)))
                       for k, v in res.items()})
         cases.append({"label": label, "text1": t1, "text2": t2, "error_rate": error_rate, "read_ops": read_ops or {},
-                      "mode": "insert" if adapter_args is None else "adapter", "times": times, "result": res})
+                      "mode": "insert" if adapter_args is None else "adapter", "times": times,
+                      "mismatch_action": mismatch_action, "result": res})
 
     add("pe150", make_pairs(rng, 500, seed=11))
     add("pe150_suffix_names", make_pairs(rng, 300, suffix=True, seed=12))
@@ -177,6 +183,23 @@ def main():
         extra=["-q", "10", "--trim-n", "-m", "20"], read_ops=dict(quality_cutoff=[10], trim_n=True, minimum_length=20))
     r = make_pairs(rng, 300, seed=26)
     add("adapter_mode_read1_only", r, adapter_args=["-a", A1], extra=["--discard-untrimmed"], read_ops=dict(discard_untrimmed=True, legacy_first=True))
+
+    # --- --correct-mismatches (ErrorCorrectorMixin, modifiers.py:201-357): equal-length reads with mismatching overlaps ----
+    def noisy(recs):
+        out = []
+        for name, seq, name2, q in recs:
+            L = len(seq)
+            q = "".join(chr(33 + int(max(2, min(40, rng.normal(30, 8))))) for _ in range(L))
+            seq = "".join(("N" if rng.random() < 0.01 else c) for c in seq)
+            out.append((name, seq, name2, q))
+        return out
+    for act, seed in (("liberal", 27), ("conservative", 28), ("N", 29)):
+        r1_, r2_ = synth.synth_pe(300, 150, seed=seed, device="cpu", sub=0.03)
+        recs = make_pairs(rng, 300, seed=seed)
+        recs = ([(n_, bytes(r1_[i].numpy()).decode(), n2_, q_) for i, (n_, s_, n2_, q_) in enumerate(recs[0])],
+                [(n_, bytes(r2_[i].numpy()).decode(), n2_, q_) for i, (n_, s_, n2_, q_) in enumerate(recs[1])])
+        add("correct_" + act.lower(), (noisy(recs[0]), noisy(recs[1])), mismatch_action=act,
+            extra=["--trim-n", "-m", "20"], read_ops=dict(trim_n=True, minimum_length=20))
 
     # --- improper pairing / malformed input --------------------------------------------------------------------
     def drop_last(which):

@@ -250,7 +250,13 @@ int sim_trim_fastq_pe(const atr_insert_desc* idesc, const atr_adapter_desc* d1, 
                       const atr_trim_pe_opts* o, const unsigned char* text1, long long nbytes1, const unsigned char* text2,
                       long long nbytes2, unsigned char* out1, unsigned char* out2, long long* out_bytes, long long* consumed,
                       long long* counters, long long* eb1, long long* eb2, long long* adj1, long long* adj2, atr_fastq_error* err,
-                      FqOpsCounters* oc) {
+                      FqOpsCounters* oc, long long* corrected /* {records, bp1, bp2} */) {
+    // error correction edits the reads in place: work on private copies of the texts, like the GPU path on its chunk
+    std::vector<unsigned char> copy1(text1, text1 + nbytes1), copy2(text2, text2 + nbytes2);
+    copy1.push_back(0); copy2.push_back(0);
+    unsigned char* const mtext1 = copy1.data();
+    unsigned char* const mtext2 = copy2.data();
+    text1 = mtext1; text2 = mtext2;
     SimText T[2];
     T[0].text = text1; T[0].nbytes = nbytes1; T[1].text = text2; T[1].nbytes = nbytes2;
     for (int f = 0; f < 2; f++) if (!T[f].index(o->final_chunk)) { err->kind = ATR_FQ_BARE_CR; err->file = f; err->record = -1; return ATR_E_FORMAT; }
@@ -301,7 +307,8 @@ int sim_trim_fastq_pe(const atr_insert_desc* idesc, const atr_adapter_desc* d1, 
         oc->bp_cut[0] += bpc; oc->bp_quality[0] += bpq;
         fq_pre_ops(o->ops, 1, text2, B, bpc, bpq);
         oc->bp_cut[1] += bpc; oc->bp_quality[1] += bpq;
-        const int len1 = A.seq_len, len2 = B.seq_len;
+        int len1 = A.seq_len;
+        const int len2 = B.seq_len;
         int k1 = len1, k2 = len2;
         PeMatch m1, m2;
         m1.present = m2.present = 0;
@@ -320,10 +327,24 @@ int sim_trim_fastq_pe(const atr_insert_desc* idesc, const atr_adapter_desc* d1, 
                     if (rc) return rc;
                 }
             }
-            int hit = 0, invalid = 0;
-            fq_pe_decide(ins, fb1, fb2, len1, len2, o->min_insert_overlap, o->symmetric, m1, m2, hit, invalid);
+            int hit = 0, invalid = 0, im[4];
+            bool correct = false;
+            fq_pe_decide(ins, fb1, fb2, len1, len2, o->min_insert_overlap, o->symmetric, o->mismatch_action, m1, m2, hit, invalid, correct, im);
             if (invalid) { err->kind = ATR_FQ_INVALID_MATCH; err->record = r; return ATR_E_FORMAT; }
             counters[1] += hit;
+            if (correct) {
+                atr::HostInsert hi;
+                std::string msg;
+                AtrTables tb;
+                atr::build_tables(tb);
+                if (atr::prepare_insert(*idesc, tb, hi, msg)) return -200;
+                int c1 = 0, c2 = 0, nl1 = len1;
+                if (!fq_pe_correct(mtext1 + A.seq_b, mtext1 + A.qual_b, len1, mtext2 + B.seq_b, mtext2 + B.qual_b, len2, im[0], im[1], im[2],
+                                   im[3], o->mismatch_action, hi.comp.data(), c1, c2, nl1)) { err->kind = ATR_FQ_CORRECTION; err->record = r; return ATR_E_FORMAT; }
+                if (c1 || c2) corrected[0]++;
+                corrected[1] += c1; corrected[2] += c2;
+                len1 = nl1;
+            }
             FqApply ap;
             bool counted;
             k1 = fq_pe_trim(m1, len1, text1 + A.seq_b, ap, counted);

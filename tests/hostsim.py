@@ -44,7 +44,7 @@ def lib():
                                         C.c_longlong, C.c_char_p, C.c_longlong, C.c_void_p, C.c_void_p,
                                         C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_abi.AtrFastqError),
-                                        C.POINTER(SimOpsCounters)]
+                                        C.POINTER(SimOpsCounters), C.POINTER(C.c_longlong)]
         L.sim_trim_fastq_pe.restype = C.c_int
         _lib = L
     return _lib
@@ -124,7 +124,7 @@ def trim_fastq(text, adapters, times=1, max_len=512, final=True, **read_ops):
 
 
 def trim_fastq_pe(text1, text2, adapter1, adapter2, insert_aligner=None, symmetric=True, min_insert_overlap=1, max_len=256,
-                  final=True, times=1, **read_ops):
+                  final=True, times=1, mismatch_action=None, **read_ops):
     """CPU run of the paired-end FASTQ path's device functions (insert mode, or adapter mode when insert_aligner is
     None and adapter1 / adapter2 are lists). Returns ((out1, out2), PairTrimStats, consumed)."""
     import numpy as np
@@ -144,8 +144,9 @@ def trim_fastq_pe(text1, text2, adapter1, adapter2, insert_aligner=None, symmetr
         iref = None
         max_errors = max([int(a.max_error_rate * len(a.sequence)) for a in ads[0] + ads[1]] or [0])
     stats = fastq.PairTrimStats(max_len, max_errors, (len(ads[0]), len(ads[1])))
-    opts = _abi.AtrTrimPeOpts(int(symmetric), min_insert_overlap, max_len, max_errors, int(bool(final)), times, 0,
-                              _abi.make_read_ops(**read_ops))
+    opts = _abi.AtrTrimPeOpts(int(symmetric), min_insert_overlap, max_len, max_errors, int(bool(final)), times,
+                              _abi.MISMATCH_ACTIONS[mismatch_action], 0, 0, _abi.make_read_ops(**read_ops))
+    corrected = (C.c_longlong * 3)()
     oc = SimOpsCounters()
     o1 = np.empty(max(len(text1), 1), dtype=np.uint8)
     o2 = np.empty(max(len(text2), 1), dtype=np.uint8)
@@ -156,7 +157,7 @@ def trim_fastq_pe(text1, text2, adapter1, adapter2, insert_aligner=None, symmetr
                                  stats.errors_front[1].ctypes.data, C.byref(opts), text1, len(text1), text2, len(text2),
                                  o1.ctypes.data, o2.ctypes.data, nout, consumed, counters.ctypes.data,
                                  stats.errors_back[0].ctypes.data, stats.errors_back[1].ctypes.data,
-                                 stats.adjacent[0].ctypes.data, stats.adjacent[1].ctypes.data, C.byref(err), C.byref(oc))
+                                 stats.adjacent[0].ctypes.data, stats.adjacent[1].ctypes.data, C.byref(err), C.byref(oc), corrected)
     if rc == _abi.ATR_E_FORMAT:
         raise fastq.FormatError(fastq.format_error_message((np.frombuffer(text1, dtype=np.uint8),
                                                             np.frombuffer(text2, dtype=np.uint8)), err))
@@ -166,4 +167,5 @@ def trim_fastq_pe(text1, text2, adapter1, adapter2, insert_aligner=None, symmetr
     c = [int(x) for x in counters]
     stats.records, stats.insert_matches, stats.overflow = c[0], c[1], c[8]
     stats.with_adapters, stats.bp_in, stats.bp_out = [c[2], c[3]], [c[4], c[5]], [c[6], c[7]]
+    stats.records_corrected, stats.bp_corrected = int(corrected[0]), [int(corrected[1]), int(corrected[2])]
     return (bytes(o1[:nout[0]]), bytes(o2[:nout[1]])), stats, (consumed[0], consumed[1])

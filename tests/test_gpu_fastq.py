@@ -83,7 +83,7 @@ def test_pe_against_reference_cli(case, chunk):
     a1, a2, ia = fastq_cases.pe_objects(case)
     t1, t2 = case["text1"].encode("latin-1"), case["text2"].encode("latin-1")
     res = case["result"]
-    tr = fastq.FastqPairTrimmer(a1, a2, ia, chunk_bytes=chunk, times=case.get("times", 1), **case.get("read_ops", {}))
+    tr = fastq.FastqPairTrimmer(a1, a2, ia, chunk_bytes=chunk, times=case.get("times", 1), mismatch_action=case.get("mismatch_action"), **case.get("read_ops", {}))
     if "error" in res:
         with pytest.raises(fastq.FormatError) as ei:
             tr.trim(t1, t2)
