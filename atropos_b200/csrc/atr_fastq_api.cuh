@@ -523,7 +523,7 @@ int pe_back(atr_ctx* ctx, Slot& s, const PeStep& P, const atr_insertset* iset, c
                                                      s.fq[0].fwin.as<uint16_t>(), s.fq[1].fwin.as<uint16_t>(),
                                                      (unsigned long long*)(d_stats + L.o_hist[0]), (unsigned long long*)(d_stats + L.o_hist[1]),
                                                      (unsigned long long*)(d_stats + L.o_adj[0]), (unsigned long long*)(d_stats + L.o_adj[1]), d_ctr,
-                                                     o->ops, d_ops);
+                                                     o->ops, d_ops, o->mismatch_action, iset->dev.comp);
         LAUNCHED(ctx);
     } else {
         // "--aligner adapter": two independent AdapterCutters (the single-end adapter stage per read), then the pair filters
