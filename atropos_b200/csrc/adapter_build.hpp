@@ -183,24 +183,18 @@ inline void fill_k1a(const HostAdapter& h, const AtrTables& tb, int index, int r
     // within k columns of its anchored position (locate_core.cuh: anchor_filter)
     a.anchor_ok = h.k1a_ok && !a.fused_ok && !h.cmp_only && !h.need_find && a.exact_ok &&
                   (h.desc.flags == ATR_STOP_WITHIN_SEQ2 || h.desc.flags == ATR_START_WITHIN_SEQ2);
-    // Shift-And pieces over the adapter's first sa_rows rows: k+1 pieces, each at least 6 rows (shorter pieces hit at
-    // random too often to be a filter); needs row-m candidates to be reported inside the loop (stop_in_query). A 32-bit
-    // state word over the first min(m, 32) rows when that works, else a 64-bit word over the first min(m, 64) rows.
-    a.sa_ok = 0; a.sa_wide = 0; a.sa_rows = h.m < 32 ? h.m : 32; a.sa_start = 0; a.sa_end = 0; a.tail_gate_ok = 0; a.tail_mask = 0;
+    // Shift-And pieces over the first min(m, 32) rows: k+1 pieces, each at least 6 rows (shorter pieces hit at
+    // random too often to be a filter); needs row-m candidates to be reported inside the loop (stop_in_query)
+    a.sa_ok = 0; a.sa_rows = h.m < 32 ? h.m : 32; a.sa_start = 0; a.sa_end = 0; a.tail_gate_ok = 0; a.tail_mask = 0;
     const bool stop_in_query = h.desc.flags & ATR_STOP_WITHIN_SEQ2;
     const int pieces = h.k + 1;
-    const bool sa_shape = (a.fused_ok || a.filter_only) && !start_in_ref && stop_in_query;
-    if (sa_shape && !(pieces <= a.sa_rows && a.sa_rows / pieces >= 6) && h.m > 32) {
-        const int rows64 = h.m < 64 ? h.m : 64;
-        if (pieces <= rows64 && rows64 / pieces >= 6) { a.sa_wide = 1; a.sa_rows = rows64; }
-    }
-    if (sa_shape && pieces <= a.sa_rows && a.sa_rows / pieces >= 6) {
+    if ((a.fused_ok || a.filter_only) && !start_in_ref && stop_in_query && pieces <= a.sa_rows && a.sa_rows / pieces >= 6) {
         a.sa_ok = 1;
         int row = 1;
         for (int pc = 0; pc < pieces; pc++) {
             const int len = a.sa_rows / pieces + (pc < a.sa_rows % pieces ? 1 : 0);
-            a.sa_start |= 1ull << (row - 1);
-            a.sa_end |= 1ull << (row + len - 2);
+            a.sa_start |= 1u << (row - 1);
+            a.sa_end |= 1u << (row + len - 2);
             row += len;
         }
         // Gate for the exact tail pass. A last-column candidate (i, n), i <= sa_rows, has e <= thr_mul[i] errors
@@ -221,7 +215,7 @@ inline void fill_k1a(const HostAdapter& h, const AtrTables& tb, int index, int r
             }
             const int e = (int)h.thr_mul[i];
             if (e < c) continue;
-            if (e == c && i > end_c) { a.tail_mask |= 1ull << (i - 1); continue; }
+            if (e == c && i > end_c) { a.tail_mask |= 1u << (i - 1); continue; }
             a.tail_gate_ok = 0;
         }
     }

@@ -55,13 +55,12 @@ struct AdapterK1a {                   // passed by value as a __grid_constant__ 
     // Shift-And pre-filter (k_filter_sa): the first sa_rows (<= 32) adapter rows cut into k+1 pieces; an alignment
     // with <= k errors must contain one piece verbatim (pigeonhole)
     int sa_ok, sa_rows;
-    int sa_wide;                      // 64-bit state word (sa_rows up to 64) instead of 32
     int tail_gate_ok;                 // the Shift-And state can tell when no partial match at the read end is possible
-    unsigned long long tail_mask;     // bit i-1: a candidate (i, n) without a verbatim complete piece leaves this bit set
+    unsigned tail_mask;               // bit i-1: a candidate (i, n) without a verbatim complete piece leaves this bit set
     unsigned apack[ATR_K1A_MAXM / 8]; // the adapter's compare codes packed like a read (exact-occurrence shortcut)
     int exact_ok;                     // shortcut usable (codes fit nibbles; not the ACGT-filtered query mode)
     short thrJ[ATR_K1A_MAXM + 1];     // start_in_ref adapters: bound on D[m][j] for j = 0..m (j > m uses thrJ[m]); -1 = never
-    unsigned long long sa_start, sa_end;   // bit r-1: row r is the first / last row of a piece
+    unsigned sa_start, sa_end;        // bit r-1: row r is the first / last row of a piece
     int filter_only;                  // funnel shape but indel cost != 1: the funnel's first stage as a pure filter, then k1a_read
     int anchor_ok;                    // PREFIX / SUFFIX flag set outside the funnel: fixed-position piece filter (k_filter_anchor)
 };

@@ -349,22 +349,21 @@ __global__ void __launch_bounds__(ATR_K1F_THREADS) k_filter(const __grid_constan
 // ---------------------------------------------------------------------------------------------
 // The tail pass is a separate (non-inlined) device function: it is executed by few, compacted warps and must
 // not inflate the register allocation of the Shift-And scan that every thread runs.
-template <class SW>
-__device__ __noinline__ int sa_tail_packed(const AdapterK1a* ad, const SW* tail_peq, const uint32_t* rd, int lo, int n) {
+__device__ __noinline__ int sa_tail_packed(const AdapterK1a* ad, const unsigned* tail_peq, const uint32_t* rd, int lo, int n) {
     int imin, imax;
-    sa_tail<SW>(*ad, tail_peq, rd, lo, n, imin, imax);
+    sa_tail(*ad, tail_peq, rd, lo, n, imin, imax);
     return (imin << 16) | imax;
 }
 
-template <bool AND_MODE, class SW>
+template <bool AND_MODE>
 __global__ void __launch_bounds__(ATR_K1F_THREADS) k_filter_sa(const __grid_constant__ AdapterK1a ad,
         const uint32_t* __restrict__ codes, const uint32_t* __restrict__ woff, const uint16_t* __restrict__ len,
         const uint16_t* __restrict__ win, int64_t n_reads, atr_match* __restrict__ out,
         Survivor* __restrict__ narrow, Survivor* __restrict__ wide, Survivor* __restrict__ refine, int* __restrict__ counters) {
     __shared__ __align__(128) uint32_t s_tile[ATR_K1F_TILE_WORDS];
     __shared__ __align__(8) uint64_t s_bar;
-    __shared__ SW s_sa_peq[16], s_tail_peq[16];
-    __shared__ typename SaPairT<SW>::type s_sa_pair[256];      // Peq of two bases per byte of the packed read
+    __shared__ unsigned s_sa_peq[16], s_tail_peq[16];
+    __shared__ unsigned long long s_sa_pair[256];      // Peq of two bases per byte of the packed read
     __shared__ int s_im[ATR_K1F_THREADS];
     __shared__ unsigned short s_tail_list[ATR_K1F_THREADS];
     __shared__ int s_tail_count;
@@ -379,11 +378,17 @@ __global__ void __launch_bounds__(ATR_K1F_THREADS) k_filter_sa(const __grid_cons
     const bool fits = span <= ATR_K1F_TILE_WORDS;
     const bool use_tma = fits && !last_tile && span > 0 && ((reinterpret_cast<uintptr_t>(codes) & 15) == 0);
     if (tid < 16) {
-        s_sa_peq[tid] = sa_low_peq<SW>(ad, tid);
-        s_tail_peq[tid] = sa_tail_peq_of<SW>(ad, tid);
+        const int mp = ad.sa_rows, sh32 = 32 - mp;
+        const unsigned low = (unsigned)(ad.peq[tid] & (mp >= 32 ? 0xFFFFFFFFull : ((1ull << mp) - 1)));
+        s_sa_peq[tid] = low;
+        s_tail_peq[tid] = sh32 ? ((low << sh32) | ((1u << sh32) - 1u)) : low;
     }
     if (tid == 0) s_tail_count = 0;
-    s_sa_pair[tid] = SaPairT<SW>::make(sa_low_peq<SW>(ad, tid & 15), sa_low_peq<SW>(ad, tid >> 4));
+    {
+        const int mp = ad.sa_rows;
+        const unsigned long long mk = mp >= 32 ? 0xFFFFFFFFull : ((1ull << mp) - 1);
+        s_sa_pair[tid] = (ad.peq[tid & 15] & mk) | ((ad.peq[tid >> 4] & mk) << 32);
+    }
     if (tid == 0 && use_tma) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar)) : "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -421,15 +426,15 @@ __global__ void __launch_bounds__(ATR_K1F_THREADS) k_filter_sa(const __grid_cons
     int hmin = 0x7fffffff, hmax = -0x7fffffff;
     bool exact = false, need_tail = false;
     if (mine && !routed) {
-        SW st_final;
-        sa_scan<SW>(ad, s_sa_peq, s_sa_pair, rd, lo, n, hmin, hmax, st_final);
+        unsigned st_final;
+        sa_scan(ad, s_sa_peq, s_sa_pair, rd, lo, n, hmin, hmax, st_final);
         exact = sa_exact(ad, rd, lo, n, hmin, hmax);
         if (exact) {                                                // verbatim occurrence: result known (str.find shortcut)
             Best b;
             b.matches = ad.m; b.cost = 0; b.origin = hmin; b.ref_stop = ad.m; b.q_stop = hmin + ad.m;
             finalize(ad, b, n, out + r);
         } else {
-            need_tail = sa_need_tail<SW>(ad, n, hmax, st_final);
+            need_tail = sa_need_tail(ad, n, hmax, st_final);
         }
     }
     // ---- phase B: the exact 32-bit Myers over the read tail, only for the reads that can have a partial match at
@@ -444,7 +449,7 @@ __global__ void __launch_bounds__(ATR_K1F_THREADS) k_filter_sa(const __grid_cons
         const uint32_t wr2 = woff[t0 + t2];
         const uint32_t* rd2 = codes + wr2;
         if (fits) rd2 = s_tile + (wr2 - a_begin);
-        s_im[t2] = sa_tail_packed<SW>(&ad, s_tail_peq, rd2, lo2, n2);
+        s_im[t2] = sa_tail_packed(&ad, s_tail_peq, rd2, lo2, n2);
     }
     __syncthreads();
     // ---- phase C (every thread): classify ----

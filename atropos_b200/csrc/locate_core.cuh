@@ -51,21 +51,6 @@ ATR_HD int atr_ctz(unsigned x) {
 #endif
 }
 
-ATR_HD int atr_msb(unsigned long long x) {
-#if defined(__CUDA_ARCH__)
-    return 63 - __clzll((long long)x);
-#else
-    return 63 - __builtin_clzll(x);
-#endif
-}
-ATR_HD int atr_ctz(unsigned long long x) {
-#if defined(__CUDA_ARCH__)
-    return __ffsll((long long)x) - 1;
-#else
-    return __builtin_ctzll(x);
-#endif
-}
-
 // candidate acceptance: _align.pyx:443-449 (row m inside the loop) and :465-474 (last column)
 template <class A>
 ATR_HD void consider(const A& ad, Best& b, int cost, int origin, int matches, int ref_stop, int q_stop) {
@@ -414,57 +399,24 @@ struct SaResult {
 #ifndef ATR_SA_PAIR_TABLE
 #define ATR_SA_PAIR_TABLE 1          // measured on B200: pair table 0.856 ms, single-base table 0.891 ms per 10 M reads
 #endif
-// State word of the Shift-And stage: 32 bits when k+1 pieces of >= 6 rows fit the adapter's first 32 rows, else 64
-// bits over its first 64 rows (AdapterK1a.sa_wide; e.g. the 58-nt TruSeq adapter at rate 0.1: 6 pieces). The pair
-// table entry holds the Peq words of the two bases of one byte of the packed read.
-struct alignas(16) SaPair64 { unsigned long long a, b; };
-template <class SW> struct SaPairT;
-template <> struct SaPairT<unsigned> {
-    typedef unsigned long long type;
-    static ATR_HD type make(unsigned a, unsigned b) { return (type)a | ((type)b << 32); }
-    static ATR_HD unsigned first(const type& p) { return (unsigned)p; }
-    static ATR_HD unsigned second(const type& p) { return (unsigned)(p >> 32); }
-};
-template <> struct SaPairT<unsigned long long> {
-    typedef SaPair64 type;
-    static ATR_HD type make(unsigned long long a, unsigned long long b) { SaPair64 p; p.a = a; p.b = b; return p; }
-    static ATR_HD unsigned long long first(const type& p) { return p.a; }
-    static ATR_HD unsigned long long second(const type& p) { return p.b; }
-};
-// the adapter's first sa_rows rows of Peq[c] as a state word
-template <class SW>
-ATR_HD SW sa_low_peq(const AdapterK1a& ad, int c) {
-    const int mp = ad.sa_rows, W = (int)(8 * sizeof(SW));
-    const unsigned long long mk = mp >= 64 ? ~0ull : ((1ull << mp) - 1ull);
-    (void)W;
-    return (SW)(ad.peq[c] & mk);
-}
-// ... left-aligned for the tail Myers, unused low bits all ones (virtual free rows)
-template <class SW>
-ATR_HD SW sa_tail_peq_of(const AdapterK1a& ad, int c) {
-    const int W = (int)(8 * sizeof(SW)), sh = W - ad.sa_rows;
-    const SW low = sa_low_peq<SW>(ad, c);
-    return sh ? (SW)((low << sh) | (((SW)1 << sh) - (SW)1)) : low;
-}
-
 // eight columns (one packed word) of the Shift-And automaton; G = columns per hit-accumulation group (see sa_scan)
-template <int G, class SW>
-ATR_HD void sa_word(uint32_t w, SW& St, SW S0, SW E, const SW* __restrict__ sa_peq,
-                    const typename SaPairT<SW>::type* __restrict__ sa_pair, int j, int& hmin, int& hmax) {
+template <int G>
+ATR_HD void sa_word(uint32_t w, unsigned& St, unsigned S0, unsigned E, const unsigned* __restrict__ sa_peq,
+                    const unsigned long long* __restrict__ sa_pair, int j, int& hmin, int& hmax) {
 #pragma unroll
     for (int g = 0; g < 8; g += G) {
-        SW H = 0;
+        unsigned H = 0;
 #pragma unroll
         for (int t = g; t < g + G; t += 2) {
 #if ATR_SA_PAIR_TABLE
-            const typename SaPairT<SW>::type pr = sa_pair[(w >> (4 * t)) & 255u];
-            const SW p0 = SaPairT<SW>::first(pr), p1 = SaPairT<SW>::second(pr);
+            const unsigned long long pr = sa_pair[(w >> (4 * t)) & 255u];
+            const unsigned p0 = (unsigned)pr, p1 = (unsigned)(pr >> 32);
 #else
             // Alternative kept for the record: 16 entries x 4 bytes sit in 16 different banks, so every load is one
             // wavefront, whereas the pair table's random accesses conflict (7 wavefronts per load measured, the
             // shared-memory pipe busy for 64 % of the kernel). It still loses: the kernel is bound by instruction
             // issue, and this form needs one more index extraction per column.
-            const SW p0 = sa_peq[(w >> (4 * t)) & 15u], p1 = sa_peq[(w >> (4 * t + 4)) & 15u];
+            const unsigned p0 = sa_peq[(w >> (4 * t)) & 15u], p1 = sa_peq[(w >> (4 * t + 4)) & 15u];
 #endif
             St = ((St << 1) | S0) & p0;
             H |= (St & E) >> (t - g);
@@ -476,13 +428,12 @@ ATR_HD void sa_word(uint32_t w, SW& St, SW S0, SW E, const SW* __restrict__ sa_p
 }
 
 // (a) Shift-And over all columns: range of hit diagonals and the automaton's final state
-// sa_pair: 256-entry table indexed by a byte of the packed read (two bases): Peq of the first and of the second base
-// -- one shared-memory load serves two columns.
-template <class SW>
-ATR_HD void sa_scan(const AdapterK1a& ad, const SW* __restrict__ sa_peq, const typename SaPairT<SW>::type* __restrict__ sa_pair,
-                    const uint32_t* __restrict__ codes, int lo, int n, int& hmin, int& hmax, SW& st_final) {
-    const SW S0 = (SW)ad.sa_start, E = (SW)ad.sa_end;
-    SW St = 0;
+// sa_pair: 256-entry table indexed by a byte of the packed read (two bases): low word = Peq of the first base,
+// high word = Peq of the second -- one 8-byte shared-memory load serves two columns.
+ATR_HD void sa_scan(const AdapterK1a& ad, const unsigned* __restrict__ sa_peq, const unsigned long long* __restrict__ sa_pair,
+                    const uint32_t* __restrict__ codes, int lo, int n, int& hmin, int& hmax, unsigned& st_final) {
+    const unsigned S0 = ad.sa_start, E = ad.sa_end;
+    unsigned St = 0;
     hmin = 0x7fffffff; hmax = -0x7fffffff;           // over hits: (column of the piece end) - (row of the piece end)
     int j = 0, pos = lo;
     const int pend = lo + n;
@@ -490,24 +441,24 @@ ATR_HD void sa_scan(const AdapterK1a& ad, const SW* __restrict__ sa_peq, const t
         const unsigned qc = (codes[pos >> 3] >> ((pos & 7) * 4)) & 15u;
         St = ((St << 1) | S0) & sa_peq[qc];
         j++; pos++;
-        const SW hb = St & E;
+        const unsigned hb = St & E;
         if (hb) { hmin = atr_min(hmin, j - 1 - atr_msb(hb)); hmax = atr_max(hmax, j - 1 - atr_ctz(hb)); }
     }
     // Whole words: the piece ends of G consecutive columns are folded into one word H, column t's shifted right by
     // t, so that bit b of H = a piece ending in row r1 at column j + t with r1 - t = b, i.e. on diagonal v = j - b:
     // one test and one msb / ctz per group instead of one per column (the hits sit in a few lanes of a warp, so
     // every instruction spent on them runs almost empty). G = 8 needs every piece to end in row >= 8 (bit >= 7).
-    if (ad.sa_end & 0x7Full) {
-        while (pos + 8 <= pend) { sa_word<4, SW>(codes[pos >> 3], St, S0, E, sa_peq, sa_pair, j, hmin, hmax); j += 8; pos += 8; }
+    if (ad.sa_end & 0x7Fu) {
+        while (pos + 8 <= pend) { sa_word<4>(codes[pos >> 3], St, S0, E, sa_peq, sa_pair, j, hmin, hmax); j += 8; pos += 8; }
     } else {
-        while (pos + 8 <= pend) { sa_word<8, SW>(codes[pos >> 3], St, S0, E, sa_peq, sa_pair, j, hmin, hmax); j += 8; pos += 8; }
+        while (pos + 8 <= pend) { sa_word<8>(codes[pos >> 3], St, S0, E, sa_peq, sa_pair, j, hmin, hmax); j += 8; pos += 8; }
     }
     if (pos < pend) {
         const uint32_t w = codes[pos >> 3];
         for (int t = 0; pos < pend; t++) {
             St = ((St << 1) | S0) & sa_peq[(w >> (4 * t)) & 15u];
             j++; pos++;
-            const SW hb = St & E;
+            const unsigned hb = St & E;
             if (hb) { hmin = atr_min(hmin, j - 1 - atr_msb(hb)); hmax = atr_max(hmax, j - 1 - atr_ctz(hb)); }
         }
     }
@@ -542,26 +493,24 @@ ATR_HD bool sa_exact(const AdapterK1a& ad, const uint32_t* __restrict__ codes, i
 }
 
 // (c) can there be a candidate in the last column with row <= sa_rows? (see adapter_build.hpp: tail gate)
-template <class SW>
-ATR_HD bool sa_need_tail(const AdapterK1a& ad, int n, int hmax, SW st_final) {
+ATR_HD bool sa_need_tail(const AdapterK1a& ad, int n, int hmax, unsigned st_final) {
     const bool stop_in_ref = ad.flags & ATR_STOP_WITHIN_SEQ1;
     if (!(stop_in_ref || ad.m <= ad.sa_rows)) return false;
     if (!ad.tail_gate_ok) return true;
-    if (st_final & (SW)ad.tail_mask) return true;
+    if (st_final & ad.tail_mask) return true;
     return hmax != -0x7fffffff && hmax >= n - ad.sa_rows - ad.k;
 }
 
-// (d) exact D[i][n] for rows i <= sa_rows from a Myers pass over the last sa_rows + k columns (rows left-aligned)
-template <class SW>
-ATR_HD void sa_tail(const AdapterK1a& ad, const SW* __restrict__ tail_peq, const uint32_t* __restrict__ codes, int lo, int n,
+// (d) exact D[i][n] for rows i <= sa_rows from a 32-bit Myers over the last sa_rows + k columns (rows left-aligned)
+ATR_HD void sa_tail(const AdapterK1a& ad, const unsigned* __restrict__ tail_peq, const uint32_t* __restrict__ codes, int lo, int n,
                     int& imin, int& imax) {
-    const int m = ad.m, k = ad.k, mp = ad.sa_rows, W = (int)(8 * sizeof(SW));
+    const int m = ad.m, k = ad.k, mp = ad.sa_rows;
     const bool stop_in_ref = ad.flags & ATR_STOP_WITHIN_SEQ1;
     const int pend = lo + n;
     imin = 0; imax = 0;
-    const int sh = W - mp;
-    MyersState<SW> st;
-    st.Pv = (sh == 0) ? (SW)~(SW)0 : (SW)(~(SW)0 << sh);
+    const int sh = 32 - mp;
+    MyersState<unsigned> st;
+    st.Pv = (sh == 0) ? ~0u : (~0u << sh);
     st.Mv = 0; st.score = mp;
     // start on a word boundary at or before column n - mp - k (an earlier start is always safe)
     int p = atr_max(lo, (lo + atr_max(0, n - mp - k)) & ~7);
@@ -577,11 +526,11 @@ ATR_HD void sa_tail(const AdapterK1a& ad, const SW* __restrict__ tail_peq, const
         for (int t = 0; p < pend; t++, p++) myers_col(st, tail_peq[(w >> (4 * t)) & 15u]);
     }
     // D[i][n] = running sum of the vertical deltas; rows right-aligned so that the shifts are static
-    const SW pv = st.Pv >> sh, mv = st.Mv >> sh;
+    const unsigned pv = st.Pv >> sh, mv = st.Mv >> sh;
     const int row_lo = atr_max(stop_in_ref ? 1 : m, ad.min_overlap);
     int d = 0;
 #pragma unroll
-    for (int i = 1; i <= W; i++) {
+    for (int i = 1; i <= 32; i++) {
         d += (int)((pv >> (i - 1)) & 1u) - (int)((mv >> (i - 1)) & 1u);
         if (i >= row_lo && i <= mp && d <= (int)ad.thr_mul[i]) { imin = imin == 0 ? i : imin; imax = i; }
     }
@@ -623,17 +572,15 @@ ATR_HD void sa_classify(const AdapterK1a& ad, int lo, int n, int hmin, int hmax,
 }
 
 // the whole stage for one read (host simulator; the kernel interleaves a block-level compaction before (d))
-template <class SW>
-ATR_HD void sa_filter(const AdapterK1a& ad, const uint32_t* __restrict__ codes, int lo, int n, SaResult& res) {
+ATR_HD void sa_filter(const AdapterK1a& ad, const unsigned* __restrict__ sa_peq, const unsigned* __restrict__ tail_peq,
+                      const uint32_t* __restrict__ codes, int lo, int n, SaResult& res) {
     int hmin, hmax, imin = 0, imax = 0;
-    SW st_final;
-    SW sa_peq[16], tail_peq[16];
-    for (int c = 0; c < 16; c++) { sa_peq[c] = sa_low_peq<SW>(ad, c); tail_peq[c] = sa_tail_peq_of<SW>(ad, c); }
-    typename SaPairT<SW>::type sa_pair[256];
-    for (int b = 0; b < 256; b++) sa_pair[b] = SaPairT<SW>::make(sa_peq[b & 15], sa_peq[b >> 4]);
-    sa_scan<SW>(ad, sa_peq, sa_pair, codes, lo, n, hmin, hmax, st_final);
+    unsigned st_final;
+    unsigned long long sa_pair[256];
+    for (int b = 0; b < 256; b++) sa_pair[b] = (unsigned long long)sa_peq[b & 15] | ((unsigned long long)sa_peq[b >> 4] << 32);
+    sa_scan(ad, sa_peq, sa_pair, codes, lo, n, hmin, hmax, st_final);
     if (sa_exact(ad, codes, lo, n, hmin, hmax)) { res.cls = 3; res.v = hmin; return; }
-    if (sa_need_tail<SW>(ad, n, hmax, st_final)) sa_tail<SW>(ad, tail_peq, codes, lo, n, imin, imax);
+    if (sa_need_tail(ad, n, hmax, st_final)) sa_tail(ad, tail_peq, codes, lo, n, imin, imax);
     sa_classify(ad, lo, n, hmin, hmax, imin, imax, res);
 }
 
@@ -984,9 +931,15 @@ ATR_HD void k1f_read(const AdapterK1a& ad, const uint32_t* __restrict__ codes, i
     if (path) *path = 0;
     bool have = false;
     if (ad.sa_ok) {
+        unsigned sa_peq[16], tail_peq[16];
+        const int mp = ad.sa_rows, sh32 = 32 - mp;
+        for (int c = 0; c < 16; c++) {
+            const unsigned low = (unsigned)(ad.peq[c] & (mp >= 32 ? 0xFFFFFFFFull : ((1ull << mp) - 1)));
+            sa_peq[c] = low;
+            tail_peq[c] = (sh32 ? (low << sh32) | ((1u << sh32) - 1u) : low);
+        }
         SaResult sr;
-        if (ad.sa_wide) sa_filter<unsigned long long>(ad, codes, lo, n, sr);
-        else sa_filter<unsigned>(ad, codes, lo, n, sr);
+        sa_filter(ad, sa_peq, tail_peq, codes, lo, n, sr);
         if (sr.cls == 3) {
             b.matches = ad.m; b.cost = 0; b.origin = sr.v; b.ref_stop = ad.m; b.q_stop = sr.v + ad.m;
             if (path) *path = 5;
@@ -1030,9 +983,15 @@ ATR_HD void icfilter_read(const AdapterK1a& ad, const uint32_t* __restrict__ cod
     bool have = false;
     if (path) *path = 0;
     if (ad.sa_ok) {
+        unsigned sa_peq[16], tail_peq[16];
+        const int mp = ad.sa_rows, sh32 = 32 - mp;
+        for (int c = 0; c < 16; c++) {
+            const unsigned low = (unsigned)(ad.peq[c] & (mp >= 32 ? 0xFFFFFFFFull : ((1ull << mp) - 1)));
+            sa_peq[c] = low;
+            tail_peq[c] = (sh32 ? (low << sh32) | ((1u << sh32) - 1u) : low);
+        }
         SaResult sr;
-        if (ad.sa_wide) sa_filter<unsigned long long>(ad, codes, lo, n, sr);
-        else sa_filter<unsigned>(ad, codes, lo, n, sr);
+        sa_filter(ad, sa_peq, tail_peq, codes, lo, n, sr);
         if (sr.cls == 3) {
             b.matches = ad.m; b.cost = 0; b.origin = sr.v; b.ref_stop = ad.m; b.q_stop = sr.v + ad.m;
             if (path) *path = 5;

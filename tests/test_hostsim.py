@@ -321,31 +321,3 @@ def test_filter_only_funnel_for_dearer_indels(where):
             found += exp is not None
     assert took > 2000 and found > 400
     assert dp < 0.9 * took
-
-
-def test_wide_shift_and_for_long_adapters():
-    """adapters whose k+1 pieces do not fit 32 rows (e.g. the 58-nt TruSeq adapter at 0.1: 6 pieces) run the
-    Shift-And stage on a 64-bit state word over up to 64 rows; partial matches at the read end beyond row 32 included"""
-    rng = np.random.default_rng(900)
-    took = found = deep = 0
-    seqs = [T2] + [fuzzgen.rand_seq(rng, int(rng.integers(40, 65)), "ACGT") for _ in range(40)]
-    for seq in seqs:
-        m = len(seq)
-        for rate in (0.1, 0.12, 0.15):
-            d, keep = _abi.make_adapter_desc(seq, rate, BACK, False, False, 3, 1)
-            for _ in range(25):
-                n = int(rng.integers(20, 160))
-                r = rng.random()
-                body = fuzzgen.rand_seq(rng, n, "ACGT")
-                if r < 0.45:                      # adapter prefix (mutated) running off the read end
-                    cut = int(rng.integers(3, m + 1))
-                    body = (body + fuzzgen.mutate(rng, seq[:cut], sub=rate / 2, ins=rate / 5, dele=rate / 5))[-n:]
-                elif r < 0.8:
-                    body = fuzzgen.read_with_adapter(rng, seq, n, n_rate=0.01)
-                exp = oracle.locate(seq, body, rate, BACK, False, False, 3, 1)
-                got, used, _ = hostsim.locate(body, d)
-                assert got == exp, (seq, rate, body)
-                took += used >= 12
-                found += exp is not None
-                deep += exp is not None and exp[1] > 32 and exp[3] == len(body)
-    assert took > 2500 and found > 1000 and deep > 100
