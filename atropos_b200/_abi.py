@@ -96,7 +96,7 @@ def make_read_ops(cut=(), cut2=(), quality_cutoff=None, quality_base=33, trim_n=
 
 class AtrTrimOpts(C.Structure):
     _fields_ = [("times", C.c_int32), ("max_len", C.c_int32), ("max_errors", C.c_int32), ("final_chunk", C.c_int32),
-                ("chunk_bytes", C.c_int64), ("ops", AtrReadOps)]
+                ("chunk_bytes", C.c_int64), ("linked_back", C.c_void_p), ("ops", AtrReadOps)]
 
 
 class AtrTrimStats(C.Structure):

@@ -180,21 +180,37 @@ int fq_back(atr_ctx* ctx, Slot& s, const FqChunk& c, const atr_adapterset* set, 
         if (rc) return rc;
         int gather_all = 0;
         for (const atr::HostAdapter& h : set->host) if (!h.k1a_ok) gather_all = 1;
+        if (o->linked_back) for (const atr::HostAdapter& h : o->linked_back->host) if (!h.k1a_ok) gather_all = 1;
         k_fq_gather<<<grid_for(n * 32, 256), 256, 0, st>>>(d_text, f.recs.as<FqRec>(), (const long long*)s.offsets.p, s.len.as<uint16_t>(), n,
                                                            gather_all, s.ascii.as<unsigned char>());
         LAUNCHED(ctx);
         k_fq_init_win<<<grid_for(n, 256), 256, 0, st>>>(f.recs.as<FqRec>(), n, f.fwin.as<uint16_t>(), &d_ctr->records);
         LAUNCHED(ctx);
+        const atr_adapterset* back = o->linked_back;
         for (int round = 0; round < o->times; round++) {
             rc = locate_on_stream(ctx, s, set, s.codes.as<uint32_t>(), s.woff.as<uint32_t>(), s.len.as<uint16_t>(),
                                   round ? s.win.as<uint16_t>() : nullptr, s.ascii.as<uint8_t>(), s.offsets.as<int64_t>(), 0, 1, n,
                                   s.out.as<atr_match>());
             if (rc) return rc;
             k_fq_apply<<<grid_for(n, 256), 256, 0, st>>>(d_text, f.recs.as<FqRec>(), s.out.as<atr_match>(), n, round,
-                                                         round + 1 < o->times ? 1 : 0, (const signed char*)(d_stats + L.o_flags),
+                                                         (round + 1 < o->times || back) ? 1 : 0, (const signed char*)(d_stats + L.o_flags),
                                                          o->max_len, o->max_errors, f.fwin.as<uint16_t>(), s.win.as<uint16_t>(),
-                                                         f.flags.as<unsigned char>(), (unsigned long long*)(d_stats + L.o_front), (unsigned long long*)(d_stats + L.o_back),
-                                                         (unsigned long long*)(d_stats + L.o_adj), d_ctr);
+                                                         f.flags.as<unsigned char>(), (unsigned long long*)(d_stats + L.o_front),
+                                                         (unsigned long long*)(d_stats + L.o_back),
+                                                         (unsigned long long*)(d_stats + L.o_adj), d_ctr, 0);
+            LAUNCHED(ctx);
+        }
+        if (back) {
+            // LinkedAdapter.match_to (:671-690): the back adapter inside what the front adapter left, only where the front
+            // adapter matched (the round's windows are empty elsewhere)
+            rc = locate_on_stream(ctx, s, back, s.codes.as<uint32_t>(), s.woff.as<uint32_t>(), s.len.as<uint16_t>(), s.win.as<uint16_t>(),
+                                  s.ascii.as<uint8_t>(), s.offsets.as<int64_t>(), 0, 1, n, s.out.as<atr_match>());
+            if (rc) return rc;
+            k_fq_apply<<<grid_for(n, 256), 256, 0, st>>>(d_text, f.recs.as<FqRec>(), s.out.as<atr_match>(), n, 1, 0,
+                                                         (const signed char*)(d_stats + L.o_flags), o->max_len, o->max_errors,
+                                                         f.fwin.as<uint16_t>(), s.win.as<uint16_t>(), f.flags.as<unsigned char>(),
+                                                         (unsigned long long*)(d_stats + L.o_front), (unsigned long long*)(d_stats + L.o_back),
+                                                         (unsigned long long*)(d_stats + L.o_adj), d_ctr, 1);
             LAUNCHED(ctx);
         }
         // N-end trimming and the filters
@@ -251,13 +267,21 @@ extern "C" int atr_trim_fastq_host(atr_ctx* ctx, const atr_adapterset* set, cons
         return fail(ctx, ATR_E_ARG, "bad atr_trim_opts (times >= 1, 0 <= max_len <= 32767, 0 <= max_errors <= 4095)");
     for (const atr::HostAdapter& h : set->host)
         if (!h.desc.match_to_semantics) return fail(ctx, ATR_E_ARG, "atr_trim_fastq_host needs adapters created with match_to_semantics = 1");
+    const atr_adapterset* back = opts->linked_back;
+    if (back) {
+        if (back->ctx != ctx || set->host.size() != 1 || back->host.size() != 1 || opts->times != 1 || !back->host[0].desc.match_to_semantics)
+            return fail(ctx, ATR_E_ARG, "a linked adapter is one front and one back adapter (match_to_semantics = 1) with times == 1");
+        const int wf = set->host[0].desc.flags, wb = back->host[0].desc.flags;
+        if (!(wf == 8 || wf == 11) || !(wb == 14 || wb == 2))
+            return fail(ctx, ATR_E_ARG, "a linked adapter needs a 5' (PREFIX / FRONT) front adapter and a 3' (BACK / SUFFIX) back adapter");
+    }
     CU(cudaSetDevice(ctx->device));
     memset(err, 0, sizeof(*err));
     *out_bytes = 0;
     *consumed = 0;
     int64_t chunk = opts->chunk_bytes > 0 ? opts->chunk_bytes : ((int64_t)64 << 20);
     chunk = std::max<int64_t>(4096, std::min<int64_t>(chunk, (int64_t)1 << 30));
-    const size_t nA = set->host.size();
+    const size_t nA = set->host.size() + (back ? 1 : 0);
     const FqStatsLayout L = fq_layout(nA, opts->max_len, opts->max_errors);
     int rc = ctx->fq_stats.ensure(L.total);
     if (rc) return fail(ctx, rc, "out of device memory (statistics)");
@@ -266,7 +290,7 @@ extern "C" int atr_trim_fastq_host(atr_ctx* ctx, const atr_adapterset* set, cons
     {
         std::vector<signed char> ff(nA);
         for (size_t a = 0; a < nA; a++) {                // Adapter.__init__: adapters/__init__.py:301-304
-            const int w = set->host[a].desc.flags;
+            const int w = (back && a == nA - 1) ? back->host[0].desc.flags : set->host[a].desc.flags;
             ff[a] = (w == ATR_SEMIGLOBAL) ? (signed char)-1 : ((w == 14 || w == 2) ? (signed char)0 : (signed char)1);
         }
         CU(cudaMemcpy(d_stats + L.o_flags, ff.data(), nA, cudaMemcpyHostToDevice));
@@ -542,7 +566,7 @@ int pe_back(atr_ctx* ctx, Slot& s, const PeStep& P, const atr_insertset* iset, c
                                                              o->max_len, o->max_errors, q.fwin.as<uint16_t>(), b.win.as<uint16_t>(),
                                                              q.flags.as<unsigned char>(), (unsigned long long*)(d_stats + L.o_front[f]),
                                                              (unsigned long long*)(d_stats + L.o_hist[f]),
-                                                             (unsigned long long*)(d_stats + L.o_adj[f]), (FqCounters*)(d_stats + L.o_side[f]));
+                                                             (unsigned long long*)(d_stats + L.o_adj[f]), (FqCounters*)(d_stats + L.o_side[f]), 0);
                 LAUNCHED(ctx);
             }
         }

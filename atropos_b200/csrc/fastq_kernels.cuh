@@ -245,11 +245,13 @@ __global__ void __launch_bounds__(256) k_fq_apply(const unsigned char* __restric
                                                   const signed char* __restrict__ front_flags, int max_len, int max_errors,
                                                   uint16_t* __restrict__ fwin, uint16_t* __restrict__ rwin, unsigned char* __restrict__ flags,
                                                   unsigned long long* __restrict__ hist_front, unsigned long long* __restrict__ hist_back,
-                                                  unsigned long long* __restrict__ adjacent, FqCounters* __restrict__ ctr) {
+                                                  unsigned long long* __restrict__ adjacent, FqCounters* __restrict__ ctr,
+                                                  int adapter_base) {
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     bool hit = false;
     if (r < n_rec) {
-        const atr_match m = matches[r];
+        atr_match m = matches[r];
+        if (m.adapter >= 0) m.adapter = (int16_t)(m.adapter + adapter_base);   // linked adapters: the back adapter is index 1
         const int lo = fwin[2 * r], hi = fwin[2 * r + 1];
         FqApply a;
         if (m.status == ATR_ST_INVALID) atomicAdd(&ctr->invalid, 1ull);

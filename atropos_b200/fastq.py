@@ -14,7 +14,7 @@ import ctypes as C
 import numpy as np
 
 from . import _abi, _lib, engine
-from .adapters import ANYWHERE, BACK, SUFFIX
+from .adapters import ANYWHERE, BACK, LINKED, SUFFIX
 
 
 class FormatError(Exception):
@@ -157,9 +157,21 @@ class FastqTrimmer(object):
         self.adapters = list(adapters)
         self.times = int(times)
         self.max_len = int(max_len)
-        self.max_errors = max(int(a.max_error_rate * len(a.sequence)) for a in self.adapters)
         self.ctx = engine.default_context(device)
-        self._set = engine.AdapterSet(self.ctx, [a.descriptor() for a in self.adapters])
+        self._back_set = None
+        if len(self.adapters) == 1 and getattr(self.adapters[0], "where", None) == LINKED:
+            # "-a FRONT...BACK": statistics index 0 = the front adapter, 1 = the back adapter
+            linked = self.adapters[0]
+            if self.times != 1:
+                raise ValueError("a linked adapter works with times == 1 only")
+            self.adapters = [linked.front_adapter, linked.back_adapter]
+            self._set = engine.AdapterSet(self.ctx, [linked.front_adapter.descriptor()])
+            self._back_set = engine.AdapterSet(self.ctx, [linked.back_adapter.descriptor()])
+        else:
+            if any(getattr(a, "where", None) == LINKED for a in self.adapters):
+                raise ValueError("a linked adapter cannot be combined with other adapters (the reference fails there too)")
+            self._set = engine.AdapterSet(self.ctx, [a.descriptor() for a in self.adapters])
+        self.max_errors = max(int(a.max_error_rate * len(a.sequence)) for a in self.adapters)
         self.chunk_bytes = int(chunk_bytes)
 
     def new_stats(self):
@@ -173,7 +185,8 @@ class FastqTrimmer(object):
             out = np.empty(max(n, 1), dtype=np.uint8)
         if stats is None:
             stats = self.new_stats()
-        opts = _abi.AtrTrimOpts(self.times, self.max_len, self.max_errors, int(bool(final)), self.chunk_bytes, self.ops)
+        opts = _abi.AtrTrimOpts(self.times, self.max_len, self.max_errors, int(bool(final)), self.chunk_bytes,
+                                self._back_set.handle if self._back_set is not None else None, self.ops)
         st = _abi.AtrTrimStats()
         st.errors_front = stats.errors_front.ctypes.data
         st.errors_back = stats.errors_back.ctypes.data

@@ -284,6 +284,11 @@ typedef struct atr_trim_opts {
     int32_t final_chunk;      /* 1: `text` ends the file (a partial last record is an error, an unterminated last
                                  line is a line); 0: stop after the last complete record and report `consumed` */
     int64_t chunk_bytes;      /* internal H2D chunk size, 0 = default (64 MiB) */
+    /* LinkedAdapter (adapters/__init__.py:637-690, "-a FRONT...BACK"): non-NULL = `set` holds the one anchored front
+     * adapter and linked_back the one back adapter; the back adapter is only looked for, in what the front adapter
+     * leaves, when the front adapter matched. Statistics: adapter index 0 = front, 1 = back. Needs times == 1 (with
+     * further adapters or rounds the reference itself fails: LinkedMatch has no `matches`, modifiers.py:120). */
+    const atr_adapterset* linked_back;
     atr_read_ops ops;         /* index 0 of the per-read fields */
 } atr_trim_opts;
 

@@ -1,7 +1,7 @@
 """Shared by the CPU (host simulator) and GPU tests of the FASTQ path: golden cases produced by the reference
 command line (tests/golden/make_fastq_golden.py) and the comparison of a result with them."""
 import golden_util
-from atropos_b200.adapters import ANYWHERE, BACK, FRONT, Adapter
+from atropos_b200.adapters import ANYWHERE, BACK, FRONT, PREFIX, Adapter, LinkedAdapter
 
 WHERE = {"back": BACK, "front": FRONT, "anywhere": ANYWHERE}
 
@@ -13,6 +13,9 @@ def cases():
 def adapters_of(case):
     """Adapter objects in the order the reference's AdapterCutter tried them (the order of its report)."""
     res = case["result"]
+    if any(w == "linked" for _, w in case["adapters"]):          # "-a FRONT...BACK": one LinkedAdapter
+        front, back = case["adapters"][0][0].split("...")
+        return [LinkedAdapter(front, back, max_error_rate=case["error_rate"], min_overlap=case["overlap"])]
     if "adapters" in res:
         order = [(a["sequence"], a["where"]) for a in res["adapters"]]
     else:
@@ -48,6 +51,12 @@ def check(case, out, stats, adapters):
     if res["bp_out"] is not None:
         assert stats.bp_out == res["bp_out"]
     assert stats.overflow == 0
+    if len(adapters) == 1 and isinstance(adapters[0], LinkedAdapter):
+        for a, gold in enumerate(res["adapters"]):               # index 0 = the front adapter, 1 = the back adapter
+            mine = stats.adapter_summary(a, ANYWHERE)             # both histograms of that sub-adapter
+            for key in ("lengths_front", "lengths_back", "errors_front", "errors_back"):
+                assert _str_keys(mine[key]) == gold[key], (case["label"], a, key)
+        return
     for a, (ad, gold) in enumerate(zip(adapters, res["adapters"])):
         mine = stats.adapter_summary(a, ad.where)
         for key in ("lengths_front", "lengths_back", "errors_front", "errors_back", "adjacent_bases"):

@@ -92,7 +92,7 @@ def run_reference(text, adapters, times, error_rate, overlap, extra=()):
             fh.write(text)
         args = []
         for seq, where in adapters:
-            args += [WHERE_OPT[where], seq]
+            args += [WHERE_OPT.get(where, "-a"), seq]          # "linked": -a FRONT...BACK
         args += ["-se", inp, "-o", outp, "-n", str(times), "-e", repr(error_rate), "-O", str(overlap),
                  "--no-default-adapters", "--no-cache-adapters", "--quiet", "--report-file", rep,
                  "--report-formats", "json"] + list(extra)
@@ -118,6 +118,17 @@ def run_reference(text, adapters, times, error_rate, overlap, extra=()):
         cutter = rj["trim"]["modifiers"]["AdapterCutter"]
         ad_stats = []
         for name, st in cutter["adapters"][0].items():
+            if st["where"]["name"] == "linked":        # LinkedAdapter.summarize (adapters/__init__.py:705-745)
+                for part, where in (("front", "front"), ("back", "back")):
+                    d = {"name": name, "linked": part, "sequence": st[part + "_sequence"], "where": where}
+                    for key in ("lengths_front", "lengths_back"):
+                        d[key] = st["%s_%s" % (part, key)]
+                    for key in ("errors_front", "errors_back"):
+                        e = st["%s_%s" % (part, key)]
+                        cols = e.get("columns", [])
+                        d[key] = {ln: {str(c): v for c, v in zip(cols, row) if v} for ln, row in e.get("rows", {}).items()}
+                    ad_stats.append(d)
+                continue
             # the command line groups the adapters by option (-a, then -b, then -g): this list is the order the
             # AdapterCutter tries them in, which decides ties (modifiers.py:107-122)
             d = {"name": name, "sequence": st["sequence"], "where": st["where"]["name"]}
@@ -162,6 +173,23 @@ def main():
     add("no_final_newline", fastq(make_records(rng, 50, one, ragged=False), final_eol=False), one)
     add("empty_file", "", one)
     add("single_empty_read", "@r\n\n+\n\n", one)
+    # --- a linked adapter: anchored 5' adapter, then (only if it matched) the 3' adapter in the remainder ------------------
+    def linked_records(n):
+        recs = []
+        for i in range(n):
+            body = fuzzgen.read_with_adapter(rng, SMALL3, 150, n_rate=0.01)
+            r = rng.random()
+            if r < 0.6:
+                body = fuzzgen.mutate(rng, FRONT5, 0.03, 0.01, 0.01) + body
+            elif r < 0.7:
+                body = FRONT5[int(rng.integers(1, 10)):] + body          # partial: an anchored adapter must not match
+            body = body[:int(rng.integers(20, 151))]
+            recs.append(("lk%d" % i, body, "", quals(rng, len(body))))
+        return recs
+    add("linked_adapter", fastq(linked_records(500)), [(FRONT5 + "..." + SMALL3, "linked")])
+    add("linked_adapter_ops", fastq(linked_records(300)), [(FRONT5 + "..." + SMALL3, "linked")],
+        extra=["--trim-n", "-m", "30", "--discard-untrimmed"], read_ops=dict(trim_n=True, minimum_length=30, discard_untrimmed=True))
+
     # --- the modifiers / filters around the adapter stage (default operation order) --------------------------------
     def lowq(recs, rng):                                   # qualities that decay towards the ends, some N ends
         out = []

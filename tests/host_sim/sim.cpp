@@ -134,7 +134,7 @@ static void sim_count_filter(FqOpsCounters& oc, int f) {
 int sim_trim_fastq(const atr_adapter_desc* descs, int n_adapters, const atr_trim_opts* o, const unsigned char* text,
                    long long nbytes, unsigned char* out_text, long long* out_bytes, long long* consumed, long long* counters,
                    long long* errors_front, long long* errors_back, long long* adjacent, atr_fastq_error* err,
-                   FqOpsCounters* oc) {
+                   FqOpsCounters* oc, const atr_adapter_desc* linked_back /* NULL, or the back adapter of a linked adapter */) {
     std::vector<uint32_t> nl;
     for (long long i = 0; i < nbytes; i++) {
         if (text[i] == '\n') nl.push_back((uint32_t)i);
@@ -201,6 +201,23 @@ int sim_trim_fastq(const atr_adapter_desc* descs, int n_adapters, const atr_trim
             else counters[4]++;
             if (!ap.front) adjacent[(size_t)m.adapter * 5 + (size_t)ap.adjacent]++;
             lo = ap.new_lo; hi = ap.new_hi;
+            if (linked_back) {                          // LinkedAdapter.match_to: the back adapter in what the front adapter left
+                atr_match mb;
+                im_clear(mb);
+                int used = 0;
+                int rc = sim_locate(linked_back, 0, 0, text + R.seq_b, R.seq_len, lo, hi, 1, 0, &mb, &used);
+                if (rc) return rc;
+                if (mb.status == ATR_ST_INVALID) { err->kind = ATR_FQ_INVALID_MATCH; err->record = -1; return ATR_E_FORMAT; }
+                const int wb = linked_back->flags;
+                FqApply ab;
+                if (fq_apply(mb, (wb == 14 || wb == 2) ? 0 : 1, lo, hi, text + R.seq_b, ab)) {
+                    if (ab.length <= o->max_len && ab.errors <= o->max_errors)
+                        (ab.front ? errors_front : errors_back)[((size_t)1 * (size_t)(o->max_len + 1) + (size_t)ab.length) * (size_t)(o->max_errors + 1) + (size_t)ab.errors]++;
+                    else counters[4]++;
+                    if (!ab.front) adjacent[(size_t)1 * 5 + (size_t)ab.adjacent]++;
+                    lo = ab.new_lo; hi = ab.new_hi;
+                }
+            }
         }
         (void)H;
         if (any) counters[1]++;

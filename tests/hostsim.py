@@ -36,7 +36,7 @@ def lib():
         L.sim_trim_fastq.argtypes = [C.POINTER(_abi.AtrAdapterDesc), C.c_int, C.POINTER(_abi.AtrTrimOpts), C.c_char_p,
                                      C.c_longlong, C.c_void_p, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong),
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_abi.AtrFastqError),
-                                     C.POINTER(SimOpsCounters)]
+                                     C.POINTER(SimOpsCounters), C.POINTER(_abi.AtrAdapterDesc)]
         L.sim_trim_fastq.restype = C.c_int
         L.sim_trim_fastq_pe.argtypes = [C.POINTER(_abi.AtrInsertDesc), C.POINTER(_abi.AtrAdapterDesc), C.c_int,
                                         C.POINTER(_abi.AtrAdapterDesc), C.c_int, C.c_void_p, C.c_void_p,
@@ -101,19 +101,30 @@ def trim_fastq(text, adapters, times=1, max_len=512, final=True, **read_ops):
     Returns (out bytes, TrimStats, consumed) or raises atropos_b200.fastq.FormatError."""
     import numpy as np
     from atropos_b200 import fastq
-    descs, keep = zip(*[a.descriptor() for a in adapters])
+    from atropos_b200.adapters import LINKED
+    back_ref = None
+    if len(adapters) == 1 and getattr(adapters[0], "where", None) == LINKED:
+        linked = adapters[0]
+        adapters = [linked.front_adapter, linked.back_adapter]
+        back_desc, back_keep = linked.back_adapter.descriptor()
+        back_ref = C.byref(back_desc)
+        descs, keep = zip(*[linked.front_adapter.descriptor()])
+        n_front = 1
+    else:
+        descs, keep = zip(*[a.descriptor() for a in adapters])
+        n_front = len(descs)
     arr = (_abi.AtrAdapterDesc * len(descs))(*descs)
     max_errors = max(int(a.max_error_rate * len(a.sequence)) for a in adapters)
     stats = fastq.TrimStats(len(adapters), max_len, max_errors)
-    opts = _abi.AtrTrimOpts(times, max_len, max_errors, int(bool(final)), 0, _abi.make_read_ops(**read_ops))
+    opts = _abi.AtrTrimOpts(times, max_len, max_errors, int(bool(final)), 0, None, _abi.make_read_ops(**read_ops))
     oc = SimOpsCounters()
     out = np.empty(max(len(text), 1), dtype=np.uint8)
     counters = np.zeros(5, dtype=np.int64)
     nout, consumed = C.c_longlong(0), C.c_longlong(0)
     err = _abi.AtrFastqError()
-    rc = lib().sim_trim_fastq(arr, len(descs), C.byref(opts), text, len(text), out.ctypes.data, C.byref(nout),
+    rc = lib().sim_trim_fastq(arr, n_front, C.byref(opts), text, len(text), out.ctypes.data, C.byref(nout),
                               C.byref(consumed), counters.ctypes.data, stats.errors_front.ctypes.data,
-                              stats.errors_back.ctypes.data, stats.adjacent.ctypes.data, C.byref(err), C.byref(oc))
+                              stats.errors_back.ctypes.data, stats.adjacent.ctypes.data, C.byref(err), C.byref(oc), back_ref)
     if rc == _abi.ATR_E_FORMAT:
         raise fastq.FormatError(fastq.format_error_message(np.frombuffer(text, dtype=np.uint8), err))
     if rc != 0:
