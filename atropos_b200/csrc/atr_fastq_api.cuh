@@ -296,8 +296,7 @@ extern "C" int atr_trim_fastq_host(atr_ctx* ctx, const atr_adapterset* set, cons
         CU(cudaMemcpy(d_stats + L.o_flags, ff.data(), nA, cudaMemcpyHostToDevice));
     }
     int64_t opos = 0, records_before = 0, done = 0;
-    // measurement knobs (never set in production): skip the D2H of the text / print per-phase device times
-    static const bool dbg_no_d2h = getenv("ATR_FQ_NO_D2H") != nullptr;
+    // measurement knob: ATR_FQ_TIMING=1 prints the kernels' device time and the host's waits to stderr
     static const bool dbg_timing = getenv("ATR_FQ_TIMING") != nullptr;
     double t_front = 0, t_back = 0, t_wait_front = 0, t_wait_back = 0;
     cudaEvent_t evs[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};
@@ -374,7 +373,7 @@ extern "C" int atr_trim_fastq_host(atr_ctx* ctx, const atr_adapterset* set, cons
         }
         if (opos + (int64_t)hb.out_bytes > out_cap) { result = fail(ctx, ATR_E_ARG, "out_cap too small for the trimmed text"); break; }
         // own stream: the next chunk's H2D into this slot must not queue behind this copy
-        if (hb.out_bytes && !dbg_no_d2h) {
+        if (hb.out_bytes) {
             CU(cudaMemcpyAsync(out_text + opos, f.outtext.p, (size_t)hb.out_bytes, cudaMemcpyDeviceToHost, f.out_stream));
             CU(cudaEventRecord(f.ev_d2h, f.out_stream));
             f.d2h_pending = 1;

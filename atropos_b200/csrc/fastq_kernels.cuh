@@ -26,6 +26,12 @@ struct FqCounters {
     unsigned long long records, with_adapters, bp_in, bp_out, overflow, invalid;
 };
 
+// one atomicAdd per warp: every lane of the warp must call this (convergent)
+__device__ __forceinline__ void fq_warp_add(unsigned long long* counter, unsigned v) {
+    const unsigned t = __reduce_add_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0 && t) atomicAdd(counter, (unsigned long long)t);
+}
+
 // 16 text bytes -> bit i set iff byte i == c. __vcmpeq4 gives 0xff per equal byte; the multiply gathers the four
 // low bits into bits 24..27 (distinct powers, no carries).
 __device__ __forceinline__ unsigned fq_eq_mask16(const uint4& v, unsigned c4) {
@@ -249,6 +255,7 @@ __global__ void __launch_bounds__(256) k_fq_apply(const unsigned char* __restric
                                                   int adapter_base) {
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     bool hit = false;
+    unsigned long long *h_addr = nullptr, *a_addr = nullptr;       // this read's histogram / adjacent-base counters
     if (r < n_rec) {
         atr_match m = matches[r];
         if (m.adapter >= 0) m.adapter = (int16_t)(m.adapter + adapter_base);   // linked adapters: the back adapter is index 1
@@ -260,16 +267,25 @@ __global__ void __launch_bounds__(256) k_fq_apply(const unsigned char* __restric
             if (round == 0) flags[r] = 1;                            // read.match is not None (filters.py:170-180)
             if (a.length <= max_len && a.errors <= max_errors) {
                 unsigned long long* h = a.front ? hist_front : hist_back;
-                atomicAdd(&h[((size_t)m.adapter * (size_t)(max_len + 1) + (size_t)a.length) * (size_t)(max_errors + 1) + (size_t)a.errors], 1ull);
+                h_addr = &h[((size_t)m.adapter * (size_t)(max_len + 1) + (size_t)a.length) * (size_t)(max_errors + 1) + (size_t)a.errors];
             } else {
                 atomicAdd(&ctr->overflow, 1ull);
             }
-            if (!a.front) atomicAdd(&adjacent[(size_t)m.adapter * 5 + (size_t)a.adjacent], 1ull);
+            if (!a.front) a_addr = &adjacent[(size_t)m.adapter * 5 + (size_t)a.adjacent];
             fwin[2 * r] = (uint16_t)a.new_lo; fwin[2 * r + 1] = (uint16_t)a.new_hi;
             if (more_rounds) { rwin[2 * r] = (uint16_t)a.new_lo; rwin[2 * r + 1] = (uint16_t)a.new_hi; }
         } else if (more_rounds) {
             rwin[2 * r] = 0; rwin[2 * r + 1] = 0;                // no match: the loop ends for this read (:145-147)
         }
+    }
+    // The removed lengths pile up on a few bins (3-mers at the read end, the full adapter length): lanes that hit the
+    // same counter add once per warp.
+    {
+        const int lane = threadIdx.x & 31;
+        unsigned peers = __match_any_sync(0xffffffffu, (unsigned long long)h_addr);
+        if (h_addr != nullptr && lane == __ffs((int)peers) - 1) atomicAdd(h_addr, (unsigned long long)__popc(peers));
+        peers = __match_any_sync(0xffffffffu, (unsigned long long)a_addr);
+        if (a_addr != nullptr && lane == __ffs((int)peers) - 1) atomicAdd(a_addr, (unsigned long long)__popc(peers));
     }
     if (round == 0) {
         const unsigned b = __ballot_sync(0xffffffffu, hit);
@@ -380,61 +396,77 @@ __global__ void __launch_bounds__(256) k_pe_apply(unsigned char* __restrict__ t1
                                                   FqOpsCounters* __restrict__ oc, int mismatch_action,
                                                   const unsigned char* __restrict__ comp) {
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n) return;
-    const FqRec A = r1[r], B = r2[r];
-    int len1 = A.seq_len;
-    const int len2 = B.seq_len;
-    PeMatch m1, m2;
-    int hit = 0, invalid = 0, im[4];
-    bool correct = false;
-    fq_pe_decide(ins[r], fb1[r], fb2[r], len1, len2, min_insert_len, symmetric, mismatch_action, m1, m2, hit, invalid, correct, im);
-    if (invalid) atomicAdd(&ctr->invalid, 1ull);
-    if (hit) atomicAdd(&ctr->insert_matches, 1ull);
-    if (correct) {                                     // error correction edits this chunk's copy of the text in place
-        int c1 = 0, c2 = 0, nl1 = len1;
-        if (!fq_pe_correct(t1 + A.seq_b, t1 + A.qual_b, len1, t2 + B.seq_b, t2 + B.qual_b, len2, im[0], im[1], im[2], im[3],
-                           mismatch_action, comp, c1, c2, nl1)) atomicAdd(&ctr->correction_errors, 1ull);
-        if (c1 || c2) atomicAdd(&ctr->records_corrected, 1ull);
-        if (c1) atomicAdd(&ctr->bp_corrected[0], (unsigned long long)c1);
-        if (c2) atomicAdd(&ctr->bp_corrected[1], (unsigned long long)c2);
-        len1 = nl1;
+    // per-thread increments, added once per warp at the end (every lane reaches it)
+    unsigned n_invalid = 0, n_hit = 0, n_cerr = 0, n_corr = 0, bpc1 = 0, bpc2 = 0, with1 = 0, with2 = 0, n_over = 0, bpn1 = 0, bpn2 = 0;
+    int flt = -1;
+    unsigned long long *h1 = nullptr, *h2 = nullptr, *a1 = nullptr, *a2 = nullptr;
+    if (r < n) {
+        const FqRec A = r1[r], B = r2[r];
+        int len1 = A.seq_len;
+        const int len2 = B.seq_len;
+        PeMatch m1, m2;
+        int hit = 0, invalid = 0, im[4];
+        bool correct = false;
+        fq_pe_decide(ins[r], fb1[r], fb2[r], len1, len2, min_insert_len, symmetric, mismatch_action, m1, m2, hit, invalid, correct, im);
+        n_invalid = invalid; n_hit = hit;
+        if (correct) {                                     // error correction edits this chunk's copy of the text in place
+            int c1 = 0, c2 = 0, nl1 = len1;
+            if (!fq_pe_correct(t1 + A.seq_b, t1 + A.qual_b, len1, t2 + B.seq_b, t2 + B.qual_b, len2, im[0], im[1], im[2], im[3],
+                               mismatch_action, comp, c1, c2, nl1)) n_cerr = 1;
+            n_corr = (c1 || c2); bpc1 = (unsigned)c1; bpc2 = (unsigned)c2;
+            len1 = nl1;
+        }
+        FqApply ap;
+        bool counted;
+        const int k1 = fq_pe_trim(m1, len1, t1 + A.seq_b, ap, counted);
+        with1 = m1.present;
+        if (counted) {
+            if (ap.length <= max_len && ap.errors <= max_errors) h1 = &hist1[(size_t)ap.length * (size_t)(max_errors + 1) + (size_t)ap.errors];
+            else n_over++;
+            a1 = &adj1[ap.adjacent];
+        }
+        const int k2 = fq_pe_trim(m2, len2, t2 + B.seq_b, ap, counted);
+        with2 = m2.present;
+        if (counted) {
+            if (ap.length <= max_len && ap.errors <= max_errors) h2 = &hist2[(size_t)ap.length * (size_t)(max_errors + 1) + (size_t)ap.errors];
+            else n_over++;
+            a2 = &adj2[ap.adjacent];
+        }
+        // NEndTrimmer on both reads, then the pair filters ("any": either read)
+        int lo1 = 0, hi1 = k1, lo2 = 0, hi2 = k2;
+        if (ops.trim_n) {
+            fq_trim_n(t1 + A.seq_b, lo1, hi1, bpn1);
+            fq_trim_n(t2 + B.seq_b, lo2, hi2, bpn2);
+        }
+        flt = fq_filter(ops, t1 + A.seq_b, lo1, hi1, m1.present != 0, t2 + B.seq_b, lo2, hi2, m2.present != 0, true);
+        if (flt) { lo1 = lo2 = 1; hi1 = hi2 = 0; }
+        fwin1[2 * r] = (uint16_t)lo1; fwin1[2 * r + 1] = (uint16_t)hi1;
+        fwin2[2 * r] = (uint16_t)lo2; fwin2[2 * r + 1] = (uint16_t)hi2;
     }
-    FqApply ap;
-    bool counted;
-    const int k1 = fq_pe_trim(m1, len1, t1 + A.seq_b, ap, counted);
-    if (m1.present) atomicAdd(&ctr->with_adapters[0], 1ull);
-    if (counted) {
-        if (ap.length <= max_len && ap.errors <= max_errors) atomicAdd(&hist1[(size_t)ap.length * (size_t)(max_errors + 1) + (size_t)ap.errors], 1ull);
-        else atomicAdd(&ctr->overflow, 1ull);
-        atomicAdd(&adj1[ap.adjacent], 1ull);
+    const int lane = threadIdx.x & 31;
+    unsigned long long* addrs[4] = {h1, h2, a1, a2};
+#pragma unroll
+    for (int q = 0; q < 4; q++) {                          // mates trim at the same place: the same bins in both histograms
+        const unsigned peers = __match_any_sync(0xffffffffu, (unsigned long long)addrs[q]);
+        if (addrs[q] != nullptr && lane == __ffs((int)peers) - 1) atomicAdd(addrs[q], (unsigned long long)__popc(peers));
     }
-    const int k2 = fq_pe_trim(m2, len2, t2 + B.seq_b, ap, counted);
-    if (m2.present) atomicAdd(&ctr->with_adapters[1], 1ull);
-    if (counted) {
-        if (ap.length <= max_len && ap.errors <= max_errors) atomicAdd(&hist2[(size_t)ap.length * (size_t)(max_errors + 1) + (size_t)ap.errors], 1ull);
-        else atomicAdd(&ctr->overflow, 1ull);
-        atomicAdd(&adj2[ap.adjacent], 1ull);
-    }
-    // NEndTrimmer on both reads, then the pair filters ("any": either read)
-    int lo1 = 0, hi1 = k1, lo2 = 0, hi2 = k2;
-    if (ops.trim_n) {
-        unsigned bp_n;
-        fq_trim_n(t1 + A.seq_b, lo1, hi1, bp_n);
-        if (bp_n) atomicAdd(&oc->bp_n_ends[0], (unsigned long long)bp_n);
-        fq_trim_n(t2 + B.seq_b, lo2, hi2, bp_n);
-        if (bp_n) atomicAdd(&oc->bp_n_ends[1], (unsigned long long)bp_n);
-    }
-    const int flt = fq_filter(ops, t1 + A.seq_b, lo1, hi1, m1.present != 0, t2 + B.seq_b, lo2, hi2, m2.present != 0, true);
-    if (flt) {
-        unsigned long long* c = flt == 1 ? &oc->too_short : flt == 2 ? &oc->too_long : flt == 3 ? &oc->too_many_n
-                                : flt == 4 ? &oc->discarded_trimmed : &oc->discarded_untrimmed;
-        atomicAdd(c, 1ull);
-        lo1 = lo2 = 1; hi1 = hi2 = 0;
-    } else {
-        atomicAdd(&oc->records_written, 1ull);
-    }
-    fwin1[2 * r] = (uint16_t)lo1; fwin1[2 * r + 1] = (uint16_t)hi1;
-    fwin2[2 * r] = (uint16_t)lo2; fwin2[2 * r + 1] = (uint16_t)hi2;
+    fq_warp_add(&ctr->invalid, n_invalid);
+    fq_warp_add(&ctr->insert_matches, n_hit);
+    fq_warp_add(&ctr->correction_errors, n_cerr);
+    fq_warp_add(&ctr->records_corrected, n_corr);
+    fq_warp_add(&ctr->bp_corrected[0], bpc1);
+    fq_warp_add(&ctr->bp_corrected[1], bpc2);
+    fq_warp_add(&ctr->with_adapters[0], with1);
+    fq_warp_add(&ctr->with_adapters[1], with2);
+    fq_warp_add(&ctr->overflow, n_over);
+    fq_warp_add(&oc->bp_n_ends[0], bpn1);
+    fq_warp_add(&oc->bp_n_ends[1], bpn2);
+    fq_warp_add(&oc->records_written, flt == 0);
+    fq_warp_add(&oc->too_short, flt == 1);
+    fq_warp_add(&oc->too_long, flt == 2);
+    fq_warp_add(&oc->too_many_n, flt == 3);
+    fq_warp_add(&oc->discarded_trimmed, flt == 4);
+    fq_warp_add(&oc->discarded_untrimmed, flt == 5);
 }
 
 // adapter mode: NEndTrimmer + the pair filters after two independent AdapterCutters (flags: bit 0 = read.match is set)
@@ -444,27 +476,28 @@ __global__ void __launch_bounds__(256) k_pe_post(const unsigned char* __restrict
                                                  uint16_t* __restrict__ fwin2, const unsigned char* __restrict__ flags1,
                                                  const unsigned char* __restrict__ flags2, FqOpsCounters* __restrict__ oc) {
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n) return;
-    const FqRec A = r1[r], B = r2[r];
-    int lo1 = fwin1[2 * r], hi1 = fwin1[2 * r + 1], lo2 = fwin2[2 * r], hi2 = fwin2[2 * r + 1];
-    if (ops.trim_n) {
-        unsigned bp_n;
-        fq_trim_n(t1 + A.seq_b, lo1, hi1, bp_n);
-        if (bp_n) atomicAdd(&oc->bp_n_ends[0], (unsigned long long)bp_n);
-        fq_trim_n(t2 + B.seq_b, lo2, hi2, bp_n);
-        if (bp_n) atomicAdd(&oc->bp_n_ends[1], (unsigned long long)bp_n);
+    unsigned bpn1 = 0, bpn2 = 0;
+    int flt = -1;
+    if (r < n) {
+        const FqRec A = r1[r], B = r2[r];
+        int lo1 = fwin1[2 * r], hi1 = fwin1[2 * r + 1], lo2 = fwin2[2 * r], hi2 = fwin2[2 * r + 1];
+        if (ops.trim_n) {
+            fq_trim_n(t1 + A.seq_b, lo1, hi1, bpn1);
+            fq_trim_n(t2 + B.seq_b, lo2, hi2, bpn2);
+        }
+        flt = fq_filter(ops, t1 + A.seq_b, lo1, hi1, flags1[r] != 0, t2 + B.seq_b, lo2, hi2, flags2[r] != 0, true);
+        if (flt) { lo1 = lo2 = 1; hi1 = hi2 = 0; }
+        fwin1[2 * r] = (uint16_t)lo1; fwin1[2 * r + 1] = (uint16_t)hi1;
+        fwin2[2 * r] = (uint16_t)lo2; fwin2[2 * r + 1] = (uint16_t)hi2;
     }
-    const int flt = fq_filter(ops, t1 + A.seq_b, lo1, hi1, flags1[r] != 0, t2 + B.seq_b, lo2, hi2, flags2[r] != 0, true);
-    if (flt) {
-        unsigned long long* c = flt == 1 ? &oc->too_short : flt == 2 ? &oc->too_long : flt == 3 ? &oc->too_many_n
-                                : flt == 4 ? &oc->discarded_trimmed : &oc->discarded_untrimmed;
-        atomicAdd(c, 1ull);
-        lo1 = lo2 = 1; hi1 = hi2 = 0;
-    } else {
-        atomicAdd(&oc->records_written, 1ull);
-    }
-    fwin1[2 * r] = (uint16_t)lo1; fwin1[2 * r + 1] = (uint16_t)hi1;
-    fwin2[2 * r] = (uint16_t)lo2; fwin2[2 * r + 1] = (uint16_t)hi2;
+    fq_warp_add(&oc->bp_n_ends[0], bpn1);
+    fq_warp_add(&oc->bp_n_ends[1], bpn2);
+    fq_warp_add(&oc->records_written, flt == 0);
+    fq_warp_add(&oc->too_short, flt == 1);
+    fq_warp_add(&oc->too_long, flt == 2);
+    fq_warp_add(&oc->too_many_n, flt == 3);
+    fq_warp_add(&oc->discarded_trimmed, flt == 4);
+    fq_warp_add(&oc->discarded_untrimmed, flt == 5);
 }
 
 // bytes consumed by the first n records (n < the chunk's complete records): -> mapped pinned host memory
@@ -477,23 +510,22 @@ __global__ void __launch_bounds__(256) k_fq_post(const unsigned char* __restrict
                                                  const __grid_constant__ atr_read_ops ops, uint16_t* __restrict__ fwin,
                                                  const unsigned char* __restrict__ flags, FqOpsCounters* __restrict__ oc) {
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n_rec) return;
-    const FqRec R = recs[r];
-    int lo = fwin[2 * r], hi = fwin[2 * r + 1];
-    const unsigned char* seq = text + R.seq_b;
-    if (ops.trim_n) {
-        unsigned bp_n;
-        fq_trim_n(seq, lo, hi, bp_n);
-        if (bp_n) atomicAdd(&oc->bp_n_ends[0], (unsigned long long)bp_n);
+    unsigned bp_n = 0;
+    int f = -1;                                        // -1 no record, 0 kept, 1..5 the filter that fired
+    if (r < n_rec) {
+        const FqRec R = recs[r];
+        int lo = fwin[2 * r], hi = fwin[2 * r + 1];
+        const unsigned char* seq = text + R.seq_b;
+        if (ops.trim_n) fq_trim_n(seq, lo, hi, bp_n);
+        f = fq_filter(ops, seq, lo, hi, flags[r] != 0, seq, 0, 0, false, false);
+        if (f) { lo = 1; hi = 0; }
+        fwin[2 * r] = (uint16_t)lo; fwin[2 * r + 1] = (uint16_t)hi;
     }
-    const int f = fq_filter(ops, seq, lo, hi, flags[r] != 0, seq, 0, 0, false, false);
-    if (f) {
-        unsigned long long* c = f == 1 ? &oc->too_short : f == 2 ? &oc->too_long : f == 3 ? &oc->too_many_n
-                                : f == 4 ? &oc->discarded_trimmed : &oc->discarded_untrimmed;
-        atomicAdd(c, 1ull);
-        lo = 1; hi = 0;
-    } else {
-        atomicAdd(&oc->records_written, 1ull);
-    }
-    fwin[2 * r] = (uint16_t)lo; fwin[2 * r + 1] = (uint16_t)hi;
+    fq_warp_add(&oc->bp_n_ends[0], bp_n);
+    fq_warp_add(&oc->records_written, f == 0);
+    fq_warp_add(&oc->too_short, f == 1);
+    fq_warp_add(&oc->too_long, f == 2);
+    fq_warp_add(&oc->too_many_n, f == 3);
+    fq_warp_add(&oc->discarded_trimmed, f == 4);
+    fq_warp_add(&oc->discarded_untrimmed, f == 5);
 }

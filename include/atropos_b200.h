@@ -3,7 +3,9 @@
  *
  * This is the drop-in boundary for ONE hot path of jdidion/atropos: the compiled extension
  * module `atropos.align._align` (Cython) and the two Python methods that call it per read,
- * `Adapter.match_to()` and `InsertAligner.match_insert()`.  Every entry point below names the
+ * `Adapter.match_to()` and `InsertAligner.match_insert()` -- plus, at the end of this file, the
+ * path's immediate callers as whole-batch calls (FASTQ text in, trimmed FASTQ text out:
+ * atr_trim_fastq_host, atr_trim_fastq_pe_host).  Every entry point below names the
  * reference interface it replaces (paths relative to the reference checkout).  The reference-side
  * binding a maintainer would add (a ctypes stub inside atropos/align/__init__.py) is shown in
  * INTEGRATION.md; `atropos_b200/` in this repository is that binding plus batched twins of the
