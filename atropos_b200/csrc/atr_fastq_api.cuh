@@ -47,6 +47,7 @@ void fq_add_ops(atr_read_ops_stats& dst, const FqOpsCounters& c) {
         dst.bp_cut[i] += (int64_t)c.bp_cut[i];
         dst.bp_quality[i] += (int64_t)c.bp_quality[i];
         dst.bp_n_ends[i] += (int64_t)c.bp_n_ends[i];
+        dst.bp_nextseq[i] += (int64_t)c.bp_nextseq[i];
     }
     dst.too_short += (int64_t)c.too_short;
     dst.too_long += (int64_t)c.too_long;

@@ -258,7 +258,7 @@ ATR_HD int fq_pe_trim(const PeMatch& m, int len, const unsigned char* __restrict
 // ---- the modifiers and filters around the adapter stage (atr_read_ops) ------------------------------------------------
 // Device-side counters, one block per call.
 struct FqOpsCounters {
-    unsigned long long bp_cut[2], bp_quality[2], bp_n_ends[2];
+    unsigned long long bp_cut[2], bp_quality[2], bp_n_ends[2], bp_nextseq[2];
     unsigned long long too_short, too_long, too_many_n, discarded_trimmed, discarded_untrimmed;
     unsigned long long records_written;
 };
@@ -282,12 +282,25 @@ ATR_HD void fq_quality_trim_index(const unsigned char* __restrict__ q, int len, 
     if (start >= stop) { start = 0; stop = 0; }
 }
 
-// UnconditionalCutter then QualityTrimmer on one record, BEFORE the adapters: the record table entry is narrowed to what
+// nextseq_trim_index (commands/trim/_qualtrim.pyx:52-84): the 3' BWA rule with every 'G' counted as quality cutoff - 1
+ATR_HD int fq_nextseq_trim_index(const unsigned char* __restrict__ seq, const unsigned char* __restrict__ q, int len, int cutoff, int base) {
+    int s = 0, max_qual = 0, max_i = len;
+    for (int i = len - 1; i >= 0; i--) {
+        int qq = (int)q[i] - base;
+        if (seq[i] == 'G') qq = cutoff - 1;
+        s += cutoff - qq;
+        if (s < 0) break;
+        if (s > max_qual) { max_qual = s; max_i = i; }
+    }
+    return max_i;
+}
+
+// UnconditionalCutter, NextseqQualityTrimmer, then QualityTrimmer on one record, BEFORE the adapters: the record table entry is narrowed to what
 // is left (nothing downstream needs the removed ends). bp_cut / bp_quality get Trimmer.trimmed_bases' increments:
 // clip() counts the nominal lengths (modifiers.py:73-82, _seqio.pyx:76-88), subseq() begin + (len - end) (:54-71).
 ATR_HD void fq_pre_ops(const atr_read_ops& o, int side, const unsigned char* __restrict__ text, FqRec& R,
-                       unsigned& bp_cut, unsigned& bp_quality) {
-    bp_cut = bp_quality = 0;
+                       unsigned& bp_cut, unsigned& bp_quality, unsigned& bp_nextseq) {
+    bp_cut = bp_quality = bp_nextseq = 0;
     int lo = 0, hi = R.seq_len;
     const int front = o.cut_front[side], back = o.cut_back[side];
     if ((front || back) && hi - lo > 0) {
@@ -297,6 +310,11 @@ ATR_HD void fq_pre_ops(const atr_read_ops& o, int side, const unsigned char* __r
         if (a > b) a = b;
         bp_cut = (unsigned)(front + (back < 0 ? -back : 0));
         hi = lo + b; lo = lo + a;
+    }
+    if (o.nextseq_trim[side] >= 0 && hi - lo > 0) {          // subseq(read, end=stop): counts len - stop (modifiers.py:742-746)
+        const int stop = fq_nextseq_trim_index(text + R.seq_b + lo, text + R.qual_b + lo, hi - lo, o.nextseq_trim[side], o.quality_base);
+        bp_nextseq = (unsigned)((hi - lo) - stop);
+        hi = lo + stop;
     }
     if ((o.quality_front > 0 || o.quality_back > 0) && hi - lo > 0) {
         int start, stop;

@@ -215,25 +215,27 @@ __global__ void __launch_bounds__(256) k_fq_pre(const unsigned char* __restrict_
                                                 const __grid_constant__ atr_read_ops ops, int side, long long* __restrict__ seq_len64,
                                                 unsigned long long* __restrict__ bp_in, FqOpsCounters* __restrict__ oc) {
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned long long bp = 0, cut = 0, qual = 0;
+    unsigned long long bp = 0, cut = 0, qual = 0, nxs = 0;
     if (r < n_rec) {
         FqRec R = recs[r];
         bp = R.seq_len;
-        unsigned c, q;
-        fq_pre_ops(ops, side, text, R, c, q);
-        cut = c; qual = q;
-        if (c || q) { recs[r] = R; seq_len64[r] = R.seq_len; }
+        unsigned c, q, g;
+        fq_pre_ops(ops, side, text, R, c, q, g);
+        cut = c; qual = q; nxs = g;
+        if (c || q || g) { recs[r] = R; seq_len64[r] = R.seq_len; }
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
         bp += __shfl_down_sync(0xffffffffu, bp, d);
         cut += __shfl_down_sync(0xffffffffu, cut, d);
         qual += __shfl_down_sync(0xffffffffu, qual, d);
+        nxs += __shfl_down_sync(0xffffffffu, nxs, d);
     }
     if ((threadIdx.x & 31) == 0) {
         if (bp) atomicAdd(bp_in, bp);
         if (cut) atomicAdd(&oc->bp_cut[side], cut);
         if (qual) atomicAdd(&oc->bp_quality[side], qual);
+        if (nxs) atomicAdd(&oc->bp_nextseq[side], nxs);
     }
 }
 

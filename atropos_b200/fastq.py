@@ -27,7 +27,7 @@ _BASES = ('A', 'C', 'G', 'T', '')
 def new_ops_stats():
     """Trimmer.trimmed_bases per modifier ([read 1, read 2]) and FilterWrapper.filtered per filter, as the report
     names them (modifiers.py:84-88, filters.py:48-52), plus the records written."""
-    d = {"bp_cut": [0, 0], "bp_quality": [0, 0], "bp_n_ends": [0, 0]}
+    d = {"bp_cut": [0, 0], "bp_quality": [0, 0], "bp_n_ends": [0, 0], "bp_nextseq": [0, 0]}
     d.update({k: 0 for k in _abi.OPS_STAT_KEYS})
     return d
 
@@ -41,7 +41,7 @@ def merge_ops_stats(mine, theirs):
 
 
 def _add_ops_stats(dst, st):
-    for k in ("bp_cut", "bp_quality", "bp_n_ends"):
+    for k in ("bp_cut", "bp_quality", "bp_n_ends", "bp_nextseq"):
         dst[k] = [dst[k][i] + int(getattr(st, k)[i]) for i in range(2)]
     for k in _abi.OPS_STAT_KEYS:
         dst[k] += int(getattr(st, k))

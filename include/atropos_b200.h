@@ -264,6 +264,8 @@ typedef struct atr_read_ops {
     int32_t maximum_length;   /* -M: TooLongReadFilter, < 0 = off (filters.py:130-140) */
     int32_t discard_trimmed;  /* --discard-trimmed: TrimmedFilter (filters.py:176-180) */
     int32_t discard_untrimmed;/* --discard-untrimmed: UntrimmedFilter (filters.py:170-174) */
+    int32_t nextseq_trim[2];  /* --nextseq-trim CUTOFF per read, < 0 = off (NextseqQualityTrimmer modifiers.py:732-746,
+                                 nextseq_trim_index _qualtrim.pyx:52-84): after the cut, before -q ("CGQAW") */
     int32_t legacy_first;     /* paired-end "legacy mode" (paired == 'first', trim/cli.py:629-645: no option touches read 2):
                                  the filters look at read 1 only (SingleWrapper, filters.py:54-61) */
     int32_t pad;
@@ -273,7 +275,7 @@ typedef struct atr_read_ops {
 /* Trimmer.trimmed_bases per modifier and read (modifiers.py:45-88), FilterWrapper.filtered per filter (filters.py:18-52;
  * paired-end: the pair filter "any", PairedWrapper with min_affected = 1), and what was written. ADDED to. */
 typedef struct atr_read_ops_stats {
-    int64_t bp_cut[2], bp_quality[2], bp_n_ends[2];
+    int64_t bp_cut[2], bp_quality[2], bp_n_ends[2], bp_nextseq[2];
     int64_t too_short, too_long, too_many_n, discarded_trimmed, discarded_untrimmed;
     int64_t records_written;  /* reads (pairs) that passed every filter; their bases are bp_out of the enclosing struct */
 } atr_read_ops_stats;

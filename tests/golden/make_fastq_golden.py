@@ -78,6 +78,7 @@ def ops_stats(rj, read):
     bp = lambda name: [int(x or 0) for x in mods[name]["bp_trimmed"]] if name in mods else None
     nf = lambda name: flt[name]["records_filtered"] if name in flt else None
     return {"bp_cut": bp("UnconditionalCutter"), "bp_quality": bp("QualityTrimmer"), "bp_n_ends": bp("NEndTrimmer"),
+            "bp_nextseq": bp("NextseqQualityTrimmer"),
             "too_short": nf("too_short"), "too_long": nf("too_long"), "too_many_n": nf("too_many_n"),
             "discarded_trimmed": nf("TrimmedFilter"), "discarded_untrimmed": nf("UntrimmedFilter"),
             "records_written": t["formatters"]["records_written"]}
@@ -209,6 +210,16 @@ def main():
         extra=["-u", "5", "-u", "-3", "-M", "120", "--max-n", "2"], read_ops=dict(cut=[5, -3], maximum_length=120, max_n=2))
     add("ops_q_single_maxn_frac_discard_untrimmed", fastq(lowq(make_records(rng, 400, one, ragged=True), rng)), one,
         extra=["-q", "20", "--max-n", "0.05", "--discard-untrimmed"], read_ops=dict(quality_cutoff=[20], max_n=0.05, discard_untrimmed=True))
+    def nextseq(recs):                                      # dark cycles: runs of high-quality G at the 3' end
+        out = []
+        for name, seq, name2, q in recs:
+            if rng.random() < 0.5 and len(seq) > 20:
+                g = min(int(rng.integers(1, 30)), len(seq))
+                seq = seq[:len(seq) - g] + "G" * g
+            out.append((name, seq, name2, q))
+        return out
+    add("ops_nextseq_quality", fastq(nextseq(lowq(make_records(rng, 400, one, ragged=True), rng))), one,
+        extra=["--nextseq-trim", "20", "-q", "10", "-m", "15"], read_ops=dict(nextseq_trim=20, quality_cutoff=[10], minimum_length=15))
     add("ops_panel_times2_all", fastq(lowq(make_records(rng, 500, panel), rng)), panel, times=2,
         extra=["-u", "2", "-q", "10,10", "--trim-n", "-m", "20", "-M", "140", "--discard-trimmed"],
         read_ops=dict(cut=[2], quality_cutoff=[10, 10], trim_n=True, minimum_length=20, maximum_length=140, discard_trimmed=True))

@@ -79,6 +79,7 @@ def ops_stats(rj):
     bp = lambda name: [int(x or 0) for x in mods[name]["bp_trimmed"]] if name in mods else None
     nf = lambda name: flt[name]["records_filtered"] if name in flt else None
     return {"bp_cut": bp("UnconditionalCutter"), "bp_quality": bp("QualityTrimmer"), "bp_n_ends": bp("NEndTrimmer"),
+            "bp_nextseq": bp("NextseqQualityTrimmer"),
             "too_short": nf("too_short"), "too_long": nf("too_long"), "too_many_n": nf("too_many_n"),
             "discarded_trimmed": nf("TrimmedFilter"), "discarded_untrimmed": nf("UntrimmedFilter"),
             "records_written": t["formatters"]["records_written"]}

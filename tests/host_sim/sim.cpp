@@ -177,9 +177,9 @@ int sim_trim_fastq(const atr_adapter_desc* descs, int n_adapters, const atr_trim
     for (long long r = 0; r < n_rec; r++) {
         FqRec R = recs[(size_t)r];
         counters[0]++; counters[2] += R.seq_len;
-        unsigned bpc, bpq;
-        fq_pre_ops(o->ops, 0, text, R, bpc, bpq);
-        oc->bp_cut[0] += bpc; oc->bp_quality[0] += bpq;
+        unsigned bpc, bpq, bpg;
+        fq_pre_ops(o->ops, 0, text, R, bpc, bpq, bpg);
+        oc->bp_cut[0] += bpc; oc->bp_quality[0] += bpq; oc->bp_nextseq[0] += bpg;
         int lo = 0, hi = R.seq_len;
         bool any = false;
         for (int round = 0; round < o->times; round++) {
@@ -319,11 +319,11 @@ int sim_trim_fastq_pe(const atr_insert_desc* idesc, const atr_adapter_desc* d1, 
     for (long long r = 0; r < n; r++) {
         FqRec A = R1[(size_t)r], B = R2[(size_t)r];
         counters[0]++; counters[4] += A.seq_len; counters[5] += B.seq_len;
-        unsigned bpc, bpq;
-        fq_pre_ops(o->ops, 0, text1, A, bpc, bpq);
-        oc->bp_cut[0] += bpc; oc->bp_quality[0] += bpq;
-        fq_pre_ops(o->ops, 1, text2, B, bpc, bpq);
-        oc->bp_cut[1] += bpc; oc->bp_quality[1] += bpq;
+        unsigned bpc, bpq, bpg;
+        fq_pre_ops(o->ops, 0, text1, A, bpc, bpq, bpg);
+        oc->bp_cut[0] += bpc; oc->bp_quality[0] += bpq; oc->bp_nextseq[0] += bpg;
+        fq_pre_ops(o->ops, 1, text2, B, bpc, bpq, bpg);
+        oc->bp_cut[1] += bpc; oc->bp_quality[1] += bpq; oc->bp_nextseq[1] += bpg;
         int len1 = A.seq_len;
         const int len2 = B.seq_len;
         int k1 = len1, k2 = len2;
