@@ -311,27 +311,10 @@ __global__ void __launch_bounds__(256) k_fq_outlen(const FqRec* __restrict__ rec
     if ((threadIdx.x & 31) == 0 && bp) atomicAdd(bp_out, bp);
 }
 
-// Warp-cooperative copy of `len` bytes between arbitrarily aligned addresses: byte stores up to the destination's
-// 4-byte boundary, then one aligned 32-bit store per lane built from two aligned source words (funnel shift), then the
-// tail. Reads up to 3 bytes past src + len inside the same (padded) buffer.
-__device__ __forceinline__ void fq_warp_copy(unsigned char* __restrict__ dst, const unsigned char* __restrict__ src, int len, int lane) {
-    int head = (int)((4u - (unsigned)(reinterpret_cast<uintptr_t>(dst) & 3u)) & 3u);
-    if (head > len) head = len;
-    if (lane < head) dst[lane] = src[lane];
-    const int nwords = (len - head) >> 2;
-    const unsigned char* s0 = src + head;
-    const unsigned sh = (unsigned)(reinterpret_cast<uintptr_t>(s0) & 3u) * 8u;
-    const uint32_t* sw = reinterpret_cast<const uint32_t*>(s0 - (sh >> 3));
-    uint32_t* dw = reinterpret_cast<uint32_t*>(dst + head);
-    for (int t = lane; t < nwords; t += 32) {
-        const uint32_t a = sw[t];
-        dw[t] = sh ? __funnelshift_r(a, sw[t + 1], sh) : a;
-    }
-    const int done = head + 4 * nwords;
-    if (lane < len - done) dst[done + lane] = src[done + lane];
-}
-
-// formatted records: warp per record, '@name' / sequence / '+[name]' / qualities as four word-wise copies
+// formatted records: warp per record. The record is produced as aligned 32-bit words of the output: a word that lies
+// inside one of the four copied pieces ('@name', sequence, name after '+', qualities) is fetched from the text with two
+// aligned loads and a funnel shift; the few words that touch a piece boundary or a literal ('\n', '+'), the bytes
+// before the first aligned word and the last bytes are written bytewise by one lane each in a single pass.
 __global__ void __launch_bounds__(256) k_fq_format(const unsigned char* __restrict__ text, const FqRec* __restrict__ recs,
                                                    const uint16_t* __restrict__ fwin, const long long* __restrict__ out_off,
                                                    long long n_rec, unsigned char* __restrict__ out, FqInfo* __restrict__ info) {
@@ -340,20 +323,46 @@ __global__ void __launch_bounds__(256) k_fq_format(const unsigned char* __restri
     const int lane = threadIdx.x & 31;
     const FqRec R = recs[r];
     const int lo = fwin[2 * r], hi = fwin[2 * r + 1];
-    const uint32_t total = lo <= hi ? fq_out_len(R, lo, hi) : 0u;
+    const int total = lo <= hi ? (int)fq_out_len(R, lo, hi) : 0;
     unsigned char* dst = out + out_off[r];
     if (total) {
-        const int w = hi - lo, H = R.hdr_len;
-        const int P = R.name2 ? H : 1;
-        fq_warp_copy(dst, text + R.hdr_b, H, lane);
-        fq_warp_copy(dst + H + 1, text + R.seq_b + lo, w, lane);
-        if (P > 1) fq_warp_copy(dst + H + 1 + w + 2, text + R.hdr_b + 1, P - 1, lane);
-        fq_warp_copy(dst + H + 1 + w + 1 + P + 1, text + R.qual_b + lo, w, lane);
-        if (lane == 0) dst[H] = '\n';
-        if (lane == 1) dst[H + 1 + w] = '\n';
-        if (lane == 2) dst[H + 1 + w + 1] = '+';
-        if (lane == 3) dst[H + 1 + w + 1 + P] = '\n';
-        if (lane == 4) dst[total - 1] = '\n';
+        const int w = hi - lo, H = R.hdr_len, P = R.name2 ? H : 1;
+        // output coordinates: [0,H) header | H '\n' | [s2,e2) sequence | e2 '\n' | e2+1 '+' | [s3,e3) name | e3 '\n' | [s4,e4) qualities | e4 '\n'
+        const int s2 = H + 1, e2 = s2 + w, s3 = e2 + 2, e3 = s3 + P - 1, s4 = e3 + 1, e4 = s4 + w;
+        // source offset such that text[off + i] is output byte i inside a piece
+        const long long o1 = (long long)R.hdr_b, o2 = (long long)R.seq_b + lo - s2, o3 = (long long)R.hdr_b + 1 - s3,
+                        o4 = (long long)R.qual_b + lo - s4;
+        const int head = (int)((4u - (unsigned)(reinterpret_cast<uintptr_t>(dst) & 3u)) & 3u);
+        const int nwords = total > head ? (total - head) >> 2 : 0;
+        uint32_t* dw = reinterpret_cast<uint32_t*>(dst + head);
+        for (int t = lane; t < nwords; t += 32) {
+            const int i = head + 4 * t, j = i + 3;
+            long long off;
+            if (j < H) off = o1;
+            else if (i >= s2 && j < e2) off = o2;
+            else if (i >= s4 && j < e4) off = o4;
+            else if (i >= s3 && j < e3) off = o3;
+            else continue;                                        // touches a boundary: the bytewise pass below
+            const unsigned char* p = text + (off + i);
+            const unsigned sh = (unsigned)(reinterpret_cast<uintptr_t>(p) & 3u) * 8u;
+            const uint32_t* pw = reinterpret_cast<const uint32_t*>(p - (sh >> 3));
+            const uint32_t a = pw[0];
+            dw[t] = sh ? __funnelshift_r(a, pw[1], sh) : a;
+        }
+        // bytewise: four runs of up to 8 bytes around the boundaries (lanes 0-7, 8-15, 16-23, 24-31) ...
+        {
+            const int run = lane >> 3, k = lane & 7;
+            const int start = run == 0 ? H - 3 : run == 1 ? e2 - 3 : run == 2 ? e3 - 3 : e4 - 3;
+            const int stop = run == 0 ? H + 3 : run == 1 ? e2 + 4 : run == 2 ? e3 + 3 : e4;       // inclusive
+            const int i = start + k;
+            if (i >= 0 && i <= stop && i < total) dst[i] = fq_out_byte(text, R, lo, hi, (uint32_t)i);
+        }
+        // ... the bytes before the first aligned word and after the last one
+        if (lane < head && lane < total) dst[lane] = fq_out_byte(text, R, lo, hi, (uint32_t)lane);
+        {
+            const int i = head + 4 * nwords + lane;
+            if (lane < 4 && i < total) dst[i] = fq_out_byte(text, R, lo, hi, (uint32_t)i);
+        }
     }
     if (r == n_rec - 1 && lane == 0) info->out_bytes = (unsigned long long)(out_off[r] + total);
 }
