@@ -222,7 +222,7 @@ int fq_back(atr_ctx* ctx, Slot& s, const FqChunk& c, const atr_adapterset* set, 
         LAUNCHED(ctx);
         rc = fq_scan_i64(ctx, st, s.scan_tmp, f.len64.as<long long>(), f.outoff.as<long long>(), n + 1);
         if (rc) return rc;
-        k_fq_format<<<grid_for(n * 32, 256), 256, 0, st>>>(d_text, f.recs.as<FqRec>(), f.fwin.as<uint16_t>(),
+        k_fq_format<<<grid_for(n, FQF_RECS), 256, 0, st>>>(d_text, f.recs.as<FqRec>(), f.fwin.as<uint16_t>(),
                                                            f.outoff.as<long long>(), n, f.outtext.as<unsigned char>(), d_info);
         LAUNCHED(ctx);
     }
@@ -583,7 +583,7 @@ int pe_back(atr_ctx* ctx, Slot& s, const PeStep& P, const atr_insertset* iset, c
         LAUNCHED(ctx);
         rc = fq_scan_i64(ctx, st, s.scan_tmp, q.len64.as<long long>(), q.outoff.as<long long>(), n + 1);
         if (rc) return rc;
-        k_fq_format<<<grid_for(n * 32, 256), 256, 0, st>>>(q.text.as<unsigned char>(), q.recs.as<FqRec>(), q.fwin.as<uint16_t>(),
+        k_fq_format<<<grid_for(n, FQF_RECS), 256, 0, st>>>(q.text.as<unsigned char>(), q.recs.as<FqRec>(), q.fwin.as<uint16_t>(),
                                                            q.outoff.as<long long>(), n, q.outtext.as<unsigned char>(), q.info.as<FqInfo>());
         LAUNCHED(ctx);
         k_fq_publish<<<1, 32, 0, st>>>(q.info.as<FqInfo>(), q.hinfo);

@@ -311,60 +311,88 @@ __global__ void __launch_bounds__(256) k_fq_outlen(const FqRec* __restrict__ rec
     if ((threadIdx.x & 31) == 0 && bp) atomicAdd(bp_out, bp);
 }
 
-// formatted records: warp per record. The record is produced as aligned 32-bit words of the output: a word that lies
-// inside one of the four copied pieces ('@name', sequence, name after '+', qualities) is fetched from the text with two
-// aligned loads and a funnel shift; the few words that touch a piece boundary or a literal ('\n', '+'), the bytes
-// before the first aligned word and the last bytes are written bytewise by one lane each in a single pass.
+// Formatted records. One CTA = FQF_RECS consecutive records; their text is one contiguous span of the chunk, staged in
+// shared memory by a single TMA bulk copy (cp.async.bulk + mbarrier) while the warps fetch the records' table entries,
+// so that the piece-wise copies read shared memory instead of waiting on scattered global loads. A warp formats one
+// record at a time: the record is produced as aligned 32-bit words of the output; a word inside one of the four copied
+// pieces ('@name', sequence, name after '+', qualities) comes from two aligned loads and a funnel shift; the few words
+// that touch a piece boundary or a literal ('\n', '+'), the bytes before the first aligned word and the last bytes
+// are written bytewise by one lane each in a single pass. Spans that do not fit the tile are read from global memory.
+#define FQF_RECS 32
+#define FQF_TILE 32768
+__device__ __forceinline__ void fq_format_record(const unsigned char* __restrict__ src /* src[pos] = text[pos] */, const FqRec& R,
+                                                 int lo, int hi, int total, unsigned char* __restrict__ dst, int lane) {
+    const int w = hi - lo, H = R.hdr_len, P = R.name2 ? H : 1;
+    // output coordinates: [0,H) header | H '\n' | [s2,e2) sequence | e2 '\n' | e2+1 '+' | [s3,e3) name | e3 '\n' | [s4,e4) qualities | e4 '\n'
+    const int s2 = H + 1, e2 = s2 + w, s3 = e2 + 2, e3 = s3 + P - 1, s4 = e3 + 1, e4 = s4 + w;
+    // source offset such that src[off + i] is output byte i inside a piece
+    const long long o1 = (long long)R.hdr_b, o2 = (long long)R.seq_b + lo - s2, o3 = (long long)R.hdr_b + 1 - s3,
+                    o4 = (long long)R.qual_b + lo - s4;
+    const int head = (int)((4u - (unsigned)(reinterpret_cast<uintptr_t>(dst) & 3u)) & 3u);
+    const int nwords = total > head ? (total - head) >> 2 : 0;
+    uint32_t* dw = reinterpret_cast<uint32_t*>(dst + head);
+    for (int t = lane; t < nwords; t += 32) {
+        const int i = head + 4 * t, j = i + 3;
+        long long off;
+        if (j < H) off = o1;
+        else if (i >= s2 && j < e2) off = o2;
+        else if (i >= s4 && j < e4) off = o4;
+        else if (i >= s3 && j < e3) off = o3;
+        else continue;                                        // touches a boundary: the bytewise pass below
+        const unsigned char* p = src + (off + i);
+        const unsigned sh = (unsigned)(reinterpret_cast<uintptr_t>(p) & 3u) * 8u;
+        const uint32_t* pw = reinterpret_cast<const uint32_t*>(p - (sh >> 3));
+        const uint32_t a = pw[0];
+        dw[t] = sh ? __funnelshift_r(a, pw[1], sh) : a;
+    }
+    // bytewise: four runs of up to 8 bytes around the boundaries (lanes 0-7, 8-15, 16-23, 24-31) ...
+    {
+        const int run = lane >> 3, k = lane & 7;
+        const int start = run == 0 ? H - 3 : run == 1 ? e2 - 3 : run == 2 ? e3 - 3 : e4 - 3;
+        const int stop = run == 0 ? H + 3 : run == 1 ? e2 + 4 : run == 2 ? e3 + 3 : e4;       // inclusive
+        const int i = start + k;
+        if (i >= 0 && i <= stop && i < total) dst[i] = fq_out_byte(src, R, lo, hi, (uint32_t)i);
+    }
+    // ... the bytes before the first aligned word and after the last one
+    if (lane < head && lane < total) dst[lane] = fq_out_byte(src, R, lo, hi, (uint32_t)lane);
+    {
+        const int i = head + 4 * nwords + lane;
+        if (lane < 4 && i < total) dst[i] = fq_out_byte(src, R, lo, hi, (uint32_t)i);
+    }
+}
+
 __global__ void __launch_bounds__(256) k_fq_format(const unsigned char* __restrict__ text, const FqRec* __restrict__ recs,
                                                    const uint16_t* __restrict__ fwin, const long long* __restrict__ out_off,
                                                    long long n_rec, unsigned char* __restrict__ out, FqInfo* __restrict__ info) {
-    const long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (r >= n_rec) return;
-    const int lane = threadIdx.x & 31;
-    const FqRec R = recs[r];
-    const int lo = fwin[2 * r], hi = fwin[2 * r + 1];
-    const int total = lo <= hi ? (int)fq_out_len(R, lo, hi) : 0;
-    unsigned char* dst = out + out_off[r];
-    if (total) {
-        const int w = hi - lo, H = R.hdr_len, P = R.name2 ? H : 1;
-        // output coordinates: [0,H) header | H '\n' | [s2,e2) sequence | e2 '\n' | e2+1 '+' | [s3,e3) name | e3 '\n' | [s4,e4) qualities | e4 '\n'
-        const int s2 = H + 1, e2 = s2 + w, s3 = e2 + 2, e3 = s3 + P - 1, s4 = e3 + 1, e4 = s4 + w;
-        // source offset such that text[off + i] is output byte i inside a piece
-        const long long o1 = (long long)R.hdr_b, o2 = (long long)R.seq_b + lo - s2, o3 = (long long)R.hdr_b + 1 - s3,
-                        o4 = (long long)R.qual_b + lo - s4;
-        const int head = (int)((4u - (unsigned)(reinterpret_cast<uintptr_t>(dst) & 3u)) & 3u);
-        const int nwords = total > head ? (total - head) >> 2 : 0;
-        uint32_t* dw = reinterpret_cast<uint32_t*>(dst + head);
-        for (int t = lane; t < nwords; t += 32) {
-            const int i = head + 4 * t, j = i + 3;
-            long long off;
-            if (j < H) off = o1;
-            else if (i >= s2 && j < e2) off = o2;
-            else if (i >= s4 && j < e4) off = o4;
-            else if (i >= s3 && j < e3) off = o3;
-            else continue;                                        // touches a boundary: the bytewise pass below
-            const unsigned char* p = text + (off + i);
-            const unsigned sh = (unsigned)(reinterpret_cast<uintptr_t>(p) & 3u) * 8u;
-            const uint32_t* pw = reinterpret_cast<const uint32_t*>(p - (sh >> 3));
-            const uint32_t a = pw[0];
-            dw[t] = sh ? __funnelshift_r(a, pw[1], sh) : a;
-        }
-        // bytewise: four runs of up to 8 bytes around the boundaries (lanes 0-7, 8-15, 16-23, 24-31) ...
-        {
-            const int run = lane >> 3, k = lane & 7;
-            const int start = run == 0 ? H - 3 : run == 1 ? e2 - 3 : run == 2 ? e3 - 3 : e4 - 3;
-            const int stop = run == 0 ? H + 3 : run == 1 ? e2 + 4 : run == 2 ? e3 + 3 : e4;       // inclusive
-            const int i = start + k;
-            if (i >= 0 && i <= stop && i < total) dst[i] = fq_out_byte(text, R, lo, hi, (uint32_t)i);
-        }
-        // ... the bytes before the first aligned word and after the last one
-        if (lane < head && lane < total) dst[lane] = fq_out_byte(text, R, lo, hi, (uint32_t)lane);
-        {
-            const int i = head + 4 * nwords + lane;
-            if (lane < 4 && i < total) dst[i] = fq_out_byte(text, R, lo, hi, (uint32_t)i);
-        }
+    __shared__ __align__(128) unsigned char s_text[FQF_TILE + 16];
+    __shared__ __align__(8) uint64_t s_bar;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long r0 = (long long)blockIdx.x * FQF_RECS;
+    const int cnt = (int)(n_rec - r0 < FQF_RECS ? n_rec - r0 : FQF_RECS);
+    // the CTA's span of the text: from the first record's header to the end of the last record's qualities
+    const FqRec Rf = recs[r0], Rl = recs[r0 + cnt - 1];
+    const uint32_t a_begin = Rf.hdr_b & ~15u;
+    const uint32_t span = ((Rl.qual_b + (uint32_t)Rl.seq_len - a_begin) + 15u) & ~15u;
+    const bool use_tma = span <= FQF_TILE && span > 0 && ((reinterpret_cast<uintptr_t>(text) & 15) == 0);
+    if (tid == 0 && use_tma) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar)) : "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    if (r == n_rec - 1 && lane == 0) info->out_bytes = (unsigned long long)(out_off[r] + total);
+    __syncthreads();
+    if (tid == 0 && use_tma) tma_load_1d(s_text, text + a_begin, span, &s_bar);
+    // src[pos] = text[pos]: the staged copy, or the text itself
+    const unsigned char* src = use_tma ? (const unsigned char*)s_text - a_begin : text;
+    bool waited = !use_tma;
+    for (int k = warp; k < cnt; k += 8) {
+        const long long r = r0 + k;
+        const FqRec R = recs[r];
+        const int lo = fwin[2 * r], hi = fwin[2 * r + 1];
+        const int total = lo <= hi ? (int)fq_out_len(R, lo, hi) : 0;
+        unsigned char* dst = out + out_off[r];
+        if (!waited) { mbar_wait(&s_bar, 0); waited = true; }
+        if (total) fq_format_record(src, R, lo, hi, total, dst, lane);
+        if (r == n_rec - 1 && lane == 0) info->out_bytes = (unsigned long long)(out_off[r] + total);
+    }
 }
 
 // ---- paired-end ------------------------------------------------------------------------------------------------
