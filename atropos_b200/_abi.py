@@ -26,6 +26,20 @@ INSERT_DTYPE = np.dtype([("insert", MATCH_DTYPE), ("match1", MATCH_DTYPE), ("mat
 assert C.sizeof(AtrMatch) == 16 and MATCH_DTYPE.itemsize == 16 and INSERT_DTYPE.itemsize == 48
 
 
+class AtrMergeResult(C.Structure):
+    _fields_ = [("r2_start", C.c_uint16), ("r2_stop", C.c_uint16), ("r1_start", C.c_uint16), ("r1_stop", C.c_uint16),
+                ("matches", C.c_uint16), ("errors", C.c_uint16), ("min_overlap", C.c_uint16), ("status", C.c_uint8),
+                ("action", C.c_uint8)]
+
+
+#: numpy view of an array of atr_merge_result
+MERGE_DTYPE = np.dtype([("r2_start", "<u2"), ("r2_stop", "<u2"), ("r1_start", "<u2"), ("r1_stop", "<u2"),
+                        ("matches", "<u2"), ("errors", "<u2"), ("min_overlap", "<u2"), ("status", "u1"), ("action", "u1")])
+ATR_MERGE_KEEP1, ATR_MERGE_TAKE2, ATR_MERGE_APPEND, ATR_MERGE_PREPEND = 1, 2, 3, 4
+
+assert C.sizeof(AtrMergeResult) == 16 and MERGE_DTYPE.itemsize == 16
+
+
 class AtrAdapterDesc(C.Structure):
     _fields_ = [("sequence", C.c_char_p), ("length", C.c_int32), ("max_error_rate", C.c_double),
                 ("flags", C.c_int32), ("wildcard_ref", C.c_int32), ("wildcard_query", C.c_int32),

@@ -20,7 +20,7 @@ SYMBOLS = [
     "atr_ctx_last_phase_ms", "atr_adapterset_create",
     "atr_adapterset_destroy", "atr_packed_words", "atr_pack_device", "atr_locate_batch_device",
     "atr_locate_batch_host", "atr_compare_prefixes", "atr_insertset_create", "atr_insertset_destroy",
-    "atr_match_insert_batch_device", "atr_match_insert_batch_host", "atr_multi_locate", "atr_trim_fastq_host", "atr_trim_fastq_pe_host",
+    "atr_match_insert_batch_device", "atr_match_insert_batch_host", "atr_multi_locate", "atr_merge_overlap_batch_host", "atr_trim_fastq_host", "atr_trim_fastq_pe_host",
 ]
 
 
@@ -71,6 +71,7 @@ def load():
     L.atr_match_insert_batch_host.argtypes = [vp, vp, vp, vp, vp, vp, i64, vp]
     L.atr_multi_locate.argtypes = [vp, C.c_char_p, i32, C.c_char_p, i32, f64, i32, i32, i32, C.POINTER(i32),
                                    C.POINTER(i32)]
+    L.atr_merge_overlap_batch_host.argtypes = [vp, vp, vp, vp, vp, vp, i64, f64, f64, vp]
     L.atr_trim_fastq_host.argtypes = [vp, vp, C.POINTER(_abi.AtrTrimOpts), vp, i64, vp, i64, C.POINTER(i64), C.POINTER(i64),
                                       C.POINTER(_abi.AtrTrimStats), C.POINTER(_abi.AtrFastqError)]
     L.atr_trim_fastq_pe_host.argtypes = [vp, vp, vp, vp, C.POINTER(_abi.AtrTrimPeOpts), vp, i64, vp, i64, vp, i64, vp, i64,

@@ -339,4 +339,27 @@ inline int prepare_insert(const atr_insert_desc& d, const AtrTables& tb, HostIns
     return ATR_OK;
 }
 
+// ---- MergeOverlapping(min_overlap, error_rate) (commands/trim/modifiers.py:867-879): per-length tables -----------
+// h = [thr_mul (max_len + 1) | minov (max_len + 1)], comp = BASE_COMPLEMENTS (util/__init__.py:67-88; 0 = KeyError)
+inline void build_merge_tables(int max_len, double min_overlap, double error_rate, std::vector<unsigned short>& h,
+                               unsigned char comp[256]) {
+    h.assign((size_t)2 * (max_len + 1), 0);
+    std::fesetround(FE_TONEAREST);
+    // __init__ keeps int(min_overlap) if min_overlap > 1 (:871); __call__ then treats a value <= 1 as a fraction
+    // of the shorter read: max(2, round(...)), Python's round = half to even (:877-879)
+    const double v = min_overlap > 1 ? std::floor(min_overlap) : min_overlap;
+    for (int l = 0; l <= max_len; l++) {
+        h[l] = thr_mul_of(l, error_rate);
+        const double mo = v <= 1 ? std::max(2.0, std::nearbyint(v * l)) : v;
+        h[(size_t)max_len + 1 + l] = (unsigned short)std::min(60000.0, mo);
+    }
+    memset(comp, 0, 256);
+    const char* a = "ACRSWKBDN";
+    const char* b = "TGYSWMVHN";
+    for (int i = 0; a[i]; i++) {
+        comp[(unsigned char)a[i]] = (unsigned char)b[i]; comp[(unsigned char)b[i]] = (unsigned char)a[i];
+        comp[(unsigned char)(a[i] + 32)] = (unsigned char)(b[i] + 32); comp[(unsigned char)(b[i] + 32)] = (unsigned char)(a[i] + 32);
+    }
+}
+
 }  // namespace atr

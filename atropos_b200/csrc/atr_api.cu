@@ -749,3 +749,4 @@ int atr_multi_locate(atr_ctx* ctx, const char* reference, int32_t m, const char*
 }  // extern "C"
 
 #include "atr_fastq_api.cuh"
+#include "atr_merge_api.cuh"

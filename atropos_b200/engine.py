@@ -95,6 +95,26 @@ class Context(object):
             return None
         return [tuple(out[6 * t:6 * t + 6]) for t in range(cnt.value)]
 
+    def merge_overlap_host(self, ascii1, offsets1, ascii2, offsets2, min_overlap, error_rate, insert_matched=None, out=None):
+        """atr_merge_overlap_batch_host: one MERGE_DTYPE record per pair."""
+        ascii1 = np.ascontiguousarray(ascii1, dtype=np.uint8)
+        ascii2 = np.ascontiguousarray(ascii2, dtype=np.uint8)
+        offsets1 = np.ascontiguousarray(offsets1, dtype=np.int64)
+        offsets2 = np.ascontiguousarray(offsets2, dtype=np.int64)
+        n = len(offsets1) - 1
+        assert len(offsets2) - 1 == n
+        if out is None:
+            out = np.empty(n, dtype=_abi.MERGE_DTYPE)
+        im = None
+        if insert_matched is not None:
+            im = np.ascontiguousarray(insert_matched, dtype=np.uint8)
+            assert im.shape == (n,)
+        _lib.check(self._L.atr_merge_overlap_batch_host(
+            self.handle, ascii1.ctypes.data if ascii1.size else None, offsets1.ctypes.data,
+            ascii2.ctypes.data if ascii2.size else None, offsets2.ctypes.data, im.ctypes.data if im is not None else None,
+            n, float(min_overlap), float(error_rate), out.ctypes.data), self.handle)
+        return out
+
 
 def default_context(device=0):
     with _lock:

@@ -220,6 +220,32 @@ int  atr_multi_locate(atr_ctx* ctx, const char* reference, int32_t m, const char
                       double max_error_rate, int32_t flags, int32_t min_overlap, int32_t max_matches,
                       int32_t* out6, int32_t* n_out);
 
+/* ---- MergeOverlapping -------------------------------------------------------------------- */
+/* One pair's outcome of MergeOverlapping.__call__ (commands/trim/modifiers.py:864-931). 16 bytes.
+ * status: ATR_ST_NONE  -> the pair stays as it is (a read shorter than min_overlap :881-882, locate() returned None, or
+ *                         matches < min_overlap :900; the six alignment fields are still filled in when there was one);
+ *         ATR_ST_MATCH -> merged (read1.merged = True, read 2 dropped), `action` says how read 1 is rebuilt;
+ *         ATR_ST_INVALID  -> the reference raises AtroposError("Invalid alignment while trying to merge ...") (:923-927);
+ *         ATR_ST_KEYERROR -> reverse_complement(read 2) raises KeyError (util/__init__.py:479-482).
+ * action (ATR_ST_MATCH only): 1 read 2 inside read 1, read 1 unchanged (:905-907); 2 read 1 inside read 2, read 1 :=
+ * rc(read 2) with reversed qualities (:908-911); 3 read 1 + rc(read 2)[r2_stop:] (:912-916); 4 rc(read 2) +
+ * read 1[r1_stop:] (:917-922). */
+typedef struct atr_merge_result {
+    uint16_t r2_start, r2_stop;   /* refstart, refstop: within reverse_complement(read 2) */
+    uint16_t r1_start, r1_stop;   /* querystart, querystop: within read 1 */
+    uint16_t matches, errors;
+    uint16_t min_overlap;         /* the pair's effective minimum: max(2, round(frac * min(len1, len2))) or int(value) (:877-879) */
+    uint8_t  status, action;
+} atr_merge_result;
+/* replaces, for n pairs, the alignment and the decision of MergeOverlapping(min_overlap, error_rate).__call__: per pair
+ * Aligner(reverse_complement(read2), error_rate, flags).locate(read1) (_align.pyx:197-208, :266-491) with flags
+ * SEMIGLOBAL, or START_WITHIN_SEQ1 | STOP_WITHIN_SEQ2 where insert_matched[i] != 0 (read.insert_overlap set by
+ * InsertAdapterCutter, modifiers.py:884-893); insert_matched may be NULL (all 0). min_overlap as on the command line
+ * (--merge-min-overlap: a fraction of the shorter read if <= 1, else a number of bases). Reads up to 4000 nt. */
+int  atr_merge_overlap_batch_host(atr_ctx* ctx, const uint8_t* ascii1, const int64_t* offsets1,
+                                  const uint8_t* ascii2, const int64_t* offsets2, const uint8_t* insert_matched,
+                                  int64_t n, double min_overlap, double error_rate, atr_merge_result* out);
+
 /* ---- FASTQ text in -> trimmed FASTQ text out ("next" rows of the hot path: its reader and its consumer) ---- */
 /* atr_fastq_error.kind: the FormatErrors of FastqReader.__iter__ (io/_seqio.pyx:180-245) */
 #define ATR_FQ_OK            0

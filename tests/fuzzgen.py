@@ -146,3 +146,59 @@ def insert_pairs(seed, count, adapter1, adapter2, lengths=(50, 100, 150), err=0.
             else:
                 r2 = r2[:cut]
         yield r1, r2
+
+
+_COMP = {"A": "T", "C": "G", "G": "C", "T": "A", "N": "N", "R": "Y", "Y": "R", "a": "t", "c": "g", "g": "c", "t": "a", "n": "n"}
+
+
+def _rc(seq):
+    return "".join(_COMP[c] for c in reversed(seq))
+
+
+def merge_cases(seed, count):
+    """Pairs for MergeOverlapping: both reads sequenced from one fragment (read 1 from its start, read 2 from the
+    other strand's start), with substitutions / indels / Ns, so that the reads overlap by anything from nothing to
+    everything; some unrelated pairs, very short and empty reads, lower case, IUPAC codes and bytes
+    reverse_complement rejects; qualities that decide the error correction either way."""
+    rng = np.random.default_rng(seed)
+    quals = "#(-2:AFIJ"
+    out = []
+    for t in range(count):
+        L1 = int(rng.choice([0, 1, 2, 5, 12, 30, 50, 75, 100, 150, 250]) if rng.random() < 0.3 else rng.integers(20, 160))
+        L2 = L1 if rng.random() < 0.6 else int(rng.integers(0, 200))
+        shape = rng.random()
+        if shape < 0.12:                                   # unrelated reads
+            s1, s2 = rand_seq(rng, L1), rand_seq(rng, L2)
+        else:
+            lo = max(1, min(L1, L2) // 4)
+            F = int(rng.integers(lo, max(lo + 1, L1 + L2 + 30)))
+            frag = rand_seq(rng, F, "ACGT" if rng.random() < 0.9 else "AC")      # low complexity: many equally good alignments
+            err = float(rng.choice([0.0, 0.0, 0.01, 0.03, 0.08, 0.15]))
+            indel = err / 4 if rng.random() < 0.5 else 0.0
+            s1 = mutate(rng, frag, sub=err, ins=indel, dele=indel)[:L1]
+            s2 = mutate(rng, _rc(frag), sub=err, ins=indel, dele=indel)[:L2]
+        def spice(s):
+            s = list(s)
+            r = rng.random()
+            for i in range(len(s)):
+                if rng.random() < 0.01:
+                    s[i] = "N"
+            if r < 0.04 and s:
+                for i in range(len(s)):
+                    if rng.random() < 0.3:
+                        s[i] = s[i].lower()
+            elif r < 0.07 and s:
+                s[int(rng.integers(0, len(s)))] = str(rng.choice(["R", "Y", "X", "U", ".", "-"]))
+            return "".join(s)
+        s1, s2 = spice(s1), spice(s2)
+        qmode = rng.random()
+        def qual(n):
+            if qmode < 0.3:
+                return "I" * n
+            return "".join(quals[i] for i in rng.integers(0, len(quals), size=n))
+        out.append(dict(seq1=s1, seq2=s2, qual1=qual(len(s1)), qual2=qual(len(s2)),
+                        insert_matched=bool(rng.random() < 0.25),
+                        min_overlap=float(rng.choice([0.9, 0.9, 0.5, 0.25, 1.0, 1.5, 2.0, 10.0, 30.0, 0.05])),
+                        error_rate=float(rng.choice([0.1, 0.2, 0.2, 0.05, 0.0, 0.3])),
+                        mismatch_action=[None, None, "liberal", "conservative", "N"][int(rng.integers(0, 5))]))
+    return out

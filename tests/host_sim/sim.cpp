@@ -8,6 +8,7 @@
 #include "../../atropos_b200/csrc/locate_core.cuh"
 #include "../../atropos_b200/csrc/insert_core.cuh"
 #include "../../atropos_b200/csrc/fastq_core.cuh"
+#include "../../atropos_b200/csrc/merge_core.cuh"
 
 extern "C" {
 
@@ -430,6 +431,20 @@ int sim_trim_fastq_pe(const atr_insert_desc* idesc, const atr_adapter_desc* d1, 
         opos2 += total;
     }
     out_bytes[0] = opos1; out_bytes[1] = opos2;
+    return 0;
+}
+
+// MergeOverlapping.__call__ up to the decision (merge_core.cuh: merge_pair), one pair
+int sim_merge_overlap(const unsigned char* r1, int len1, const unsigned char* r2, int len2, int insert_matched,
+                      double min_overlap, double error_rate, atr_merge_result* out) {
+    const int max_len = std::max(len1, len2);
+    std::vector<unsigned short> h;
+    unsigned char comp[256];
+    atr::build_merge_tables(max_len, min_overlap, error_rate, h, comp);
+    MergeTables tb;
+    tb.thr_mul = h.data(); tb.minov = h.data() + (max_len + 1); tb.comp = comp; tb.max_len = max_len;
+    std::vector<GCell> col((size_t)len2 + 1);
+    merge_pair(r1, len1, r2, len2, insert_matched, tb, col.data(), 1, out);
     return 0;
 }
 

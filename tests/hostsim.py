@@ -46,8 +46,22 @@ def lib():
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_abi.AtrFastqError),
                                         C.POINTER(SimOpsCounters), C.POINTER(C.c_longlong)]
         L.sim_trim_fastq_pe.restype = C.c_int
+        L.sim_merge_overlap.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_double, C.c_double,
+                                        C.POINTER(_abi.AtrMergeResult)]
+        L.sim_merge_overlap.restype = C.c_int
         _lib = L
     return _lib
+
+
+def merge_overlap(seq1, seq2, insert_matched, min_overlap, error_rate):
+    """AtrMergeResult of one pair (merge_core.cuh on the CPU)."""
+    b1 = seq1 if isinstance(seq1, bytes) else seq1.encode("latin-1")
+    b2 = seq2 if isinstance(seq2, bytes) else seq2.encode("latin-1")
+    out = _abi.AtrMergeResult()
+    rc = lib().sim_merge_overlap(b1, len(b1), b2, len(b2), int(bool(insert_matched)), float(min_overlap), float(error_rate),
+                                 C.byref(out))
+    assert rc == 0
+    return out
 
 
 def locate(read, desc, route=0, lo=0, hi=None, fold_case=False, prev=None, adapter_index=0):
