@@ -28,6 +28,154 @@ __global__ void __launch_bounds__(ATR_MERGE_THREADS) k_merge_overlap(const unsig
     }
 }
 
+// ---- k_merge_warp: one warp = one pair, the DP as a wavefront over the lanes ------------------------------------------
+// Lane l owns the R = ceil(len2 / 32) rows l*R+1 .. (l+1)*R of the DP (rows = rc(read 2)) as packed 32-bit cells in
+// registers and works on column s - l in step s: the cell above its first row is the last row of lane l-1 in the same
+// column, computed one step earlier and handed down with one shuffle per step; the diagonal one is the value it received
+// the step before. Every cell of the matrix is evaluated (no data-dependent band): costs are clamped to k + 1 ("dead"),
+// which cannot change an accepted alignment because cells above k never feed one (the argument of K1a,
+// locate_core.cuh). Packed cell, compared as one unsigned: cost [24,32) | tie-break priority [22,24) (0 while stored) |
+// origin + 1024 [10,22) | matches [0,10); min(diag + SUB, up + INS, left + DEL) reproduces the reference's
+// "mismatch, then insertion, then deletion" order (_align.pyx:405-419). Row len2 is offered as a candidate after every
+// column (:440-458) by the lane that owns it; the last column's candidates (:461-474) are reduced over the warp with
+// the reference's first-best-wins order encoded in the score. Limits: len2 <= 32 * RMAX, k + 1 <= 250, len1 <= 3000
+// (else k_merge_overlap).
+#define MW_COST_SHIFT 24
+#define MW_ORG_SHIFT 10
+#define MW_ORG_BIAS 1024
+#define MW_SUB (1u << MW_COST_SHIFT)
+#define MW_INS ((1u << MW_COST_SHIFT) | (1u << 22))
+#define MW_DEL ((1u << MW_COST_SHIFT) | (2u << 22))
+#define MW_PRIO_CLEAR (~(3u << 22))
+__device__ __forceinline__ unsigned mw_key(int cost, int origin, int matches) {
+    return ((unsigned)cost << MW_COST_SHIFT) | ((unsigned)(origin + MW_ORG_BIAS) << MW_ORG_SHIFT) | (unsigned)matches;
+}
+__device__ __forceinline__ int mw_cost(unsigned key) { return (int)(key >> MW_COST_SHIFT); }
+__device__ __forceinline__ int mw_origin(unsigned key) { return (int)((key >> MW_ORG_SHIFT) & 0xFFFu) - MW_ORG_BIAS; }
+__device__ __forceinline__ int mw_matches(unsigned key) { return (int)(key & 0x3FFu); }
+
+template <int RMAX>
+__global__ void __launch_bounds__(256) k_merge_warp(const unsigned char* __restrict__ ascii1, const int64_t* __restrict__ offsets1, int64_t base1,
+                                                    const unsigned char* __restrict__ ascii2, const int64_t* __restrict__ offsets2, int64_t base2,
+                                                    const unsigned char* __restrict__ insert_matched, int64_t n, const MergeTables tb,
+                                                    atr_merge_result* __restrict__ out) {
+    const unsigned FULL = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t p = warp; p < n; p += nwarps) {
+        const int64_t a0 = offsets1[p] - base1, b0 = offsets2[p] - base2;
+        const int len1 = (int)(offsets1[p + 1] - base1 - a0), len2 = (int)(offsets2[p + 1] - base2 - b0);
+        const unsigned char* __restrict__ r1 = ascii1 + a0;
+        const unsigned char* __restrict__ r2 = ascii2 + b0;
+        atr_merge_result res;
+        res.r2_start = res.r2_stop = res.r1_start = res.r1_stop = res.matches = res.errors = 0;
+        res.status = ATR_ST_NONE; res.action = 0;
+        const int min_ov = (int)tb.minov[atr_min(len1, len2)];
+        res.min_overlap = (uint16_t)min_ov;
+        if (len1 < min_ov || len2 < min_ov) { if (lane == 0) out[p] = res; continue; }            // :881-882
+        const int m = len2, nq = len1;
+        const int R = (m + 31) >> 5;                                                                // rows per lane
+        // this lane's rows of rc(read 2); a byte the complement table rejects = KeyError for the whole pair
+        int refc[RMAX];
+        bool bad = false;
+#pragma unroll
+        for (int r = 0; r < RMAX; r++) {
+            const int i = lane * R + r + 1;
+            refc[r] = 256;
+            if (r < R && i <= m) { const unsigned char c = tb.comp[r2[m - i]]; bad = bad || c == 0; refc[r] = c; }
+        }
+        if (__any_sync(FULL, bad)) { res.status = ATR_ST_KEYERROR; if (lane == 0) out[p] = res; continue; }
+        const int k = (int)tb.thr_mul[m];
+        const unsigned DEAD = (unsigned)(k + 1) << MW_COST_SHIFT;
+        const bool siq = !(insert_matched && insert_matched[p]);       // SEMIGLOBAL; else START_WITHIN_SEQ1 | STOP_WITHIN_SEQ2 (:886-890)
+        const int max_n = siq ? nq : atr_min(nq, m + k);               // min_n = 0: both flag sets stop within read 1 (:315-321)
+        // column 0 (:338-352): cost 0, origin -i for both flag sets
+        unsigned key[RMAX];
+#pragma unroll
+        for (int r = 0; r < RMAX; r++) key[r] = mw_key(0, -(lane * R + r + 1), 0);
+        unsigned diag_in = mw_key(0, -(lane * R), 0);                  // the row above this lane's block, one column back
+        unsigned bottom = 0;
+        const int lanes_used = (m + R - 1) / R;
+        const int lm = (m - 1) / R, rm = (m - 1) - lm * R;             // where row m lives
+        int b_mat = 0, b_cost = m + nq, b_org = 0, b_ref = m, b_q = nq;           // this lane's best candidate (:358-363)
+        const int total = max_n + lanes_used - 1;
+        for (int s = 1; s <= total; s++) {
+            const int c = s - lane;                                    // this lane's column in this step
+            const unsigned up_sh = __shfl_up_sync(FULL, bottom, 1);
+            if (c >= 1 && c <= max_n && lane < lanes_used) {
+                const int qc = (int)r1[c - 1];
+                unsigned up = up_sh;
+                if (lane == 0) up = siq ? mw_key(0, c, 0) : (c > k ? DEAD : mw_key(c, 0, 0));      // row 0 (:384-388)
+                unsigned diag = diag_in;
+                diag_in = up;
+#pragma unroll
+                for (int r = 0; r < RMAX; r++) {
+                    if (r < R) {
+                        const unsigned left = key[r];
+                        const unsigned mn = atr_umin(atr_umin(diag + MW_SUB, up + MW_INS), left + MW_DEL) & MW_PRIO_CLEAR;
+                        unsigned nw = refc[r] == qc ? diag + 1u : mn;
+                        nw = atr_umin(nw, DEAD);
+                        diag = left;
+                        key[r] = nw;
+                        up = nw;
+                    }
+                }
+                bottom = up;
+                if (lane == lm) {                                      // row m after this column (:440-458)
+                    unsigned cm = key[0];
+#pragma unroll
+                    for (int r = 1; r < RMAX; r++) if (r == rm) cm = key[r];
+                    if (cm < DEAD) {
+                        const int cost = mw_cost(cm), org = mw_origin(cm), mat = mw_matches(cm);
+                        const int length = m + atr_min(org, 0);
+                        if (length >= 1 && cost <= (int)tb.thr_mul[length] && (mat > b_mat || (mat == b_mat && cost < b_cost))) {
+                            b_mat = mat; b_cost = cost; b_org = org; b_ref = m; b_q = c;
+                        }
+                    }
+                }
+            }
+        }
+        // score: valid | matches | 1023 - cost | order (the in-loop best first, then the last column's rows top down)
+        unsigned score = b_cost != m + nq ? ((1u << 30) | ((unsigned)b_mat << 20) | ((unsigned)(1023 - b_cost) << 10) | 1023u) : 0u;
+        if (siq) {                                                     // max_n == n and STOP_WITHIN_SEQ1: the last column (:461-474)
+#pragma unroll
+            for (int r = 0; r < RMAX; r++) {
+                const int i = lane * R + r + 1;
+                if (r < R && i <= m && key[r] < DEAD) {
+                    const int cost = mw_cost(key[r]), org = mw_origin(key[r]), mat = mw_matches(key[r]);
+                    const int length = i + atr_min(org, 0);
+                    if (length >= 1 && cost <= (int)tb.thr_mul[length]) {
+                        const unsigned sc = (1u << 30) | ((unsigned)mat << 20) | ((unsigned)(1023 - cost) << 10) | (unsigned)(1023 - i);
+                        if (sc > score) { score = sc; b_mat = mat; b_cost = cost; b_org = org; b_ref = i; b_q = nq; }
+                    }
+                }
+            }
+        }
+        const unsigned top = __reduce_max_sync(FULL, score);
+        if (top == 0u) { if (lane == 0) out[p] = res; continue; }     // locate() returned None
+        const int src = __ffs(__ballot_sync(FULL, score == top)) - 1;
+        b_mat = __shfl_sync(FULL, b_mat, src); b_cost = __shfl_sync(FULL, b_cost, src); b_org = __shfl_sync(FULL, b_org, src);
+        b_ref = __shfl_sync(FULL, b_ref, src); b_q = __shfl_sync(FULL, b_q, src);
+        if (lane == 0) {
+            int start1 = 0, start2 = b_org;
+            if (b_org < 0) { start1 = -b_org; start2 = 0; }
+            res.r2_start = (uint16_t)start1; res.r2_stop = (uint16_t)b_ref;
+            res.r1_start = (uint16_t)start2; res.r1_stop = (uint16_t)b_q;
+            res.matches = (uint16_t)b_mat; res.errors = (uint16_t)b_cost;
+            if (b_mat >= min_ov) {                                     // :900-927
+                res.status = ATR_ST_MATCH;
+                if (start1 == 0 && b_ref == len2) res.action = ATR_MERGE_KEEP1;
+                else if (start2 == 0 && b_q == len1) res.action = ATR_MERGE_TAKE2;
+                else if (start2 > 0) res.action = ATR_MERGE_APPEND;
+                else if (start1 > 0) res.action = ATR_MERGE_PREPEND;
+                else res.status = ATR_ST_INVALID;
+            }
+            out[p] = res;
+        }
+    }
+}
+
 namespace {
 
 // thr_mul / minov / comp tables of one call, uploaded next to each other into ctx->misc
@@ -74,10 +222,16 @@ extern "C" int atr_merge_overlap_batch_host(atr_ctx* ctx, const uint8_t* ascii1,
     if (rc) return rc;
     CU(cudaEventRecord(ctx->ev0, ctx->slot[0].stream));
     CU(cudaStreamWaitEvent(ctx->slot[1].stream, ctx->ev0, 0));
+    // warp-per-pair wavefront kernel whenever its limits hold (ATR_MERGE_KERNEL=thread forces the other one: tests)
+    int max_len1 = 0;
+    for (int64_t i = 0; i < n; i++) max_len1 = std::max(max_len1, (int)(offsets1[i + 1] - offsets1[i]));
+    const char* force = getenv("ATR_MERGE_KERNEL");
+    const int kmax = (int)thr_mul_of(max_len2, error_rate);
+    const bool use_warp = !(force && force[0] == 't') && max_len2 <= 320 && max_len1 <= 3000 && kmax + 1 <= 250;
     const size_t col_bytes = (size_t)(max_len2 + 1) * sizeof(GCell);
     const size_t smem = col_bytes * ATR_MERGE_THREADS;
     const bool use_shared = smem <= (size_t)200 * 1024;
-    if (use_shared) CU(cudaFuncSetAttribute(k_merge_overlap<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (use_shared && !use_warp) CU(cudaFuncSetAttribute(k_merge_overlap<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t max_pairs = 1 << 19;
     int64_t c0 = 0;
     int which = 0;
@@ -98,7 +252,7 @@ extern "C" int atr_merge_overlap_batch_host(atr_ctx* ctx, const uint8_t* ascii1,
         if (!rc) rc = s.offsets2.ensure((size_t)(cn + 1) * sizeof(int64_t));
         if (!rc) rc = s.out.ensure((size_t)cn * sizeof(atr_merge_result));
         if (!rc && insert_matched) rc = s.win.ensure((size_t)cn);
-        if (!rc && !use_shared) rc = s.gen_scratch.ensure((size_t)blocks * ATR_MERGE_THREADS * col_bytes);
+        if (!rc && !use_shared && !use_warp) rc = s.gen_scratch.ensure((size_t)blocks * ATR_MERGE_THREADS * col_bytes);
         if (rc) return fail(ctx, rc, "out of device memory (merge staging)");
         if (b1) CU(cudaMemcpyAsync(s.ascii.p, ascii1 + offsets1[c0], (size_t)b1, cudaMemcpyHostToDevice, st));
         if (b2) CU(cudaMemcpyAsync(s.ascii2.p, ascii2 + offsets2[c0], (size_t)b2, cudaMemcpyHostToDevice, st));
@@ -107,7 +261,15 @@ extern "C" int atr_merge_overlap_batch_host(atr_ctx* ctx, const uint8_t* ascii1,
         if (insert_matched) CU(cudaMemcpyAsync(s.win.p, insert_matched + c0, (size_t)cn, cudaMemcpyHostToDevice, st));
         const unsigned char* d_im = insert_matched ? s.win.as<unsigned char>() : nullptr;
         if (ctx->profile) CU(cudaEventRecord(ctx->pev[0], st));      // profiling mode: the kernel timed alone, chunk after chunk
-        if (use_shared)
+        if (use_warp) {
+            const unsigned wblocks = (unsigned)std::min<int64_t>((cn + 7) / 8, 148 * 16);
+            if (max_len2 <= 160)
+                k_merge_warp<5><<<wblocks, 256, 0, st>>>(s.ascii.as<unsigned char>(), s.offsets.as<int64_t>(), offsets1[c0], s.ascii2.as<unsigned char>(),
+                                                         s.offsets2.as<int64_t>(), offsets2[c0], d_im, cn, tb, s.out.as<atr_merge_result>());
+            else
+                k_merge_warp<10><<<wblocks, 256, 0, st>>>(s.ascii.as<unsigned char>(), s.offsets.as<int64_t>(), offsets1[c0], s.ascii2.as<unsigned char>(),
+                                                          s.offsets2.as<int64_t>(), offsets2[c0], d_im, cn, tb, s.out.as<atr_merge_result>());
+        } else if (use_shared)
             k_merge_overlap<true><<<(unsigned)blocks, ATR_MERGE_THREADS, smem, st>>>(s.ascii.as<unsigned char>(), s.offsets.as<int64_t>(), offsets1[c0],
                                                                                     s.ascii2.as<unsigned char>(), s.offsets2.as<int64_t>(), offsets2[c0],
                                                                                     d_im, cn, tb, nullptr, s.out.as<atr_merge_result>());

@@ -2,6 +2,8 @@
 golden vectors from the reference modifier (atropos/commands/trim/modifiers.py:864-931), both column placements
 (shared memory / global scratch), and a size-independent property at 1 M pairs: two error-free reads of one fragment
 merge back into the fragment."""
+import os
+
 import numpy as np
 import pytest
 
@@ -28,10 +30,14 @@ def _run(cs, idx, mo, er):
     return ctx.merge_overlap_host(a1, o1, a2, o2, mo, er, insert_matched=im)
 
 
+@pytest.mark.parametrize("kernel", ["warp", "thread"])
 @pytest.mark.parametrize("short_only", [False, True])
-def test_merge_golden(short_only):
+def test_merge_golden(short_only, kernel, monkeypatch):
+    """kernel: k_merge_warp (one warp per pair, 5 or 10 rows per lane) / k_merge_overlap (one thread per pair, columns
+    in shared memory or global scratch) -- the library picks the first whenever its limits hold"""
+    monkeypatch.setenv("ATR_MERGE_KERNEL", kernel)
     cs = merge_cases.cases()
-    if short_only:                                  # read 2 <= 150 nt: the DP columns live in shared memory
+    if short_only:                                  # read 2 <= 150 nt: 5 rows per lane / the DP columns in shared memory
         cs = [c for c in cs if len(c["seq2"]) <= 150]
     ctx = engine.default_context(0)
     before = ctx.launch_count()
@@ -105,3 +111,17 @@ def test_merge_fragments_roundtrip(L, n):
         b = merge_cases.Read(r2[i].tobytes().decode(), "I" * L, False)
         a, b = mod.apply_record(a, b, recs[i], False)
         assert b is None and a.sequence == acgt[frag[i, :F[i]]].tobytes().decode() and len(a.qualities) == F[i]
+
+
+def test_merge_long_reads_fall_back():
+    """reads beyond the warp kernel's 320 nt take the thread-per-pair kernel: same answers as for the same pair inside
+    the limits (an exact overlap of 40 bases between two 400 nt reads)"""
+    rng = np.random.default_rng(5)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    comp = bytes.maketrans(b"ACGT", b"TGCA")
+    frag = acgt[rng.integers(0, 4, size=760)].tobytes()
+    a, o1 = engine.encode_reads([frag[:400]])
+    b, o2 = engine.encode_reads([frag[360:].translate(comp)[::-1]])
+    rec = engine.default_context(0).merge_overlap_host(a, o1, b, o2, 20, 0.1)[0]
+    assert tuple(int(rec[f]) for f in merge_cases.FIELDS) == (0, 40, 360, 400, 40, 0)
+    assert (int(rec["status"]), int(rec["action"])) == (_abi.ATR_ST_MATCH, _abi.ATR_MERGE_APPEND)
