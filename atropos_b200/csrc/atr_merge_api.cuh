@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(ATR_MERGE_THREADS) k_merge_overlap(const unsig
 }
 
 // ---- k_merge_warp: one warp = one pair, the DP as a wavefront over the lanes ------------------------------------------
-// Lane l owns the R = ceil(len2 / 32) rows l*R+1 .. (l+1)*R of the DP (rows = rc(read 2)) as packed 32-bit cells in
+// Lane l owns R = ceil(len2 / 32) consecutive rows of the DP (rows = rc(read 2)) as packed 32-bit cells in
 // registers and works on column s - l in step s: the cell above its first row is the last row of lane l-1 in the same
 // column, computed one step earlier and handed down with one shuffle per step; the diagonal one is the value it received
 // the step before. Every cell of the matrix is evaluated (no data-dependent band): costs are clamped to k + 1 ("dead"),
@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(ATR_MERGE_THREADS) k_merge_overlap(const unsig
 // origin + 1024 [10,22) | matches [0,10); min(diag + SUB, up + INS, left + DEL) reproduces the reference's
 // "mismatch, then insertion, then deletion" order (_align.pyx:405-419). Row len2 is offered as a candidate after every
 // column (:440-458) by the lane that owns it; the last column's candidates (:461-474) are reduced over the warp with
-// the reference's first-best-wins order encoded in the score. Limits: len2 <= 32 * RMAX, k + 1 <= 250, len1 <= 3000
+// the reference's first-best-wins order encoded in the score. Limits: len2 <= 320, k + 1 <= 250, len1 <= 3000
 // (else k_merge_overlap).
 #define MW_COST_SHIFT 24
 #define MW_ORG_SHIFT 10
@@ -54,12 +54,121 @@ __device__ __forceinline__ int mw_cost(unsigned key) { return (int)(key >> MW_CO
 __device__ __forceinline__ int mw_origin(unsigned key) { return (int)((key >> MW_ORG_SHIFT) & 0xFFFu) - MW_ORG_BIAS; }
 __device__ __forceinline__ int mw_matches(unsigned key) { return (int)(key & 0x3FFu); }
 
-template <int RMAX>
+// one pair with R = ceil(len2 / 32) rows per lane (R is uniform over the warp: the caller switches on it). The first
+// `a` = len2 - 32*(R-1) lanes own R rows, the others R - 1, so that the rows add up to len2 exactly: all 32 lanes work
+// (for R = 1: len2 lanes), only a lane's last register is conditional, and row len2 is always the last cell the last
+// lane computes -- the candidate of every column, with no search for it.
+template <int R>
+__device__ __forceinline__ void mw_pair(const unsigned char* __restrict__ r1, const int nq, const unsigned char* __restrict__ r2, const int m,
+                                        const bool siq, const int min_ov, const MergeTables& tb, const int lane,
+                                        atr_merge_result& res, atr_merge_result* __restrict__ dst) {
+    const unsigned FULL = 0xFFFFFFFFu;
+    const int a = m - 32 * (R - 1);                                    // lanes with R rows (1..32)
+    const bool full = lane < a;
+    const int lanes_used = R > 1 ? 32 : m;
+    const int row0 = full ? lane * R + 1 : a * R + (lane - a) * (R - 1) + 1;      // row of register 0
+    int refc[R];
+    bool bad = false;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const int i = row0 + r;
+        refc[r] = 256;
+        if ((r < R - 1 || full) && i <= m) { const unsigned char c = tb.comp[r2[m - i]]; bad = bad || c == 0; refc[r] = c; }
+    }
+    if (__any_sync(FULL, bad)) { res.status = ATR_ST_KEYERROR; if (lane == 0) *dst = res; return; }    // reverse_complement raises
+    const int k = (int)tb.thr_mul[m];
+    const unsigned DEAD = (unsigned)(k + 1) << MW_COST_SHIFT;
+    const unsigned BIAS0 = (unsigned)MW_ORG_BIAS << MW_ORG_SHIFT;      // origin 0, matches 0, cost 0
+    const int max_n = siq ? nq : atr_min(nq, m + k);                   // min_n = 0: both flag sets stop within read 1 (:315-321)
+    unsigned key[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) key[r] = mw_key(0, -(row0 + r), 0);    // column 0 (:338-352): cost 0, origin -i for both flag sets
+    unsigned diag_in = mw_key(0, -(row0 - 1), 0);                      // the row above this lane's first row, one column back
+    unsigned bottom = 0;
+    const bool is_last = lane == lanes_used - 1;
+    const unsigned c_hi = lane < lanes_used ? (unsigned)max_n : 0u;
+    int b_mat = 0, b_cost = m + nq, b_org = 0, b_ref = m, b_q = nq;    // this lane's best candidate (:358-363)
+    const int total = max_n + lanes_used - 1;
+    const unsigned char* __restrict__ q = r1 - 1 - lane;               // q[s] = read 1 base of this lane's column in step s
+    for (int s = 1; s <= total; s++) {
+        const int c = s - lane;                                        // this lane's column in this step
+        const unsigned up_sh = __shfl_up_sync(FULL, bottom, 1);
+        if ((unsigned)(c - 1) < c_hi) {
+            const int qc = (int)q[s];
+            // row 0 (:384-388): free start in read 1 (origin = column) or cost = column
+            const unsigned top = siq ? BIAS0 + ((unsigned)c << MW_ORG_SHIFT)
+                                     : atr_umin(((unsigned)atr_min(c, k + 1) << MW_COST_SHIFT) | BIAS0, DEAD);
+            unsigned up = lane == 0 ? top : up_sh;
+            unsigned diag = diag_in;
+            diag_in = up;
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                if (r < R - 1 || full) {
+                    const unsigned left = key[r];
+                    const unsigned mn = atr_umin(atr_umin(diag + MW_SUB, up + MW_INS), left + MW_DEL) & MW_PRIO_CLEAR;
+                    unsigned nw = refc[r] == qc ? diag + 1u : mn;
+                    nw = atr_umin(nw, DEAD);
+                    diag = left;
+                    key[r] = nw;
+                    up = nw;
+                }
+            }
+            bottom = up;
+            if (is_last && up < DEAD) {                                // row m after this column, if it is alive (:440-458)
+                const int cost = mw_cost(up), org = mw_origin(up), mat = mw_matches(up);
+                const int length = m + atr_min(org, 0);
+                if (length >= 1 && cost <= (int)tb.thr_mul[length] && (mat > b_mat || (mat == b_mat && cost < b_cost))) {
+                    b_mat = mat; b_cost = cost; b_org = org; b_ref = m; b_q = c;
+                }
+            }
+        }
+    }
+    // score: valid | matches | 1023 - cost | order (the in-loop best first, then the last column's rows top down)
+    unsigned score = b_cost != m + nq ? ((1u << 30) | ((unsigned)b_mat << 20) | ((unsigned)(1023 - b_cost) << 10) | 1023u) : 0u;
+    if (siq) {                                                         // max_n == n and STOP_WITHIN_SEQ1: the last column (:461-474)
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const int i = row0 + r;
+            if ((r < R - 1 || full) && lane < lanes_used && key[r] < DEAD) {
+                const int cost = mw_cost(key[r]), org = mw_origin(key[r]), mat = mw_matches(key[r]);
+                const int length = i + atr_min(org, 0);
+                if (length >= 1 && cost <= (int)tb.thr_mul[length]) {
+                    const unsigned sc = (1u << 30) | ((unsigned)mat << 20) | ((unsigned)(1023 - cost) << 10) | (unsigned)(1023 - i);
+                    if (sc > score) { score = sc; b_mat = mat; b_cost = cost; b_org = org; b_ref = i; b_q = nq; }
+                }
+            }
+        }
+    }
+    const unsigned best = __reduce_max_sync(FULL, score);
+    if (best == 0u) { if (lane == 0) *dst = res; return; }             // locate() returned None
+    const int src = __ffs(__ballot_sync(FULL, score == best)) - 1;
+    b_mat = __shfl_sync(FULL, b_mat, src); b_cost = __shfl_sync(FULL, b_cost, src); b_org = __shfl_sync(FULL, b_org, src);
+    b_ref = __shfl_sync(FULL, b_ref, src); b_q = __shfl_sync(FULL, b_q, src);
+    if (lane == 0) {
+        int start1 = 0, start2 = b_org;
+        if (b_org < 0) { start1 = -b_org; start2 = 0; }
+        res.r2_start = (uint16_t)start1; res.r2_stop = (uint16_t)b_ref;
+        res.r1_start = (uint16_t)start2; res.r1_stop = (uint16_t)b_q;
+        res.matches = (uint16_t)b_mat; res.errors = (uint16_t)b_cost;
+        if (b_mat >= min_ov) {                                         // :900-927
+            res.status = ATR_ST_MATCH;
+            if (start1 == 0 && b_ref == m) res.action = ATR_MERGE_KEEP1;
+            else if (start2 == 0 && b_q == nq) res.action = ATR_MERGE_TAKE2;
+            else if (start2 > 0) res.action = ATR_MERGE_APPEND;
+            else if (start1 > 0) res.action = ATR_MERGE_PREPEND;
+            else res.status = ATR_ST_INVALID;
+        }
+        *dst = res;
+    }
+}
+
+// RLO..RLO+4 rows per lane: read 2 up to 160 nt (RLO = 1) or 161..320 nt (RLO = 6; the batch decides, so a shorter
+// pair of a long batch takes the other kernel's code path through mw_pair<1..5> as well)
+template <int RLO>
 __global__ void __launch_bounds__(256) k_merge_warp(const unsigned char* __restrict__ ascii1, const int64_t* __restrict__ offsets1, int64_t base1,
                                                     const unsigned char* __restrict__ ascii2, const int64_t* __restrict__ offsets2, int64_t base2,
                                                     const unsigned char* __restrict__ insert_matched, int64_t n, const MergeTables tb,
                                                     atr_merge_result* __restrict__ out) {
-    const unsigned FULL = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -74,104 +183,25 @@ __global__ void __launch_bounds__(256) k_merge_warp(const unsigned char* __restr
         const int min_ov = (int)tb.minov[atr_min(len1, len2)];
         res.min_overlap = (uint16_t)min_ov;
         if (len1 < min_ov || len2 < min_ov) { if (lane == 0) out[p] = res; continue; }            // :881-882
-        const int m = len2, nq = len1;
-        const int R = (m + 31) >> 5;                                                                // rows per lane
-        // this lane's rows of rc(read 2); a byte the complement table rejects = KeyError for the whole pair
-        int refc[RMAX];
-        bool bad = false;
-#pragma unroll
-        for (int r = 0; r < RMAX; r++) {
-            const int i = lane * R + r + 1;
-            refc[r] = 256;
-            if (r < R && i <= m) { const unsigned char c = tb.comp[r2[m - i]]; bad = bad || c == 0; refc[r] = c; }
-        }
-        if (__any_sync(FULL, bad)) { res.status = ATR_ST_KEYERROR; if (lane == 0) out[p] = res; continue; }
-        const int k = (int)tb.thr_mul[m];
-        const unsigned DEAD = (unsigned)(k + 1) << MW_COST_SHIFT;
         const bool siq = !(insert_matched && insert_matched[p]);       // SEMIGLOBAL; else START_WITHIN_SEQ1 | STOP_WITHIN_SEQ2 (:886-890)
-        const int max_n = siq ? nq : atr_min(nq, m + k);               // min_n = 0: both flag sets stop within read 1 (:315-321)
-        // column 0 (:338-352): cost 0, origin -i for both flag sets
-        unsigned key[RMAX];
-#pragma unroll
-        for (int r = 0; r < RMAX; r++) key[r] = mw_key(0, -(lane * R + r + 1), 0);
-        unsigned diag_in = mw_key(0, -(lane * R), 0);                  // the row above this lane's block, one column back
-        unsigned bottom = 0;
-        const int lanes_used = (m + R - 1) / R;
-        const int lm = (m - 1) / R, rm = (m - 1) - lm * R;             // where row m lives
-        int b_mat = 0, b_cost = m + nq, b_org = 0, b_ref = m, b_q = nq;           // this lane's best candidate (:358-363)
-        const int total = max_n + lanes_used - 1;
-        for (int s = 1; s <= total; s++) {
-            const int c = s - lane;                                    // this lane's column in this step
-            const unsigned up_sh = __shfl_up_sync(FULL, bottom, 1);
-            if (c >= 1 && c <= max_n && lane < lanes_used) {
-                const int qc = (int)r1[c - 1];
-                unsigned up = up_sh;
-                if (lane == 0) up = siq ? mw_key(0, c, 0) : (c > k ? DEAD : mw_key(c, 0, 0));      // row 0 (:384-388)
-                unsigned diag = diag_in;
-                diag_in = up;
-#pragma unroll
-                for (int r = 0; r < RMAX; r++) {
-                    if (r < R) {
-                        const unsigned left = key[r];
-                        const unsigned mn = atr_umin(atr_umin(diag + MW_SUB, up + MW_INS), left + MW_DEL) & MW_PRIO_CLEAR;
-                        unsigned nw = refc[r] == qc ? diag + 1u : mn;
-                        nw = atr_umin(nw, DEAD);
-                        diag = left;
-                        key[r] = nw;
-                        up = nw;
+        const int R = (len2 + 31) >> 5;                                // rows per lane, uniform over the warp
+        switch (R) {
+            case 1: mw_pair<1>(r1, len1, r2, len2, siq, min_ov, tb, lane, res, out + p); break;
+            case 2: mw_pair<2>(r1, len1, r2, len2, siq, min_ov, tb, lane, res, out + p); break;
+            case 3: mw_pair<3>(r1, len1, r2, len2, siq, min_ov, tb, lane, res, out + p); break;
+            case 4: mw_pair<4>(r1, len1, r2, len2, siq, min_ov, tb, lane, res, out + p); break;
+            case 5: mw_pair<5>(r1, len1, r2, len2, siq, min_ov, tb, lane, res, out + p); break;
+            default:
+                if (RLO > 1) {
+                    switch (R) {
+                        case 6: mw_pair<RLO>(r1, len1, r2, len2, siq, min_ov, tb, lane, res, out + p); break;
+                        case 7: mw_pair<RLO + 1>(r1, len1, r2, len2, siq, min_ov, tb, lane, res, out + p); break;
+                        case 8: mw_pair<RLO + 2>(r1, len1, r2, len2, siq, min_ov, tb, lane, res, out + p); break;
+                        case 9: mw_pair<RLO + 3>(r1, len1, r2, len2, siq, min_ov, tb, lane, res, out + p); break;
+                        default: mw_pair<RLO + 4>(r1, len1, r2, len2, siq, min_ov, tb, lane, res, out + p); break;
                     }
                 }
-                bottom = up;
-                if (lane == lm) {                                      // row m after this column (:440-458)
-                    unsigned cm = key[0];
-#pragma unroll
-                    for (int r = 1; r < RMAX; r++) if (r == rm) cm = key[r];
-                    if (cm < DEAD) {
-                        const int cost = mw_cost(cm), org = mw_origin(cm), mat = mw_matches(cm);
-                        const int length = m + atr_min(org, 0);
-                        if (length >= 1 && cost <= (int)tb.thr_mul[length] && (mat > b_mat || (mat == b_mat && cost < b_cost))) {
-                            b_mat = mat; b_cost = cost; b_org = org; b_ref = m; b_q = c;
-                        }
-                    }
-                }
-            }
-        }
-        // score: valid | matches | 1023 - cost | order (the in-loop best first, then the last column's rows top down)
-        unsigned score = b_cost != m + nq ? ((1u << 30) | ((unsigned)b_mat << 20) | ((unsigned)(1023 - b_cost) << 10) | 1023u) : 0u;
-        if (siq) {                                                     // max_n == n and STOP_WITHIN_SEQ1: the last column (:461-474)
-#pragma unroll
-            for (int r = 0; r < RMAX; r++) {
-                const int i = lane * R + r + 1;
-                if (r < R && i <= m && key[r] < DEAD) {
-                    const int cost = mw_cost(key[r]), org = mw_origin(key[r]), mat = mw_matches(key[r]);
-                    const int length = i + atr_min(org, 0);
-                    if (length >= 1 && cost <= (int)tb.thr_mul[length]) {
-                        const unsigned sc = (1u << 30) | ((unsigned)mat << 20) | ((unsigned)(1023 - cost) << 10) | (unsigned)(1023 - i);
-                        if (sc > score) { score = sc; b_mat = mat; b_cost = cost; b_org = org; b_ref = i; b_q = nq; }
-                    }
-                }
-            }
-        }
-        const unsigned top = __reduce_max_sync(FULL, score);
-        if (top == 0u) { if (lane == 0) out[p] = res; continue; }     // locate() returned None
-        const int src = __ffs(__ballot_sync(FULL, score == top)) - 1;
-        b_mat = __shfl_sync(FULL, b_mat, src); b_cost = __shfl_sync(FULL, b_cost, src); b_org = __shfl_sync(FULL, b_org, src);
-        b_ref = __shfl_sync(FULL, b_ref, src); b_q = __shfl_sync(FULL, b_q, src);
-        if (lane == 0) {
-            int start1 = 0, start2 = b_org;
-            if (b_org < 0) { start1 = -b_org; start2 = 0; }
-            res.r2_start = (uint16_t)start1; res.r2_stop = (uint16_t)b_ref;
-            res.r1_start = (uint16_t)start2; res.r1_stop = (uint16_t)b_q;
-            res.matches = (uint16_t)b_mat; res.errors = (uint16_t)b_cost;
-            if (b_mat >= min_ov) {                                     // :900-927
-                res.status = ATR_ST_MATCH;
-                if (start1 == 0 && b_ref == len2) res.action = ATR_MERGE_KEEP1;
-                else if (start2 == 0 && b_q == len1) res.action = ATR_MERGE_TAKE2;
-                else if (start2 > 0) res.action = ATR_MERGE_APPEND;
-                else if (start1 > 0) res.action = ATR_MERGE_PREPEND;
-                else res.status = ATR_ST_INVALID;
-            }
-            out[p] = res;
+                break;
         }
     }
 }
@@ -264,10 +294,10 @@ extern "C" int atr_merge_overlap_batch_host(atr_ctx* ctx, const uint8_t* ascii1,
         if (use_warp) {
             const unsigned wblocks = (unsigned)std::min<int64_t>((cn + 7) / 8, 148 * 16);
             if (max_len2 <= 160)
-                k_merge_warp<5><<<wblocks, 256, 0, st>>>(s.ascii.as<unsigned char>(), s.offsets.as<int64_t>(), offsets1[c0], s.ascii2.as<unsigned char>(),
+                k_merge_warp<1><<<wblocks, 256, 0, st>>>(s.ascii.as<unsigned char>(), s.offsets.as<int64_t>(), offsets1[c0], s.ascii2.as<unsigned char>(),
                                                          s.offsets2.as<int64_t>(), offsets2[c0], d_im, cn, tb, s.out.as<atr_merge_result>());
             else
-                k_merge_warp<10><<<wblocks, 256, 0, st>>>(s.ascii.as<unsigned char>(), s.offsets.as<int64_t>(), offsets1[c0], s.ascii2.as<unsigned char>(),
+                k_merge_warp<6><<<wblocks, 256, 0, st>>>(s.ascii.as<unsigned char>(), s.offsets.as<int64_t>(), offsets1[c0], s.ascii2.as<unsigned char>(),
                                                           s.offsets2.as<int64_t>(), offsets2[c0], d_im, cn, tb, s.out.as<atr_merge_result>());
         } else if (use_shared)
             k_merge_overlap<true><<<(unsigned)blocks, ATR_MERGE_THREADS, smem, st>>>(s.ascii.as<unsigned char>(), s.offsets.as<int64_t>(), offsets1[c0],
