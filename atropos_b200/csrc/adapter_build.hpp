@@ -185,6 +185,7 @@ inline void fill_k1a(const HostAdapter& h, const AtrTables& tb, int index, int r
                   (h.desc.flags == ATR_STOP_WITHIN_SEQ2 || h.desc.flags == ATR_START_WITHIN_SEQ2);
     // Shift-And pieces over the first min(m, 32) rows: k+1 pieces, each at least 6 rows (shorter pieces hit at
     // random too often to be a filter); needs row-m candidates to be reported inside the loop (stop_in_query)
+    a.split8 = 0;
     a.sa_ok = 0; a.sa_rows = h.m < 32 ? h.m : 32; a.sa_start = 0; a.sa_end = 0; a.tail_gate_ok = 0; a.tail_mask = 0;
     const bool stop_in_query = h.desc.flags & ATR_STOP_WITHIN_SEQ2;
     const int pieces = h.k + 1;

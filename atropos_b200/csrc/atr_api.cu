@@ -200,6 +200,7 @@ int locate_on_stream(atr_ctx* ctx, Slot& slot, const atr_adapterset* set,
                 Survivor* wide = narrow + n;
                 Survivor* refine = wide + n;
                 CU(cudaMemsetAsync(counters, 0, 4 * sizeof(int), st));
+                p.split8 = 1;                                  // bands of <= 8 diagonals: back of the narrow list, k_band<8>
                 const bool prof = ctx->profile && set->host.size() == 1;
                 if (prof) CU(cudaEventRecord(ctx->pev[0], st));
                 const unsigned g = grid_for(n, ATR_K1F_THREADS);
@@ -232,8 +233,11 @@ int locate_on_stream(atr_ctx* ctx, Slot& slot, const atr_adapterset* set,
                 // the (small, latency-bound) windowed kernel runs on a side stream underneath the banded one
                 cudaStream_t sw = prof ? st : slot.aux;
                 if (!prof) { CU(cudaEventRecord(slot.ev_fork, st)); CU(cudaStreamWaitEvent(sw, slot.ev_fork, 0)); }
-                if (h.and_mode) k_band<true><<<gp, 128, 0, st>>>(p, d_codes, d_woff, d_len, d_win, d_out, narrow, counters + 0);
-                else k_band<false><<<gp, 128, 0, st>>>(p, d_codes, d_woff, d_len, d_win, d_out, narrow, counters + 0);
+                if (h.and_mode) k_band<true, 16><<<gp, 128, 0, st>>>(p, d_codes, d_woff, d_len, d_win, d_out, narrow, counters + 0);
+                else k_band<false, 16><<<gp, 128, 0, st>>>(p, d_codes, d_woff, d_len, d_win, d_out, narrow, counters + 0);
+                LAUNCHED(ctx);
+                if (h.and_mode) k_band<true, 8><<<gp, 128, 0, st>>>(p, d_codes, d_woff, d_len, d_win, d_out, wide, counters + 3);
+                else k_band<false, 8><<<gp, 128, 0, st>>>(p, d_codes, d_woff, d_len, d_win, d_out, wide, counters + 3);
                 LAUNCHED(ctx);
                 if (prof) CU(cudaEventRecord(ctx->pev[2], st));
                 if (h.and_mode) k_wide<true><<<gp, 128, 0, sw>>>(p, d_codes, d_woff, d_len, d_win, d_out, wide, counters + 1);

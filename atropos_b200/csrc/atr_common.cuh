@@ -61,6 +61,7 @@ struct AdapterK1a {                   // passed by value as a __grid_constant__ 
     int exact_ok;                     // shortcut usable (codes fit nibbles; not the ACGT-filtered query mode)
     short thrJ[ATR_K1A_MAXM + 1];     // start_in_ref adapters: bound on D[m][j] for j = 0..m (j > m uses thrJ[m]); -1 = never
     unsigned sa_start, sa_end;        // bit r-1: row r is the first / last row of a piece
+    int split8;                       // fused path: survivors whose band is <= 8 diagonals go to the back of the narrow list (k_band<8>)
     int filter_only;                  // funnel shape but indel cost != 1: the funnel's first stage as a pure filter, then k1a_read
     int anchor_ok;                    // PREFIX / SUFFIX flag set outside the funnel: fixed-position piece filter (k_filter_anchor)
 };

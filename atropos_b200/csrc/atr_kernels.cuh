@@ -255,6 +255,19 @@ __device__ __forceinline__ void list_append(bool want, Survivor sv, Survivor* __
     if (want) list[base + __popc(mask & ((1u << lane) - 1u))] = sv;
 }
 
+// the same from the end of a list downwards: end[-1], end[-2], ... (the 8-diagonal survivors share the narrow list's
+// storage with the 16-diagonal ones, which fill it from the front)
+__device__ __forceinline__ void list_append_back(bool want, Survivor sv, Survivor* __restrict__ end, int* __restrict__ counter) {
+    const unsigned mask = __ballot_sync(0xffffffffu, want);
+    if (mask == 0) return;
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(mask) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(counter, __popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (want) end[-1 - (base + __popc(mask & ((1u << lane) - 1u)))] = sv;
+}
+
 __device__ __forceinline__ void read_extent(const uint16_t* __restrict__ len, const uint16_t* __restrict__ win, int64_t r,
                                             int& lo, int& n, bool& esc) {
     const unsigned l = len[r];
@@ -419,7 +432,7 @@ __global__ void __launch_bounds__(ATR_K1F_THREADS) k_filter_sa(const __grid_cons
     else __syncthreads();
     const uint32_t* rd = codes + wr;                       // generic pointer: shared tile or global
     if (fits) rd = s_tile + (wr - a_begin);
-    bool to_narrow = false, to_wide = false, to_refine = false;
+    bool to_narrow = false, to_wide = false, to_refine = false, narrow8 = false;
     Survivor sv;
     sv.read = (uint32_t)r; sv.a = 0; sv.b = 0;
     // ---- phase A (every thread): Shift-And scan, exact-occurrence shortcut, does this read need the tail pass? ----
@@ -462,15 +475,17 @@ __global__ void __launch_bounds__(ATR_K1F_THREADS) k_filter_sa(const __grid_cons
             b.ref_stop = ad.m; b.q_stop = n; b.cost = ad.m + n; b.origin = 0; b.matches = 0;
             finalize(ad, b, n, out + r);
         } else if (sr.cls == 1) {
-            if (ad.band_ok && sr.width <= ATR_K1D_W) { to_narrow = true; sv.a = (short)sr.dlo; }
+            if (ad.band_ok && sr.width <= ATR_K1D_W) { to_narrow = true; sv.a = (short)sr.dlo; narrow8 = ad.split8 && sr.width <= 8; }
             else { to_wide = true; sv.a = (short)sr.c0; sv.b = (short)sr.c1; }
         } else if (ad.band_ok && sr.width <= ATR_K1D_W) {
             to_narrow = true; sv.a = (short)sr.dlo;                 // band known from the hits: no exact pass needed
+            narrow8 = ad.split8 && sr.width <= 8;
         } else {
             to_refine = true; sv.a = (short)sr.c0; sv.b = (short)sr.c1;
         }
     }
-    list_append(to_narrow, sv, narrow, counters + 0);
+    list_append(to_narrow && !narrow8, sv, narrow, counters + 0);
+    list_append_back(narrow8, sv, wide, counters + 3);             // `wide` starts where the narrow list's storage ends
     list_append(to_wide, sv, wide, counters + 1);
     list_append(to_refine, sv, refine, counters + 2);
 }
@@ -492,7 +507,7 @@ __global__ void __launch_bounds__(128) k_refine(const __grid_constant__ AdapterK
     const int rounds = (count + stride - 1) / stride;          // uniform trip count: the appends use warp ballots
     for (int it = 0; it < rounds; it++) {
         const int s = it * stride + blockIdx.x * blockDim.x + threadIdx.x;
-        bool to_narrow = false, to_wide = false;
+        bool to_narrow = false, to_wide = false, narrow8 = false;
         Survivor sv;
         sv.read = 0; sv.a = 0; sv.b = 0;
         if (s < count) {
@@ -502,7 +517,7 @@ __global__ void __launch_bounds__(128) k_refine(const __grid_constant__ AdapterK
             FilterHit hit;
             sv.read = in.read;
             if (myers_filter<WORD>(ad, s_peq, codes + woff[in.read], lo, n, hit, (int)in.a, (int)in.b)) {
-                if (ad.band_ok && hit.width <= ATR_K1D_W) { to_narrow = true; sv.a = (short)hit.dlo; }
+                if (ad.band_ok && hit.width <= ATR_K1D_W) { to_narrow = true; sv.a = (short)hit.dlo; narrow8 = ad.split8 && hit.width <= 8; }
                 else { to_wide = true; sv.a = (short)hit.c0; sv.b = (short)hit.c1; }
             } else {
                 Best b;
@@ -510,12 +525,14 @@ __global__ void __launch_bounds__(128) k_refine(const __grid_constant__ AdapterK
                 finalize(ad, b, n, out + in.read);
             }
         }
-        list_append(to_narrow, sv, narrow, counters + 0);
+        list_append(to_narrow && !narrow8, sv, narrow, counters + 0);
+        list_append_back(narrow8, sv, wide, counters + 3);
         list_append(to_wide, sv, wide, counters + 1);
     }
 }
 
-template <bool AND_MODE>
+// W = 16: the narrow list from the front; W = 8: the survivors appended from its end (AdapterK1a.split8), list = that end
+template <bool AND_MODE, int W>
 __global__ void __launch_bounds__(128) k_band(const __grid_constant__ AdapterK1a ad,
         const uint32_t* __restrict__ codes, const uint32_t* __restrict__ woff, const uint16_t* __restrict__ len,
         const uint16_t* __restrict__ win, atr_match* __restrict__ out,
@@ -523,12 +540,12 @@ __global__ void __launch_bounds__(128) k_band(const __grid_constant__ AdapterK1a
     const int count = *counter;
     const int stride = gridDim.x * blockDim.x;
     for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < count; s += stride) {
-        const Survivor sv = list[s];
+        const Survivor sv = W == 8 ? list[-1 - s] : list[s];
         int lo, n; bool esc;
         read_extent(len, win, sv.read, lo, n, esc);
         Best b;
-        if (ad.flags & ATR_START_WITHIN_SEQ1) k1d_band<AND_MODE, ATR_K1D_W, true>(ad, codes + woff[sv.read], lo, n, (int)sv.a, b);
-        else k1d_band<AND_MODE, ATR_K1D_W, false>(ad, codes + woff[sv.read], lo, n, (int)sv.a, b);
+        if (ad.flags & ATR_START_WITHIN_SEQ1) k1d_band<AND_MODE, W, true>(ad, codes + woff[sv.read], lo, n, (int)sv.a, b);
+        else k1d_band<AND_MODE, W, false>(ad, codes + woff[sv.read], lo, n, (int)sv.a, b);
         finalize(ad, b, n, out + sv.read);
     }
 }

@@ -552,11 +552,14 @@ ATR_HD void sa_classify(const AdapterK1a& ad, int lo, int n, int hmin, int hmax,
     // a verbatim piece ending at (row r1, column jh), v = jh - r1: the alignment through it starts in row 0 at a
     // column >= v - k and reaches row m at a column in [v + m - k, v + m + k]
     res.cls = 2;
-    // Every candidate tied to a hit v ends on a diagonal in [v - k, v + k] and its cheap alignments stay within
-    // [v - 2k, v + 2k]: if that (plus the last-column candidates' diagonals) fits the banded kernel, the band
-    // is known without the exact Myers pass and the read skips k_refine.
+    // An accepted alignment of the whole adapter (cost <= k) contains one of the pieces verbatim (pigeonhole), i.e. it
+    // passes through a hit diagonal v in [hmin, hmax], and with at most k indels in total every cell of it lies
+    // within [v - k, v + k]. The reference's own path to such a cell is one of these, and inside that band the DP
+    // sees it with its exact predecessors (cells outside can only be worse, and a worse neighbour never wins a
+    // tie), so the band [hmin - k, hmax + k] (plus the last-column candidates' diagonals) is exact: if it fits the
+    // banded kernel the read skips k_refine.
     {
-        int blo = hmin - 2 * k, bhi = hmax + 2 * k;
+        int blo = hmin - k, bhi = hmax + k;
         if (imax > 0) { blo = atr_min(blo, n - imax - k); bhi = atr_max(bhi, n - imin + k); }
         res.dlo = blo;
         res.width = bhi - blo + 1;
@@ -592,6 +595,8 @@ ATR_HD void sa_filter(const AdapterK1a& ad, const unsigned* __restrict__ sa_peq,
 // that matches nothing. With unit indel cost their cells reproduce the reference's first column exactly
 // (cost i, 0 matches); their origins may come out below 0 / below the true max(0, min_n - i) only where the
 // true origin is 0, hence the clamp at the end (these flag sets never have negative origins).
+template <int W> struct BandWin { typedef unsigned long long type; };      // W read codes of 4 bits
+template <> struct BandWin<8> { typedef unsigned int type; };
 template <bool AND_MODE, int W, bool SIR = false>
 ATR_HD void k1d_band(const AdapterK1a& ad, const uint32_t* __restrict__ codes, int lo, int n, int dlo, Best& best) {
     // SIR (start_in_ref: FRONT / ANYWHERE adapters): the first DP column costs 0 in every row with origin -i
@@ -621,7 +626,9 @@ ATR_HD void k1d_band(const AdapterK1a& ad, const uint32_t* __restrict__ codes, i
     //  * right of the read end: a base that matches EVERYTHING (vm marks those nibbles). A match always takes
     //    the diagonal, so cell (i, n) travels unchanged (plus one match per step) down its diagonal to row m:
     //    the reference's last-column candidates (:461-474) are read off row m at columns n+1.., no per-row tap.
-    unsigned long long win = 0, vm = 0;
+    typedef typename BandWin<W>::type WIN;
+    const WIN ONES = (WIN)0x1111111111111111ull;
+    WIN win = 0, vm = 0;
     auto base_at = [&](int p) -> unsigned {            // p = 0-based position in the (windowed) read
         if (p < min_n) return SIR ? 0u : nomatch;
         if (p >= n) return 0u;
@@ -632,8 +639,8 @@ ATR_HD void k1d_band(const AdapterK1a& ad, const uint32_t* __restrict__ codes, i
     };
 #pragma unroll 1
     for (int d = 0; d < W - 1; d++) {                  // row 1 needs columns 1+dlo .. W+dlo -> positions dlo .. dlo+W-1
-        win |= (unsigned long long)base_at(dlo + d) << (4 * (d + 1));
-        if (dlo + d >= n || (SIR && dlo + d < 0)) vm |= 0xFull << (4 * (d + 1));
+        win |= (WIN)base_at(dlo + d) << (4 * (d + 1));
+        if (dlo + d >= n || (SIR && dlo + d < 0)) vm |= (WIN)0xF << (4 * (d + 1));
     }
     // Rows beyond R = n - dlo have their whole band right of the read end: pure forced-match propagation, which
     // the candidate extraction below accounts for in closed form (partial adapters at the read end stop early).
@@ -641,15 +648,15 @@ ATR_HD void k1d_band(const AdapterK1a& ad, const uint32_t* __restrict__ codes, i
 #pragma unroll 1
     for (int i = 1; i <= R; i++) {
         const int pnew = i + dlo + W - 2;
-        win = (win >> 4) | ((unsigned long long)base_at(pnew) << (4 * (W - 1)));
-        vm = (vm >> 4) | ((pnew >= n || (SIR && pnew < 0)) ? (0xFull << (4 * (W - 1))) : 0ull);
+        win = (win >> 4) | ((WIN)base_at(pnew) << (4 * (W - 1)));
+        vm = (vm >> 4) | ((pnew >= n || (SIR && pnew < 0)) ? ((WIN)0xF << (4 * (W - 1))) : (WIN)0);
         const unsigned a = (unsigned)ad.code[i - 1];
         // per-nibble (mis)match flags for the whole row at once
-        unsigned long long x;
-        if (AND_MODE) x = (win & (0x1111111111111111ull * a)) | vm;
-        else x = (win ^ (0x1111111111111111ull * a)) & ~vm;
+        WIN x;
+        if (AND_MODE) x = (win & (ONES * a)) | vm;
+        else x = (win ^ (ONES * a)) & ~vm;
         x |= x >> 1; x |= x >> 2;                      // bit 4d set <=> nibble d non-zero
-        const unsigned xl = (unsigned)x, xh = (unsigned)(x >> 32);
+        const unsigned xl = (unsigned)x, xh = (unsigned)((unsigned long long)x >> 32);
         unsigned left = DEAD;                          // cell (i, i + dlo - 1): outside the band
 #pragma unroll
         for (int d = 0; d < W; d++) {
@@ -955,7 +962,11 @@ ATR_HD void k1f_read(const AdapterK1a& ad, const uint32_t* __restrict__ codes, i
     if (have) {
         if (ad.band_ok && hit.width <= ATR_K1D_W) {
             if (path) *path = 1;
-            if (ad.flags & ATR_START_WITHIN_SEQ1) k1d_band<AND_MODE, ATR_K1D_W, true>(ad, codes, lo, n, hit.dlo, b);
+            if (hit.width <= 8) {                      // k_band8
+                if (ad.flags & ATR_START_WITHIN_SEQ1) k1d_band<AND_MODE, 8, true>(ad, codes, lo, n, hit.dlo, b);
+                else k1d_band<AND_MODE, 8, false>(ad, codes, lo, n, hit.dlo, b);
+            }
+            else if (ad.flags & ATR_START_WITHIN_SEQ1) k1d_band<AND_MODE, ATR_K1D_W, true>(ad, codes, lo, n, hit.dlo, b);
             else k1d_band<AND_MODE, ATR_K1D_W, false>(ad, codes, lo, n, hit.dlo, b);
         }
         else { if (path) *path = 2; k1a_locate<AND_MODE>(ad, codes, lo, n, b, hit.c0, hit.c1); }
