@@ -539,12 +539,23 @@ ATR_HD void sa_tail(const AdapterK1a& ad, const unsigned* __restrict__ tail_peq,
 // (e) classes 0 / 1 / 2 from the hit range and the last-column rows
 ATR_HD void sa_classify(const AdapterK1a& ad, int lo, int n, int hmin, int hmax, int imin, int imax, SaResult& res) {
     const int m = ad.m, k = ad.k;
-    const bool have_hit = hmax != -0x7fffffff;
+    bool have_hit = hmax != -0x7fffffff;
+    // Which hits can belong to a candidate? A row-m candidate (m, j), j <= n, passes through a hit diagonal
+    // v <= j - m + k; a last-column candidate (i, n) with i > sa_rows (it contains every piece) through one with
+    // v <= n - i + k; rows i <= sa_rows of the last column are the tail pass's (imin..imax), hit or not. Hits further
+    // right -- a piece of an adapter that sticks out of the read -- bound nothing.
+    if (have_hit) {
+        const int vmax = (m > ad.sa_rows ? n - ad.sa_rows - 1 : n - m) + k;
+        if (hmin > vmax) have_hit = false;
+        else hmax = atr_min(hmax, vmax);
+    }
+    // a last-column candidate in row i has at most thr_mul[i] <= thr_mul[imax] errors, hence as many indels
+    const int t = imax > 0 ? (int)ad.thr_mul[imax] : 0;
     if (!have_hit && imax == 0) { res.cls = 0; return; }
     if (!have_hit) {
         res.cls = 1;
-        res.dlo = (n - imax) - k;
-        res.width = (imax - imin) + 2 * k + 1;
+        res.dlo = (n - imax) - t;
+        res.width = (imax - imin) + 2 * t + 1;
         res.c0 = atr_max(0, n - imax - k);
         res.c1 = n;
         return;
@@ -560,7 +571,7 @@ ATR_HD void sa_classify(const AdapterK1a& ad, int lo, int n, int hmin, int hmax,
     // banded kernel the read skips k_refine.
     {
         int blo = hmin - k, bhi = hmax + k;
-        if (imax > 0) { blo = atr_min(blo, n - imax - k); bhi = atr_max(bhi, n - imin + k); }
+        if (imax > 0) { blo = atr_min(blo, n - imax - t); bhi = atr_max(bhi, n - imin + t); }
         res.dlo = blo;
         res.width = bhi - blo + 1;
     }
