@@ -158,7 +158,7 @@ int pack_on_stream(atr_ctx* ctx, cudaStream_t st, DevBuf& counts, DevBuf& scan_t
     if (rc) return fail(ctx, rc, "out of device memory (scan)");
     CU(cub::DeviceScan::ExclusiveSum(scan_tmp.p, tmp_bytes, counts.as<uint32_t>(), d_woff, (int)(n + 1), st));
     ctx->launches += 2;              // CUB's scan is two kernels (library plumbing, counted for honesty)
-    k_pack<<<grid_for(n * 32, 256), 256, 0, st>>>(d_ascii, d_offsets, base, n, fold_case, ctx->d_tables, d_woff, d_codes, d_len);
+    k_pack<<<(unsigned)std::min<int64_t>(grid_for(n, ATR_PK_READS), 148 * 8), 256, 0, st>>>(d_ascii, d_offsets, base, n, fold_case, ctx->d_tables, d_woff, d_codes, d_len);
     LAUNCHED(ctx);
     return ATR_OK;
 }

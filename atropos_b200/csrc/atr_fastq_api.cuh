@@ -88,7 +88,7 @@ int fq_pack_on_stream(atr_ctx* ctx, cudaStream_t st, DevBuf& counts, DevBuf& sca
     LAUNCHED(ctx);
     rc = fq_scan_u32(ctx, st, scan_tmp, counts.as<unsigned>(), d_woff, (int)(n + 1));
     if (rc) return rc;
-    k_fq_pack<<<grid_for(n * 32, 256), 256, 0, st>>>(d_text, d_recs, n, fold_case, ctx->d_tables, d_woff, d_codes, d_len);
+    k_fq_pack<<<(unsigned)std::min<int64_t>(grid_for(n, ATR_PK_READS), 148 * 8), 256, 0, st>>>(d_text, d_recs, n, fold_case, ctx->d_tables, d_woff, d_codes, d_len);
     LAUNCHED(ctx);
     return ATR_OK;
 }

@@ -172,18 +172,34 @@ __global__ void __launch_bounds__(256) k_fq_pack(const unsigned char* __restrict
                                                  int fold_case, const AtrTables* __restrict__ tables, const uint32_t* __restrict__ woff,
                                                  uint32_t* __restrict__ codes, uint16_t* __restrict__ len_out) {
     __shared__ unsigned char s_iupac[256];
-    s_iupac[threadIdx.x] = tables->iupac[threadIdx.x];
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (r >= n_rec) return;
-    const FqRec R = recs[r];
-    const int len = R.seq_len, nwords = (len + 7) >> 3;
-    const uint32_t w0 = woff[r];
-    int esc = 0;
-    for (int w = lane; w < nwords; w += 32) codes[w0 + w] = atr::pack_word(text + R.seq_b, len, w, fold_case, s_iupac, &esc);
-    esc = __any_sync(0xffffffffu, esc);
-    if (lane == 0) len_out[r] = (uint16_t)(len | (esc ? ATR_ESC_BIT : 0));
+    __shared__ uint32_t s_seq[ATR_PK_READS], s_woff[ATR_PK_READS + 1];
+    __shared__ int s_len[ATR_PK_READS], s_esc[ATR_PK_READS];
+    const int tid = threadIdx.x;
+    s_iupac[tid] = tables->iupac[tid];
+    // a sequence line is followed by "\n+...\n" and a quality line as long as itself inside the chunk: the bytes the
+    // fast path reads behind a word (up to 3 behind a full word, up to 10 behind the read's last base) exist
+    const bool aligned = (reinterpret_cast<uintptr_t>(text) & 3) == 0;
+    for (long long r0 = (long long)blockIdx.x * ATR_PK_READS; r0 < n_rec; r0 += (long long)gridDim.x * ATR_PK_READS) {
+        const int cnt = (int)(n_rec - r0 < ATR_PK_READS ? n_rec - r0 : ATR_PK_READS);
+        __syncthreads();
+        if (tid <= cnt) s_woff[tid] = woff[r0 + tid];
+        if (tid < cnt) { const FqRec R = recs[r0 + tid]; s_seq[tid] = R.seq_b; s_len[tid] = R.seq_len; s_esc[tid] = 0; }
+        __syncthreads();
+        const uint32_t wbeg = s_woff[0], wcnt = s_woff[cnt] - wbeg;
+        for (uint32_t j = tid; j < wcnt; j += 256) {                   // one thread per output word, like k_pack
+            const int i = pk_find(s_woff, cnt, wbeg + j);
+            const int w = (int)(wbeg + j - s_woff[i]);
+            const int len = s_len[i];
+            const unsigned char* __restrict__ seq = text + s_seq[i];
+            uint32_t v;
+            int esc = 0;
+            if (!(aligned && pack8_acgt(seq + 8 * w, atr_min(8, len - 8 * w), v))) v = atr::pack_word(seq, len, w, fold_case, s_iupac, &esc);
+            codes[wbeg + j] = v;
+            if (esc) s_esc[i] = 1;
+        }
+        __syncthreads();
+        if (tid < cnt) len_out[r0 + tid] = (uint16_t)(s_len[tid] | (s_esc[tid] ? ATR_ESC_BIT : 0));
+    }
 }
 
 __global__ void __launch_bounds__(256) k_fq_word_counts(const FqRec* __restrict__ recs, long long n, uint32_t* __restrict__ counts) {
