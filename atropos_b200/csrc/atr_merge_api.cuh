@@ -58,14 +58,17 @@ __device__ __forceinline__ int mw_matches(unsigned key) { return (int)(key & 0x3
 // `a` = len2 - 32*(R-1) lanes own R rows, the others R - 1, so that the rows add up to len2 exactly: all 32 lanes work
 // (for R = 1: len2 lanes), only a lane's last register is conditional, and row len2 is always the last cell the last
 // lane computes -- the candidate of every column, with no search for it.
-template <int R>
+template <int R, int LANES>
 __device__ __forceinline__ void mw_pair(const unsigned char* __restrict__ r1, const int nq, const unsigned char* __restrict__ r2, const int m,
-                                        const bool siq, const int min_ov, const MergeTables& tb, const int lane,
+                                        const bool siq, const int min_ov, const MergeTables& tb, const int wlane,
                                         atr_merge_result& res, atr_merge_result* __restrict__ dst) {
-    const unsigned FULL = 0xFFFFFFFFu;
-    const int a = m - 32 * (R - 1);                                    // lanes with R rows (1..32)
+    // LANES = 32: the whole warp works on this pair; 16: each half of the warp on its own pair (all shuffles, votes
+    // and reductions name the half's lanes only, so the halves may run different trip counts)
+    const unsigned FULL = LANES == 32 ? 0xFFFFFFFFu : (0xFFFFu << (wlane & 16));
+    const int lane = wlane & (LANES - 1);
+    const int a = m - LANES * (R - 1);                                 // lanes with R rows (1..LANES)
     const bool full = lane < a;
-    const int lanes_used = R > 1 ? 32 : m;
+    const int lanes_used = R > 1 ? LANES : m;
     const int row0 = full ? lane * R + 1 : a * R + (lane - a) * (R - 1) + 1;      // row of register 0
     int refc[R];
     bool bad = false;
@@ -92,7 +95,7 @@ __device__ __forceinline__ void mw_pair(const unsigned char* __restrict__ r1, co
     const unsigned char* __restrict__ q = r1 - 1 - lane;               // q[s] = read 1 base of this lane's column in step s
     for (int s = 1; s <= total; s++) {
         const int c = s - lane;                                        // this lane's column in this step
-        const unsigned up_sh = __shfl_up_sync(FULL, bottom, 1);
+        const unsigned up_sh = __shfl_up_sync(FULL, bottom, 1, LANES);
         if ((unsigned)(c - 1) < c_hi) {
             const int qc = (int)q[s];
             // row 0 (:384-388): free start in read 1 (origin = column) or cost = column
@@ -162,46 +165,90 @@ __device__ __forceinline__ void mw_pair(const unsigned char* __restrict__ r1, co
     }
 }
 
-// RLO..RLO+4 rows per lane: read 2 up to 160 nt (RLO = 1) or 161..320 nt (RLO = 6; the batch decides, so a shorter
-// pair of a long batch takes the other kernel's code path through mw_pair<1..5> as well)
-template <int RLO>
+// One warp takes two consecutive pairs. If both need the same number R16 = ceil(len2 / 16) <= 10 of rows per lane on 16
+// lanes (always, for reads of one length up to 160 nt), each half of the warp runs its own pair: per wavefront step the
+// fixed cost (shuffle, loop, the read-1 base) is paid once for two pairs and a lane does twice the cells, 15 instead of
+// 31 steps of fill and drain. Otherwise the two pairs run one after the other on all 32 lanes. RHI = most rows per lane
+// in the 32-lane mode: 5 (read 2 up to 160 nt; the kernel with the two-pair mode) or 10 (up to 320 nt).
+template <int RHI>
 __global__ void __launch_bounds__(256) k_merge_warp(const unsigned char* __restrict__ ascii1, const int64_t* __restrict__ offsets1, int64_t base1,
                                                     const unsigned char* __restrict__ ascii2, const int64_t* __restrict__ offsets2, int64_t base2,
                                                     const unsigned char* __restrict__ insert_matched, int64_t n, const MergeTables tb,
                                                     atr_merge_result* __restrict__ out) {
-    const int lane = threadIdx.x & 31;
+    const unsigned ALL = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31, half = lane >> 4;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t p = warp; p < n; p += nwarps) {
-        const int64_t a0 = offsets1[p] - base1, b0 = offsets2[p] - base2;
-        const int len1 = (int)(offsets1[p + 1] - base1 - a0), len2 = (int)(offsets2[p + 1] - base2 - b0);
-        const unsigned char* __restrict__ r1 = ascii1 + a0;
-        const unsigned char* __restrict__ r2 = ascii2 + b0;
+    for (int64_t pp = 2 * warp; pp < n; pp += 2 * nwarps) {
+        // this half's pair
+        const int64_t p = pp + half;
+        const bool have = p < n;
+        int64_t a0 = 0, b0 = 0;
+        int len1 = 0, len2 = 0, min_ov = 0;
+        bool siq = true, work = false;
         atr_merge_result res;
         res.r2_start = res.r2_stop = res.r1_start = res.r1_stop = res.matches = res.errors = 0;
-        res.status = ATR_ST_NONE; res.action = 0;
-        const int min_ov = (int)tb.minov[atr_min(len1, len2)];
-        res.min_overlap = (uint16_t)min_ov;
-        if (len1 < min_ov || len2 < min_ov) { if (lane == 0) out[p] = res; continue; }            // :881-882
-        const bool siq = !(insert_matched && insert_matched[p]);       // SEMIGLOBAL; else START_WITHIN_SEQ1 | STOP_WITHIN_SEQ2 (:886-890)
-        const int R = (len2 + 31) >> 5;                                // rows per lane, uniform over the warp
-        switch (R) {
-            case 1: mw_pair<1>(r1, len1, r2, len2, siq, min_ov, tb, lane, res, out + p); break;
-            case 2: mw_pair<2>(r1, len1, r2, len2, siq, min_ov, tb, lane, res, out + p); break;
-            case 3: mw_pair<3>(r1, len1, r2, len2, siq, min_ov, tb, lane, res, out + p); break;
-            case 4: mw_pair<4>(r1, len1, r2, len2, siq, min_ov, tb, lane, res, out + p); break;
-            case 5: mw_pair<5>(r1, len1, r2, len2, siq, min_ov, tb, lane, res, out + p); break;
-            default:
-                if (RLO > 1) {
-                    switch (R) {
-                        case 6: mw_pair<RLO>(r1, len1, r2, len2, siq, min_ov, tb, lane, res, out + p); break;
-                        case 7: mw_pair<RLO + 1>(r1, len1, r2, len2, siq, min_ov, tb, lane, res, out + p); break;
-                        case 8: mw_pair<RLO + 2>(r1, len1, r2, len2, siq, min_ov, tb, lane, res, out + p); break;
-                        case 9: mw_pair<RLO + 3>(r1, len1, r2, len2, siq, min_ov, tb, lane, res, out + p); break;
-                        default: mw_pair<RLO + 4>(r1, len1, r2, len2, siq, min_ov, tb, lane, res, out + p); break;
+        res.min_overlap = 0; res.status = ATR_ST_NONE; res.action = 0;
+        if (have) {
+            a0 = offsets1[p] - base1; b0 = offsets2[p] - base2;
+            len1 = (int)(offsets1[p + 1] - base1 - a0); len2 = (int)(offsets2[p + 1] - base2 - b0);
+            min_ov = (int)tb.minov[atr_min(len1, len2)];
+            res.min_overlap = (uint16_t)min_ov;
+            work = len1 >= min_ov && len2 >= min_ov;                   // :881-882
+            if (!work && (lane & 15) == 0) out[p] = res;
+            siq = !(insert_matched && insert_matched[p]);              // SEMIGLOBAL; else START_WITHIN_SEQ1 | STOP_WITHIN_SEQ2 (:886-890)
+        }
+        const int r16 = work ? (len2 + 15) >> 4 : 0;
+        const int r16_other = __shfl_xor_sync(ALL, r16, 16);
+        if (RHI == 5 && r16 == r16_other && r16 >= 1 && r16 <= 10) {   // both halves at once (the 320-nt kernel keeps its registers for 10 rows per lane)
+            const unsigned char* __restrict__ r1 = ascii1 + a0;
+            const unsigned char* __restrict__ r2 = ascii2 + b0;
+            switch (r16) {
+                case 1: mw_pair<1, 16>(r1, len1, r2, len2, siq, min_ov, tb, lane, res, out + p); break;
+                case 2: mw_pair<2, 16>(r1, len1, r2, len2, siq, min_ov, tb, lane, res, out + p); break;
+                case 3: mw_pair<3, 16>(r1, len1, r2, len2, siq, min_ov, tb, lane, res, out + p); break;
+                case 4: mw_pair<4, 16>(r1, len1, r2, len2, siq, min_ov, tb, lane, res, out + p); break;
+                case 5: mw_pair<5, 16>(r1, len1, r2, len2, siq, min_ov, tb, lane, res, out + p); break;
+                case 6: mw_pair<6, 16>(r1, len1, r2, len2, siq, min_ov, tb, lane, res, out + p); break;
+                case 7: mw_pair<7, 16>(r1, len1, r2, len2, siq, min_ov, tb, lane, res, out + p); break;
+                case 8: mw_pair<8, 16>(r1, len1, r2, len2, siq, min_ov, tb, lane, res, out + p); break;
+                case 9: mw_pair<9, 16>(r1, len1, r2, len2, siq, min_ov, tb, lane, res, out + p); break;
+                default: mw_pair<10, 16>(r1, len1, r2, len2, siq, min_ov, tb, lane, res, out + p); break;
+            }
+            __syncwarp();
+            continue;
+        }
+        for (int h = 0; h < 2; h++) {                                  // one pair after the other on the whole warp
+            const int src = 16 * h;
+            if (!__shfl_sync(ALL, (int)work, src)) continue;
+            const int64_t q = pp + h;
+            const int64_t qa0 = __shfl_sync(ALL, a0, src), qb0 = __shfl_sync(ALL, b0, src);
+            const int l1 = __shfl_sync(ALL, len1, src), l2 = __shfl_sync(ALL, len2, src), mo = __shfl_sync(ALL, min_ov, src);
+            const bool sq = __shfl_sync(ALL, (int)siq, src) != 0;
+            const unsigned char* __restrict__ r1 = ascii1 + qa0;
+            const unsigned char* __restrict__ r2 = ascii2 + qb0;
+            atr_merge_result rs;
+            rs.r2_start = rs.r2_stop = rs.r1_start = rs.r1_stop = rs.matches = rs.errors = 0;
+            rs.min_overlap = (uint16_t)mo; rs.status = ATR_ST_NONE; rs.action = 0;
+            const int R = (l2 + 31) >> 5;                              // rows per lane, uniform over the warp
+            switch (R) {
+                case 1: mw_pair<1, 32>(r1, l1, r2, l2, sq, mo, tb, lane, rs, out + q); break;
+                case 2: mw_pair<2, 32>(r1, l1, r2, l2, sq, mo, tb, lane, rs, out + q); break;
+                case 3: mw_pair<3, 32>(r1, l1, r2, l2, sq, mo, tb, lane, rs, out + q); break;
+                case 4: mw_pair<4, 32>(r1, l1, r2, l2, sq, mo, tb, lane, rs, out + q); break;
+                case 5: mw_pair<5, 32>(r1, l1, r2, l2, sq, mo, tb, lane, rs, out + q); break;
+                default:
+                    if (RHI > 5) {
+                        switch (R) {
+                            case 6: mw_pair<RHI - 4, 32>(r1, l1, r2, l2, sq, mo, tb, lane, rs, out + q); break;
+                            case 7: mw_pair<RHI - 3, 32>(r1, l1, r2, l2, sq, mo, tb, lane, rs, out + q); break;
+                            case 8: mw_pair<RHI - 2, 32>(r1, l1, r2, l2, sq, mo, tb, lane, rs, out + q); break;
+                            case 9: mw_pair<RHI - 1, 32>(r1, l1, r2, l2, sq, mo, tb, lane, rs, out + q); break;
+                            default: mw_pair<RHI, 32>(r1, l1, r2, l2, sq, mo, tb, lane, rs, out + q); break;
+                        }
                     }
-                }
-                break;
+                    break;
+            }
         }
     }
 }
@@ -292,12 +339,12 @@ extern "C" int atr_merge_overlap_batch_host(atr_ctx* ctx, const uint8_t* ascii1,
         const unsigned char* d_im = insert_matched ? s.win.as<unsigned char>() : nullptr;
         if (ctx->profile) CU(cudaEventRecord(ctx->pev[0], st));      // profiling mode: the kernel timed alone, chunk after chunk
         if (use_warp) {
-            const unsigned wblocks = (unsigned)std::min<int64_t>((cn + 7) / 8, 148 * 16);
+            const unsigned wblocks = (unsigned)std::min<int64_t>((cn + 15) / 16, 148 * 16);      // 8 warps per CTA, two pairs per warp
             if (max_len2 <= 160)
-                k_merge_warp<1><<<wblocks, 256, 0, st>>>(s.ascii.as<unsigned char>(), s.offsets.as<int64_t>(), offsets1[c0], s.ascii2.as<unsigned char>(),
+                k_merge_warp<5><<<wblocks, 256, 0, st>>>(s.ascii.as<unsigned char>(), s.offsets.as<int64_t>(), offsets1[c0], s.ascii2.as<unsigned char>(),
                                                          s.offsets2.as<int64_t>(), offsets2[c0], d_im, cn, tb, s.out.as<atr_merge_result>());
             else
-                k_merge_warp<6><<<wblocks, 256, 0, st>>>(s.ascii.as<unsigned char>(), s.offsets.as<int64_t>(), offsets1[c0], s.ascii2.as<unsigned char>(),
+                k_merge_warp<10><<<wblocks, 256, 0, st>>>(s.ascii.as<unsigned char>(), s.offsets.as<int64_t>(), offsets1[c0], s.ascii2.as<unsigned char>(),
                                                           s.offsets2.as<int64_t>(), offsets2[c0], d_im, cn, tb, s.out.as<atr_merge_result>());
         } else if (use_shared)
             k_merge_overlap<true><<<(unsigned)blocks, ATR_MERGE_THREADS, smem, st>>>(s.ascii.as<unsigned char>(), s.offsets.as<int64_t>(), offsets1[c0],

@@ -163,6 +163,28 @@ def main():
                       "h2d_bytes": int(texts[0].numel() + texts[1].numel()), "d2h_bytes": int(o[0].size + o[1].size),
                       "insert_matches": int(st.insert_matches), "with_adapters": st.with_adapters}))
 
+    # ---- MergeOverlapping: pairs of the cfg3 shape after trimming, i.e. both reads cut to the fragment ---
+    import numpy as np
+    del texts, o
+    for Lm, nm in ((150, 1_000_000), (300, 250_000)):
+        r1, r2 = synth.synth_pe(nm, Lm, seed=synth.seed_for(3) + Lm, device=dev, short_frac=0.0)    # fragments of L..3L: no adapter in the reads
+        a1, a2 = r1.cpu().numpy().reshape(-1), r2.cpu().numpy().reshape(-1)
+        offs = engine.fixed_length_offsets(nm, Lm)
+        ctx.merge_overlap_host(a1, offs, a2, offs, 0.9, 0.2)                                      # warm-up (allocations)
+        ctx.set_profiling(True)
+        recs = ctx.merge_overlap_host(a1, offs, a2, offs, 0.9, 0.2)
+        k_ms = ctx.last_kernel_ms()
+        ctx.set_profiling(False)
+        t0 = time.perf_counter()
+        ctx.merge_overlap_host(a1, offs, a2, offs, 0.9, 0.2)
+        dt = time.perf_counter() - t0
+        b = 2 * Lm + 16 + 16
+        print(json.dumps({"config": "MergeOverlapping 2x%d, error rate 0.2, min_overlap 0.9 (atr_merge_overlap_batch_host)" % Lm,
+                          "pairs": nm, "kernel_ms": k_ms, "kernel_M_pairs_per_s": nm / k_ms / 1e3, "host_call_ms": dt * 1e3,
+                          "host_call_M_pairs_per_s": nm / dt / 1e6, "algo_bytes_per_pair": b,
+                          "hbm_frac": b * nm / (k_ms * 1e-3) / 1e9 / peak, "cell_updates_per_s": nm / (k_ms * 1e-3) * Lm * Lm,
+                          "merged_fraction": float((recs["status"] == _abi.ATR_ST_MATCH).mean())}))
+
 
 if __name__ == "__main__":
     main()
