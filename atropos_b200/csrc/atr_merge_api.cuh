@@ -168,21 +168,22 @@ __device__ __forceinline__ void mw_pair(const unsigned char* __restrict__ r1, co
 // One warp takes two consecutive pairs. If both need the same number R16 = ceil(len2 / 16) <= 10 of rows per lane on 16
 // lanes (always, for reads of one length up to 160 nt), each half of the warp runs its own pair: per wavefront step the
 // fixed cost (shuffle, loop, the read-1 base) is paid once for two pairs and a lane does twice the cells, 15 instead of
-// 31 steps of fill and drain. Otherwise the two pairs run one after the other on all 32 lanes. RHI = most rows per lane
+// 31 steps of fill and drain. Otherwise the two pairs run one after the other on all 32 lanes (for reads of mixed
+// lengths the host hands the pairs over sorted by ceil(len2 / 16), `order`, so that neighbours usually agree). RHI = most rows per lane
 // in the 32-lane mode: 5 (read 2 up to 160 nt; the kernel with the two-pair mode) or 10 (up to 320 nt).
 template <int RHI>
 __global__ void __launch_bounds__(256) k_merge_warp(const unsigned char* __restrict__ ascii1, const int64_t* __restrict__ offsets1, int64_t base1,
                                                     const unsigned char* __restrict__ ascii2, const int64_t* __restrict__ offsets2, int64_t base2,
                                                     const unsigned char* __restrict__ insert_matched, int64_t n, const MergeTables tb,
-                                                    atr_merge_result* __restrict__ out) {
+                                                    const uint32_t* __restrict__ order, atr_merge_result* __restrict__ out) {
     const unsigned ALL = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31, half = lane >> 4;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t pp = 2 * warp; pp < n; pp += 2 * nwarps) {
         // this half's pair
-        const int64_t p = pp + half;
-        const bool have = p < n;
+        const bool have = pp + half < n;
+        const int64_t p = have ? (order ? (int64_t)order[pp + half] : pp + half) : 0;      // order: pairs sorted by rows per lane
         int64_t a0 = 0, b0 = 0;
         int len1 = 0, len2 = 0, min_ov = 0;
         bool siq = true, work = false;
@@ -221,7 +222,7 @@ __global__ void __launch_bounds__(256) k_merge_warp(const unsigned char* __restr
         for (int h = 0; h < 2; h++) {                                  // one pair after the other on the whole warp
             const int src = 16 * h;
             if (!__shfl_sync(ALL, (int)work, src)) continue;
-            const int64_t q = pp + h;
+            const int64_t q = __shfl_sync(ALL, p, src);
             const int64_t qa0 = __shfl_sync(ALL, a0, src), qb0 = __shfl_sync(ALL, b0, src);
             const int l1 = __shfl_sync(ALL, len1, src), l2 = __shfl_sync(ALL, len2, src), mo = __shfl_sync(ALL, min_ov, src);
             const bool sq = __shfl_sync(ALL, (int)siq, src) != 0;
@@ -313,6 +314,7 @@ extern "C" int atr_merge_overlap_batch_host(atr_ctx* ctx, const uint8_t* ascii1,
     int64_t c0 = 0;
     int which = 0;
     float kernel_ms = 0.f;
+    std::vector<uint32_t> order_host;
     while (c0 < n) {
         const int64_t c1 = std::min(n, c0 + max_pairs), cn = c1 - c0;
         const int64_t b1 = offsets1[c1] - offsets1[c0], b2 = offsets2[c1] - offsets2[c0];
@@ -337,15 +339,33 @@ extern "C" int atr_merge_overlap_batch_host(atr_ctx* ctx, const uint8_t* ascii1,
         CU(cudaMemcpyAsync(s.offsets2.p, offsets2 + c0, (size_t)(cn + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, st));
         if (insert_matched) CU(cudaMemcpyAsync(s.win.p, insert_matched + c0, (size_t)cn, cudaMemcpyHostToDevice, st));
         const unsigned char* d_im = insert_matched ? s.win.as<unsigned char>() : nullptr;
+        // mixed read lengths: a counting sort of the chunk's pairs by ceil(len2 / 16) lets neighbours share the two-pair mode
+        const uint32_t* d_order = nullptr;
+        if (use_warp && max_len2 <= 160) {
+            bool mixed = false;
+            const int64_t first = offsets2[c0 + 1] - offsets2[c0];
+            for (int64_t i = c0 + 1; i < c1 && !mixed; i++) mixed = (offsets2[i + 1] - offsets2[i]) != first;
+            if (mixed) {
+                size_t start[12] = {0};
+                for (int64_t i = c0; i < c1; i++) start[((offsets2[i + 1] - offsets2[i] + 15) >> 4) + 1]++;
+                for (int b = 1; b < 12; b++) start[b] += start[b - 1];
+                order_host.resize((size_t)cn);
+                for (int64_t i = c0; i < c1; i++) order_host[start[(offsets2[i + 1] - offsets2[i] + 15) >> 4]++] = (uint32_t)(i - c0);
+                rc = s.woff.ensure((size_t)cn * sizeof(uint32_t));
+                if (rc) return fail(ctx, rc, "out of device memory (merge staging)");
+                CU(cudaMemcpyAsync(s.woff.p, order_host.data(), (size_t)cn * sizeof(uint32_t), cudaMemcpyHostToDevice, st));   // pageable: staged before the call returns
+                d_order = s.woff.as<uint32_t>();
+            }
+        }
         if (ctx->profile) CU(cudaEventRecord(ctx->pev[0], st));      // profiling mode: the kernel timed alone, chunk after chunk
         if (use_warp) {
             const unsigned wblocks = (unsigned)std::min<int64_t>((cn + 15) / 16, 148 * 16);      // 8 warps per CTA, two pairs per warp
             if (max_len2 <= 160)
                 k_merge_warp<5><<<wblocks, 256, 0, st>>>(s.ascii.as<unsigned char>(), s.offsets.as<int64_t>(), offsets1[c0], s.ascii2.as<unsigned char>(),
-                                                         s.offsets2.as<int64_t>(), offsets2[c0], d_im, cn, tb, s.out.as<atr_merge_result>());
+                                                         s.offsets2.as<int64_t>(), offsets2[c0], d_im, cn, tb, d_order, s.out.as<atr_merge_result>());
             else
                 k_merge_warp<10><<<wblocks, 256, 0, st>>>(s.ascii.as<unsigned char>(), s.offsets.as<int64_t>(), offsets1[c0], s.ascii2.as<unsigned char>(),
-                                                          s.offsets2.as<int64_t>(), offsets2[c0], d_im, cn, tb, s.out.as<atr_merge_result>());
+                                                          s.offsets2.as<int64_t>(), offsets2[c0], d_im, cn, tb, d_order, s.out.as<atr_merge_result>());
         } else if (use_shared)
             k_merge_overlap<true><<<(unsigned)blocks, ATR_MERGE_THREADS, smem, st>>>(s.ascii.as<unsigned char>(), s.offsets.as<int64_t>(), offsets1[c0],
                                                                                     s.ascii2.as<unsigned char>(), s.offsets2.as<int64_t>(), offsets2[c0],

@@ -125,3 +125,24 @@ def test_merge_long_reads_fall_back():
     rec = engine.default_context(0).merge_overlap_host(a, o1, b, o2, 20, 0.1)[0]
     assert tuple(int(rec[f]) for f in merge_cases.FIELDS) == (0, 40, 360, 400, 40, 0)
     assert (int(rec["status"]), int(rec["action"])) == (_abi.ATR_ST_MATCH, _abi.ATR_MERGE_APPEND)
+
+
+def test_merge_mixed_lengths_complete_overlap():
+    """1 M pairs of mixed lengths (60..150 nt), read 2 = reverse complement of read 1: every pair overlaps completely
+    (matches = length, no errors, read 2 inside read 1). Mixed lengths go through the host's ordering by rows per lane."""
+    rng = np.random.default_rng(3)
+    n = 1_000_000
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    lens = rng.integers(60, 151, size=n)
+    offs = np.zeros(n + 1, np.int64)
+    np.cumsum(lens, out=offs[1:])
+    a1 = acgt[rng.integers(0, 4, size=int(offs[-1]))]
+    comp = np.zeros(256, np.uint8)
+    comp[list(b"ACGT")] = list(b"TGCA")
+    idx = np.repeat(offs[:-1] + lens - 1, lens) - (np.arange(int(offs[-1])) - np.repeat(offs[:-1], lens))
+    a2 = comp[a1[idx]]
+    recs = engine.default_context(0).merge_overlap_host(a1, offs, a2, offs, 0.9, 0.2)
+    assert np.all(recs["status"] == _abi.ATR_ST_MATCH) and np.all(recs["action"] == _abi.ATR_MERGE_KEEP1)
+    assert np.array_equal(recs["matches"], lens) and np.all(recs["errors"] == 0)
+    assert np.all(recs["r1_start"] == 0) and np.array_equal(recs["r1_stop"], lens)
+    assert np.all(recs["r2_start"] == 0) and np.array_equal(recs["r2_stop"], lens)
