@@ -202,3 +202,28 @@ def merge_cases(seed, count):
                         error_rate=float(rng.choice([0.1, 0.2, 0.2, 0.05, 0.0, 0.3])),
                         mismatch_action=[None, None, "liberal", "conservative", "N"][int(rng.integers(0, 5))]))
     return out
+
+
+def band_cases(seed, adapter, count):
+    """Reads for the banded stage of the fast path: the adapter (mutated, also with indels) somewhere in the read, or a
+    prefix of it near the read end, sometimes with a second partial copy in the middle -- the shapes that decide which
+    diagonals the band must cover (piece hits on several diagonals, last-column candidates, pieces of an adapter that
+    sticks out of the read)."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(count):
+        L = int(rng.integers(20, 170))
+        if rng.random() < 0.5:
+            err = float(rng.choice([0.0, 0.02, 0.05, 0.1, 0.15, 0.25]))
+            read = read_with_adapter(rng, adapter, L, err=err, alphabet="ACGT" if rng.random() < 0.8 else "AC")
+        else:
+            P = int(rng.integers(1, len(adapter) + 1))
+            mut = mutate(rng, adapter[:P], sub=float(rng.choice([0, 0.05, 0.1])), ins=float(rng.choice([0, 0.03, 0.08])),
+                         dele=float(rng.choice([0, 0.03, 0.08]))) or adapter[:P]
+            pre = rand_seq(rng, max(0, L - len(mut) - int(rng.integers(0, 4))))
+            read = (pre + mut + rand_seq(rng, 3))[:L]
+            if rng.random() < 0.2:
+                read = read[:len(read) // 2] + adapter[:int(rng.integers(5, len(adapter)))] + read[len(read) // 2:]
+            read = read[:L]
+        out.append(read)
+    return out

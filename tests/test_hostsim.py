@@ -321,3 +321,20 @@ def test_filter_only_funnel_for_dearer_indels(where):
             found += exp is not None
     assert took > 2000 and found > 400
     assert dp < 0.9 * took
+
+
+@pytest.mark.parametrize("adapter,rate,min_overlap", [
+    (T1, 0.1, 3), (T1, 0.12, 1), ("AGATCGGAAGAGC", 0.1, 3), ("TGGAATTCTCGGGTGCCAAGG", 0.1, 3), (T1, 0.2, 5),
+    ("ACGTACGTACGTACGTACGTAAAA", 0.13, 3), ("A" * 30, 0.1, 3), ("GATCGGAAGAGCACACGTCTGAACTCCAGTCACGATC", 0.09, 3),
+    ("CTGTCTCTTATACACATCTCCGAGCCCACGAGAC", 0.1, 3)])
+def test_band_margins_fuzz(adapter, rate, min_overlap):
+    """the diagonals the banded kernels keep (margin k around the piece hits, floor(i*rate) around the last-column
+    candidates, hits no candidate can pass through dropped) against the oracle's full DP"""
+    d, keep = _abi.make_adapter_desc(adapter, rate, 14, False, False, min_overlap, 1)
+    banded = 0
+    for read in fuzzgen.band_cases(4100 + len(adapter), adapter, 4000):
+        exp = oracle.locate(adapter, read, rate, 14, False, False, min_overlap, 1)
+        got, path, _ = hostsim.locate(read, d, route=0)
+        assert got == exp, (adapter, rate, read, exp, got, path)
+        banded += path in (3, 13)
+    assert banded > 500
