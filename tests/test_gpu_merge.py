@@ -146,3 +146,27 @@ def test_merge_mixed_lengths_complete_overlap():
     assert np.array_equal(recs["matches"], lens) and np.all(recs["errors"] == 0)
     assert np.all(recs["r1_start"] == 0) and np.array_equal(recs["r1_stop"], lens)
     assert np.all(recs["r2_start"] == 0) and np.array_equal(recs["r2_stop"], lens)
+
+
+@pytest.mark.parametrize("L,n,rate", [(150, 400_000, 0.2), (100, 300_000, 0.1), (300, 60_000, 0.2)])
+def test_merge_warp_equals_thread_kernel(L, n, rate, monkeypatch):
+    """the wavefront kernel (every cell, costs clamped) against the thread-per-pair kernel (the reference's banded loop,
+    the code the CPU simulator checks against the golden vectors) on pairs with substitutions, indels and Ns:
+    identical records, both flag sets"""
+    from merge_probe import pairs
+    r1, r2, F = pairs(n, L, 900 + L)
+    rng = np.random.default_rng(L)
+    for arr in (r1, r2):                                   # a few Ns and a deletion-like shift in some reads
+        hit = rng.random(arr.shape) < 0.002
+        arr[hit] = ord("N")
+    shift = rng.random(n) < 0.1
+    r2[shift, 40:-1] = r2[shift, 41:]
+    offs = engine.fixed_length_offsets(n, L)
+    im = (rng.random(n) < 0.3).astype(np.uint8)
+    ctx = engine.default_context(0)
+    monkeypatch.setenv("ATR_MERGE_KERNEL", "warp")
+    a = ctx.merge_overlap_host(r1.reshape(-1), offs, r2.reshape(-1), offs, 0.5, rate, insert_matched=im)
+    monkeypatch.setenv("ATR_MERGE_KERNEL", "thread")
+    b = ctx.merge_overlap_host(r1.reshape(-1), offs, r2.reshape(-1), offs, 0.5, rate, insert_matched=im)
+    assert a.tobytes() == b.tobytes()
+    assert (a["status"] == _abi.ATR_ST_MATCH).mean() > 0.1 and (a["errors"] > 0).mean() > 0.1
