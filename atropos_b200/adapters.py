@@ -90,8 +90,10 @@ class Adapter(object):
             no_indels=not self.indels, rmp_ok=rmp_ok)
 
     def _adapterset(self):
-        if self._set is None:
+        key = engine.context_key(self._device)
+        if self._set is None or self._set_key != key:
             self._set = engine.AdapterSet(engine.default_context(self._device), [self.descriptor()])
+            self._set_key = key
         return self._set
 
     def match_to(self, read):

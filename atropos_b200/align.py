@@ -100,11 +100,13 @@ class Aligner(object):
         self.debug = True
 
     def _adapterset(self):
-        if self._set is None:
+        key = engine.context_key(self._device)         # a set belongs to one context = one (process, thread)
+        if self._set is None or self._set_key != key:
             ctx = engine.default_context(self._device)
             desc = _abi.make_adapter_desc(self.str_reference, self.max_error_rate, self.flags, self.wildcard_ref,
                                           self.wildcard_query, self._min_overlap, self._indel_cost)
             self._set = engine.AdapterSet(ctx, [desc])
+            self._set_key = key
         return self._set
 
     def locate(self, query):
@@ -303,6 +305,9 @@ class InsertAligner(object):
         return d, [a1, a2, ins, adp]
 
     def _insertset(self, max_len):
+        key = engine.context_key(self._device)
+        if self._set is not None and self._set_key != key:
+            self._set = None
         if self._set is not None and self._set.max_len >= max_len:
             return self._set
         L = max(int(max_len), 1)
@@ -310,6 +315,7 @@ class InsertAligner(object):
             L = max(L, 2 * self._set.max_len)          # grow geometrically
         d, keep = self.descriptor(L)
         self._set = engine.InsertSet(engine.default_context(self._device), d, keep)
+        self._set_key = key
         return self._set
 
     # -- the reference's per-pair call --------------------------------------------------------------

@@ -5,6 +5,7 @@ int64[n+1]. `encode_reads` builds them from a list of str. Results come back as 
 arrays (`_abi.MATCH_DTYPE` / `_abi.INSERT_DTYPE`) -- one record per read, no Python objects.
 """
 import ctypes as C
+import os
 import threading
 
 import numpy as np
@@ -116,11 +117,22 @@ class Context(object):
         return out
 
 
+def context_key(device=0):
+    """An atr_ctx owns staging buffers and is not re-entrant (include/atropos_b200.h: one per GPU per host
+    thread), and a CUDA context does not survive fork(): the implicit contexts are cached per
+    (device, process, thread)."""
+    return (int(device), os.getpid(), threading.get_ident())
+
+
 def default_context(device=0):
+    key = context_key(device)
     with _lock:
-        ctx = _default_ctx.get(device)
+        ctx = _default_ctx.get(key)
         if ctx is None or ctx.handle is None:
-            ctx = _default_ctx[device] = Context(device)
+            for k in [k for k in _default_ctx if k[1] != key[1]]:
+                # inherited from the parent of a fork(): the handle means nothing here and must not be destroyed
+                _default_ctx.pop(k).handle = None
+            ctx = _default_ctx[key] = Context(device)
         return ctx
 
 

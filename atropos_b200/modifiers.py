@@ -21,8 +21,10 @@ class AdapterCutter(object):
         self._set = None
 
     def _adapterset(self):
-        if self._set is None:
+        key = engine.context_key(self._device)
+        if self._set is None or self._set_key != key:
             self._set = engine.AdapterSet(engine.default_context(self._device), [a.descriptor() for a in self.adapters])
+            self._set_key = key
         return self._set
 
     def best_match_batch(self, reads, win=None):

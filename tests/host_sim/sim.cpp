@@ -124,6 +124,21 @@ int sim_multi_locate(const unsigned char* ref, int m, const unsigned char* query
     return gen_multi_locate(ref, m, query, n, (int)(rate * m), thr.data(), flags, min_overlap, max_matches, col.data(), out6);
 }
 
+// compare_prefixes as atr_compare_prefixes / k_compare_prefixes evaluate it (_align.pyx:501-544)
+int sim_compare_prefixes(const unsigned char* ref, int m, const unsigned char* query, int n, int wildcard_ref,
+                         int wildcard_query, int* out6) {
+    AtrTables tb;
+    atr::build_tables(tb);
+    const int length = m < n ? m : n;
+    const int mode = (wildcard_ref || wildcard_query) ? 1 : 0;
+    const unsigned char* tr = wildcard_ref ? tb.iupac : tb.acgt;
+    const unsigned char* tq = wildcard_query ? tb.iupac : tb.acgt;
+    int matches = 0;
+    for (int i = 0; i < length; i++) matches += mode == 0 ? (ref[i] == query[i]) : ((tr[ref[i]] & tq[query[i]]) != 0);
+    out6[0] = 0; out6[1] = length; out6[2] = 0; out6[3] = length; out6[4] = matches; out6[5] = length - matches;
+    return 0;
+}
+
 // The FASTQ-in -> trimmed-FASTQ-out path with the device functions of fastq_core.cuh (framing, window/statistics
 // bookkeeping, formatting) and sim_locate for the alignments: what atr_trim_fastq_host computes, one record at a
 // time. counters = {records, with_adapters, bp_in, bp_out, overflow}. Returns 0, or ATR_E_FORMAT with *err filled.

@@ -33,6 +33,8 @@ def lib():
         L.sim_multi_locate.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int,
                                        C.POINTER(C.c_int)]
         L.sim_multi_locate.restype = C.c_int
+        L.sim_compare_prefixes.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
+        L.sim_compare_prefixes.restype = C.c_int
         L.sim_trim_fastq.argtypes = [C.POINTER(_abi.AtrAdapterDesc), C.c_int, C.POINTER(_abi.AtrTrimOpts), C.c_char_p,
                                      C.c_longlong, C.c_void_p, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong),
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_abi.AtrFastqError),
