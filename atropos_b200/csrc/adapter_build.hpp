@@ -222,6 +222,88 @@ inline void fill_k1a(const HostAdapter& h, const AtrTables& tb, int index, int r
     }
 }
 
+// ---- q-gram sampling pre-filter tables (qgram_core.cuh) ----------------------------------------------------------
+// Needs the Shift-And piece layout of fill_k1a (a.sa_ok). tab: 1 << ATR_QG_BITS bytes, to be placed where the kernels
+// (device memory) or the simulator (host memory) can read it; the caller stores that pointer in a.qg_tab.
+// Returns false (and leaves a.qg_ok = 0) when the adapter does not qualify.
+inline bool build_qg(AdapterK1a& a, std::vector<unsigned char>& tab) {
+    a.qg_ok = 0; a.qg_tab = nullptr; a.qg_npat = 0; a.n_tail_cmp = 0;
+    if (!a.sa_ok || a.and_mode) return false;
+    // pieces: runs of rows between sa_start bits and sa_end bits
+    int pstart[8], plen[8], np = 0, lmin = 1 << 30, lmax = 0;
+    for (int r = 0; r < a.sa_rows; r++) {
+        if (a.sa_start & (1u << r)) {
+            int e = r;
+            while (!(a.sa_end & (1u << e))) e++;
+            if (np == 8) return false;
+            pstart[np] = r; plen[np] = e - r + 1;
+            lmin = std::min(lmin, plen[np]); lmax = std::max(lmax, plen[np]);
+            np++;
+        }
+    }
+    if (np == 0) return false;
+    const int q = ATR_QG_Q;
+    int step = lmin - q + 1;                              // q + step - 1 <= shortest piece
+    if (step < 2) return false;                           // every column would be sampled: the automaton is as cheap
+    if (step > 3) step = 3;
+    // patterns: the 6-mers at offsets 0 .. step-1 of every piece. Whatever the piece's position a in the read,
+    // exactly one of these offsets o makes a + o a sampled position, and o + 6 <= step - 1 + 6 <= piece length.
+    if (np * step > 14 && step == 3) step = 2;
+    struct Pat { unsigned x; int piece, off; };
+    std::vector<Pat> pats;
+    for (int p = 0; p < np; p++)
+        for (int o = 0; o < step; o++) {
+            unsigned x = 0;
+            for (int t = 0; t < q; t++) x |= ((unsigned)a.code[pstart[p] + o + t] & 15u) << (4 * t);
+            pats.push_back({x, p, o});
+        }
+    if (pats.size() > 14) return false;
+    // hash multiplier: low 8 bits zero (the 8 bits above the 6-mer in the extracted word must not count); prefer one
+    // that keeps the patterns in distinct buckets
+    static const unsigned cands[] = {0x02416821u, 0x5b33e441u, 0x23e9f297u, 0x9e3779b1u, 0x85ebca6bu, 0xc2b2ae35u, 0x27d4eb2fu, 0x165667b1u};
+    unsigned best_mul = 0; int best_coll = 1 << 30;
+    for (unsigned c : cands) {
+        const unsigned mul = (c | 1u) << 8;
+        std::vector<int> seen;
+        int coll = 0;
+        for (const Pat& pt : pats) {
+            const int key = (int)((pt.x * mul) >> (32 - ATR_QG_BITS));
+            for (size_t t = 0; t < seen.size(); t++) if (seen[t] == key && pats[t].x != pt.x) coll++;
+            seen.push_back(key);
+        }
+        if (coll < best_coll) { best_coll = coll; best_mul = mul; }
+    }
+    tab.assign((size_t)1 << ATR_QG_BITS, 0);
+    for (size_t t = 0; t < pats.size(); t++) {
+        const unsigned key = (pats[t].x * best_mul) >> (32 - ATR_QG_BITS);
+        tab[key] = tab[key] == 0 ? (unsigned char)(t + 1) : 15;       // 15: verify every pattern (repeats inside the adapter land here too)
+        a.qg_prow[t + 1] = (unsigned char)pstart[pats[t].piece];
+        a.qg_plen[t + 1] = (unsigned char)plen[pats[t].piece];
+        a.qg_poff[t + 1] = (unsigned char)pats[t].off;
+    }
+    a.qg_npat = (int)pats.size();
+    a.qg_step = step; a.qg_mul = best_mul;
+    // need-tail gate: one compare per tail_mask row (see fill_k1a). Rows whose prefix is longer than 8 bases are
+    // tested on their last 8 only (a necessary condition; the gate only decides whether the exact tail pass runs).
+    if (a.tail_gate_ok) {
+        for (int i = 1; i <= a.sa_rows; i++) {
+            if (!(a.tail_mask & (1u << (i - 1)))) continue;
+            int p = 0;
+            while (p + 1 < np && pstart[p + 1] < i) p++;              // piece containing row i (1-based): pstart[p] < i
+            const int l = i - pstart[p];                               // rows pstart[p]+1 .. i
+            const int lc = l > 8 ? 8 : l;
+            unsigned c = 0;                                            // rows i-lc+1 .. i in the top lc nibbles
+            for (int t = 0; t < lc; t++) c |= ((unsigned)a.code[i - lc + t] & 15u) << (4 * (8 - lc + t));
+            if (a.n_tail_cmp == 24) { a.n_tail_cmp = -1; break; }      // too many rows: the tail pass always runs
+            a.tail_c[a.n_tail_cmp] = c;
+            a.tail_m[a.n_tail_cmp] = lc == 8 ? 0xFFFFFFFFu : ~((1u << (4 * (8 - lc))) - 1u);
+            a.n_tail_cmp++;
+        }
+    }
+    a.qg_ok = 1;
+    return true;
+}
+
 inline void fill_gen(const HostAdapter& h, int index, int reduce, const unsigned char* ref_dev, const unsigned char* lit_dev,
                      const unsigned short* thr_mul_dev, const unsigned short* thr_div_dev,
                      const unsigned char* rmp_ok_dev, AdapterGen& g) {

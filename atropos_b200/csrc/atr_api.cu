@@ -88,6 +88,9 @@ struct atr_ctx {
     int profile = 0, phases_valid = 0;
     cudaEvent_t pev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // start, after refine, after band, after wide, after filter
     int disable_sa = 0;
+    int disable_qg = 0;              // ATR_DISABLE_QG=1: Shift-And first stage even where the q-gram form is eligible (A/B measurements)
+    int sm_count = 148;
+    int qg_ctas = 5;                 // persistent CTAs per SM of k_filter_qg (51 registers, 42 KB shared memory: 5 fit); ATR_QG_CTAS overrides
     int disable_fused = 0;           // ATR_DISABLE_FUSED=1: always use the plain register-DP kernel (A/B measurements)
     DevBuf misc;                     // small single-call scratch (compare_prefixes, multi_locate)
     DevBuf fq_stats;                 // counters + histograms of atr_trim_fastq_host
@@ -206,7 +209,11 @@ int locate_on_stream(atr_ctx* ctx, Slot& slot, const atr_adapterset* set,
                 const unsigned g = grid_for(n, ATR_K1F_THREADS);
                 const unsigned gp = (unsigned)std::min<int64_t>((n + 127) / 128, 148 * 12);
                 const bool use_sa = p.sa_ok && !ctx->disable_sa;
-                if (use_sa) {
+                if (use_sa && p.qg_ok && !ctx->disable_qg) {
+                    const unsigned gq = (unsigned)std::min<int64_t>((n + ATR_QG_THREADS - 1) / ATR_QG_THREADS, (int64_t)ctx->sm_count * ctx->qg_ctas);
+                    if (p.qg_step == 3) k_filter_qg<3><<<gq, ATR_QG_THREADS, 0, st>>>(p, d_codes, d_woff, d_len, d_win, n, d_out, narrow, wide, refine, counters);
+                    else k_filter_qg<2><<<gq, ATR_QG_THREADS, 0, st>>>(p, d_codes, d_woff, d_len, d_win, n, d_out, narrow, wide, refine, counters);
+                } else if (use_sa) {
                     if (h.and_mode) k_filter_sa<true><<<g, ATR_K1F_THREADS, 0, st>>>(p, d_codes, d_woff, d_len, d_win, n, d_out, narrow, wide, refine, counters);
                     else k_filter_sa<false><<<g, ATR_K1F_THREADS, 0, st>>>(p, d_codes, d_woff, d_len, d_win, n, d_out, narrow, wide, refine, counters);
                 } else if (h.m <= 32) {
@@ -257,7 +264,11 @@ int locate_on_stream(atr_ctx* ctx, Slot& slot, const atr_adapterset* set,
                 const unsigned g = grid_for(n, ATR_K1F_THREADS);
                 const unsigned gp = (unsigned)std::min<int64_t>((n + 127) / 128, 148 * 12);
                 const bool use_sa = p.sa_ok && !ctx->disable_sa;
-                if (use_sa) {
+                if (use_sa && p.qg_ok && !ctx->disable_qg) {
+                    const unsigned gq = (unsigned)std::min<int64_t>((n + ATR_QG_THREADS - 1) / ATR_QG_THREADS, (int64_t)ctx->sm_count * ctx->qg_ctas);
+                    if (p.qg_step == 3) k_filter_qg<3><<<gq, ATR_QG_THREADS, 0, st>>>(p, d_codes, d_woff, d_len, d_win, n, d_out, narrow, wide, refine, counters);
+                    else k_filter_qg<2><<<gq, ATR_QG_THREADS, 0, st>>>(p, d_codes, d_woff, d_len, d_win, n, d_out, narrow, wide, refine, counters);
+                } else if (use_sa) {
                     if (h.and_mode) k_filter_sa<true><<<g, ATR_K1F_THREADS, 0, st>>>(p, d_codes, d_woff, d_len, d_win, n, d_out, narrow, wide, refine, counters);
                     else k_filter_sa<false><<<g, ATR_K1F_THREADS, 0, st>>>(p, d_codes, d_woff, d_len, d_win, n, d_out, narrow, wide, refine, counters);
                 } else if (h.m <= 32) {
@@ -362,7 +373,10 @@ int atr_ctx_create(int device, atr_ctx** out) {
     ctx->device = device;
     { const char* e = getenv("ATR_DISABLE_FUSED"); ctx->disable_fused = (e && e[0] == '1'); }
     { const char* e = getenv("ATR_DISABLE_SA"); ctx->disable_sa = (e && e[0] == '1'); }
+    { const char* e = getenv("ATR_DISABLE_QG"); ctx->disable_qg = (e && e[0] == '1'); }
+    { const char* e = getenv("ATR_QG_CTAS"); if (e && atoi(e) > 0) ctx->qg_ctas = atoi(e); }
     CU(cudaSetDevice(device));
+    { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && v > 0) ctx->sm_count = v; }
     for (int s = 0; s < 2; s++) {
         CU(cudaStreamCreateWithFlags(&ctx->slot[s].stream, cudaStreamNonBlocking));
         CU(cudaStreamCreateWithFlags(&ctx->slot[s].aux, cudaStreamNonBlocking));
@@ -472,7 +486,17 @@ int atr_adapterset_create(atr_ctx* ctx, int32_t n_adapters, const atr_adapter_de
         if (!rc && !h.rmp_ok.empty()) rc = upload(ctx, set->dev_allocs, h.rmp_ok.data(), h.rmp_ok.size(), &d_rmp);
         if (rc) { atr_adapterset_destroy(set); return rc; }
         atr::fill_gen(h, a, a > 0, d_ref, d_lit, d_mul, d_div, d_rmp, set->gen[(size_t)a]);
-        if (h.k1a_ok) atr::fill_k1a(h, ctx->h_tables, a, a > 0, d_rmp, set->k1a[(size_t)a]);
+        if (h.k1a_ok) {
+            AdapterK1a& ka = set->k1a[(size_t)a];
+            atr::fill_k1a(h, ctx->h_tables, a, a > 0, d_rmp, ka);
+            std::vector<unsigned char> qtab;
+            if (atr::build_qg(ka, qtab)) {
+                const unsigned char* d_qtab = nullptr;
+                rc = upload(ctx, set->dev_allocs, qtab.data(), qtab.size(), &d_qtab);
+                if (rc) { atr_adapterset_destroy(set); return rc; }
+                ka.qg_tab = d_qtab;
+            }
+        }
     }
     *out = set;
     return ATR_OK;
@@ -514,6 +538,7 @@ int atr_locate_batch_device(atr_ctx* ctx, const atr_adapterset* set, const uint3
             cudaGetLastError();
             return fail(ctx, ATR_E_ARG, "d_out is not device memory of this context's GPU");
         }
+        if (reinterpret_cast<uintptr_t>(d_out) & 15) return fail(ctx, ATR_E_ARG, "d_out must be 16-byte aligned");
     }
     Slot& s = ctx->slot[0];
     CU(cudaEventRecord(ctx->ev0, s.stream));

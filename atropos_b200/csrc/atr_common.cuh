@@ -64,7 +64,24 @@ struct AdapterK1a {                   // passed by value as a __grid_constant__ 
     int split8;                       // fused path: survivors whose band is <= 8 diagonals go to the back of the narrow list (k_band<8>)
     int filter_only;                  // funnel shape but indel cost != 1: the funnel's first stage as a pure filter, then k1a_read
     int anchor_ok;                    // PREFIX / SUFFIX flag set outside the funnel: fixed-position piece filter (k_filter_anchor)
+    // q-gram sampling pre-filter (k_filter_qg; qgram_core.cuh): the same pieces as the Shift-And stage, but instead of
+    // running an automaton over every column only every qg_step-th read position is looked at: a verbatim piece of
+    // length L >= 6 + qg_step - 1 contains a 6-mer that starts at a sampled position. One hashed byte-table lookup
+    // per sample; hits are verified by comparing the whole piece, so the hit set is exactly the automaton's.
+    int qg_ok, qg_step;               // step 2 or 3 (ASCII compare mode only)
+    unsigned qg_mul;                  // key = (x * qg_mul) >> (32 - ATR_QG_BITS); low 8 bits zero: only 24 bits of x count
+    const unsigned char* qg_tab;      // [1 << ATR_QG_BITS]: 0 none, 1..14 pattern index, 15 several patterns share the bucket
+    int qg_npat;
+    unsigned char qg_prow[16];        // per pattern: 0-based first row of its piece ...
+    unsigned char qg_plen[16];        // ... the piece's length ...
+    unsigned char qg_poff[16];        // ... and the offset of the 6-mer inside the piece
+    // need-tail gate without the automaton's final state: tail_mask bit i-1 (row i inside a begun piece p, l = i - first
+    // row of p) <=> the read's last l bases equal the first l rows of p: (last8 ^ tail_c[t]) & tail_m[t] == 0
+    int n_tail_cmp;
+    unsigned tail_c[24], tail_m[24];
 };
+#define ATR_QG_BITS 13
+#define ATR_QG_Q 6
 
 struct AdapterGen {                   // general kernel: tables live in global memory
     int m, k, flags, ic, min_overlap;

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "locate_core.cuh"
+#include "qgram_core.cuh"
 #include "insert_core.cuh"
 #include "adapter_build.hpp"
 
@@ -554,6 +555,158 @@ __global__ void __launch_bounds__(ATR_K1F_THREADS) k_filter_sa(const __grid_cons
     list_append_back(narrow8, sv, wide, counters + 3);             // `wide` starts where the narrow list's storage ends
     list_append(to_wide, sv, wide, counters + 1);
     list_append(to_refine, sv, refine, counters + 2);
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_filter_qg: the first stage for adapters with a q-gram form (AdapterK1a.qg_ok; qgram_core.cuh) -- the headline
+// configuration. Same outputs as k_filter_sa (finished reads, narrow / 8-diagonal / wide / refine survivor lists), a
+// third of the instructions: every `step`-th read position costs one hashed byte-table lookup instead of every column an
+// automaton step.
+//   * persistent CTAs (grid = a few per SM) walk the tiles of 256 reads; the 8 KB lookup table and the Myers tables
+//     are built in shared memory once per CTA;
+//   * a tile's packed reads are one contiguous span of `codes`, fetched by one TMA bulk copy (cp.async.bulk +
+//     mbarrier) into the CTA's tile buffer; the other CTAs of the SM compute meanwhile;
+//   * phase A (all threads) scan + verification + verbatim-occurrence shortcut + need-tail gate; phase B the exact
+//     32-bit Myers over the read tail for the ~20 % of reads that can have a partial match there, compacted so that
+//     the warps running it are full; phase C classification, one 16-byte record store per finished read, warp-
+//     aggregated list appends.
+// ---------------------------------------------------------------------------------------------
+#define ATR_QG_THREADS 256
+#define ATR_QG_TILE_WORDS 6144       // 24 KB: 256 reads of up to 192 nt
+#define ATR_QG_PAD 8                 // a group of lookups reads up to 3 words past the read's last word
+
+template <int S>
+__global__ void __launch_bounds__(ATR_QG_THREADS, 4) k_filter_qg(const __grid_constant__ AdapterK1a ad,
+        const uint32_t* __restrict__ codes, const uint32_t* __restrict__ woff, const uint16_t* __restrict__ len,
+        const uint16_t* __restrict__ win, int64_t n_reads, atr_match* __restrict__ out,
+        Survivor* __restrict__ narrow, Survivor* __restrict__ wide, Survivor* __restrict__ refine, int* __restrict__ counters) {
+    __shared__ __align__(128) uint32_t s_tile[ATR_QG_TILE_WORDS + ATR_QG_PAD];
+    __shared__ __align__(16) unsigned char s_qtab[1 << ATR_QG_BITS];
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ uint32_t s_acc[ATR_QG_GROUPS * ATR_QG_THREADS];
+    __shared__ unsigned s_tail_peq[16];
+    __shared__ int s_im[ATR_QG_THREADS];
+    __shared__ unsigned short s_tail_list[ATR_QG_THREADS];
+    __shared__ int s_tail_count;
+
+    const int tid = threadIdx.x;
+    // ---- once per CTA: tables, zeroed tile buffer, barrier ----
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(ad.qg_tab);
+        uint4* dst = reinterpret_cast<uint4*>(s_qtab);
+        for (int i = tid; i < (1 << ATR_QG_BITS) / 16; i += ATR_QG_THREADS) dst[i] = src[i];
+        for (int i = tid; i < ATR_QG_TILE_WORDS + ATR_QG_PAD; i += ATR_QG_THREADS) s_tile[i] = 0u;
+    }
+    if (tid < 16) {
+        const int mp = ad.sa_rows, sh32 = 32 - mp;
+        const unsigned low = (unsigned)(ad.peq[tid] & (mp >= 32 ? 0xFFFFFFFFull : ((1ull << mp) - 1)));
+        s_tail_peq[tid] = sh32 ? ((low << sh32) | ((1u << sh32) - 1u)) : low;
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar)) : "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    uint32_t parity = 0;
+    const int64_t n_tiles = (n_reads + ATR_QG_THREADS - 1) / ATR_QG_THREADS;
+    const bool aligned = (reinterpret_cast<uintptr_t>(codes) & 15) == 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t t0 = tile * ATR_QG_THREADS;
+        const int cnt = (int)(n_reads - t0 < ATR_QG_THREADS ? n_reads - t0 : ATR_QG_THREADS);
+        const uint32_t w_begin = woff[t0], w_end = woff[t0 + cnt];
+        const uint32_t a_begin = w_begin & ~3u;                        // TMA: 16-byte aligned address and size
+        const uint32_t span = ((w_end - a_begin) + 3u) & ~3u;
+        const bool last_tile = (t0 + cnt == n_reads);                  // may not read past the end of `codes`
+        const bool fits = span <= ATR_QG_TILE_WORDS;
+        const bool use_tma = fits && !last_tile && span > 0 && aligned;
+        __syncthreads();                       // everybody is done with the previous tile (and with the set-up above)
+        if (tid == 0) {
+            s_tail_count = 0;
+            if (use_tma) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads of the tile before the async write
+                tma_load_1d(s_tile, codes + a_begin, span * 4u, &s_bar);
+            }
+        }
+        if (fits && !use_tma)
+            for (uint32_t w = tid; w < w_end - a_begin; w += ATR_QG_THREADS) s_tile[w] = codes[a_begin + w];
+        // per-read bookkeeping while the copy is in flight
+        const int64_t r = t0 + tid;
+        const bool mine = tid < cnt;
+        bool routed = false, esc = false;
+        int lo = 0, n = 0;
+        uint32_t wr = a_begin;
+        int nw = 0;
+        if (mine) {
+            const unsigned l = len[r];
+            nw = (int)(((l & ATR_LEN_MASK) + 7u) >> 3);
+            read_extent(len, win, r, lo, n, esc);
+            wr = woff[r];
+            routed = esc || n > ATR_K1A_MAXN;                          // ASCII compare mode: escaped reads take k_locate_gen
+            if (routed && ad.mark_routed) {
+                atr_match m;
+                m.astart = m.astop = m.rstart = m.rstop = m.matches = m.errors = 0;
+                m.adapter = -1; m.status = ATR_ST_ESCAPED;
+                store_match(out + r, m);
+            }
+        }
+        __syncthreads();                       // s_tail_count = 0 and the cooperative copy are visible
+        if (use_tma) { mbar_wait(&s_bar, parity); parity ^= 1u; }
+        const uint32_t* rd = codes + wr;       // generic pointer: shared tile or global
+        int wlimit = nw;
+        if (fits) { rd = s_tile + (wr - a_begin); wlimit = (int)(ATR_QG_TILE_WORDS + ATR_QG_PAD - (wr - a_begin)); }
+        // ---- phase A (every thread) ----
+        int hmin = 0x7fffffff, hmax = -0x7fffffff;
+        bool exact = false, need_tail = false;
+        if (mine && !routed) {
+            qg_scan<S>(ad, s_qtab, rd, wlimit, lo, n, s_acc + tid, ATR_QG_THREADS, hmin, hmax);
+            exact = sa_exact(ad, rd, lo, n, hmin, hmax);
+            if (!exact) need_tail = qg_need_tail(ad, rd, lo, n, hmax);
+        }
+        // ---- phase B: exact tail Myers, compacted ----
+        s_im[tid] = 0;
+        if (need_tail) s_tail_list[atomicAdd(&s_tail_count, 1)] = (unsigned short)tid;
+        __syncthreads();
+        for (int e = tid; e < s_tail_count; e += ATR_QG_THREADS) {
+            const int t2 = s_tail_list[e];
+            int lo2, n2; bool esc2;
+            read_extent(len, win, t0 + t2, lo2, n2, esc2);
+            const uint32_t wr2 = woff[t0 + t2];
+            const uint32_t* rd2 = codes + wr2;
+            if (fits) rd2 = s_tile + (wr2 - a_begin);
+            s_im[t2] = sa_tail_packed(&ad, s_tail_peq, rd2, lo2, n2);
+        }
+        __syncthreads();
+        // ---- phase C (every thread): classify, store, append ----
+        bool to_narrow = false, to_wide = false, to_refine = false, narrow8 = false, finished = false;
+        Survivor sv;
+        sv.read = (uint32_t)r; sv.a = 0; sv.b = 0;
+        Best b;
+        b.ref_stop = ad.m; b.q_stop = n; b.cost = ad.m + n; b.origin = 0; b.matches = 0;       // "no match"
+        if (mine && !routed) {
+            if (exact) {                                                // verbatim occurrence: the str.find shortcut
+                b.matches = ad.m; b.cost = 0; b.origin = hmin; b.q_stop = hmin + ad.m;
+                finished = true;
+            } else {
+                const int im = s_im[tid];
+                SaResult sr;
+                sa_classify(ad, lo, n, hmin, hmax, im >> 16, im & 0xFFFF, sr);
+                if (sr.cls == 0) finished = true;
+                else if (sr.cls == 1) {
+                    if (ad.band_ok && sr.width <= ATR_K1D_W) { to_narrow = true; sv.a = (short)sr.dlo; narrow8 = ad.split8 && sr.width <= 8; }
+                    else { to_wide = true; sv.a = (short)sr.c0; sv.b = (short)sr.c1; }
+                } else if (ad.band_ok && sr.width <= ATR_K1D_W) {
+                    to_narrow = true; sv.a = (short)sr.dlo;
+                    narrow8 = ad.split8 && sr.width <= 8;
+                } else {
+                    to_refine = true; sv.a = (short)sr.c0; sv.b = (short)sr.c1;
+                }
+            }
+        }
+        if (finished) finalize(ad, b, n, out + r);
+        list_append(to_narrow && !narrow8, sv, narrow, counters + 0);
+        list_append_back(narrow8, sv, wide, counters + 3);
+        list_append(to_wide, sv, wide, counters + 1);
+        list_append(to_refine, sv, refine, counters + 2);
+    }
 }
 
 // k_refine: exact Myers over the column range the piece hits point at; dense over the refine list

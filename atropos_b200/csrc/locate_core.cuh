@@ -63,15 +63,36 @@ ATR_HD void consider(const A& ad, Best& b, int cost, int origin, int matches, in
 
 // AdapterCutter._best_match's reduction over the adapters of a set (modifiers.py:116-121): the kernels run
 // adapter after adapter in list order, a later adapter only replaces the stored match with strictly more matches.
+// a record is one 16-byte transaction on the device (every record array the kernels write is 16-byte aligned: the
+// library's own buffers, and atr_locate_batch_device checks the caller's)
+ATR_HD void store_match(atr_match* out, const atr_match& r) {
+#if defined(__CUDA_ARCH__)
+    union { atr_match m; uint4 v; } u;
+    u.m = r;
+    *reinterpret_cast<uint4*>(out) = u.v;
+#else
+    *out = r;
+#endif
+}
+ATR_HD atr_match load_match(const atr_match* p) {
+#if defined(__CUDA_ARCH__)
+    union { atr_match m; uint4 v; } u;
+    u.v = *reinterpret_cast<const uint4*>(p);
+    return u.m;
+#else
+    return *p;
+#endif
+}
+
 template <class A>
 ATR_HD void emit(const A& ad, const atr_match& r, atr_match* out) {
     if (ad.reduce) {
-        const atr_match prev = *out;
+        const atr_match prev = load_match(out);
         if (prev.status >= ATR_ST_ESCAPED) return;      // ESCAPED / INVALID / KEYERROR are sticky: the host raises
         if (r.status == ATR_ST_NONE) return;
         if (r.status == ATR_ST_MATCH && prev.status == ATR_ST_MATCH && r.matches <= prev.matches) return;
     }
-    *out = r;
+    store_match(out, r);
 }
 
 // the literal-hit result of the str.find / startswith / endswith shortcut (adapters/__init__.py:363-367)
@@ -938,6 +959,9 @@ ATR_HD void anchor_read(const AdapterK1a& ad, const uint32_t* __restrict__ codes
 
 // ---- the whole funnel for one read (what the kernels do, minus the compaction between the stages) ----
 #define ATR_K1D_W 16
+// qgram_core.cuh: the q-gram sampling form of the first stage (AdapterK1a.qg_ok), same result classes
+ATR_HD void qg_filter(const AdapterK1a& ad, const unsigned* __restrict__ tail_peq, const uint32_t* __restrict__ codes, int wlimit,
+                      int lo, int n, SaResult& res);
 template <class WORD, bool AND_MODE>
 ATR_HD void k1f_read(const AdapterK1a& ad, const uint32_t* __restrict__ codes, int lo, int n, atr_match* out, int* path = nullptr) {
     Best b;
@@ -957,7 +981,8 @@ ATR_HD void k1f_read(const AdapterK1a& ad, const uint32_t* __restrict__ codes, i
             tail_peq[c] = (sh32 ? (low << sh32) | ((1u << sh32) - 1u) : low);
         }
         SaResult sr;
-        sa_filter(ad, sa_peq, tail_peq, codes, lo, n, sr);
+        if (ad.qg_ok) qg_filter(ad, tail_peq, codes, (lo + n + 7) >> 3, lo, n, sr);
+        else sa_filter(ad, sa_peq, tail_peq, codes, lo, n, sr);
         if (sr.cls == 3) {
             b.matches = ad.m; b.cost = 0; b.origin = sr.v; b.ref_stop = ad.m; b.q_stop = sr.v + ad.m;
             if (path) *path = 5;
@@ -1013,7 +1038,8 @@ ATR_HD void icfilter_read(const AdapterK1a& ad, const uint32_t* __restrict__ cod
             tail_peq[c] = (sh32 ? (low << sh32) | ((1u << sh32) - 1u) : low);
         }
         SaResult sr;
-        sa_filter(ad, sa_peq, tail_peq, codes, lo, n, sr);
+        if (ad.qg_ok) qg_filter(ad, tail_peq, codes, (lo + n + 7) >> 3, lo, n, sr);
+        else sa_filter(ad, sa_peq, tail_peq, codes, lo, n, sr);
         if (sr.cls == 3) {
             b.matches = ad.m; b.cost = 0; b.origin = sr.v; b.ref_stop = ad.m; b.q_stop = sr.v + ad.m;
             if (path) *path = 5;

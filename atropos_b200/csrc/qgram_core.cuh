@@ -1,0 +1,135 @@
+// qgram_core.cuh -- q-gram sampling form of the funnel's first stage (k_filter_qg), one thread = one read.
+//
+// Same necessary condition as the Shift-And stage (locate_core.cuh: sa_scan): an alignment of the adapter's first
+// sa_rows rows with <= k unit-cost errors contains one of k+1 pieces verbatim. The automaton finds the pieces by
+// touching every column of the read (~7.5 instructions per column, the kernel is bound by instruction issue). Here a
+// read position is only looked at if it is a multiple of `step` (2 or 3): a verbatim piece of length
+// L >= 6 + step - 1 contains a 6-mer that starts at such a position, whatever the piece's own position. One lookup =
+// 24 bits of the packed read -> multiplicative hash -> one byte of an 8 KB table in shared memory (0 = no adapter 6-mer
+// hashes here, else which 6-mer of which piece). The few hits are verified by comparing the whole piece at the position
+// the 6-mer implies, so the verified hit set -- and with it the range [hmin, hmax] of hit diagonals, the exact-occurrence
+// shortcut, the bands and every result -- is exactly that of the automaton (tests/test_hostsim.py compares them).
+// ASCII compare mode only (verbatim = equal codes); wildcard modes keep the automaton.
+#pragma once
+#include "locate_core.cuh"
+
+#define ATR_QG_GROUPS 8               // groups per chunk: 8 lookups each, one 32-bit accumulator per group
+
+// 8 lookups of group g: S = 3 -> 24 columns (3 packed words + 1), S = 2 -> 16 columns (2 words + 1).
+// codes: the packed read; word indices >= wlimit are not read (they count as zeros).
+template <int S>
+ATR_HD uint32_t qg_group(const unsigned char* __restrict__ tab, unsigned mul, const uint32_t* __restrict__ codes,
+                         int g, int wlimit) {
+    const int w0i = (S == 3 ? 3 : 2) * g;
+    uint32_t w0, w1, w2, w3 = 0;
+    if (w0i + (S == 3 ? 3 : 2) < wlimit) {               // the common case: every word of the group exists
+        w0 = codes[w0i]; w1 = codes[w0i + 1]; w2 = codes[w0i + 2];
+        if (S == 3) w3 = codes[w0i + 3];
+    } else {
+        w0 = w0i < wlimit ? codes[w0i] : 0u;
+        w1 = w0i + 1 < wlimit ? codes[w0i + 1] : 0u;
+        w2 = w0i + 2 < wlimit ? codes[w0i + 2] : 0u;
+        if (S == 3) w3 = w0i + 3 < wlimit ? codes[w0i + 3] : 0u;
+    }
+    uint32_t x[8];
+    if (S == 3) {                                         // nibble offsets 0, 3, 6, ..., 21
+        x[0] = w0;                     x[1] = funnel_r32(w0, w1, 12); x[2] = funnel_r32(w0, w1, 24);
+        x[3] = funnel_r32(w1, w2, 4);  x[4] = funnel_r32(w1, w2, 16); x[5] = funnel_r32(w1, w2, 28);
+        x[6] = funnel_r32(w2, w3, 8);  x[7] = funnel_r32(w2, w3, 20);
+    } else {                                              // nibble offsets 0, 2, 4, ..., 14
+        x[0] = w0; x[1] = funnel_r32(w0, w1, 8); x[2] = funnel_r32(w0, w1, 16); x[3] = funnel_r32(w0, w1, 24);
+        x[4] = w1; x[5] = funnel_r32(w1, w2, 8); x[6] = funnel_r32(w1, w2, 16); x[7] = funnel_r32(w1, w2, 24);
+    }
+    uint32_t acc = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc += (uint32_t)tab[(x[i] * mul) >> (32 - ATR_QG_BITS)] << (4 * i);
+    return acc;
+}
+
+// a hit of pattern `id` at sampled absolute position c of the packed read: is the whole piece there, inside the window?
+ATR_HD void qg_verify_pattern(const AdapterK1a& ad, const uint32_t* __restrict__ codes, int lo, int n, int id, int c,
+                              int& hmin, int& hmax) {
+    const int prow = ad.qg_prow[id], plen = ad.qg_plen[id];
+    const int a = c - (int)ad.qg_poff[id];               // absolute position of the piece's first base
+    if (a < lo || a + plen > lo + n) return;
+    if (!anchor_piece_equal(ad, codes, a, prow, plen)) return;
+    const int v = (a - lo) - prow;                       // diagonal: (column of the piece end) - (row of the piece end)
+    hmin = atr_min(hmin, v); hmax = atr_max(hmax, v);
+}
+
+template <int S>
+ATR_HD void qg_verify_group(const AdapterK1a& ad, const uint32_t* __restrict__ codes, int lo, int n, int g, uint32_t acc,
+                            int& hmin, int& hmax) {
+    while (acc) {
+        const int i = atr_ctz(acc) >> 2;
+        const int id = (int)((acc >> (4 * i)) & 15u);
+        acc &= ~(15u << (4 * i));
+        const int c = (S == 3 ? 24 : 16) * g + S * i;
+        if (id == 15) { for (int t = 1; t <= ad.qg_npat; t++) qg_verify_pattern(ad, codes, lo, n, t, c, hmin, hmax); }
+        else qg_verify_pattern(ad, codes, lo, n, id, c, hmin, hmax);
+    }
+}
+
+// groups that hold a sampled position at which a 6-mer can lie inside the window [lo, lo + n)
+template <int S>
+ATR_HD void qg_group_range(int lo, int n, int& g0, int& g1) {
+    const int G = S == 3 ? 24 : 16;
+    g0 = lo / G;
+    g1 = n >= ATR_QG_Q ? (lo + n - ATR_QG_Q) / G + 1 : g0;        // exclusive
+}
+
+// (a) the whole scan for one read: range of the verified hit diagonals. acc: scratch of ATR_QG_GROUPS words, element
+// t at acc[t * stride] (shared memory [group][thread] in the kernel).
+template <int S>
+ATR_HD void qg_scan(const AdapterK1a& ad, const unsigned char* __restrict__ tab, const uint32_t* __restrict__ codes, int wlimit,
+                    int lo, int n, uint32_t* acc, int stride, int& hmin, int& hmax) {
+    hmin = 0x7fffffff; hmax = -0x7fffffff;
+    int g0, g1;
+    qg_group_range<S>(lo, n, g0, g1);
+    for (int gb = g0; gb < g1; gb += ATR_QG_GROUPS) {
+        const int ng = atr_min(ATR_QG_GROUPS, g1 - gb);
+        uint32_t any = 0;
+        for (int t = 0; t < ng; t++) {
+            const uint32_t a = qg_group<S>(tab, ad.qg_mul, codes, gb + t, wlimit);
+            acc[t * stride] = a;
+            any |= a;
+        }
+        if (any) for (int t = 0; t < ng; t++) {
+            const uint32_t a = acc[t * stride];
+            if (a) qg_verify_group<S>(ad, codes, lo, n, gb + t, a, hmin, hmax);
+        }
+    }
+}
+
+// (c) the need-tail gate of sa_need_tail without the automaton's final state
+ATR_HD bool qg_need_tail(const AdapterK1a& ad, const uint32_t* __restrict__ codes, int lo, int n, int hmax) {
+    const bool stop_in_ref = ad.flags & ATR_STOP_WITHIN_SEQ1;
+    if (!(stop_in_ref || ad.m <= ad.sa_rows)) return false;
+    if (!ad.tail_gate_ok || ad.n_tail_cmp < 0 || n < 8) return true;
+    if (hmax != -0x7fffffff && hmax >= n - ad.sa_rows - ad.k) return true;
+    const int q = lo + n - 8;                              // the read's last 8 bases: nibble j = position n - 8 + j
+    const uint32_t w0 = codes[q >> 3];
+    const uint32_t w1 = (q & 7) ? codes[(q >> 3) + 1] : 0u;
+    const uint32_t tw = funnel_r32(w0, w1, (unsigned)(q & 7) * 4u);
+    bool need = false;
+    for (int t = 0; t < ad.n_tail_cmp; t++) need = need || ((tw ^ ad.tail_c[t]) & ad.tail_m[t]) == 0u;
+    return need;
+}
+
+// the whole stage for one read (host simulator; the kernel interleaves a block-level compaction before the tail pass)
+template <int S>
+ATR_HD void qg_filter_s(const AdapterK1a& ad, const unsigned* __restrict__ tail_peq, const uint32_t* __restrict__ codes, int wlimit,
+                        int lo, int n, SaResult& res) {
+    int hmin, hmax, imin = 0, imax = 0;
+    uint32_t acc[ATR_QG_GROUPS];
+    qg_scan<S>(ad, ad.qg_tab, codes, wlimit, lo, n, acc, 1, hmin, hmax);
+    if (sa_exact(ad, codes, lo, n, hmin, hmax)) { res.cls = 3; res.v = hmin; return; }
+    if (qg_need_tail(ad, codes, lo, n, hmax)) sa_tail(ad, tail_peq, codes, lo, n, imin, imax);
+    sa_classify(ad, lo, n, hmin, hmax, imin, imax, res);
+}
+
+ATR_HD void qg_filter(const AdapterK1a& ad, const unsigned* __restrict__ tail_peq, const uint32_t* __restrict__ codes, int wlimit,
+                      int lo, int n, SaResult& res) {
+    if (ad.qg_step == 3) qg_filter_s<3>(ad, tail_peq, codes, wlimit, lo, n, res);
+    else qg_filter_s<2>(ad, tail_peq, codes, wlimit, lo, n, res);
+}

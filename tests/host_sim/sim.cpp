@@ -6,11 +6,69 @@
 #include <vector>
 #include "../../atropos_b200/csrc/adapter_build.hpp"
 #include "../../atropos_b200/csrc/locate_core.cuh"
+#include "../../atropos_b200/csrc/qgram_core.cuh"
 #include "../../atropos_b200/csrc/insert_core.cuh"
 #include "../../atropos_b200/csrc/fastq_core.cuh"
 #include "../../atropos_b200/csrc/merge_core.cuh"
 
+static int g_sim_qg = 1;          // 0: keep the Shift-And first stage even where the q-gram form is eligible (A/B)
+
 extern "C" {
+
+void sim_set_qg(int on) { g_sim_qg = on; }
+
+// First stage of the funnel both ways for one read: the Shift-And automaton (sa_filter) and the q-gram sampling
+// (qg_filter). out[0..5] = cls, dlo, width, c0, c1, v of the automaton, out[6..11] of the q-gram form; also the raw
+// hit ranges out[12..13] (automaton hmin, hmax), out[14..15] (q-gram). Returns 1 if the adapter has both forms.
+int sim_filter_compare(const atr_adapter_desc* d, const unsigned char* read, int len, int lo, int hi, int fold_case, int* out) {
+    AtrTables tb;
+    atr::build_tables(tb);
+    atr::HostAdapter h;
+    std::string msg;
+    if (atr::prepare_adapter(*d, tb, h, msg) != ATR_OK || !h.k1a_ok) return 0;
+    AdapterK1a a;
+    atr::fill_k1a(h, tb, 0, 0, nullptr, a);
+    std::vector<unsigned char> tab;
+    if (!a.sa_ok || !atr::build_qg(a, tab)) return 0;
+    a.qg_tab = tab.data();
+    if (hi > len) hi = len;
+    if (lo > hi) lo = hi;
+    const int n = hi - lo, nwords = (len + 7) / 8;
+    std::vector<uint32_t> codes((size_t)nwords + 1, 0);
+    int esc = 0;
+    for (int w = 0; w < nwords; w++) codes[w] = atr::pack_word(read, len, w, fold_case, tb.iupac, &esc);
+    if (esc || n > ATR_K1A_MAXN) return 0;
+    unsigned sa_peq[16], tail_peq[16];
+    const int mp = a.sa_rows, sh32 = 32 - mp;
+    for (int c = 0; c < 16; c++) {
+        const unsigned low = (unsigned)(a.peq[c] & (mp >= 32 ? 0xFFFFFFFFull : ((1ull << mp) - 1)));
+        sa_peq[c] = low;
+        tail_peq[c] = (sh32 ? (low << sh32) | ((1u << sh32) - 1u) : low);
+    }
+    SaResult r1, r2;
+    memset(&r1, 0, sizeof r1); memset(&r2, 0, sizeof r2);
+    sa_filter(a, sa_peq, tail_peq, codes.data(), lo, n, r1);
+    qg_filter(a, tail_peq, codes.data(), (lo + n + 7) >> 3, lo, n, r2);
+    const SaResult* rs[2] = {&r1, &r2};
+    for (int t = 0; t < 2; t++) {
+        int* o = out + 6 * t;
+        o[0] = rs[t]->cls;
+        o[1] = rs[t]->cls == 1 || rs[t]->cls == 2 ? rs[t]->dlo : 0; o[2] = rs[t]->cls == 1 || rs[t]->cls == 2 ? rs[t]->width : 0;
+        o[3] = rs[t]->cls == 1 || rs[t]->cls == 2 ? rs[t]->c0 : 0; o[4] = rs[t]->cls == 1 || rs[t]->cls == 2 ? rs[t]->c1 : 0;
+        o[5] = rs[t]->cls == 3 ? rs[t]->v : 0;
+    }
+    unsigned st_final;
+    unsigned long long sa_pair[256];
+    for (int b = 0; b < 256; b++) sa_pair[b] = (unsigned long long)sa_peq[b & 15] | ((unsigned long long)sa_peq[b >> 4] << 32);
+    sa_scan(a, sa_peq, sa_pair, codes.data(), lo, n, out[12], out[13], st_final);
+    uint32_t acc[ATR_QG_GROUPS];
+    if (a.qg_step == 3) qg_scan<3>(a, a.qg_tab, codes.data(), (lo + n + 7) >> 3, lo, n, acc, 1, out[14], out[15]);
+    else qg_scan<2>(a, a.qg_tab, codes.data(), (lo + n + 7) >> 3, lo, n, acc, 1, out[14], out[15]);
+    out[16] = sa_need_tail(a, n, out[13], st_final);
+    out[17] = qg_need_tail(a, codes.data(), lo, n, out[15]);
+    out[18] = a.qg_step;
+    return 1;
+}
 
 // route: 0 = as the kernels would (K1f if eligible, else K1a, else K1g), 1 = force the general kernel (K1g),
 // 2 = force plain K1a (error if not possible), 3 = require K1f (error if not eligible). *used_k1a: 0 K1g, 1 K1a, 2 K1f
@@ -37,6 +95,8 @@ int sim_locate(const atr_adapter_desc* d, int adapter_index, int reduce, const u
     if (k1a) {
         AdapterK1a a;
         atr::fill_k1a(h, tb, adapter_index, reduce, rmp, a);
+        std::vector<unsigned char> qg_tab;
+        if (g_sim_qg && atr::build_qg(a, qg_tab)) a.qg_tab = qg_tab.data(); else a.qg_ok = 0;
         if (route == 3 && !a.fused_ok) return -101;
         if (used_k1a && a.fused_ok && route != 2) *used_k1a = 2;
         if (a.fused_ok && route != 2) {                // as the library does: the fused kernels whenever eligible

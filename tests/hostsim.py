@@ -33,6 +33,11 @@ def lib():
         L.sim_multi_locate.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int,
                                        C.POINTER(C.c_int)]
         L.sim_multi_locate.restype = C.c_int
+        L.sim_filter_compare.argtypes = [C.POINTER(_abi.AtrAdapterDesc), C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                         C.POINTER(C.c_int)]
+        L.sim_filter_compare.restype = C.c_int
+        L.sim_set_qg.argtypes = [C.c_int]
+        L.sim_set_qg.restype = None
         L.sim_compare_prefixes.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]
         L.sim_compare_prefixes.restype = C.c_int
         L.sim_trim_fastq.argtypes = [C.POINTER(_abi.AtrAdapterDesc), C.c_int, C.POINTER(_abi.AtrTrimOpts), C.c_char_p,
@@ -53,6 +58,17 @@ def lib():
         L.sim_merge_overlap.restype = C.c_int
         _lib = L
     return _lib
+
+
+def filter_compare(read, desc, lo=0, hi=None, fold_case=False):
+    """First funnel stage both ways (Shift-And automaton / q-gram sampling) for one read: None if the adapter has no
+    q-gram form, else (automaton SaResult 6-tuple, q-gram SaResult 6-tuple, (hmin, hmax) x 2, need_tail x 2, step)."""
+    rb = read if isinstance(read, bytes) else read.encode("latin-1")
+    out = (C.c_int * 24)()
+    if not lib().sim_filter_compare(C.byref(desc), rb, len(rb), lo, len(rb) if hi is None else hi, int(fold_case), out):
+        return None
+    o = list(out)
+    return tuple(o[0:6]), tuple(o[6:12]), (o[12], o[13]), (o[14], o[15]), o[16], o[17], o[18]
 
 
 def merge_overlap(seq1, seq2, insert_matched, min_overlap, error_rate):

@@ -338,3 +338,33 @@ def test_band_margins_fuzz(adapter, rate, min_overlap):
         assert got == exp, (adapter, rate, read, exp, got, path)
         banded += path in (3, 13)
     assert banded > 500
+
+
+@pytest.mark.parametrize("adapter,rate,min_overlap,step", [
+    (T1, 0.1, 3, 3), ("GATCGGAAGAGCACACGTCTGAACTCCA", 0.08, 1, 3), ("TGGAATTCTCGGGTGCCAAGG", 0.1, 3, 2), ("GTTCAGAGTTCTACAGTCCGACGATC", 0.1, 3, 3),
+    ("ACACTCTTTCCCTACACGACGCTCTTCCGATCT", 0.1, 3, 3), ("ACGTACGTACGTACGTACGTAAAAACGTACGTAC", 0.1, 3, 3),
+    ("A" * 34, 0.1, 3, 3), ("CTGTCTCTTATACACATCTCCGAGCCCACGAGAC", 0.06, 5, 3)])
+def test_qgram_filter_equals_shift_and(adapter, rate, min_overlap, step):
+    """the q-gram sampling form of the funnel's first stage finds exactly the automaton's piece hits: same hit range,
+    same class / band / window for every read, windows included; its need-tail gate fires at least where the
+    automaton's does"""
+    rng = np.random.default_rng(len(adapter) * 7 + step)
+    d, keep = _abi.make_adapter_desc(adapter, rate, 14, False, False, min_overlap, 1)
+    seen = {0: 0, 1: 0, 2: 0, 3: 0}
+    reads = list(fuzzgen.band_cases(5100 + len(adapter), adapter, 2500))
+    for _ in range(1500):
+        reads.append(fuzzgen.read_with_adapter(rng, adapter, int(rng.integers(0, 330)), n_rate=0.01))
+    for read in reads:
+        lo = hi = None
+        if rng.random() < 0.25 and len(read) > 4:
+            lo = int(rng.integers(0, len(read) // 2))
+            hi = int(rng.integers(lo, len(read) + 1))
+        res = hostsim.filter_compare(read, d, lo=lo or 0, hi=hi)
+        assert res is not None
+        sa, qg, sa_h, qg_h, sa_tail, qg_tail, st = res
+        assert st == step
+        assert sa_h == qg_h, (adapter, read, lo, hi, sa_h, qg_h)
+        assert qg_tail >= sa_tail, (adapter, read, lo, hi)
+        assert sa == qg, (adapter, read, lo, hi, sa, qg)
+        seen[sa[0]] += 1
+    assert seen[0] > 100 and seen[2] > 100 and (seen[3] > 20 or len(set(adapter)) < 4 or "ACGTACGT" in adapter), seen
