@@ -227,7 +227,7 @@ inline void fill_k1a(const HostAdapter& h, const AtrTables& tb, int index, int r
 // (device memory) or the simulator (host memory) can read it; the caller stores that pointer in a.qg_tab.
 // Returns false (and leaves a.qg_ok = 0) when the adapter does not qualify.
 inline bool build_qg(AdapterK1a& a, std::vector<unsigned char>& tab) {
-    a.qg_ok = 0; a.qg_tab = nullptr; a.qg_npat = 0; a.n_tail_cmp = 0;
+    a.qg_ok = 0; a.qg_tab = nullptr; a.qg_npat = 0; a.n_tail_cmp = 0; a.tail_cols = 0;
     if (!a.sa_ok || a.and_mode) return false;
     // pieces: runs of rows between sa_start bits and sa_end bits
     int pstart[8], plen[8], np = 0, lmin = 1 << 30, lmax = 0;
@@ -280,7 +280,13 @@ inline bool build_qg(AdapterK1a& a, std::vector<unsigned char>& tab) {
         a.qg_prow[t + 1] = (unsigned char)pstart[pats[t].piece];
         a.qg_plen[t + 1] = (unsigned char)plen[pats[t].piece];
         a.qg_poff[t + 1] = (unsigned char)pats[t].off;
+        for (int h = 0; h < 2; h++) { a.qg_pw[t + 1][h] = 0; a.qg_pm[t + 1][h] = 0; }
+        for (int r = 0; r < plen[pats[t].piece] && r < 16; r++) {
+            a.qg_pw[t + 1][r >> 3] |= ((unsigned)a.code[pstart[pats[t].piece] + r] & 15u) << (4 * (r & 7));
+            a.qg_pm[t + 1][r >> 3] |= 15u << (4 * (r & 7));
+        }
     }
+    if (lmax > 16) return false;
     a.qg_npat = (int)pats.size();
     a.qg_step = step; a.qg_mul = best_mul;
     // need-tail gate: one compare per tail_mask row (see fill_k1a). Rows whose prefix is longer than 8 bases are
@@ -291,6 +297,7 @@ inline bool build_qg(AdapterK1a& a, std::vector<unsigned char>& tab) {
             int p = 0;
             while (p + 1 < np && pstart[p + 1] < i) p++;              // piece containing row i (1-based): pstart[p] < i
             const int l = i - pstart[p];                               // rows pstart[p]+1 .. i
+            a.tail_cols = std::max(a.tail_cols, l);
             const int lc = l > 8 ? 8 : l;
             unsigned c = 0;                                            // rows i-lc+1 .. i in the top lc nibbles
             for (int t = 0; t < lc; t++) c |= ((unsigned)a.code[i - lc + t] & 15u) << (4 * (8 - lc + t));

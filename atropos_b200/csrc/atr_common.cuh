@@ -75,10 +75,13 @@ struct AdapterK1a {                   // passed by value as a __grid_constant__ 
     unsigned char qg_prow[16];        // per pattern: 0-based first row of its piece ...
     unsigned char qg_plen[16];        // ... the piece's length ...
     unsigned char qg_poff[16];        // ... and the offset of the 6-mer inside the piece
+    unsigned qg_pw[16][2], qg_pm[16][2];  // ... the piece itself packed like a read (up to 16 rows) and its nibble mask
     // need-tail gate without the automaton's final state: tail_mask bit i-1 (row i inside a begun piece p, l = i - first
     // row of p) <=> the read's last l bases equal the first l rows of p: (last8 ^ tail_c[t]) & tail_m[t] == 0
     int n_tail_cmp;
     unsigned tail_c[24], tail_m[24];
+    int tail_cols;                    // the same test as an automaton run over the read's last tail_cols columns (<= 16): rows of tail_mask never
+                                      // lie deeper than that inside their piece
 };
 #define ATR_QG_BITS 13
 #define ATR_QG_Q 6

@@ -559,35 +559,80 @@ __global__ void __launch_bounds__(ATR_K1F_THREADS) k_filter_sa(const __grid_cons
 
 // ---------------------------------------------------------------------------------------------
 // k_filter_qg: the first stage for adapters with a q-gram form (AdapterK1a.qg_ok; qgram_core.cuh) -- the headline
-// configuration. Same outputs as k_filter_sa (finished reads, narrow / 8-diagonal / wide / refine survivor lists), a
-// third of the instructions: every `step`-th read position costs one hashed byte-table lookup instead of every column an
-// automaton step.
-//   * persistent CTAs (grid = a few per SM) walk the tiles of 256 reads; the 8 KB lookup table and the Myers tables
-//     are built in shared memory once per CTA;
+// configuration. Same outputs as k_filter_sa (finished reads, narrow / 8-diagonal / wide / refine survivor lists) for a
+// fraction of the instructions: every `step`-th read position costs one hashed byte-table lookup instead of every
+// column an automaton step, and everything that only some reads need runs DENSE over a queue in shared memory instead
+// of divergently inside the scan (the first build verified hits inline: 3.4 of 32 lanes active, 37 % of the kernel's
+// instructions).
+//   * persistent CTAs (a few per SM) walk the tiles of 256 reads; the 8 KB lookup table and the Peq tables are built
+//     in shared memory once per CTA;
 //   * a tile's packed reads are one contiguous span of `codes`, fetched by one TMA bulk copy (cp.async.bulk +
 //     mbarrier) into the CTA's tile buffer; the other CTAs of the SM compute meanwhile;
-//   * phase A (all threads) scan + verification + verbatim-occurrence shortcut + need-tail gate; phase B the exact
-//     32-bit Myers over the read tail for the ~20 % of reads that can have a partial match there, compacted so that
-//     the warps running it are full; phase C classification, one 16-byte record store per finished read, warp-
-//     aggregated list appends.
+//   * A1 scan (every thread, uniform): q-gram hits go to the tile's verify queue as (read, position, pattern) items;
+//   * A2 verification, one thread per ITEM: compare the whole piece, atomicMin/Max the hit diagonal into the read's slot;
+//   * A3 per read: verbatim-occurrence shortcut, need-tail gate; reads that need the exact tail pass go to a queue that
+//     lives ACROSS tiles, all others are classified and stored / appended right away;
+//   * whenever 256 tail candidates have accumulated: the exact 32-bit Myers over the read tail with full warps
+//     (the reads come back from L2), then their classification.
 // ---------------------------------------------------------------------------------------------
 #define ATR_QG_THREADS 256
-#define ATR_QG_TILE_WORDS 6144       // 24 KB: 256 reads of up to 192 nt
+#define ATR_QG_TILE_WORDS 5120       // 20 KB: 256 reads of up to 160 nt (longer reads: the tile is read from global memory)
 #define ATR_QG_PAD 8                 // a group of lookups reads up to 3 words past the read's last word
+#define ATR_QG_VQ_CAP 1536           // verify items per tile (~2 per read expected; overflow: that tile verifies inline)
+#define ATR_QG_NONE_LO 0x7fffffff
+
+struct QgTailItem { uint32_t read; short hmin, hmax; };
+
+// classification + record store / list appends of one read. Called by EVERY thread of the CTA (warp ballots inside);
+// `active`: this thread holds a read. im = (imin << 16) | imax of the tail pass, 0 if it did not run.
+__device__ __forceinline__ void qg_finish(const AdapterK1a& ad, bool active, uint32_t read, int lo, int n, int hmin, int hmax,
+                                          bool exact, int im, atr_match* __restrict__ out, Survivor* __restrict__ narrow,
+                                          Survivor* __restrict__ wide, Survivor* __restrict__ refine, int* __restrict__ counters) {
+    bool to_narrow = false, to_wide = false, to_refine = false, narrow8 = false, finished = false;
+    Survivor sv;
+    sv.read = read; sv.a = 0; sv.b = 0;
+    Best b;
+    b.ref_stop = ad.m; b.q_stop = n; b.cost = ad.m + n; b.origin = 0; b.matches = 0;           // "no match"
+    if (active) {
+        if (exact) {                                                    // verbatim occurrence: the str.find shortcut
+            b.matches = ad.m; b.cost = 0; b.origin = hmin; b.q_stop = hmin + ad.m;
+            finished = true;
+        } else {
+            SaResult sr;
+            sa_classify(ad, lo, n, hmin, hmax, im >> 16, im & 0xFFFF, sr);
+            if (sr.cls == 0) finished = true;
+            else if (sr.cls == 1) {
+                if (ad.band_ok && sr.width <= ATR_K1D_W) { to_narrow = true; sv.a = (short)sr.dlo; narrow8 = ad.split8 && sr.width <= 8; }
+                else { to_wide = true; sv.a = (short)sr.c0; sv.b = (short)sr.c1; }
+            } else if (ad.band_ok && sr.width <= ATR_K1D_W) {
+                to_narrow = true; sv.a = (short)sr.dlo;                 // band known from the hits: no exact pass needed
+                narrow8 = ad.split8 && sr.width <= 8;
+            } else {
+                to_refine = true; sv.a = (short)sr.c0; sv.b = (short)sr.c1;
+            }
+        }
+    }
+    if (finished) finalize(ad, b, n, out + read);
+    list_append(to_narrow && !narrow8, sv, narrow, counters + 0);
+    list_append_back(narrow8, sv, wide, counters + 3);                 // `wide` starts where the narrow list's storage ends
+    list_append(to_wide, sv, wide, counters + 1);
+    list_append(to_refine, sv, refine, counters + 2);
+}
 
 template <int S>
-__global__ void __launch_bounds__(ATR_QG_THREADS, 4) k_filter_qg(const __grid_constant__ AdapterK1a ad,
+__global__ void __launch_bounds__(ATR_QG_THREADS, 5) k_filter_qg(const __grid_constant__ AdapterK1a ad,
         const uint32_t* __restrict__ codes, const uint32_t* __restrict__ woff, const uint16_t* __restrict__ len,
         const uint16_t* __restrict__ win, int64_t n_reads, atr_match* __restrict__ out,
         Survivor* __restrict__ narrow, Survivor* __restrict__ wide, Survivor* __restrict__ refine, int* __restrict__ counters) {
     __shared__ __align__(128) uint32_t s_tile[ATR_QG_TILE_WORDS + ATR_QG_PAD];
     __shared__ __align__(16) unsigned char s_qtab[1 << ATR_QG_BITS];
     __shared__ __align__(8) uint64_t s_bar;
-    __shared__ uint32_t s_acc[ATR_QG_GROUPS * ATR_QG_THREADS];
-    __shared__ unsigned s_tail_peq[16];
-    __shared__ int s_im[ATR_QG_THREADS];
-    __shared__ unsigned short s_tail_list[ATR_QG_THREADS];
-    __shared__ int s_tail_count;
+    __shared__ uint32_t s_vq[ATR_QG_VQ_CAP];                 // verify items: id [0,4) | position [4,17) | thread [17,25)
+    __shared__ QgTailItem s_tq[2 * ATR_QG_THREADS];
+    __shared__ uint2 s_meta[ATR_QG_THREADS];                 // x: first word of the read relative to the tile, y: lo | n << 16
+    __shared__ int s_hmin[ATR_QG_THREADS], s_hmax[ATR_QG_THREADS];
+    __shared__ unsigned s_sa_peq[16], s_tail_peq[16];
+    __shared__ int s_vq_count, s_tq_count;
 
     const int tid = threadIdx.x;
     // ---- once per CTA: tables, zeroed tile buffer, barrier ----
@@ -600,9 +645,11 @@ __global__ void __launch_bounds__(ATR_QG_THREADS, 4) k_filter_qg(const __grid_co
     if (tid < 16) {
         const int mp = ad.sa_rows, sh32 = 32 - mp;
         const unsigned low = (unsigned)(ad.peq[tid] & (mp >= 32 ? 0xFFFFFFFFull : ((1ull << mp) - 1)));
+        s_sa_peq[tid] = low;
         s_tail_peq[tid] = sh32 ? ((low << sh32) | ((1u << sh32) - 1u)) : low;
     }
     if (tid == 0) {
+        s_tq_count = 0;
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar)) : "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -620,7 +667,7 @@ __global__ void __launch_bounds__(ATR_QG_THREADS, 4) k_filter_qg(const __grid_co
         const bool use_tma = fits && !last_tile && span > 0 && aligned;
         __syncthreads();                       // everybody is done with the previous tile (and with the set-up above)
         if (tid == 0) {
-            s_tail_count = 0;
+            s_vq_count = 0;
             if (use_tma) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads of the tile before the async write
                 tma_load_1d(s_tile, codes + a_begin, span * 4u, &s_bar);
@@ -632,12 +679,10 @@ __global__ void __launch_bounds__(ATR_QG_THREADS, 4) k_filter_qg(const __grid_co
         const int64_t r = t0 + tid;
         const bool mine = tid < cnt;
         bool routed = false, esc = false;
-        int lo = 0, n = 0;
+        int lo = 0, n = 0, nw = 0;
         uint32_t wr = a_begin;
-        int nw = 0;
         if (mine) {
-            const unsigned l = len[r];
-            nw = (int)(((l & ATR_LEN_MASK) + 7u) >> 3);
+            nw = (int)(((len[r] & ATR_LEN_MASK) + 7u) >> 3);
             read_extent(len, win, r, lo, n, esc);
             wr = woff[r];
             routed = esc || n > ATR_K1A_MAXN;                          // ASCII compare mode: escaped reads take k_locate_gen
@@ -648,64 +693,103 @@ __global__ void __launch_bounds__(ATR_QG_THREADS, 4) k_filter_qg(const __grid_co
                 store_match(out + r, m);
             }
         }
-        __syncthreads();                       // s_tail_count = 0 and the cooperative copy are visible
+        s_meta[tid] = make_uint2(wr - a_begin, (unsigned)lo | ((unsigned)n << 16));
+        s_hmin[tid] = 0x7fffffff; s_hmax[tid] = -0x7fffffff;
+        __syncthreads();                       // counters, slots and the cooperative copy are visible
         if (use_tma) { mbar_wait(&s_bar, parity); parity ^= 1u; }
         const uint32_t* rd = codes + wr;       // generic pointer: shared tile or global
         int wlimit = nw;
         if (fits) { rd = s_tile + (wr - a_begin); wlimit = (int)(ATR_QG_TILE_WORDS + ATR_QG_PAD - (wr - a_begin)); }
-        // ---- phase A (every thread) ----
-        int hmin = 0x7fffffff, hmax = -0x7fffffff;
-        bool exact = false, need_tail = false;
+        // ---- A1 (every thread): sampled lookups; hits -> verify queue ----
         if (mine && !routed) {
-            qg_scan<S>(ad, s_qtab, rd, wlimit, lo, n, s_acc + tid, ATR_QG_THREADS, hmin, hmax);
-            exact = sa_exact(ad, rd, lo, n, hmin, hmax);
-            if (!exact) need_tail = qg_need_tail(ad, rd, lo, n, hmax);
-        }
-        // ---- phase B: exact tail Myers, compacted ----
-        s_im[tid] = 0;
-        if (need_tail) s_tail_list[atomicAdd(&s_tail_count, 1)] = (unsigned short)tid;
-        __syncthreads();
-        for (int e = tid; e < s_tail_count; e += ATR_QG_THREADS) {
-            const int t2 = s_tail_list[e];
-            int lo2, n2; bool esc2;
-            read_extent(len, win, t0 + t2, lo2, n2, esc2);
-            const uint32_t wr2 = woff[t0 + t2];
-            const uint32_t* rd2 = codes + wr2;
-            if (fits) rd2 = s_tile + (wr2 - a_begin);
-            s_im[t2] = sa_tail_packed(&ad, s_tail_peq, rd2, lo2, n2);
-        }
-        __syncthreads();
-        // ---- phase C (every thread): classify, store, append ----
-        bool to_narrow = false, to_wide = false, to_refine = false, narrow8 = false, finished = false;
-        Survivor sv;
-        sv.read = (uint32_t)r; sv.a = 0; sv.b = 0;
-        Best b;
-        b.ref_stop = ad.m; b.q_stop = n; b.cost = ad.m + n; b.origin = 0; b.matches = 0;       // "no match"
-        if (mine && !routed) {
-            if (exact) {                                                // verbatim occurrence: the str.find shortcut
-                b.matches = ad.m; b.cost = 0; b.origin = hmin; b.q_stop = hmin + ad.m;
-                finished = true;
-            } else {
-                const int im = s_im[tid];
-                SaResult sr;
-                sa_classify(ad, lo, n, hmin, hmax, im >> 16, im & 0xFFFF, sr);
-                if (sr.cls == 0) finished = true;
-                else if (sr.cls == 1) {
-                    if (ad.band_ok && sr.width <= ATR_K1D_W) { to_narrow = true; sv.a = (short)sr.dlo; narrow8 = ad.split8 && sr.width <= 8; }
-                    else { to_wide = true; sv.a = (short)sr.c0; sv.b = (short)sr.c1; }
-                } else if (ad.band_ok && sr.width <= ATR_K1D_W) {
-                    to_narrow = true; sv.a = (short)sr.dlo;
-                    narrow8 = ad.split8 && sr.width <= 8;
-                } else {
-                    to_refine = true; sv.a = (short)sr.c0; sv.b = (short)sr.c1;
+            int g0, g1;
+            qg_group_range<S>(lo, n, g0, g1);
+            for (int g = g0; g < g1; g++) {
+                uint32_t acc = qg_group<S>(s_qtab, ad.qg_mul, rd, g, wlimit);
+                while (acc) {
+                    const int i = atr_ctz(acc) >> 2;
+                    const unsigned id = (acc >> (4 * i)) & 15u;
+                    acc &= ~(15u << (4 * i));
+                    const unsigned c = (unsigned)((S == 3 ? 24 : 16) * g + S * i);
+                    const int slot = atomicAdd(&s_vq_count, 1);
+                    if (slot < ATR_QG_VQ_CAP) s_vq[slot] = id | (c << 4) | ((unsigned)tid << 17);
                 }
             }
         }
-        if (finished) finalize(ad, b, n, out + r);
-        list_append(to_narrow && !narrow8, sv, narrow, counters + 0);
-        list_append_back(narrow8, sv, wide, counters + 3);
-        list_append(to_wide, sv, wide, counters + 1);
-        list_append(to_refine, sv, refine, counters + 2);
+        __syncthreads();
+        // ---- A2 (one thread per item): the whole piece at the position the 6-mer implies? ----
+        const int n_items = s_vq_count;
+        if (n_items <= ATR_QG_VQ_CAP) {
+            for (int e = tid; e < n_items; e += ATR_QG_THREADS) {
+                const uint32_t it = s_vq[e];
+                const int id = (int)(it & 15u), c = (int)((it >> 4) & 0x1FFFu), t = (int)(it >> 17);
+                const uint2 mt = s_meta[t];
+                const uint32_t* rdt = fits ? s_tile + mt.x : codes + (a_begin + mt.x);
+                const int lo_t = (int)(mt.y & 0xFFFFu), n_t = (int)(mt.y >> 16);
+                if (id == 15) {
+                    for (int p = 1; p <= ad.qg_npat; p++) {
+                        const int v = qg_hit_diagonal(ad, rdt, lo_t, n_t, p, c);
+                        if (v != ATR_QG_NOHIT) { atomicMin(&s_hmin[t], v); atomicMax(&s_hmax[t], v); }
+                    }
+                } else {
+                    const int v = qg_hit_diagonal(ad, rdt, lo_t, n_t, id, c);
+                    if (v != ATR_QG_NOHIT) { atomicMin(&s_hmin[t], v); atomicMax(&s_hmax[t], v); }
+                }
+            }
+        }
+        __syncthreads();
+        // ---- A3 (every thread): shortcut, need-tail gate, finish or queue ----
+        int hmin = s_hmin[tid], hmax = s_hmax[tid];
+        bool exact = false, need_tail = false;
+        const bool live = mine && !routed;
+        if (live) {
+            if (n_items > ATR_QG_VQ_CAP) {                              // queue overflow (low-complexity reads): verify inline
+                uint32_t acc1[ATR_QG_GROUPS];
+                qg_scan<S>(ad, s_qtab, rd, wlimit, lo, n, acc1, 1, hmin, hmax);
+            }
+            exact = sa_exact(ad, rd, lo, n, hmin, hmax);
+            if (!exact) need_tail = qg_need_tail(ad, s_sa_peq, rd, lo, n, hmax);
+            if (need_tail) {
+                QgTailItem q;
+                q.read = (uint32_t)r;
+                q.hmin = (short)(hmax == -0x7fffffff ? 32767 : hmin);
+                q.hmax = (short)(hmax == -0x7fffffff ? -32768 : hmax);
+                s_tq[atomicAdd(&s_tq_count, 1)] = q;
+            }
+        }
+        qg_finish(ad, live && !need_tail, (uint32_t)r, lo, n, hmin, hmax, exact, 0, out, narrow, wide, refine, counters);
+        __syncthreads();
+        // ---- B: 256 tail candidates accumulated -> exact tail Myers + classification, full warps ----
+        const int n_tail = s_tq_count;
+        if (n_tail >= ATR_QG_THREADS) {
+            const QgTailItem q = s_tq[n_tail - ATR_QG_THREADS + tid];
+            int lo2, n2; bool esc2;
+            read_extent(len, win, q.read, lo2, n2, esc2);
+            const int im = sa_tail_packed(&ad, s_tail_peq, codes + woff[q.read], lo2, n2);
+            const bool nohit = q.hmax == -32768;
+            qg_finish(ad, true, q.read, lo2, n2, nohit ? 0x7fffffff : (int)q.hmin, nohit ? -0x7fffffff : (int)q.hmax, false, im,
+                      out, narrow, wide, refine, counters);
+            __syncthreads();
+            if (tid == 0) s_tq_count = n_tail - ATR_QG_THREADS;
+        }
+    }
+    // ---- the tail candidates left over ----
+    __syncthreads();
+    {
+        const int n_tail = s_tq_count;
+        const bool active = tid < n_tail;
+        QgTailItem q;
+        q.read = 0; q.hmin = 32767; q.hmax = -32768;
+        int lo2 = 0, n2 = 0, im = 0;
+        if (active) {
+            q = s_tq[tid];
+            bool esc2;
+            read_extent(len, win, q.read, lo2, n2, esc2);
+            im = sa_tail_packed(&ad, s_tail_peq, codes + woff[q.read], lo2, n2);
+        }
+        const bool nohit = q.hmax == -32768;
+        qg_finish(ad, active, q.read, lo2, n2, nohit ? 0x7fffffff : (int)q.hmin, nohit ? -0x7fffffff : (int)q.hmax, false, im,
+                  out, narrow, wide, refine, counters);
     }
 }
 

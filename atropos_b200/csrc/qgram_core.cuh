@@ -46,15 +46,37 @@ ATR_HD uint32_t qg_group(const unsigned char* __restrict__ tab, unsigned mul, co
     return acc;
 }
 
-// a hit of pattern `id` at sampled absolute position c of the packed read: is the whole piece there, inside the window?
-ATR_HD void qg_verify_pattern(const AdapterK1a& ad, const uint32_t* __restrict__ codes, int lo, int n, int id, int c,
-                              int& hmin, int& hmax) {
+// is the piece of pattern `id` at absolute position a of the packed read? (a + piece length <= end of the read;
+// only the words that hold needed bases are loaded)
+ATR_HD bool qg_piece_at(const AdapterK1a& ad, const uint32_t* __restrict__ codes, int a, int id) {
+    const int plen = ad.qg_plen[id];
+    const int wi = a >> 3, sh = a & 7;
+    const uint32_t w0 = codes[wi];
+    const uint32_t w1 = (sh + atr_min(plen, 8) > 8) ? codes[wi + 1] : 0u;
+    uint32_t bad = (funnel_r32(w0, w1, (unsigned)sh * 4u) ^ ad.qg_pw[id][0]) & ad.qg_pm[id][0];
+    if (plen > 8) {
+        const uint32_t v1 = codes[wi + 1];
+        const uint32_t v2 = (sh + plen > 16) ? codes[wi + 2] : 0u;
+        bad |= (funnel_r32(v1, v2, (unsigned)sh * 4u) ^ ad.qg_pw[id][1]) & ad.qg_pm[id][1];
+    }
+    return bad == 0u;
+}
+
+// a hit of pattern `id` at sampled absolute position c of the packed read: is the whole piece there, inside the
+// window? -> its diagonal v = (column of the piece end) - (row of the piece end), else ATR_QG_NOHIT
+#define ATR_QG_NOHIT 0x7fffffff
+ATR_HD int qg_hit_diagonal(const AdapterK1a& ad, const uint32_t* __restrict__ codes, int lo, int n, int id, int c) {
     const int prow = ad.qg_prow[id], plen = ad.qg_plen[id];
     const int a = c - (int)ad.qg_poff[id];               // absolute position of the piece's first base
-    if (a < lo || a + plen > lo + n) return;
-    if (!anchor_piece_equal(ad, codes, a, prow, plen)) return;
-    const int v = (a - lo) - prow;                       // diagonal: (column of the piece end) - (row of the piece end)
-    hmin = atr_min(hmin, v); hmax = atr_max(hmax, v);
+    if (a < lo || a + plen > lo + n) return ATR_QG_NOHIT;
+    if (!qg_piece_at(ad, codes, a, id)) return ATR_QG_NOHIT;
+    return (a - lo) - prow;
+}
+
+ATR_HD void qg_verify_pattern(const AdapterK1a& ad, const uint32_t* __restrict__ codes, int lo, int n, int id, int c,
+                              int& hmin, int& hmax) {
+    const int v = qg_hit_diagonal(ad, codes, lo, n, id, c);
+    if (v != ATR_QG_NOHIT) { hmin = atr_min(hmin, v); hmax = atr_max(hmax, v); }
 }
 
 template <int S>
@@ -101,19 +123,33 @@ ATR_HD void qg_scan(const AdapterK1a& ad, const unsigned char* __restrict__ tab,
     }
 }
 
-// (c) the need-tail gate of sa_need_tail without the automaton's final state
-ATR_HD bool qg_need_tail(const AdapterK1a& ad, const uint32_t* __restrict__ codes, int lo, int n, int hmax) {
+// (c) the need-tail gate of sa_need_tail without the automaton's state after the whole read: a tail_mask bit
+// (row i, l rows deep in its piece) only depends on the read's last l <= tail_cols columns, so the automaton is run over
+// the last 8 (or 16) columns only. sa_peq: the 16-entry Peq table of the first sa_rows rows (as for sa_scan).
+ATR_HD bool qg_need_tail(const AdapterK1a& ad, const unsigned* __restrict__ sa_peq, const uint32_t* __restrict__ codes,
+                         int lo, int n, int hmax) {
     const bool stop_in_ref = ad.flags & ATR_STOP_WITHIN_SEQ1;
     if (!(stop_in_ref || ad.m <= ad.sa_rows)) return false;
-    if (!ad.tail_gate_ok || ad.n_tail_cmp < 0 || n < 8) return true;
+    if (!ad.tail_gate_ok || ad.tail_cols > 16) return true;
     if (hmax != -0x7fffffff && hmax >= n - ad.sa_rows - ad.k) return true;
-    const int q = lo + n - 8;                              // the read's last 8 bases: nibble j = position n - 8 + j
+    const int cols = ad.tail_cols > 8 ? 16 : 8;
+    if (lo + n < cols) return true;                        // shorter than the look-back: let the exact pass decide
+    const int q = lo + n - cols;                           // columns before the window start only add chains: a superset
+    const unsigned sh = (unsigned)(q & 7) * 4u;
     const uint32_t w0 = codes[q >> 3];
-    const uint32_t w1 = (q & 7) ? codes[(q >> 3) + 1] : 0u;
-    const uint32_t tw = funnel_r32(w0, w1, (unsigned)(q & 7) * 4u);
-    bool need = false;
-    for (int t = 0; t < ad.n_tail_cmp; t++) need = need || ((tw ^ ad.tail_c[t]) & ad.tail_m[t]) == 0u;
-    return need;
+    const uint32_t w1 = (q & 7) || cols == 16 ? codes[(q >> 3) + 1] : 0u;
+    const unsigned S0 = ad.sa_start;
+    unsigned St = 0;
+    uint32_t tw = funnel_r32(w0, w1, sh);
+#pragma unroll
+    for (int t = 0; t < 8; t++) St = ((St << 1) | S0) & sa_peq[(tw >> (4 * t)) & 15u];
+    if (cols == 16) {
+        const uint32_t w2 = (q & 7) ? codes[(q >> 3) + 2] : 0u;
+        tw = funnel_r32(w1, w2, sh);
+#pragma unroll
+        for (int t = 0; t < 8; t++) St = ((St << 1) | S0) & sa_peq[(tw >> (4 * t)) & 15u];
+    }
+    return (St & ad.tail_mask) != 0u;
 }
 
 // the whole stage for one read (host simulator; the kernel interleaves a block-level compaction before the tail pass)
@@ -122,9 +158,11 @@ ATR_HD void qg_filter_s(const AdapterK1a& ad, const unsigned* __restrict__ tail_
                         int lo, int n, SaResult& res) {
     int hmin, hmax, imin = 0, imax = 0;
     uint32_t acc[ATR_QG_GROUPS];
+    unsigned sa_peq[16];
+    for (int c = 0; c < 16; c++) sa_peq[c] = (unsigned)(ad.peq[c] & (ad.sa_rows >= 32 ? 0xFFFFFFFFull : ((1ull << ad.sa_rows) - 1)));
     qg_scan<S>(ad, ad.qg_tab, codes, wlimit, lo, n, acc, 1, hmin, hmax);
     if (sa_exact(ad, codes, lo, n, hmin, hmax)) { res.cls = 3; res.v = hmin; return; }
-    if (qg_need_tail(ad, codes, lo, n, hmax)) sa_tail(ad, tail_peq, codes, lo, n, imin, imax);
+    if (qg_need_tail(ad, sa_peq, codes, lo, n, hmax)) sa_tail(ad, tail_peq, codes, lo, n, imin, imax);
     sa_classify(ad, lo, n, hmin, hmax, imin, imax, res);
 }
 

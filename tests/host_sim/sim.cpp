@@ -65,7 +65,7 @@ int sim_filter_compare(const atr_adapter_desc* d, const unsigned char* read, int
     if (a.qg_step == 3) qg_scan<3>(a, a.qg_tab, codes.data(), (lo + n + 7) >> 3, lo, n, acc, 1, out[14], out[15]);
     else qg_scan<2>(a, a.qg_tab, codes.data(), (lo + n + 7) >> 3, lo, n, acc, 1, out[14], out[15]);
     out[16] = sa_need_tail(a, n, out[13], st_final);
-    out[17] = qg_need_tail(a, codes.data(), lo, n, out[15]);
+    out[17] = qg_need_tail(a, sa_peq, codes.data(), lo, n, out[15]);
     out[18] = a.qg_step;
     return 1;
 }
