@@ -9,7 +9,8 @@ import os
 from . import _abi
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "libatropos_b200.so")
+# ATROPOS_B200_LIB: another build of the same library (developer A/B measurements of kernel variants); still the CUDA library
+LIB_PATH = os.environ.get("ATROPOS_B200_LIB") or os.path.join(PKG, "libatropos_b200.so")
 
 _lib = None
 

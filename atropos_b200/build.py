@@ -33,6 +33,15 @@ def up_to_date():
     return os.path.exists(LIB) and os.path.getmtime(LIB) >= max(os.path.getmtime(p) for p in deps())
 
 
+def build_variant(out, defines, verbose=False):
+    """A second build with -D overrides (kernel-variant A/B runs: ATROPOS_B200_LIB=<out> selects it)."""
+    cmd = [NVCC] + FLAGS + ["-D" + d for d in defines] + ["-I", os.path.join(ROOT, "include"), "-o", out] + sources()
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.check_call(cmd)
+    return out
+
+
 def build(force=False, verbose=False):
     if not force and up_to_date():
         return LIB

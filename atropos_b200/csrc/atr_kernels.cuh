@@ -568,17 +568,21 @@ __global__ void __launch_bounds__(ATR_K1F_THREADS) k_filter_sa(const __grid_cons
 //     in shared memory once per CTA;
 //   * a tile's packed reads are one contiguous span of `codes`, fetched by one TMA bulk copy (cp.async.bulk +
 //     mbarrier) into the CTA's tile buffer; the other CTAs of the SM compute meanwhile;
-//   * A1 scan (every thread, uniform): q-gram hits go to the tile's verify queue as (read, position, pattern) items;
-//   * A2 verification, one thread per ITEM: compare the whole piece, atomicMin/Max the hit diagonal into the read's slot;
+//   * A1 scan (every thread, uniform, no branches): the 8 lookups of a group of 24 (16) columns leave one word of
+//     pattern indices in shared memory;
+//   * A2 verification, one thread per read WITH hits (a compacted list, about half of the tile): compare the whole
+//     piece of every hit, then the verbatim-occurrence shortcut where all hits lie on one diagonal;
 //   * A3 per read: verbatim-occurrence shortcut, need-tail gate; reads that need the exact tail pass go to a queue that
 //     lives ACROSS tiles, all others are classified and stored / appended right away;
 //   * whenever 256 tail candidates have accumulated: the exact 32-bit Myers over the read tail with full warps
 //     (the reads come back from L2), then their classification.
 // ---------------------------------------------------------------------------------------------
+#ifndef ATR_QG_THREADS
 #define ATR_QG_THREADS 256
-#define ATR_QG_TILE_WORDS 5120       // 20 KB: 256 reads of up to 160 nt (longer reads: the tile is read from global memory)
+#define ATR_QG_TILE_WORDS 4992       // 19.5 KB: 256 reads of up to 156 nt; 5 CTAs fit an SM
+#define ATR_QG_MINCTAS 5
+#endif                               // (longer reads: the tile is read from global memory)
 #define ATR_QG_PAD 8                 // a group of lookups reads up to 3 words past the read's last word
-#define ATR_QG_VQ_CAP 1536           // verify items per tile (~2 per read expected; overflow: that tile verifies inline)
 #define ATR_QG_NONE_LO 0x7fffffff
 
 struct QgTailItem { uint32_t read; short hmin, hmax; };
@@ -620,19 +624,20 @@ __device__ __forceinline__ void qg_finish(const AdapterK1a& ad, bool active, uin
 }
 
 template <int S>
-__global__ void __launch_bounds__(ATR_QG_THREADS, 5) k_filter_qg(const __grid_constant__ AdapterK1a ad,
+__global__ void __launch_bounds__(ATR_QG_THREADS, ATR_QG_MINCTAS) k_filter_qg(const __grid_constant__ AdapterK1a ad,
         const uint32_t* __restrict__ codes, const uint32_t* __restrict__ woff, const uint16_t* __restrict__ len,
         const uint16_t* __restrict__ win, int64_t n_reads, atr_match* __restrict__ out,
         Survivor* __restrict__ narrow, Survivor* __restrict__ wide, Survivor* __restrict__ refine, int* __restrict__ counters) {
     __shared__ __align__(128) uint32_t s_tile[ATR_QG_TILE_WORDS + ATR_QG_PAD];
     __shared__ __align__(16) unsigned char s_qtab[1 << ATR_QG_BITS];
     __shared__ __align__(8) uint64_t s_bar;
-    __shared__ uint32_t s_vq[ATR_QG_VQ_CAP];                 // verify items: id [0,4) | position [4,17) | thread [17,25)
+    __shared__ uint32_t s_acc[ATR_QG_GROUPS * ATR_QG_THREADS];   // [group of the chunk][thread]: the group's 8 lookups, 4 bits each
     __shared__ QgTailItem s_tq[2 * ATR_QG_THREADS];
     __shared__ uint2 s_meta[ATR_QG_THREADS];                 // x: first word of the read relative to the tile, y: lo | n << 16
     __shared__ int s_hmin[ATR_QG_THREADS], s_hmax[ATR_QG_THREADS];
     __shared__ unsigned s_sa_peq[16], s_tail_peq[16];
-    __shared__ int s_vq_count, s_tq_count;
+    __shared__ unsigned char s_hl[ATR_QG_THREADS], s_flag[ATR_QG_THREADS];   // reads of the tile with hits; bit 0 shortcut checked, bit 1 verbatim
+    __shared__ int s_tq_count, s_hl_count;
 
     const int tid = threadIdx.x;
     // ---- once per CTA: tables, zeroed tile buffer, barrier ----
@@ -649,7 +654,7 @@ __global__ void __launch_bounds__(ATR_QG_THREADS, 5) k_filter_qg(const __grid_co
         s_tail_peq[tid] = sh32 ? ((low << sh32) | ((1u << sh32) - 1u)) : low;
     }
     if (tid == 0) {
-        s_tq_count = 0;
+        s_tq_count = 0; s_hl_count = 0;
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar)) : "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -667,7 +672,6 @@ __global__ void __launch_bounds__(ATR_QG_THREADS, 5) k_filter_qg(const __grid_co
         const bool use_tma = fits && !last_tile && span > 0 && aligned;
         __syncthreads();                       // everybody is done with the previous tile (and with the set-up above)
         if (tid == 0) {
-            s_vq_count = 0;
             if (use_tma) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads of the tile before the async write
                 tma_load_1d(s_tile, codes + a_begin, span * 4u, &s_bar);
@@ -694,60 +698,81 @@ __global__ void __launch_bounds__(ATR_QG_THREADS, 5) k_filter_qg(const __grid_co
             }
         }
         s_meta[tid] = make_uint2(wr - a_begin, (unsigned)lo | ((unsigned)n << 16));
-        s_hmin[tid] = 0x7fffffff; s_hmax[tid] = -0x7fffffff;
+        s_hmin[tid] = 0x7fffffff; s_hmax[tid] = -0x7fffffff; s_flag[tid] = 0;
         __syncthreads();                       // counters, slots and the cooperative copy are visible
         if (use_tma) { mbar_wait(&s_bar, parity); parity ^= 1u; }
         const uint32_t* rd = codes + wr;       // generic pointer: shared tile or global
         int wlimit = nw;
         if (fits) { rd = s_tile + (wr - a_begin); wlimit = (int)(ATR_QG_TILE_WORDS + ATR_QG_PAD - (wr - a_begin)); }
-        // ---- A1 (every thread): sampled lookups; hits -> verify queue ----
-        if (mine && !routed) {
-            int g0, g1;
-            qg_group_range<S>(lo, n, g0, g1);
-            for (int g = g0; g < g1; g++) {
-                uint32_t acc = qg_group<S>(s_qtab, ad.qg_mul, rd, g, wlimit);
-                while (acc) {
-                    const int i = atr_ctz(acc) >> 2;
-                    const unsigned id = (acc >> (4 * i)) & 15u;
-                    acc &= ~(15u << (4 * i));
-                    const unsigned c = (unsigned)((S == 3 ? 24 : 16) * g + S * i);
-                    const int slot = atomicAdd(&s_vq_count, 1);
-                    if (slot < ATR_QG_VQ_CAP) s_vq[slot] = id | (c << 4) | ((unsigned)tid << 17);
+        // ---- A1 / A2 in chunks of 8 groups (192 or 128 columns; one chunk for reads up to that length) ----
+        {
+            int g0 = 0, g1 = 0;
+            if (mine && !routed) qg_group_range<S>(lo, n, g0, g1);
+            int gb = 0;
+            bool more;
+            do {
+                // A1 (every thread, uniform): 8 lookups per group, the group's hits as one word of pattern indices
+                uint32_t any = 0;
+#pragma unroll 1
+                for (int j = 0; j < ATR_QG_GROUPS; j++) {
+                    const int g = gb + j;
+                    uint32_t acc = 0;
+                    if (g >= g0 && g < g1) acc = qg_group<S>(s_qtab, ad.qg_mul, rd, g, wlimit);
+                    s_acc[j * ATR_QG_THREADS + tid] = acc;
+                    any |= acc;
                 }
-            }
-        }
-        __syncthreads();
-        // ---- A2 (one thread per item): the whole piece at the position the 6-mer implies? ----
-        const int n_items = s_vq_count;
-        if (n_items <= ATR_QG_VQ_CAP) {
-            for (int e = tid; e < n_items; e += ATR_QG_THREADS) {
-                const uint32_t it = s_vq[e];
-                const int id = (int)(it & 15u), c = (int)((it >> 4) & 0x1FFFu), t = (int)(it >> 17);
-                const uint2 mt = s_meta[t];
-                const uint32_t* rdt = fits ? s_tile + mt.x : codes + (a_begin + mt.x);
-                const int lo_t = (int)(mt.y & 0xFFFFu), n_t = (int)(mt.y >> 16);
-                if (id == 15) {
-                    for (int p = 1; p <= ad.qg_npat; p++) {
-                        const int v = qg_hit_diagonal(ad, rdt, lo_t, n_t, p, c);
-                        if (v != ATR_QG_NOHIT) { atomicMin(&s_hmin[t], v); atomicMax(&s_hmax[t], v); }
+                {                                                       // reads with hits -> the chunk's list (one atomic per warp)
+                    const unsigned m = __ballot_sync(0xffffffffu, any != 0u);
+                    if (m) {
+                        const int lane = tid & 31, leader = __ffs(m) - 1;
+                        int base = 0;
+                        if (lane == leader) base = atomicAdd(&s_hl_count, __popc(m));
+                        base = __shfl_sync(0xffffffffu, base, leader);
+                        if (any) s_hl[base + __popc(m & ((1u << lane) - 1u))] = (unsigned char)tid;
                     }
-                } else {
-                    const int v = qg_hit_diagonal(ad, rdt, lo_t, n_t, id, c);
-                    if (v != ATR_QG_NOHIT) { atomicMin(&s_hmin[t], v); atomicMax(&s_hmax[t], v); }
                 }
-            }
+                __syncthreads();
+                // A2: one thread per read WITH hits (about half of the tile, dense): verify every hit of the chunk; if the read
+                // is done (single chunk) and its hits lie on one diagonal, the verbatim-occurrence check as well
+                const int n_hl = s_hl_count;
+                for (int e = tid; e < n_hl; e += ATR_QG_THREADS) {
+                    const int t = s_hl[e];
+                    const uint2 mt = s_meta[t];
+                    const uint32_t* rdt = fits ? s_tile + mt.x : codes + (a_begin + mt.x);
+                    const int lo_t = (int)(mt.y & 0xFFFFu), n_t = (int)(mt.y >> 16);
+                    int vmin = s_hmin[t], vmax = s_hmax[t];
+                    // one flat loop over the read's hits: every trip of the warp verifies one hit in every lane that
+                    // still has one (a loop per group ran at 6 of 32 lanes: the lanes' hits sit in different groups)
+                    int j = -1;
+                    uint32_t acc = 0;
+                    for (;;) {
+                        while (acc == 0u && ++j < ATR_QG_GROUPS) acc = s_acc[j * ATR_QG_THREADS + t];
+                        if (acc == 0u) break;
+                        const int i = atr_ctz(acc) >> 2;
+                        const int id = (int)((acc >> (4 * i)) & 15u);
+                        acc &= ~(15u << (4 * i));
+                        const int c = (S == 3 ? 24 : 16) * (gb + j) + S * i;
+                        if (id == 15) { for (int p2 = 1; p2 <= ad.qg_npat; p2++) qg_verify_pattern(ad, rdt, lo_t, n_t, p2, c, vmin, vmax); }
+                        else qg_verify_pattern(ad, rdt, lo_t, n_t, id, c, vmin, vmax);
+                    }
+                    s_hmin[t] = vmin; s_hmax[t] = vmax;
+                    int g0t, g1t;
+                    qg_group_range<S>(lo_t, n_t, g0t, g1t);
+                    if (g1t <= ATR_QG_GROUPS) s_flag[t] = (unsigned char)(1 | (sa_exact(ad, rdt, lo_t, n_t, vmin, vmax) ? 2 : 0));
+                }
+                gb += ATR_QG_GROUPS;
+                more = gb < g1;
+                __syncthreads();
+                if (tid == 0) s_hl_count = 0;
+            } while (__syncthreads_or(more));
         }
-        __syncthreads();
         // ---- A3 (every thread): shortcut, need-tail gate, finish or queue ----
         int hmin = s_hmin[tid], hmax = s_hmax[tid];
         bool exact = false, need_tail = false;
         const bool live = mine && !routed;
         if (live) {
-            if (n_items > ATR_QG_VQ_CAP) {                              // queue overflow (low-complexity reads): verify inline
-                uint32_t acc1[ATR_QG_GROUPS];
-                qg_scan<S>(ad, s_qtab, rd, wlimit, lo, n, acc1, 1, hmin, hmax);
-            }
-            exact = sa_exact(ad, rd, lo, n, hmin, hmax);
+            const unsigned fl = s_flag[tid];
+            exact = (fl & 1u) ? (fl & 2u) != 0u : sa_exact(ad, rd, lo, n, hmin, hmax);
             if (!exact) need_tail = qg_need_tail(ad, s_sa_peq, rd, lo, n, hmax);
             if (need_tail) {
                 QgTailItem q;
