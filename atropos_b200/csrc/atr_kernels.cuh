@@ -623,20 +623,26 @@ __device__ __forceinline__ void qg_finish(const AdapterK1a& ad, bool active, uin
     list_append(to_refine, sv, refine, counters + 2);
 }
 
+// groups per chunk: 192 columns at step 3, 160 at step 2 (one chunk for reads up to that length; 48 KB of static shared memory)
+template <int S> struct QgChunk { static const int NG = S == 3 ? 8 : 10; };
+
 template <int S>
 __global__ void __launch_bounds__(ATR_QG_THREADS, ATR_QG_MINCTAS) k_filter_qg(const __grid_constant__ AdapterK1a ad,
         const uint32_t* __restrict__ codes, const uint32_t* __restrict__ woff, const uint16_t* __restrict__ len,
         const uint16_t* __restrict__ win, int64_t n_reads, atr_match* __restrict__ out,
         Survivor* __restrict__ narrow, Survivor* __restrict__ wide, Survivor* __restrict__ refine, int* __restrict__ counters) {
+    constexpr int NG = QgChunk<S>::NG;
+    constexpr int GCOLS = S == 3 ? 24 : 16;
     __shared__ __align__(128) uint32_t s_tile[ATR_QG_TILE_WORDS + ATR_QG_PAD];
     __shared__ __align__(16) unsigned char s_qtab[1 << ATR_QG_BITS];
     __shared__ __align__(8) uint64_t s_bar;
-    __shared__ uint32_t s_acc[ATR_QG_GROUPS * ATR_QG_THREADS];   // [group of the chunk][thread]: the group's 8 lookups, 4 bits each
+    __shared__ uint32_t s_acc[NG * ATR_QG_THREADS];          // [group of the chunk][thread]: the group's 8 lookups, 4 bits each
     __shared__ QgTailItem s_tq[2 * ATR_QG_THREADS];
     __shared__ uint2 s_meta[ATR_QG_THREADS];                 // x: first word of the read relative to the tile, y: lo | n << 16
     __shared__ int s_hmin[ATR_QG_THREADS], s_hmax[ATR_QG_THREADS];
+    __shared__ unsigned short s_gm[ATR_QG_THREADS];          // groups of the chunk with hits
     __shared__ unsigned s_sa_peq[16], s_tail_peq[16];
-    __shared__ unsigned char s_hl[ATR_QG_THREADS], s_flag[ATR_QG_THREADS];   // reads of the tile with hits; bit 0 shortcut checked, bit 1 verbatim
+    __shared__ unsigned char s_hl[ATR_QG_THREADS];           // reads of the tile with hits
     __shared__ int s_tq_count, s_hl_count;
 
     const int tid = threadIdx.x;
@@ -671,11 +677,9 @@ __global__ void __launch_bounds__(ATR_QG_THREADS, ATR_QG_MINCTAS) k_filter_qg(co
         const bool fits = span <= ATR_QG_TILE_WORDS;
         const bool use_tma = fits && !last_tile && span > 0 && aligned;
         __syncthreads();                       // everybody is done with the previous tile (and with the set-up above)
-        if (tid == 0) {
-            if (use_tma) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads of the tile before the async write
-                tma_load_1d(s_tile, codes + a_begin, span * 4u, &s_bar);
-            }
+        if (tid == 0 && use_tma) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic reads of the tile before the async write
+            tma_load_1d(s_tile, codes + a_begin, span * 4u, &s_bar);
         }
         if (fits && !use_tma)
             for (uint32_t w = tid; w < w_end - a_begin; w += ATR_QG_THREADS) s_tile[w] = codes[a_begin + w];
@@ -697,93 +701,110 @@ __global__ void __launch_bounds__(ATR_QG_THREADS, ATR_QG_MINCTAS) k_filter_qg(co
                 store_match(out + r, m);
             }
         }
+        const bool live = mine && !routed;
         s_meta[tid] = make_uint2(wr - a_begin, (unsigned)lo | ((unsigned)n << 16));
-        s_hmin[tid] = 0x7fffffff; s_hmax[tid] = -0x7fffffff; s_flag[tid] = 0;
-        __syncthreads();                       // counters, slots and the cooperative copy are visible
+        s_hmin[tid] = 0x7fffffff; s_hmax[tid] = -0x7fffffff;
+        __syncthreads();                       // slots and the cooperative copy are visible
         if (use_tma) { mbar_wait(&s_bar, parity); parity ^= 1u; }
         const uint32_t* rd = codes + wr;       // generic pointer: shared tile or global
         int wlimit = nw;
         if (fits) { rd = s_tile + (wr - a_begin); wlimit = (int)(ATR_QG_TILE_WORDS + ATR_QG_PAD - (wr - a_begin)); }
-        // ---- A1 / A2 in chunks of 8 groups (192 or 128 columns; one chunk for reads up to that length) ----
-        {
-            int g0 = 0, g1 = 0;
-            if (mine && !routed) qg_group_range<S>(lo, n, g0, g1);
-            int gb = 0;
-            bool more;
-            do {
-                // A1 (every thread, uniform): 8 lookups per group, the group's hits as one word of pattern indices
-                uint32_t any = 0;
-#pragma unroll 1
-                for (int j = 0; j < ATR_QG_GROUPS; j++) {
-                    const int g = gb + j;
-                    uint32_t acc = 0;
-                    if (g >= g0 && g < g1) acc = qg_group<S>(s_qtab, ad.qg_mul, rd, g, wlimit);
-                    s_acc[j * ATR_QG_THREADS + tid] = acc;
-                    any |= acc;
+        int g0 = 0, g1 = 0;
+        if (live) qg_group_range<S>(lo, n, g0, g1);
+        int gb = 0;
+        bool more;
+        do {
+            // ---- A1 (every thread, uniform, branch-free): 8 lookups per group -> one word of pattern indices ----
+            unsigned gm = 0;
+#pragma unroll
+            for (int j = 0; j < NG; j++) {
+                const int g = gb + j;
+                uint32_t acc = 0;
+                if (g >= g0 && g < g1) acc = qg_group<S>(s_qtab, ad.qg_mul, rd, g, wlimit);
+                s_acc[j * ATR_QG_THREADS + tid] = acc;
+                gm |= acc ? (1u << j) : 0u;
+            }
+            s_gm[tid] = (unsigned short)gm;
+            more = gb + NG < g1;                                        // this read continues in the next chunk
+            const bool last_chunk = !__syncthreads_or(more);            // (also: the chunk's words are visible)
+            // reads with hits (in this or an earlier chunk) -> the chunk's list, one atomic per warp. In the last chunk
+            // whoever takes a read from the list also finishes it; a read that never had a hit is finished by its own thread.
+            const bool listed = live && (gm != 0u || (last_chunk && gb > 0 && s_hmax[tid] != -0x7fffffff));
+            {
+                const unsigned m = __ballot_sync(0xffffffffu, listed);
+                if (m) {
+                    const int lane = tid & 31, leader = __ffs(m) - 1;
+                    int base = 0;
+                    if (lane == leader) base = atomicAdd(&s_hl_count, __popc(m));
+                    base = __shfl_sync(0xffffffffu, base, leader);
+                    if (listed) s_hl[base + __popc(m & ((1u << lane) - 1u))] = (unsigned char)tid;
                 }
-                {                                                       // reads with hits -> the chunk's list (one atomic per warp)
-                    const unsigned m = __ballot_sync(0xffffffffu, any != 0u);
-                    if (m) {
-                        const int lane = tid & 31, leader = __ffs(m) - 1;
-                        int base = 0;
-                        if (lane == leader) base = atomicAdd(&s_hl_count, __popc(m));
-                        base = __shfl_sync(0xffffffffu, base, leader);
-                        if (any) s_hl[base + __popc(m & ((1u << lane) - 1u))] = (unsigned char)tid;
-                    }
+            }
+            if (last_chunk && live && !listed) {                        // no piece anywhere: a partial match at the read end?
+                if (qg_need_tail(ad, s_sa_peq, rd, lo, n, -0x7fffffff)) {
+                    QgTailItem q;
+                    q.read = (uint32_t)r; q.hmin = 32767; q.hmax = -32768;
+                    s_tq[atomicAdd(&s_tq_count, 1)] = q;
+                } else {
+                    Best b;
+                    b.ref_stop = ad.m; b.q_stop = n; b.cost = ad.m + n; b.origin = 0; b.matches = 0;
+                    finalize(ad, b, n, out + r);
                 }
-                __syncthreads();
-                // A2: one thread per read WITH hits (about half of the tile, dense): verify every hit of the chunk; if the read
-                // is done (single chunk) and its hits lie on one diagonal, the verbatim-occurrence check as well
-                const int n_hl = s_hl_count;
-                for (int e = tid; e < n_hl; e += ATR_QG_THREADS) {
-                    const int t = s_hl[e];
+            }
+            __syncthreads();
+            // ---- A2: one thread per read WITH hits (dense): verify every hit of the chunk; in the last chunk the verbatim-
+            // occurrence shortcut, the need-tail gate and the read's classification follow at once ----
+            const int n_hl = s_hl_count;
+            {
+                const bool act = tid < n_hl;
+                int t = 0, lo_t = 0, n_t = 0, vmin = 0x7fffffff, vmax = -0x7fffffff;
+                bool exact = false, need_tail = false;
+                if (act) {
+                    t = s_hl[tid];
                     const uint2 mt = s_meta[t];
                     const uint32_t* rdt = fits ? s_tile + mt.x : codes + (a_begin + mt.x);
-                    const int lo_t = (int)(mt.y & 0xFFFFu), n_t = (int)(mt.y >> 16);
-                    int vmin = s_hmin[t], vmax = s_hmax[t];
-                    // one flat loop over the read's hits: every trip of the warp verifies one hit in every lane that
-                    // still has one (a loop per group ran at 6 of 32 lanes: the lanes' hits sit in different groups)
-                    int j = -1;
+                    lo_t = (int)(mt.y & 0xFFFFu); n_t = (int)(mt.y >> 16);
+                    vmin = s_hmin[t]; vmax = s_hmax[t];
+                    // one flat loop over the read's hits: every trip of the warp verifies one hit in every lane that still
+                    // has one (a loop per group ran at 6 of 32 lanes: the lanes' hits sit in different groups)
+                    unsigned gmt = s_gm[t];
                     uint32_t acc = 0;
+                    int j = 0;
                     for (;;) {
-                        while (acc == 0u && ++j < ATR_QG_GROUPS) acc = s_acc[j * ATR_QG_THREADS + t];
-                        if (acc == 0u) break;
+                        if (acc == 0u) {
+                            if (gmt == 0u) break;
+                            j = atr_ctz(gmt);
+                            gmt &= gmt - 1u;
+                            acc = s_acc[j * ATR_QG_THREADS + t];
+                        }
                         const int i = atr_ctz(acc) >> 2;
                         const int id = (int)((acc >> (4 * i)) & 15u);
                         acc &= ~(15u << (4 * i));
-                        const int c = (S == 3 ? 24 : 16) * (gb + j) + S * i;
+                        const int c = GCOLS * (gb + j) + S * i;
                         if (id == 15) { for (int p2 = 1; p2 <= ad.qg_npat; p2++) qg_verify_pattern(ad, rdt, lo_t, n_t, p2, c, vmin, vmax); }
                         else qg_verify_pattern(ad, rdt, lo_t, n_t, id, c, vmin, vmax);
                     }
-                    s_hmin[t] = vmin; s_hmax[t] = vmax;
-                    int g0t, g1t;
-                    qg_group_range<S>(lo_t, n_t, g0t, g1t);
-                    if (g1t <= ATR_QG_GROUPS) s_flag[t] = (unsigned char)(1 | (sa_exact(ad, rdt, lo_t, n_t, vmin, vmax) ? 2 : 0));
+                    if (!last_chunk) { s_hmin[t] = vmin; s_hmax[t] = vmax; }
+                    else {
+                        exact = sa_exact(ad, rdt, lo_t, n_t, vmin, vmax);
+                        if (!exact) need_tail = qg_need_tail(ad, s_sa_peq, rdt, lo_t, n_t, vmax);
+                        if (need_tail) {
+                            QgTailItem q;
+                            q.read = (uint32_t)(t0 + t);
+                            q.hmin = (short)(vmax == -0x7fffffff ? 32767 : vmin);
+                            q.hmax = (short)(vmax == -0x7fffffff ? -32768 : vmax);
+                            s_tq[atomicAdd(&s_tq_count, 1)] = q;
+                        }
+                    }
                 }
-                gb += ATR_QG_GROUPS;
-                more = gb < g1;
-                __syncthreads();
-                if (tid == 0) s_hl_count = 0;
-            } while (__syncthreads_or(more));
-        }
-        // ---- A3 (every thread): shortcut, need-tail gate, finish or queue ----
-        int hmin = s_hmin[tid], hmax = s_hmax[tid];
-        bool exact = false, need_tail = false;
-        const bool live = mine && !routed;
-        if (live) {
-            const unsigned fl = s_flag[tid];
-            exact = (fl & 1u) ? (fl & 2u) != 0u : sa_exact(ad, rd, lo, n, hmin, hmax);
-            if (!exact) need_tail = qg_need_tail(ad, s_sa_peq, rd, lo, n, hmax);
-            if (need_tail) {
-                QgTailItem q;
-                q.read = (uint32_t)r;
-                q.hmin = (short)(hmax == -0x7fffffff ? 32767 : hmin);
-                q.hmax = (short)(hmax == -0x7fffffff ? -32768 : hmax);
-                s_tq[atomicAdd(&s_tq_count, 1)] = q;
+                if (last_chunk)
+                    qg_finish(ad, act && !need_tail, (uint32_t)(t0 + t), lo_t, n_t, vmin, vmax, exact, 0, out, narrow, wide, refine, counters);
             }
-        }
-        qg_finish(ad, live && !need_tail, (uint32_t)r, lo, n, hmin, hmax, exact, 0, out, narrow, wide, refine, counters);
-        __syncthreads();
+            gb += NG;
+            __syncthreads();                                            // s_acc / s_hl are free again; tail pushes visible
+            if (tid == 0) s_hl_count = 0;
+            if (last_chunk) break;
+        } while (true);
         // ---- B: 256 tail candidates accumulated -> exact tail Myers + classification, full warps ----
         const int n_tail = s_tq_count;
         if (n_tail >= ATR_QG_THREADS) {
