@@ -18,7 +18,7 @@ _lib = None
 SYMBOLS = [
     "atr_abi_version", "atr_device_count", "atr_ctx_create", "atr_ctx_destroy", "atr_last_error", "atr_ctx_sync",
     "atr_ctx_stream", "atr_ctx_launch_count", "atr_ctx_last_kernel_ms", "atr_ctx_set_profiling",
-    "atr_ctx_last_phase_ms", "atr_adapterset_create",
+    "atr_ctx_last_phase_ms", "atr_ctx_last_phase_name", "atr_adapterset_create",
     "atr_adapterset_destroy", "atr_packed_words", "atr_pack_device", "atr_locate_batch_device",
     "atr_locate_batch_host", "atr_compare_prefixes", "atr_insertset_create", "atr_insertset_destroy",
     "atr_match_insert_batch_device", "atr_match_insert_batch_host", "atr_multi_locate", "atr_merge_overlap_batch_host", "atr_trim_fastq_host", "atr_trim_fastq_pe_host",
@@ -56,6 +56,8 @@ def load():
     L.atr_ctx_last_kernel_ms.restype = C.c_float
     L.atr_ctx_set_profiling.argtypes = [vp, C.c_int]
     L.atr_ctx_last_phase_ms.argtypes = [vp, C.POINTER(C.c_float), C.c_int]
+    L.atr_ctx_last_phase_name.argtypes = [vp, C.c_int]
+    L.atr_ctx_last_phase_name.restype = C.c_char_p
     L.atr_adapterset_create.argtypes = [vp, i32, C.POINTER(_abi.AtrAdapterDesc), C.POINTER(vp)]
     L.atr_adapterset_destroy.argtypes = [vp]
     L.atr_adapterset_destroy.restype = None

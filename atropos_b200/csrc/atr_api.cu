@@ -87,6 +87,7 @@ struct atr_ctx {
     float last_ms = -1.f;
     int profile = 0, phases_valid = 0;
     cudaEvent_t pev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // start, after refine, after band, after wide, after filter
+    const char* phase_names[4] = {"", "", "", ""};   // kernels behind atr_ctx_last_phase_ms' four intervals
     int disable_sa = 0;
     int disable_qg = 0;              // ATR_DISABLE_QG=1: Shift-And first stage even where the q-gram form is eligible (A/B measurements)
     int sm_count = 148;
@@ -209,6 +210,12 @@ int locate_on_stream(atr_ctx* ctx, Slot& slot, const atr_adapterset* set,
                 const unsigned g = grid_for(n, ATR_K1F_THREADS);
                 const unsigned gp = (unsigned)std::min<int64_t>((n + 127) / 128, 148 * 12);
                 const bool use_sa = p.sa_ok && !ctx->disable_sa;
+                if (prof) {
+                    ctx->phase_names[0] = use_sa ? (p.qg_ok && !ctx->disable_qg ? "k_filter_qg" : "k_filter_sa") : "k_filter";
+                    ctx->phase_names[1] = use_sa ? "k_refine" : "";
+                    ctx->phase_names[2] = "k_band<16>+k_band<8>";
+                    ctx->phase_names[3] = "k_wide";
+                }
                 if (use_sa && p.qg_ok && !ctx->disable_qg) {
                     const unsigned gq = (unsigned)std::min<int64_t>((n + ATR_QG_THREADS - 1) / ATR_QG_THREADS, (int64_t)ctx->sm_count * ctx->qg_ctas);
                     if (p.qg_step == 3) k_filter_qg<3><<<gq, ATR_QG_THREADS, 0, st>>>(p, d_codes, d_woff, d_len, d_win, n, d_out, narrow, wide, refine, counters);
@@ -446,6 +453,11 @@ int atr_ctx_last_phase_ms(atr_ctx* ctx, float* out_ms, int n) {
     for (; k < 4 && k < n; k++)
         if (cudaEventElapsedTime(&out_ms[k], ctx->pev[order[k]], ctx->pev[order[k + 1]]) != cudaSuccess) { cudaGetLastError(); break; }
     return k;
+}
+
+const char* atr_ctx_last_phase_name(atr_ctx* ctx, int i) {
+    if (!ctx || i < 0 || i >= 4 || !ctx->phases_valid) return "";
+    return ctx->phase_names[i];
 }
 
 float atr_ctx_last_kernel_ms(atr_ctx* ctx) {

@@ -78,6 +78,10 @@ class Context(object):
         k = self._L.atr_ctx_last_phase_ms(self.handle, buf, 4)
         return [float(buf[i]) for i in range(k)]
 
+    def last_phase_names(self):
+        """the kernels behind the four intervals of last_phase_ms()"""
+        return [(self._L.atr_ctx_last_phase_name(self.handle, i) or b"").decode() for i in range(4)]
+
     # ---- single-call functions ----
     def compare_prefixes(self, ref, query, wildcard_ref=False, wildcard_query=False):
         r, q = ref.encode("ascii"), query.encode("ascii")

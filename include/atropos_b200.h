@@ -156,6 +156,8 @@ float       atr_ctx_last_kernel_ms(atr_ctx* ctx);
  * valid entries (0 if the last call did not take the fast path or profiling is off). */
 int         atr_ctx_set_profiling(atr_ctx* ctx, int on);
 int         atr_ctx_last_phase_ms(atr_ctx* ctx, float* out_ms, int n);
+/* name of the kernel(s) timed by interval i (0..3) of the last profiled call, "" if none */
+const char* atr_ctx_last_phase_name(atr_ctx* ctx, int i);
 
 /* ---- adapters: Aligner.__cinit__ / Adapter.__init__ ---------------------------------------- */
 /* replaces Aligner(reference, max_error_rate, flags, wildcard_ref, wildcard_query, min_overlap,
