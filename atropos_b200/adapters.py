@@ -11,7 +11,7 @@ import numpy as np
 from . import _abi, engine
 from .align import (Match, START_WITHIN_SEQ1, START_WITHIN_SEQ2, STOP_WITHIN_SEQ1, STOP_WITHIN_SEQ2, SEMIGLOBAL,
                     _tuple_of)
-from .util import IUPAC_BASES, RandomMatchProbability
+from .util import IUPAC_BASES, RandomMatchProbability, expand_braces
 
 # adapters/__init__.py:41-56
 BACK = START_WITHIN_SEQ2 | STOP_WITHIN_SEQ2 | STOP_WITHIN_SEQ1
@@ -38,7 +38,7 @@ class Adapter(object):
                  device=0):
         if len(sequence) == 0:
             raise ValueError("Empty adapter sequence")
-        sequence = sequence.upper().replace('U', 'T')
+        sequence = expand_braces(sequence.upper().replace('U', 'T'))     # adapters/__init__.py:267
         seq_set = set(sequence)
         if seq_set <= set('ACGT'):
             adapter_wildcards = False

@@ -91,6 +91,7 @@ struct atr_ctx {
     int disable_sa = 0;
     int disable_qg = 0;              // ATR_DISABLE_QG=1: Shift-And first stage even where the q-gram form is eligible (A/B measurements)
     int sm_count = 148;
+    int64_t panel_chunk = 1 << 19;   // reads per piece of a multi-adapter device call (ATR_PANEL_CHUNK)
     int qg_ctas = 5;                 // persistent CTAs per SM of k_filter_qg (51 registers, 42 KB shared memory: 5 fit); ATR_QG_CTAS overrides
     int disable_fused = 0;           // ATR_DISABLE_FUSED=1: always use the plain register-DP kernel (A/B measurements)
     DevBuf misc;                     // small single-call scratch (compare_prefixes, multi_locate)
@@ -382,6 +383,7 @@ int atr_ctx_create(int device, atr_ctx** out) {
     { const char* e = getenv("ATR_DISABLE_SA"); ctx->disable_sa = (e && e[0] == '1'); }
     { const char* e = getenv("ATR_DISABLE_QG"); ctx->disable_qg = (e && e[0] == '1'); }
     { const char* e = getenv("ATR_QG_CTAS"); if (e && atoi(e) > 0) ctx->qg_ctas = atoi(e); }
+    { const char* e = getenv("ATR_PANEL_CHUNK"); if (e && atoll(e) > 0) ctx->panel_chunk = atoll(e); }
     CU(cudaSetDevice(device));
     { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && v > 0) ctx->sm_count = v; }
     for (int s = 0; s < 2; s++) {
@@ -554,8 +556,19 @@ int atr_locate_batch_device(atr_ctx* ctx, const atr_adapterset* set, const uint3
     }
     Slot& s = ctx->slot[0];
     CU(cudaEventRecord(ctx->ev0, s.stream));
-    int rc = locate_on_stream(ctx, s, set, d_codes, d_woff, d_len, d_win, d_ascii, d_offsets, 0,
-                              fold_case, n, d_out);
+    int rc = ATR_OK;
+    if (set->host.size() > 1 && n > ctx->panel_chunk) {
+        // a panel runs one pass per adapter: in pieces of panel_chunk reads (packed reads + records ~ 50 MB) every pass
+        // after the first finds the reads in the 126 MB L2 instead of streaming them from HBM again
+        for (int64_t c0 = 0; c0 < n && !rc; c0 += ctx->panel_chunk) {
+            const int64_t cn = std::min<int64_t>(ctx->panel_chunk, n - c0);
+            rc = locate_on_stream(ctx, s, set, d_codes, d_woff ? d_woff + c0 : nullptr, d_len ? d_len + c0 : nullptr,
+                                  d_win ? d_win + 2 * c0 : nullptr, d_ascii, d_offsets ? d_offsets + c0 : nullptr, 0,
+                                  fold_case, cn, d_out + c0);
+        }
+    } else {
+        rc = locate_on_stream(ctx, s, set, d_codes, d_woff, d_len, d_win, d_ascii, d_offsets, 0, fold_case, n, d_out);
+    }
     if (rc) return rc;
     CU(cudaEventRecord(ctx->ev1, s.stream));
     ctx->last_ms = -2.f;             // resolved lazily by atr_ctx_last_kernel_ms()

@@ -258,6 +258,9 @@ int fq_describe(atr_ctx* ctx, FqSide& f, const FqChunk& c, int64_t line, int kin
 
 }  // namespace
 
+// inside the chunk loops an error must not return: D2H copies into the caller's buffers may still be in flight on the
+// slots' out_streams -- record it and leave the loop; the common tail synchronises everything before returning
+#define CUB(call) { cudaError_t e_ = (call); if (e_ != cudaSuccess) { result = cuda_fail(ctx, e_, #call); break; } }
 extern "C" int atr_trim_fastq_host(atr_ctx* ctx, const atr_adapterset* set, const atr_trim_opts* opts, const uint8_t* text,
                                    int64_t nbytes, uint8_t* out_text, int64_t out_cap, int64_t* out_bytes, int64_t* consumed,
                                    atr_trim_stats* stats, atr_fastq_error* err) {
@@ -325,7 +328,7 @@ extern "C" int atr_trim_fastq_host(atr_ctx* ctx, const atr_adapterset* set, cons
         Slot& s = ctx->slot[cur.slot];
         FqSide& f = s.fq[0];
         const double tw0 = now();
-        CU(cudaStreamSynchronize(s.stream));
+        CUB(cudaStreamSynchronize(s.stream));
         t_wait_front += now() - tw0;
         if (f.hinfo->nl_overflow) {                   // more lines than the index was sized for: grow, redo the index
             // (an error leaves the loop instead of returning: copies into the caller's buffers may still be in flight)
@@ -334,7 +337,7 @@ extern "C" int atr_trim_fastq_host(atr_ctx* ctx, const atr_adapterset* set, cons
             flags_of(cur, ft, ut);
             rc = fq_index(ctx, s, 0, cur, ft, ut);
             if (rc) { result = rc; break; }
-            CU(cudaStreamSynchronize(s.stream));
+            CUB(cudaStreamSynchronize(s.stream));
         }
         const FqInfo hi = *f.hinfo;
         cur.n_rec = hi.n_rec; cur.n_nl = hi.n_nl; cur.consumed = hi.consumed;
@@ -363,7 +366,7 @@ extern "C" int atr_trim_fastq_host(atr_ctx* ctx, const atr_adapterset* set, cons
         if (rc) { result = rc; break; }
         if (dbg_timing) cudaEventRecord(evs[cur.slot][3], s.stream);
         const double tw1 = now();
-        CU(cudaStreamSynchronize(s.stream));
+        CUB(cudaStreamSynchronize(s.stream));
         t_wait_back += now() - tw1;
         if (dbg_timing) { float ms = 0; cudaEventElapsedTime(&ms, evs[cur.slot][2], evs[cur.slot][3]); t_back += ms; }
         const FqInfo hb = *f.hinfo;
@@ -372,11 +375,11 @@ extern "C" int atr_trim_fastq_host(atr_ctx* ctx, const atr_adapterset* set, cons
             result = rc ? rc : fail(ctx, ATR_E_FORMAT, "malformed FASTQ (see atr_fastq_error)");
             break;
         }
-        if (opos + (int64_t)hb.out_bytes > out_cap) { result = fail(ctx, ATR_E_ARG, "out_cap too small for the trimmed text"); break; }
+        if (opos + (int64_t)hb.out_bytes > out_cap) { result = fail(ctx, ATR_E_ARG, "out_cap too small for the trimmed text (nbytes + 1 always suffices)"); break; }
         // own stream: the next chunk's H2D into this slot must not queue behind this copy
         if (hb.out_bytes) {
-            CU(cudaMemcpyAsync(out_text + opos, f.outtext.p, (size_t)hb.out_bytes, cudaMemcpyDeviceToHost, f.out_stream));
-            CU(cudaEventRecord(f.ev_d2h, f.out_stream));
+            CUB(cudaMemcpyAsync(out_text + opos, f.outtext.p, (size_t)hb.out_bytes, cudaMemcpyDeviceToHost, f.out_stream));
+            CUB(cudaEventRecord(f.ev_d2h, f.out_stream));
             f.d2h_pending = 1;
         }
         opos += (int64_t)hb.out_bytes;
@@ -695,7 +698,7 @@ extern "C" int atr_trim_fastq_pe_host(atr_ctx* ctx, const atr_insertset* iset, c
     int result = ATR_OK;
     while (true) {
         Slot& s = ctx->slot[cur.slot];
-        CU(cudaStreamSynchronize(s.stream));
+        CUB(cudaStreamSynchronize(s.stream));
         bool redo = false;
         for (int f = 0; f < 2 && result == ATR_OK; f++) {
             if (s.fq[f].hinfo->nl_overflow) {
@@ -709,7 +712,7 @@ extern "C" int atr_trim_fastq_pe_host(atr_ctx* ctx, const atr_insertset* iset, c
             }
         }
         if (result != ATR_OK) break;
-        if (redo) CU(cudaStreamSynchronize(s.stream));
+        if (redo) CUB(cudaStreamSynchronize(s.stream));
         bool bare = false;
         for (int f = 0; f < 2; f++) {
             const FqInfo hi = *s.fq[f].hinfo;
@@ -786,7 +789,7 @@ extern "C" int atr_trim_fastq_pe_host(atr_ctx* ctx, const atr_insertset* iset, c
             }
         }
         if (need_sync) {
-            CU(cudaStreamSynchronize(s.stream));
+            CUB(cudaStreamSynchronize(s.stream));
             for (int f = 0; f < 2; f++) cur.c[f].consumed = s.fq[f].hinfo->consumed;
         }
         for (int f = 0; f < 2; f++) pos[f] = cur.c[f].start + cur.c[f].consumed;
@@ -796,7 +799,7 @@ extern "C" int atr_trim_fastq_pe_host(atr_ctx* ctx, const atr_insertset* iset, c
         if (rc) { result = rc; break; }
         rc = pe_back(ctx, s, cur, iset, sets, opts, L, d_stats);
         if (rc) { result = rc; break; }
-        CU(cudaStreamSynchronize(s.stream));
+        CUB(cudaStreamSynchronize(s.stream));
         const unsigned long long key = s.fq[0].hinfo->err_key;
         if (key != ~0ull) {
             const int64_t code = (int64_t)(key >> 8), r = code / 16, sub = code % 16;
@@ -806,7 +809,8 @@ extern "C" int atr_trim_fastq_pe_host(atr_ctx* ctx, const atr_insertset* iset, c
                 result = line_error(s, f, cur.c[f], 4 * r + (sub & 3), kind, records_before);
             } else {                                 // names: both header lines
                 FqRec R[2];
-                for (int f = 0; f < 2; f++) CU(cudaMemcpy(&R[f], s.fq[f].recs.as<FqRec>() + r, sizeof(FqRec), cudaMemcpyDeviceToHost));
+                for (int f = 0; f < 2; f++) CUB(cudaMemcpy(&R[f], s.fq[f].recs.as<FqRec>() + r, sizeof(FqRec), cudaMemcpyDeviceToHost));
+                if (result) break;                   // (the CUB above only left the inner loop)
                 err->kind = kind; err->file = 0; err->record = records_before + r; err->terminated = 1;
                 err->line_begin = cur.c[0].start + R[0].hdr_b; err->line_end = err->line_begin + R[0].hdr_len;
                 err->line_begin2 = cur.c[1].start + R[1].hdr_b; err->line_end2 = err->line_begin2 + R[1].hdr_len;
@@ -820,13 +824,14 @@ extern "C" int atr_trim_fastq_pe_host(atr_ctx* ctx, const atr_insertset* iset, c
             const int64_t ob = (int64_t)q.hinfo->out_bytes;
             if (opos[f] + ob > out_cap[f]) { cap_bad = true; break; }
             if (ob) {
-                CU(cudaMemcpyAsync(outp[f] + opos[f], q.outtext.p, (size_t)ob, cudaMemcpyDeviceToHost, q.out_stream));
-                CU(cudaEventRecord(q.ev_d2h, q.out_stream));
+                CUB(cudaMemcpyAsync(outp[f] + opos[f], q.outtext.p, (size_t)ob, cudaMemcpyDeviceToHost, q.out_stream));
+                CUB(cudaEventRecord(q.ev_d2h, q.out_stream));
                 q.d2h_pending = 1;
             }
             opos[f] += ob;
         }
-        if (cap_bad) { result = fail(ctx, ATR_E_ARG, "out_cap too small for the trimmed text"); break; }
+        if (result) break;                           // (a CUB inside the loop over the two sides)
+        if (cap_bad) { result = fail(ctx, ATR_E_ARG, "out_cap too small for the trimmed text (nbytes + 1 always suffices)"); break; }
         records_before += n;
         cur = nxt;
     }

@@ -182,7 +182,7 @@ class FastqTrimmer(object):
         buf = np.frombuffer(text, dtype=np.uint8) if not isinstance(text, np.ndarray) else text
         n = int(buf.size)
         if out is None:
-            out = np.empty(max(n, 1), dtype=np.uint8)
+            out = np.empty(n + 1, dtype=np.uint8)          # an unterminated last record gains its newline
         if stats is None:
             stats = self.new_stats()
         opts = _abi.AtrTrimOpts(self.times, self.max_len, self.max_errors, int(bool(final)), self.chunk_bytes,
@@ -360,9 +360,9 @@ class FastqPairTrimmer(object):
         b1 = np.frombuffer(text1, dtype=np.uint8) if not isinstance(text1, np.ndarray) else text1
         b2 = np.frombuffer(text2, dtype=np.uint8) if not isinstance(text2, np.ndarray) else text2
         if out1 is None:
-            out1 = np.empty(max(int(b1.size), 1), dtype=np.uint8)
+            out1 = np.empty(int(b1.size) + 1, dtype=np.uint8)
         if out2 is None:
-            out2 = np.empty(max(int(b2.size), 1), dtype=np.uint8)
+            out2 = np.empty(int(b2.size) + 1, dtype=np.uint8)
         if stats is None:
             stats = self.new_stats()
         opts = _abi.AtrTrimPeOpts(int(self.symmetric), self.min_insert_overlap, self.max_len, self.max_errors,

@@ -343,7 +343,8 @@ typedef struct atr_trim_stats {
  *   -> FastqFormat.format (io/seqio.py:686-700)
  * by one pass on the GPU: newline index, record framing + validation, 4-bit packing, the adapter-alignment
  * kernels, trimming windows + statistics, formatting. `text`/`out_text` are HOST buffers (pinned for full speed);
- * out_cap >= nbytes always suffices (trimming never grows a record). The adapter set must have been created with
+ * out_cap >= nbytes + 1 always suffices (trimming never grows a record; an unterminated last line gains its
+ * newline, FastqFormat.format io/seqio.py:686-700). The adapter set must have been created with
  * match_to_semantics = 1. *consumed = bytes of `text` that were processed (all of it if final_chunk).
  * On ATR_E_FORMAT *err describes the first malformed line. */
 int  atr_trim_fastq_host(atr_ctx* ctx, const atr_adapterset* set, const atr_trim_opts* opts,

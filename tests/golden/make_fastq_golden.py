@@ -237,6 +237,10 @@ def main():
     add("err_qual_len", "\n".join(bad), one)
     add("err_truncated", "\n".join(lines[:18]) + "\n", one)
     add("err_truncated_mid", "\n".join(lines[:17]) + "\n", one)
+    # --- nothing is removed and the last line has no newline: the output is ONE BYTE LONGER than the input (appended last
+    # so that the cases above keep their random streams) ----------------------------------------------------------
+    plain = [("u%d" % i, fuzzgen.rand_seq(rng, 60), "", quals(rng, 60)) for i in range(12)]
+    add("no_final_newline_untrimmed", fastq(plain, final_eol=False), one, overlap=20)
 
     path = os.path.join(HERE, "fastq_trim.json.gz")
     with open(path, "wb") as raw, gzip.GzipFile(fileobj=raw, mode="wb", mtime=0) as fh:

@@ -150,7 +150,7 @@ def trim_fastq(text, adapters, times=1, max_len=512, final=True, **read_ops):
     stats = fastq.TrimStats(len(adapters), max_len, max_errors)
     opts = _abi.AtrTrimOpts(times, max_len, max_errors, int(bool(final)), 0, None, _abi.make_read_ops(**read_ops))
     oc = SimOpsCounters()
-    out = np.empty(max(len(text), 1), dtype=np.uint8)
+    out = np.empty(len(text) + 1, dtype=np.uint8)
     counters = np.zeros(5, dtype=np.int64)
     nout, consumed = C.c_longlong(0), C.c_longlong(0)
     err = _abi.AtrFastqError()
@@ -191,8 +191,8 @@ def trim_fastq_pe(text1, text2, adapter1, adapter2, insert_aligner=None, symmetr
                               _abi.MISMATCH_ACTIONS[mismatch_action], 0, 0, _abi.make_read_ops(**read_ops))
     corrected = (C.c_longlong * 3)()
     oc = SimOpsCounters()
-    o1 = np.empty(max(len(text1), 1), dtype=np.uint8)
-    o2 = np.empty(max(len(text2), 1), dtype=np.uint8)
+    o1 = np.empty(len(text1) + 1, dtype=np.uint8)
+    o2 = np.empty(len(text2) + 1, dtype=np.uint8)
     counters = np.zeros(9, dtype=np.int64)
     nout, consumed = (C.c_longlong * 2)(), (C.c_longlong * 2)()
     err = _abi.AtrFastqError()
