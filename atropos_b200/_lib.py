@@ -19,8 +19,8 @@ SYMBOLS = [
     "atr_abi_version", "atr_device_count", "atr_ctx_create", "atr_ctx_destroy", "atr_last_error", "atr_ctx_sync",
     "atr_ctx_stream", "atr_ctx_launch_count", "atr_ctx_last_kernel_ms", "atr_ctx_set_profiling",
     "atr_ctx_last_phase_ms", "atr_ctx_last_phase_name", "atr_adapterset_create",
-    "atr_adapterset_destroy", "atr_packed_words", "atr_pack_device", "atr_locate_batch_device",
-    "atr_locate_batch_host", "atr_compare_prefixes", "atr_insertset_create", "atr_insertset_destroy",
+    "atr_adapterset_destroy", "atr_packed_words", "atr_pack_device", "atr_pack_reads_host", "atr_locate_batch_device",
+    "atr_locate_batch_host", "atr_locate_batch_host_packed", "atr_compare_prefixes", "atr_insertset_create", "atr_insertset_destroy",
     "atr_match_insert_batch_device", "atr_match_insert_batch_host", "atr_multi_locate", "atr_merge_overlap_batch_host", "atr_trim_fastq_host", "atr_trim_fastq_pe_host",
 ]
 
@@ -66,6 +66,8 @@ def load():
     L.atr_pack_device.argtypes = [vp, vp, vp, i64, C.c_int, vp, vp, vp]
     L.atr_locate_batch_device.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, i64, vp]
     L.atr_locate_batch_host.argtypes = [vp, vp, vp, vp, vp, i64, C.c_int, vp]
+    L.atr_pack_reads_host.argtypes = [vp, vp, i64, C.c_int, C.c_int, vp, vp, vp]
+    L.atr_locate_batch_host_packed.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, i64, vp]
     L.atr_compare_prefixes.argtypes = [vp, C.c_char_p, i32, C.c_char_p, i32, C.c_int, C.c_int, C.POINTER(i32)]
     L.atr_insertset_create.argtypes = [vp, C.POINTER(_abi.AtrInsertDesc), C.POINTER(vp)]
     L.atr_insertset_destroy.argtypes = [vp]

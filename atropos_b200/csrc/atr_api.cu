@@ -630,6 +630,82 @@ int atr_locate_batch_host(atr_ctx* ctx, const atr_adapterset* set, const uint8_t
     return ATR_OK;
 }
 
+int atr_locate_batch_host_packed(atr_ctx* ctx, const atr_adapterset* set, const uint32_t* codes, const uint32_t* woff,
+                                 const uint16_t* len, const uint16_t* win, const uint8_t* ascii, const int64_t* offsets,
+                                 int fold_case, int64_t n, atr_match* out) {
+    if (!ctx || !set || !codes || !woff || !len || !out || n < 0) return fail(ctx, ATR_E_ARG, "bad arguments to atr_locate_batch_host_packed");
+    if (set->ctx != ctx) return fail(ctx, ATR_E_ARG, "adapter set belongs to another context");
+    CU(cudaSetDevice(ctx->device));
+    const bool have_ascii = ascii != nullptr && offsets != nullptr;
+    const int64_t max_reads = 1 << 20;
+    std::vector<int64_t> esc_offsets;
+    std::vector<uint8_t> esc_bytes;
+    int64_t c0 = 0;
+    int which = 0;
+    while (c0 < n) {
+        int64_t c1 = std::min(n, c0 + max_reads);
+        while (c1 > c0 + 1 && (int64_t)(woff[c1] - woff[c0]) > ((int64_t)64 << 20)) c1 = c0 + (c1 - c0) / 2;     // <= 256 MiB of codes
+        const int64_t cn = c1 - c0;
+        const uint32_t w0 = woff[c0], nwords = woff[c1] - w0;
+        bool uniform = true, any_esc = false;
+        for (int64_t i = c0; i < c1; i++) {
+            uniform = uniform && len[i] == len[c0] && woff[i + 1] - woff[i] == woff[c0 + 1] - woff[c0];
+            any_esc = any_esc || (len[i] & ATR_ESC_BIT);
+        }
+        Slot& s = ctx->slot[which];
+        int rc = s.codes.ensure(((size_t)nwords + 16) * sizeof(uint32_t));
+        if (!rc) rc = s.woff.ensure((size_t)(cn + 1) * sizeof(uint32_t));
+        if (!rc) rc = s.len.ensure((size_t)cn * sizeof(uint16_t));
+        if (!rc) rc = s.out.ensure((size_t)cn * sizeof(atr_match));
+        if (!rc && win) rc = s.win.ensure((size_t)cn * 2 * sizeof(uint16_t));
+        if (rc) return fail(ctx, rc, "out of device memory (packed host entry point staging)");
+        // the chunk's words land (w0 & 3) words into the buffer, so that `base + woff[i]` addresses them with the caller's
+        // own word offsets and 16-byte alignment (the TMA tile copies) is the same as in the caller's array
+        uint32_t* d_words = s.codes.as<uint32_t>() + (w0 & 3u);
+        const uint32_t* d_base = d_words - w0;
+        if (nwords) CU(cudaMemcpyAsync(d_words, codes + w0, (size_t)nwords * sizeof(uint32_t), cudaMemcpyHostToDevice, s.stream));
+        if (uniform) {
+            k_make_packed_index<<<grid_for(cn + 1, 256), 256, 0, s.stream>>>(s.woff.as<uint32_t>(), s.len.as<uint16_t>(), cn, w0,
+                                                                              woff[c0 + 1] - woff[c0], len[c0]);
+            LAUNCHED(ctx);
+        } else {
+            CU(cudaMemcpyAsync(s.woff.p, woff + c0, (size_t)(cn + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, s.stream));
+            CU(cudaMemcpyAsync(s.len.p, len + c0, (size_t)cn * sizeof(uint16_t), cudaMemcpyHostToDevice, s.stream));
+        }
+        if (win) CU(cudaMemcpyAsync(s.win.p, win + 2 * c0, (size_t)cn * 2 * sizeof(uint16_t), cudaMemcpyHostToDevice, s.stream));
+        const uint8_t* d_ascii = nullptr;
+        const int64_t* d_offsets = nullptr;
+        if (any_esc && have_ascii) {
+            // only the escaped reads' bytes travel: offsets of zero-length entries for every other read of the chunk
+            CU(cudaStreamSynchronize(s.stream));          // the staging vectors of the previous use of this slot are free
+            esc_offsets.assign((size_t)cn + 1, 0);
+            esc_bytes.clear();
+            for (int64_t i = 0; i < cn; i++) {
+                esc_offsets[(size_t)i] = (int64_t)esc_bytes.size();
+                if (len[c0 + i] & ATR_ESC_BIT) esc_bytes.insert(esc_bytes.end(), ascii + offsets[c0 + i], ascii + offsets[c0 + i + 1]);
+            }
+            esc_offsets[(size_t)cn] = (int64_t)esc_bytes.size();
+            rc = s.ascii.ensure(esc_bytes.size() + 16);
+            if (!rc) rc = s.offsets.ensure((size_t)(cn + 1) * sizeof(int64_t));
+            if (rc) return fail(ctx, rc, "out of device memory (escaped reads)");
+            CU(cudaMemcpyAsync(s.ascii.p, esc_bytes.data(), esc_bytes.size(), cudaMemcpyHostToDevice, s.stream));
+            CU(cudaMemcpyAsync(s.offsets.p, esc_offsets.data(), (size_t)(cn + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, s.stream));
+            CU(cudaStreamSynchronize(s.stream));          // pageable staging: the vectors are reused by the next chunk
+            d_ascii = s.ascii.as<uint8_t>();
+            d_offsets = s.offsets.as<int64_t>();
+        }
+        rc = locate_on_stream(ctx, s, set, d_base, s.woff.as<uint32_t>(), s.len.as<uint16_t>(), win ? s.win.as<uint16_t>() : nullptr,
+                              d_ascii, d_offsets, 0, fold_case, cn, s.out.as<atr_match>());
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(out + c0, s.out.p, (size_t)cn * sizeof(atr_match), cudaMemcpyDeviceToHost, s.stream));
+        c0 = c1;
+        which ^= 1;
+    }
+    for (int s = 0; s < 2; s++) CU(cudaStreamSynchronize(ctx->slot[s].stream));
+    ctx->last_ms = -1.f;
+    return ATR_OK;
+}
+
 // ---- compare_prefixes -----------------------------------------------------------------------------
 int atr_compare_prefixes(atr_ctx* ctx, const char* ref, int32_t m, const char* query, int32_t n, int wildcard_ref,
                          int wildcard_query, int32_t* out6) {

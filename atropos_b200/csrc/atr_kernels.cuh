@@ -22,6 +22,14 @@ __global__ void __launch_bounds__(256) k_make_offsets(int64_t* __restrict__ offs
     if (i <= n) offsets[i] = first + i * len;
 }
 
+// fixed-length packed chunk: word offsets and lengths are arithmetic, generated here instead of crossing PCIe (6 B/read)
+__global__ void __launch_bounds__(256) k_make_packed_index(uint32_t* __restrict__ woff, uint16_t* __restrict__ len, int64_t n,
+                                                           uint32_t first_word, uint32_t words_per_read, uint16_t len_value) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= n) woff[i] = first_word + (uint32_t)i * words_per_read;
+    if (i < n) len[i] = len_value;
+}
+
 // Fast path of the packers: the eight bytes of a full output word are all upper-case A / C / G / T (nearly every word of
 // real data). Three aligned 32-bit loads and two byte permutes fetch them whatever the read's alignment; bits 1-2 of
 // a base (A 00, C 01, T 10, G 11) become the selector of two more permutes, one producing the 4-bit codes, the other

@@ -31,6 +31,24 @@ def encode_reads(reads):
     return np.frombuffer(blob, dtype=np.uint8), offsets
 
 
+def pack_reads_host(ascii, offsets, fold_case=False, threads=0, out=None):
+    """atr_pack_reads_host: (ascii, offsets) -> (codes uint32[], woff uint32[n+1], len uint16[n]) in host memory, the
+    layout of include/atropos_b200.h (no GPU involved). `out`: optional (codes, woff, len) arrays to fill, e.g. pinned."""
+    L = _lib.load()
+    ascii = np.ascontiguousarray(ascii, dtype=np.uint8)
+    offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+    n = len(offsets) - 1
+    if out is None:
+        words = int(L.atr_packed_words(offsets.ctypes.data, n))
+        out = (np.empty(words + 8, dtype=np.uint32), np.empty(n + 1, dtype=np.uint32), np.empty(n, dtype=np.uint16))
+    codes, woff, lens = out
+    rc = L.atr_pack_reads_host(ascii.ctypes.data if ascii.size else None, offsets.ctypes.data, n, int(bool(fold_case)),
+                               int(threads), codes.ctypes.data, woff.ctypes.data, lens.ctypes.data)
+    if rc != 0:
+        raise ValueError("atr_pack_reads_host failed (%d): a read longer than 32767 nt or bad offsets" % rc)
+    return codes, woff, lens
+
+
 def fixed_length_offsets(n, length):
     return np.arange(n + 1, dtype=np.int64) * int(length)
 
@@ -179,6 +197,27 @@ class AdapterSet(object):
         _lib.check(self._L.atr_locate_batch_host(self.ctx.handle, self.handle, ascii.ctypes.data if ascii.size else None,
                                                  offsets.ctypes.data, wptr, n, int(bool(fold_case)), out.ctypes.data),
                    self.ctx.handle)
+        return out
+
+    def locate_host_packed(self, codes, woff, lens, win=None, ascii=None, offsets=None, fold_case=False, out=None):
+        """atr_locate_batch_host_packed: reads packed in host memory (pack_reads_host); ascii / offsets only serve the
+        escaped reads."""
+        n = len(lens)
+        if out is None:
+            out = np.empty(n, dtype=_abi.MATCH_DTYPE)
+        wptr = None
+        if win is not None:
+            win = np.ascontiguousarray(win, dtype=np.uint16)
+            assert win.shape == (n, 2)
+            wptr = win.ctypes.data
+        a_ptr = o_ptr = None
+        if ascii is not None and offsets is not None:
+            ascii = np.ascontiguousarray(ascii, dtype=np.uint8)
+            offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+            a_ptr, o_ptr = (ascii.ctypes.data if ascii.size else None), offsets.ctypes.data
+        _lib.check(self._L.atr_locate_batch_host_packed(self.ctx.handle, self.handle, codes.ctypes.data, woff.ctypes.data,
+                                                        lens.ctypes.data, wptr, a_ptr, o_ptr, int(bool(fold_case)), int(n),
+                                                        out.ctypes.data), self.ctx.handle)
         return out
 
     def locate_device(self, d_codes, d_woff, d_len, n, d_out, d_win=None, d_ascii=None, d_offsets=None,

@@ -174,6 +174,13 @@ int64_t atr_packed_words(const int64_t* offsets, int64_t n);
 int  atr_pack_device(atr_ctx* ctx, const uint8_t* d_ascii, const int64_t* d_offsets, int64_t n,
                      int fold_case, uint32_t* d_codes, uint32_t* d_woff, uint16_t* d_len);
 
+/* Host-side twin of atr_pack_device (no GPU involved): the same layout in HOST memory -- codes must hold
+ * atr_packed_words(offsets, n) words, woff n + 1 entries, len n entries. n_threads <= 0: every hardware thread.
+ * For callers that keep reads packed (their own reader, a packed file format) and ship them with
+ * atr_locate_batch_host_packed: 75 + 6 bytes per 150-nt read over PCIe instead of 150. */
+int  atr_pack_reads_host(const uint8_t* ascii, const int64_t* offsets, int64_t n, int fold_case, int n_threads,
+                         uint32_t* codes, uint32_t* woff, uint16_t* len);
+
 /* ---- Aligner.locate / Adapter.match_to / AdapterCutter._best_match over a batch ------------- */
 /* Device-resident form. For every read i (window d_win[2i], d_win[2i+1] if d_win != NULL, else the
  * whole read) aligns every adapter of the set and keeps the best (strictly more matches wins, the
@@ -189,6 +196,14 @@ int  atr_locate_batch_device(atr_ctx* ctx, const atr_adapterset* set, const uint
 int  atr_locate_batch_host(atr_ctx* ctx, const atr_adapterset* set, const uint8_t* ascii,
                            const int64_t* offsets, const uint16_t* win, int64_t n, int fold_case,
                            atr_match* out);
+
+/* The same for reads that are packed already, in HOST memory (atr_pack_reads_host or the caller's own packer): only
+ * codes / woff / len cross PCIe (fixed-length chunks: just the codes, the index is rebuilt on the device).
+ * ascii / offsets: optional, only read for ESCAPED reads (len bit 15), whose bytes are sent along; NULL: escaped reads
+ * come back with status ATR_ST_ESCAPED. */
+int  atr_locate_batch_host_packed(atr_ctx* ctx, const atr_adapterset* set, const uint32_t* codes, const uint32_t* woff,
+                                  const uint16_t* len, const uint16_t* win, const uint8_t* ascii, const int64_t* offsets,
+                                  int fold_case, int64_t n, atr_match* out);
 
 /* ---- compare_prefixes (_align.pyx:501-544) -------------------------------------------------- */
 /* One (ref, query) pair per call: compare_prefixes(ref, query, wildcard_ref, wildcard_query);

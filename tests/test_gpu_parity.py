@@ -552,3 +552,39 @@ def test_batched_trim_consumes_gpu_records():
         assert a.errors_front == b.errors_front and a.errors_back == b.errors_back
         assert a.adjacent_bases == b.adjacent_bases
     assert g[3] > 1000
+
+
+def test_packed_host_entry_point_equals_ascii_entry_point():
+    """atr_locate_batch_host_packed (reads packed on the host by atr_pack_reads_host; only codes / index cross PCIe,
+    escaped reads' bytes ride along) == atr_locate_batch_host: single adapter and panel, windows, ragged and
+    fixed-length batches, lower case / other bytes, with and without the ASCII for the escaped reads."""
+    from atropos_b200 import _abi, engine
+    from atropos_b200.adapters import Adapter, BACK, FRONT
+    from atropos_b200.modifiers import AdapterCutter
+    rng = np.random.default_rng(77)
+    for fixed in (True, False):
+        reads = []
+        for i in range(30000):
+            L = 150 if fixed else int(rng.integers(0, 260))
+            r = fuzzgen.read_with_adapter(rng, T1, L, n_rate=0.01)
+            if not fixed and rng.random() < 0.03:
+                r = r.lower() if rng.random() < 0.5 else r.replace("A", ".", 1)
+            reads.append(r)
+        ascii, offsets = engine.encode_reads(reads)
+        for adapters, fold in (([Adapter(T1, BACK)], True), ([Adapter(T1, BACK), Adapter("TGGAATTCTCGGGTGCCAAGG", BACK),
+                                                              Adapter("AATGATACGGCGACCACCGA", FRONT)], False)):
+            aset = AdapterCutter(adapters)._adapterset()
+            win = None
+            if not fixed:
+                lens_ = np.diff(offsets)
+                lo = (rng.random(len(reads)) * lens_ * 0.3).astype(np.uint16)
+                win = np.stack([lo, lens_.astype(np.uint16)], axis=1)
+            exp = aset.locate_host(ascii, offsets, win=win, fold_case=fold)
+            codes, woff, lens = engine.pack_reads_host(ascii, offsets, fold_case=fold)
+            got = aset.locate_host_packed(codes, woff, lens, win=win, ascii=ascii, offsets=offsets, fold_case=fold)
+            assert np.array_equal(got, exp)
+            got2 = aset.locate_host_packed(codes, woff, lens, win=win, fold_case=fold)
+            esc = (lens & 0x8000) != 0
+            assert np.array_equal(got2[~esc], exp[~esc])
+            if esc.any():
+                assert (got2["status"][esc] == _abi.ATR_ST_ESCAPED).all()
