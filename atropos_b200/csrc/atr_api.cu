@@ -2,6 +2,7 @@
 // chunked double-buffered host entry points and the kernel launch logic.
 #include <cuda_runtime.h>
 #include <cub/device/device_scan.cuh>
+#include <nvtx3/nvToolsExt.h>        // header-only; ranges cost nothing unless a tool (nsys / ncu --nvtx) is attached
 
 #include <algorithm>
 #include <cfenv>
@@ -16,6 +17,12 @@
 #include "atr_kernels.cuh"
 
 static thread_local std::string g_last_error;
+
+// NVTX range around a host-side chunk / entry point (shows the double-buffered pipeline in a timeline)
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 namespace {
 
@@ -589,6 +596,7 @@ int atr_locate_batch_host(atr_ctx* ctx, const atr_adapterset* set, const uint8_t
         int64_t c1 = std::min(n, c0 + max_reads);
         while (c1 > c0 + 1 && offsets[c1] - offsets[c0] > max_bytes) c1 = c0 + (c1 - c0) / 2;
         const int64_t cn = c1 - c0, bytes = offsets[c1] - offsets[c0];
+        NvtxRange nvtx_chunk("atr_locate_batch_host: chunk (H2D, pack, locate, D2H enqueue)");
         bool uniform = true;
         const int64_t len0 = offsets[c0 + 1] - offsets[c0];
         for (int64_t i = c0; i < c1; i++) {
@@ -646,6 +654,7 @@ int atr_locate_batch_host_packed(atr_ctx* ctx, const atr_adapterset* set, const 
         int64_t c1 = std::min(n, c0 + max_reads);
         while (c1 > c0 + 1 && (int64_t)(woff[c1] - woff[c0]) > ((int64_t)64 << 20)) c1 = c0 + (c1 - c0) / 2;     // <= 256 MiB of codes
         const int64_t cn = c1 - c0;
+        NvtxRange nvtx_chunk("atr_locate_batch_host_packed: chunk");
         const uint32_t w0 = woff[c0], nwords = woff[c1] - w0;
         bool uniform = true, any_esc = false;
         for (int64_t i = c0; i < c1; i++) {
@@ -801,6 +810,7 @@ int atr_match_insert_batch_host(atr_ctx* ctx, const atr_insertset* set, const ui
     int which = 0;
     while (c0 < n) {
         const int64_t c1 = std::min(n, c0 + max_pairs), cn = c1 - c0;
+        NvtxRange nvtx_chunk("atr_match_insert_batch_host: chunk");
         const int64_t b1 = offsets1[c1] - offsets1[c0], b2 = offsets2[c1] - offsets2[c0];
         for (int64_t i = c0; i < c1; i++) {
             const int64_t la = offsets1[i + 1] - offsets1[i], lb = offsets2[i + 1] - offsets2[i];

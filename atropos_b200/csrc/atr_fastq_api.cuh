@@ -327,6 +327,7 @@ extern "C" int atr_trim_fastq_host(atr_ctx* ctx, const atr_adapterset* set, cons
     while (true) {
         Slot& s = ctx->slot[cur.slot];
         FqSide& f = s.fq[0];
+        NvtxRange nvtx_chunk("atr_trim_fastq_host: chunk");
         const double tw0 = now();
         CUB(cudaStreamSynchronize(s.stream));
         t_wait_front += now() - tw0;

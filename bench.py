@@ -521,6 +521,31 @@ def run_cfg2(rig, args):
     link["M_reads_per_s"] = world * n / link["seconds_per_step"] / 1e6
     link["e2e_fraction_of_link_roof"] = e2e_value / link["M_reads_per_s"]
 
+    # ---- e2e for callers that keep reads PACKED on the host (SURVEY 8d timing (ii)): pinned packed buffers -> H2D of the
+    # codes only (75 B/read; fixed-length index rebuilt on the device) -> kernels -> D2H of the records; the host packer
+    # (threaded AVX2, atr_pack_reads_host) is timed separately ----
+    from atropos_b200 import engine as engine_mod
+    nwords = n * ((L + 7) // 8)
+    pk = [torch.empty((nwords + 8) * 4, dtype=torch.uint8, pin_memory=True), torch.empty((n + 1) * 4, dtype=torch.uint8, pin_memory=True),
+          torch.empty(n * 2, dtype=torch.uint8, pin_memory=True)]
+    pk_np = (pk[0].numpy().view(np.uint32), pk[1].numpy().view(np.uint32), pk[2].numpy().view(np.uint16))
+    pack_s = rig.time_host(lambda: engine_mod.pack_reads_host(reads_host.numpy().reshape(-1), offsets_host.numpy(), fold_case=True,
+                                                              out=pk_np), 2, 1)
+    out_packed = torch.empty((n, 16), dtype=torch.uint8, pin_memory=True)
+    opv = out_packed.numpy().view(_abi.MATCH_DTYPE).reshape(-1)
+    packed_s = rig.time_host(lambda: aset.locate_host_packed(pk_np[0], pk_np[1], pk_np[2], fold_case=True, out=opv), e2e_steps, 1)
+    assert np.array_equal(opv, out_host.numpy().view(_abi.MATCH_DTYPE).reshape(-1)), "packed and ASCII host entry points disagree"
+    plink = rig.link_roof(int(nwords * 4), int(16 * n))
+    e2e_packed = {"value": world * n / packed_s / 1e6, "unit": "M reads/s", "h2d_bytes_per_step": int(nwords * 4),
+                  "d2h_bytes_per_step": int(16 * n), "ms_per_step": packed_s * 1e3,
+                  "api": "atr_locate_batch_host_packed: reads packed in pinned host memory (4-bit codes), records back",
+                  "link_roof": dict(plink, M_reads_per_s=world * n / plink["seconds_per_step"] / 1e6),
+                  "host_packer": {"M_reads_per_s": world * n / pack_s / 1e6, "ms": pack_s * 1e3, "threads": os.cpu_count(),
+                                  "api": "atr_pack_reads_host (AVX2, one thread per core), ASCII -> packed, both in pinned host memory"},
+                  "including_host_packing": {"value": world * n / (pack_s + packed_s) / 1e6,
+                                             "note": "packer and packed call back to back, not overlapped"}}
+    del pk, out_packed
+
     # ---- FASTQ leg ("next" rows f-1/f-2/f-3): FASTQ text in pinned host memory -> atr_trim_fastq_host -> trimmed FASTQ
     # text + the report's statistics in host memory. Same reads; reader, trimming and formatting on the GPU. ----
     fq = None
@@ -576,6 +601,7 @@ def run_cfg2(rig, args):
         "e2e": {"value": e2e_value, "unit": "M reads/s", "h2d_bytes_per_step": int(n * L),      # fixed-length batch: the offsets are rebuilt on the device
                 "d2h_bytes_per_step": int(16 * n), "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
                 "api": "atr_locate_batch_host (Adapter.match_to_batch)", "link_roof": link},
+        "e2e_packed": e2e_packed,
         "e2e_fastq": fq,
         "strong_scaling": strong,
         "gpu_launches": int(launches),
