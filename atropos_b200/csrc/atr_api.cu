@@ -346,9 +346,7 @@ int insert_on_stream(atr_ctx* ctx, cudaStream_t st, const atr_insertset* set,
                      const uint8_t* a1, const int64_t* o1, int64_t base1,
                      const uint8_t* a2, const int64_t* o2, int64_t base2, int64_t n, atr_insert_result* d_out) {
     if (n <= 0) return ATR_OK;
-    // bounds that a 32-base look cannot exceed (rate x read length >= ATR_K2_INLINE_THR) take the other instantiation
-    if (set->kmax >= ATR_K2_INLINE_THR) k_insert_packed<true><<<grid_for(n, ATR_K2_THREADS), ATR_K2_THREADS, 0, st>>>(set->dev, c1, w1, l1, c2, w2, l2, n, d_out);
-    else k_insert_packed<false><<<grid_for(n, ATR_K2_THREADS), ATR_K2_THREADS, 0, st>>>(set->dev, c1, w1, l1, c2, w2, l2, n, d_out);
+    k_insert_packed<<<grid_for(n, ATR_K2_THREADS), ATR_K2_THREADS, 0, st>>>(set->dev, c1, w1, l1, c2, w2, l2, n, d_out);
     LAUNCHED(ctx);
     if (a1 && o1 && a2 && o2) {
         const unsigned g = (unsigned)std::min<int64_t>((n + 127) / 128, 148 * 8);

@@ -15,7 +15,7 @@
 #pragma once
 #include "atr_common.cuh"
 
-#define ATR_K2_MAXW 40             // packed fast path: reads up to 304 nt (38 words + 2 guard words)
+#define ATR_K2_MAXW 40             // packed fast path: reads up to 304 nt (38 4-bit words + 2 guard words)
 #define ATR_K2_MAXLEN 304
 #define ATR_MAX_CAND 100           // MultiAligner.locate(max_matches=100) (_align.pyx:593)
 
@@ -82,120 +82,154 @@ ATR_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, unsigned shift) {   // (hi:lo
 #endif
 }
 
-// Accessors give the pair's two sequences to the shared decision code.
-//   PackedPair: R/Q are per-thread word arrays with element w at [w * stride] (shared memory on the GPU)
-#ifndef ATR_K2_INLINE_THR
-#define ATR_K2_INLINE_THR 18
+// ---- the packed pair: 2-bit look-ahead filter + exact 4-bit verification ------------------------------------------
+// The sliding Hamming distance is evaluated for every overlap length j, and almost every j is a random alignment that
+// fails within a few bases. The scan therefore runs on a 2-BIT recoding of both sequences (A 0, C 1, G 2, T 3; N and
+// the other IUPAC codes fall on one of these): 16 bases per word, mismatches of 16 bases = one funnel shift, XOR,
+// fold, POPC. The recoding is a function of the 4-bit code, so differing 2-bit codes imply differing bases: the
+// 2-bit count is a LOWER BOUND of the true cost and never rejects a real candidate. An overlap that survives the
+// look-ahead (the first 16..80 bases, more where the error budget is larger) is verified with the exact 4-bit
+// comparison straight from the packed reads in global memory (the reverse complement of 8 bases is one __brev).
+//   rc(read2[:m]) in 2-bit words lives in shared memory ([word][thread]); the first 80 bases of read 1 in registers.
+#define ATR_K2_MAXW2 22            // 2-bit words of rc(read 2): 304 nt = 19 words + guard
+#define ATR_K2_QW 5                // look-ahead: up to 5 words = 80 bases
+
+ATR_HD uint32_t conv2(uint32_t w) {                   // 8 bases as 4-bit codes -> 16 bits of 2-bit codes
+    uint32_t t = ((w >> 1) | (w >> 3)) & 0x11111111u;
+    t |= (((w >> 2) | (w >> 3)) & 0x11111111u) << 1;
+    t = (t | (t >> 2)) & 0x0F0F0F0Fu;
+    t = (t | (t >> 4)) & 0x00FF00FFu;
+    return (t | (t >> 8)) & 0xFFFFu;
+}
+ATR_HD unsigned mism2(uint32_t x) {                   // differing 2-bit fields of x = a ^ b
+    x = (x | (x >> 1)) & 0x55555555u;
+#if defined(__CUDA_ARCH__)
+    return (unsigned)__popc(x);
+#else
+    return (unsigned)__builtin_popcount(x);
 #endif
-// INLINE_HIGH selects, at compile time, the scan that finishes high-bound overlaps inline (see scan_impl): the kernel
-// for insert sets whose bounds stay below ATR_K2_INLINE_THR keeps the leaner loop.
-template <bool INLINE_HIGH>
-struct PackedPairT {
-    uint32_t* R;            // rc(seq2[:m]) packed, >= W+2 words, zero padded
-    uint32_t* Q;            // seq1 packed (only the first m bases are looked at)
-    const uint32_t* S2;     // forward read2 packed (for the overhang)
+}
+// look-ahead words for an error budget: the expected 12 mismatches per random 16 bases must clear it by >= 3.5 sigma
+ATR_HD int k2_words_for(int bound) { return bound <= 6 ? 1 : bound <= 15 ? 2 : bound <= 24 ? 3 : bound <= 33 ? 4 : 5; }
+
+struct PackedPair {
+    uint32_t* R2;           // rc(seq2[:m]) in 2-bit words, element u at R2[u * stride], zero padded by 2 words
+    uint32_t q2[ATR_K2_QW]; // seq1[0:80] in 2-bit words
+    const uint32_t* S2;     // forward read2 packed (4-bit)
     const uint32_t* S1;
+    const unsigned short* thr;   // thr_ins (shared-memory copy in the kernel)
     int stride;
-    int m;
-    // Hamming(R[m-j:m], Q[0:j]) continued from whole word w0 (cost so far c0), abandoned once it exceeds `bound`
-    ATR_HD int overlap_cost(int j, int bound, int w0 = 0, unsigned c0 = 0) const {
+    int m, W, pad;
+    ATR_HD uint32_t rc_word(int i) const {             // word i of rc(seq2[:m]) in 4-bit codes; zero beyond the sequence
+        if (i >= W) return 0u;
+        uint32_t a = S2[W - 1 - i];
+        if (i == 0 && (m & 7)) a &= (1u << ((m & 7) * 4)) - 1u;              // drop bases beyond m in the last word
+        const uint32_t b = (i + 1 < W) ? S2[W - 2 - i] : 0u;
+        return funnel_r(brev32(a), brev32(b), (unsigned)pad * 4u);
+    }
+    // exact Hamming(rc2[m-j:m], seq1[0:j]), abandoned once it exceeds `bound`
+    ATR_HD int overlap_cost(int j, int bound) const {
         const int s = m - j, ws = s >> 3;
         const unsigned bs = (unsigned)(s & 7) * 4u;
-        const int nfull = j >> 3;                       // whole words
-        unsigned cost = c0;
-        int w = w0;
-        uint32_t lo = R[(ws + w) * stride];
+        const int nfull = j >> 3;
+        unsigned cost = 0;
+        int w = 0;
+        uint32_t lo = rc_word(ws);
         for (; w < nfull; w++) {
-            const uint32_t hi = R[(ws + w + 1) * stride];
-            cost += nib_mismatches(funnel_r(lo, hi, bs) ^ Q[w * stride]);
+            const uint32_t hi = rc_word(ws + w + 1);
+            cost += nib_mismatches(funnel_r(lo, hi, bs) ^ S1[w]);
             lo = hi;
             if ((int)cost > bound) return (int)cost;
         }
         if (j & 7) {
-            const uint32_t hi = R[(ws + w + 1) * stride];
-            const uint32_t x = (funnel_r(lo, hi, bs) ^ Q[w * stride]) & ((1u << ((j & 7) * 4)) - 1u);
+            const uint32_t hi = rc_word(ws + w + 1);
+            const uint32_t x = (funnel_r(lo, hi, bs) ^ S1[w]) & ((1u << ((j & 7) * 4)) - 1u);
             cost += nib_mismatches(x);
         }
         return (int)cost;
     }
-
+    // lower bound of the cost of overlap j from its first min(j, 32) bases
+    ATR_HD int small_lb(int j) const {
+        const int s = m - j, us = s >> 4;
+        const unsigned b2 = (unsigned)(s & 15) * 2u;
+        const uint32_t r0 = R2[us * stride], r1 = R2[(us + 1) * stride];
+        if (j <= 16) {
+            const uint32_t mask = j == 16 ? 0xFFFFFFFFu : ((1u << (2 * j)) - 1u);
+            return (int)mism2((funnel_r(r0, r1, b2) ^ q2[0]) & mask);
+        }
+        const uint32_t r2 = R2[(us + 2) * stride];
+        const uint32_t mask = j == 32 ? 0xFFFFFFFFu : ((1u << (2 * (j - 16))) - 1u);
+        return (int)(mism2(funnel_r(r0, r1, b2) ^ q2[0]) + mism2((funnel_r(r1, r2, b2) ^ q2[1]) & mask));
+    }
+    // 16 overlaps that share one 2-bit word offset `us` (shifts b = blo..bhi within the word), NW look-ahead words
+    template <int NW, class P>
+    ATR_HD void group(int us, int bhi, int blo, int k, int min_overlap, P&& park) const {
+        uint32_t r[NW + 1];
+#pragma unroll
+        for (int t = 0; t <= NW; t++) r[t] = R2[(us + t) * stride];
+#pragma unroll
+        for (int b = 15; b >= 0; b--) {                    // ascending overlap length
+            if (b > bhi || b < blo) continue;
+            unsigned c = 0;
+#pragma unroll
+            for (int t = 0; t < NW; t++) c += mism2(funnel_r(r[t], r[t + 1], 2u * (unsigned)b) ^ q2[t]);
+            const int j = m - (16 * us + b);
+            const int bound = atr_imin(k, (int)thr[j]);
+            if ((int)c <= bound && j >= min_overlap) park(j);
+        }
+    }
     // Enumerate the overlap lengths j = 1..m in ascending order and call emit(j, cost) for every j >= min_overlap
     // with cost <= min(k, thr[j]); emit returns false to stop (_align.pyx:722-745).
-    // Overlaps of >= 32 bases are handled in groups of 8 shifts that share the same word offset: the 5 words of
-    // rc(read2) a group needs and the first 4 words of read 1 stay in registers, the funnel shifts are static,
-    // and the first 16 or 32 bases are compared unconditionally (no per-word exit test, no shared-memory
-    // traffic). A random overlap is almost surely over its bound after that; only real overlaps continue with
-    // the word-by-word scan.
     template <class F>
     ATR_HD void scan(const InsertDev& d, int k, F&& emit) const {
         const int jsmall = m < 31 ? m : 31;
         for (int j = 1; j <= jsmall; j++) {
             if (j < d.min_insert_overlap) continue;
-            const int bound = atr_imin(k, (int)d.thr_ins[j]);
+            const int bound = atr_imin(k, (int)thr[j]);
+            if (small_lb(j) > bound) continue;
             const int cost = overlap_cost(j, bound);
             if (cost <= bound && !emit(j, cost)) return;
         }
         if (m < 32) return;
-        const uint32_t q0 = Q[0], q1 = Q[stride], q2 = Q[2 * stride], q3 = Q[3 * stride];
-        int g = (m - 32) >> 3;                         // word offset of the first (shortest) overlap handled here
-        int bstart = (m - 32) & 7;
-        uint32_t r0 = R[g * stride], r1 = R[(g + 1) * stride], r2 = R[(g + 2) * stride], r3 = R[(g + 3) * stride],
-                 r4 = R[(g + 4) * stride];
-        // Overlaps that survive the unconditional part are rare (the real one, plus noise): they are parked and
-        // finished after the loop, all lanes together, instead of one lane at a time in the middle of it.
-        // pend[] holds (j << 16 | words done << 8 | cost so far), in ascending j.
-        unsigned pend0 = 0, pend1 = 0, pend2 = 0, pend3 = 0;
+        // survivors of the look-ahead are rare (the real overlap, plus noise): they are parked and verified after the
+        // group, all lanes together, in ascending j
+        unsigned pend0 = 0, pend1 = 0, pend2 = 0, pend3 = 0;   // explicit slots: no local-memory array
         int npend = 0;
         bool go_on = true;
-        auto finish = [&](unsigned e) -> bool {        // complete one parked overlap; false = stop everything
-            const int j = (int)(e >> 16), wdone = (int)((e >> 8) & 255u);
-            const int bound = atr_imin(k, (int)d.thr_ins[j]);
-            const int full = overlap_cost(j, bound, wdone, e & 255u);
-            return !(full <= bound) || emit(j, full);
+        auto finish = [&](unsigned e) {
+            const int j = (int)e;
+            const int bound = atr_imin(k, (int)thr[j]);
+            const int full = overlap_cost(j, bound);
+            if (full <= bound) go_on = emit(j, full);
         };
-        auto flush = [&]() -> bool {
-            if (npend > 0 && !finish(pend0)) return false;
-            if (npend > 1 && !finish(pend1)) return false;
-            if (npend > 2 && !finish(pend2)) return false;
-            if (npend > 3 && !finish(pend3)) return false;
+        auto flush = [&]() {
+            if (npend > 0 && go_on) finish(pend0);
+            if (npend > 1 && go_on) finish(pend1);
+            if (npend > 2 && go_on) finish(pend2);
+            if (npend > 3 && go_on) finish(pend3);
             npend = 0;
-            return true;
         };
-        for (; g >= 0 && go_on; g--) {
-#pragma unroll
-            for (int b = 7; b >= 0; b--) {
-                if (b > bstart || !go_on) continue;
-                const int j = m - (8 * g + b);
-                const int tj = (int)d.thr_ins[j];
-                const int bound = atr_imin(k, tj);
-                unsigned cost = nib_mismatches(funnel_r(r0, r1, 4u * b) ^ q0) + nib_mismatches(funnel_r(r1, r2, 4u * b) ^ q1);
-                unsigned wdone = 2;
-                if (tj > 6) {                          // long overlaps tolerate more mismatches: look at 32 bases
-                    cost += nib_mismatches(funnel_r(r2, r3, 4u * b) ^ q2) + nib_mismatches(funnel_r(r3, r4, 4u * b) ^ q3);
-                    wdone = 4;
-                }
-                if (INLINE_HIGH && (int)cost <= bound && j >= d.min_insert_overlap && tj >= ATR_K2_INLINE_THR) {
-                    // A bound this high cannot be exceeded within 32 bases often enough (random bases mismatch at
-                    // 3/4: 24 +- 2.4 of 32), so nearly every lane would park nearly every overlap: finish it right
-                    // here, word by word with the exit test -- all lanes are in the same situation, so this does
-                    // not diverge. A real candidate is emitted after the parked (shorter) ones, in order.
-                    const int full = overlap_cost(j, bound, (int)wdone, cost);
-                    if (full <= bound) {
-                        go_on = flush();
-                        if (go_on) go_on = emit(j, full);
-                    }
-                } else if ((int)cost <= bound && j >= d.min_insert_overlap) {
-                    if (npend == 4) go_on = flush();   // full (low-complexity read): finish the parked ones in order
-                    if (go_on) {
-                        const unsigned e = ((unsigned)j << 16) | (wdone << 8) | cost;
-                        if (npend == 0) pend0 = e; else if (npend == 1) pend1 = e; else if (npend == 2) pend2 = e; else pend3 = e;
-                        npend++;
-                    }
-                }
+        auto park = [&](int j) {
+            if (npend == 4) flush();                           // full (low-complexity reads): verify the parked ones in order
+            if (go_on) {
+                if (npend == 0) pend0 = (unsigned)j; else if (npend == 1) pend1 = (unsigned)j;
+                else if (npend == 2) pend2 = (unsigned)j; else pend3 = (unsigned)j;
+                npend++;
             }
-            bstart = 7;
-            r4 = r3; r3 = r2; r2 = r1; r1 = r0;
-            if (g > 0) r0 = R[(g - 1) * stride];
+        };
+        const int s_first = m - 32;                            // shift of the shortest overlap handled here
+        for (int us = s_first >> 4; us >= 0 && go_on; us--) {
+            const int bhi = us == (s_first >> 4) ? (s_first & 15) : 15;
+            const int jmax = m - 16 * us;                       // the longest overlap of the group has the largest budget,
+            const int jmin = m - (16 * us + bhi);               // the shortest limits how far the look-ahead may reach
+            const int nw = atr_imin(k2_words_for(atr_imin(k, (int)thr[jmax])), jmin >> 4);
+            switch (nw) {
+                case 1: group<1>(us, bhi, 0, k, d.min_insert_overlap, park); break;
+                case 2: group<2>(us, bhi, 0, k, d.min_insert_overlap, park); break;
+                case 3: group<3>(us, bhi, 0, k, d.min_insert_overlap, park); break;
+                case 4: group<4>(us, bhi, 0, k, d.min_insert_overlap, park); break;
+                default: group<5>(us, bhi, 0, k, d.min_insert_overlap, park); break;
+            }
         }
         if (go_on) flush();
     }
@@ -204,7 +238,6 @@ struct PackedPairT {
     ATR_HD const uint32_t* fwd1() const { return S1; }
     ATR_HD const uint32_t* fwd2() const { return S2; }
 };
-typedef PackedPairT<false> PackedPair;
 
 
 struct BytePair {
@@ -354,34 +387,29 @@ ATR_HD void insert_pair(const InsertDev& d, const P& pr, bool packed, int m, int
     }
 }
 
-// Build the packed operands of a pair. S1/S2: forward packed reads; m = min(len1, len2).
+// Build the packed operands of a pair. S1/S2: forward packed reads (4-bit); m = min(len1, len2); W1 = words of read 1.
 // Returns 0 if read2[:m] contains code 0 ('X': reverse_complement raises KeyError) -> byte path decides.
-template <bool IH>
-ATR_HD int packed_pair_setup(PackedPairT<IH>& pp, const uint32_t* S1, const uint32_t* S2, int m) {
+ATR_HD int packed_pair_setup(PackedPair& pp, const uint32_t* S1, const uint32_t* S2, int m, int W1) {
     const int W = (m + 7) >> 3;
     const int st = pp.stride;
     int ok = 1;
-    // zero-nibble scan of read2[:m]
-    for (int w = 0; w < W; w++) {
-        uint32_t x = S2[w];
-        uint32_t valid = (w == W - 1 && (m & 7)) ? ((1u << ((m & 7) * 4)) - 1u) : 0xFFFFFFFFu;
+    for (int w = 0; w < W; w++) {                      // zero-nibble scan of read2[:m]
+        const uint32_t x = S2[w];
+        const uint32_t valid = (w == W - 1 && (m & 7)) ? ((1u << ((m & 7) * 4)) - 1u) : 0xFFFFFFFFu;
         uint32_t nz = x | (x >> 1); nz |= nz >> 2; nz &= valid & 0x11111111u;
         if (nz != (valid & 0x11111111u)) ok = 0;
     }
-    // reversed words: big[w] = brev(S2m[W-1-w]) holds rc of the 8W-nibble padded read; the m real
-    // bases start at nibble 8W - m -> shift right by that many nibbles
-    const int pad = 8 * W - m;                      // 0..7
-    const unsigned bs = (unsigned)pad * 4u;
-    for (int w = 0; w < W; w++) {
-        uint32_t a = S2[W - 1 - w];
-        if (w == 0 && (m & 7)) a &= (1u << ((m & 7) * 4)) - 1u;         // drop bases beyond m in the last word
-        uint32_t b = 0;
-        if (w + 1 < W) b = S2[W - 2 - w];
-        pp.R[w * st] = funnel_r(brev32(a), brev32(b), bs);
+    pp.S1 = S1; pp.S2 = S2; pp.m = m; pp.W = W; pp.pad = 8 * W - m;
+    // rc(read2[:m]): reversed words, each bit-reversed (A1<->T8, C2<->G4), shifted so that base 0 sits in nibble 0
+    const int U = (W + 1) >> 1;
+    for (int u = 0; u < U; u++) pp.R2[u * st] = conv2(pp.rc_word(2 * u)) | (conv2(pp.rc_word(2 * u + 1)) << 16);
+    pp.R2[U * st] = 0; pp.R2[(U + 1) * st] = 0;
+    if (U + 2 < ATR_K2_MAXW2) pp.R2[(U + 2) * st] = 0;
+#pragma unroll
+    for (int t = 0; t < ATR_K2_QW; t++) {
+        const uint32_t a = 2 * t < W1 ? S1[2 * t] : 0u, b = 2 * t + 1 < W1 ? S1[2 * t + 1] : 0u;
+        pp.q2[t] = conv2(a) | (conv2(b) << 16);
     }
-    pp.R[W * st] = 0; pp.R[(W + 1) * st] = 0;
-    for (int w = 0; w < W; w++) pp.Q[w * st] = S1[w];
-    pp.S1 = S1; pp.S2 = S2; pp.m = m;
     return ok;
 }
 

@@ -207,6 +207,23 @@ class FastqTrimmer(object):
         return out[:nout.value], stats, int(consumed.value)
 
 
+def open_fastq(path, mode="rb", compresslevel=6):
+    """Open a FASTQ file for the streaming helpers below by its suffix, like the reference's xopen
+    (atropos/io/compression.py:17-71, io/__init__.py:128-173): .gz (multi-member files included), .bz2, .xz / .lzma, else
+    plain. Decompression is host work (zlib); the text still crosses PCIe uncompressed."""
+    p = path.decode() if isinstance(path, bytes) else path
+    if p.endswith(".gz"):
+        import gzip
+        return gzip.open(p, mode, compresslevel=compresslevel) if "w" in mode else gzip.open(p, mode)
+    if p.endswith(".bz2"):
+        import bz2
+        return bz2.open(p, mode)
+    if p.endswith((".xz", ".lzma")):
+        import lzma
+        return lzma.open(p, mode)
+    return open(p, mode)
+
+
 def _stream_blocks(fh, block_bytes):
     while True:
         block = fh.read(block_bytes)
@@ -218,8 +235,8 @@ def _stream_blocks(fh, block_bytes):
 def trim_file(trimmer, src, dst, block_bytes=1 << 28):
     """Stream a FASTQ file through a FastqTrimmer block by block: the partial last record of a block is carried
     into the next one (`consumed`). src / dst: paths or binary file objects. Returns the accumulated TrimStats."""
-    fin = open(src, "rb") if isinstance(src, (str, bytes)) else src
-    fout = open(dst, "wb") if isinstance(dst, (str, bytes)) else dst
+    fin = open_fastq(src, "rb") if isinstance(src, (str, bytes)) else src
+    fout = open_fastq(dst, "wb") if isinstance(dst, (str, bytes)) else dst
     try:
         stats, carry = trimmer.new_stats(), b""
         for block in _stream_blocks(fin, block_bytes):
@@ -241,7 +258,7 @@ def trim_file_pair(trimmer, src1, src2, dst1, dst2, block_bytes=1 << 27):
 
     def _open(x, mode):
         if isinstance(x, (str, bytes)):
-            fh = open(x, mode)
+            fh = open_fastq(x, mode)
             opened.append(fh)
             return fh
         return x

@@ -162,3 +162,23 @@ def test_file_streaming_helpers(tmp_path):
     pstats = fastq.trim_file_pair(ptr, str(tmp_path / "in1.fq"), str(tmp_path / "in2.fq"), str(tmp_path / "o1.fq"),
                                   str(tmp_path / "o2.fq"), block_bytes=9973)
     fastq_cases.pe_check(pcase, ((tmp_path / "o1.fq").read_bytes(), (tmp_path / "o2.fq").read_bytes()), pstats)
+
+
+def test_compressed_files(tmp_path):
+    """trim_file / trim_file_pair on .gz (two members), .bz2 and .xz inputs and a .gz output == the plain-text run"""
+    import bz2
+    import gzip
+    import lzma
+    from atropos_b200 import fastq
+    case = [c for c in CASES if c["label"] == "ragged_lower_n"][0]
+    text = case["text"].encode("latin-1")
+    tr = fastq.FastqTrimmer(fastq_cases.adapters_of(case), times=case["times"])
+    want = case["result"]["out"].encode("latin-1")
+    cut = text.index(b"\n@", len(text) // 2) + 1
+    (tmp_path / "a.fq.gz").write_bytes(gzip.compress(text[:cut]) + gzip.compress(text[cut:]))
+    (tmp_path / "a.fq.bz2").write_bytes(bz2.compress(text))
+    (tmp_path / "a.fq.xz").write_bytes(lzma.compress(text))
+    for name in ("a.fq.gz", "a.fq.bz2", "a.fq.xz"):
+        st = fastq.trim_file(tr, str(tmp_path / name), str(tmp_path / "out.fq.gz"), block_bytes=20000)
+        assert gzip.open(tmp_path / "out.fq.gz").read() == want
+        assert st.records == case["result"]["records"] and st.with_adapters == case["result"]["with_adapters"]

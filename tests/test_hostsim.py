@@ -368,3 +368,37 @@ def test_qgram_filter_equals_shift_and(adapter, rate, min_overlap, step):
         assert sa == qg, (adapter, read, lo, hi, sa, qg)
         seen[sa[0]] += 1
     assert seen[0] > 100 and seen[2] > 100 and (seen[3] > 20 or len(set(adapter)) < 4 or "ACGTACGT" in adapter), seen
+
+
+@pytest.mark.parametrize("rate,L", [(0.25, 150), (0.5, 120), (0.9, 64), (0.2, 300), (0.05, 200)])
+def test_match_insert_lookahead_budgets(rate, L):
+    """the 2-bit look-ahead of the packed insert scan may never reach past the overlap (high rates: the budget of a short
+    overlap asks for more look-ahead words than the overlap has) and never rejects a real candidate (N, IUPAC codes and
+    low-complexity mates included): bit-exact against the oracle at error rates the benchmark does not touch"""
+    from atropos_b200 import synth
+    kw = dict(max_insert_mismatch_frac=rate, max_adapter_mismatch_frac=min(rate, 0.3))
+    d, keep = InsertAligner(T1, T2, **kw).descriptor(L)
+    orc = oracle.OracleInsertAligner(T1, T2, **kw)
+    r1, r2 = synth.synth_pe(220, L, seed=int(rate * 100) + L, device="cpu", sub=min(0.3, rate * 0.6), n_rate=0.01)
+    r1, r2 = r1.numpy(), r2.numpy()
+    rng = np.random.default_rng(int(rate * 1000) + L)
+    matched = 0
+    for i in range(220):
+        a, b = bytes(r1[i]).decode(), bytes(r2[i]).decode()
+        if i % 6 == 0:
+            a = ("ACN" * 150)[:int(rng.integers(33, L + 1))]
+            b = ("GTR" * 150)[:int(rng.integers(33, L + 1))]
+        elif i % 4 == 0:
+            a, b = a[:int(rng.integers(1, L + 1))], b[:int(rng.integers(1, L + 1))]
+        exp = orc.match_insert(a, b)
+        rec, used = hostsim.match_insert(d, a, b, 0)
+        assert used
+        st = int(rec["insert"]["status"])
+        if exp is None:
+            assert st == _abi.ATR_ST_NONE, (i, a, b)
+        else:
+            matched += 1
+            assert st == _abi.ATR_ST_MATCH and _tup(rec["insert"]) == exp[0], (i, a, b)
+            for e, g in ((exp[1], rec["match1"]), (exp[2], rec["match2"])):
+                assert (int(g["status"]) == _abi.ATR_ST_NONE) if e is None else (_tup(g) == e), i
+    assert matched > 25
