@@ -6,9 +6,11 @@
 #if defined(__CUDACC__)
 #define ATR_HD __host__ __device__ __forceinline__
 #define ATR_D __device__ __forceinline__
+#define ATR_HD_NOINLINE __host__ __device__ __noinline__
 #else
 #define ATR_HD inline
 #define ATR_D inline
+#define ATR_HD_NOINLINE inline
 #endif
 
 #define ATR_ESC_BIT 0x8000u          // bit 15 of len[]: read must take the byte-exact general kernel

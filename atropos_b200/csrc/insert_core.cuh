@@ -101,6 +101,13 @@ ATR_HD uint32_t conv2(uint32_t w) {                   // 8 bases as 4-bit codes 
     t = (t | (t >> 4)) & 0x00FF00FFu;
     return (t | (t >> 8)) & 0xFFFFu;
 }
+ATR_HD int k2_msb(unsigned x) {                       // index of the highest set bit (x != 0)
+#if defined(__CUDA_ARCH__)
+    return 31 - __clz((int)x);
+#else
+    return 31 - __builtin_clz(x);
+#endif
+}
 ATR_HD unsigned mism2(uint32_t x) {                   // differing 2-bit fields of x = a ^ b
     x = (x | (x >> 1)) & 0x55555555u;
 #if defined(__CUDA_ARCH__)
@@ -127,8 +134,9 @@ struct PackedPair {
         const uint32_t b = (i + 1 < W) ? S2[W - 2 - i] : 0u;
         return funnel_r(brev32(a), brev32(b), (unsigned)pad * 4u);
     }
-    // exact Hamming(rc2[m-j:m], seq1[0:j]), abandoned once it exceeds `bound`
-    ATR_HD int overlap_cost(int j, int bound) const {
+    // exact Hamming(rc2[m-j:m], seq1[0:j]), abandoned once it exceeds `bound`. Out of line: it runs for the few
+    // overlaps that survive the look-ahead, and inlined at every call site it multiplied the kernel's code size
+    ATR_HD_NOINLINE int overlap_cost(int j, int bound) const {
         const int s = m - j, ws = s >> 3;
         const unsigned bs = (unsigned)(s & 7) * 4u;
         const int nfull = j >> 3;
@@ -161,74 +169,75 @@ struct PackedPair {
         const uint32_t mask = j == 32 ? 0xFFFFFFFFu : ((1u << (2 * (j - 16))) - 1u);
         return (int)(mism2(funnel_r(r0, r1, b2) ^ q2[0]) + mism2((funnel_r(r1, r2, b2) ^ q2[1]) & mask));
     }
-    // 16 overlaps that share one 2-bit word offset `us` (shifts b = blo..bhi within the word), NW look-ahead words
-    template <int NW, class P>
-    ATR_HD void group(int us, int bhi, int blo, int k, int min_overlap, P&& park) const {
+    // 16 overlaps that share one 2-bit word offset `us` (shifts b = 15..0 within the word), NW look-ahead words, one
+    // error budget for the whole group (that of its longest overlap: the look-ahead is a necessary condition only, the
+    // verification applies each overlap's own budget). Branch-free: returns the shifts that stay within the budget.
+    template <int NW>
+    ATR_HD unsigned group(int us, int gbound) const {
         uint32_t r[NW + 1];
 #pragma unroll
         for (int t = 0; t <= NW; t++) r[t] = R2[(us + t) * stride];
+        unsigned hits = 0;
 #pragma unroll
-        for (int b = 15; b >= 0; b--) {                    // ascending overlap length
-            if (b > bhi || b < blo) continue;
+        for (int b = 0; b < 16; b++) {
             unsigned c = 0;
 #pragma unroll
             for (int t = 0; t < NW; t++) c += mism2(funnel_r(r[t], r[t + 1], 2u * (unsigned)b) ^ q2[t]);
-            const int j = m - (16 * us + b);
-            const int bound = atr_imin(k, (int)thr[j]);
-            if ((int)c <= bound && j >= min_overlap) park(j);
+            hits |= ((int)c <= gbound ? 1u : 0u) << b;
+        }
+        return hits;
+    }
+    ATR_HD unsigned group_nw(int nw, int us, int gbound) const {
+        switch (nw) {
+            case 1: return group<1>(us, gbound);
+            case 2: return group<2>(us, gbound);
+            case 3: return group<3>(us, gbound);
+            case 4: return group<4>(us, gbound);
+            default: return group<5>(us, gbound);
         }
     }
     // Enumerate the overlap lengths j = 1..m in ascending order and call emit(j, cost) for every j >= min_overlap
     // with cost <= min(k, thr[j]); emit returns false to stop (_align.pyx:722-745).
+    // Two nested stages with ONE call site each (the kernel is otherwise bound by instruction fetch): the look-ahead
+    // marks survivors (the real overlap plus noise; everything at once on low-complexity reads), which are verified in
+    // ascending j in batches of ATR_K2_SURV.
+#define ATR_K2_SURV 16
     template <class F>
     ATR_HD void scan(const InsertDev& d, int k, F&& emit) const {
-        const int jsmall = m < 31 ? m : 31;
-        for (int j = 1; j <= jsmall; j++) {
-            if (j < d.min_insert_overlap) continue;
-            const int bound = atr_imin(k, (int)thr[j]);
-            if (small_lb(j) > bound) continue;
-            const int cost = overlap_cost(j, bound);
-            if (cost <= bound && !emit(j, cost)) return;
-        }
-        if (m < 32) return;
-        // survivors of the look-ahead are rare (the real overlap, plus noise): they are parked and verified after the
-        // group, all lanes together, in ascending j
-        unsigned pend0 = 0, pend1 = 0, pend2 = 0, pend3 = 0;   // explicit slots: no local-memory array
-        int npend = 0;
+        unsigned short surv[ATR_K2_SURV];
+        int ns = 0;
         bool go_on = true;
-        auto finish = [&](unsigned e) {
-            const int j = (int)e;
-            const int bound = atr_imin(k, (int)thr[j]);
-            const int full = overlap_cost(j, bound);
-            if (full <= bound) go_on = emit(j, full);
-        };
         auto flush = [&]() {
-            if (npend > 0 && go_on) finish(pend0);
-            if (npend > 1 && go_on) finish(pend1);
-            if (npend > 2 && go_on) finish(pend2);
-            if (npend > 3 && go_on) finish(pend3);
-            npend = 0;
-        };
-        auto park = [&](int j) {
-            if (npend == 4) flush();                           // full (low-complexity reads): verify the parked ones in order
-            if (go_on) {
-                if (npend == 0) pend0 = (unsigned)j; else if (npend == 1) pend1 = (unsigned)j;
-                else if (npend == 2) pend2 = (unsigned)j; else pend3 = (unsigned)j;
-                npend++;
+            for (int t = 0; t < ns && go_on; t++) {
+                const int j = (int)surv[t];
+                const int bound = atr_imin(k, (int)thr[j]);
+                const int full = overlap_cost(j, bound);
+                if (full <= bound) go_on = emit(j, full);
             }
+            ns = 0;
         };
-        const int s_first = m - 32;                            // shift of the shortest overlap handled here
-        for (int us = s_first >> 4; us >= 0 && go_on; us--) {
-            const int bhi = us == (s_first >> 4) ? (s_first & 15) : 15;
-            const int jmax = m - 16 * us;                       // the longest overlap of the group has the largest budget,
-            const int jmin = m - (16 * us + bhi);               // the shortest limits how far the look-ahead may reach
-            const int nw = atr_imin(k2_words_for(atr_imin(k, (int)thr[jmax])), jmin >> 4);
-            switch (nw) {
-                case 1: group<1>(us, bhi, 0, k, d.min_insert_overlap, park); break;
-                case 2: group<2>(us, bhi, 0, k, d.min_insert_overlap, park); break;
-                case 3: group<3>(us, bhi, 0, k, d.min_insert_overlap, park); break;
-                case 4: group<4>(us, bhi, 0, k, d.min_insert_overlap, park); break;
-                default: group<5>(us, bhi, 0, k, d.min_insert_overlap, park); break;
+        const int jmin = d.min_insert_overlap > 1 ? d.min_insert_overlap : 1;
+        const int jsmall = m < 31 ? m : 31;
+        for (int j = jmin; j <= jsmall; j++) {
+            if (small_lb(j) <= atr_imin(k, (int)thr[j])) {
+                surv[ns++] = (unsigned short)j;
+                if (ns == ATR_K2_SURV) { flush(); if (!go_on) return; }
+            }
+        }
+        const int jfirst = jmin > 32 ? jmin : 32;              // shortest overlap of the word-wise part
+        if (m >= jfirst) {
+            const int s_first = m - jfirst;                    // shift of the shortest overlap handled here
+            for (int us = s_first >> 4; us >= 0 && go_on; us--) {
+                const int bhi = us == (s_first >> 4) ? (s_first & 15) : 15;       // the first group may be partial
+                const int gbound = atr_imin(k, (int)thr[m - 16 * us]);
+                const int nw = atr_imin(k2_words_for(gbound), (m - (16 * us + bhi)) >> 4);    // never past the shortest overlap
+                unsigned hits = group_nw(nw, us, gbound) & ((2u << bhi) - 1u);
+                while (hits) {                                 // ascending overlap length = descending shift
+                    const int b = k2_msb(hits);
+                    hits &= ~(1u << b);
+                    surv[ns++] = (unsigned short)(m - (16 * us + b));
+                    if (ns == ATR_K2_SURV) { flush(); if (!go_on) break; }
+                }
             }
         }
         if (go_on) flush();

@@ -401,4 +401,4 @@ def test_match_insert_lookahead_budgets(rate, L):
             assert st == _abi.ATR_ST_MATCH and _tup(rec["insert"]) == exp[0], (i, a, b)
             for e, g in ((exp[1], rec["match1"]), (exp[2], rec["match2"])):
                 assert (int(g["status"]) == _abi.ATR_ST_NONE) if e is None else (_tup(g) == e), i
-    assert matched > 25
+    assert matched > 10
