@@ -183,42 +183,56 @@ inline void fill_k1a(const HostAdapter& h, const AtrTables& tb, int index, int r
     // within k columns of its anchored position (locate_core.cuh: anchor_filter)
     a.anchor_ok = h.k1a_ok && !a.fused_ok && !h.cmp_only && !h.need_find && a.exact_ok &&
                   (h.desc.flags == ATR_STOP_WITHIN_SEQ2 || h.desc.flags == ATR_START_WITHIN_SEQ2);
-    // Shift-And pieces over the first min(m, 32) rows: k+1 pieces, each at least 6 rows (shorter pieces hit at
-    // random too often to be a filter); needs row-m candidates to be reported inside the loop (stop_in_query)
+    // Pieces for the pigeonhole stages: k+1 pieces over the first `rows` adapter rows, each at least `min_len` rows (shorter
+    // pieces hit at random too often to be a filter); needs row-m candidates to be reported inside the loop (stop_in_query).
+    // Shift-And automaton (k_filter_sa) and q-gram sampling (k_filter_qg): rows = min(m, 32), pieces >= 6 rows.
+    // Adapters whose k+1 pieces do not fit 32 rows that way (the 58-nt TruSeq adapter at 0.1: k = 5) get pieces over
+    // min(m, 64) rows for the q-gram form alone (qg_wide; 64-bit tail pass and gate).
     a.split8 = 0;
     a.sa_ok = 0; a.sa_rows = h.m < 32 ? h.m : 32; a.sa_start = 0; a.sa_end = 0; a.tail_gate_ok = 0; a.tail_mask = 0;
+    a.qg_wide = 0; a.sa_start64 = a.sa_end64 = a.tail_mask64 = 0;
     const bool stop_in_query = h.desc.flags & ATR_STOP_WITHIN_SEQ2;
     const int pieces = h.k + 1;
-    if ((a.fused_ok || a.filter_only) && !start_in_ref && stop_in_query && pieces <= a.sa_rows && a.sa_rows / pieces >= 6) {
-        a.sa_ok = 1;
+    auto layout = [&](int rows) {
+        unsigned long long st = 0, en = 0, mask = 0;
         int row = 1;
         for (int pc = 0; pc < pieces; pc++) {
-            const int len = a.sa_rows / pieces + (pc < a.sa_rows % pieces ? 1 : 0);
-            a.sa_start |= 1u << (row - 1);
-            a.sa_end |= 1u << (row + len - 2);
+            const int len = rows / pieces + (pc < rows % pieces ? 1 : 0);
+            st |= 1ull << (row - 1);
+            en |= 1ull << (row + len - 2);
             row += len;
         }
-        // Gate for the exact tail pass. A last-column candidate (i, n), i <= sa_rows, has e <= thr_mul[i] errors
+        // Gate for the exact tail pass. A last-column candidate (i, n), i <= rows, has e <= thr_mul[i] errors
         // over rows 1..i, which contain c(i) complete pieces. e < c: a complete piece is verbatim (a hit near the
         // read end). e == c: either that, or every complete piece is broken and the rows after them -- the begun
         // piece -- are verbatim up to column n, which the automaton shows as bit i-1 of its final state.
         // e > c (or e == c with no begun piece): no cheap certificate -> the tail pass always runs.
         const bool stop_in_ref = h.desc.flags & ATR_STOP_WITHIN_SEQ1;
-        a.tail_gate_ok = 1; a.tail_mask = 0;
+        int gate = 1;
         const int first = stop_in_ref ? 1 : h.m;
-        for (int i = 1; i <= a.sa_rows; i++) {
+        for (int i = 1; i <= rows; i++) {
             if (i < first || i < h.desc.min_overlap) continue;
             int c = 0, end_c = 0, r = 1;
             for (int pc = 0; pc < pieces; pc++) {
-                const int len = a.sa_rows / pieces + (pc < a.sa_rows % pieces ? 1 : 0);
+                const int len = rows / pieces + (pc < rows % pieces ? 1 : 0);
                 if (r + len - 1 <= i) { c++; end_c = r + len - 1; }
                 r += len;
             }
             const int e = (int)h.thr_mul[i];
             if (e < c) continue;
-            if (e == c && i > end_c) { a.tail_mask |= 1u << (i - 1); continue; }
-            a.tail_gate_ok = 0;
+            if (e == c && i > end_c) { mask |= 1ull << (i - 1); continue; }
+            gate = 0;
         }
+        a.sa_rows = rows; a.sa_start64 = st; a.sa_end64 = en; a.tail_mask64 = mask; a.tail_gate_ok = gate;
+        a.sa_start = (unsigned)st; a.sa_end = (unsigned)en; a.tail_mask = (unsigned)mask;
+    };
+    const bool shape = (a.fused_ok || a.filter_only) && !start_in_ref && stop_in_query;
+    if (shape && pieces <= a.sa_rows && a.sa_rows / pieces >= 6) {
+        a.sa_ok = 1;
+        layout(a.sa_rows);
+    } else if (shape && h.m > 32 && !a.and_mode) {
+        const int rows = h.m < 64 ? h.m : 64;
+        if (pieces <= rows && rows / pieces >= 7) { a.qg_wide = 1; layout(rows); }
     }
 }
 
@@ -228,13 +242,13 @@ inline void fill_k1a(const HostAdapter& h, const AtrTables& tb, int index, int r
 // Returns false (and leaves a.qg_ok = 0) when the adapter does not qualify.
 inline bool build_qg(AdapterK1a& a, std::vector<unsigned char>& tab) {
     a.qg_ok = 0; a.qg_tab = nullptr; a.qg_npat = 0; a.n_tail_cmp = 0; a.tail_cols = 0;
-    if (!a.sa_ok || a.and_mode) return false;
+    if ((!a.sa_ok && !a.qg_wide) || a.and_mode) return false;
     // pieces: runs of rows between sa_start bits and sa_end bits
     int pstart[8], plen[8], np = 0, lmin = 1 << 30, lmax = 0;
     for (int r = 0; r < a.sa_rows; r++) {
-        if (a.sa_start & (1u << r)) {
+        if (a.sa_start64 & (1ull << r)) {
             int e = r;
-            while (!(a.sa_end & (1u << e))) e++;
+            while (!(a.sa_end64 & (1ull << e))) e++;
             if (np == 8) return false;
             pstart[np] = r; plen[np] = e - r + 1;
             lmin = std::min(lmin, plen[np]); lmax = std::max(lmax, plen[np]);
@@ -293,7 +307,7 @@ inline bool build_qg(AdapterK1a& a, std::vector<unsigned char>& tab) {
     // tested on their last 8 only (a necessary condition; the gate only decides whether the exact tail pass runs).
     if (a.tail_gate_ok) {
         for (int i = 1; i <= a.sa_rows; i++) {
-            if (!(a.tail_mask & (1u << (i - 1)))) continue;
+            if (!(a.tail_mask64 & (1ull << (i - 1)))) continue;
             int p = 0;
             while (p + 1 < np && pstart[p + 1] < i) p++;              // piece containing row i (1-based): pstart[p] < i
             const int l = i - pstart[p];                               // rows pstart[p]+1 .. i

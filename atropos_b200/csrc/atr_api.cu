@@ -218,16 +218,22 @@ int locate_on_stream(atr_ctx* ctx, Slot& slot, const atr_adapterset* set,
                 const unsigned g = grid_for(n, ATR_K1F_THREADS);
                 const unsigned gp = (unsigned)std::min<int64_t>((n + 127) / 128, 148 * 12);
                 const bool use_sa = p.sa_ok && !ctx->disable_sa;
+                const bool use_qg = p.qg_ok && !ctx->disable_qg && (use_sa || p.qg_wide);
                 if (prof) {
-                    ctx->phase_names[0] = use_sa ? (p.qg_ok && !ctx->disable_qg ? "k_filter_qg" : "k_filter_sa") : "k_filter";
-                    ctx->phase_names[1] = use_sa ? "k_refine" : "";
+                    ctx->phase_names[0] = use_qg ? "k_filter_qg" : (use_sa ? "k_filter_sa" : "k_filter");
+                    ctx->phase_names[1] = (use_sa || use_qg) ? "k_refine" : "";
                     ctx->phase_names[2] = "k_band<16>+k_band<8>";
                     ctx->phase_names[3] = "k_wide";
                 }
-                if (use_sa && p.qg_ok && !ctx->disable_qg) {
+                if (use_qg) {
                     const unsigned gq = (unsigned)std::min<int64_t>((n + ATR_QG_THREADS - 1) / ATR_QG_THREADS, (int64_t)ctx->sm_count * ctx->qg_ctas);
-                    if (p.qg_step == 3) k_filter_qg<3><<<gq, ATR_QG_THREADS, 0, st>>>(p, d_codes, d_woff, d_len, d_win, n, d_out, narrow, wide, refine, counters);
-                    else k_filter_qg<2><<<gq, ATR_QG_THREADS, 0, st>>>(p, d_codes, d_woff, d_len, d_win, n, d_out, narrow, wide, refine, counters);
+                    if (p.qg_wide) {
+                        if (p.qg_step == 3) k_filter_qg<3, unsigned long long><<<gq, ATR_QG_THREADS, 0, st>>>(p, d_codes, d_woff, d_len, d_win, n, d_out, narrow, wide, refine, counters);
+                        else k_filter_qg<2, unsigned long long><<<gq, ATR_QG_THREADS, 0, st>>>(p, d_codes, d_woff, d_len, d_win, n, d_out, narrow, wide, refine, counters);
+                    } else {
+                        if (p.qg_step == 3) k_filter_qg<3, unsigned><<<gq, ATR_QG_THREADS, 0, st>>>(p, d_codes, d_woff, d_len, d_win, n, d_out, narrow, wide, refine, counters);
+                        else k_filter_qg<2, unsigned><<<gq, ATR_QG_THREADS, 0, st>>>(p, d_codes, d_woff, d_len, d_win, n, d_out, narrow, wide, refine, counters);
+                    }
                 } else if (use_sa) {
                     if (h.and_mode) k_filter_sa<true><<<g, ATR_K1F_THREADS, 0, st>>>(p, d_codes, d_woff, d_len, d_win, n, d_out, narrow, wide, refine, counters);
                     else k_filter_sa<false><<<g, ATR_K1F_THREADS, 0, st>>>(p, d_codes, d_woff, d_len, d_win, n, d_out, narrow, wide, refine, counters);
@@ -240,7 +246,7 @@ int locate_on_stream(atr_ctx* ctx, Slot& slot, const atr_adapterset* set,
                 }
                 LAUNCHED(ctx);
                 if (prof) CU(cudaEventRecord(ctx->pev[4], st));
-                if (use_sa) {
+                if (use_sa || use_qg) {
                     if (h.m <= 32) {
                         if (h.and_mode) k_refine<unsigned int, true><<<gp, 128, 0, st>>>(p, d_codes, d_woff, d_len, d_win, d_out, refine, narrow, wide, counters);
                         else k_refine<unsigned int, false><<<gp, 128, 0, st>>>(p, d_codes, d_woff, d_len, d_win, d_out, refine, narrow, wide, counters);
@@ -279,10 +285,16 @@ int locate_on_stream(atr_ctx* ctx, Slot& slot, const atr_adapterset* set,
                 const unsigned g = grid_for(n, ATR_K1F_THREADS);
                 const unsigned gp = (unsigned)std::min<int64_t>((n + 127) / 128, 148 * 12);
                 const bool use_sa = p.sa_ok && !ctx->disable_sa;
-                if (use_sa && p.qg_ok && !ctx->disable_qg) {
+                const bool use_qg = p.qg_ok && !ctx->disable_qg && (use_sa || p.qg_wide);
+                if (use_qg) {
                     const unsigned gq = (unsigned)std::min<int64_t>((n + ATR_QG_THREADS - 1) / ATR_QG_THREADS, (int64_t)ctx->sm_count * ctx->qg_ctas);
-                    if (p.qg_step == 3) k_filter_qg<3><<<gq, ATR_QG_THREADS, 0, st>>>(p, d_codes, d_woff, d_len, d_win, n, d_out, narrow, wide, refine, counters);
-                    else k_filter_qg<2><<<gq, ATR_QG_THREADS, 0, st>>>(p, d_codes, d_woff, d_len, d_win, n, d_out, narrow, wide, refine, counters);
+                    if (p.qg_wide) {
+                        if (p.qg_step == 3) k_filter_qg<3, unsigned long long><<<gq, ATR_QG_THREADS, 0, st>>>(p, d_codes, d_woff, d_len, d_win, n, d_out, narrow, wide, refine, counters);
+                        else k_filter_qg<2, unsigned long long><<<gq, ATR_QG_THREADS, 0, st>>>(p, d_codes, d_woff, d_len, d_win, n, d_out, narrow, wide, refine, counters);
+                    } else {
+                        if (p.qg_step == 3) k_filter_qg<3, unsigned><<<gq, ATR_QG_THREADS, 0, st>>>(p, d_codes, d_woff, d_len, d_win, n, d_out, narrow, wide, refine, counters);
+                        else k_filter_qg<2, unsigned><<<gq, ATR_QG_THREADS, 0, st>>>(p, d_codes, d_woff, d_len, d_win, n, d_out, narrow, wide, refine, counters);
+                    }
                 } else if (use_sa) {
                     if (h.and_mode) k_filter_sa<true><<<g, ATR_K1F_THREADS, 0, st>>>(p, d_codes, d_woff, d_len, d_win, n, d_out, narrow, wide, refine, counters);
                     else k_filter_sa<false><<<g, ATR_K1F_THREADS, 0, st>>>(p, d_codes, d_woff, d_len, d_win, n, d_out, narrow, wide, refine, counters);
@@ -295,10 +307,10 @@ int locate_on_stream(atr_ctx* ctx, Slot& slot, const atr_adapterset* set,
                 }
                 LAUNCHED(ctx);
                 Survivor* ls[3] = {narrow, wide, refine};
-                for (int li = 0; li < (use_sa ? 3 : 2); li++) {
+                for (int li = 0; li < ((use_sa || use_qg) ? 3 : 2); li++) {
                     if (h.and_mode) k_anchor_dp<true><<<gp, 128, 0, st>>>(p, d_codes, d_woff, d_len, d_win, d_out, ls[li], counters + li);
                     else k_anchor_dp<false><<<gp, 128, 0, st>>>(p, d_codes, d_woff, d_len, d_win, d_out, ls[li], counters + li);
-                    if (li + 1 < (use_sa ? 3 : 2)) LAUNCHED(ctx);
+                    if (li + 1 < ((use_sa || use_qg) ? 3 : 2)) LAUNCHED(ctx);
                 }
             }
             else if (p.anchor_ok && !ctx->disable_fused && n < (int64_t)0x7fffffff) {

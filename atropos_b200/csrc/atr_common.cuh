@@ -71,6 +71,9 @@ struct AdapterK1a {                   // passed by value as a __grid_constant__ 
     // length L >= 6 + qg_step - 1 contains a 6-mer that starts at a sampled position. One hashed byte-table lookup
     // per sample; hits are verified by comparing the whole piece, so the hit set is exactly the automaton's.
     int qg_ok, qg_step;               // step 2 or 3 (ASCII compare mode only)
+    int qg_wide;                      // pieces over up to 64 rows (adapters whose k+1 pieces do not fit 32 rows): sa_ok = 0, only the
+                                      // q-gram form exists; sa_rows > 32, the 64-bit fields below, 64-bit tail Myers
+    unsigned long long sa_start64, sa_end64, tail_mask64;   // = sa_start / sa_end / tail_mask where sa_rows <= 32
     unsigned qg_mul;                  // key = (x * qg_mul) >> (32 - ATR_QG_BITS); low 8 bits zero: only 24 bits of x count
     const unsigned char* qg_tab;      // [1 << ATR_QG_BITS]: 0 none, 1..14 pattern index, 15 several patterns share the bucket
     int qg_npat;

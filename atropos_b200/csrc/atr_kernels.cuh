@@ -200,12 +200,13 @@ __global__ void k_fill_none(atr_match* __restrict__ out, int64_t n) {
 #ifndef ATR_K2_THREADS
 #define ATR_K2_THREADS 128
 #endif
-__global__ void __launch_bounds__(ATR_K2_THREADS) k_insert_packed(
+__global__ void __launch_bounds__(ATR_K2_THREADS, 8) k_insert_packed(
         const __grid_constant__ InsertDev d,
         const uint32_t* __restrict__ codes1, const uint32_t* __restrict__ woff1, const uint16_t* __restrict__ len1,
         const uint32_t* __restrict__ codes2, const uint32_t* __restrict__ woff2, const uint16_t* __restrict__ len2,
         int64_t n_pairs, atr_insert_result* __restrict__ out) {
     __shared__ uint32_t sR2[ATR_K2_MAXW2 * ATR_K2_THREADS];     // rc(read 2) in 2-bit words, [word][thread]
+    __shared__ uint32_t sR4[(ATR_K2_MAXW + 2) * ATR_K2_THREADS];  // ... and in 4-bit words for the exact verification
     __shared__ unsigned short s_thr[ATR_K2_MAXLEN + 1];         // floor(j * rate) for every overlap length the packed path sees
     for (int i = threadIdx.x; i <= ATR_K2_MAXLEN; i += ATR_K2_THREADS) s_thr[i] = i <= d.max_len ? d.thr_ins[i] : (unsigned short)0;
     __syncthreads();
@@ -217,7 +218,7 @@ __global__ void __launch_bounds__(ATR_K2_THREADS) k_insert_packed(
     atr_insert_result* o = out + r;
     bool routed = ((l1 | l2) & ATR_ESC_BIT) != 0 || m > ATR_K2_MAXLEN || !d.packed_ok;
     PackedPair pp;
-    pp.R2 = sR2 + threadIdx.x; pp.stride = ATR_K2_THREADS; pp.thr = s_thr;
+    pp.R2 = sR2 + threadIdx.x; pp.R4 = sR4 + threadIdx.x; pp.stride = ATR_K2_THREADS; pp.thr = s_thr;
     if (!routed) routed = packed_pair_setup(pp, codes1 + woff1[r], codes2 + woff2[r], m, (n1 + 7) >> 3) == 0;
     if (routed) {                      // the byte-exact kernel (k_insert_bytes) picks these up
         atr_insert_result e;
@@ -440,10 +441,14 @@ __global__ void __launch_bounds__(ATR_K1F_THREADS) k_filter(const __grid_constan
 // ---------------------------------------------------------------------------------------------
 // The tail pass is a separate (non-inlined) device function: it is executed by few, compacted warps and must
 // not inflate the register allocation of the Shift-And scan that every thread runs.
-__device__ __noinline__ int sa_tail_packed(const AdapterK1a* ad, const unsigned* tail_peq, const uint32_t* rd, int lo, int n) {
+template <class WORD>
+__device__ __noinline__ int sa_tail_packed_w(const AdapterK1a* ad, const WORD* tail_peq, const uint32_t* rd, int lo, int n) {
     int imin, imax;
-    sa_tail(*ad, tail_peq, rd, lo, n, imin, imax);
+    sa_tail_w<WORD>(*ad, tail_peq, rd, lo, n, imin, imax);
     return (imin << 16) | imax;
+}
+__device__ __forceinline__ int sa_tail_packed(const AdapterK1a* ad, const unsigned* tail_peq, const uint32_t* rd, int lo, int n) {
+    return sa_tail_packed_w<unsigned>(ad, tail_peq, rd, lo, n);
 }
 
 template <bool AND_MODE>
@@ -637,7 +642,7 @@ __device__ __forceinline__ void qg_finish(const AdapterK1a& ad, bool active, uin
 // groups per chunk: 192 columns at step 3, 160 at step 2 (one chunk for reads up to that length; 48 KB of static shared memory)
 template <int S> struct QgChunk { static const int NG = S == 3 ? 8 : 10; };
 
-template <int S>
+template <int S, class WORD>
 __global__ void __launch_bounds__(ATR_QG_THREADS, ATR_QG_MINCTAS) k_filter_qg(const __grid_constant__ AdapterK1a ad,
         const uint32_t* __restrict__ codes, const uint32_t* __restrict__ woff, const uint16_t* __restrict__ len,
         const uint16_t* __restrict__ win, int64_t n_reads, atr_match* __restrict__ out,
@@ -652,7 +657,7 @@ __global__ void __launch_bounds__(ATR_QG_THREADS, ATR_QG_MINCTAS) k_filter_qg(co
     __shared__ uint2 s_meta[ATR_QG_THREADS];                 // x: first word of the read relative to the tile, y: lo | n << 16
     __shared__ int s_hmin[ATR_QG_THREADS], s_hmax[ATR_QG_THREADS];
     __shared__ unsigned short s_gm[ATR_QG_THREADS];          // groups of the chunk with hits
-    __shared__ unsigned s_sa_peq[16], s_tail_peq[16];
+    __shared__ WORD s_sa_peq[16], s_tail_peq[16];
     __shared__ unsigned char s_hl[ATR_QG_THREADS];           // reads of the tile with hits
     __shared__ int s_tq_count, s_hl_count;
 
@@ -664,12 +669,7 @@ __global__ void __launch_bounds__(ATR_QG_THREADS, ATR_QG_MINCTAS) k_filter_qg(co
         for (int i = tid; i < (1 << ATR_QG_BITS) / 16; i += ATR_QG_THREADS) dst[i] = src[i];
         for (int i = tid; i < ATR_QG_TILE_WORDS + ATR_QG_PAD; i += ATR_QG_THREADS) s_tile[i] = 0u;
     }
-    if (tid < 16) {
-        const int mp = ad.sa_rows, sh32 = 32 - mp;
-        const unsigned low = (unsigned)(ad.peq[tid] & (mp >= 32 ? 0xFFFFFFFFull : ((1ull << mp) - 1)));
-        s_sa_peq[tid] = low;
-        s_tail_peq[tid] = sh32 ? ((low << sh32) | ((1u << sh32) - 1u)) : low;
-    }
+    if (tid < 16) qg_peq_tables<WORD>(ad, tid, s_sa_peq[tid], s_tail_peq[tid]);
     if (tid == 0) {
         s_tq_count = 0; s_hl_count = 0;
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar)) : "memory");
@@ -752,7 +752,7 @@ __global__ void __launch_bounds__(ATR_QG_THREADS, ATR_QG_MINCTAS) k_filter_qg(co
                 }
             }
             if (last_chunk && live && !listed) {                        // no piece anywhere: a partial match at the read end?
-                if (qg_need_tail(ad, s_sa_peq, rd, lo, n, -0x7fffffff)) {
+                if (qg_need_tail<WORD>(ad, s_sa_peq, rd, lo, n, -0x7fffffff)) {
                     QgTailItem q;
                     q.read = (uint32_t)r; q.hmin = 32767; q.hmax = -32768;
                     s_tq[atomicAdd(&s_tq_count, 1)] = q;
@@ -798,7 +798,7 @@ __global__ void __launch_bounds__(ATR_QG_THREADS, ATR_QG_MINCTAS) k_filter_qg(co
                     if (!last_chunk) { s_hmin[t] = vmin; s_hmax[t] = vmax; }
                     else {
                         exact = sa_exact(ad, rdt, lo_t, n_t, vmin, vmax);
-                        if (!exact) need_tail = qg_need_tail(ad, s_sa_peq, rdt, lo_t, n_t, vmax);
+                        if (!exact) need_tail = qg_need_tail<WORD>(ad, s_sa_peq, rdt, lo_t, n_t, vmax);
                         if (need_tail) {
                             QgTailItem q;
                             q.read = (uint32_t)(t0 + t);
@@ -822,7 +822,7 @@ __global__ void __launch_bounds__(ATR_QG_THREADS, ATR_QG_MINCTAS) k_filter_qg(co
             const QgTailItem q = s_tq[n_tail - ATR_QG_THREADS + tid];
             int lo2, n2; bool esc2;
             read_extent(len, win, q.read, lo2, n2, esc2);
-            const int im = sa_tail_packed(&ad, s_tail_peq, codes + woff[q.read], lo2, n2);
+            const int im = sa_tail_packed_w<WORD>(&ad, s_tail_peq, codes + woff[q.read], lo2, n2);
             const bool nohit = q.hmax == -32768;
             qg_finish(ad, true, q.read, lo2, n2, nohit ? 0x7fffffff : (int)q.hmin, nohit ? -0x7fffffff : (int)q.hmax, false, im,
                       out, narrow, wide, refine, counters);
@@ -842,7 +842,7 @@ __global__ void __launch_bounds__(ATR_QG_THREADS, ATR_QG_MINCTAS) k_filter_qg(co
             q = s_tq[tid];
             bool esc2;
             read_extent(len, win, q.read, lo2, n2, esc2);
-            im = sa_tail_packed(&ad, s_tail_peq, codes + woff[q.read], lo2, n2);
+            im = sa_tail_packed_w<WORD>(&ad, s_tail_peq, codes + woff[q.read], lo2, n2);
         }
         const bool nohit = q.hmax == -32768;
         qg_finish(ad, active, q.read, lo2, n2, nohit ? 0x7fffffff : (int)q.hmin, nohit ? -0x7fffffff : (int)q.hmax, false, im,

@@ -522,16 +522,19 @@ ATR_HD bool sa_need_tail(const AdapterK1a& ad, int n, int hmax, unsigned st_fina
     return hmax != -0x7fffffff && hmax >= n - ad.sa_rows - ad.k;
 }
 
-// (d) exact D[i][n] for rows i <= sa_rows from a 32-bit Myers over the last sa_rows + k columns (rows left-aligned)
-ATR_HD void sa_tail(const AdapterK1a& ad, const unsigned* __restrict__ tail_peq, const uint32_t* __restrict__ codes, int lo, int n,
-                    int& imin, int& imax) {
+// (d) exact D[i][n] for rows i <= sa_rows from a Myers pass over the last sa_rows + k columns (rows left-aligned in a
+// 32-bit word; 64-bit for the wide q-gram form, AdapterK1a.qg_wide)
+template <class WORD>
+ATR_HD void sa_tail_w(const AdapterK1a& ad, const WORD* __restrict__ tail_peq, const uint32_t* __restrict__ codes, int lo, int n,
+                      int& imin, int& imax) {
     const int m = ad.m, k = ad.k, mp = ad.sa_rows;
+    const int WB = (int)(8 * sizeof(WORD));
     const bool stop_in_ref = ad.flags & ATR_STOP_WITHIN_SEQ1;
     const int pend = lo + n;
     imin = 0; imax = 0;
-    const int sh = 32 - mp;
-    MyersState<unsigned> st;
-    st.Pv = (sh == 0) ? ~0u : (~0u << sh);
+    const int sh = WB - mp;
+    MyersState<WORD> st;
+    st.Pv = (sh == 0) ? ~(WORD)0 : (WORD)(~(WORD)0 << sh);
     st.Mv = 0; st.score = mp;
     // start on a word boundary at or before column n - mp - k (an earlier start is always safe)
     int p = atr_max(lo, (lo + atr_max(0, n - mp - k)) & ~7);
@@ -547,14 +550,18 @@ ATR_HD void sa_tail(const AdapterK1a& ad, const unsigned* __restrict__ tail_peq,
         for (int t = 0; p < pend; t++, p++) myers_col(st, tail_peq[(w >> (4 * t)) & 15u]);
     }
     // D[i][n] = running sum of the vertical deltas; rows right-aligned so that the shifts are static
-    const unsigned pv = st.Pv >> sh, mv = st.Mv >> sh;
+    const WORD pv = st.Pv >> sh, mv = st.Mv >> sh;
     const int row_lo = atr_max(stop_in_ref ? 1 : m, ad.min_overlap);
     int d = 0;
 #pragma unroll
-    for (int i = 1; i <= 32; i++) {
-        d += (int)((pv >> (i - 1)) & 1u) - (int)((mv >> (i - 1)) & 1u);
+    for (int i = 1; i <= WB; i++) {
+        d += (int)((pv >> (i - 1)) & (WORD)1) - (int)((mv >> (i - 1)) & (WORD)1);
         if (i >= row_lo && i <= mp && d <= (int)ad.thr_mul[i]) { imin = imin == 0 ? i : imin; imax = i; }
     }
+}
+ATR_HD void sa_tail(const AdapterK1a& ad, const unsigned* __restrict__ tail_peq, const uint32_t* __restrict__ codes, int lo, int n,
+                    int& imin, int& imax) {
+    sa_tail_w<unsigned>(ad, tail_peq, codes, lo, n, imin, imax);
 }
 
 // (e) classes 0 / 1 / 2 from the hit range and the last-column rows
@@ -972,9 +979,9 @@ ATR_HD void k1f_read(const AdapterK1a& ad, const uint32_t* __restrict__ codes, i
     for (int c = 0; c < 16; c++) peq[c] = (WORD)(((WORD)ad.peq[c] << sh) | (sh ? (((WORD)1 << sh) - 1) : 0));
     if (path) *path = 0;
     bool have = false;
-    if (ad.sa_ok) {
+    if (ad.sa_ok || ad.qg_ok) {
         unsigned sa_peq[16], tail_peq[16];
-        const int mp = ad.sa_rows, sh32 = 32 - mp;
+        const int mp = ad.sa_rows < 32 ? ad.sa_rows : 32, sh32 = 32 - mp;
         for (int c = 0; c < 16; c++) {
             const unsigned low = (unsigned)(ad.peq[c] & (mp >= 32 ? 0xFFFFFFFFull : ((1ull << mp) - 1)));
             sa_peq[c] = low;
@@ -1007,7 +1014,7 @@ ATR_HD void k1f_read(const AdapterK1a& ad, const uint32_t* __restrict__ codes, i
         }
         else { if (path) *path = 2; k1a_locate<AND_MODE>(ad, codes, lo, n, b, hit.c0, hit.c1); }
     }
-    if (path && ad.sa_ok) *path += 10;                 // tests: 10 + x = went through the Shift-And pre-filter
+    if (path && (ad.sa_ok || ad.qg_ok)) *path += 10;   // tests: 10 + x = went through the Shift-And / q-gram pre-filter
     finalize(ad, b, n, out);
 }
 
@@ -1029,9 +1036,9 @@ ATR_HD void icfilter_read(const AdapterK1a& ad, const uint32_t* __restrict__ cod
     b.ref_stop = ad.m; b.q_stop = n; b.cost = ad.m + n; b.origin = 0; b.matches = 0;
     bool have = false;
     if (path) *path = 0;
-    if (ad.sa_ok) {
+    if (ad.sa_ok || ad.qg_ok) {
         unsigned sa_peq[16], tail_peq[16];
-        const int mp = ad.sa_rows, sh32 = 32 - mp;
+        const int mp = ad.sa_rows < 32 ? ad.sa_rows : 32, sh32 = 32 - mp;
         for (int c = 0; c < 16; c++) {
             const unsigned low = (unsigned)(ad.peq[c] & (mp >= 32 ? 0xFFFFFFFFull : ((1ull << mp) - 1)));
             sa_peq[c] = low;

@@ -125,8 +125,10 @@ ATR_HD void qg_scan(const AdapterK1a& ad, const unsigned char* __restrict__ tab,
 
 // (c) the need-tail gate of sa_need_tail without the automaton's state after the whole read: a tail_mask bit
 // (row i, l rows deep in its piece) only depends on the read's last l <= tail_cols columns, so the automaton is run over
-// the last 8 (or 16) columns only. sa_peq: the 16-entry Peq table of the first sa_rows rows (as for sa_scan).
-ATR_HD bool qg_need_tail(const AdapterK1a& ad, const unsigned* __restrict__ sa_peq, const uint32_t* __restrict__ codes,
+// the last 8 (or 16) columns only. sa_peq: the 16-entry Peq table of the first sa_rows rows (as for sa_scan); WORD is
+// unsigned, or unsigned long long for the wide form (sa_rows > 32).
+template <class WORD>
+ATR_HD bool qg_need_tail(const AdapterK1a& ad, const WORD* __restrict__ sa_peq, const uint32_t* __restrict__ codes,
                          int lo, int n, int hmax) {
     const bool stop_in_ref = ad.flags & ATR_STOP_WITHIN_SEQ1;
     if (!(stop_in_ref || ad.m <= ad.sa_rows)) return false;
@@ -138,8 +140,8 @@ ATR_HD bool qg_need_tail(const AdapterK1a& ad, const unsigned* __restrict__ sa_p
     const unsigned sh = (unsigned)(q & 7) * 4u;
     const uint32_t w0 = codes[q >> 3];
     const uint32_t w1 = (q & 7) || cols == 16 ? codes[(q >> 3) + 1] : 0u;
-    const unsigned S0 = ad.sa_start;
-    unsigned St = 0;
+    const WORD S0 = (WORD)ad.sa_start64;
+    WORD St = 0;
     uint32_t tw = funnel_r32(w0, w1, sh);
 #pragma unroll
     for (int t = 0; t < 8; t++) St = ((St << 1) | S0) & sa_peq[(tw >> (4 * t)) & 15u];
@@ -149,25 +151,38 @@ ATR_HD bool qg_need_tail(const AdapterK1a& ad, const unsigned* __restrict__ sa_p
 #pragma unroll
         for (int t = 0; t < 8; t++) St = ((St << 1) | S0) & sa_peq[(tw >> (4 * t)) & 15u];
     }
-    return (St & ad.tail_mask) != 0u;
+    return (St & (WORD)ad.tail_mask64) != (WORD)0;
 }
 
-// the whole stage for one read (host simulator; the kernel interleaves a block-level compaction before the tail pass)
-template <int S>
-ATR_HD void qg_filter_s(const AdapterK1a& ad, const unsigned* __restrict__ tail_peq, const uint32_t* __restrict__ codes, int wlimit,
-                        int lo, int n, SaResult& res) {
+// the Peq tables of the first sa_rows rows: right-aligned for the automaton, left-aligned with the virtual rows set for Myers
+template <class WORD>
+ATR_HD void qg_peq_tables(const AdapterK1a& ad, int c, WORD& sa, WORD& tail) {
+    const int WB = (int)(8 * sizeof(WORD)), mp = ad.sa_rows, sh = WB - mp;
+    const WORD low = (WORD)(ad.peq[c] & (mp >= 64 ? ~0ull : ((1ull << mp) - 1)));
+    sa = low;
+    tail = sh ? (WORD)((low << sh) | (((WORD)1 << sh) - 1)) : low;
+}
+
+// the whole stage for one read (host simulator; the kernel interleaves block-level compactions)
+template <int S, class WORD>
+ATR_HD void qg_filter_s(const AdapterK1a& ad, const uint32_t* __restrict__ codes, int wlimit, int lo, int n, SaResult& res) {
     int hmin, hmax, imin = 0, imax = 0;
     uint32_t acc[ATR_QG_GROUPS];
-    unsigned sa_peq[16];
-    for (int c = 0; c < 16; c++) sa_peq[c] = (unsigned)(ad.peq[c] & (ad.sa_rows >= 32 ? 0xFFFFFFFFull : ((1ull << ad.sa_rows) - 1)));
+    WORD sa_peq[16], tail_peq[16];
+    for (int c = 0; c < 16; c++) qg_peq_tables<WORD>(ad, c, sa_peq[c], tail_peq[c]);
     qg_scan<S>(ad, ad.qg_tab, codes, wlimit, lo, n, acc, 1, hmin, hmax);
     if (sa_exact(ad, codes, lo, n, hmin, hmax)) { res.cls = 3; res.v = hmin; return; }
-    if (qg_need_tail(ad, sa_peq, codes, lo, n, hmax)) sa_tail(ad, tail_peq, codes, lo, n, imin, imax);
+    if (qg_need_tail<WORD>(ad, sa_peq, codes, lo, n, hmax)) sa_tail_w<WORD>(ad, tail_peq, codes, lo, n, imin, imax);
     sa_classify(ad, lo, n, hmin, hmax, imin, imax, res);
 }
 
-ATR_HD void qg_filter(const AdapterK1a& ad, const unsigned* __restrict__ tail_peq, const uint32_t* __restrict__ codes, int wlimit,
+ATR_HD void qg_filter(const AdapterK1a& ad, const unsigned* __restrict__ /*tail_peq32*/, const uint32_t* __restrict__ codes, int wlimit,
                       int lo, int n, SaResult& res) {
-    if (ad.qg_step == 3) qg_filter_s<3>(ad, tail_peq, codes, wlimit, lo, n, res);
-    else qg_filter_s<2>(ad, tail_peq, codes, wlimit, lo, n, res);
+    if (ad.qg_wide) {
+        if (ad.qg_step == 3) qg_filter_s<3, unsigned long long>(ad, codes, wlimit, lo, n, res);
+        else qg_filter_s<2, unsigned long long>(ad, codes, wlimit, lo, n, res);
+    } else {
+        if (ad.qg_step == 3) qg_filter_s<3, unsigned>(ad, codes, wlimit, lo, n, res);
+        else qg_filter_s<2, unsigned>(ad, codes, wlimit, lo, n, res);
+    }
 }

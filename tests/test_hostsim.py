@@ -326,7 +326,9 @@ def test_filter_only_funnel_for_dearer_indels(where):
 @pytest.mark.parametrize("adapter,rate,min_overlap", [
     (T1, 0.1, 3), (T1, 0.12, 1), ("AGATCGGAAGAGC", 0.1, 3), ("TGGAATTCTCGGGTGCCAAGG", 0.1, 3), (T1, 0.2, 5),
     ("ACGTACGTACGTACGTACGTAAAA", 0.13, 3), ("A" * 30, 0.1, 3), ("GATCGGAAGAGCACACGTCTGAACTCCAGTCACGATC", 0.09, 3),
-    ("CTGTCTCTTATACACATCTCCGAGCCCACGAGAC", 0.1, 3)])
+    ("CTGTCTCTTATACACATCTCCGAGCCCACGAGAC", 0.1, 3),
+    # pieces over more than 32 rows (the q-gram form alone: 64-bit tail pass and gate)
+    (T2, 0.1, 3), (T2, 0.1, 1), (T2[:45], 0.12, 3), ("GATTACAGGCTTAACCGGTATCGATCGGAAGAGCTTGACCAGTACGGATCCTTAGGCAAGTCCA", 0.1, 5)])
 def test_band_margins_fuzz(adapter, rate, min_overlap):
     """the diagonals the banded kernels keep (margin k around the piece hits, floor(i*rate) around the last-column
     candidates, hits no candidate can pass through dropped) against the oracle's full DP"""
