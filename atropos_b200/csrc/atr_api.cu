@@ -98,7 +98,8 @@ struct atr_ctx {
     int disable_sa = 0;
     int disable_qg = 0;              // ATR_DISABLE_QG=1: Shift-And first stage even where the q-gram form is eligible (A/B measurements)
     int sm_count = 148;
-    int64_t panel_chunk = 1 << 19;   // reads per piece of a multi-adapter device call (ATR_PANEL_CHUNK)
+    int64_t panel_chunk = (int64_t)1 << 40;   // ATR_PANEL_CHUNK: reads per piece of a multi-adapter device call. Off by default: pieces of
+                                     // 512 Ki reads keep the later passes in L2 but multiply the launches (9.97 vs 5.68 ms per 5 M reads x 8 adapters)
     int qg_ctas = 5;                 // persistent CTAs per SM of k_filter_qg (51 registers, 42 KB shared memory: 5 fit); ATR_QG_CTAS overrides
     int disable_fused = 0;           // ATR_DISABLE_FUSED=1: always use the plain register-DP kernel (A/B measurements)
     DevBuf misc;                     // small single-call scratch (compare_prefixes, multi_locate)

@@ -200,13 +200,12 @@ __global__ void k_fill_none(atr_match* __restrict__ out, int64_t n) {
 #ifndef ATR_K2_THREADS
 #define ATR_K2_THREADS 128
 #endif
-__global__ void __launch_bounds__(ATR_K2_THREADS, 8) k_insert_packed(
+__global__ void __launch_bounds__(ATR_K2_THREADS) k_insert_packed(
         const __grid_constant__ InsertDev d,
         const uint32_t* __restrict__ codes1, const uint32_t* __restrict__ woff1, const uint16_t* __restrict__ len1,
         const uint32_t* __restrict__ codes2, const uint32_t* __restrict__ woff2, const uint16_t* __restrict__ len2,
         int64_t n_pairs, atr_insert_result* __restrict__ out) {
     __shared__ uint32_t sR2[ATR_K2_MAXW2 * ATR_K2_THREADS];     // rc(read 2) in 2-bit words, [word][thread]
-    __shared__ uint32_t sR4[(ATR_K2_MAXW + 2) * ATR_K2_THREADS];  // ... and in 4-bit words for the exact verification
     __shared__ unsigned short s_thr[ATR_K2_MAXLEN + 1];         // floor(j * rate) for every overlap length the packed path sees
     for (int i = threadIdx.x; i <= ATR_K2_MAXLEN; i += ATR_K2_THREADS) s_thr[i] = i <= d.max_len ? d.thr_ins[i] : (unsigned short)0;
     __syncthreads();
@@ -218,7 +217,7 @@ __global__ void __launch_bounds__(ATR_K2_THREADS, 8) k_insert_packed(
     atr_insert_result* o = out + r;
     bool routed = ((l1 | l2) & ATR_ESC_BIT) != 0 || m > ATR_K2_MAXLEN || !d.packed_ok;
     PackedPair pp;
-    pp.R2 = sR2 + threadIdx.x; pp.R4 = sR4 + threadIdx.x; pp.stride = ATR_K2_THREADS; pp.thr = s_thr;
+    pp.R2 = sR2 + threadIdx.x; pp.stride = ATR_K2_THREADS; pp.thr = s_thr;
     if (!routed) routed = packed_pair_setup(pp, codes1 + woff1[r], codes2 + woff2[r], m, (n1 + 7) >> 3) == 0;
     if (routed) {                      // the byte-exact kernel (k_insert_bytes) picks these up
         atr_insert_result e;

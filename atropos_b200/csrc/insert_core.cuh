@@ -121,7 +121,6 @@ ATR_HD int k2_words_for(int bound) { return bound <= 6 ? 1 : bound <= 15 ? 2 : b
 
 struct PackedPair {
     uint32_t* R2;           // rc(seq2[:m]) in 2-bit words, element u at R2[u * stride], zero padded by 2 words
-    uint32_t* R4;           // the same in 4-bit words (W + 2 words, zero padded): the exact verification reads it
     uint32_t q2[ATR_K2_QW]; // seq1[0:80] in 2-bit words
     const uint32_t* S2;     // forward read2 packed (4-bit)
     const uint32_t* S1;
@@ -143,15 +142,15 @@ struct PackedPair {
         const int nfull = j >> 3;
         unsigned cost = 0;
         int w = 0;
-        uint32_t lo = R4[ws * stride];
+        uint32_t lo = rc_word(ws);
         for (; w < nfull; w++) {
-            const uint32_t hi = R4[(ws + w + 1) * stride];
+            const uint32_t hi = rc_word(ws + w + 1);
             cost += nib_mismatches(funnel_r(lo, hi, bs) ^ S1[w]);
             lo = hi;
             if ((int)cost > bound) return (int)cost;
         }
         if (j & 7) {
-            const uint32_t hi = R4[(ws + w + 1) * stride];
+            const uint32_t hi = rc_word(ws + w + 1);
             const uint32_t x = (funnel_r(lo, hi, bs) ^ S1[w]) & ((1u << ((j & 7) * 4)) - 1u);
             cost += nib_mismatches(x);
         }
@@ -202,7 +201,7 @@ struct PackedPair {
     // Two nested stages with ONE call site each (the kernel is otherwise bound by instruction fetch): the look-ahead
     // marks survivors (the real overlap plus noise; everything at once on low-complexity reads), which are verified in
     // ascending j in batches of ATR_K2_SURV.
-#define ATR_K2_SURV 32
+#define ATR_K2_SURV 16
     template <class F>
     ATR_HD void scan(const InsertDev& d, int k, F&& emit) const {
         unsigned short surv[ATR_K2_SURV];
@@ -219,38 +218,29 @@ struct PackedPair {
         };
         const int jmin = d.min_insert_overlap > 1 ? d.min_insert_overlap : 1;
         const int jsmall = m < 31 ? m : 31;
+        for (int j = jmin; j <= jsmall; j++) {
+            if (small_lb(j) <= atr_imin(k, (int)thr[j])) {
+                surv[ns++] = (unsigned short)j;
+                if (ns == ATR_K2_SURV) { flush(); if (!go_on) return; }
+            }
+        }
         const int jfirst = jmin > 32 ? jmin : 32;              // shortest overlap of the word-wise part
-        const int s_first = m - jfirst;                        // its shift
-        // stage 0: the overlaps shorter than 32, one by one; stages 1..: one 2-bit word offset (16 overlaps) each. The
-        // survivors are verified when the batch is full and after stage 0 (short verifications apart from long ones) --
-        // one call site for everything.
-        int us = s_first >> 4;
-        for (int stage = 0; ; stage++) {
-            bool want_flush = false, last = false;
-            unsigned hits = 0;
-            int bhi = 15;
-            if (stage == 0) {
-                for (int j = jmin; j <= jsmall; j++)           // at most 31 survivors: they fit
-                    if (small_lb(j) <= atr_imin(k, (int)thr[j])) surv[ns++] = (unsigned short)j;
-                want_flush = true;
-            } else if (m < jfirst || us < 0) {
-                want_flush = true; last = true;
-            } else {
-                bhi = us == (s_first >> 4) ? (s_first & 15) : 15;                 // the first group may be partial
+        if (m >= jfirst) {
+            const int s_first = m - jfirst;                    // shift of the shortest overlap handled here
+            for (int us = s_first >> 4; us >= 0 && go_on; us--) {
+                const int bhi = us == (s_first >> 4) ? (s_first & 15) : 15;       // the first group may be partial
                 const int gbound = atr_imin(k, (int)thr[m - 16 * us]);
                 const int nw = atr_imin(k2_words_for(gbound), (m - (16 * us + bhi)) >> 4);    // never past the shortest overlap
-                hits = group_nw(nw, us, gbound) & ((2u << bhi) - 1u);
-                want_flush = hits != 0u && ns + 16 > ATR_K2_SURV;               // room for a whole group
+                unsigned hits = group_nw(nw, us, gbound) & ((2u << bhi) - 1u);
+                while (hits) {                                 // ascending overlap length = descending shift
+                    const int b = k2_msb(hits);
+                    hits &= ~(1u << b);
+                    surv[ns++] = (unsigned short)(m - (16 * us + b));
+                    if (ns == ATR_K2_SURV) { flush(); if (!go_on) break; }
+                }
             }
-            if (want_flush) { flush(); if (!go_on) break; }
-            if (last) break;
-            while (hits) {                                     // ascending overlap length = descending shift
-                const int b = k2_msb(hits);
-                hits &= ~(1u << b);
-                surv[ns++] = (unsigned short)(m - (16 * us + b));
-            }
-            if (stage > 0) us--;
         }
+        if (go_on) flush();
     }
     ATR_HD unsigned ov1(int p) const { return (S1[p >> 3] >> ((p & 7) * 4)) & 15u; }
     ATR_HD unsigned ov2(int p) const { return (S2[p >> 3] >> ((p & 7) * 4)) & 15u; }
@@ -421,12 +411,7 @@ ATR_HD int packed_pair_setup(PackedPair& pp, const uint32_t* S1, const uint32_t*
     pp.S1 = S1; pp.S2 = S2; pp.m = m; pp.W = W; pp.pad = 8 * W - m;
     // rc(read2[:m]): reversed words, each bit-reversed (A1<->T8, C2<->G4), shifted so that base 0 sits in nibble 0
     const int U = (W + 1) >> 1;
-    for (int u = 0; u < U; u++) {
-        const uint32_t a = pp.rc_word(2 * u), b = pp.rc_word(2 * u + 1);
-        pp.R4[(2 * u) * st] = a; pp.R4[(2 * u + 1) * st] = b;
-        pp.R2[u * st] = conv2(a) | (conv2(b) << 16);
-    }
-    pp.R4[(2 * U) * st] = 0; pp.R4[(2 * U + 1) * st] = 0;
+    for (int u = 0; u < U; u++) pp.R2[u * st] = conv2(pp.rc_word(2 * u)) | (conv2(pp.rc_word(2 * u + 1)) << 16);
     pp.R2[U * st] = 0; pp.R2[(U + 1) * st] = 0;
     if (U + 2 < ATR_K2_MAXW2) pp.R2[(U + 2) * st] = 0;
 #pragma unroll

@@ -148,12 +148,12 @@ int sim_match_insert(const atr_insert_desc* d, const unsigned char* r1, int len1
     int esc = 0;
     for (int w = 0; w < (len1 + 7) / 8; w++) c1[w] = atr::pack_word(r1, len1, w, 0, tb.iupac, &esc);
     for (int w = 0; w < (len2 + 7) / 8; w++) c2[w] = atr::pack_word(r2, len2, w, 0, tb.iupac, &esc);
-    std::vector<uint32_t> R2(ATR_K2_MAXW2 + 2, 0), R4(ATR_K2_MAXW + 4, 0);
+    std::vector<uint32_t> R2(ATR_K2_MAXW2 + 2, 0);
     std::vector<Cand> cand(ATR_MAX_CAND + 1);
     bool routed = esc || m > ATR_K2_MAXLEN || !v.packed_ok || route == 1;
     {
         PackedPair pp;
-        pp.R2 = R2.data(); pp.R4 = R4.data(); pp.stride = 1; pp.thr = v.thr_ins;
+        pp.R2 = R2.data(); pp.stride = 1; pp.thr = v.thr_ins;
         if (!routed) routed = packed_pair_setup(pp, c1.data(), c2.data(), m, (len1 + 7) / 8) == 0;
         if (used_packed) *used_packed = !routed;
         if (!routed) { insert_pair(v, pp, true, m, len1, len2, cand.data(), out); return 0; }
