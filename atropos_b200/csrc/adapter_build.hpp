@@ -193,15 +193,16 @@ inline void fill_k1a(const HostAdapter& h, const AtrTables& tb, int index, int r
     a.qg_wide = 0; a.sa_start64 = a.sa_end64 = a.tail_mask64 = 0;
     const bool stop_in_query = h.desc.flags & ATR_STOP_WITHIN_SEQ2;
     const int pieces = h.k + 1;
-    auto layout = [&](int rows) {
+    // lens: the pieces' lengths in rows (they cover rows 1 .. sum). Returns whether the tail gate works for this layout.
+    auto layout = [&](const std::vector<int>& lens) -> int {
         unsigned long long st = 0, en = 0, mask = 0;
         int row = 1;
-        for (int pc = 0; pc < pieces; pc++) {
-            const int len = rows / pieces + (pc < rows % pieces ? 1 : 0);
+        for (int len : lens) {
             st |= 1ull << (row - 1);
             en |= 1ull << (row + len - 2);
             row += len;
         }
+        const int rows = row - 1;
         // Gate for the exact tail pass. A last-column candidate (i, n), i <= rows, has e <= thr_mul[i] errors
         // over rows 1..i, which contain c(i) complete pieces. e < c: a complete piece is verbatim (a hit near the
         // read end). e == c: either that, or every complete piece is broken and the rows after them -- the begun
@@ -213,8 +214,7 @@ inline void fill_k1a(const HostAdapter& h, const AtrTables& tb, int index, int r
         for (int i = 1; i <= rows; i++) {
             if (i < first || i < h.desc.min_overlap) continue;
             int c = 0, end_c = 0, r = 1;
-            for (int pc = 0; pc < pieces; pc++) {
-                const int len = rows / pieces + (pc < rows % pieces ? 1 : 0);
+            for (int len : lens) {
                 if (r + len - 1 <= i) { c++; end_c = r + len - 1; }
                 r += len;
             }
@@ -225,14 +225,44 @@ inline void fill_k1a(const HostAdapter& h, const AtrTables& tb, int index, int r
         }
         a.sa_rows = rows; a.sa_start64 = st; a.sa_end64 = en; a.tail_mask64 = mask; a.tail_gate_ok = gate;
         a.sa_start = (unsigned)st; a.sa_end = (unsigned)en; a.tail_mask = (unsigned)mask;
+        return gate;
+    };
+    auto equal_split = [&](int rows) {
+        std::vector<int> lens;
+        for (int pc = 0; pc < pieces; pc++) lens.push_back(rows / pieces + (pc < rows % pieces ? 1 : 0));
+        return lens;
+    };
+    // pieces that end right before the rows where the error budget grows (thr_mul[i] steps from p - 1 to p): then the
+    // budget never reaches the number of complete pieces AT a piece end, which is the one case the gate cannot certify
+    // (equal pieces of exactly 1 / rate rows, the 58-nt adapter at 0.1, have it at every piece end)
+    auto budget_split = [&](int rows) {
+        std::vector<int> lens;
+        int prev = 0;
+        for (int pc = 1; pc < pieces; pc++) {
+            int i = prev + 1;
+            while (i <= rows && (int)h.thr_mul[i] < pc) i++;     // first row whose budget is pc
+            const int end = i - 1;
+            lens.push_back(end - prev);
+            prev = end;
+        }
+        lens.push_back(rows - prev);
+        return lens;
     };
     const bool shape = (a.fused_ok || a.filter_only) && !start_in_ref && stop_in_query;
     if (shape && pieces <= a.sa_rows && a.sa_rows / pieces >= 6) {
         a.sa_ok = 1;
-        layout(a.sa_rows);
+        layout(equal_split(a.sa_rows));
     } else if (shape && h.m > 32 && !a.and_mode) {
         const int rows = h.m < 64 ? h.m : 64;
-        if (pieces <= rows && rows / pieces >= 7) { a.qg_wide = 1; layout(rows); }
+        if (pieces <= rows && rows / pieces >= 7) {
+            a.qg_wide = 1;
+            if (!layout(equal_split(rows))) {
+                const std::vector<int> alt = budget_split(rows);
+                bool ok = true;
+                for (int len : alt) ok = ok && len >= 7 && len <= 16;
+                if (!ok || !layout(alt)) layout(equal_split(rows));
+            }
+        }
     }
 }
 

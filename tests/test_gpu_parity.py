@@ -588,3 +588,43 @@ def test_packed_host_entry_point_equals_ascii_entry_point():
             assert np.array_equal(got2[~esc], exp[~esc])
             if esc.any():
                 assert (got2["status"][esc] == _abi.ATR_ST_ESCAPED).all()
+
+
+def test_panel_cfg4_all_eight_adapters():
+    """BASELINE cfg 4's panel exactly as bench.py runs it (three 3' adapters incl. the 58-mer, two anchored 5', one
+    unanchored 5', the duplicate and the 13-mer): best match per read on the GPU == the reference's rule
+    (modifiers.py:107-122: strictly more matches wins, the first adapter on ties) over the oracle's match_to."""
+    import bench
+    from atropos_b200 import _abi, adapters as ad_mod, engine
+    from atropos_b200.modifiers import AdapterCutter
+    rng = np.random.default_rng(404)
+    reads = []
+    for i in range(12000):
+        which = int(rng.integers(0, len(bench.PANEL)))
+        seq, where = bench.PANEL[which]
+        body = fuzzgen.read_with_adapter(rng, seq, 150, n_rate=0.005) if where == "BACK" else fuzzgen.rand_seq(rng, 150)
+        r = rng.random()
+        if where != "BACK" and r < 0.7:
+            body = (fuzzgen.mutate(rng, seq, 0.03, 0.01, 0.01) + body)[:150]
+        elif r < 0.1:
+            body = (bench.PANEL[3][0] + body)[:150]
+        reads.append(body)
+    cutter = AdapterCutter([ad_mod.Adapter(s, getattr(ad_mod, w), max_error_rate=0.1, min_overlap=3) for s, w in bench.PANEL])
+    got = cutter.best_match_batch(reads)
+    oads = [oracle.OracleAdapter(s, getattr(oracle, w), 0.1, 3) for s, w in bench.PANEL]
+    hits = 0
+    winners = set()
+    for i, seq in enumerate(reads):
+        best, bi = None, -1
+        for ai, oa in enumerate(oads):
+            m = oa.match_to(seq)
+            if m is not None and (best is None or m[4] > best[4]):
+                best, bi = m, ai
+        g = got[i]
+        if best is None:
+            assert int(g["status"]) == _abi.ATR_ST_NONE, (i, seq)
+        else:
+            hits += 1
+            winners.add(bi)
+            assert int(g["status"]) == _abi.ATR_ST_MATCH and _tup(g) == tuple(best[:6]) and int(g["adapter"]) == bi, (i, seq, best, bi)
+    assert hits > 6000 and len(winners) >= 6
