@@ -112,6 +112,8 @@ struct atr_adapterset {
     std::vector<AdapterK1a> k1a;     // valid where host[i].k1a_ok
     std::vector<AdapterGen> gen;
     std::vector<void*> dev_allocs;
+    std::vector<char> shadowed;      // adapter i repeats an earlier adapter of the set in every respect: it can never win
+                                     // (AdapterCutter._best_match keeps the first on equal matches, modifiers.py:120) and is skipped
     int max_m = 0;
 };
 
@@ -200,6 +202,7 @@ int locate_on_stream(atr_ctx* ctx, Slot& slot, const atr_adapterset* set,
     }
     for (size_t a = 0; a < set->host.size(); a++) {
         const atr::HostAdapter& h = set->host[a];
+        if (a < set->shadowed.size() && set->shadowed[a]) continue;
         if (h.k1a_ok && have_packed) {
             AdapterK1a p = set->k1a[a];
             p.reduce = a > 0;
@@ -528,6 +531,18 @@ int atr_adapterset_create(atr_ctx* ctx, int32_t n_adapters, const atr_adapter_de
                 if (rc) { atr_adapterset_destroy(set); return rc; }
                 ka.qg_tab = d_qtab;
             }
+        }
+    }
+    set->shadowed.assign((size_t)n_adapters, 0);
+    for (int a = 1; a < n_adapters; a++) {
+        const atr::HostAdapter& x = set->host[(size_t)a];
+        for (int b = 0; b < a && !set->shadowed[(size_t)a]; b++) {
+            const atr::HostAdapter& y = set->host[(size_t)b];
+            const atr_adapter_desc &p = x.desc, &q = y.desc;
+            if (x.seq == y.seq && p.max_error_rate == q.max_error_rate && p.flags == q.flags && p.wildcard_ref == q.wildcard_ref &&
+                p.wildcard_query == q.wildcard_query && p.min_overlap == q.min_overlap && p.indel_cost == q.indel_cost &&
+                p.match_to_semantics == q.match_to_semantics && p.no_indels == q.no_indels && x.rmp_ok == y.rmp_ok)
+                set->shadowed[(size_t)a] = 1;
         }
     }
     *out = set;
