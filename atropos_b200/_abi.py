@@ -131,6 +131,15 @@ class AtrTrimPeOpts(C.Structure):
                 ("ops", AtrReadOps)]
 
 
+class AtrMergeOpts(C.Structure):
+    _fields_ = [("min_overlap", C.c_double), ("error_rate", C.c_double)]
+
+
+class AtrMergeStats(C.Structure):
+    _fields_ = [("merged", C.c_int64), ("merged_written", C.c_int64), ("bp_merged_written", C.c_int64),
+                ("records_corrected", C.c_int64), ("bp_corrected", C.c_int64 * 2)]
+
+
 class AtrTrimPeStats(C.Structure):
     _fields_ = [("records", C.c_int64), ("insert_matches", C.c_int64), ("with_adapters", C.c_int64 * 2),
                 ("bp_in", C.c_int64 * 2), ("bp_out", C.c_int64 * 2), ("overflow", C.c_int64),

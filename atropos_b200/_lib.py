@@ -21,7 +21,7 @@ SYMBOLS = [
     "atr_ctx_last_phase_ms", "atr_ctx_last_phase_name", "atr_adapterset_create",
     "atr_adapterset_destroy", "atr_packed_words", "atr_pack_device", "atr_pack_reads_host", "atr_locate_batch_device",
     "atr_locate_batch_host", "atr_locate_batch_host_packed", "atr_compare_prefixes", "atr_insertset_create", "atr_insertset_destroy",
-    "atr_match_insert_batch_device", "atr_match_insert_batch_host", "atr_multi_locate", "atr_merge_overlap_batch_host", "atr_trim_fastq_host", "atr_trim_fastq_pe_host",
+    "atr_match_insert_batch_device", "atr_match_insert_batch_host", "atr_multi_locate", "atr_merge_overlap_batch_host", "atr_trim_fastq_host", "atr_trim_fastq_pe_host", "atr_trim_fastq_pe_merge_host",
 ]
 
 
@@ -82,6 +82,10 @@ def load():
     L.atr_trim_fastq_pe_host.argtypes = [vp, vp, vp, vp, C.POINTER(_abi.AtrTrimPeOpts), vp, i64, vp, i64, vp, i64, vp, i64,
                                          C.POINTER(i64), C.POINTER(i64), C.POINTER(_abi.AtrTrimPeStats),
                                          C.POINTER(_abi.AtrFastqError)]
+    L.atr_trim_fastq_pe_merge_host.argtypes = [vp, vp, vp, vp, C.POINTER(_abi.AtrTrimPeOpts), C.POINTER(_abi.AtrMergeOpts), vp, i64, vp, i64,
+                                               vp, i64, vp, i64, vp, i64, C.POINTER(i64), C.POINTER(i64),
+                                               C.POINTER(_abi.AtrTrimPeStats), C.POINTER(_abi.AtrMergeStats),
+                                               C.POINTER(_abi.AtrFastqError)]
     if L.atr_abi_version() != _abi.ATR_ABI_VERSION:
         raise ImportError("atropos_b200: ABI version mismatch, rebuild with `python -m atropos_b200.build --force`")
     _lib = L

@@ -72,12 +72,13 @@ struct Slot {
     // FASTQ paths (atr_fastq_api.cuh): one FqSide per input text (single-end uses fq[0]); second mate's windows,
     // fallback matches and the insert-aligner results of the paired-end path
     FqSide fq[2];
+    FqSide fqm;                          // merged reads of the paired-end path (third output: atr_trim_fastq_pe_merge_host)
     DevBuf win2, out2, ins_out;
     void release() {
         DevBuf* all[] = {&ascii, &offsets, &win, &counts, &woff, &codes, &len, &out, &scan_tmp, &gen_scratch, &lists,
                          &ascii2, &offsets2, &counts2, &woff2, &codes2, &len2, &win2, &out2, &ins_out};
         for (DevBuf* b : all) b->release();
-        fq[0].release(); fq[1].release();
+        fq[0].release(); fq[1].release(); fqm.release();
     }
 };
 
@@ -914,5 +915,5 @@ int atr_multi_locate(atr_ctx* ctx, const char* reference, int32_t m, const char*
 
 }  // extern "C"
 
-#include "atr_fastq_api.cuh"
 #include "atr_merge_api.cuh"
+#include "atr_fastq_api.cuh"

@@ -439,7 +439,14 @@ struct PeStep {
 };
 
 // statistics block: pair counters | per read: AdapterCutter counters, back / front histograms, adjacent bases, front flags
-struct PeLayout { size_t H, nA[2], o_ctr, o_side[2], o_hist[2], o_front[2], o_adj[2], o_flags[2], o_ops, total; };
+struct PeLayout { size_t H, nA[2], o_ctr, o_side[2], o_hist[2], o_front[2], o_adj[2], o_flags[2], o_ops, o_merge, total; };
+
+// MergeOverlapping behind the modifiers (atr_trim_fastq_pe_merge_host): what pe_back needs of it
+struct PeMerge {
+    MergeTables tb;
+    double error_rate = 0;
+    int write_merged = 0;            // a merged output exists; else merged pairs are discarded
+};
 
 PeLayout pe_layout(int max_len, int max_errors, size_t nA0, size_t nA1) {
     PeLayout L;
@@ -455,7 +462,8 @@ PeLayout pe_layout(int max_len, int max_errors, size_t nA0, size_t nA1) {
         L.o_flags[f] = o; o += ((L.nA[f] + 63) & ~(size_t)63);
     }
     L.o_ops = o;
-    L.total = L.o_ops + ((sizeof(FqOpsCounters) + 15) & ~(size_t)15);
+    L.o_merge = L.o_ops + ((sizeof(FqOpsCounters) + 15) & ~(size_t)15);
+    L.total = L.o_merge + ((sizeof(FqMergeCounters) + 15) & ~(size_t)15);
     return L;
 }
 
@@ -469,7 +477,7 @@ PeSide pe_side(Slot& s, int f) {
 }
 
 int pe_back(atr_ctx* ctx, Slot& s, const PeStep& P, const atr_insertset* iset, const atr_adapterset* const sets[2],
-            const atr_trim_pe_opts* o, const PeLayout& L, char* d_stats) {
+            const atr_trim_pe_opts* o, const PeLayout& L, char* d_stats, const PeMerge* mg) {
     cudaStream_t st = s.stream;
     const int64_t n = P.n;
     FqPeCounters* d_ctr = (FqPeCounters*)(d_stats + L.o_ctr);
@@ -497,6 +505,28 @@ int pe_back(atr_ctx* ctx, Slot& s, const PeStep& P, const atr_insertset* iset, c
     }
     int rc = iset ? s.ins_out.ensure((size_t)(n + 1) * sizeof(atr_insert_result)) : ATR_OK;
     if (rc) return fail(ctx, rc, "out of device memory (insert results)");
+    // merged reads: pair flags, insert_matched bytes, merge results, merge records, the third formatted text
+    FqSide& qm = s.fqm;
+    unsigned char* d_pflags = nullptr;
+    if (mg) {
+        rc = qm.flags.ensure((size_t)n + 16);
+        if (!rc) rc = qm.tiles.ensure((size_t)n + 16);
+        if (!rc) rc = qm.text.ensure((size_t)(n + 1) * sizeof(atr_merge_result));
+        if (!rc) rc = qm.recs.ensure((size_t)(n + 1) * sizeof(FqMergeRec));
+        if (!rc) rc = qm.len64.ensure((size_t)(n + 2) * sizeof(long long));
+        if (!rc) rc = qm.outoff.ensure((size_t)(n + 2) * sizeof(long long));
+        if (!rc) rc = qm.nl.ensure(64);
+        if (!rc) rc = qm.info.ensure(sizeof(FqInfo));
+        if (!rc && mg->write_merged) rc = qm.outtext.ensure((size_t)(P.c[0].len + P.c[1].len) + 64);
+        if (rc) return fail(ctx, rc, "out of device memory (merged reads)");
+        if (!qm.hinfo) {
+            CU(cudaHostAlloc((void**)&qm.hinfo, sizeof(FqInfo), cudaHostAllocMapped));
+            CU(cudaStreamCreateWithFlags(&qm.out_stream, cudaStreamNonBlocking));
+            CU(cudaEventCreateWithFlags(&qm.ev_d2h, cudaEventDisableTiming));
+        }
+        if (qm.d2h_pending) { CU(cudaStreamWaitEvent(st, qm.ev_d2h, 0)); qm.d2h_pending = 0; }
+        d_pflags = qm.flags.as<unsigned char>();
+    }
     // frame + validate both sides, then the names; every error goes to side 0's key
     for (int f = 0; f < 2; f++) {
         FqSide& q = s.fq[f];
@@ -551,7 +581,7 @@ int pe_back(atr_ctx* ctx, Slot& s, const PeStep& P, const atr_insertset* iset, c
                                                      s.fq[0].fwin.as<uint16_t>(), s.fq[1].fwin.as<uint16_t>(),
                                                      (unsigned long long*)(d_stats + L.o_hist[0]), (unsigned long long*)(d_stats + L.o_hist[1]),
                                                      (unsigned long long*)(d_stats + L.o_adj[0]), (unsigned long long*)(d_stats + L.o_adj[1]), d_ctr,
-                                                     o->ops, d_ops, o->mismatch_action, iset->dev.comp);
+                                                     o->ops, d_ops, o->mismatch_action, iset->dev.comp, d_pflags);
         LAUNCHED(ctx);
     } else {
         // "--aligner adapter": two independent AdapterCutters (the single-end adapter stage per read), then the pair filters
@@ -577,7 +607,59 @@ int pe_back(atr_ctx* ctx, Slot& s, const PeStep& P, const atr_insertset* iset, c
         k_pe_post<<<grid_for(n, 256), 256, 0, st>>>(s.fq[0].text.as<unsigned char>(), s.fq[0].recs.as<FqRec>(),
                                                     s.fq[1].text.as<unsigned char>(), s.fq[1].recs.as<FqRec>(), n, o->ops,
                                                     s.fq[0].fwin.as<uint16_t>(), s.fq[1].fwin.as<uint16_t>(),
-                                                    s.fq[0].flags.as<unsigned char>(), s.fq[1].flags.as<unsigned char>(), d_ops);
+                                                    s.fq[0].flags.as<unsigned char>(), s.fq[1].flags.as<unsigned char>(), d_ops, d_pflags);
+        LAUNCHED(ctx);
+    }
+    if (mg) {
+        // MergeOverlapping, the last modifier (commands/trim/__init__.py:546-552): what trimming left of the two reads goes
+        // to the merge kernels as two contiguous ASCII batches; then the decision, MergedReadFilter and the waiting filters
+        FqMergeCounters* d_mc = (FqMergeCounters*)(d_stats + L.o_merge);
+        int* d_max = qm.nl.as<int>();
+        int* h_max = &qm.hinfo->nl_overflow;                 // two consecutive ints of the mapped FqInfo (unused for this side)
+        CU(cudaMemsetAsync(d_max, 0, 2 * sizeof(int), st));
+        for (int f = 0; f < 2; f++) CU(cudaMemsetAsync(s.fq[f].len64.p, 0, (size_t)(n + 2) * sizeof(long long), st));
+        k_pe_merge_len<<<grid_for(n, 256), 256, 0, st>>>(s.fq[0].fwin.as<uint16_t>(), s.fq[1].fwin.as<uint16_t>(), d_pflags, n,
+                                                         s.fq[0].len64.as<long long>(), s.fq[1].len64.as<long long>(),
+                                                         qm.tiles.as<unsigned char>(), d_max);
+        LAUNCHED(ctx);
+        k_pe_merge_publish<<<1, 32, 0, st>>>(d_max, h_max);
+        LAUNCHED(ctx);
+        for (int f = 0; f < 2; f++) {
+            PeSide b = pe_side(s, f);
+            rc = fq_scan_i64(ctx, st, s.scan_tmp, s.fq[f].len64.as<long long>(), (long long*)b.offsets.p, n + 1);
+            if (rc) return rc;
+            k_pe_merge_gather<<<grid_for(n * 32, 256), 256, 0, st>>>(s.fq[f].text.as<unsigned char>(), s.fq[f].recs.as<FqRec>(),
+                                                                    s.fq[f].fwin.as<uint16_t>(), (const long long*)b.offsets.p, n,
+                                                                    b.ascii.as<unsigned char>());
+            LAUNCHED(ctx);
+        }
+        CU(cudaStreamSynchronize(st));                       // the longest windows decide which merge kernel runs
+        const int max1 = h_max[0], max2 = h_max[1];
+        if (max1 > ATR_MERGE_MAX_READ || max2 > ATR_MERGE_MAX_READ) return fail(ctx, ATR_E_LIMIT, "read longer than 4000 nt (merge)");
+        const MergePlan plan = merge_plan(max1, max2, mg->error_rate);
+        rc = merge_launch(ctx, s, st, plan, max2, b0.ascii.as<unsigned char>(), b0.offsets.as<int64_t>(), 0, b1.ascii.as<unsigned char>(),
+                          b1.offsets.as<int64_t>(), 0, qm.tiles.as<unsigned char>(), n, mg->tb, nullptr, qm.text.as<atr_merge_result>());
+        if (rc) return rc;
+        CU(cudaMemsetAsync(qm.len64.p, 0, (size_t)(n + 2) * sizeof(long long), st));
+        CU(cudaMemsetAsync(qm.info.p, 0, sizeof(FqInfo), st));
+        k_pe_merge_apply<<<grid_for(n, 256), 256, 0, st>>>(s.fq[0].text.as<unsigned char>(), s.fq[0].recs.as<FqRec>(),
+                                                           s.fq[1].text.as<unsigned char>(), s.fq[1].recs.as<FqRec>(),
+                                                           qm.text.as<atr_merge_result>(), d_pflags, n, o->ops, o->mismatch_action,
+                                                           mg->tb.comp, mg->write_merged, s.fq[0].fwin.as<uint16_t>(),
+                                                           s.fq[1].fwin.as<uint16_t>(), qm.recs.as<FqMergeRec>(), qm.len64.as<long long>(),
+                                                           d_ops, d_mc);
+        LAUNCHED(ctx);
+        if (mg->write_merged) {
+            rc = fq_scan_i64(ctx, st, s.scan_tmp, qm.len64.as<long long>(), qm.outoff.as<long long>(), n + 1);
+            if (rc) return rc;
+            k_pe_merge_format<<<grid_for(n * 32, 256), 256, 0, st>>>(s.fq[0].text.as<unsigned char>(), s.fq[0].recs.as<FqRec>(),
+                                                                    s.fq[1].text.as<unsigned char>(), s.fq[1].recs.as<FqRec>(),
+                                                                    b1.ascii.as<unsigned char>(), (const long long*)b1.offsets.p,
+                                                                    qm.recs.as<FqMergeRec>(), qm.outoff.as<long long>(), mg->tb.comp, n,
+                                                                    qm.outtext.as<unsigned char>(), qm.info.as<FqInfo>());
+            LAUNCHED(ctx);
+        }
+        k_fq_publish<<<1, 32, 0, st>>>(qm.info.as<FqInfo>(), qm.hinfo);
         LAUNCHED(ctx);
     }
     for (int f = 0; f < 2; f++) {
@@ -618,18 +700,22 @@ int pe_probe(atr_ctx* ctx, Slot& s, int f, const FqChunk& c, int64_t first, int 
 
 }  // namespace
 
-extern "C" int atr_trim_fastq_pe_host(atr_ctx* ctx, const atr_insertset* iset, const atr_adapterset* set1, const atr_adapterset* set2,
-                                      const atr_trim_pe_opts* opts, const uint8_t* text1, int64_t nbytes1, const uint8_t* text2,
-                                      int64_t nbytes2, uint8_t* out1, int64_t out_cap1, uint8_t* out2, int64_t out_cap2,
-                                      int64_t* out_bytes, int64_t* consumed, atr_trim_pe_stats* stats, atr_fastq_error* err) {
+namespace {
+int trim_fastq_pe_impl(atr_ctx* ctx, const atr_insertset* iset, const atr_adapterset* set1, const atr_adapterset* set2,
+                       const atr_trim_pe_opts* opts, const atr_merge_opts* mopts, const uint8_t* text1, int64_t nbytes1,
+                       const uint8_t* text2, int64_t nbytes2, uint8_t* out1, int64_t out_cap1, uint8_t* out2, int64_t out_cap2,
+                       uint8_t* out_merged, int64_t out_cap_merged, int64_t* out_bytes /* [3] */, int64_t* consumed,
+                       atr_trim_pe_stats* stats, atr_merge_stats* mstats, atr_fastq_error* err) {
     if (!ctx || (iset && (!set1 || !set2)) || !opts || nbytes1 < 0 || nbytes2 < 0 || (nbytes1 > 0 && (!text1 || !out1)) ||
-        (nbytes2 > 0 && (!text2 || !out2)) || !out_bytes || !consumed || !stats || !err)
+        (nbytes2 > 0 && (!text2 || !out2)) || !out_bytes || !consumed || !stats || !err || (mopts && !mstats))
         return fail(ctx, ATR_E_ARG, "bad arguments to atr_trim_fastq_pe_host");
+    if (mopts && (!(mopts->min_overlap > 0) || !(mopts->error_rate >= 0) || mopts->error_rate > 1 || out_cap_merged < 0))
+        return fail(ctx, ATR_E_ARG, "bad atr_merge_opts");
     if ((set1 && set1->ctx != ctx) || (set2 && set2->ctx != ctx) || (iset && iset->ctx != ctx))
         return fail(ctx, ATR_E_ARG, "adapter / insert set belongs to another context");
     if (!iset && opts->times < 1) return fail(ctx, ATR_E_ARG, "atr_trim_pe_opts.times must be >= 1 in adapter mode");
-    if (opts->mismatch_action < 0 || opts->mismatch_action > 3 || (opts->mismatch_action && !iset))
-        return fail(ctx, ATR_E_ARG, "mismatch_action is 0..3 and needs the insert aligner");
+    if (opts->mismatch_action < 0 || opts->mismatch_action > 3 || (opts->mismatch_action && !iset && !mopts))
+        return fail(ctx, ATR_E_ARG, "mismatch_action is 0..3 and needs the insert aligner or MergeOverlapping");
     if (opts->max_len < 0 || opts->max_len > ATR_MAX_READ || opts->max_errors < 0 || opts->max_errors > 4095 || opts->min_insert_overlap < 0)
         return fail(ctx, ATR_E_ARG, "bad atr_trim_pe_opts");
     const atr_adapterset* sets[2] = {set1, set2};
@@ -641,7 +727,7 @@ extern "C" int atr_trim_fastq_pe_host(atr_ctx* ctx, const atr_insertset* iset, c
     }
     CU(cudaSetDevice(ctx->device));
     memset(err, 0, sizeof(*err));
-    out_bytes[0] = out_bytes[1] = 0;
+    out_bytes[0] = out_bytes[1] = out_bytes[2] = 0;
     consumed[0] = consumed[1] = 0;
     const uint8_t* text[2] = {text1, text2};
     const int64_t nbytes[2] = {nbytes1, nbytes2};
@@ -654,6 +740,17 @@ extern "C" int atr_trim_fastq_pe_host(atr_ctx* ctx, const atr_insertset* iset, c
     if (rc) return fail(ctx, rc, "out of device memory (statistics)");
     char* d_stats = ctx->fq_stats.as<char>();
     CU(cudaMemset(d_stats, 0, L.total));
+    PeMerge merge;
+    if (mopts) {
+        // thresholds and minimum overlaps for every read length the merge kernels take (ctx->misc; nothing else in this call uses it)
+        rc = merge_tables(ctx, ctx->slot[0].stream, ATR_MERGE_MAX_READ, mopts->min_overlap, mopts->error_rate, merge.tb);
+        if (rc) return rc;
+        CU(cudaStreamSynchronize(ctx->slot[0].stream));
+        merge.error_rate = mopts->error_rate;
+        merge.write_merged = out_merged != nullptr;
+    }
+    const PeMerge* mg = mopts ? &merge : nullptr;
+    int64_t opos_m = 0;
     for (int f = 0; f < 2; f++) {
         if (!sets[f]) continue;
         std::vector<signed char> ff(sets[f]->host.size());
@@ -798,7 +895,7 @@ extern "C" int atr_trim_fastq_pe_host(atr_ctx* ctx, const atr_insertset* iset, c
         nxt = make_step(cur.slot ^ 1);
         rc = front(nxt);
         if (rc) { result = rc; break; }
-        rc = pe_back(ctx, s, cur, iset, sets, opts, L, d_stats);
+        rc = pe_back(ctx, s, cur, iset, sets, opts, L, d_stats, mg);
         if (rc) { result = rc; break; }
         CUB(cudaStreamSynchronize(s.stream));
         const unsigned long long key = s.fq[0].hinfo->err_key;
@@ -832,6 +929,20 @@ extern "C" int atr_trim_fastq_pe_host(atr_ctx* ctx, const atr_insertset* iset, c
             opos[f] += ob;
         }
         if (result) break;                           // (a CUB inside the loop over the two sides)
+        if (mg && mg->write_merged && !cap_bad) {
+            FqSide& q = s.fqm;
+            const int64_t ob = (int64_t)q.hinfo->out_bytes;
+            if (opos_m + ob > out_cap_merged) cap_bad = true;
+            else {
+                if (ob) {
+                    CUB(cudaMemcpyAsync(out_merged + opos_m, q.outtext.p, (size_t)ob, cudaMemcpyDeviceToHost, q.out_stream));
+                    CUB(cudaEventRecord(q.ev_d2h, q.out_stream));
+                    q.d2h_pending = 1;
+                }
+                opos_m += ob;
+            }
+            if (result) break;
+        }
         if (cap_bad) { result = fail(ctx, ATR_E_ARG, "out_cap too small for the trimmed text (nbytes + 1 always suffices)"); break; }
         records_before += n;
         cur = nxt;
@@ -842,6 +953,8 @@ extern "C" int atr_trim_fastq_pe_host(atr_ctx* ctx, const atr_insertset* iset, c
             if (ctx->slot[k].fq[f].out_stream) CU(cudaStreamSynchronize(ctx->slot[k].fq[f].out_stream));
             ctx->slot[k].fq[f].d2h_pending = 0;
         }
+        if (ctx->slot[k].fqm.out_stream) CU(cudaStreamSynchronize(ctx->slot[k].fqm.out_stream));
+        ctx->slot[k].fqm.d2h_pending = 0;
     }
     if (result != ATR_OK) return result;
     std::vector<char> hst(L.total);
@@ -880,8 +993,47 @@ extern "C" int atr_trim_fastq_pe_host(atr_ctx* ctx, const atr_insertset* iset, c
         if (stats->adjacent_bases[f]) for (size_t i = 0; i < L.nA[f] * 5; i++) stats->adjacent_bases[f][i] += (int64_t)ha[i];
     }
     fq_add_ops(stats->ops, *(const FqOpsCounters*)(hst.data() + L.o_ops));
-    out_bytes[0] = opos[0]; out_bytes[1] = opos[1];
+    if (mg) {
+        const FqMergeCounters* mc = (const FqMergeCounters*)(hst.data() + L.o_merge);
+        if (mc->raises) {
+            err->kind = ATR_FQ_INVALID_MATCH; err->record = -1;
+            return fail(ctx, ATR_E_FORMAT, "a pair for which MergeOverlapping raises in the reference (a byte reverse_complement rejects, or an invalid alignment)");
+        }
+        if (mc->correction_errors) {
+            err->kind = ATR_FQ_CORRECTION; err->record = -1;
+            return fail(ctx, ATR_E_FORMAT, "error correction would raise in the reference (bytes outside the complement table)");
+        }
+        mstats->merged += (int64_t)mc->merged;
+        mstats->merged_written += (int64_t)mc->merged_written;
+        mstats->bp_merged_written += (int64_t)mc->bp_merged;
+        mstats->records_corrected += (int64_t)mc->records_corrected;
+        mstats->bp_corrected[0] += (int64_t)mc->bp_corrected[0];
+        mstats->bp_corrected[1] += (int64_t)mc->bp_corrected[1];
+    }
+    out_bytes[0] = opos[0]; out_bytes[1] = opos[1]; out_bytes[2] = opos_m;
     consumed[0] = pos[0]; consumed[1] = pos[1];
     ctx->last_ms = -1.f;
     return ATR_OK;
+}
+}  // namespace
+
+extern "C" int atr_trim_fastq_pe_host(atr_ctx* ctx, const atr_insertset* iset, const atr_adapterset* set1, const atr_adapterset* set2,
+                                      const atr_trim_pe_opts* opts, const uint8_t* text1, int64_t nbytes1, const uint8_t* text2,
+                                      int64_t nbytes2, uint8_t* out1, int64_t out_cap1, uint8_t* out2, int64_t out_cap2,
+                                      int64_t* out_bytes, int64_t* consumed, atr_trim_pe_stats* stats, atr_fastq_error* err) {
+    int64_t ob[3] = {0, 0, 0};
+    const int rc = trim_fastq_pe_impl(ctx, iset, set1, set2, opts, nullptr, text1, nbytes1, text2, nbytes2, out1, out_cap1, out2, out_cap2,
+                                      nullptr, 0, out_bytes ? ob : nullptr, consumed, stats, nullptr, err);
+    if (out_bytes) { out_bytes[0] = ob[0]; out_bytes[1] = ob[1]; }
+    return rc;
+}
+
+extern "C" int atr_trim_fastq_pe_merge_host(atr_ctx* ctx, const atr_insertset* iset, const atr_adapterset* set1, const atr_adapterset* set2,
+                                            const atr_trim_pe_opts* opts, const atr_merge_opts* mopts, const uint8_t* text1,
+                                            int64_t nbytes1, const uint8_t* text2, int64_t nbytes2, uint8_t* out1, int64_t out_cap1,
+                                            uint8_t* out2, int64_t out_cap2, uint8_t* out_merged, int64_t out_cap_merged,
+                                            int64_t* out_bytes, int64_t* consumed, atr_trim_pe_stats* stats, atr_merge_stats* mstats,
+                                            atr_fastq_error* err) {
+    return trim_fastq_pe_impl(ctx, iset, set1, set2, opts, mopts, text1, nbytes1, text2, nbytes2, out1, out_cap1, out2, out_cap2,
+                              out_merged, out_cap_merged, out_bytes, consumed, stats, mstats, err);
 }

@@ -275,6 +275,52 @@ int merge_tables(atr_ctx* ctx, cudaStream_t st, int max_len, double min_overlap,
     return ATR_OK;
 }
 
+// which kernel serves a batch whose longest reads are max_len1 / max_len2 (read 2 = the DP's rows)
+struct MergePlan {
+    bool use_warp = false, use_shared = false;
+    size_t col_bytes = 0, smem = 0;
+};
+MergePlan merge_plan(int max_len1, int max_len2, double error_rate) {
+    MergePlan P;
+    // warp-per-pair wavefront kernel whenever its limits hold (ATR_MERGE_KERNEL=thread forces the other one: tests)
+    const char* force = getenv("ATR_MERGE_KERNEL");
+    const int kmax = (int)thr_mul_of(max_len2, error_rate);
+    P.use_warp = !(force && force[0] == 't') && max_len2 <= 320 && max_len1 <= 3000 && kmax + 1 <= 250;
+    P.col_bytes = (size_t)(max_len2 + 1) * sizeof(GCell);
+    P.smem = P.col_bytes * ATR_MERGE_THREADS;
+    P.use_shared = P.smem <= (size_t)200 * 1024;
+    return P;
+}
+
+// one launch over cn pairs that are already on the device (offsets absolute, base subtracted); scratch: the slot's
+// gen_scratch when the thread-per-pair kernel keeps its columns in global memory
+int merge_launch(atr_ctx* ctx, Slot& s, cudaStream_t st, const MergePlan& P, int max_len2, const unsigned char* d_a1, const int64_t* d_o1,
+                 int64_t base1, const unsigned char* d_a2, const int64_t* d_o2, int64_t base2, const unsigned char* d_im, int64_t cn,
+                 const MergeTables& tb, const uint32_t* d_order, atr_merge_result* d_out) {
+    if (cn <= 0) return ATR_OK;
+    if (P.use_warp) {
+        const unsigned wblocks = (unsigned)std::min<int64_t>((cn + 15) / 16, 148 * 16);      // 8 warps per CTA, two pairs per warp
+        if (max_len2 <= 160) k_merge_warp<5><<<wblocks, 256, 0, st>>>(d_a1, d_o1, base1, d_a2, d_o2, base2, d_im, cn, tb, d_order, d_out);
+        else k_merge_warp<10><<<wblocks, 256, 0, st>>>(d_a1, d_o1, base1, d_a2, d_o2, base2, d_im, cn, tb, d_order, d_out);
+        LAUNCHED(ctx);
+        return ATR_OK;
+    }
+    int64_t blocks = std::min<int64_t>((cn + ATR_MERGE_THREADS - 1) / ATR_MERGE_THREADS, 148 * 8);
+    if (P.use_shared) {
+        CU(cudaFuncSetAttribute(k_merge_overlap<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P.smem));
+        k_merge_overlap<true><<<(unsigned)blocks, ATR_MERGE_THREADS, P.smem, st>>>(d_a1, d_o1, base1, d_a2, d_o2, base2, d_im, cn, tb, nullptr, d_out);
+    } else {
+        const size_t budget = (size_t)768 << 20;
+        blocks = std::max<int64_t>(1, std::min<int64_t>(blocks, (int64_t)(budget / (P.col_bytes * ATR_MERGE_THREADS))));
+        int rc = s.gen_scratch.ensure((size_t)blocks * ATR_MERGE_THREADS * P.col_bytes);
+        if (rc) return fail(ctx, rc, "out of device memory (merge scratch)");
+        k_merge_overlap<false><<<(unsigned)blocks, ATR_MERGE_THREADS, 0, st>>>(d_a1, d_o1, base1, d_a2, d_o2, base2, d_im, cn, tb,
+                                                                              s.gen_scratch.as<GCell>(), d_out);
+    }
+    LAUNCHED(ctx);
+    return ATR_OK;
+}
+
 }  // namespace
 
 extern "C" int atr_merge_overlap_batch_host(atr_ctx* ctx, const uint8_t* ascii1, const int64_t* offsets1, const uint8_t* ascii2,
@@ -300,16 +346,10 @@ extern "C" int atr_merge_overlap_batch_host(atr_ctx* ctx, const uint8_t* ascii1,
     if (rc) return rc;
     CU(cudaEventRecord(ctx->ev0, ctx->slot[0].stream));
     CU(cudaStreamWaitEvent(ctx->slot[1].stream, ctx->ev0, 0));
-    // warp-per-pair wavefront kernel whenever its limits hold (ATR_MERGE_KERNEL=thread forces the other one: tests)
     int max_len1 = 0;
     for (int64_t i = 0; i < n; i++) max_len1 = std::max(max_len1, (int)(offsets1[i + 1] - offsets1[i]));
-    const char* force = getenv("ATR_MERGE_KERNEL");
-    const int kmax = (int)thr_mul_of(max_len2, error_rate);
-    const bool use_warp = !(force && force[0] == 't') && max_len2 <= 320 && max_len1 <= 3000 && kmax + 1 <= 250;
-    const size_t col_bytes = (size_t)(max_len2 + 1) * sizeof(GCell);
-    const size_t smem = col_bytes * ATR_MERGE_THREADS;
-    const bool use_shared = smem <= (size_t)200 * 1024;
-    if (use_shared && !use_warp) CU(cudaFuncSetAttribute(k_merge_overlap<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const MergePlan plan = merge_plan(max_len1, max_len2, error_rate);
+    const bool use_warp = plan.use_warp;
     const int64_t max_pairs = 1 << 19;
     int64_t c0 = 0;
     int which = 0;
@@ -320,18 +360,12 @@ extern "C" int atr_merge_overlap_batch_host(atr_ctx* ctx, const uint8_t* ascii1,
         const int64_t b1 = offsets1[c1] - offsets1[c0], b2 = offsets2[c1] - offsets2[c0];
         Slot& s = ctx->slot[which];
         cudaStream_t st = s.stream;
-        int64_t blocks = std::min<int64_t>((cn + ATR_MERGE_THREADS - 1) / ATR_MERGE_THREADS, 148 * 8);
-        if (!use_shared) {
-            const size_t budget = (size_t)768 << 20;
-            blocks = std::max<int64_t>(1, std::min<int64_t>(blocks, (int64_t)(budget / (col_bytes * ATR_MERGE_THREADS))));
-        }
         rc = s.ascii.ensure((size_t)b1 + 16);
         if (!rc) rc = s.ascii2.ensure((size_t)b2 + 16);
         if (!rc) rc = s.offsets.ensure((size_t)(cn + 1) * sizeof(int64_t));
         if (!rc) rc = s.offsets2.ensure((size_t)(cn + 1) * sizeof(int64_t));
         if (!rc) rc = s.out.ensure((size_t)cn * sizeof(atr_merge_result));
         if (!rc && insert_matched) rc = s.win.ensure((size_t)cn);
-        if (!rc && !use_shared && !use_warp) rc = s.gen_scratch.ensure((size_t)blocks * ATR_MERGE_THREADS * col_bytes);
         if (rc) return fail(ctx, rc, "out of device memory (merge staging)");
         if (b1) CU(cudaMemcpyAsync(s.ascii.p, ascii1 + offsets1[c0], (size_t)b1, cudaMemcpyHostToDevice, st));
         if (b2) CU(cudaMemcpyAsync(s.ascii2.p, ascii2 + offsets2[c0], (size_t)b2, cudaMemcpyHostToDevice, st));
@@ -358,23 +392,9 @@ extern "C" int atr_merge_overlap_batch_host(atr_ctx* ctx, const uint8_t* ascii1,
             }
         }
         if (ctx->profile) CU(cudaEventRecord(ctx->pev[0], st));      // profiling mode: the kernel timed alone, chunk after chunk
-        if (use_warp) {
-            const unsigned wblocks = (unsigned)std::min<int64_t>((cn + 15) / 16, 148 * 16);      // 8 warps per CTA, two pairs per warp
-            if (max_len2 <= 160)
-                k_merge_warp<5><<<wblocks, 256, 0, st>>>(s.ascii.as<unsigned char>(), s.offsets.as<int64_t>(), offsets1[c0], s.ascii2.as<unsigned char>(),
-                                                         s.offsets2.as<int64_t>(), offsets2[c0], d_im, cn, tb, d_order, s.out.as<atr_merge_result>());
-            else
-                k_merge_warp<10><<<wblocks, 256, 0, st>>>(s.ascii.as<unsigned char>(), s.offsets.as<int64_t>(), offsets1[c0], s.ascii2.as<unsigned char>(),
-                                                          s.offsets2.as<int64_t>(), offsets2[c0], d_im, cn, tb, d_order, s.out.as<atr_merge_result>());
-        } else if (use_shared)
-            k_merge_overlap<true><<<(unsigned)blocks, ATR_MERGE_THREADS, smem, st>>>(s.ascii.as<unsigned char>(), s.offsets.as<int64_t>(), offsets1[c0],
-                                                                                    s.ascii2.as<unsigned char>(), s.offsets2.as<int64_t>(), offsets2[c0],
-                                                                                    d_im, cn, tb, nullptr, s.out.as<atr_merge_result>());
-        else
-            k_merge_overlap<false><<<(unsigned)blocks, ATR_MERGE_THREADS, 0, st>>>(s.ascii.as<unsigned char>(), s.offsets.as<int64_t>(), offsets1[c0],
-                                                                                  s.ascii2.as<unsigned char>(), s.offsets2.as<int64_t>(), offsets2[c0],
-                                                                                  d_im, cn, tb, s.gen_scratch.as<GCell>(), s.out.as<atr_merge_result>());
-        LAUNCHED(ctx);
+        rc = merge_launch(ctx, s, st, plan, max_len2, s.ascii.as<unsigned char>(), s.offsets.as<int64_t>(), offsets1[c0], s.ascii2.as<unsigned char>(),
+                          s.offsets2.as<int64_t>(), offsets2[c0], d_im, cn, tb, d_order, s.out.as<atr_merge_result>());
+        if (rc) return rc;
         if (ctx->profile) {
             float ms = 0.f;
             CU(cudaEventRecord(ctx->pev[1], st));

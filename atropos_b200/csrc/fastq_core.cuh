@@ -384,12 +384,14 @@ ATR_HD void fq_py_slice(int& a, int& b, int L) {
 
 ATR_HD bool fq_pe_correct(unsigned char* s1, unsigned char* q1, int len1_full, unsigned char* s2, unsigned char* q2, int len2_full,
                           int im0, int im1, int im2, int im3, int action, const unsigned char* __restrict__ comp,
-                          int& changed1, int& changed2, int& new_len1) {
+                          int& changed1, int& changed2, int& new_len1, bool truncate = true) {
     changed1 = changed2 = 0;
     new_len1 = len1_full;
     int L1 = len1_full, L2 = len2_full, len2 = len2_full;
-    if (len1_full > len2_full) L1 = len2_full;
-    else if (len2_full > len1_full) { L2 = len1_full; len2 = len1_full; }
+    if (truncate) {                                      // truncate_seqs=True (:246-255): InsertAdapterCutter; MergeOverlapping passes False
+        if (len1_full > len2_full) L1 = len2_full;
+        else if (len2_full > len1_full) { L2 = len1_full; len2 = len1_full; }
+    }
     const int r1_start = im2, r1_end = im3, r2_start = len2 - im1, r2_end = len2 - im0;
     int n1 = r1_end - r1_start, n2 = r2_end - r2_start;
     if (n1 < 0) n1 = 0;
@@ -439,6 +441,98 @@ ATR_HD bool fq_pe_correct(unsigned char* s1, unsigned char* q1, int len1_full, u
         }
         if (action != 1) break;
     }
-    if (changed1 && len1_full > len2_full) new_len1 = len2_full;
+    if (truncate && changed1 && len1_full > len2_full) new_len1 = len2_full;
     return true;
+}
+
+// ---- MergeOverlapping behind the paired-end modifiers (commands/trim/modifiers.py:864-931) -------------------------
+// What one merged pair needs for its record in the merged output: the two reads' windows after trimming (relative to
+// FqRec.seq_b / qual_b), where the alignment stops in each (r1_stop in read 1, r2_stop in rc(read 2)) and the action.
+struct FqMergeRec {                   // 16 bytes
+    uint16_t lo1, hi1, lo2, hi2;
+    uint16_t r1_stop, r2_stop;
+    uint16_t mlen;                    // length of the merged read
+    uint8_t action;                   // ATR_MERGE_* (merge_core.cuh), 0 = the pair was not merged
+    uint8_t pad;
+};
+// per-pair flags handed from the adapter stage to the merge stage
+#define FQ_PF_MATCH1     1            // read 1 has an adapter match (TrimmedFilter / UntrimmedFilter look at it)
+#define FQ_PF_MATCH2     2
+#define FQ_PF_INSERT     4            // read.insert_overlap: match_insert returned a match (modifiers.py:397)
+#define FQ_PF_CORRECTED1 8            // read.corrected > 0 (modifiers.py:232-233, set by :333)
+#define FQ_PF_CORRECTED2 16
+
+// length of the merged read (:905-922); action 1 keep read 1, 2 take rc(read 2), 3 read 1 + rc(read 2)[r2_stop:],
+// 4 rc(read 2) + read 1[r1_stop:]
+ATR_HD int fq_merged_len(int action, int len1, int len2, int r1_stop, int r2_stop) {
+    if (action == 1) return len1;
+    if (action == 2) return len2;
+    if (action == 3) return len1 + (len2 - r2_stop);
+    return len2 + (len1 - r1_stop);
+}
+// which base / quality of which read is position i of the merged read: src = 1 -> read 1 position j, 2 -> position j of
+// rc(read 2) = complement of read 2's base len2 - 1 - j (quality: read 2's quality at len2 - 1 - j)
+ATR_HD void fq_merged_source(int action, int len1, int len2, int r1_stop, int r2_stop, int i, int& src, int& j) {
+    if (action == 1) { src = 1; j = i; }
+    else if (action == 2) { src = 2; j = i; }
+    else if (action == 3) { if (i < len1) { src = 1; j = i; } else { src = 2; j = r2_stop + (i - len1); } }
+    else { if (i < len2) { src = 2; j = i; } else { src = 1; j = r1_stop + (i - len2); } }
+}
+// byte i of the merged read's FASTQ record: read 1's header, the merged bases, '+' (and the name again if the input
+// repeated it), the merged qualities. s1 / q1 / q2: the reads' windows in the chunk text AFTER error correction;
+// s2: read 2's window BEFORE it (the reference computes read2_rc before it corrects, :891 vs :901-903, and a merged
+// pair's read 2 is never written, so only this copy is ever used); hdr: read 1's header line.
+ATR_HD unsigned char fq_merged_out_byte(const unsigned char* __restrict__ hdr, int H, int name2, const unsigned char* __restrict__ s1,
+                                        const unsigned char* __restrict__ q1, const unsigned char* __restrict__ s2,
+                                        const unsigned char* __restrict__ q2, const unsigned char* __restrict__ comp,
+                                        const FqMergeRec& M, uint32_t i) {
+    const uint32_t w = M.mlen;
+    const int len1 = (int)M.hi1 - (int)M.lo1, len2 = (int)M.hi2 - (int)M.lo2;
+    if (i < (uint32_t)H) return hdr[i];
+    i -= (uint32_t)H;
+    if (i == 0) return '\n';
+    i -= 1;
+    int src, j;
+    if (i < w) {
+        fq_merged_source(M.action, len1, len2, M.r1_stop, M.r2_stop, (int)i, src, j);
+        return src == 1 ? s1[j] : comp[s2[len2 - 1 - j]];
+    }
+    i -= w;
+    if (i == 0) return '\n';
+    i -= 1;
+    const uint32_t P = name2 ? (uint32_t)H : 1u;
+    if (i < P) return i == 0 ? (unsigned char)'+' : hdr[i];
+    i -= P;
+    if (i == 0) return '\n';
+    i -= 1;
+    if (i < w) {
+        fq_merged_source(M.action, len1, len2, M.r1_stop, M.r2_stop, (int)i, src, j);
+        return src == 1 ? q1[j] : q2[len2 - 1 - j];
+    }
+    return '\n';
+}
+ATR_HD uint32_t fq_merged_out_len(int H, int name2, int mlen) {
+    return (uint32_t)H + 1u + (uint32_t)mlen + 1u + (name2 ? (uint32_t)H : 1u) + 1u + (uint32_t)mlen + 1u;
+}
+
+// one pair after the merge alignment: the decision, the optional correction of the overlap, the record for the merged
+// output. res: atr_merge_result of the pair's windows. Returns 0 not merged, 1 merged, -1 the reference raises
+// (KeyError / AtroposError), -2 correction raises. c1 / c2: bases corrected in read 1 / read 2.
+ATR_HD int fq_merge_decide(const atr_merge_result& res, int pflags, int mismatch_action, unsigned char* t1, const FqRec& A, int lo1, int hi1,
+                           unsigned char* t2, const FqRec& B, int lo2, int hi2, const unsigned char* __restrict__ comp,
+                           FqMergeRec& M, int& c1, int& c2) {
+    c1 = c2 = 0;
+    M.lo1 = (uint16_t)lo1; M.hi1 = (uint16_t)hi1; M.lo2 = (uint16_t)lo2; M.hi2 = (uint16_t)hi2;
+    M.r1_stop = res.r1_stop; M.r2_stop = res.r2_stop; M.mlen = 0; M.action = 0; M.pad = 0;
+    if (res.status == ATR_ST_KEYERROR || res.status == ATR_ST_INVALID) return -1;
+    if (res.status != ATR_ST_MATCH) return 0;
+    const int len1 = hi1 - lo1, len2 = hi2 - lo2;
+    if (mismatch_action && res.errors > 0 && !(pflags & FQ_PF_INSERT) && !(pflags & (FQ_PF_CORRECTED1 | FQ_PF_CORRECTED2))) {
+        int nl1;
+        if (!fq_pe_correct(t1 + A.seq_b + lo1, t1 + A.qual_b + lo1, len1, t2 + B.seq_b + lo2, t2 + B.qual_b + lo2, len2,
+                           res.r2_start, res.r2_stop, res.r1_start, res.r1_stop, mismatch_action, comp, c1, c2, nl1, false)) return -2;
+    }
+    M.action = res.action;
+    M.mlen = (uint16_t)fq_merged_len(res.action, len1, len2, res.r1_stop, res.r2_stop);
+    return 1;
 }

@@ -449,7 +449,9 @@ __global__ void __launch_bounds__(256) k_pe_apply(unsigned char* __restrict__ t1
                                                   unsigned long long* __restrict__ adj1, unsigned long long* __restrict__ adj2,
                                                   FqPeCounters* __restrict__ ctr, const __grid_constant__ atr_read_ops ops,
                                                   FqOpsCounters* __restrict__ oc, int mismatch_action,
-                                                  const unsigned char* __restrict__ comp) {
+                                                  const unsigned char* __restrict__ comp, unsigned char* __restrict__ pflags) {
+    // pflags != nullptr: MergeOverlapping follows (k_pe_merge_apply). The filters wait for it; this kernel leaves the
+    // windows and, per pair, what the merge stage and the filters need to know (FQ_PF_*)
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     // per-thread increments, added once per warp at the end (every lane reaches it)
     unsigned n_invalid = 0, n_hit = 0, n_cerr = 0, n_corr = 0, bpc1 = 0, bpc2 = 0, with1 = 0, with2 = 0, n_over = 0, bpn1 = 0, bpn2 = 0;
@@ -493,8 +495,13 @@ __global__ void __launch_bounds__(256) k_pe_apply(unsigned char* __restrict__ t1
             fq_trim_n(t1 + A.seq_b, lo1, hi1, bpn1);
             fq_trim_n(t2 + B.seq_b, lo2, hi2, bpn2);
         }
-        flt = fq_filter(ops, t1 + A.seq_b, lo1, hi1, m1.present != 0, t2 + B.seq_b, lo2, hi2, m2.present != 0, true);
-        if (flt) { lo1 = lo2 = 1; hi1 = hi2 = 0; }
+        if (pflags) {
+            pflags[r] = (unsigned char)((m1.present ? FQ_PF_MATCH1 : 0) | (m2.present ? FQ_PF_MATCH2 : 0) | (hit ? FQ_PF_INSERT : 0) |
+                                        (bpc1 ? FQ_PF_CORRECTED1 : 0) | (bpc2 ? FQ_PF_CORRECTED2 : 0));
+        } else {
+            flt = fq_filter(ops, t1 + A.seq_b, lo1, hi1, m1.present != 0, t2 + B.seq_b, lo2, hi2, m2.present != 0, true);
+            if (flt) { lo1 = lo2 = 1; hi1 = hi2 = 0; }
+        }
         fwin1[2 * r] = (uint16_t)lo1; fwin1[2 * r + 1] = (uint16_t)hi1;
         fwin2[2 * r] = (uint16_t)lo2; fwin2[2 * r + 1] = (uint16_t)hi2;
     }
@@ -529,7 +536,8 @@ __global__ void __launch_bounds__(256) k_pe_post(const unsigned char* __restrict
                                                  const unsigned char* __restrict__ t2, const FqRec* __restrict__ r2, long long n,
                                                  const __grid_constant__ atr_read_ops ops, uint16_t* __restrict__ fwin1,
                                                  uint16_t* __restrict__ fwin2, const unsigned char* __restrict__ flags1,
-                                                 const unsigned char* __restrict__ flags2, FqOpsCounters* __restrict__ oc) {
+                                                 const unsigned char* __restrict__ flags2, FqOpsCounters* __restrict__ oc,
+                                                 unsigned char* __restrict__ pflags) {
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned bpn1 = 0, bpn2 = 0;
     int flt = -1;
@@ -540,8 +548,12 @@ __global__ void __launch_bounds__(256) k_pe_post(const unsigned char* __restrict
             fq_trim_n(t1 + A.seq_b, lo1, hi1, bpn1);
             fq_trim_n(t2 + B.seq_b, lo2, hi2, bpn2);
         }
-        flt = fq_filter(ops, t1 + A.seq_b, lo1, hi1, flags1[r] != 0, t2 + B.seq_b, lo2, hi2, flags2[r] != 0, true);
-        if (flt) { lo1 = lo2 = 1; hi1 = hi2 = 0; }
+        if (pflags) {                                       // MergeOverlapping follows: the filters wait for it
+            pflags[r] = (unsigned char)((flags1[r] ? FQ_PF_MATCH1 : 0) | (flags2[r] ? FQ_PF_MATCH2 : 0));
+        } else {
+            flt = fq_filter(ops, t1 + A.seq_b, lo1, hi1, flags1[r] != 0, t2 + B.seq_b, lo2, hi2, flags2[r] != 0, true);
+            if (flt) { lo1 = lo2 = 1; hi1 = hi2 = 0; }
+        }
         fwin1[2 * r] = (uint16_t)lo1; fwin1[2 * r + 1] = (uint16_t)hi1;
         fwin2[2 * r] = (uint16_t)lo2; fwin2[2 * r + 1] = (uint16_t)hi2;
     }
@@ -553,6 +565,120 @@ __global__ void __launch_bounds__(256) k_pe_post(const unsigned char* __restrict
     fq_warp_add(&oc->too_many_n, flt == 3);
     fq_warp_add(&oc->discarded_trimmed, flt == 4);
     fq_warp_add(&oc->discarded_untrimmed, flt == 5);
+}
+
+// ---- MergeOverlapping behind the paired-end modifiers (fastq_core.cuh: FqMergeRec, fq_merge_decide) ----------------
+struct FqMergeCounters {
+    unsigned long long merged, merged_written, bp_merged, records_corrected, bp_corrected[2], raises, correction_errors;
+};
+
+// window lengths of both reads (-> offsets of the contiguous copies the merge kernels read), the pairs' insert_matched
+// bytes and the chunk's longest windows (h_max: two ints in mapped pinned memory, zeroed by the host before the launch)
+__global__ void __launch_bounds__(256) k_pe_merge_len(const uint16_t* __restrict__ fwin1, const uint16_t* __restrict__ fwin2,
+                                                      const unsigned char* __restrict__ pflags, long long n, long long* __restrict__ len1,
+                                                      long long* __restrict__ len2, unsigned char* __restrict__ insert_matched,
+                                                      int* __restrict__ d_max) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int l1 = 0, l2 = 0;
+    if (r < n) {
+        l1 = (int)fwin1[2 * r + 1] - (int)fwin1[2 * r];
+        l2 = (int)fwin2[2 * r + 1] - (int)fwin2[2 * r];
+        len1[r] = l1; len2[r] = l2;
+        insert_matched[r] = (pflags[r] & FQ_PF_INSERT) ? 1 : 0;
+    }
+    const int m1 = __reduce_max_sync(0xffffffffu, l1), m2 = __reduce_max_sync(0xffffffffu, l2);
+    if ((threadIdx.x & 31) == 0) {
+        if (m1) atomicMax(&d_max[0], m1);
+        if (m2) atomicMax(&d_max[1], m2);
+    }
+}
+__global__ void k_pe_merge_publish(const int* __restrict__ d_max, int* h_max) {
+    if (blockIdx.x == 0 && threadIdx.x < 2) h_max[threadIdx.x] = d_max[threadIdx.x];
+}
+
+// the windows as one contiguous ASCII batch (warp per read)
+__global__ void __launch_bounds__(256) k_pe_merge_gather(const unsigned char* __restrict__ text, const FqRec* __restrict__ recs,
+                                                         const uint16_t* __restrict__ fwin, const long long* __restrict__ offsets,
+                                                         long long n, unsigned char* __restrict__ ascii) {
+    const long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (r >= n) return;
+    const int lane = threadIdx.x & 31;
+    const int lo = fwin[2 * r], hi = fwin[2 * r + 1];
+    const unsigned char* src = text + recs[r].seq_b + lo;
+    unsigned char* dst = ascii + offsets[r];
+    for (int i = lane; i < hi - lo; i += 32) dst[i] = src[i];
+}
+
+// MergeOverlapping's decision per pair (+ the correction of the overlap), MergedReadFilter, then the filters that had
+// to wait (k_pe_apply / k_pe_post with pflags): a merged pair leaves both paired outputs (window mark lo > hi) and
+// gets a record length in the merged output; every other pair meets the remaining filters as usual
+__global__ void __launch_bounds__(256) k_pe_merge_apply(unsigned char* __restrict__ t1, const FqRec* __restrict__ r1,
+                                                        unsigned char* __restrict__ t2, const FqRec* __restrict__ r2,
+                                                        const atr_merge_result* __restrict__ mres, const unsigned char* __restrict__ pflags,
+                                                        long long n, const __grid_constant__ atr_read_ops ops, int mismatch_action,
+                                                        const unsigned char* __restrict__ comp, int write_merged,
+                                                        uint16_t* __restrict__ fwin1, uint16_t* __restrict__ fwin2,
+                                                        FqMergeRec* __restrict__ mrec, long long* __restrict__ mlen64,
+                                                        FqOpsCounters* __restrict__ oc, FqMergeCounters* __restrict__ mc) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int flt = -1;
+    unsigned merged = 0, raises = 0, cerr = 0, corr = 0, bpc1 = 0, bpc2 = 0, bpm = 0;
+    if (r < n) {
+        const FqRec A = r1[r], B = r2[r];
+        int lo1 = fwin1[2 * r], hi1 = fwin1[2 * r + 1], lo2 = fwin2[2 * r], hi2 = fwin2[2 * r + 1];
+        const int pf = pflags[r];
+        FqMergeRec M;
+        int c1 = 0, c2 = 0;
+        const int d = fq_merge_decide(mres[r], pf, mismatch_action, t1, A, lo1, hi1, t2, B, lo2, hi2, comp, M, c1, c2);
+        if (d == -1) raises = 1;
+        if (d == -2) cerr = 1;
+        corr = (c1 || c2); bpc1 = (unsigned)c1; bpc2 = (unsigned)c2;
+        mrec[r] = M;
+        if (d == 1) {
+            merged = 1;
+            if (write_merged) { mlen64[r] = (long long)fq_merged_out_len(A.hdr_len, A.name2, M.mlen); bpm = M.mlen; }
+            lo1 = lo2 = 1; hi1 = hi2 = 0;
+        } else {
+            flt = fq_filter(ops, t1 + A.seq_b, lo1, hi1, (pf & FQ_PF_MATCH1) != 0, t2 + B.seq_b, lo2, hi2, (pf & FQ_PF_MATCH2) != 0, true);
+            if (flt) { lo1 = lo2 = 1; hi1 = hi2 = 0; }
+        }
+        fwin1[2 * r] = (uint16_t)lo1; fwin1[2 * r + 1] = (uint16_t)hi1;
+        fwin2[2 * r] = (uint16_t)lo2; fwin2[2 * r + 1] = (uint16_t)hi2;
+    }
+    fq_warp_add(&mc->merged, merged);
+    fq_warp_add(&mc->merged_written, merged && write_merged);
+    fq_warp_add(&mc->bp_merged, bpm);
+    fq_warp_add(&mc->raises, raises);
+    fq_warp_add(&mc->correction_errors, cerr);
+    fq_warp_add(&mc->records_corrected, corr);
+    fq_warp_add(&mc->bp_corrected[0], bpc1);
+    fq_warp_add(&mc->bp_corrected[1], bpc2);
+    fq_warp_add(&oc->records_written, flt == 0);
+    fq_warp_add(&oc->too_short, flt == 1);
+    fq_warp_add(&oc->too_long, flt == 2);
+    fq_warp_add(&oc->too_many_n, flt == 3);
+    fq_warp_add(&oc->discarded_trimmed, flt == 4);
+    fq_warp_add(&oc->discarded_untrimmed, flt == 5);
+}
+
+// the merged reads' records (warp per merged pair; read 2's bases come from the copy made BEFORE the correction)
+__global__ void __launch_bounds__(256) k_pe_merge_format(const unsigned char* __restrict__ t1, const FqRec* __restrict__ r1,
+                                                         const unsigned char* __restrict__ t2, const FqRec* __restrict__ r2,
+                                                         const unsigned char* __restrict__ ascii2, const long long* __restrict__ off2,
+                                                         const FqMergeRec* __restrict__ mrec, const long long* __restrict__ out_off,
+                                                         const unsigned char* __restrict__ comp, long long n,
+                                                         unsigned char* __restrict__ out, FqInfo* __restrict__ info) {
+    const long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (r >= n) return;
+    const int lane = threadIdx.x & 31;
+    const FqMergeRec M = mrec[r];
+    const FqRec A = r1[r], B = r2[r];
+    const uint32_t total = M.action ? fq_merged_out_len(A.hdr_len, A.name2, M.mlen) : 0u;
+    unsigned char* dst = out + out_off[r];
+    for (uint32_t i = lane; i < total; i += 32)
+        dst[i] = fq_merged_out_byte(t1 + A.hdr_b, A.hdr_len, A.name2, t1 + A.seq_b + M.lo1, t1 + A.qual_b + M.lo1, ascii2 + off2[r],
+                                    t2 + B.qual_b + M.lo2, comp, M, i);
+    if (r == n - 1 && lane == 0) info->out_bytes = (unsigned long long)(out_off[r] + total);
 }
 
 // bytes consumed by the first n records (n < the chunk's complete records): -> mapped pinned host memory

@@ -252,8 +252,9 @@ def trim_file(trimmer, src, dst, block_bytes=1 << 28):
             fout.close()
 
 
-def trim_file_pair(trimmer, src1, src2, dst1, dst2, block_bytes=1 << 27):
-    """Paired-end twin of trim_file for a FastqPairTrimmer: the two inputs advance independently."""
+def trim_file_pair(trimmer, src1, src2, dst1, dst2, block_bytes=1 << 27, dst_merged=None):
+    """Paired-end twin of trim_file for a FastqPairTrimmer: the two inputs advance independently.
+    dst_merged: the --merged-output file of a trimmer created with merge_overlapping=True."""
     opened = []
 
     def _open(x, mode):
@@ -264,6 +265,7 @@ def trim_file_pair(trimmer, src1, src2, dst1, dst2, block_bytes=1 << 27):
         return x
 
     f1, f2, o1, o2 = _open(src1, "rb"), _open(src2, "rb"), _open(dst1, "wb"), _open(dst2, "wb")
+    om = _open(dst_merged, "wb") if dst_merged is not None else None
     try:
         stats, c1, c2 = trimmer.new_stats(), b"", b""
         eof1 = eof2 = False
@@ -276,6 +278,8 @@ def trim_file_pair(trimmer, src1, src2, dst1, dst2, block_bytes=1 << 27):
             outs, stats, consumed = trimmer.trim(t1, t2, final=final, stats=stats)
             o1.write(outs[0].tobytes())
             o2.write(outs[1].tobytes())
+            if om is not None and len(outs) > 2:
+                om.write(outs[2].tobytes())
             c1, c2 = t1[consumed[0]:], t2[consumed[1]:]
             if final:
                 return stats
@@ -297,13 +301,22 @@ class PairTrimStats(object):
         self.records = self.insert_matches = self.overflow = 0
         self.with_adapters, self.bp_in, self.bp_out = [0, 0], [0, 0], [0, 0]
         self.records_corrected, self.bp_corrected = 0, [0, 0]      # ErrorCorrectorMixin.summarize (modifiers.py:352-357)
+        # MergeOverlapping + MergedReadFilter (FastqPairTrimmer(merge_overlapping=True)): pairs merged, merged reads written
+        # (and their bases: the report adds them to bp_written[0]), and the merge stage's own correction counters
+        self.merged = self.merged_written = self.bp_merged_written = 0
+        self.merge_records_corrected, self.merge_bp_corrected = 0, [0, 0]
         self.ops = new_ops_stats()
 
     def merge(self, other):
         merge_ops_stats(self.ops, other.ops)
         self.records_corrected += other.records_corrected
+        self.merged += other.merged
+        self.merged_written += other.merged_written
+        self.bp_merged_written += other.bp_merged_written
+        self.merge_records_corrected += other.merge_records_corrected
         for i in range(2):
             self.bp_corrected[i] += other.bp_corrected[i]
+            self.merge_bp_corrected[i] += other.merge_bp_corrected[i]
             self.errors_back[i] += other.errors_back[i]
             self.errors_front[i] += other.errors_front[i]
             self.adjacent[i] += other.adjacent[i]
@@ -339,8 +352,12 @@ class FastqPairTrimmer(object):
     insert_aligner: atropos_b200.align.InsertAligner with the same sequences."""
 
     def __init__(self, adapter1, adapter2, insert_aligner=None, symmetric=True, min_insert_overlap=1, max_len=256, device=0,
-                 chunk_bytes=0, times=1, mismatch_action=None, **read_ops):
-        """mismatch_action: --correct-mismatches ('liberal', 'conservative', 'N'; insert mode only).
+                 chunk_bytes=0, times=1, mismatch_action=None, merge_overlapping=False, merge_min_overlap=0.9,
+                 merge_error_rate=0.2, merged_output=True, **read_ops):
+        """mismatch_action: --correct-mismatches ('liberal', 'conservative', 'N'; insert mode, or with merge_overlapping).
+        merge_overlapping: --merge-overlapping with --merge-min-overlap / --merge-error-rate (MergeOverlapping as the last
+        modifier, MergedReadFilter as the first filter: commands/trim/__init__.py:546-552, :576-579); trim() then returns
+        a third text, the merged reads (--merged-output). merged_output=False: no such file, merged pairs are discarded.
         insert_aligner given: `--aligner insert` (adapter1 / adapter2 = the one 3' adapter of each read).
         insert_aligner None: the command's default `--aligner adapter`: adapter1 / adapter2 are lists of Adapters (or
         None) for read 1 / read 2, cut independently with `times` rounds each (commands/trim/__init__.py:457-476)."""
@@ -356,8 +373,10 @@ class FastqPairTrimmer(object):
         self.adapter2 = self.adapters[1][0] if self.adapters[1] else None
         self.symmetric, self.min_insert_overlap, self.times = bool(symmetric), int(min_insert_overlap), int(times)
         self.mismatch_action = _abi.MISMATCH_ACTIONS[mismatch_action]
-        if self.mismatch_action and insert_aligner is None:
-            raise ValueError("error correction needs the insert aligner")
+        self.merge = (float(merge_min_overlap), float(merge_error_rate)) if merge_overlapping else None
+        self.merged_output = bool(merged_output)
+        if self.mismatch_action and insert_aligner is None and self.merge is None:
+            raise ValueError("error correction needs the insert aligner or merge_overlapping")
         self.max_len = int(max_len)
         every = self.adapters[0] + self.adapters[1]
         if insert_aligner is not None:
@@ -372,8 +391,9 @@ class FastqPairTrimmer(object):
     def new_stats(self):
         return PairTrimStats(self.max_len, self.max_errors, (len(self.adapters[0]), len(self.adapters[1])))
 
-    def trim(self, text1, text2, final=True, stats=None, out1=None, out2=None):
-        """Returns ((out1, out2) uint8 views, stats, (consumed1, consumed2))."""
+    def trim(self, text1, text2, final=True, stats=None, out1=None, out2=None, out_merged=None):
+        """Returns ((out1, out2) uint8 views, stats, (consumed1, consumed2)); with merge_overlapping the first element is
+        (out1, out2, merged)."""
         b1 = np.frombuffer(text1, dtype=np.uint8) if not isinstance(text1, np.ndarray) else text1
         b2 = np.frombuffer(text2, dtype=np.uint8) if not isinstance(text2, np.ndarray) else text2
         if out1 is None:
@@ -393,11 +413,24 @@ class FastqPairTrimmer(object):
         nout, consumed = (C.c_int64 * 2)(), (C.c_int64 * 2)()
         L = _lib.load()
         h = lambda x: x.handle if x is not None else None
-        rc = L.atr_trim_fastq_pe_host(self.ctx.handle, h(self._iset), h(self._sets[0]), h(self._sets[1]), C.byref(opts),
-                                      b1.ctypes.data if b1.size else None, int(b1.size),
-                                      b2.ctypes.data if b2.size else None, int(b2.size),
-                                      out1.ctypes.data, int(out1.size), out2.ctypes.data, int(out2.size), nout, consumed,
-                                      C.byref(st), C.byref(err))
+        if self.merge is None:
+            rc = L.atr_trim_fastq_pe_host(self.ctx.handle, h(self._iset), h(self._sets[0]), h(self._sets[1]), C.byref(opts),
+                                          b1.ctypes.data if b1.size else None, int(b1.size),
+                                          b2.ctypes.data if b2.size else None, int(b2.size),
+                                          out1.ctypes.data, int(out1.size), out2.ctypes.data, int(out2.size), nout, consumed,
+                                          C.byref(st), C.byref(err))
+        else:
+            mo, ms = _abi.AtrMergeOpts(*self.merge), _abi.AtrMergeStats()
+            nout = (C.c_int64 * 3)()
+            if out_merged is None and self.merged_output:
+                out_merged = np.empty(int(b1.size) + int(b2.size) + 1, dtype=np.uint8)
+            rc = L.atr_trim_fastq_pe_merge_host(self.ctx.handle, h(self._iset), h(self._sets[0]), h(self._sets[1]), C.byref(opts),
+                                                C.byref(mo), b1.ctypes.data if b1.size else None, int(b1.size),
+                                                b2.ctypes.data if b2.size else None, int(b2.size),
+                                                out1.ctypes.data, int(out1.size), out2.ctypes.data, int(out2.size),
+                                                out_merged.ctypes.data if self.merged_output else None,
+                                                int(out_merged.size) if self.merged_output else 0, nout, consumed,
+                                                C.byref(st), C.byref(ms), C.byref(err))
         if rc == _abi.ATR_E_FORMAT:
             raise FormatError(format_error_message((b1, b2), err))
         _lib.check(rc, self.ctx.handle)
@@ -413,4 +446,13 @@ class FastqPairTrimmer(object):
         _add_ops_stats(stats.ops, st.ops)
         if st.overflow:
             raise OverflowError("a removed length exceeds max_len=%d: create the FastqPairTrimmer with a larger max_len" % self.max_len)
+        if self.merge is not None:
+            stats.merged += int(ms.merged)
+            stats.merged_written += int(ms.merged_written)
+            stats.bp_merged_written += int(ms.bp_merged_written)
+            stats.merge_records_corrected += int(ms.records_corrected)
+            for i in range(2):
+                stats.merge_bp_corrected[i] += int(ms.bp_corrected[i])
+            merged = out_merged[:nout[2]] if self.merged_output else np.empty(0, dtype=np.uint8)
+            return (out1[:nout[0]], out2[:nout[1]], merged), stats, (int(consumed[0]), int(consumed[1]))
         return (out1[:nout[0]], out2[:nout[1]]), stats, (int(consumed[0]), int(consumed[1]))

@@ -410,6 +410,44 @@ int  atr_trim_fastq_pe_host(atr_ctx* ctx, const atr_insertset* iset, const atr_a
                             int64_t nbytes2, uint8_t* out1, int64_t out_cap1, uint8_t* out2, int64_t out_cap2,
                             int64_t* out_bytes, int64_t* consumed, atr_trim_pe_stats* stats, atr_fastq_error* err);
 
+/* ---- ... and the merged reads as a third output ("--merge-overlapping [--merged-output FILE]") ---- */
+/* MergeOverlapping(min_overlap, error_rate, mismatch_action) as the LAST modifier of the paired-end command
+ * (commands/trim/__init__.py:546-552) + MergedReadFilter as its FIRST filter (:576-579, filters.py:108-113). */
+typedef struct atr_merge_opts {
+    double  min_overlap;        /* --merge-min-overlap (0.9): a fraction of the shorter read if <= 1, else bases (modifiers.py:871, :877-879) */
+    double  error_rate;         /* --merge-error-rate (0.2) */
+} atr_merge_opts;
+
+typedef struct atr_merge_stats {
+    int64_t merged;             /* MergedReadFilter.records_filtered: pairs whose read 1 became the merged read (read 2 dropped) */
+    int64_t merged_written;     /* of those, records written to the merged output (0 when there is none: they are discarded) */
+    int64_t bp_merged_written;  /* their bases (part of the report's bp_written[0]) */
+    int64_t records_corrected;  /* ErrorCorrectorMixin counters of the MergeOverlapping instance (not in the reference's report: */
+    int64_t bp_corrected[2];    /* ReadPairModifier.summarize comes first in its MRO) */
+} atr_merge_stats;
+
+/* atr_trim_fastq_pe_host with MergeOverlapping behind the other modifiers. Per pair, on what trimming left of the two
+ * reads: Aligner(reverse_complement(read 2), error_rate, flags).locate(read 1) (modifiers.py:864-931; flags SEMIGLOBAL, or
+ * START_WITHIN_SEQ1 | STOP_WITHIN_SEQ2 for a pair the insert aligner matched, read.insert_overlap :397, :882-890); a pair
+ * with matches >= min_overlap is merged into read 1 in one of four ways (:905-922) -- after error correction of the
+ * overlap when opts->mismatch_action is set, the alignment has errors and the pair was neither insert-matched nor
+ * corrected before (:899-903, :232-233) -- and leaves through MergedReadFilter: written to `out_merged` as a single-end
+ * record under read 1's name (FastqFormat, io/seqio.py:686-700), or discarded when out_merged is NULL (no
+ * --merged-output: Formatters.format counts it as discarded, writers.py:151-154). Every other pair goes on to the
+ * remaining filters and the two paired outputs exactly as in atr_trim_fastq_pe_host. Reads up to 4000 nt.
+ * out_bytes / consumed: [0], [1] as above; out_bytes[2] = bytes written to out_merged (out_cap_merged >= nbytes1 +
+ * nbytes2 always suffices). mopts == NULL: identical to atr_trim_fastq_pe_host (mstats may then be NULL too).
+ * Where the reference raises -- reverse_complement KeyError on a byte outside its table (util/__init__.py:479-482),
+ * AtroposError("Invalid alignment while trying to merge read ...") (:923-927) -- the call fails with ATR_E_FORMAT,
+ * err->kind = ATR_FQ_INVALID_MATCH. */
+int  atr_trim_fastq_pe_merge_host(atr_ctx* ctx, const atr_insertset* iset, const atr_adapterset* set1, const atr_adapterset* set2,
+                                  const atr_trim_pe_opts* opts, const atr_merge_opts* mopts,
+                                  const uint8_t* text1, int64_t nbytes1, const uint8_t* text2, int64_t nbytes2,
+                                  uint8_t* out1, int64_t out_cap1, uint8_t* out2, int64_t out_cap2,
+                                  uint8_t* out_merged, int64_t out_cap_merged,
+                                  int64_t* out_bytes, int64_t* consumed, atr_trim_pe_stats* stats, atr_merge_stats* mstats,
+                                  atr_fastq_error* err);
+
 #ifdef __cplusplus
 }
 #endif

@@ -93,8 +93,27 @@ def pe_objects(case):
     return a1, a2, ia
 
 
+def merge_kwargs(case):
+    """FastqPairTrimmer / hostsim keyword arguments of a case run with --merge-overlapping (trim/cli.py:686-691: the merge
+    error rate defaults to -e, else 0.2; --merge-min-overlap to 0.9)"""
+    m = case.get("merge")
+    if m is None:
+        return {}
+    return dict(merge_overlapping=True, merge_min_overlap=m.get("min_overlap", 0.9),
+                merge_error_rate=m.get("error_rate", case["error_rate"] or 0.2), merged_output=m.get("output", True))
+
+
 def pe_check(case, outs, stats):
     res = case["result"]
+    merged = res.get("merged")
+    if merged:
+        # Formatters.summarize (writers.py:161-170) counts the merged output's records and bases with the paired outputs
+        assert bytes(outs[2]) == merged["out"].encode("latin-1")
+        assert stats.merged == merged["records_filtered"]
+        assert stats.merged_written == (stats.merged if case["merge"].get("output", True) else 0)
+        assert stats.ops["records_written"] + stats.merged_written == res["ops"]["records_written"]
+        stats.ops["records_written"] += stats.merged_written
+        stats.bp_out[0] += stats.bp_merged_written
     check_ops(case, stats, paired=True)
     assert bytes(outs[0]) == res["out1"].encode("latin-1")
     assert bytes(outs[1]) == res["out2"].encode("latin-1")

@@ -85,11 +85,11 @@ def ops_stats(rj):
             "records_written": t["formatters"]["records_written"]}
 
 
-def run_reference(text1, text2, error_rate, extra=(), adapter_args=None):
+def run_reference(text1, text2, error_rate, extra=(), adapter_args=None, merge=None):
     from atropos.commands import get_command
     tmp = tempfile.mkdtemp(prefix="fqpegold")
     try:
-        p = {k: os.path.join(tmp, k) for k in ("in1.fq", "in2.fq", "out1.fq", "out2.fq", "rep")}
+        p = {k: os.path.join(tmp, k) for k in ("in1.fq", "in2.fq", "out1.fq", "out2.fq", "merged.fq", "rep")}
         for key, text in (("in1.fq", text1), ("in2.fq", text2)):
             with open(p[key], "w", newline="") as fh:
                 fh.write(text)
@@ -98,6 +98,14 @@ def run_reference(text1, text2, error_rate, extra=(), adapter_args=None):
                 "--report-formats", "json"] + list(extra)
         if error_rate is not None:
             args += ["-e", repr(error_rate)]
+        if merge is not None:                          # --merge-overlapping [--merged-output] (trim/__init__.py:546-552, :576-579)
+            args += ["--merge-overlapping"]
+            if merge.get("output", True):
+                args += ["--merged-output", p["merged.fq"]]
+            if "min_overlap" in merge:
+                args += ["--merge-min-overlap", repr(merge["min_overlap"])]
+            if "error_rate" in merge:
+                args += ["--merge-error-rate", repr(merge["error_rate"])]
         rc, summary = get_command("trim").execute(args)
         if rc != 0:
             from atropos.io.seqio import FormatError, PairedSequenceReader
@@ -124,7 +132,14 @@ def run_reference(text1, text2, error_rate, extra=(), adapter_args=None):
         else:                                          # two AdapterCutters: per read a dict name -> statistics
             cutter = rj["trim"]["modifiers"]["AdapterCutter"]
             ads = [[adapter_stats(st) for st in (d or {}).values()] for d in cutter["adapters"]]
-        return {"ops": ops_stats(rj), "corrected": corrected, "out1": outs[0], "out2": outs[1], "records": rj["record_counts"].get("0", 0),
+        merged = None
+        if merge is not None:
+            mtext = ""
+            if merge.get("output", True) and os.path.exists(p["merged.fq"]):
+                with open(p["merged.fq"], "r", newline="") as fh:
+                    mtext = fh.read()
+            merged = {"out": mtext, "records_filtered": rj["trim"]["filters"]["MergedReadFilter"]["records_filtered"]}
+        return {"ops": ops_stats(rj), "corrected": corrected, "merged": merged, "out1": outs[0], "out2": outs[1], "records": rj["record_counts"].get("0", 0),
                 "with_adapters": cutter["records_with_adapters"], "bp_in": rj["bp_counts"].get("0", [0, 0]),
                 "bp_out": rj["trim"]["formatters"]["bp_written"], "adapters": ads}
     finally:
@@ -137,18 +152,18 @@ def main():
     rng = np.random.default_rng(9101)
     cases = []
 
-    def add(label, recs, error_rate=0.1, edit=None, extra=(), read_ops=None, adapter_args=None, times=1, mismatch_action=None):
+    def add(label, recs, error_rate=0.1, edit=None, extra=(), read_ops=None, adapter_args=None, times=1, mismatch_action=None, merge=None):
         if mismatch_action:
             extra = list(extra) + ["--correct-mismatches", mismatch_action]
         t1, t2 = fastq(recs[0]), fastq(recs[1])
         if edit:
             t1, t2 = edit(t1, t2)
-        res = run_reference(t1, t2, error_rate, extra, adapter_args)
+        res = run_reference(t1, t2, error_rate, extra, adapter_args, merge)
         print(label, {k: (v if not isinstance(v, (str, list)) else (len(v) if isinstance(v, str) else v if len(v) < 3 else len(v)))
                       for k, v in res.items()})
         cases.append({"label": label, "text1": t1, "text2": t2, "error_rate": error_rate, "read_ops": read_ops or {},
                       "mode": "insert" if adapter_args is None else "adapter", "times": times,
-                      "mismatch_action": mismatch_action, "result": res})
+                      "mismatch_action": mismatch_action, "merge": merge, "result": res})
 
     add("pe150", make_pairs(rng, 500, seed=11))
     add("pe150_suffix_names", make_pairs(rng, 300, suffix=True, seed=12))
@@ -213,6 +228,28 @@ def main():
     add("err_names", make_pairs(rng, 6, seed=18), edit=lambda t1, t2: (t1, t2.replace("@pair3", "@other3")))
     add("err_format_file2", make_pairs(rng, 6, seed=19), edit=lambda t1, t2: (t1, t2.replace("\n+\n", "\n-\n", 3).replace("\n-\n", "\n+\n", 2)))
     add("err_truncated_file1", make_pairs(rng, 6, seed=20), edit=lambda t1, t2: ("\n".join(t1.split("\n")[:-3]) + "\n", t2))
+
+    # --- --merge-overlapping --merged-output (MergeOverlapping modifiers.py:864-931 + MergedReadFilter): added last so that the
+    # cases above keep their random draws ---------------------------------------------------------------------------------
+    add("merge_insert", make_pairs(rng, 400, seed=41), merge={})
+    r = make_pairs(rng, 400, ragged=True, lower=0.03, seed=42)
+    add("merge_insert_ragged_ops", (lowq(r[0]), lowq(r[1])), extra=["--trim-n", "-m", "25"], read_ops=dict(trim_n=True, minimum_length=25), merge={})
+    add("merge_adapter_mode", make_pairs(rng, 300, ragged=True, seed=43), adapter_args=["-a", A1, "-A", A2], merge={"min_overlap": 0.5})
+    add("merge_abs_overlap_e01", make_pairs(rng, 300, L=100, seed=44), merge={"min_overlap": 30, "error_rate": 0.1})
+    add("merge_discarded", make_pairs(rng, 200, seed=45), merge={"output": False}, extra=["-m", "40"], read_ops=dict(minimum_length=40))
+    for act, seed in (("liberal", 46), ("conservative", 47), ("N", 48)):
+        r1_, r2_ = synth.synth_pe(300, 150, seed=seed, device="cpu", sub=0.03)
+        recs = make_pairs(rng, 300, seed=seed)
+        recs = ([(n_, bytes(r1_[i].numpy()).decode(), n2_, q_) for i, (n_, s_, n2_, q_) in enumerate(recs[0])],
+                [(n_, bytes(r2_[i].numpy()).decode(), n2_, q_) for i, (n_, s_, n2_, q_) in enumerate(recs[1])])
+        add("merge_correct_" + act.lower(), (noisy(recs[0]), noisy(recs[1])), mismatch_action=act, merge={"min_overlap": 0.6},
+            extra=["--trim-n"], read_ops=dict(trim_n=True))
+    r1_, r2_ = synth.synth_pe(300, 150, seed=49, device="cpu", sub=0.03)
+    recs = make_pairs(rng, 300, seed=49)
+    recs = ([(n_, bytes(r1_[i].numpy()).decode(), n2_, q_) for i, (n_, s_, n2_, q_) in enumerate(recs[0])],
+            [(n_, bytes(r2_[i].numpy()).decode(), n2_, q_) for i, (n_, s_, n2_, q_) in enumerate(recs[1])])
+    add("merge_adapter_mode_correct", (noisy(recs[0]), noisy(recs[1])), adapter_args=["-a", A1, "-A", A2], mismatch_action="liberal",
+        merge={"min_overlap": 0.3, "error_rate": 0.25})
 
     path = os.path.join(HERE, "fastq_trim_pe.json.gz")
     with open(path, "wb") as raw, gzip.GzipFile(fileobj=raw, mode="wb", mtime=0) as fh:

@@ -336,7 +336,9 @@ int sim_trim_fastq_pe(const atr_insert_desc* idesc, const atr_adapter_desc* d1, 
                       const atr_trim_pe_opts* o, const unsigned char* text1, long long nbytes1, const unsigned char* text2,
                       long long nbytes2, unsigned char* out1, unsigned char* out2, long long* out_bytes, long long* consumed,
                       long long* counters, long long* eb1, long long* eb2, long long* adj1, long long* adj2, atr_fastq_error* err,
-                      FqOpsCounters* oc, long long* corrected /* {records, bp1, bp2} */) {
+                      FqOpsCounters* oc, long long* corrected /* {records, bp1, bp2} */,
+                      const atr_merge_opts* mopts /* NULL: no MergeOverlapping */, unsigned char* outm /* NULL: merged reads are discarded */,
+                      long long* mcounters /* {merged, written, bp, records corrected, bp1, bp2} */) {
     // error correction edits the reads in place: work on private copies of the texts, like the GPU path on its chunk
     std::vector<unsigned char> copy1(text1, text1 + nbytes1), copy2(text2, text2 + nbytes2);
     copy1.push_back(0); copy2.push_back(0);
@@ -384,10 +386,18 @@ int sim_trim_fastq_pe(const atr_insert_desc* idesc, const atr_adapter_desc* d1, 
     }
     consumed[0] = o->final_chunk ? nbytes1 : T[0].consumed_for(n);
     consumed[1] = o->final_chunk ? nbytes2 : T[1].consumed_for(n);
-    long long opos1 = 0, opos2 = 0;
+    long long opos1 = 0, opos2 = 0, oposm = 0;
+    std::vector<unsigned short> mh;
+    unsigned char mcomp[256];
+    MergeTables mtb;
+    if (mopts) {
+        atr::build_merge_tables(4000, mopts->min_overlap, mopts->error_rate, mh, mcomp);
+        mtb.thr_mul = mh.data(); mtb.minov = mh.data() + 4001; mtb.comp = mcomp; mtb.max_len = 4000;
+    }
     for (long long r = 0; r < n; r++) {
         FqRec A = R1[(size_t)r], B = R2[(size_t)r];
         counters[0]++; counters[4] += A.seq_len; counters[5] += B.seq_len;
+        int pflags = 0;
         unsigned bpc, bpq, bpg;
         fq_pre_ops(o->ops, 0, text1, A, bpc, bpq, bpg);
         oc->bp_cut[0] += bpc; oc->bp_quality[0] += bpq; oc->bp_nextseq[0] += bpg;
@@ -418,6 +428,7 @@ int sim_trim_fastq_pe(const atr_insert_desc* idesc, const atr_adapter_desc* d1, 
             fq_pe_decide(ins, fb1, fb2, len1, len2, o->min_insert_overlap, o->symmetric, o->mismatch_action, m1, m2, hit, invalid, correct, im);
             if (invalid) { err->kind = ATR_FQ_INVALID_MATCH; err->record = r; return ATR_E_FORMAT; }
             counters[1] += hit;
+            if (hit) pflags |= FQ_PF_INSERT;
             if (correct) {
                 atr::HostInsert hi;
                 std::string msg;
@@ -429,6 +440,8 @@ int sim_trim_fastq_pe(const atr_insert_desc* idesc, const atr_adapter_desc* d1, 
                                    im[3], o->mismatch_action, hi.comp.data(), c1, c2, nl1)) { err->kind = ATR_FQ_CORRECTION; err->record = r; return ATR_E_FORMAT; }
                 if (c1 || c2) corrected[0]++;
                 corrected[1] += c1; corrected[2] += c2;
+                if (c1) pflags |= FQ_PF_CORRECTED1;
+                if (c2) pflags |= FQ_PF_CORRECTED2;
                 len1 = nl1;
             }
             FqApply ap;
@@ -487,6 +500,36 @@ int sim_trim_fastq_pe(const atr_insert_desc* idesc, const atr_adapter_desc* d1, 
             fq_trim_n(text1 + A.seq_b, lo1, hi1, bpn); oc->bp_n_ends[0] += bpn;
             fq_trim_n(text2 + B.seq_b, lo2, hi2, bpn); oc->bp_n_ends[1] += bpn;
         }
+        if (mopts) {                                     // MergeOverlapping, then MergedReadFilter in front of the other filters
+            if (m1.present) pflags |= FQ_PF_MATCH1;
+            if (m2.present) pflags |= FQ_PF_MATCH2;
+            const int l1 = hi1 - lo1, l2 = hi2 - lo2;
+            if (l1 > 4000 || l2 > 4000) return ATR_E_LIMIT;
+            atr_merge_result mres;
+            std::vector<GCell> col((size_t)l2 + 1);
+            std::vector<unsigned char> before(text2 + B.seq_b + lo2, text2 + B.seq_b + hi2);      // read 2 before any correction
+            before.push_back(0);
+            merge_pair(text1 + A.seq_b + lo1, l1, text2 + B.seq_b + lo2, l2, (pflags & FQ_PF_INSERT) ? 1 : 0, mtb, col.data(), 1, &mres);
+            FqMergeRec M;
+            int c1 = 0, c2 = 0;
+            const int d = fq_merge_decide(mres, pflags, o->mismatch_action, mtext1, A, lo1, hi1, mtext2, B, lo2, hi2, mcomp, M, c1, c2);
+            if (d == -1) { err->kind = ATR_FQ_INVALID_MATCH; err->record = r; return ATR_E_FORMAT; }
+            if (d == -2) { err->kind = ATR_FQ_CORRECTION; err->record = r; return ATR_E_FORMAT; }
+            if (c1 || c2) mcounters[3]++;
+            mcounters[4] += c1; mcounters[5] += c2;
+            if (d == 1) {
+                mcounters[0]++;
+                if (outm) {
+                    const uint32_t total = fq_merged_out_len(A.hdr_len, A.name2, M.mlen);
+                    for (uint32_t i = 0; i < total; i++)
+                        outm[oposm + i] = fq_merged_out_byte(text1 + A.hdr_b, A.hdr_len, A.name2, text1 + A.seq_b + lo1, text1 + A.qual_b + lo1,
+                                                             before.data(), text2 + B.qual_b + lo2, mcomp, M, i);
+                    oposm += total;
+                    mcounters[1]++; mcounters[2] += M.mlen;
+                }
+                continue;
+            }
+        }
         const int flt = fq_filter(o->ops, text1 + A.seq_b, lo1, hi1, m1.present != 0, text2 + B.seq_b, lo2, hi2, m2.present != 0, true);
         sim_count_filter(*oc, flt);
         if (flt) continue;
@@ -499,6 +542,7 @@ int sim_trim_fastq_pe(const atr_insert_desc* idesc, const atr_adapter_desc* d1, 
         opos2 += total;
     }
     out_bytes[0] = opos1; out_bytes[1] = opos2;
+    if (mopts) out_bytes[2] = oposm;
     return 0;
 }
 

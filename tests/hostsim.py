@@ -51,7 +51,8 @@ def lib():
                                         C.c_longlong, C.c_char_p, C.c_longlong, C.c_void_p, C.c_void_p,
                                         C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(_abi.AtrFastqError),
-                                        C.POINTER(SimOpsCounters), C.POINTER(C.c_longlong)]
+                                        C.POINTER(SimOpsCounters), C.POINTER(C.c_longlong), C.POINTER(_abi.AtrMergeOpts),
+                                        C.c_void_p, C.POINTER(C.c_longlong)]
         L.sim_trim_fastq_pe.restype = C.c_int
         L.sim_merge_overlap.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_double, C.c_double,
                                         C.POINTER(_abi.AtrMergeResult)]
@@ -167,7 +168,8 @@ def trim_fastq(text, adapters, times=1, max_len=512, final=True, **read_ops):
 
 
 def trim_fastq_pe(text1, text2, adapter1, adapter2, insert_aligner=None, symmetric=True, min_insert_overlap=1, max_len=256,
-                  final=True, times=1, mismatch_action=None, **read_ops):
+                  final=True, times=1, mismatch_action=None, merge_overlapping=False, merge_min_overlap=0.9, merge_error_rate=0.2,
+                  merged_output=True, **read_ops):
     """CPU run of the paired-end FASTQ path's device functions (insert mode, or adapter mode when insert_aligner is
     None and adapter1 / adapter2 are lists). Returns ((out1, out2), PairTrimStats, consumed)."""
     import numpy as np
@@ -194,13 +196,17 @@ def trim_fastq_pe(text1, text2, adapter1, adapter2, insert_aligner=None, symmetr
     o1 = np.empty(len(text1) + 1, dtype=np.uint8)
     o2 = np.empty(len(text2) + 1, dtype=np.uint8)
     counters = np.zeros(9, dtype=np.int64)
-    nout, consumed = (C.c_longlong * 2)(), (C.c_longlong * 2)()
+    nout, consumed = (C.c_longlong * 3)(), (C.c_longlong * 2)()
     err = _abi.AtrFastqError()
+    mo = _abi.AtrMergeOpts(float(merge_min_overlap), float(merge_error_rate)) if merge_overlapping else None
+    om = np.empty(len(text1) + len(text2) + 1, dtype=np.uint8)
+    mcounters = (C.c_longlong * 6)()
     rc = lib().sim_trim_fastq_pe(iref, arrs[0], len(ads[0]), arrs[1], len(ads[1]), stats.errors_front[0].ctypes.data,
                                  stats.errors_front[1].ctypes.data, C.byref(opts), text1, len(text1), text2, len(text2),
                                  o1.ctypes.data, o2.ctypes.data, nout, consumed, counters.ctypes.data,
                                  stats.errors_back[0].ctypes.data, stats.errors_back[1].ctypes.data,
-                                 stats.adjacent[0].ctypes.data, stats.adjacent[1].ctypes.data, C.byref(err), C.byref(oc), corrected)
+                                 stats.adjacent[0].ctypes.data, stats.adjacent[1].ctypes.data, C.byref(err), C.byref(oc), corrected,
+                                 C.byref(mo) if mo is not None else None, om.ctypes.data if merged_output else None, mcounters)
     if rc == _abi.ATR_E_FORMAT:
         raise fastq.FormatError(fastq.format_error_message((np.frombuffer(text1, dtype=np.uint8),
                                                             np.frombuffer(text2, dtype=np.uint8)), err))
@@ -211,4 +217,8 @@ def trim_fastq_pe(text1, text2, adapter1, adapter2, insert_aligner=None, symmetr
     stats.records, stats.insert_matches, stats.overflow = c[0], c[1], c[8]
     stats.with_adapters, stats.bp_in, stats.bp_out = [c[2], c[3]], [c[4], c[5]], [c[6], c[7]]
     stats.records_corrected, stats.bp_corrected = int(corrected[0]), [int(corrected[1]), int(corrected[2])]
+    if merge_overlapping:
+        stats.merged, stats.merged_written, stats.bp_merged_written = int(mcounters[0]), int(mcounters[1]), int(mcounters[2])
+        stats.merge_records_corrected, stats.merge_bp_corrected = int(mcounters[3]), [int(mcounters[4]), int(mcounters[5])]
+        return (bytes(o1[:nout[0]]), bytes(o2[:nout[1]]), bytes(om[:nout[2]]) if merged_output else b""), stats, (consumed[0], consumed[1])
     return (bytes(o1[:nout[0]]), bytes(o2[:nout[1]])), stats, (consumed[0], consumed[1])

@@ -53,9 +53,9 @@ def test_pe_against_reference_cli(case):
     res = case["result"]
     if "error" in res:
         with pytest.raises(fastq.FormatError) as ei:
-            hostsim.trim_fastq_pe(t1, t2, a1, a2, ia, times=case.get("times", 1), mismatch_action=case.get("mismatch_action"), **case.get("read_ops", {}))
+            hostsim.trim_fastq_pe(t1, t2, a1, a2, ia, times=case.get("times", 1), mismatch_action=case.get("mismatch_action"), **fastq_cases.merge_kwargs(case), **case.get("read_ops", {}))
         assert str(ei.value) == res["error"]
         return
-    outs, stats, consumed = hostsim.trim_fastq_pe(t1, t2, a1, a2, ia, times=case.get("times", 1), mismatch_action=case.get("mismatch_action"), **case.get("read_ops", {}))
+    outs, stats, consumed = hostsim.trim_fastq_pe(t1, t2, a1, a2, ia, times=case.get("times", 1), mismatch_action=case.get("mismatch_action"), **fastq_cases.merge_kwargs(case), **case.get("read_ops", {}))
     assert consumed == (len(t1), len(t2))
     fastq_cases.pe_check(case, outs, stats)

@@ -83,7 +83,8 @@ def test_pe_against_reference_cli(case, chunk):
     a1, a2, ia = fastq_cases.pe_objects(case)
     t1, t2 = case["text1"].encode("latin-1"), case["text2"].encode("latin-1")
     res = case["result"]
-    tr = fastq.FastqPairTrimmer(a1, a2, ia, chunk_bytes=chunk, times=case.get("times", 1), mismatch_action=case.get("mismatch_action"), **case.get("read_ops", {}))
+    tr = fastq.FastqPairTrimmer(a1, a2, ia, chunk_bytes=chunk, times=case.get("times", 1), mismatch_action=case.get("mismatch_action"),
+                                **fastq_cases.merge_kwargs(case), **case.get("read_ops", {}))
     if "error" in res:
         with pytest.raises(fastq.FormatError) as ei:
             tr.trim(t1, t2)
@@ -91,7 +92,28 @@ def test_pe_against_reference_cli(case, chunk):
         return
     outs, stats, consumed = tr.trim(t1, t2)
     assert consumed == (len(t1), len(t2))
-    fastq_cases.pe_check(case, (outs[0].tobytes(), outs[1].tobytes()), stats)
+    fastq_cases.pe_check(case, tuple(o.tobytes() for o in outs), stats)
+
+
+def test_pe_merge_streaming_and_both_kernels(monkeypatch):
+    """--merge-overlapping through streaming calls with unequal cuts (merged text and counters add up), and with the
+    thread-per-pair merge kernel forced instead of the warp wavefront"""
+    case = [c for c in PE_CASES if c["label"] == "merge_correct_liberal"][0]
+    a1, a2, ia = fastq_cases.pe_objects(case)
+    t1, t2 = case["text1"].encode("latin-1"), case["text2"].encode("latin-1")
+    kw = dict(times=case.get("times", 1), mismatch_action=case.get("mismatch_action"), **fastq_cases.merge_kwargs(case), **case.get("read_ops", {}))
+    tr = fastq.FastqPairTrimmer(a1, a2, ia, chunk_bytes=8192, **kw)
+    parts, stats, p1, p2 = [[], [], []], tr.new_stats(), 0, 0
+    for c1, c2 in [(20_000, 9_000), (50_000, 80_000), (len(t1), len(t2))]:
+        outs, stats, consumed = tr.trim(t1[p1:c1], t2[p2:c2], final=(c1, c2) == (len(t1), len(t2)), stats=stats)
+        for k in range(3):
+            parts[k].append(outs[k].tobytes())
+        p1 += consumed[0]; p2 += consumed[1]
+    assert (p1, p2) == (len(t1), len(t2))
+    fastq_cases.pe_check(case, tuple(b"".join(p) for p in parts), stats)
+    monkeypatch.setenv("ATR_MERGE_KERNEL", "thread")
+    outs, stats, consumed = fastq.FastqPairTrimmer(a1, a2, ia, **kw).trim(t1, t2)
+    fastq_cases.pe_check(case, tuple(o.tobytes() for o in outs), stats)
 
 
 def test_pe_streaming_calls_reassemble():
