@@ -602,6 +602,18 @@ __global__ void __launch_bounds__(ATR_K1F_THREADS) k_filter_sa(const __grid_cons
 
 struct QgTailItem { uint32_t read; short hmin, hmax; };
 
+// warp-aggregated push into the CTA's tail queue (one shared-memory atomic per warp instead of one per thread: the
+// per-thread form serialised, 4.7 active lanes per atomic in the profile). Called by every thread of the warp.
+__device__ __forceinline__ void qg_tail_push(bool want, const QgTailItem& q, QgTailItem* __restrict__ s_tq, int* __restrict__ s_tq_count) {
+    const unsigned m = __ballot_sync(0xffffffffu, want);
+    if (m == 0u) return;
+    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(s_tq_count, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (want) s_tq[base + __popc(m & ((1u << lane) - 1u))] = q;
+}
+
 // classification + record store / list appends of one read. Called by EVERY thread of the CTA (warp ballots inside);
 // `active`: this thread holds a read. im = (imin << 16) | imax of the tail pass, 0 if it did not run.
 __device__ __forceinline__ void qg_finish(const AdapterK1a& ad, bool active, uint32_t read, int lo, int n, int hmin, int hmax,
@@ -750,16 +762,19 @@ __global__ void __launch_bounds__(ATR_QG_THREADS, ATR_QG_MINCTAS) k_filter_qg(co
                     if (listed) s_hl[base + __popc(m & ((1u << lane) - 1u))] = (unsigned char)tid;
                 }
             }
-            if (last_chunk && live && !listed) {                        // no piece anywhere: a partial match at the read end?
-                if (qg_need_tail<WORD>(ad, s_sa_peq, rd, lo, n, -0x7fffffff)) {
-                    QgTailItem q;
-                    q.read = (uint32_t)r; q.hmin = 32767; q.hmax = -32768;
-                    s_tq[atomicAdd(&s_tq_count, 1)] = q;
-                } else {
-                    Best b;
-                    b.ref_stop = ad.m; b.q_stop = n; b.cost = ad.m + n; b.origin = 0; b.matches = 0;
-                    finalize(ad, b, n, out + r);
+            {
+                bool push = false;
+                if (last_chunk && live && !listed) {                    // no piece anywhere: a partial match at the read end?
+                    push = qg_need_tail<WORD>(ad, s_sa_peq, rd, lo, n, -0x7fffffff);
+                    if (!push) {
+                        Best b;
+                        b.ref_stop = ad.m; b.q_stop = n; b.cost = ad.m + n; b.origin = 0; b.matches = 0;
+                        finalize(ad, b, n, out + r);
+                    }
                 }
+                QgTailItem q;
+                q.read = (uint32_t)r; q.hmin = 32767; q.hmax = -32768;
+                qg_tail_push(push, q, s_tq, &s_tq_count);
             }
             __syncthreads();
             // ---- A2: one thread per read WITH hits (dense): verify every hit of the chunk; in the last chunk the verbatim-
@@ -798,14 +813,14 @@ __global__ void __launch_bounds__(ATR_QG_THREADS, ATR_QG_MINCTAS) k_filter_qg(co
                     else {
                         exact = sa_exact(ad, rdt, lo_t, n_t, vmin, vmax);
                         if (!exact) need_tail = qg_need_tail<WORD>(ad, s_sa_peq, rdt, lo_t, n_t, vmax);
-                        if (need_tail) {
-                            QgTailItem q;
-                            q.read = (uint32_t)(t0 + t);
-                            q.hmin = (short)(vmax == -0x7fffffff ? 32767 : vmin);
-                            q.hmax = (short)(vmax == -0x7fffffff ? -32768 : vmax);
-                            s_tq[atomicAdd(&s_tq_count, 1)] = q;
-                        }
                     }
+                }
+                {
+                    QgTailItem q;
+                    q.read = (uint32_t)(t0 + t);
+                    q.hmin = (short)(vmax == -0x7fffffff ? 32767 : vmin);
+                    q.hmax = (short)(vmax == -0x7fffffff ? -32768 : vmax);
+                    qg_tail_push(need_tail, q, s_tq, &s_tq_count);
                 }
                 if (last_chunk)
                     qg_finish(ad, act && !need_tail, (uint32_t)(t0 + t), lo_t, n_t, vmin, vmax, exact, 0, out, narrow, wide, refine, counters);

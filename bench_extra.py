@@ -163,6 +163,26 @@ def main():
                       "h2d_bytes": int(texts[0].numel() + texts[1].numel()), "d2h_bytes": int(o[0].size + o[1].size),
                       "insert_matches": int(st.insert_matches), "with_adapters": st.with_adapters}))
 
+    # ... and the same with --merge-overlapping --merged-output (atr_trim_fastq_pe_merge_host: merge kernels on what trimming left)
+    trm = fastq.FastqPairTrimmer(Adapter(synth.TRUSEQ_R1, BACK, **kw), Adapter(synth.TRUSEQ_R2, BACK, **kw),
+                                 InsertAligner(synth.TRUSEQ_R1, synth.TRUSEQ_R2, match_probability=rmp,
+                                               max_insert_mismatch_frac=0.1, max_adapter_mismatch_frac=0.1), max_len=L,
+                                 merge_overlapping=True, merge_min_overlap=0.9, merge_error_rate=0.2)
+    outm = torch.empty(texts[0].numel() + texts[1].numel() + 1, dtype=torch.uint8, pin_memory=True)
+    runm = lambda: trm.trim(texts[0].numpy(), texts[1].numpy(), out1=outs[0].numpy(), out2=outs[1].numpy(), out_merged=outm.numpy())
+    runm()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(2):
+        om, stm, _ = runm()
+    dtm = (time.perf_counter() - t0) / 2
+    print(json.dumps({"config": "cfg3 PE 2x150 FASTQ text -> trimmed + merged FASTQ text (atr_trim_fastq_pe_merge_host, --aligner insert "
+                                "--merge-overlapping --merged-output)",
+                      "pairs": n, "ms": dtm * 1e3, "M_pairs_per_s": n / dtm / 1e6,
+                      "h2d_bytes": int(texts[0].numel() + texts[1].numel()), "d2h_bytes": int(om[0].size + om[1].size + om[2].size),
+                      "merged_pairs": int(stm.merged), "merged_bytes": int(om[2].size), "insert_matches": int(stm.insert_matches)}))
+    del outm, om
+
     # ---- MergeOverlapping: pairs of the cfg3 shape after trimming, i.e. both reads cut to the fragment ---
     import numpy as np
     del texts, o
