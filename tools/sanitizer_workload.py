@@ -4,7 +4,7 @@
     compute-sanitizer --tool memcheck python tools/sanitizer_workload.py
 
 K1 funnel both ways (q-gram first stage and Shift-And), the Myers filter path (FRONT), anchored and general kernels, a panel
-with rounds, K2 packed + byte kernels, the merge kernels, the packers and both FASTQ paths -- each checked against the
+with rounds, K2 packed + byte kernels, the merge kernels, the packers, the single-end and the paired-end FASTQ paths (with MergeOverlapping) -- each checked against the
 oracle or the golden records, so a sanitizer run is also a parity run. Prints 'sanitizer workload ok'."""
 import gzip
 import json
@@ -88,6 +88,16 @@ def main():
         tr = fastq.FastqTrimmer(fastq_cases.adapters_of(case), times=case["times"], chunk_bytes=20000, **case.get("read_ops", {}))
         out, st, _ = tr.trim(case["text"].encode("latin-1"))
         assert bytes(out) == case["result"]["out"].encode("latin-1"), case["label"]
+    # paired-end FASTQ paths: insert mode with correction, adapter mode, and MergeOverlapping with a merged output
+    for case in fastq_cases.pe_cases():
+        if case["label"] not in ("ragged_lower", "correct_liberal", "adapter_mode_panel_times2_ops", "merge_insert_ragged_ops",
+                                 "merge_correct_liberal", "merge_adapter_mode_correct", "merge_discarded"):
+            continue
+        a1, a2, ia = fastq_cases.pe_objects(case)
+        tr = fastq.FastqPairTrimmer(a1, a2, ia, chunk_bytes=30000, times=case.get("times", 1), mismatch_action=case.get("mismatch_action"),
+                                    **fastq_cases.merge_kwargs(case), **case.get("read_ops", {}))
+        outs, st, _ = tr.trim(case["text1"].encode("latin-1"), case["text2"].encode("latin-1"))
+        fastq_cases.pe_check(case, tuple(o.tobytes() for o in outs), st)
     print("sanitizer workload ok")
 
 
