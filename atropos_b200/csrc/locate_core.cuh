@@ -338,12 +338,15 @@ ATR_HD bool myers_filter(const AdapterK1a& ad, const WORD* __restrict__ peq, con
         // FRONT / ANYWHERE (:349-352 with min_n = 0): the first column costs 0 in every row, and an alignment
         // may start inside the adapter, so the bound on D[m][j] depends on j (AdapterK1a.thrJ). Plain loop.
         st.Pv = 0; st.score = 0;
-        for (int j = 1; j <= n; j++) {
+        // columns 1..m one by one (the bound changes with j); from column m on the bound is thrJ[m] == k and the
+        // word-wise loops below take over (FRONT / ANYWHERE always have stop_in_query)
+        const int head = (ad.thrJ[m] == k && stop_in_query) ? atr_min(n, m) : n;
+        for (int j = 1; j <= head; j++) {
             const int pos = lo + j - 1;
             myers_col(st, peq[(codes[pos >> 3] >> ((pos & 7) * 4)) & 15u]);
             if (st.score <= (int)ad.thrJ[j < m ? j : m]) { jmin = atr_min(jmin, j); jmax = j; }
         }
-        min_n = n;                                     // the loops below have nothing left to do
+        min_n = head;
     }
     int j = min_n;                                     // columns done so far
     int pos = lo + min_n;                              // packed position of the next column's base
