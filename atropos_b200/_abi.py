@@ -69,7 +69,7 @@ class AtrReadOps(C.Structure):
                 ("quality_back", C.c_int32), ("quality_base", C.c_int32), ("trim_n", C.c_int32),
                 ("minimum_length", C.c_int32), ("maximum_length", C.c_int32), ("discard_trimmed", C.c_int32),
                 ("discard_untrimmed", C.c_int32), ("nextseq_trim", C.c_int32 * 2), ("legacy_first", C.c_int32),
-                ("pad", C.c_int32), ("max_n", C.c_double)]
+                ("pair_filter_both", C.c_int32), ("max_n", C.c_double)]
 
 
 class AtrReadOpsStats(C.Structure):
@@ -83,7 +83,7 @@ OPS_STAT_KEYS = ("too_short", "too_long", "too_many_n", "discarded_trimmed", "di
 
 def make_read_ops(cut=(), cut2=(), quality_cutoff=None, quality_base=33, trim_n=False, minimum_length=None,
                   maximum_length=None, max_n=None, discard_trimmed=False, discard_untrimmed=False, legacy_first=False,
-                  nextseq_trim=None):
+                  nextseq_trim=None, pair_filter="any"):
     """The `trim` command's options (trim/cli.py) -> atr_read_ops. cut / cut2: the -u / -U values (lists of ints);
     quality_cutoff: -q as the command normalises it, [back] or [front, back] (trim/cli.py:750-754)."""
     o = AtrReadOps()
@@ -107,6 +107,9 @@ def make_read_ops(cut=(), cut2=(), quality_cutoff=None, quality_base=33, trim_n=
     o.discard_trimmed, o.discard_untrimmed = int(bool(discard_trimmed)), int(bool(discard_untrimmed))
     # paired-end legacy mode (trim/cli.py:629-645): nothing on the command line touches read 2 -> filters see read 1 only
     o.legacy_first = int(bool(legacy_first))
+    if pair_filter not in ("any", "both"):
+        raise ValueError("pair_filter must be 'any' or 'both'")
+    o.pair_filter_both = int(pair_filter == "both")      # --pair-filter: PairedWrapper.min_affected (trim/__init__.py:556-557)
     # --nextseq-trim: NextseqQualityTrimmer on both reads, on read 1 only in legacy mode (PairedEndModifiers.add_modifier)
     o.nextseq_trim[0] = -1 if nextseq_trim is None else int(nextseq_trim)
     o.nextseq_trim[1] = -1 if (nextseq_trim is None or legacy_first) else int(nextseq_trim)

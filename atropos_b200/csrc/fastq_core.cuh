@@ -362,8 +362,11 @@ ATR_HD int fq_filter_one(const atr_read_ops& o, const unsigned char* __restrict_
 ATR_HD int fq_filter(const atr_read_ops& o, const unsigned char* __restrict__ seq1, int lo1, int hi1, bool matched1,
                      const unsigned char* __restrict__ seq2, int lo2, int hi2, bool matched2, bool paired) {
     for (int which = 1; which <= 5; which++) {
-        if (fq_filter_one(o, seq1, lo1, hi1, matched1, which)) return which;
-        if (paired && !o.legacy_first && fq_filter_one(o, seq2, lo2, hi2, matched2, which)) return which;
+        const int f1 = fq_filter_one(o, seq1, lo1, hi1, matched1, which);
+        if (!paired || o.legacy_first) { if (f1) return which; continue; }
+        if (o.pair_filter_both) {                        // PairedWrapper(min_affected = 2), filters.py:86-95
+            if (f1 && fq_filter_one(o, seq2, lo2, hi2, matched2, which)) return which;
+        } else if (f1 || fq_filter_one(o, seq2, lo2, hi2, matched2, which)) return which;
     }
     return 0;
 }

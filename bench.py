@@ -83,10 +83,40 @@ class ClockSampler(object):
 
     def __init__(self, index=0):
         self.index, self.rows, self.proc, self.marks = index, [], None, []
+        self.nvml_rows, self.nvml_on, self.nvml_thread = [], False, None
 
     def mark(self):
-        """remember how many samples existed at this point (start / end of the kernel-only timed region)"""
+        """remember how many samples existed at this point (start / end of the kernel-only timed region). Between the
+        two marks an in-process NVML poller (same counters as nvidia-smi's: SM clock, clocks-event reasons) samples every
+        ~1 ms: nvidia-smi's 50 ms period puts 0-1 samples into a 25 ms timed region."""
         self.marks.append(len(self.rows))
+        if len(self.marks) == 1:
+            self._nvml_start()
+        elif len(self.marks) == 2:
+            self.nvml_on = False
+            if self.nvml_thread is not None:
+                self.nvml_thread.join(timeout=2)
+
+    def _nvml_start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            return
+        self.nvml_on = True
+
+        def poll():
+            while self.nvml_on and len(self.nvml_rows) < 100000:
+                try:
+                    self.nvml_rows.append((pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM),
+                                           pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)))
+                except Exception:
+                    break
+                time.sleep(0.001)
+        self.nvml_thread = threading.Thread(target=poll, daemon=True)
+        self.nvml_thread.start()
 
     def start(self):
         try:
@@ -122,8 +152,23 @@ class ClockSampler(object):
                 for nm, v in zip(names, r[5:9]):
                     if v.lower().startswith("active"):
                         reasons.add(nm)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm), "samples_in_timed_region": len(timed)}
+        out = {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+               "reasons": sorted(reasons), "samples": len(sm), "samples_in_timed_region": len(timed)}
+        if self.nvml_rows:
+            # NVML reason bits (nvml.h nvmlClocksEventReasons*): 0x4 sw_power_cap, 0x8 hw_slowdown, 0x20 sw_thermal, 0x40 hw_thermal
+            bits = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown"}
+            clk = sorted(c for c, _ in self.nvml_rows)
+            seen = set()
+            for _, r in self.nvml_rows:
+                for b, nm in bits.items():
+                    if r & b:
+                        seen.add(nm)
+            out["timed_region_nvml"] = {"samples": len(clk), "sm_mhz_median": clk[len(clk) // 2], "sm_mhz_min": clk[0],
+                                        "reasons": sorted(seen)}
+            if len(timed) < 2:
+                out["sm_mhz"] = clk[len(clk) // 2]
+            out["reasons"] = sorted(set(out["reasons"]) | seen)
+        return out
 
 
 # ------------------------------------------------------------------------------------------------

@@ -311,7 +311,8 @@ typedef struct atr_read_ops {
                                  nextseq_trim_index _qualtrim.pyx:52-84): after the cut, before -q ("CGQAW") */
     int32_t legacy_first;     /* paired-end "legacy mode" (paired == 'first', trim/cli.py:629-645: no option touches read 2):
                                  the filters look at read 1 only (SingleWrapper, filters.py:54-61) */
-    int32_t pad;
+    int32_t pair_filter_both; /* --pair-filter both: PairedWrapper(min_affected = 2), a pair is discarded only if BOTH reads
+                                 meet the filter's criterion (filters.py:63-95; read 2 is only looked at when read 1 does) */
     double  max_n;            /* --max-n: NContentFilter, < 0 = off; < 1 is a proportion (filters.py:142-168) */
 } atr_read_ops;
 

@@ -251,6 +251,15 @@ def main():
     add("merge_adapter_mode_correct", (noisy(recs[0]), noisy(recs[1])), adapter_args=["-a", A1, "-A", A2], mismatch_action="liberal",
         merge={"min_overlap": 0.3, "error_rate": 0.25})
 
+    # --- --pair-filter both: a pair is discarded only if both reads meet a filter's criterion (PairedWrapper min_affected 2) ----
+    r = make_pairs(rng, 400, ragged=True, seed=50)
+    add("pair_filter_both", (lowq(r[0]), lowq(r[1])), extra=["--pair-filter", "both", "--trim-n", "-m", "60", "--max-n", "1"],
+        read_ops=dict(pair_filter="both", trim_n=True, minimum_length=60, max_n=1))
+    r = make_pairs(rng, 300, ragged=True, seed=51)
+    add("pair_filter_both_adapter_mode_merge", (lowq(r[0]), lowq(r[1])), adapter_args=["-a", A1, "-A", A2],
+        extra=["--pair-filter", "both", "-m", "80", "--discard-untrimmed"], read_ops=dict(pair_filter="both", minimum_length=80, discard_untrimmed=True),
+        merge={"min_overlap": 0.7})
+
     path = os.path.join(HERE, "fastq_trim_pe.json.gz")
     with open(path, "wb") as raw, gzip.GzipFile(fileobj=raw, mode="wb", mtime=0) as fh:
         fh.write(json.dumps(cases, separators=(",", ":")).encode("ascii"))
