@@ -235,18 +235,33 @@ inline void fill_k1a(const HostAdapter& h, const AtrTables& tb, int index, int r
     // pieces that end right before the rows where the error budget grows (thr_mul[i] steps from p - 1 to p): then the
     // budget never reaches the number of complete pieces AT a piece end, which is the one case the gate cannot certify
     // (equal pieces of exactly 1 / rate rows, the 58-nt adapter at 0.1, have it at every piece end)
-    auto budget_split = [&](int rows) {
+    // slack > 0 ends the pieces that many rows earlier still: the first mask row after a piece end then lies slack + 1
+    // rows deep in the begun piece, and a gate bit l rows deep fires by chance in 4^-l of the reads (with slack 0 the 58-nt
+    // adapter has five mask rows of depth 1: some begun piece "matches" the last base of 3 reads in 4, and the 64-bit
+    // tail pass ran for 95 % of the reads -- 55 % of the kernel's instructions)
+    auto budget_split = [&](int rows, int slack) {
         std::vector<int> lens;
         int prev = 0;
         for (int pc = 1; pc < pieces; pc++) {
             int i = prev + 1;
             while (i <= rows && (int)h.thr_mul[i] < pc) i++;     // first row whose budget is pc
-            const int end = i - 1;
+            const int end = i - 1 - slack;
             lens.push_back(end - prev);
             prev = end;
         }
         lens.push_back(rows - prev);
         return lens;
+    };
+    // expected fraction of random reads that pass the gate: sum over the mask rows of 4^-(rows into the begun piece)
+    auto gate_pass_rate = [&](const std::vector<int>& lens) {
+        double p = 0;
+        int r = 1;
+        for (int len : lens) {
+            for (int d = 1; d <= len; d++)
+                if ((a.tail_mask64 >> (r + d - 2)) & 1ull) p += std::pow(0.25, d);
+            r += len;
+        }
+        return p;
     };
     const bool shape = (a.fused_ok || a.filter_only) && !start_in_ref && stop_in_query;
     if (shape && pieces <= a.sa_rows && a.sa_rows / pieces >= 6) {
@@ -257,10 +272,18 @@ inline void fill_k1a(const HostAdapter& h, const AtrTables& tb, int index, int r
         if (pieces <= rows && rows / pieces >= 7) {
             a.qg_wide = 1;
             if (!layout(equal_split(rows))) {
-                const std::vector<int> alt = budget_split(rows);
-                bool ok = true;
-                for (int len : alt) ok = ok && len >= 7 && len <= 16;
-                if (!ok || !layout(alt)) layout(equal_split(rows));
+                // among the budget-aligned layouts with a working gate take the one whose gate fires least often by chance
+                std::vector<int> best;
+                double best_rate = 1e9;
+                for (int slack = 0; slack <= 3; slack++) {
+                    const std::vector<int> alt = budget_split(rows, slack);
+                    bool ok = true;
+                    for (int len : alt) ok = ok && len >= 7 && len <= 16;
+                    if (!ok || !layout(alt)) continue;
+                    const double rate = gate_pass_rate(alt) + (alt[0] < 8 ? 0.02 : 0.0);   // a 7-row piece costs the step-3 sampling
+                    if (rate < best_rate) { best_rate = rate; best = alt; }
+                }
+                if (best.empty() || !layout(best)) layout(equal_split(rows));
             }
         }
     }
