@@ -146,12 +146,17 @@ inline void fill_k1a(const HostAdapter& h, const AtrTables& tb, int index, int r
     // at most k unit-cost edits, so the unit-cost filter stage is still a valid necessary condition (and its verbatim-
     // occurrence shortcut is still the answer); only the DP itself has to price the indels -- the register DP does.
     a.filter_only = funnel_shape && h.desc.indel_cost != 1;
-    // an alignment that starts inside the adapter and ends at (m, j) covers at most j + k adapter rows, so its
-    // cost is bounded by floor(min(m, j + k) * rate) and it needs j + k >= min_overlap rows
+    // an alignment that ends at (m, j) and covers r adapter rows (it starts inside the adapter at row m - r, or r = m)
+    // needs r >= min_overlap and a cost c <= floor(r * rate) (consider(): length = r); r rows over j columns take at
+    // least r - j deletions, so r - j <= c. The bound on D[m][j] is the largest budget among the r that can do that;
+    // -1 = no r can (columns 1 and 2 at min_overlap 3: the first build allowed "3 rows, cost 0" there, which one column
+    // cannot hold, and a quarter of all reads -- last adapter base == first read base -- went on to the band kernel)
     for (int j = 0; j <= ATR_K1A_MAXM; j++) {
         const int jj = j < h.m ? j : h.m;
-        const int len = jj + h.k < h.m ? jj + h.k : h.m;
-        a.thrJ[j] = (short)(len >= h.desc.min_overlap ? (int)h.thr_mul[len] : -1);
+        int best = -1;
+        for (int r = h.desc.min_overlap > 1 ? h.desc.min_overlap : 1; r <= h.m; r++)
+            if (r - jj <= (int)h.thr_mul[r]) best = best > (int)h.thr_mul[r] ? best : (int)h.thr_mul[r];
+        a.thrJ[j] = (short)best;
     }
     // a read code that no adapter row matches: 0 in AND mode, an unused letter code in ASCII mode
     a.nomatch = 0; a.band_ok = a.fused_ok;
