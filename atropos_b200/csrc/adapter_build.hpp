@@ -269,6 +269,17 @@ inline void fill_k1a(const HostAdapter& h, const AtrTables& tb, int index, int r
         return p;
     };
     const bool shape = (a.fused_ok || a.filter_only) && !start_in_ref && stop_in_query;
+    // 5' adapters that may also start before the read (FRONT): every candidate that ends beyond column m + k is a
+    // full-length occurrence (an alignment that starts inside the adapter starts in column 0 and has at most k
+    // insertions), hence holds a verbatim piece; the others are found exactly by a Myers pass over the first m + k columns
+    const bool stop_in_ref_f = h.desc.flags & ATR_STOP_WITHIN_SEQ1;
+    a.sa_front = 0;
+    if (a.fused_ok && start_in_ref && stop_in_query && !stop_in_ref_f && (h.desc.flags & ATR_START_WITHIN_SEQ2) && h.m <= 32 &&
+        pieces <= a.sa_rows && a.sa_rows / pieces >= 6) {
+        a.sa_front = 1;
+        layout(equal_split(a.sa_rows));
+        a.tail_gate_ok = 0; a.tail_mask = 0; a.tail_mask64 = 0;      // no last-column candidates below row m: nothing to gate
+    }
     if (shape && pieces <= a.sa_rows && a.sa_rows / pieces >= 6) {
         a.sa_ok = 1;
         layout(equal_split(a.sa_rows));

@@ -225,7 +225,7 @@ int locate_on_stream(atr_ctx* ctx, Slot& slot, const atr_adapterset* set,
                 const bool use_sa = p.sa_ok && !ctx->disable_sa;
                 const bool use_qg = p.qg_ok && !ctx->disable_qg && (use_sa || p.qg_wide);
                 if (prof) {
-                    ctx->phase_names[0] = use_qg ? "k_filter_qg" : (use_sa ? "k_filter_sa" : "k_filter");
+                    ctx->phase_names[0] = use_qg ? "k_filter_qg" : (use_sa ? "k_filter_sa" : ((p.sa_front && !ctx->disable_sa) ? "k_filter_front" : "k_filter"));
                     ctx->phase_names[1] = (use_sa || use_qg) ? "k_refine" : "";
                     ctx->phase_names[2] = "k_band<16>+k_band<8>";
                     ctx->phase_names[3] = "k_wide";
@@ -242,6 +242,9 @@ int locate_on_stream(atr_ctx* ctx, Slot& slot, const atr_adapterset* set,
                 } else if (use_sa) {
                     if (h.and_mode) k_filter_sa<true><<<g, ATR_K1F_THREADS, 0, st>>>(p, d_codes, d_woff, d_len, d_win, n, d_out, narrow, wide, refine, counters);
                     else k_filter_sa<false><<<g, ATR_K1F_THREADS, 0, st>>>(p, d_codes, d_woff, d_len, d_win, n, d_out, narrow, wide, refine, counters);
+                } else if (p.sa_front && !ctx->disable_sa) {
+                    if (h.and_mode) k_filter_front<true><<<g, ATR_K1F_THREADS, 0, st>>>(p, d_codes, d_woff, d_len, d_win, n, d_out, narrow, wide, counters);
+                    else k_filter_front<false><<<g, ATR_K1F_THREADS, 0, st>>>(p, d_codes, d_woff, d_len, d_win, n, d_out, narrow, wide, counters);
                 } else if (h.m <= 32) {
                     if (h.and_mode) k_filter<unsigned int, true><<<g, ATR_K1F_THREADS, 0, st>>>(p, d_codes, d_woff, d_len, d_win, n, d_out, narrow, wide, counters);
                     else k_filter<unsigned int, false><<<g, ATR_K1F_THREADS, 0, st>>>(p, d_codes, d_woff, d_len, d_win, n, d_out, narrow, wide, counters);

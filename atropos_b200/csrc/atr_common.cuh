@@ -57,6 +57,9 @@ struct AdapterK1a {                   // passed by value as a __grid_constant__ 
     // Shift-And pre-filter (k_filter_sa): the first sa_rows (<= 32) adapter rows cut into k+1 pieces; an alignment
     // with <= k errors must contain one piece verbatim (pigeonhole)
     int sa_ok, sa_rows;
+    int sa_front;                     // unanchored 5' adapters (START_WITHIN_SEQ1 | START_WITHIN_SEQ2 | STOP_WITHIN_SEQ2, m <= 32): the
+                                      // pieces find the full-length occurrences, an exact Myers pass over the first m + k columns the
+                                      // partial ones at the read start (front_filter, k_filter_front); sa_ok stays 0
     int tail_gate_ok;                 // the Shift-And state can tell when no partial match at the read end is possible
     unsigned tail_mask;               // bit i-1: a candidate (i, n) without a verbatim complete piece leaves this bit set
     unsigned apack[ATR_K1A_MAXM / 8]; // the adapter's compare codes packed like a read (exact-occurrence shortcut)

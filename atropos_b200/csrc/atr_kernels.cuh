@@ -433,6 +433,86 @@ __global__ void __launch_bounds__(ATR_K1F_THREADS) k_filter(const __grid_constan
 }
 
 // ---------------------------------------------------------------------------------------------
+// k_filter_front: first stage for unanchored 5' adapters (AdapterK1a.sa_front; locate_core.cuh: front_filter). k_filter's
+// frame (one CTA = 256 reads, TMA tile) with the whole-read Myers pass (~14 instructions per column) replaced by the
+// Shift-And automaton over the pieces (~7.5 per column) + an exact Myers pass over the first m + k columns only.
+// ---------------------------------------------------------------------------------------------
+template <bool AND_MODE>
+__global__ void __launch_bounds__(ATR_K1F_THREADS) k_filter_front(const __grid_constant__ AdapterK1a ad,
+        const uint32_t* __restrict__ codes, const uint32_t* __restrict__ woff, const uint16_t* __restrict__ len,
+        const uint16_t* __restrict__ win, int64_t n_reads, atr_match* __restrict__ out,
+        Survivor* __restrict__ narrow, Survivor* __restrict__ wide, int* __restrict__ counters) {
+    __shared__ __align__(128) uint32_t s_tile[ATR_K1F_TILE_WORDS];
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ unsigned s_peq[16], s_sa_peq[16];
+    __shared__ unsigned long long s_sa_pair[256];
+
+    const int tid = threadIdx.x;
+    const int64_t t0 = (int64_t)blockIdx.x * ATR_K1F_THREADS;
+    const int cnt = (int)(n_reads - t0 < ATR_K1F_THREADS ? n_reads - t0 : ATR_K1F_THREADS);
+    const uint32_t w_begin = woff[t0], w_end = woff[t0 + cnt];
+    const uint32_t a_begin = w_begin & ~3u;
+    const uint32_t span = ((w_end - a_begin) + 3u) & ~3u;
+    const bool last_tile = (t0 + cnt == n_reads);
+    const bool fits = span <= ATR_K1F_TILE_WORDS;
+    const bool use_tma = fits && !last_tile && span > 0 && ((reinterpret_cast<uintptr_t>(codes) & 15) == 0);
+    const unsigned long long mk = ad.sa_rows >= 32 ? 0xFFFFFFFFull : ((1ull << ad.sa_rows) - 1);
+    if (tid < 16) {
+        const int sh = 32 - ad.m;
+        s_peq[tid] = ((unsigned)ad.peq[tid] << sh) | (sh ? ((1u << sh) - 1u) : 0u);
+        s_sa_peq[tid] = (unsigned)(ad.peq[tid] & mk);
+    }
+    s_sa_pair[tid] = (ad.peq[tid & 15] & mk) | ((ad.peq[tid >> 4] & mk) << 32);
+    if (tid == 0 && use_tma) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&s_bar)) : "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    if (use_tma) {
+        if (tid == 0) tma_load_1d(s_tile, codes + a_begin, span * 4u, &s_bar);
+    } else if (fits) {
+        for (uint32_t w = tid; w < w_end - a_begin; w += ATR_K1F_THREADS) s_tile[w] = codes[a_begin + w];
+    }
+    const int64_t r = t0 + tid;
+    const bool mine = tid < cnt;
+    bool routed = false, esc = false;
+    int lo = 0, n = 0;
+    uint32_t wr = a_begin;
+    if (mine) {
+        read_extent(len, win, r, lo, n, esc);
+        wr = woff[r];
+        routed = (esc && !AND_MODE) || n > ATR_K1A_MAXN;
+        if (routed && ad.mark_routed) {
+            atr_match m;
+            m.astart = m.astop = m.rstart = m.rstop = m.matches = m.errors = 0;
+            m.adapter = -1; m.status = ATR_ST_ESCAPED;
+            out[r] = m;
+        }
+    }
+    if (use_tma) mbar_wait(&s_bar, 0);
+    else __syncthreads();
+    const uint32_t* rd = codes + wr;
+    if (fits) rd = s_tile + (wr - a_begin);
+    bool to_narrow = false, to_wide = false, narrow8 = false;
+    Survivor sv;
+    sv.read = (uint32_t)r; sv.a = 0; sv.b = 0;
+    if (mine && !routed) {
+        FilterHit hit;
+        if (front_filter(ad, s_sa_peq, s_sa_pair, s_peq, rd, lo, n, hit)) {
+            if (ad.band_ok && hit.width <= ATR_K1D_W) { to_narrow = true; sv.a = (short)hit.dlo; narrow8 = ad.split8 && hit.width <= 8; }
+            else { to_wide = true; sv.a = (short)hit.c0; sv.b = (short)hit.c1; }
+        } else {
+            Best b;
+            b.ref_stop = ad.m; b.q_stop = n; b.cost = ad.m + n; b.origin = 0; b.matches = 0;
+            finalize(ad, b, n, out + r);
+        }
+    }
+    list_append(to_narrow && !narrow8, sv, narrow, counters + 0);
+    list_append_back(narrow8, sv, wide, counters + 3);
+    list_append(to_wide, sv, wide, counters + 1);
+}
+
+// ---------------------------------------------------------------------------------------------
 // k_filter_sa: the cheaper first stage used when the adapter's pieces are long enough (AdapterK1a.sa_ok):
 // Shift-And over k+1 verbatim pieces of the first <= 32 adapter rows (~7 instructions per column) plus an exact
 // 32-bit Myers over the last columns for the partial matches at the read end. Reads with a piece hit go to

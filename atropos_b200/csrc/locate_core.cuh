@@ -629,6 +629,47 @@ ATR_HD void sa_filter(const AdapterK1a& ad, const unsigned* __restrict__ sa_peq,
     sa_classify(ad, lo, n, hmin, hmax, imin, imax, res);
 }
 
+// ---- first stage for unanchored 5' adapters (AdapterK1a.sa_front; k_filter_front) ---------------------------------
+// Candidates are row-m cells (m, j) only. (H) j <= m + k: found exactly by the Myers pass with the all-zero first column
+// (an alignment may start inside the adapter) over the first m + k columns, bound thrJ[j]. (F) j > m + k: the alignment
+// covers all m rows (one that starts inside the adapter starts in column 0 and reaches at most column m + k), so one of the
+// k + 1 pieces is verbatim on a diagonal v with |v - (j - m)| <= k, -k <= v <= n - m + k. The diagonals any accepted
+// alignment touches are [e - k, e + k] around the end diagonals e = j - m of (H) and [v - k, v + k] around the hits of (F):
+// the same FilterHit as myers_filter's, a superset of its range (a hit need not lead to a candidate; the DP decides).
+// peq: the adapter left-aligned in 32 bits with the virtual rows set (as for myers_filter<unsigned>).
+ATR_HD bool front_filter(const AdapterK1a& ad, const unsigned* __restrict__ sa_peq, const unsigned long long* __restrict__ sa_pair,
+                         const unsigned* __restrict__ peq, const uint32_t* __restrict__ codes, int lo, int n, FilterHit& hit) {
+    const int m = ad.m, k = ad.k;
+    int hmin, hmax;
+    unsigned st_final;
+    sa_scan(ad, sa_peq, sa_pair, codes, lo, n, hmin, hmax, st_final);
+    // (H)
+    MyersState<unsigned> st;
+    st.Pv = 0; st.Mv = 0; st.score = 0;
+    int jmin = 0x7fffffff, jmax = -1;
+    const int head = atr_min(n, m + k);
+    for (int j = 1; j <= head; j++) {
+        const int pos = lo + j - 1;
+        myers_col(st, peq[(codes[pos >> 3] >> ((pos & 7) * 4)) & 15u]);
+        if (st.score <= (int)ad.thrJ[j < m ? j : m]) { jmin = atr_min(jmin, j); jmax = j; }
+    }
+    // (F)
+    int vlo = 0x7fffffff, vhi = -0x7fffffff;
+    if (hmax != -0x7fffffff) {
+        vlo = atr_max(hmin, -k); vhi = atr_min(hmax, n - m + k);
+        if (vlo > vhi) { vlo = 0x7fffffff; vhi = -0x7fffffff; }
+    }
+    if (jmax < 0 && vhi == -0x7fffffff) return false;
+    int elo = 0x7fffffff, ehi = -0x7fffffff, c1 = 0;
+    if (jmax >= 0) { elo = jmin - m; ehi = jmax - m; c1 = jmax; }
+    if (vhi != -0x7fffffff) { elo = atr_min(elo, vlo); ehi = atr_max(ehi, vhi); c1 = atr_max(c1, atr_min(n, vhi + m + k)); }
+    hit.dlo = elo - k;
+    hit.width = (ehi - elo) + 2 * k + 1;
+    hit.c0 = atr_max(0, elo - k);
+    hit.c1 = c1;
+    return true;
+}
+
 // ---- DP stage for narrow bands (k_band): K1d, banded DP along diagonals ------------------------------------------
 // B[d] = cell (i, i + dlo + d) of the current row i, d = 0..W-1, as K1a packed keys. Rows run 1..m in a
 // rolled loop (the adapter base of a row is warp-uniform), the W diagonals are unrolled in registers:
@@ -1002,6 +1043,16 @@ ATR_HD void k1f_read(const AdapterK1a& ad, const uint32_t* __restrict__ codes, i
             if (ad.band_ok && sr.width <= ATR_K1D_W) { have = true; hit.dlo = sr.dlo; hit.width = sr.width; hit.c0 = sr.c0; hit.c1 = sr.c1; }
             else have = myers_filter<WORD>(ad, peq, codes, lo, n, hit, sr.c0, sr.c1);
         }
+    } else if (ad.sa_front) {
+        unsigned sa_peq[16], peq32[16];
+        const int mp = ad.sa_rows, sh32 = 32 - ad.m;
+        for (int c = 0; c < 16; c++) {
+            sa_peq[c] = (unsigned)(ad.peq[c] & (mp >= 32 ? 0xFFFFFFFFull : ((1ull << mp) - 1)));
+            peq32[c] = (unsigned)(((unsigned)ad.peq[c] << sh32) | (sh32 ? ((1u << sh32) - 1u) : 0u));
+        }
+        unsigned long long sa_pair[256];
+        for (int bb = 0; bb < 256; bb++) sa_pair[bb] = (unsigned long long)sa_peq[bb & 15] | ((unsigned long long)sa_peq[bb >> 4] << 32);
+        have = front_filter(ad, sa_peq, sa_pair, peq32, codes, lo, n, hit);
     } else {
         have = myers_filter<WORD>(ad, peq, codes, lo, n, hit);
     }
@@ -1017,7 +1068,7 @@ ATR_HD void k1f_read(const AdapterK1a& ad, const uint32_t* __restrict__ codes, i
         }
         else { if (path) *path = 2; k1a_locate<AND_MODE>(ad, codes, lo, n, b, hit.c0, hit.c1); }
     }
-    if (path && (ad.sa_ok || ad.qg_ok)) *path += 10;   // tests: 10 + x = went through the Shift-And / q-gram pre-filter
+    if (path && (ad.sa_ok || ad.qg_ok || ad.sa_front)) *path += 10;   // tests: 10 + x = went through the Shift-And / q-gram pre-filter
     finalize(ad, b, n, out);
 }
 

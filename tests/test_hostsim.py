@@ -372,6 +372,44 @@ def test_qgram_filter_equals_shift_and(adapter, rate, min_overlap, step):
     assert seen[0] > 100 and seen[2] > 100 and (seen[3] > 20 or len(set(adapter)) < 4 or "ACGTACGT" in adapter), seen
 
 
+@pytest.mark.parametrize("adapter,rate,min_overlap", [
+    ("AATGATACGGCGACCACCGA", 0.1, 3), ("GTTCAGAGTTCTACAGTCCGACGATC", 0.1, 3), ("AGATCGGAAGAGCACACGTCTGAACTCCAGTC", 0.12, 4),
+    ("ACGTACGTACGTACGTACGT", 0.1, 3), ("A" * 20, 0.1, 3), ("AATGATACGGCGACCACCGA", 0.2, 1)])
+def test_front_adapters_shift_and_form(adapter, rate, min_overlap):
+    """unanchored 5' adapters: the Shift-And pieces for the full-length occurrences + the exact Myers pass over the first
+    m + k columns for the partial ones at the read start (front_filter) against the oracle's full DP -- adapter suffixes
+    at the read start, the adapter within k columns of the start, in the middle, sticking out of the read end, twice"""
+    rng = np.random.default_rng(len(adapter) * 31 + int(rate * 100))
+    d, keep = _abi.make_adapter_desc(adapter, rate, oracle.FRONT, False, False, min_overlap, 1)
+    through, found = 0, 0
+    for _ in range(4000):
+        L = int(rng.integers(1, 160))
+        kind = rng.random()
+        if kind < 0.4:
+            suf = adapter[len(adapter) - int(rng.integers(1, len(adapter) + 1)):]
+            mut = fuzzgen.mutate(rng, suf, sub=float(rng.choice([0, 0.05, 0.1, 0.2])), ins=float(rng.choice([0, 0.05])),
+                                 dele=float(rng.choice([0, 0.05]))) or suf
+            read = (fuzzgen.rand_seq(rng, int(rng.integers(0, 4))) if rng.random() < 0.3 else "") + mut + fuzzgen.rand_seq(rng, L)
+        elif kind < 0.8:
+            mut = fuzzgen.mutate(rng, adapter, sub=float(rng.choice([0, 0.03, 0.08, 0.15])), ins=float(rng.choice([0, 0.04])),
+                                 dele=float(rng.choice([0, 0.04]))) or adapter
+            pos = int(rng.choice([0, 1, 2, 3, 4, 5, int(rng.integers(0, 100)), L]))
+            read = fuzzgen.rand_seq(rng, pos) + mut + fuzzgen.rand_seq(rng, int(rng.integers(0, 40)))
+            if rng.random() < 0.3:
+                read = read[:max(1, len(read) - int(rng.integers(0, len(adapter))))]
+            if rng.random() < 0.2:
+                read = adapter[int(rng.integers(1, len(adapter))):] + read
+        else:
+            read = fuzzgen.rand_seq(rng, L)
+        exp = oracle.locate(adapter, read, rate, oracle.FRONT, False, False, min_overlap, 1)
+        got, path, _ = hostsim.locate(read, d, route=0)
+        assert got == exp, (adapter, rate, read, exp, got, path)
+        through += path >= 10
+        found += exp is not None
+    assert found > 1000
+    assert through == 4000 or rate == 0.2          # rate 0.2 on a 20-mer: 5 pieces of 4 rows, the Myers filter stays
+
+
 @pytest.mark.parametrize("rate,L", [(0.25, 150), (0.5, 120), (0.9, 64), (0.2, 300), (0.05, 200)])
 def test_match_insert_lookahead_budgets(rate, L):
     """the 2-bit look-ahead of the packed insert scan may never reach past the overlap (high rates: the budget of a short
