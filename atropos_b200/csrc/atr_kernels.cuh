@@ -986,21 +986,53 @@ __global__ void __launch_bounds__(128) k_refine(const __grid_constant__ AdapterK
 }
 
 // W = 16: the narrow list from the front; W = 8: the survivors appended from its end (AdapterK1a.split8), list = that end
+#define ATR_BAND_BATCH 256
 template <bool AND_MODE, int W>
 __global__ void __launch_bounds__(128) k_band(const __grid_constant__ AdapterK1a ad,
         const uint32_t* __restrict__ codes, const uint32_t* __restrict__ woff, const uint16_t* __restrict__ len,
         const uint16_t* __restrict__ win, atr_match* __restrict__ out,
         const Survivor* __restrict__ list, const int* __restrict__ counter) {
+    // The DP of a survivor runs R = min(m, n - dlo) rows: all m for an adapter inside the read, fewer for one that sticks
+    // out of the read end, and a warp runs as long as its longest lane (22 of 32 lanes active on the benchmark reads). A CTA
+    // therefore takes ATR_BAND_BATCH survivors at a time, counting-sorts them by R in shared memory and hands them out in
+    // that order, so that the lanes of a warp finish together.
+    __shared__ int s_hist[ATR_K1A_MAXM + 2];
+    __shared__ unsigned short s_order[ATR_BAND_BATCH];
+    __shared__ unsigned char s_key[ATR_BAND_BATCH];
+    __shared__ Survivor s_sv[ATR_BAND_BATCH];
+    __shared__ unsigned s_ext[ATR_BAND_BATCH];             // lo | n << 16
     const int count = *counter;
-    const int stride = gridDim.x * blockDim.x;
-    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < count; s += stride) {
-        const Survivor sv = W == 8 ? list[-1 - s] : list[s];
-        int lo, n; bool esc;
-        read_extent(len, win, sv.read, lo, n, esc);
-        Best b;
-        if (ad.flags & ATR_START_WITHIN_SEQ1) k1d_band<AND_MODE, W, true>(ad, codes + woff[sv.read], lo, n, (int)sv.a, b);
-        else k1d_band<AND_MODE, W, false>(ad, codes + woff[sv.read], lo, n, (int)sv.a, b);
-        finalize(ad, b, n, out + sv.read);
+    const int tid = threadIdx.x;
+    for (int base = blockIdx.x * ATR_BAND_BATCH; base < count; base += gridDim.x * ATR_BAND_BATCH) {
+        const int nb = count - base < ATR_BAND_BATCH ? count - base : ATR_BAND_BATCH;
+        for (int i = tid; i < ATR_K1A_MAXM + 2; i += blockDim.x) s_hist[i] = 0;
+        __syncthreads();
+        for (int e = tid; e < nb; e += blockDim.x) {
+            const Survivor sv = W == 8 ? list[-1 - (base + e)] : list[base + e];
+            int lo, n; bool esc;
+            read_extent(len, win, sv.read, lo, n, esc);
+            int R = n - (int)sv.a;
+            R = R < 0 ? 0 : (R > ad.m ? ad.m : R);
+            s_key[e] = (unsigned char)R;
+            s_sv[e] = sv;
+            s_ext[e] = (unsigned)lo | ((unsigned)n << 16);
+            atomicAdd(&s_hist[R + 1], 1);
+        }
+        __syncthreads();
+        if (tid == 0) { int acc = 0; for (int i = 0; i <= ad.m + 1; i++) { acc += s_hist[i]; s_hist[i] = acc; } }   // s_hist[R] = first slot of key R
+        __syncthreads();
+        for (int e = tid; e < nb; e += blockDim.x) s_order[atomicAdd(&s_hist[s_key[e]], 1)] = (unsigned short)e;
+        __syncthreads();
+        for (int e = tid; e < nb; e += blockDim.x) {
+            const int o = s_order[e];
+            const Survivor sv = s_sv[o];
+            const int lo = (int)(s_ext[o] & 0xFFFFu), n = (int)(s_ext[o] >> 16);
+            Best b;
+            if (ad.flags & ATR_START_WITHIN_SEQ1) k1d_band<AND_MODE, W, true>(ad, codes + woff[sv.read], lo, n, (int)sv.a, b);
+            else k1d_band<AND_MODE, W, false>(ad, codes + woff[sv.read], lo, n, (int)sv.a, b);
+            finalize(ad, b, n, out + sv.read);
+        }
+        __syncthreads();
     }
 }
 
