@@ -35,7 +35,8 @@ SHIM_NAME = "atropos.align._align"
 
 #: counters a caller (and tests/test_gpu_reference_suite.py) can read to see which binding did the work
 STATS = {"percall_locate": 0, "percall_multi_locate": 0, "percall_compare_prefixes": 0,
-         "batched_batches": 0, "batched_reads": 0, "batched_gpu_calls": 0, "percall_batches": 0}
+         "batched_batches": 0, "batched_reads": 0, "batched_gpu_calls": 0, "percall_batches": 0,
+         "batched_merge_batches": 0}
 
 _installed = {"finder": False, "batched": False}
 _orig_handle_records = None
@@ -253,6 +254,48 @@ class _InsertReplay(object):
         return replay
 
 
+class _MergeReplay(object):
+    """Precomputed alignments of one MergeOverlapping modifier over the batch: stands in for the per-pair
+    ``Aligner(read2_rc, error_rate, flags).locate(read1.sequence)`` (modifiers.py:886-895); everything else of the
+    modifier -- the length test, reverse_complement, error correction, the four ways to merge -- stays reference code."""
+
+    def __init__(self, mod):
+        self.mod = mod
+        self.recs, self.lens, self.idx = None, None, -1
+
+    def seek(self, idx):
+        self.idx = idx
+
+    def precompute(self, mids, device):
+        from .modifiers import MergeOverlapping as GpuMerge
+        gm = self.mod.__dict__.setdefault("_atr_gpu_merge", {})
+        key = engine.context_key(device)
+        if key not in gm:
+            gm[key] = GpuMerge(self.mod.min_overlap, self.mod.error_rate, None, device=device)
+        im = np.fromiter((bool(a.insert_overlap and b.insert_overlap) for a, b in mids), dtype=np.uint8, count=len(mids))
+        a1, o1 = engine.encode_reads([a.sequence for a, _ in mids])
+        a2, o2 = engine.encode_reads([b.sequence for _, b in mids])
+        self.lens = (np.diff(o1), np.diff(o2))
+        self.recs = gm[key].align_batch((a1, o1), (a2, o2), insert_matched=im)
+        STATS["batched_gpu_calls"] += 1
+
+    def Aligner(self, reference, max_error_rate, flags=15, *args, **kwargs):
+        """what MergeOverlapping.__call__ constructs per pair: an object whose locate() gives this pair's alignment"""
+        rp = self
+
+        class _Located(object):
+            def locate(self, query):
+                i = rp.idx
+                if len(query) != int(rp.lens[0][i]) or len(reference) != int(rp.lens[1][i]):
+                    raise _Desync("batched binding out of step at pair %d: MergeOverlapping sees %d / %d nt, the batch call "
+                                  "aligned %d / %d" % (i, len(query), len(reference), int(rp.lens[0][i]), int(rp.lens[1][i])))
+                rec = rp.recs[i]
+                if int(rec["r2_stop"]) == 0 and int(rec["r1_stop"]) == 0:      # locate() returned None
+                    return None
+                return tuple(int(rec[f]) for f in ("r2_start", "r2_stop", "r1_start", "r1_stop", "matches", "errors"))
+        return _Located()
+
+
 class _Plan(object):
     """Where the adapter stage sits in a Modifiers chain and how to batch it. None of this changes what the chain
     computes: every modifier sees the records in the reference's order, once."""
@@ -297,6 +340,13 @@ class _Plan(object):
                 return
             self.kind, self.index = "adapter", i
             self.replays = replays
+        # MergeOverlapping behind the adapter stage (always the last modifier, commands/trim/__init__.py:546-552): its
+        # per-pair alignment is a second batched GPU stage
+        self.merge_index, self.merge = None, None
+        for j in range(self.index + 1, len(chain)):
+            if type(chain[j]) is modifiers.MergeOverlapping and self.paired:
+                self.merge_index, self.merge = j, _MergeReplay(chain[j])
+                break
 
     # -- the chain, split at the adapter stage (SingleEndModifiers.modify / PairedEndModifiers.modify,
     #    modifiers.py:1048-1051, 1096-1105) ----------------------------------------------------------------
@@ -318,6 +368,19 @@ class _Plan(object):
     def from_stage(self, read1, read2):
         read1, read2 = self._run(self.mods.modifiers[self.index:], read1, read2)
         return (read1, read2) if self.paired else (read1,)
+
+    def stage_to_merge(self, read1, read2):
+        return self._run(self.mods.modifiers[self.index:self.merge_index], read1, read2)
+
+    def from_merge(self, read1, read2):
+        """MergeOverlapping.__call__ (reference code) with its Aligner swapped for the replay, then whatever follows"""
+        _, _, _, _, _, modifiers = _ref()
+        saved = modifiers.Aligner
+        modifiers.Aligner = self.merge.Aligner
+        try:
+            return self._run(self.mods.modifiers[self.merge_index:], read1, read2)
+        finally:
+            modifiers.Aligner = saved
 
     # -- the GPU stage -----------------------------------------------------------------------------------
     def precompute(self, state, device=0):
@@ -496,11 +559,33 @@ def _batched_handle_records(self, context, records):
         plan.precompute(state, device=_device())
     except Exception as err:
         failed(0, err)
+    mids = None
+    if plan.merge is not None:
+        # two GPU stages: the adapter stage's replay runs over the whole batch first, then ONE merge-alignment call
+        mids = []
+        with plan:
+            for idx, (read1, read2) in enumerate(state):
+                try:
+                    plan.seek(idx)
+                    mids.append(plan.stage_to_merge(read1, read2))
+                except _Desync:
+                    raise
+                except Exception as err:
+                    failed(idx, err)
+        try:
+            plan.merge.precompute(mids, device=_device())
+        except Exception as err:
+            failed(0, err)
+        STATS["batched_merge_batches"] = STATS.get("batched_merge_batches", 0) + 1
     with plan:
-        for idx, (read1, read2) in enumerate(state):
+        for idx, (read1, read2) in enumerate(state if mids is None else mids):
             try:
-                plan.seek(idx)
-                reads = plan.from_stage(read1, read2)
+                if mids is None:
+                    plan.seek(idx)
+                    reads = plan.from_stage(read1, read2)
+                else:
+                    plan.merge.seek(idx)
+                    reads = plan.from_merge(read1, read2)
                 dest = handler.filters.filter(*reads)
                 handler.formatters.format(context["results"], dest, *reads)
                 if wrapper is not None and wrapper.post is not None:

@@ -29,6 +29,18 @@ class SimContext(object):
     def multi_locate(self, reference, query, max_error_rate, flags, min_overlap, max_matches=100):
         return hostsim.multi_locate(reference, query, max_error_rate, flags, min_overlap, max_matches)
 
+    def merge_overlap_host(self, ascii1, offsets1, ascii2, offsets2, min_overlap, error_rate, insert_matched=None, out=None):
+        n = len(offsets1) - 1
+        if out is None:
+            out = np.empty(n, dtype=_abi.MERGE_DTYPE)
+        b1 = np.ascontiguousarray(ascii1, dtype=np.uint8).tobytes()
+        b2 = np.ascontiguousarray(ascii2, dtype=np.uint8).tobytes()
+        for i in range(n):
+            r = hostsim.merge_overlap(b1[offsets1[i]:offsets1[i + 1]], b2[offsets2[i]:offsets2[i + 1]],
+                                      bool(insert_matched[i]) if insert_matched is not None else False, min_overlap, error_rate)
+            out[i] = (r.r2_start, r.r2_stop, r.r1_start, r.r1_stop, r.matches, r.errors, r.min_overlap, r.status, r.action)
+        return out
+
 
 _CTX = SimContext()
 
