@@ -619,14 +619,25 @@ def install_batched_pipeline():
 
 
 def main(argv=None):
-    """``python -m atropos_b200.integration [--per-call] <atropos command line>``: the reference's own launcher
-    (bin/atropos -> atropos.commands.execute_cli) on top of this engine."""
+    """``python -m atropos_b200.integration [--aligner-backend gpu|gpu-per-call|cython] <atropos command line>``: the
+    reference's own launcher (bin/atropos -> atropos.commands.execute_cli) on top of this engine."""
     argv = list(sys.argv[1:] if argv is None else argv)
-    batched = True
-    if argv and argv[0] == "--per-call":
-        batched = False
-        argv = argv[1:]
-    install(batched=batched)
+    # backend switch (SURVEY section 5: "--aligner-backend {cython,gpu}-style switch / env var in the shim"):
+    #   --aligner-backend gpu | gpu-per-call | cython   or   ATROPOS_ALIGNER_BACKEND=...   (flag wins; default gpu)
+    # `cython` leaves the reference exactly as it is (its own compiled _align module): the A/B partner of the other two.
+    import os
+    backend = os.environ.get("ATROPOS_ALIGNER_BACKEND", "gpu")
+    while argv and argv[0] in ("--per-call", "--aligner-backend"):
+        if argv[0] == "--per-call":
+            backend, argv = "gpu-per-call", argv[1:]
+        else:
+            if len(argv) < 2:
+                raise SystemExit("--aligner-backend needs a value: gpu, gpu-per-call or cython")
+            backend, argv = argv[1], argv[2:]
+    if backend not in ("gpu", "gpu-per-call", "cython"):
+        raise SystemExit("unknown aligner backend %r (gpu, gpu-per-call, cython)" % (backend,))
+    if backend != "cython":
+        install(batched=(backend == "gpu"))
     from atropos.commands import execute_cli
     return execute_cli(argv)
 
