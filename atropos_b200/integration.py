@@ -130,15 +130,22 @@ def uninstall():
 # ------------------------------------------------------------------------------------------------
 # 2. batched binding
 # ------------------------------------------------------------------------------------------------
+_REF = None
+
+
 def _ref():
-    """The reference modules the batched binding talks to (imported lazily, through the finder)."""
-    import atropos
-    import atropos.adapters as adapters
-    import atropos.align as align
-    import atropos.commands.base as base
-    import atropos.commands.trim as trim
-    import atropos.commands.trim.modifiers as modifiers
-    return atropos, adapters, align, base, trim, modifiers
+    """The reference modules the batched binding talks to (imported lazily, through the finder; looked up once: this is
+    called per record)."""
+    global _REF
+    if _REF is None:
+        import atropos
+        import atropos.adapters as adapters
+        import atropos.align as align
+        import atropos.commands.base as base
+        import atropos.commands.trim as trim
+        import atropos.commands.trim.modifiers as modifiers
+        _REF = (atropos, adapters, align, base, trim, modifiers)
+    return _REF
 
 
 def adapter_descriptor(adapter):
@@ -188,15 +195,14 @@ class _CutterReplay(object):
             return self._linked(read, i)
         if t >= len(self.rounds):
             return None
-        rec = self.rounds[t][i]
-        st = int(rec["status"])
+        # one round = a list of plain tuples in MATCH_DTYPE's field order (numpy record scalars cost ~1 us per field)
+        astart, astop, rstart, rstop, matches, errors, a_idx, st = self.rounds[t][i]
         if st == _abi.ATR_ST_NONE:
             return None
         if st == _abi.ATR_ST_INVALID:
             raise ValueError('A Match requires at least one matching position.')
-        adapter = self.cutter.adapters[int(rec["adapter"])]
-        match = align.Match(int(rec["astart"]), int(rec["astop"]), int(rec["rstart"]), int(rec["rstop"]),
-                            int(rec["matches"]), int(rec["errors"]), adapter._front_flag, adapter, read)
+        adapter = self.cutter.adapters[a_idx]
+        match = align.Match(astart, astop, rstart, rstop, matches, errors, adapter._front_flag, adapter, read)
         if match.front:                      # what adapter.trimmed(match) leaves for the next round
             self.lo += match.rstop
         else:
@@ -433,7 +439,7 @@ class _Plan(object):
             STATS["batched_gpu_calls"] += 1
             res["status"][~active] = _abi.ATR_ST_NONE
             hit = res["status"] == _abi.ATR_ST_MATCH
-            rounds.append(res)
+            rounds.append(res.tolist())
             if not hit.any():
                 break
             ff = front_flags[np.clip(res["adapter"], 0, None)]

@@ -206,5 +206,46 @@ def main():
                           "merged_fraction": float((recs["status"] == _abi.ATR_ST_MATCH).mean())}))
 
 
+def reference_cli_backends(n_reads=500_000):
+    """The reference's OWN command line (baseline/_ref, unmodified) on the same FASTQ file with its three aligner backends
+    (atropos_b200.integration --aligner-backend): what the drop-in buys while every record still goes through the
+    reference's per-record Python (reader, modifiers, filters, writers) -- and why the FASTQ-text entry points exist."""
+    import subprocess
+    import tempfile
+    import time
+    from atropos_b200 import synth
+    stage = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(stage, "atropos")):
+        print(json.dumps({"config": "reference CLI backends", "unavailable": "baseline/_ref not staged"}))
+        return
+    tmp = tempfile.mkdtemp(prefix="atrcli")
+    reads = synth.synth_se(n_reads, 150, seed=synth.seed_for(2), device="cpu").numpy()
+    with open(os.path.join(tmp, "in.fq"), "wb") as fh:
+        fh.write(synth.fastq_text(reads).tobytes())
+    out = {"config": "reference command line `atropos trim -a TRUSEQ -e 0.1 -se in.fq -o out.fq`, %d reads, one process, per backend" % n_reads}
+    texts = {}
+    for backend in ("cython", "gpu-per-call", "gpu"):
+        dst = os.path.join(tmp, "out_%s.fq" % backend)
+        cmd = [sys.executable, "-m", "atropos_b200.integration", "--aligner-backend", backend, "trim", "-a", synth.TRUSEQ_R1, "-e", "0.1",
+               "--no-default-adapters", "--no-cache-adapters", "--quiet", "--report-file", os.devnull, "-se", os.path.join(tmp, "in.fq"), "-o", dst]
+        env = dict(os.environ, PYTHONPATH=os.pathsep.join([ROOT, stage, os.environ.get("PYTHONPATH", "")]))
+        t0 = time.perf_counter()
+        p = subprocess.run(cmd, env=env, cwd=stage, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=3000)
+        dt = time.perf_counter() - t0
+        if p.returncode != 0:
+            out[backend] = "failed: " + p.stdout[-300:]
+            continue
+        out[backend + "_M_reads_per_s"] = n_reads / dt / 1e6
+        with open(dst, "rb") as fh:
+            texts[backend] = fh.read()
+    out["outputs_identical"] = len(texts) == 3 and len(set(texts.values())) == 1
+    print(json.dumps(out))
+    import shutil
+    shutil.rmtree(tmp, ignore_errors=True)
+
+
 if __name__ == "__main__":
-    main()
+    if "--cli-backends" in sys.argv:
+        reference_cli_backends()
+    else:
+        main()
