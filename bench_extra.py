@@ -240,6 +240,33 @@ def reference_cli_backends(n_reads=500_000):
             texts[backend] = fh.read()
     out["outputs_identical"] = len(texts) == 3 and len(set(texts.values())) == 1
     print(json.dumps(out))
+    # paired-end, the reference's flagship mode: --aligner insert (+ merging), where the aligner dominates its per-record cost
+    n_pairs = n_reads // 4
+    r1, r2 = synth.synth_pe(n_pairs, 150, seed=synth.seed_for(3), device="cpu")
+    for name, r in (("in1.fq", r1), ("in2.fq", r2)):
+        with open(os.path.join(tmp, name), "wb") as fh:
+            fh.write(synth.fastq_text(r.numpy()).tobytes())
+    for label, extra in (("insert", []), ("insert + merge", ["--merge-overlapping", "--merged-output", "MERGED"])):
+        out = {"config": "reference command line `atropos trim --aligner insert -a R1 -A R2 -e 0.1 -pe1 .. -pe2 .. -o .. -p ..%s`, %d pairs, "
+                         "one process, per backend" % (" -R --merged-output .." if extra else "", n_pairs)}
+        texts = {}
+        for backend in ("cython", "gpu"):
+            dst = [os.path.join(tmp, "o%d_%s.fq" % (k, backend)) for k in (1, 2, 3)]
+            cmd = [sys.executable, "-m", "atropos_b200.integration", "--aligner-backend", backend, "trim", "--aligner", "insert",
+                   "-a", synth.TRUSEQ_R1, "-A", synth.TRUSEQ_R2, "-e", "0.1", "--no-default-adapters", "--no-cache-adapters", "--quiet",
+                   "--report-file", os.devnull, "-pe1", os.path.join(tmp, "in1.fq"), "-pe2", os.path.join(tmp, "in2.fq"),
+                   "-o", dst[0], "-p", dst[1]] + [dst[2] if x == "MERGED" else x for x in extra]
+            env = dict(os.environ, PYTHONPATH=os.pathsep.join([ROOT, stage, os.environ.get("PYTHONPATH", "")]))
+            t0 = time.perf_counter()
+            p = subprocess.run(cmd, env=env, cwd=stage, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=3000)
+            dt = time.perf_counter() - t0
+            if p.returncode != 0:
+                out[backend] = "failed: " + p.stdout[-300:]
+                continue
+            out[backend + "_M_pairs_per_s"] = n_pairs / dt / 1e6
+            texts[backend] = b"".join(open(d, "rb").read() for d in dst if os.path.exists(d))
+        out["outputs_identical"] = len(texts) == 2 and len(set(texts.values())) == 1
+        print(json.dumps(out))
     import shutil
     shutil.rmtree(tmp, ignore_errors=True)
 
