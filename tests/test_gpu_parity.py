@@ -287,7 +287,7 @@ def test_insert_config_pe300():
     from atropos_b200.adapters import Adapter, BACK
     from atropos_b200.align import InsertAligner
     from atropos_b200.util import RandomMatchProbability
-    n, L = 4000, 300
+    n, L = 30000, 300
     r1, r2 = synth.synth_pe(n, L, seed=synth.seed_for(5), device="cpu", sub=0.02)
     r1, r2 = r1.numpy(), r2.numpy()
     offs = np.arange(n + 1, dtype=np.int64) * L
@@ -310,7 +310,7 @@ def test_insert_config_pe300():
     mine = Adapter(T2, BACK, match_probability=rmp, **akw)
     o_ad = oracle.OracleAdapter(T2, oracle.BACK, match_probability=rmp_o, **akw)
     rec = mine.match_to_batch((r2.reshape(-1), offs))
-    for i in range(0, n, 3):
+    for i in range(0, n, 5):
         exp = o_ad.match_to(bytes(r2[i]).decode())
         got = None if rec[i]["status"] == _abi_mod.ATR_ST_NONE else tuple(int(rec[i][k]) for k in
                                                                          ("astart", "astop", "rstart", "rstop", "matches", "errors"))
