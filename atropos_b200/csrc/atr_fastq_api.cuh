@@ -510,12 +510,13 @@ int pe_back(atr_ctx* ctx, Slot& s, const PeStep& P, const atr_insertset* iset, c
     unsigned char* d_pflags = nullptr;
     if (mg) {
         rc = qm.flags.ensure((size_t)n + 16);
-        if (!rc) rc = qm.tiles.ensure((size_t)n + 16);
         if (!rc) rc = qm.text.ensure((size_t)(n + 1) * sizeof(atr_merge_result));
         if (!rc) rc = qm.recs.ensure((size_t)(n + 1) * sizeof(FqMergeRec));
         if (!rc) rc = qm.len64.ensure((size_t)(n + 2) * sizeof(long long));
         if (!rc) rc = qm.outoff.ensure((size_t)(n + 2) * sizeof(long long));
-        if (!rc) rc = qm.nl.ensure(64);
+        if (!rc) rc = qm.nl.ensure(256);                                   // longest windows (2 ints), class histogram, cursors
+        if (!rc) rc = qm.tile_offs.ensure((size_t)(n + 1) * sizeof(uint32_t));   // the pairs in class order
+        if (!rc) rc = qm.tiles.ensure(2 * ((size_t)n + 16));               // insert_matched bytes | class keys
         if (!rc) rc = qm.info.ensure(sizeof(FqInfo));
         if (!rc && mg->write_merged) rc = qm.outtext.ensure((size_t)(P.c[0].len + P.c[1].len) + 64);
         if (rc) return fail(ctx, rc, "out of device memory (merged reads)");
@@ -616,13 +617,20 @@ int pe_back(atr_ctx* ctx, Slot& s, const PeStep& P, const atr_insertset* iset, c
         FqMergeCounters* d_mc = (FqMergeCounters*)(d_stats + L.o_merge);
         int* d_max = qm.nl.as<int>();
         int* h_max = &qm.hinfo->nl_overflow;                 // two consecutive ints of the mapped FqInfo (unused for this side)
-        CU(cudaMemsetAsync(d_max, 0, 2 * sizeof(int), st));
+        int* d_hist = d_max + 2;
+        int* d_cursor = d_hist + FQ_MERGE_BINS;
+        unsigned char* d_keys = qm.tiles.as<unsigned char>() + n + 16;
+        CU(cudaMemsetAsync(d_max, 0, (2 + 2 * FQ_MERGE_BINS) * sizeof(int), st));
         for (int f = 0; f < 2; f++) CU(cudaMemsetAsync(s.fq[f].len64.p, 0, (size_t)(n + 2) * sizeof(long long), st));
         k_pe_merge_len<<<grid_for(n, 256), 256, 0, st>>>(s.fq[0].fwin.as<uint16_t>(), s.fq[1].fwin.as<uint16_t>(), d_pflags, n,
                                                          s.fq[0].len64.as<long long>(), s.fq[1].len64.as<long long>(),
-                                                         qm.tiles.as<unsigned char>(), d_max);
+                                                         qm.tiles.as<unsigned char>(), d_max, mg->tb.minov, d_keys, d_hist);
         LAUNCHED(ctx);
         k_pe_merge_publish<<<1, 32, 0, st>>>(d_max, h_max);
+        LAUNCHED(ctx);
+        k_pe_merge_bins<<<1, 32, 0, st>>>(d_hist, d_cursor);
+        LAUNCHED(ctx);
+        k_pe_merge_order<<<grid_for(n, 256), 256, 0, st>>>(d_keys, n, d_cursor, qm.tile_offs.as<uint32_t>());
         LAUNCHED(ctx);
         for (int f = 0; f < 2; f++) {
             PeSide b = pe_side(s, f);
@@ -638,7 +646,8 @@ int pe_back(atr_ctx* ctx, Slot& s, const PeStep& P, const atr_insertset* iset, c
         if (max1 > ATR_MERGE_MAX_READ || max2 > ATR_MERGE_MAX_READ) return fail(ctx, ATR_E_LIMIT, "read longer than 4000 nt (merge)");
         const MergePlan plan = merge_plan(max1, max2, mg->error_rate);
         rc = merge_launch(ctx, s, st, plan, max2, b0.ascii.as<unsigned char>(), b0.offsets.as<int64_t>(), 0, b1.ascii.as<unsigned char>(),
-                          b1.offsets.as<int64_t>(), 0, qm.tiles.as<unsigned char>(), n, mg->tb, nullptr, qm.text.as<atr_merge_result>());
+                          b1.offsets.as<int64_t>(), 0, qm.tiles.as<unsigned char>(), n, mg->tb,
+                          (plan.use_warp && max2 <= 160) ? qm.tile_offs.as<uint32_t>() : nullptr, qm.text.as<atr_merge_result>());
         if (rc) return rc;
         CU(cudaMemsetAsync(qm.len64.p, 0, (size_t)(n + 2) * sizeof(long long), st));
         CU(cudaMemsetAsync(qm.info.p, 0, sizeof(FqInfo), st));

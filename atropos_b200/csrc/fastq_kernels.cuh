@@ -568,6 +568,10 @@ __global__ void __launch_bounds__(256) k_pe_post(const unsigned char* __restrict
 }
 
 // ---- MergeOverlapping behind the paired-end modifiers (fastq_core.cuh: FqMergeRec, fq_merge_decide) ----------------
+#define FQ_MERGE_BINS 12
+#ifndef ATR_MERGE_MAX_READ
+#define ATR_MERGE_MAX_READ 4000
+#endif
 struct FqMergeCounters {
     unsigned long long merged, merged_written, bp_merged, records_corrected, bp_corrected[2], raises, correction_errors;
 };
@@ -577,20 +581,49 @@ struct FqMergeCounters {
 __global__ void __launch_bounds__(256) k_pe_merge_len(const uint16_t* __restrict__ fwin1, const uint16_t* __restrict__ fwin2,
                                                       const unsigned char* __restrict__ pflags, long long n, long long* __restrict__ len1,
                                                       long long* __restrict__ len2, unsigned char* __restrict__ insert_matched,
-                                                      int* __restrict__ d_max) {
+                                                      int* __restrict__ d_max, const unsigned short* __restrict__ minov,
+                                                      unsigned char* __restrict__ keys, int* __restrict__ d_hist) {
+    // keys / d_hist: the pair's class for k_merge_warp's two-pair mode, ceil(len2 / 16) if the pair is aligned at all (both
+    // reads >= its minimum overlap) else 0, and how many pairs each class has (FQ_MERGE_BINS bins)
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    int l1 = 0, l2 = 0;
+    int l1 = 0, l2 = 0, key = -1;
     if (r < n) {
         l1 = (int)fwin1[2 * r + 1] - (int)fwin1[2 * r];
         l2 = (int)fwin2[2 * r + 1] - (int)fwin2[2 * r];
         len1[r] = l1; len2[r] = l2;
         insert_matched[r] = (pflags[r] & FQ_PF_INSERT) ? 1 : 0;
+        const int lm = l1 < l2 ? l1 : l2;
+        const int mo = (int)minov[lm > ATR_MERGE_MAX_READ ? ATR_MERGE_MAX_READ : lm];
+        key = (l1 >= mo && l2 >= mo) ? (l2 + 15) >> 4 : 0;
+        if (key > FQ_MERGE_BINS - 1) key = FQ_MERGE_BINS - 1;
+        keys[r] = (unsigned char)key;
     }
     const int m1 = __reduce_max_sync(0xffffffffu, l1), m2 = __reduce_max_sync(0xffffffffu, l2);
     if ((threadIdx.x & 31) == 0) {
         if (m1) atomicMax(&d_max[0], m1);
         if (m2) atomicMax(&d_max[1], m2);
     }
+    const unsigned peers = __match_any_sync(0xffffffffu, key);
+    if (key >= 0 && (int)(threadIdx.x & 31) == __ffs((int)peers) - 1) atomicAdd(&d_hist[key], __popc(peers));
+}
+// bins -> running cursors (exclusive prefix), then every pair takes a slot of its class: `order` lists the pairs class by
+// class, so that neighbours in k_merge_warp need the same rows per lane (any order inside a class will do)
+__global__ void k_pe_merge_bins(const int* __restrict__ d_hist, int* __restrict__ d_cursor) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        int acc = 0;
+        for (int b = 0; b < FQ_MERGE_BINS; b++) { d_cursor[b] = acc; acc += d_hist[b]; }
+    }
+}
+__global__ void __launch_bounds__(256) k_pe_merge_order(const unsigned char* __restrict__ keys, long long n, int* __restrict__ d_cursor,
+                                                        uint32_t* __restrict__ order) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int key = r < n ? (int)keys[r] : -1;
+    const unsigned peers = __match_any_sync(0xffffffffu, key);
+    const int lane = threadIdx.x & 31, leader = __ffs((int)peers) - 1;
+    int base = 0;
+    if (key >= 0 && lane == leader) base = atomicAdd(&d_cursor[key], __popc(peers));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (key >= 0) order[base + __popc(peers & ((1u << lane) - 1u))] = (uint32_t)r;
 }
 __global__ void k_pe_merge_publish(const int* __restrict__ d_max, int* h_max) {
     if (blockIdx.x == 0 && threadIdx.x < 2) h_max[threadIdx.x] = d_max[threadIdx.x];
