@@ -458,9 +458,34 @@ def test_insert_adapter_cutter_matching_half():
     assert n_ins > 1500 and n_fb > 20
 
 
+_PE_FULL = None
+
+
+def _pe_oracle_range(bounds):
+    """worker of test_full_size_properties_pe: OracleInsertAligner.match_insert for pairs [lo, hi) of the inherited batch"""
+    lo, hi = bounds
+    r1, r2, kw = _PE_FULL
+    orc = oracle.OracleInsertAligner(T1, T2, **kw)
+    out = np.zeros((hi - lo, 21), dtype=np.int64)
+    for i in range(lo, hi):
+        e = orc.match_insert(r1[i].tobytes().decode(), r2[i].tobytes().decode())
+        if e is None:
+            continue
+        row = out[i - lo]
+        row[0] = 1
+        row[1:7] = e[0]
+        if e[1] is not None:
+            row[7] = 1
+            row[8:14] = e[1]
+        if e[2] is not None:
+            row[14] = 1
+            row[15:21] = e[2]
+    return out
+
+
 def test_full_size_properties_pe():
-    """BASELINE config 3 at full size (10 M pairs, 2 x 150) through size-independent properties: (1) a random 20 k
-    subsample agrees with the oracle; (2) pairs are independent: a permuted batch gives the permuted records;
+    """BASELINE config 3 at full size (10 M pairs, 2 x 150): (1) all 10 M results equal the oracle's (Python restatement on
+    every host core, about a minute); (2) pairs are independent: a permuted batch gives the permuted records;
     (3) swapping mates with swapped adapters mirrors the result (the overlap is symmetric under reverse
     complement: same insert size, match1 <-> match2); (4) planted error-free fragments shorter than the read are
     all found with insert size == fragment length."""
@@ -478,15 +503,27 @@ def test_full_size_properties_pe():
     assert set(np.unique(st)) <= {_abi.ATR_ST_NONE, _abi.ATR_ST_MATCH}
     assert 0.35 < (st == _abi.ATR_ST_MATCH).mean() < 0.45
     rng = np.random.default_rng(3)
-    orc = oracle.OracleInsertAligner(T1, T2, **kw)
-    for i in rng.choice(n, 20000, replace=False):
-        exp = orc.match_insert(bytes(r1[i]).decode(), bytes(r2[i]).decode())
-        got = InsertAligner.result_from_record(res[i])
-        if exp is None:
-            assert got is None
-        else:
-            assert got[0] == exp[0] and (got[1].fields() if got[1] else None) == exp[1] and \
-                (got[2].fields() if got[2] else None) == exp[2]
+    # (1) EVERY pair of the batch against the oracle, on all host cores (forked workers: they only run the CPU oracle)
+    import multiprocessing as mp
+    import os
+    global _PE_FULL
+    _PE_FULL = (r1, r2, kw)
+    workers = max(1, os.cpu_count() or 1)
+    bounds = np.linspace(0, n, 8 * workers + 1).astype(np.int64)
+    with mp.get_context("fork").Pool(workers) as pool:
+        parts = pool.map(_pe_oracle_range, [(int(bounds[t]), int(bounds[t + 1])) for t in range(8 * workers)])
+    exp = np.concatenate(parts)                                    # [n, 21]: found | insert 6 | has1, match1 6 | has2, match2 6
+    _PE_FULL = None
+    found = exp[:, 0] == 1
+    assert np.array_equal(st == _abi.ATR_ST_MATCH, found)
+    for c, f in enumerate(FIELDS):
+        assert np.array_equal(res["insert"][f][found].astype(np.int64), exp[found, 1 + c]), ("insert", f)
+    for side, o in (("match1", 7), ("match2", 14)):
+        has = found & (exp[:, o] == 1)
+        assert np.array_equal((res[side]["status"] == _abi.ATR_ST_MATCH) & found, has), side
+        for c, f in enumerate(FIELDS):
+            assert np.array_equal(res[side][f][has].astype(np.int64), exp[has, o + 1 + c]), (side, f)
+    del exp, parts
     m = 2_000_000
     perm = rng.permutation(m)
     res_p = ia.match_insert_batch((r1[:m][perm].reshape(-1), offs[:m + 1]), (r2[:m][perm].reshape(-1), offs[:m + 1]))
