@@ -281,36 +281,26 @@ def test_insert_config_pe150():
 
 
 def test_insert_config_pe300():
-    """BASELINE config 5 shape: 2x300 synthetic pairs, error rate 0.15 (k = 45), vs the Python oracle; also the
+    """BASELINE config 5 shape: 1 M synthetic 2x300 pairs, error rate 0.15 (k = 45), every pair vs the Python oracle; also the
     per-read fallback adapters of insert mode (max_rmp 1e-6, min_overlap 1, indel cost 3) at 300 nt"""
     from atropos_b200 import synth
     from atropos_b200.adapters import Adapter, BACK
     from atropos_b200.align import InsertAligner
     from atropos_b200.util import RandomMatchProbability
-    n, L = 30000, 300
-    r1, r2 = synth.synth_pe(n, L, seed=synth.seed_for(5), device="cpu", sub=0.02)
-    r1, r2 = r1.numpy(), r2.numpy()
+    n, L = 1_000_000, 300
+    r1, r2 = synth.synth_pe(n, L, seed=synth.seed_for(5), device="cuda", sub=0.02)
+    r1, r2 = r1.cpu().numpy(), r2.cpu().numpy()
     offs = np.arange(n + 1, dtype=np.int64) * L
     kw = dict(max_insert_mismatch_frac=0.15, max_adapter_mismatch_frac=0.15)
     res = InsertAligner(T1, T2, **kw).match_insert_batch((r1.reshape(-1), offs), (r2.reshape(-1), offs))
-    orc = oracle.OracleInsertAligner(T1, T2, **kw)
-    nm = 0
-    for i in range(n):
-        exp = orc.match_insert(bytes(r1[i]).decode(), bytes(r2[i]).decode())
-        got = InsertAligner.result_from_record(res[i])
-        if exp is None:
-            assert got is None, i
-        else:
-            nm += 1
-            assert got[0] == exp[0] and (got[1].fields() if got[1] else None) == exp[1] and \
-                (got[2].fields() if got[2] else None) == exp[2], (i, got, exp)
+    nm = _pe_check_all(res, r1, r2, kw)                       # all 1 M pairs, forked oracle workers
     assert nm > n // 4
     rmp, rmp_o = RandomMatchProbability(), oracle.RandomMatchProbability()
     akw = dict(max_error_rate=0.15, min_overlap=1, indel_cost=3, max_rmp=1e-6)
     mine = Adapter(T2, BACK, match_probability=rmp, **akw)
     o_ad = oracle.OracleAdapter(T2, oracle.BACK, match_probability=rmp_o, **akw)
     rec = mine.match_to_batch((r2.reshape(-1), offs))
-    for i in range(0, n, 5):
+    for i in range(0, 30000, 5):
         exp = o_ad.match_to(bytes(r2[i]).decode())
         got = None if rec[i]["status"] == _abi_mod.ATR_ST_NONE else tuple(int(rec[i][k]) for k in
                                                                          ("astart", "astop", "rstart", "rstop", "matches", "errors"))
@@ -483,6 +473,31 @@ def _pe_oracle_range(bounds):
     return out
 
 
+def _pe_check_all(res, r1, r2, kw):
+    """every INSERT_DTYPE record of `res` against OracleInsertAligner.match_insert, one forked worker per host core"""
+    import multiprocessing as mp
+    import os
+    from atropos_b200 import _abi
+    global _PE_FULL
+    n = len(res)
+    _PE_FULL = (r1, r2, kw)
+    workers = max(1, os.cpu_count() or 1)
+    bounds = np.linspace(0, n, 8 * workers + 1).astype(np.int64)
+    with mp.get_context("fork").Pool(workers) as pool:
+        exp = np.concatenate(pool.map(_pe_oracle_range, [(int(bounds[t]), int(bounds[t + 1])) for t in range(8 * workers)]))
+    _PE_FULL = None                                                # exp: [n, 21] found | insert 6 | has1, match1 6 | has2, match2 6
+    found = exp[:, 0] == 1
+    assert np.array_equal(res["insert"]["status"] == _abi.ATR_ST_MATCH, found)
+    for c, f in enumerate(FIELDS):
+        assert np.array_equal(res["insert"][f][found].astype(np.int64), exp[found, 1 + c]), ("insert", f)
+    for side, o in (("match1", 7), ("match2", 14)):
+        has = found & (exp[:, o] == 1)
+        assert np.array_equal((res[side]["status"] == _abi.ATR_ST_MATCH) & found, has), side
+        for c, f in enumerate(FIELDS):
+            assert np.array_equal(res[side][f][has].astype(np.int64), exp[has, o + 1 + c]), (side, f)
+    return int(found.sum())
+
+
 def test_full_size_properties_pe():
     """BASELINE config 3 at full size (10 M pairs, 2 x 150): (1) all 10 M results equal the oracle's (Python restatement on
     every host core, about a minute); (2) pairs are independent: a permuted batch gives the permuted records;
@@ -504,26 +519,7 @@ def test_full_size_properties_pe():
     assert 0.35 < (st == _abi.ATR_ST_MATCH).mean() < 0.45
     rng = np.random.default_rng(3)
     # (1) EVERY pair of the batch against the oracle, on all host cores (forked workers: they only run the CPU oracle)
-    import multiprocessing as mp
-    import os
-    global _PE_FULL
-    _PE_FULL = (r1, r2, kw)
-    workers = max(1, os.cpu_count() or 1)
-    bounds = np.linspace(0, n, 8 * workers + 1).astype(np.int64)
-    with mp.get_context("fork").Pool(workers) as pool:
-        parts = pool.map(_pe_oracle_range, [(int(bounds[t]), int(bounds[t + 1])) for t in range(8 * workers)])
-    exp = np.concatenate(parts)                                    # [n, 21]: found | insert 6 | has1, match1 6 | has2, match2 6
-    _PE_FULL = None
-    found = exp[:, 0] == 1
-    assert np.array_equal(st == _abi.ATR_ST_MATCH, found)
-    for c, f in enumerate(FIELDS):
-        assert np.array_equal(res["insert"][f][found].astype(np.int64), exp[found, 1 + c]), ("insert", f)
-    for side, o in (("match1", 7), ("match2", 14)):
-        has = found & (exp[:, o] == 1)
-        assert np.array_equal((res[side]["status"] == _abi.ATR_ST_MATCH) & found, has), side
-        for c, f in enumerate(FIELDS):
-            assert np.array_equal(res[side][f][has].astype(np.int64), exp[has, o + 1 + c]), (side, f)
-    del exp, parts
+    assert _pe_check_all(res, r1, r2, kw) == int((st == _abi.ATR_ST_MATCH).sum())
     m = 2_000_000
     perm = rng.permutation(m)
     res_p = ia.match_insert_batch((r1[:m][perm].reshape(-1), offs[:m + 1]), (r2[:m][perm].reshape(-1), offs[:m + 1]))
@@ -666,3 +662,65 @@ def test_panel_cfg4_all_eight_adapters():
             winners.add(bi)
             assert int(g["status"]) == _abi.ATR_ST_MATCH and _tup(g) == tuple(best[:6]) and int(g["adapter"]) == bi, (i, seq, best, bi)
     assert hits > 6000 and len(winners) >= 6
+
+
+_PANEL_FULL = None
+
+
+def _panel_oracle_range(bounds):
+    """worker of test_panel_cfg4_two_million_reads: the reference's best-match rule over the oracle's match_to"""
+    import bench
+    lo, hi = bounds
+    reads = _PANEL_FULL
+    oads = [oracle.OracleAdapter(s, getattr(oracle, w), 0.1, 3) for s, w in bench.PANEL]
+    out = np.zeros((hi - lo, 8), dtype=np.int64)
+    for i in range(lo, hi):
+        seq = reads[i].tobytes().decode()
+        best, bi = None, -1
+        for ai, oa in enumerate(oads):
+            m = oa.match_to(seq)
+            if m is not None and (best is None or m[4] > best[4]):      # modifiers.py:116-121
+                best, bi = m, ai
+        if best is not None:
+            out[i - lo, 0] = 1
+            out[i - lo, 1:7] = best[:6]
+            out[i - lo, 7] = bi
+    return out
+
+
+def test_panel_cfg4_two_million_reads():
+    """BASELINE cfg 4's data and panel as bench.py builds them (40 % of the reads run into the TruSeq adapter, 10 % start
+    with one of the two anchored 5' adapters): the first 2 M reads of the shard, every record and winning adapter against
+    the oracle (forked workers, one per host core)."""
+    import multiprocessing as mp
+    import os
+    import bench
+    import torch
+    from atropos_b200 import _abi, adapters as ad_mod, synth
+    from atropos_b200.modifiers import AdapterCutter
+    n, L = 2_000_000, 150
+    reads = synth.synth_se(n, L, bench.ADAPTER, seed=synth.seed_for(4, 0), device="cuda")
+    g = torch.Generator(device="cuda")
+    g.manual_seed(synth.seed_for(4, 0) + 7)
+    pick = torch.rand(n, generator=g, device="cuda")
+    for k, seq in enumerate([bench.PANEL[3][0], bench.PANEL[4][0]]):
+        rows = torch.nonzero((pick >= 0.05 * k) & (pick < 0.05 * (k + 1))).squeeze(1)
+        reads[rows, :len(seq)] = torch.tensor(list(seq.encode()), dtype=torch.uint8, device="cuda")[None, :]
+    reads = reads.cpu().numpy()
+    cutter = AdapterCutter([ad_mod.Adapter(s, getattr(ad_mod, w), max_error_rate=0.1, min_overlap=3) for s, w in bench.PANEL])
+    got = cutter.best_match_batch((reads.reshape(-1), np.arange(n + 1, dtype=np.int64) * L))
+    global _PANEL_FULL
+    _PANEL_FULL = reads
+    workers = max(1, os.cpu_count() or 1)
+    bounds = np.linspace(0, n, 8 * workers + 1).astype(np.int64)
+    with mp.get_context("fork").Pool(workers) as pool:
+        exp = np.concatenate(pool.map(_panel_oracle_range, [(int(bounds[t]), int(bounds[t + 1])) for t in range(8 * workers)]))
+    _PANEL_FULL = None
+    found = exp[:, 0] == 1
+    assert np.array_equal(got["status"] == _abi.ATR_ST_MATCH, found)
+    assert np.array_equal(got["status"] == _abi.ATR_ST_NONE, ~found)
+    for c, f in enumerate(FIELDS):
+        assert np.array_equal(got[f][found].astype(np.int64), exp[found, 1 + c]), f
+    assert np.array_equal(got["adapter"][found].astype(np.int64), exp[found, 7])
+    winners = np.bincount(exp[found, 7], minlength=len(bench.PANEL))
+    assert found.mean() > 0.4 and (winners > 0).sum() >= 4, winners
