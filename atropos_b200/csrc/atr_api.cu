@@ -316,8 +316,9 @@ int locate_on_stream(atr_ctx* ctx, Slot& slot, const atr_adapterset* set,
                 LAUNCHED(ctx);
                 Survivor* ls[3] = {narrow, wide, refine};
                 for (int li = 0; li < ((use_sa || use_qg) ? 3 : 2); li++) {
-                    if (h.and_mode) k_anchor_dp<true><<<gp, 128, 0, st>>>(p, d_codes, d_woff, d_len, d_win, d_out, ls[li], counters + li);
-                    else k_anchor_dp<false><<<gp, 128, 0, st>>>(p, d_codes, d_woff, d_len, d_win, d_out, ls[li], counters + li);
+                    // narrow stays empty here (band_ok = 0 without unit indel cost): wide and refine entries carry windows
+                    if (h.and_mode) k_anchor_dp<true><<<gp, 128, 0, st>>>(p, d_codes, d_woff, d_len, d_win, d_out, ls[li], counters + li, li > 0);
+                    else k_anchor_dp<false><<<gp, 128, 0, st>>>(p, d_codes, d_woff, d_len, d_win, d_out, ls[li], counters + li, li > 0);
                     if (li + 1 < ((use_sa || use_qg) ? 3 : 2)) LAUNCHED(ctx);
                 }
             }
@@ -332,8 +333,8 @@ int locate_on_stream(atr_ctx* ctx, Slot& slot, const atr_adapterset* set,
                 if (h.and_mode) k_filter_anchor<true><<<grid_for(n, 256), 256, 0, st>>>(p, d_codes, d_woff, d_len, d_win, n, d_out, surv, counters);
                 else k_filter_anchor<false><<<grid_for(n, 256), 256, 0, st>>>(p, d_codes, d_woff, d_len, d_win, n, d_out, surv, counters);
                 LAUNCHED(ctx);
-                if (h.and_mode) k_anchor_dp<true><<<gp, 128, 0, st>>>(p, d_codes, d_woff, d_len, d_win, d_out, surv, counters);
-                else k_anchor_dp<false><<<gp, 128, 0, st>>>(p, d_codes, d_woff, d_len, d_win, d_out, surv, counters);
+                if (h.and_mode) k_anchor_dp<true><<<gp, 128, 0, st>>>(p, d_codes, d_woff, d_len, d_win, d_out, surv, counters, 0);
+                else k_anchor_dp<false><<<gp, 128, 0, st>>>(p, d_codes, d_woff, d_len, d_win, d_out, surv, counters, 0);
             }
             else if (h.and_mode) k_locate_k1a<true><<<grid_for(n, 128), 128, 0, st>>>(p, d_codes, d_woff, d_len, d_win, n, d_out);
             else k_locate_k1a<false><<<grid_for(n, 128), 128, 0, st>>>(p, d_codes, d_woff, d_len, d_win, n, d_out);

@@ -1093,13 +1093,21 @@ template <bool AND_MODE>
 __global__ void __launch_bounds__(128) k_anchor_dp(const __grid_constant__ AdapterK1a ad,
         const uint32_t* __restrict__ codes, const uint32_t* __restrict__ woff, const uint16_t* __restrict__ len,
         const uint16_t* __restrict__ win, atr_match* __restrict__ out,
-        const Survivor* __restrict__ list, const int* __restrict__ counter) {
+        const Survivor* __restrict__ list, const int* __restrict__ counter, int windowed) {
+    // windowed: the survivors of a funnel filter stage (dearer indels) carry the column window [a, b] every accepted
+    // alignment lies in (sa_classify / myers_filter: c0, c1); the register DP only runs over it, like k_wide
     const int count = *counter;
     const int stride = gridDim.x * blockDim.x;
     for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < count; s += stride) {
         const Survivor sv = list[s];
         int lo, n; bool esc;
         read_extent(len, win, sv.read, lo, n, esc);
-        k1a_read<AND_MODE>(ad, codes + woff[sv.read], lo, n, out + sv.read);
+        if (windowed) {
+            Best b;
+            k1a_locate<AND_MODE>(ad, codes + woff[sv.read], lo, n, b, (int)sv.a, (int)sv.b);
+            finalize(ad, b, n, out + sv.read);
+        } else {
+            k1a_read<AND_MODE>(ad, codes + woff[sv.read], lo, n, out + sv.read);
+        }
     }
 }

@@ -1089,6 +1089,7 @@ ATR_HD void icfilter_read(const AdapterK1a& ad, const uint32_t* __restrict__ cod
     Best b;
     b.ref_stop = ad.m; b.q_stop = n; b.cost = ad.m + n; b.origin = 0; b.matches = 0;
     bool have = false;
+    int c0 = -1, c1 = -1;
     if (path) *path = 0;
     if (ad.sa_ok || ad.qg_ok) {
         unsigned sa_peq[16], tail_peq[16];
@@ -1108,13 +1109,16 @@ ATR_HD void icfilter_read(const AdapterK1a& ad, const uint32_t* __restrict__ cod
             return;
         }
         have = sr.cls != 0;
+        c0 = sr.c0; c1 = sr.c1;
     } else {
         const int WB = (int)(8 * sizeof(WORD)), sh = WB - ad.m;
         WORD peq[16];
         for (int c = 0; c < 16; c++) peq[c] = (WORD)(((WORD)ad.peq[c] << sh) | (sh ? (((WORD)1 << sh) - 1) : 0));
         FilterHit hit;
         have = myers_filter<WORD>(ad, peq, codes, lo, n, hit);
+        c0 = hit.c0; c1 = hit.c1;
     }
-    if (have) { if (path) *path = 1; k1a_read<AND_MODE>(ad, codes, lo, n, out); return; }
+    // the register DP over the column window the filter stage leaves (what k_anchor_dp does with the survivors' windows)
+    if (have) { if (path) *path = 1; k1a_locate<AND_MODE>(ad, codes, lo, n, b, c0, c1); }
     finalize(ad, b, n, out);
 }
