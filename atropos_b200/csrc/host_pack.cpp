@@ -77,23 +77,56 @@ __attribute__((target("avx2"))) inline bool pack32_avx2(const uint8_t* s, uint32
     return true;
 }
 
-__attribute__((target("avx2"))) int pack_read_avx2(const uint8_t* s, int len, int fold, uint32_t* out) {
+// the last 1..31 bases of a read, same fast path: 32 bytes are loaded (the caller guarantees that they are readable: they
+// belong to the following reads of the batch), the lanes beyond `rem` are excluded from the letter test and give code 0,
+// and only the words the read owns are stored (a 150-nt read ends with 22 such bases: the scalar tail was 2/3 of its cost)
+__attribute__((target("avx2"))) inline bool pack_tail_avx2(const uint8_t* s, int rem, uint32_t* out) {
+    const __m256i x = _mm256_loadu_si256((const __m256i*)s);
+    const __m256i iota = _mm256_setr_epi8(0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31);
+    const __m256i valid = _mm256_cmpgt_epi8(_mm256_set1_epi8((char)rem), iota);         // 0xFF where lane < rem
+    const __m256i lo = _mm256_and_si256(x, _mm256_set1_epi8(0x0F));
+    const __m256i code_lut = _mm256_setr_epi8(0, 1, 0, 2, 8, 0, 0, 4, 0, 0, 0, 0, 0, 0, 15, 0, 0, 1, 0, 2, 8, 0, 0, 4, 0, 0, 0, 0, 0, 0, 15, 0);
+#define U(i) (char)(0x80 | (((i) + 1) & 15))
+    const __m256i char_lut = _mm256_setr_epi8(U(0), 'A', U(2), 'C', 'T', U(5), U(6), 'G', U(8), U(9), U(10), U(11), U(12), U(13), 'N', U(15),
+                                              U(0), 'A', U(2), 'C', 'T', U(5), U(6), 'G', U(8), U(9), U(10), U(11), U(12), U(13), 'N', U(15));
+#undef U
+    const __m256i want = _mm256_shuffle_epi8(char_lut, lo);
+    const __m256i ok = _mm256_or_si256(_mm256_cmpeq_epi8(want, x), _mm256_andnot_si256(valid, _mm256_set1_epi8((char)0xFF)));
+    if (_mm256_movemask_epi8(ok) != -1) return false;
+    const __m256i code = _mm256_and_si256(_mm256_shuffle_epi8(code_lut, lo), valid);
+    const __m256i pairs = _mm256_maddubs_epi16(code, _mm256_set1_epi16(0x1001));
+    const __m256i bytes = _mm256_packus_epi16(pairs, pairs);
+    const __m256i ord = _mm256_permute4x64_epi64(bytes, 0x08);
+    alignas(16) uint32_t tmp[4];
+    _mm_store_si128((__m128i*)tmp, _mm256_castsi256_si128(ord));
+    const int nw = (rem + 7) >> 3;
+    for (int w = 0; w < nw; w++) out[w] = tmp[w];
+    return true;
+}
+
+// slack: bytes readable behind the read (>= 31 lets the tail take the vector path)
+__attribute__((target("avx2"))) int pack_read_avx2(const uint8_t* s, int len, int fold, uint32_t* out, int64_t slack) {
     int esc = 0, p = 0;
     for (; p + 32 <= len; p += 32) {
         if (!pack32_avx2(s + p, out + (p >> 3))) esc |= pack_read_scalar(s + p, 32, fold, out + (p >> 3));
     }
-    if (p < len) esc |= pack_read_scalar(s + p, len - p, fold, out + (p >> 3));
+    if (p < len) {
+        if (slack < 32 - (len - p) || !pack_tail_avx2(s + p, len - p, out + (p >> 3)))
+            esc |= pack_read_scalar(s + p, len - p, fold, out + (p >> 3));
+    }
     return esc;
 }
 #endif
 
-typedef int (*pack_fn)(const uint8_t*, int, int, uint32_t*);
+int pack_read_plain(const uint8_t* s, int len, int fold, uint32_t* out, int64_t /*slack*/) { return pack_read_scalar(s, len, fold, out); }
+
+typedef int (*pack_fn)(const uint8_t*, int, int, uint32_t*, int64_t);
 
 pack_fn pick() {
 #if defined(__x86_64__)
     if (__builtin_cpu_supports("avx2")) return pack_read_avx2;
 #endif
-    return pack_read_scalar;
+    return pack_read_plain;
 }
 
 }  // namespace
@@ -101,31 +134,46 @@ pack_fn pick() {
 extern "C" int atr_pack_reads_host(const uint8_t* ascii, const int64_t* offsets, int64_t n, int fold_case, int n_threads,
                                    uint32_t* codes, uint32_t* woff, uint16_t* len) {
     if (!offsets || !codes || !woff || !len || n < 0 || (n > 0 && !ascii && offsets[n] > offsets[0])) return ATR_E_ARG;
-    // word offsets: exclusive scan of ceil(len / 8)
-    uint64_t w = 0;
-    for (int64_t i = 0; i < n; i++) {
-        const int64_t l = offsets[i + 1] - offsets[i];
-        if (l < 0 || l > 32767) return ATR_E_LIMIT;
-        woff[i] = (uint32_t)w;
-        w += (uint64_t)((l + 7) >> 3);
-        if (w > 0xFFFFFFF0ull) return ATR_E_LIMIT;
-    }
-    woff[n] = (uint32_t)w;
-    if (n == 0) return ATR_OK;
+    if (n == 0) { woff[0] = 0; return ATR_OK; }
     unsigned hw = std::thread::hardware_concurrency();
     int nt = n_threads > 0 ? n_threads : (int)(hw ? hw : 1);
     nt = (int)std::max<int64_t>(1, std::min<int64_t>(nt, n / 4096 + 1));
-    const pack_fn pack = pick();
-    auto work = [&](int64_t a, int64_t b) {
-        for (int64_t i = a; i < b; i++) {
-            const int l = (int)(offsets[i + 1] - offsets[i]);
-            const int esc = pack(ascii + offsets[i], l, fold_case, codes + woff[i]);
-            len[i] = (uint16_t)((unsigned)l | (esc ? 0x8000u : 0u));
-        }
+    // word offsets: exclusive scan of ceil(len / 8), in two threaded passes (per-range sums, then the offsets; the serial
+    // scan was a quarter of the call at 16 threads)
+    std::vector<uint64_t> part((size_t)nt + 1, 0);
+    std::vector<int> bad((size_t)nt, 0);
+    auto run = [&](auto fn) {
+        if (nt == 1) { fn(0); return; }
+        std::vector<std::thread> th;
+        for (int t = 0; t < nt; t++) th.emplace_back(fn, t);
+        for (auto& x : th) x.join();
     };
-    if (nt == 1) { work(0, n); return ATR_OK; }
-    std::vector<std::thread> th;
-    for (int t = 0; t < nt; t++) th.emplace_back(work, n * t / nt, n * (t + 1) / nt);
-    for (auto& x : th) x.join();
+    run([&](int t) {
+        uint64_t w = 0;
+        for (int64_t i = n * t / nt; i < n * (t + 1) / nt; i++) {
+            const int64_t l = offsets[i + 1] - offsets[i];
+            if (l < 0 || l > 32767) { bad[(size_t)t] = 1; return; }
+            w += (uint64_t)((l + 7) >> 3);
+        }
+        part[(size_t)t + 1] = w;
+    });
+    for (int t = 0; t < nt; t++) {
+        if (bad[(size_t)t]) return ATR_E_LIMIT;
+        part[(size_t)t + 1] += part[(size_t)t];
+    }
+    if (part[(size_t)nt] > 0xFFFFFFF0ull) return ATR_E_LIMIT;
+    woff[n] = (uint32_t)part[(size_t)nt];
+    const pack_fn pack = pick();
+    const int64_t end = offsets[n];
+    run([&](int t) {
+        uint64_t w = part[(size_t)t];
+        for (int64_t i = n * t / nt; i < n * (t + 1) / nt; i++) {
+            const int l = (int)(offsets[i + 1] - offsets[i]);
+            woff[i] = (uint32_t)w;
+            const int esc = pack(ascii + offsets[i], l, fold_case, codes + w, end - offsets[i + 1]);
+            len[i] = (uint16_t)((unsigned)l | (esc ? 0x8000u : 0u));
+            w += (uint64_t)((l + 7) >> 3);
+        }
+    });
     return ATR_OK;
 }
