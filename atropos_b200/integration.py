@@ -182,7 +182,7 @@ class _CutterReplay(object):
 
     def seek(self, idx):
         self.idx, self.t = idx, 0
-        self.lo, self.hi = 0, int(self.lens[idx])
+        self.lo, self.hi = 0, self.lens[idx]
 
     def __call__(self, read):
         _, adapters_mod, align, _, _, _ = _ref()
@@ -312,7 +312,9 @@ class _Plan(object):
         self.paired = isinstance(mods, modifiers.PairedEndModifiers)
         self.index = None
         self.kind = None
+        self._step_cache = {}
         chain = mods.modifiers
+        self.n_chain = len(chain)
         stages = [i for i, m in enumerate(chain)
                   if isinstance(m, modifiers.InsertAdapterCutter) or
                   (isinstance(m, list) and any(isinstance(x, modifiers.AdapterCutter) for x in m))]
@@ -356,27 +358,44 @@ class _Plan(object):
 
     # -- the chain, split at the adapter stage (SingleEndModifiers.modify / PairedEndModifiers.modify,
     #    modifiers.py:1048-1051, 1096-1105) ----------------------------------------------------------------
-    def _run(self, chain, read1, read2):
-        _, _, _, _, _, modifiers = _ref()
-        for mods in chain:
-            if isinstance(mods, modifiers.ReadPairModifier):
-                read1, read2 = mods(read1, read2)
+    def _steps(self, lo, hi):
+        """chain[lo:hi] as a flat list of (kind, callable): 0 = pair modifier, 1 = read 1, 2 = read 2. Built once per
+        plan (this runs per record; the generic loop spent its time on isinstance tests and slices)."""
+        key = (lo, hi)
+        steps = self._step_cache.get(key)
+        if steps is None:
+            _, _, _, _, _, modifiers = _ref()
+            steps = []
+            for mods in self.mods.modifiers[lo:hi]:
+                if isinstance(mods, modifiers.ReadPairModifier):
+                    steps.append((0, mods))
+                else:
+                    if mods[0] is not None:
+                        steps.append((1, mods[0]))
+                    if self.paired and mods[1] is not None:
+                        steps.append((2, mods[1]))
+            self._step_cache[key] = steps
+        return steps
+
+    def _run(self, lo, hi, read1, read2):
+        for kind, fn in self._steps(lo, hi):
+            if kind == 1:
+                read1 = fn(read1)
+            elif kind == 2:
+                read2 = fn(read2)
             else:
-                if mods[0] is not None:
-                    read1 = mods[0](read1)
-                if self.paired and mods[1] is not None:
-                    read2 = mods[1](read2)
+                read1, read2 = fn(read1, read2)
         return read1, read2
 
     def before(self, read1, read2):
-        return self._run(self.mods.modifiers[:self.index], read1, read2)
+        return self._run(0, self.index, read1, read2)
 
     def from_stage(self, read1, read2):
-        read1, read2 = self._run(self.mods.modifiers[self.index:], read1, read2)
+        read1, read2 = self._run(self.index, self.n_chain, read1, read2)
         return (read1, read2) if self.paired else (read1,)
 
     def stage_to_merge(self, read1, read2):
-        return self._run(self.mods.modifiers[self.index:self.merge_index], read1, read2)
+        return self._run(self.index, self.merge_index, read1, read2)
 
     def from_merge(self, read1, read2):
         """MergeOverlapping.__call__ (reference code) with its Aligner swapped for the replay, then whatever follows"""
@@ -384,7 +403,7 @@ class _Plan(object):
         saved = modifiers.Aligner
         modifiers.Aligner = self.merge.Aligner
         try:
-            return self._run(self.mods.modifiers[self.merge_index:], read1, read2)
+            return self._run(self.merge_index, self.n_chain, read1, read2)
         finally:
             modifiers.Aligner = saved
 
@@ -414,7 +433,7 @@ class _Plan(object):
         ascii, offsets = engine.encode_reads(seqs)
         n = len(seqs)
         lens = np.diff(offsets).astype(np.int64)
-        rp.lens = lens
+        rp.lens = lens.tolist()
         if rp.linked is not None:
             la = rp.linked
             front = self._set_of(c, [la.front_adapter], device).locate_host(ascii, offsets, fold_case=True)
